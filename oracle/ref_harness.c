@@ -1,0 +1,356 @@
+/* TEST INFRASTRUCTURE ONLY (oracle/_ref): drives the reference's OWN acados /
+ * HPIPM / BLASFEO code (compiled from /root/reference by oracle/Makefile) on
+ * the Crazyflie OCP, so that the product and the plain-C oracle can be checked
+ * against the real reference and so that bench.py has a "reference" CPU arm.
+ *
+ * The generated glue the reference normally gets from CasADi + Tera
+ * (c_generated_code/, not in the tree) is replaced by the call sequence below,
+ * which follows the template section by section:
+ *   acados_template/c_templates_tera/acados_solver.in.c
+ *     plan :159-199, dims :204-380, nlp_in :879-1569, opts :2028-2317,
+ *     nlp_out :2323-2352, precompute :2381-2435
+ * with the values of crazyflie_controller/scripts/crazyflie_full_model/generate_c_code.py:41-146.
+ * The model enters as an external_function_generic whose first member is the
+ * evaluate pointer (acados/utils/external_function_generic.h:75-83).
+ *
+ * Never linked into, or called from, the product library. */
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "acados/ocp_nlp/ocp_nlp_common.h"
+#include "acados/ocp_qp/ocp_qp_hpipm.h"
+#include "acados/ocp_qp/ocp_qp_xcond_solver.h"
+#include "acados/utils/external_function_generic.h"
+#include "acados_c/external_function_interface.h"
+#include "acados_c/ocp_nlp_interface.h"
+#include "blasfeo/include/blasfeo_d_aux.h"
+#include "hpipm_d_ocp_qp_ipm.h"
+
+#include "cf_model_ref.h"
+
+#define NX 13
+#define NU 4
+#define NY 17
+
+typedef struct
+{
+    int N;
+    double Ts;
+    ocp_nlp_plan_t *plan;
+    ocp_nlp_config *config;
+    ocp_nlp_dims *dims;
+    ocp_nlp_in *in;
+    ocp_nlp_out *out;
+    void *opts;
+    ocp_nlp_solver *solver;
+    external_function_generic vde, ode;
+} cfref;
+
+static void vde_eval(void *self, ext_fun_arg_t *tin, void **in, ext_fun_arg_t *tout, void **out)
+{
+    (void) self; (void) tin; (void) tout;
+    cf_ref_vde_forw((const double *) in[0], (const double *) in[1], (const double *) in[2],
+                    (const double *) in[3], (double *) out[0], (double *) out[1], (double *) out[2]);
+}
+static void ode_eval(void *self, ext_fun_arg_t *tin, void **in, ext_fun_arg_t *tout, void **out)
+{
+    (void) self; (void) tin; (void) tout;
+    cf_ref_ode((const double *) in[0], (const double *) in[1], (double *) out[0]);
+}
+
+void cfref_destroy(void *h_)
+{
+    cfref *h = h_;
+    if (!h) return;
+    if (h->solver) ocp_nlp_solver_destroy(h->solver);
+    if (h->out) ocp_nlp_out_destroy(h->out);
+    if (h->opts) ocp_nlp_solver_opts_destroy(h->opts);
+    if (h->in) ocp_nlp_in_destroy(h->in);
+    if (h->dims) ocp_nlp_dims_destroy(h->dims);
+    if (h->config) ocp_nlp_config_destroy(h->config);
+    if (h->plan) ocp_nlp_plan_destroy(h->plan);
+    free(h);
+}
+
+/* cond_N <= 0 means "what generate_c_code.py yields": qp_cond_N = N. */
+void *cfref_create(int N, double Ts, int cond_N)
+{
+    cfref *h = calloc(1, sizeof(cfref));
+    h->N = N;
+    h->Ts = Ts;
+    if (cond_N <= 0 || cond_N > N) cond_N = N;
+
+    ocp_nlp_plan_t *plan = h->plan = ocp_nlp_plan_create(N);
+    plan->nlp_solver = SQP_RTI;
+    plan->ocp_qp_solver_plan.qp_solver = PARTIAL_CONDENSING_HPIPM;
+    plan->regularization = NO_REGULARIZE;
+    for (int i = 0; i <= N; i++) { plan->nlp_cost[i] = LINEAR_LS; plan->nlp_constraints[i] = BGH; }
+    for (int i = 0; i < N; i++) { plan->nlp_dynamics[i] = CONTINUOUS_MODEL; plan->sim_solver_plan[i].sim_solver = ERK; }
+    ocp_nlp_config *config = h->config = ocp_nlp_config_create(*plan);
+
+    int *nx = calloc(N + 1, sizeof(int)), *nu = calloc(N + 1, sizeof(int)), *zz = calloc(N + 1, sizeof(int));
+    for (int i = 0; i <= N; i++) { nx[i] = NX; nu[i] = i < N ? NU : 0; }
+    ocp_nlp_dims *dims = h->dims = ocp_nlp_dims_create(config);
+    ocp_nlp_dims_set_opt_vars(config, dims, "nx", nx);
+    ocp_nlp_dims_set_opt_vars(config, dims, "nu", nu);
+    ocp_nlp_dims_set_opt_vars(config, dims, "nz", zz);
+    ocp_nlp_dims_set_opt_vars(config, dims, "ns", zz);
+    ocp_nlp_dims_set_opt_vars(config, dims, "np", zz);
+    for (int i = 0; i <= N; i++) {
+        int nbx = i == 0 ? NX : 0, nbu = i < N ? NU : 0, z = 0, nbxe = nbx, ny = i < N ? NY : NX;
+        ocp_nlp_dims_set_constraints(config, dims, i, "nbx", &nbx);
+        ocp_nlp_dims_set_constraints(config, dims, i, "nbu", &nbu);
+        ocp_nlp_dims_set_constraints(config, dims, i, "nsbx", &z);
+        ocp_nlp_dims_set_constraints(config, dims, i, "nsbu", &z);
+        ocp_nlp_dims_set_constraints(config, dims, i, "ng", &z);
+        ocp_nlp_dims_set_constraints(config, dims, i, "nsg", &z);
+        ocp_nlp_dims_set_constraints(config, dims, i, "nbxe", &nbxe);
+        ocp_nlp_dims_set_constraints(config, dims, i, "nh", &z);
+        ocp_nlp_dims_set_constraints(config, dims, i, "nsh", &z);
+        ocp_nlp_dims_set_cost(config, dims, i, "ny", &ny);
+    }
+    free(nx); free(nu); free(zz);
+
+    h->vde.evaluate = &vde_eval;
+    h->ode.evaluate = &ode_eval;
+    ocp_nlp_in *in = h->in = ocp_nlp_in_create(config, dims);
+    for (int i = 0; i < N; i++) {
+        ocp_nlp_in_set(config, dims, in, i, "Ts", &Ts);
+        ocp_nlp_cost_model_set(config, dims, in, i, "scaling", &Ts);
+        ocp_nlp_dynamics_model_set(config, dims, in, i, "expl_vde_forw", &h->vde);
+        ocp_nlp_dynamics_model_set(config, dims, in, i, "expl_ode_fun", &h->ode);
+    }
+
+    /* generate_c_code.py:50-129 */
+    const double g0 = 9.8066, mq = 33e-3, Ct = 3.25e-4;
+    double hov = sqrt((mq * g0) / (4 * Ct));
+    double Qd[NX] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
+    double W[NY * NY] = {0}, WN[NX * NX] = {0}, Vx[NY * NX] = {0}, Vu[NY * NU] = {0}, VxN[NX * NX] = {0};
+    for (int i = 0; i < NX; i++) { W[i + NY * i] = Qd[i]; WN[i + NX * i] = 50 * Qd[i]; Vx[i + NY * i] = 1; VxN[i + NX * i] = 1; }
+    for (int i = 0; i < NU; i++) { W[(NX + i) + NY * (NX + i)] = 0.06; Vu[(NX + i) + NY * i] = 1; }
+    double yref[NY] = {0, 0, 0.5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, hov, hov, hov, hov};
+    for (int i = 0; i < N; i++) {
+        ocp_nlp_cost_model_set(config, dims, in, i, "W", W);
+        ocp_nlp_cost_model_set(config, dims, in, i, "Vx", Vx);
+        ocp_nlp_cost_model_set(config, dims, in, i, "Vu", Vu);
+        ocp_nlp_cost_model_set(config, dims, in, i, "yref", yref);
+    }
+    ocp_nlp_cost_model_set(config, dims, in, N, "W", WN);
+    ocp_nlp_cost_model_set(config, dims, in, N, "Vx", VxN);
+    ocp_nlp_cost_model_set(config, dims, in, N, "yref", yref);
+
+    int idxbx0[NX], idxbu[NU] = {0, 1, 2, 3};
+    for (int i = 0; i < NX; i++) idxbx0[i] = i;
+    double x0[NX] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    ocp_nlp_constraints_model_set(config, dims, in, 0, "idxbx", idxbx0);
+    ocp_nlp_constraints_model_set(config, dims, in, 0, "lbx", x0);
+    ocp_nlp_constraints_model_set(config, dims, in, 0, "ubx", x0);
+    ocp_nlp_constraints_model_set(config, dims, in, 0, "idxbxe", idxbx0);
+    double lbu[NU] = {0, 0, 0, 0}, ubu[NU] = {22, 22, 22, 22};
+    for (int i = 0; i < N; i++) {
+        ocp_nlp_constraints_model_set(config, dims, in, i, "idxbu", idxbu);
+        ocp_nlp_constraints_model_set(config, dims, in, i, "lbu", lbu);
+        ocp_nlp_constraints_model_set(config, dims, in, i, "ubu", ubu);
+    }
+
+    void *opts = h->opts = ocp_nlp_solver_opts_create(config, dims);
+    int num_stages = 4, num_steps = 1, iter_max = 50, one = 1, zero = 0, rti_level = 4;
+    double step_length = 1.0, lm = 0.0;
+    ocp_nlp_solver_opts_set(config, opts, "globalization", "fixed_step");
+    ocp_nlp_solver_opts_set(config, opts, "full_step_dual", &zero);
+    for (int i = 0; i < N; i++) {
+        ocp_nlp_solver_opts_set_at_stage(config, opts, i, "dynamics_num_steps", &num_steps);
+        ocp_nlp_solver_opts_set_at_stage(config, opts, i, "dynamics_num_stages", &num_stages);
+    }
+    ocp_nlp_solver_opts_set(config, opts, "step_length", &step_length);
+    ocp_nlp_solver_opts_set(config, opts, "levenberg_marquardt", &lm);
+    ocp_nlp_solver_opts_set(config, opts, "qp_cond_N", &cond_N);
+    ocp_nlp_solver_opts_set(config, opts, "qp_hpipm_mode", "BALANCE");
+    ocp_nlp_solver_opts_set(config, opts, "as_rti_iter", &one);
+    ocp_nlp_solver_opts_set(config, opts, "as_rti_level", &rti_level);
+    ocp_nlp_solver_opts_set(config, opts, "rti_log_residuals", &zero);
+    ocp_nlp_solver_opts_set(config, opts, "qp_iter_max", &iter_max);
+    ocp_nlp_solver_opts_set(config, opts, "print_level", &zero);
+    ocp_nlp_solver_opts_set(config, opts, "qp_cond_ric_alg", &one);
+    ocp_nlp_solver_opts_set(config, opts, "qp_ric_alg", &one);
+
+    ocp_nlp_out *out = h->out = ocp_nlp_out_create(config, dims);
+    double u_init[NU] = {0, 0, 0, 0};
+    for (int i = 0; i <= N; i++) {
+        ocp_nlp_out_set(config, dims, out, i, "x", x0);
+        if (i < N) ocp_nlp_out_set(config, dims, out, i, "u", u_init);
+    }
+    h->solver = ocp_nlp_solver_create(config, dims, opts);
+    if (ocp_nlp_precompute(h->solver, in, out) != 0) { cfref_destroy(h); return NULL; }
+    return h;
+}
+
+/* Runtime weights (diagonals, cost order y=[x;u]) -- the node's SET_WEIGHTS path,
+ * crazyflie_controller/src/acados_mpc.cpp:596-602. */
+void cfref_set_weights(void *h_, const double *Wdiag, const double *WNdiag)
+{
+    cfref *h = h_;
+    double W[NY * NY] = {0}, WN[NX * NX] = {0};
+    for (int i = 0; i < NY; i++) W[i + NY * i] = Wdiag[i];
+    for (int i = 0; i < NX; i++) WN[i + NX * i] = WNdiag[i];
+    for (int i = 0; i < h->N; i++) ocp_nlp_cost_model_set(h->config, h->dims, h->in, i, "W", W);
+    ocp_nlp_cost_model_set(h->config, h->dims, h->in, h->N, "W", WN);
+}
+
+void cfref_set_input_bounds(void *h_, const double *lbu, const double *ubu)
+{
+    cfref *h = h_;
+    for (int i = 0; i < h->N; i++) {
+        ocp_nlp_constraints_model_set(h->config, h->dims, h->in, i, "lbu", (void *) lbu);
+        ocp_nlp_constraints_model_set(h->config, h->dims, h->in, i, "ubu", (void *) ubu);
+    }
+}
+
+/* One RTI step exactly as NMPC::iteration does it (acados_mpc.cpp:581-625):
+ * set x0 as lbx=ubx, set yref per stage, solve, read the iterate back.
+ * x[(N+1)*13], u[N*4] are in/out (iterate before -> iterate after).
+ * times[5] = time_tot, time_lin, time_qp_sol, time_qp_solver_call, time_qp_xcond. */
+int cfref_rti(void *h_, const double *x0, const double *yref, const double *yref_e,
+              double *x, double *u, int *qp_iter, int *qp_status, double *times)
+{
+    cfref *h = h_;
+    int N = h->N;
+    ocp_nlp_config *c = h->config;
+    ocp_nlp_dims *d = h->dims;
+    ocp_nlp_constraints_model_set(c, d, h->in, 0, "lbx", (void *) x0);
+    ocp_nlp_constraints_model_set(c, d, h->in, 0, "ubx", (void *) x0);
+    for (int k = 0; k < N; k++) ocp_nlp_cost_model_set(c, d, h->in, k, "yref", (void *) (yref + NY * k));
+    ocp_nlp_cost_model_set(c, d, h->in, N, "yref", (void *) yref_e);
+    for (int k = 0; k <= N; k++) {
+        ocp_nlp_out_set(c, d, h->out, k, "x", x + NX * k);
+        if (k < N) ocp_nlp_out_set(c, d, h->out, k, "u", u + NU * k);
+    }
+    int status = ocp_nlp_solve(h->solver, h->in, h->out);
+    for (int k = 0; k <= N; k++) {
+        ocp_nlp_out_get(c, d, h->out, k, "x", x + NX * k);
+        if (k < N) ocp_nlp_out_get(c, d, h->out, k, "u", u + NU * k);
+    }
+    if (qp_iter) ocp_nlp_get(c, h->solver, "qp_iter", qp_iter);
+    if (qp_status) ocp_nlp_get(c, h->solver, "qp_status", qp_status);
+    if (times) {
+        ocp_nlp_get(c, h->solver, "time_tot", times + 0);
+        ocp_nlp_get(c, h->solver, "time_lin", times + 1);
+        ocp_nlp_get(c, h->solver, "time_qp_sol", times + 2);
+        ocp_nlp_get(c, h->solver, "time_qp_solver_call", times + 3);
+        ocp_nlp_get(c, h->solver, "time_qp_xcond", times + 4);
+    }
+    return status;
+}
+
+/* QP data of the last solve, unpacked to plain row-major arrays:
+ *  BAbt[N][17][13] rows = [u;x] of stage k, cols = x_{k+1};  b[N][13];
+ *  rqz[(N)*17+13]; d_lb/d_ub: stage0 17 each ([u;x] order), stages 1..N-1 4 each;
+ *  dux[(N)*17+13], dpi[N*13] = QP solution (step).  Any pointer may be NULL. */
+void cfref_get_qp(void *h_, double *BAbt, double *b, double *rqz, double *d_lb, double *d_ub,
+                  double *dux, double *dpi)
+{
+    cfref *h = h_;
+    int N = h->N;
+    ocp_nlp_memory *m;
+    ocp_nlp_get(h->config, h->solver, "nlp_mem", &m);
+    struct d_ocp_qp *qp = m->qp_in;
+    struct d_ocp_qp_sol *sol = m->qp_out;
+    double tmp[17 * 13];
+    int od = 0;
+    for (int k = 0; k <= N; k++) {
+        int nv = k < N ? 17 : 13;
+        if (k < N && BAbt) {
+            blasfeo_unpack_dmat(17, 13, qp->BAbt + k, 0, 0, tmp, 17); /* col-major */
+            for (int r = 0; r < 17; r++)
+                for (int cc = 0; cc < 13; cc++) BAbt[(k * 17 + r) * 13 + cc] = tmp[r + 17 * cc];
+        }
+        if (k < N && b) blasfeo_unpack_dvec(13, qp->b + k, 0, b + 13 * k, 1);
+        if (rqz) blasfeo_unpack_dvec(nv, qp->rqz + k, 0, rqz + 17 * k, 1);
+        if (dux) blasfeo_unpack_dvec(nv, sol->ux + k, 0, dux + 17 * k, 1);
+        if (k < N && dpi) blasfeo_unpack_dvec(13, sol->pi + k, 0, dpi + 13 * k, 1);
+        int nb = k == 0 ? 17 : (k < N ? 4 : 0);
+        if (d_lb) blasfeo_unpack_dvec(nb, qp->d + k, 0, d_lb + od, 1);
+        if (d_ub) blasfeo_unpack_dvec(nb, qp->d + k, nb, d_ub + od, 1);
+        od += nb;
+    }
+}
+
+/* HPIPM per-iteration statistics table of the last solve
+ * (external/hpipm/ocp_qp/x_ocp_qp_ipm.c:2181-2200,2706-2714); returns rows. */
+int cfref_get_ipm_stat(void *h_, double *stat, int max_rows, int *stat_m)
+{
+    cfref *h = h_;
+    ocp_nlp_memory *m;
+    ocp_nlp_get(h->config, h->solver, "nlp_mem", &m);
+    ocp_qp_xcond_solver_memory *xm = (ocp_qp_xcond_solver_memory *) m->qp_solver_mem;
+    ocp_qp_hpipm_memory *hm = (ocp_qp_hpipm_memory *) xm->solver_memory;
+    struct d_ocp_qp_ipm_ws *w = hm->hpipm_workspace;
+    int rows = w->iter + 1;
+    if (rows > w->stat_max) rows = w->stat_max;
+    if (rows > max_rows) rows = max_rows;
+    if (stat_m) *stat_m = w->stat_m;
+    if (stat) memcpy(stat, w->stat, sizeof(double) * rows * w->stat_m);
+    return rows;
+}
+
+/* ---- batch driver: one solver object per worker thread, static slices -----
+ * (the reference has no batch API; solver objects are independent).
+ * Layouts: x0[n][13], yref[n][N*17], yref_e[n][13], x[n][(N+1)*13] in/out,
+ * u[n][N*4] in/out, status[n], qp_iter[n], time_tot[n] (acados' own timer). */
+typedef struct
+{
+    int N, cond_N, lo, hi, n_rti;
+    double Ts;
+    const double *x0, *yref, *yref_e;
+    double *x, *u, *time_tot;
+    int *status, *qp_iter;
+    int fail;
+} slice;
+
+static void *slice_run(void *arg)
+{
+    slice *s = arg;
+    void *h = cfref_create(s->N, s->Ts, s->cond_N);
+    if (!h) { s->fail = 1; return NULL; }
+    int N = s->N;
+    for (int i = s->lo; i < s->hi; i++) {
+        double t[5], tt = 0;
+        int st = 0, it = 0;
+        for (int r = 0; r < s->n_rti; r++) {
+            st = cfref_rti(h, s->x0 + 13 * (size_t) i, s->yref + (size_t) N * 17 * i, s->yref_e + 13 * (size_t) i,
+                           s->x + (size_t) (N + 1) * 13 * i, s->u + (size_t) N * 4 * i, &it, NULL, t);
+            tt += t[0];
+        }
+        if (s->status) s->status[i] = st;
+        if (s->qp_iter) s->qp_iter[i] = it;
+        if (s->time_tot) s->time_tot[i] = tt;
+    }
+    cfref_destroy(h);
+    return NULL;
+}
+
+int cfref_batch(int N, double Ts, int cond_N, int nthreads, int n_rti, int n,
+                const double *x0, const double *yref, const double *yref_e,
+                double *x, double *u, int *status, int *qp_iter, double *time_tot)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > n) nthreads = n > 0 ? n : 1;
+    pthread_t *th = calloc(nthreads, sizeof(pthread_t));
+    slice *sl = calloc(nthreads, sizeof(slice));
+    int fail = 0;
+    for (int t = 0; t < nthreads; t++) {
+        sl[t] = (slice){N, cond_N, (int) ((long) n * t / nthreads), (int) ((long) n * (t + 1) / nthreads), n_rti,
+                        Ts, x0, yref, yref_e, x, u, time_tot, status, qp_iter, 0};
+        if (nthreads == 1) slice_run(&sl[t]);
+        else pthread_create(&th[t], NULL, slice_run, &sl[t]);
+    }
+    for (int t = 0; t < nthreads; t++) {
+        if (nthreads > 1) pthread_join(th[t], NULL);
+        fail |= sl[t].fail;
+    }
+    free(th); free(sl);
+    return fail;
+}
