@@ -1,0 +1,783 @@
+/* TEST INFRASTRUCTURE ONLY -- see cfnmpc_oracle.h for scope, parity status and
+ * the reference file:line map.  Plain scalar C, one instance at a time, dense
+ * loops, no attempt at speed.  Never part of the product path. */
+#include "cfnmpc_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NX 13
+#define NU 4
+#define NV 17
+
+/* ------------------------------------------------------------------ model
+ * crazyflie_controller/scripts/crazyflie_full_model/export_ode_model.py:34-42,85-97 */
+static const double g0 = 9.8066, mq = 33e-3, Ixx = 1.395e-5, Iyy = 1.395e-5, Izz = 2.173e-5,
+                    Cd = 7.9379e-06, Ct = 3.25e-4, arm = 65e-3 / 2;
+
+void cfo_default_params(cfo_params *p)
+{
+    /* generate_c_code.py:61-84,113,133-134 */
+    static const double Q[NX] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
+    for (int i = 0; i < NX; i++) { p->Wdiag[i] = Q[i]; p->WNdiag[i] = 50 * Q[i]; }
+    for (int i = 0; i < NU; i++) { p->Wdiag[NX + i] = 0.06; p->lbu[i] = 0.0; p->ubu[i] = 22.0; }
+}
+
+void cfo_ode(const double *x, const double *u, double *f)
+{
+    double q1 = x[3], q2 = x[4], q3 = x[5], q4 = x[6], vx = x[7], vy = x[8], vz = x[9];
+    double wx = x[10], wy = x[11], wz = x[12];
+    double s1 = u[0] * u[0], s2 = u[1] * u[1], s3 = u[2] * u[2], s4 = u[3] * u[3];
+    f[0] = vx * (2 * q1 * q1 + 2 * q2 * q2 - 1) - vy * (2 * q1 * q4 - 2 * q2 * q3) + vz * (2 * q1 * q3 + 2 * q2 * q4);
+    f[1] = vy * (2 * q1 * q1 + 2 * q3 * q3 - 1) + vx * (2 * q1 * q4 + 2 * q2 * q3) - vz * (2 * q1 * q2 - 2 * q3 * q4);
+    f[2] = vz * (2 * q1 * q1 + 2 * q4 * q4 - 1) - vx * (2 * q1 * q3 - 2 * q2 * q4) + vy * (2 * q1 * q2 + 2 * q3 * q4);
+    f[3] = -(q2 * wx) / 2 - (q3 * wy) / 2 - (q4 * wz) / 2;
+    f[4] = (q1 * wx) / 2 - (q4 * wy) / 2 + (q3 * wz) / 2;
+    f[5] = (q4 * wx) / 2 + (q1 * wy) / 2 - (q2 * wz) / 2;
+    f[6] = (q2 * wy) / 2 - (q3 * wx) / 2 + (q1 * wz) / 2;
+    f[7] = vy * wz - vz * wy + g0 * (2 * q1 * q3 - 2 * q2 * q4);
+    f[8] = vz * wx - vx * wz - g0 * (2 * q1 * q2 + 2 * q3 * q4);
+    f[9] = vx * wy - vy * wx - g0 * (2 * q1 * q1 + 2 * q4 * q4 - 1) + (Ct * (s1 + s2 + s3 + s4)) / mq;
+    f[10] = -(Ct * arm * (s1 + s2 - s3 - s4) - Iyy * wy * wz + Izz * wy * wz) / Ixx;
+    f[11] = -(Ct * arm * (s1 - s2 - s3 + s4) + Ixx * wx * wz - Izz * wx * wz) / Iyy;
+    f[12] = -(Cd * (s1 - s2 + s3 - s4) - Ixx * wx * wy + Iyy * wx * wy) / Izz;
+}
+
+/* dense Jacobians, row-major Jx[13][13], Ju[13][4]; sparsity as SURVEY.md Appendix A.1 */
+static void jacobians(const double *x, const double *u, double Jx[NX][NX], double Ju[NX][NU])
+{
+    double q1 = x[3], q2 = x[4], q3 = x[5], q4 = x[6], vx = x[7], vy = x[8], vz = x[9];
+    double wx = x[10], wy = x[11], wz = x[12];
+    memset(Jx, 0, sizeof(double) * NX * NX);
+    memset(Ju, 0, sizeof(double) * NX * NU);
+    /* pdot rows */
+    Jx[0][3] = 4 * q1 * vx - 2 * q4 * vy + 2 * q3 * vz;
+    Jx[0][4] = 4 * q2 * vx + 2 * q3 * vy + 2 * q4 * vz;
+    Jx[0][5] = 2 * q2 * vy + 2 * q1 * vz;
+    Jx[0][6] = -2 * q1 * vy + 2 * q2 * vz;
+    Jx[0][7] = 2 * q1 * q1 + 2 * q2 * q2 - 1;
+    Jx[0][8] = -(2 * q1 * q4 - 2 * q2 * q3);
+    Jx[0][9] = 2 * q1 * q3 + 2 * q2 * q4;
+    Jx[1][3] = 4 * q1 * vy + 2 * q4 * vx - 2 * q2 * vz;
+    Jx[1][4] = 2 * q3 * vx - 2 * q1 * vz;
+    Jx[1][5] = 4 * q3 * vy + 2 * q2 * vx + 2 * q4 * vz;
+    Jx[1][6] = 2 * q1 * vx + 2 * q3 * vz;
+    Jx[1][7] = 2 * q1 * q4 + 2 * q2 * q3;
+    Jx[1][8] = 2 * q1 * q1 + 2 * q3 * q3 - 1;
+    Jx[1][9] = -(2 * q1 * q2 - 2 * q3 * q4);
+    Jx[2][3] = 4 * q1 * vz - 2 * q3 * vx + 2 * q2 * vy;
+    Jx[2][4] = 2 * q4 * vx + 2 * q1 * vy;
+    Jx[2][5] = -2 * q1 * vx + 2 * q4 * vy;
+    Jx[2][6] = 4 * q4 * vz + 2 * q2 * vx + 2 * q3 * vy;
+    Jx[2][7] = -(2 * q1 * q3 - 2 * q2 * q4);
+    Jx[2][8] = 2 * q1 * q2 + 2 * q3 * q4;
+    Jx[2][9] = 2 * q1 * q1 + 2 * q4 * q4 - 1;
+    /* qdot rows */
+    Jx[3][4] = -wx / 2; Jx[3][5] = -wy / 2; Jx[3][6] = -wz / 2;
+    Jx[3][10] = -q2 / 2; Jx[3][11] = -q3 / 2; Jx[3][12] = -q4 / 2;
+    Jx[4][3] = wx / 2; Jx[4][5] = wz / 2; Jx[4][6] = -wy / 2;
+    Jx[4][10] = q1 / 2; Jx[4][11] = -q4 / 2; Jx[4][12] = q3 / 2;
+    Jx[5][3] = wy / 2; Jx[5][4] = -wz / 2; Jx[5][6] = wx / 2;
+    Jx[5][10] = q4 / 2; Jx[5][11] = q1 / 2; Jx[5][12] = -q2 / 2;
+    Jx[6][3] = wz / 2; Jx[6][4] = wy / 2; Jx[6][5] = -wx / 2;
+    Jx[6][10] = -q3 / 2; Jx[6][11] = q2 / 2; Jx[6][12] = q1 / 2;
+    /* vdot rows */
+    Jx[7][3] = 2 * g0 * q3; Jx[7][4] = -2 * g0 * q4; Jx[7][5] = 2 * g0 * q1; Jx[7][6] = -2 * g0 * q2;
+    Jx[7][8] = wz; Jx[7][9] = -wy; Jx[7][11] = -vz; Jx[7][12] = vy;
+    Jx[8][3] = -2 * g0 * q2; Jx[8][4] = -2 * g0 * q1; Jx[8][5] = -2 * g0 * q4; Jx[8][6] = -2 * g0 * q3;
+    Jx[8][7] = -wz; Jx[8][9] = wx; Jx[8][10] = vz; Jx[8][12] = -vx;
+    Jx[9][3] = -4 * g0 * q1; Jx[9][6] = -4 * g0 * q4;
+    Jx[9][7] = wy; Jx[9][8] = -wx; Jx[9][10] = -vy; Jx[9][11] = vx;
+    /* wdot rows */
+    Jx[10][11] = -(Izz - Iyy) * wz / Ixx; Jx[10][12] = -(Izz - Iyy) * wy / Ixx;
+    Jx[11][10] = -(Ixx - Izz) * wz / Iyy; Jx[11][12] = -(Ixx - Izz) * wx / Iyy;
+    Jx[12][10] = -(Iyy - Ixx) * wy / Izz; Jx[12][11] = -(Iyy - Ixx) * wx / Izz;
+    static const double s10[4] = {1, 1, -1, -1}, s11[4] = {1, -1, -1, 1}, s12[4] = {1, -1, 1, -1};
+    for (int j = 0; j < NU; j++) {
+        Ju[9][j] = 2 * Ct * u[j] / mq;
+        Ju[10][j] = -2 * Ct * arm * s10[j] * u[j] / Ixx;
+        Ju[11][j] = -2 * Ct * arm * s11[j] * u[j] / Iyy;
+        Ju[12][j] = -2 * Cd * s12[j] * u[j] / Izz;
+    }
+}
+
+/* forward VDE, column-major Sx[13x13], Su[13x4] like the reference's external
+ * function (acados_template/casadi_function_generation.py:137-151) */
+void cfo_vde(const double *x, const double *Sx, const double *Su, const double *u, double *f, double *dSx, double *dSu)
+{
+    double Jx[NX][NX], Ju[NX][NU];
+    jacobians(x, u, Jx, Ju);
+    cfo_ode(x, u, f);
+    for (int j = 0; j < NX; j++)
+        for (int i = 0; i < NX; i++) {
+            double s = 0;
+            for (int k = 0; k < NX; k++) s += Jx[i][k] * Sx[k + NX * j];
+            dSx[i + NX * j] = s;
+        }
+    for (int j = 0; j < NU; j++)
+        for (int i = 0; i < NX; i++) {
+            double s = Ju[i][j];
+            for (int k = 0; k < NX; k++) s += Jx[i][k] * Su[k + NX * j];
+            dSu[i + NX * j] = s;
+        }
+}
+
+/* sim_erk_integrator.c:658-731, tableau sim_collocation_utils.c:611-640 */
+#define NXX (NX + NX * NX + NX * NU)
+void cfo_erk4(const double *x, const double *u, double h, double *xn, double *A, double *B)
+{
+    static const double a_prev[4] = {0, 0.5, 0.5, 1.0}; /* A[s][s-1], all other entries 0 */
+    static const double bw[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+    double X[NXX], K[4][NXX], R[NXX];
+    memset(X, 0, sizeof X);
+    for (int i = 0; i < NX; i++) { X[i] = x[i]; X[NX + i * (NX + 1)] = 1.0; } /* Sx = I, Su = 0 */
+    for (int s = 0; s < 4; s++) {
+        for (int i = 0; i < NXX; i++) R[i] = X[i];
+        if (s > 0) {
+            double a = a_prev[s] * h;
+            for (int i = 0; i < NXX; i++) R[i] += a * K[s - 1][i];
+        }
+        cfo_vde(R, R + NX, R + NX + NX * NX, u, K[s], K[s] + NX, K[s] + NX + NX * NX);
+    }
+    for (int s = 0; s < 4; s++) {
+        double b = h * bw[s];
+        for (int i = 0; i < NXX; i++) X[i] += b * K[s][i];
+    }
+    for (int i = 0; i < NX; i++) xn[i] = X[i];
+    for (int i = 0; i < NX; i++) {
+        for (int j = 0; j < NX; j++) A[i * NX + j] = X[NX + i + NX * j];
+        for (int j = 0; j < NU; j++) B[i * NU + j] = X[NX + NX * NX + i + NX * j];
+    }
+}
+
+void cfo_sim(const double *x, const double *u, double T, int n_steps, double *xn)
+{
+    static const double a_prev[4] = {0, 0.5, 0.5, 1.0};
+    static const double bw[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+    double h = T / n_steps, X[NX], K[4][NX], R[NX];
+    for (int i = 0; i < NX; i++) X[i] = x[i];
+    for (int st = 0; st < n_steps; st++) {
+        for (int s = 0; s < 4; s++) {
+            for (int i = 0; i < NX; i++) R[i] = X[i];
+            if (s > 0) { double a = a_prev[s] * h; for (int i = 0; i < NX; i++) R[i] += a * K[s - 1][i]; }
+            cfo_ode(R, u, K[s]);
+        }
+        for (int s = 0; s < 4; s++) { double b = h * bw[s]; for (int i = 0; i < NX; i++) X[i] += b * K[s][i]; }
+    }
+    for (int i = 0; i < NX; i++) xn[i] = X[i];
+}
+
+/* ------------------------------------------------------------ linearisation
+ * ocp_nlp_common.c:2157-2292 calling dynamics_cont :755-884, cost_ls :810-916,
+ * constraints_bgh :1613-1648.  Output layout = cfref_get_qp. */
+void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, const double *yref,
+                   const double *yref_e, const double *x, const double *u, double *BAbt, double *b,
+                   double *rqz, double *d_lb, double *d_ub)
+{
+    cfo_params pd;
+    if (!p_) { cfo_default_params(&pd); p_ = &pd; }
+    int od = 0;
+    for (int k = 0; k <= N; k++) {
+        const double *xk = x + NX * k;
+        if (k < N) {
+            const double *uk = u + NU * k;
+            double xn[NX], A[NX * NX], B[NX * NU];
+            cfo_erk4(xk, uk, Ts, xn, A, B);
+            if (BAbt) {
+                double *M = BAbt + (size_t) k * NV * NX;
+                for (int j = 0; j < NU; j++) for (int i = 0; i < NX; i++) M[j * NX + i] = B[i * NU + j];
+                for (int j = 0; j < NX; j++) for (int i = 0; i < NX; i++) M[(NU + j) * NX + i] = A[i * NX + j];
+            }
+            if (b) for (int i = 0; i < NX; i++) b[NX * k + i] = xn[i] - x[NX * (k + 1) + i];
+            if (rqz) {
+                /* grad = scaling * Cyt * W * (Cy ux - yref), [u;x] order */
+                double *g = rqz + NV * k;
+                const double *yr = yref + NV * k;
+                for (int i = 0; i < NU; i++) g[i] = (p_->Wdiag[NX + i] * (uk[i] - yr[NX + i])) * Ts;
+                for (int i = 0; i < NX; i++) g[NU + i] = (p_->Wdiag[i] * (xk[i] - yr[i])) * Ts;
+            }
+            int nb = k == 0 ? NV : NU;
+            for (int i = 0; i < NU; i++) {
+                if (d_lb) d_lb[od + i] = p_->lbu[i] - uk[i];
+                if (d_ub) d_ub[od + i] = uk[i] - p_->ubu[i];
+            }
+            if (k == 0)
+                for (int i = 0; i < NX; i++) {
+                    if (d_lb) d_lb[od + NU + i] = x0[i] - xk[i];
+                    if (d_ub) d_ub[od + NU + i] = xk[i] - x0[i];
+                }
+            od += nb;
+        } else if (rqz) {
+            double *g = rqz + NV * N;
+            for (int i = 0; i < NX; i++) g[i] = p_->WNdiag[i] * (xk[i] - yref_e[i]);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ QP / IPM
+ * Reduced QP after x0 elimination (x_ocp_qp_red.c:268-455): stage 0 has nx=0. */
+typedef struct
+{
+    int nu, nx, nv, nb;
+    double M[NV][NX]; /* [B';A'] rows (nv of them) */
+    double b[NX];
+    double H[NV], rq[NV]; /* diagonal Hessian (+ gradient) */
+    double d[2 * NU];     /* [lb; ub] (HPIPM sign convention) */
+    double ux[NV], pi[NX], lam[2 * NU], t[2 * NU];
+    double res_g[NV], res_b[NX], res_d[2 * NU], res_m[2 * NU], res_m_bkp[2 * NU];
+    double dux[NV], dpi[NX], dlam[2 * NU], dt[2 * NU];
+    double rg2[NV], rb2[NX], rd2[2 * NU], rm2[2 * NU];                /* res_itref */
+    double dux2[NV], dpi2[NX], dlam2[2 * NU], dt2[2 * NU];            /* sol_itref */
+    double L[NV + 1][NV];
+    double Gamma[2 * NU], gamma[2 * NU], t_inv[2 * NU], Pb[NX];
+} stage;
+
+typedef struct
+{
+    int N, nc;
+    stage *s;
+    double mu, alpha, mu_aff, sigma;
+    double res_max[4], res2_max[4];
+} ipm;
+
+/* HPIPM arguments in effect: BALANCE mode + acados overrides, ocp_qp_hpipm.c:96-108,
+ * x_ocp_qp_ipm.c:133-161 */
+static const double RES_G_MAX = 1e-6, RES_B_MAX = 1e-8, RES_D_MAX = 1e-8, RES_M_MAX = 1e-8;
+static const double ALPHA_MIN = 1e-8, MU0 = 1.0, REG_PRIM = 1e-15, LAM_MIN = 1e-16, T_MIN = 1e-16, TAU_MIN = 1e-16;
+static const int ITER_MAX = 50, ITREF_CORR_MAX = 2;
+
+/* lower Cholesky of the n x n top of an m x n block, remaining rows solved;
+ * non-positive pivot -> 0 (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714) */
+static void potrf_l_mn(int m, int n, double L[NV + 1][NV])
+{
+    for (int j = 0; j < n; j++) {
+        double djj = L[j][j];
+        for (int c = 0; c < j; c++) djj -= L[j][c] * L[j][c];
+        double inv;
+        if (djj > 0) { djj = sqrt(djj); inv = 1.0 / djj; } else { djj = 0.0; inv = 0.0; }
+        L[j][j] = djj;
+        for (int i = j + 1; i < m; i++) {
+            double v = L[i][j];
+            for (int c = 0; c < j; c++) v -= L[i][c] * L[j][c];
+            L[i][j] = v * inv;
+        }
+    }
+}
+
+/* Gamma, gamma: x_core_qp_ipm_aux.c:38-111 (t_lam_min==2 -> plain branch) */
+static void compute_Gamma_gamma(ipm *w, int with_Gamma, int itref)
+{
+    for (int k = 0; k <= w->N; k++) {
+        stage *s = &w->s[k];
+        const double *rd = itref ? s->rd2 : s->res_d, *rm = itref ? s->rm2 : s->res_m;
+        for (int i = 0; i < 2 * s->nb; i++) {
+            if (with_Gamma) { s->t_inv[i] = 1.0 / s->t[i]; s->Gamma[i] = s->t_inv[i] * s->lam[i]; }
+            s->gamma[i] = s->t_inv[i] * (rm[i] - s->lam[i] * rd[i]);
+        }
+    }
+}
+
+/* dlam, dt from dux: x_ocp_qp_kkt.c:741-758, x_core_qp_ipm_aux.c:117-142 */
+static void compute_lam_t(ipm *w, int itref)
+{
+    for (int k = 0; k <= w->N; k++) {
+        stage *s = &w->s[k];
+        const double *rd = itref ? s->rd2 : s->res_d, *rm = itref ? s->rm2 : s->res_m;
+        const double *dux = itref ? s->dux2 : s->dux;
+        double *dlam = itref ? s->dlam2 : s->dlam, *dt = itref ? s->dt2 : s->dt;
+        for (int i = 0; i < s->nb; i++) { dt[i] = dux[i]; dt[s->nb + i] = -dux[i]; }
+        for (int i = 0; i < 2 * s->nb; i++) {
+            dlam[i] = -s->t_inv[i] * (rm[i] + (s->lam[i] * dt[i]) - (s->lam[i] * rd[i]));
+            dt[i] -= rd[i];
+        }
+    }
+}
+
+/* forward substitution shared by factorise-and-solve and solve
+ * (x_ocp_qp_kkt.c:536-570 / :1250-1290).  On entry dux[k][0:nu] holds the
+ * u-part rhs (already negated), pl[k] the x-part "l" vector of stage k. */
+static void ric_forward(ipm *w, double (*pl)[NX], int itref, int l_is_scaled)
+{
+    int N = w->N;
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w->s[k];
+        double *dux = itref ? s->dux2 : s->dux;
+        const double *rb = itref ? s->rb2 : s->res_b;
+        /* TRSV_LTN_MN(nv, nu): du = Luu^-T (du - Lxu' dx) */
+        for (int j = s->nu - 1; j >= 0; j--) {
+            double v = dux[j];
+            for (int i = j + 1; i < s->nv; i++) v -= s->L[i][j] * dux[i];
+            dux[j] = v * (1.0 / s->L[j][j]);
+        }
+        if (k == N) break;
+        stage *n = &w->s[k + 1];
+        double *ndux = itref ? n->dux2 : n->dux, *dpi = itref ? s->dpi2 : s->dpi;
+        /* dx+ = [B A] dux + res_b */
+        for (int c = 0; c < NX; c++) {
+            double v = 0;
+            for (int r = 0; r < s->nv; r++) v += s->M[r][c] * dux[r];
+            ndux[n->nu + c] = v + rb[c];
+        }
+        /* dpi: x_ocp_qp_kkt.c:545-547 (factorise) / :1262-1266 (solve) */
+        double tmp[NX];
+        for (int c = 0; c < NX; c++) {
+            double v = 0;
+            for (int r = c; r < NX; r++) v += n->L[n->nu + r][n->nu + c] * ndux[n->nu + r];
+            tmp[c] = l_is_scaled ? v + pl[k + 1][c] : v; /* fact: Lxx (Lxx' dx + l~) */
+        }
+        for (int r = 0; r < NX; r++) {
+            double v = 0;
+            for (int c = 0; c <= r; c++) v += n->L[n->nu + r][n->nu + c] * tmp[c];
+            dpi[r] = l_is_scaled ? v : v + pl[k + 1][r]; /* solve: p + Lxx Lxx' dx */
+        }
+    }
+}
+
+/* OCP_QP_FACT_SOLVE_KKT_STEP, square-root branch: x_ocp_qp_kkt.c:445-572 */
+static void fact_solve_kkt_step(ipm *w)
+{
+    int N = w->N;
+    double(*pl)[NX] = malloc(sizeof(double[NX]) * (N + 1));
+    compute_Gamma_gamma(w, 1, 0);
+    for (int k = N; k >= 0; k--) {
+        stage *s = &w->s[k];
+        double AL[NV + 1][NX];
+        if (k < N) {
+            stage *n = &w->s[k + 1];
+            /* AL = [B';A';res_b'] * Lxx(k+1)   (TRMM_RLNN) */
+            for (int r = 0; r <= s->nv; r++)
+                for (int c = 0; c < NX; c++) {
+                    double v = 0;
+                    for (int j = c; j < NX; j++)
+                        v += (r < s->nv ? s->M[r][j] : s->res_b[j]) * n->L[n->nu + j][n->nu + c];
+                    AL[r][c] = v;
+                }
+            /* Pb = Lxx * AL[last]'  (TRMV_LNN) */
+            for (int r = 0; r < NX; r++) {
+                double v = 0;
+                for (int c = 0; c <= r; c++) v += n->L[n->nu + r][n->nu + c] * AL[s->nv][c];
+                s->Pb[r] = v;
+            }
+            for (int c = 0; c < NX; c++) AL[s->nv][c] += n->L[n->nv][n->nu + c];
+        }
+        memset(s->L, 0, sizeof s->L);
+        for (int i = 0; i < s->nv; i++) { s->L[i][i] = s->H[i] + REG_PRIM; s->L[s->nv][i] = s->res_g[i]; }
+        for (int i = 0; i < s->nb; i++) {
+            s->L[i][i] += s->Gamma[i] + s->Gamma[s->nb + i];
+            s->L[s->nv][i] += s->gamma[i] - s->gamma[s->nb + i];
+        }
+        if (k < N)
+            for (int r = 0; r <= s->nv; r++)
+                for (int c = 0; c <= r && c < s->nv; c++) {
+                    double v = 0;
+                    for (int j = 0; j < NX; j++) v += AL[r][j] * AL[c][j];
+                    s->L[r][c] += v;
+                }
+        potrf_l_mn(s->nv + 1, s->nv, s->L);
+    }
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < s->nu; i++) s->dux[i] = -s->L[s->nv][i];
+        for (int i = 0; i < s->nx; i++) pl[k][i] = s->L[s->nv][s->nu + i];
+    }
+    ric_forward(w, pl, 0, 1);
+    compute_lam_t(w, 0);
+    free(pl);
+}
+
+/* OCP_QP_SOLVE_KKT_STEP, square-root branch: x_ocp_qp_kkt.c:1147-1292.
+ * itref=0: rhs = res_*, sol = d*   (qp_step / sol_step)
+ * itref=1: rhs = r*2,   sol = d*2  (qp_itref / sol_itref), use_Pb = 0 */
+static void solve_kkt_step(ipm *w, int use_Pb, int itref)
+{
+    int N = w->N;
+    double(*pl)[NX] = malloc(sizeof(double[NX]) * (N + 1));
+    compute_Gamma_gamma(w, 0, itref);
+    for (int k = N; k >= 0; k--) {
+        stage *s = &w->s[k];
+        double *dux = itref ? s->dux2 : s->dux;
+        const double *rg = itref ? s->rg2 : s->res_g, *rb = itref ? s->rb2 : s->res_b;
+        for (int i = 0; i < s->nv; i++) dux[i] = rg[i];
+        for (int i = 0; i < s->nb; i++) dux[i] += s->gamma[i] - s->gamma[s->nb + i];
+        if (k < N) {
+            stage *n = &w->s[k + 1];
+            const double *ndux = itref ? n->dux2 : n->dux;
+            double tmp[NX];
+            if (use_Pb) {
+                for (int i = 0; i < NX; i++) tmp[i] = ndux[n->nu + i] + s->Pb[i];
+            } else {
+                double t2[NX];
+                for (int c = 0; c < NX; c++) {
+                    double v = 0;
+                    for (int r = c; r < NX; r++) v += n->L[n->nu + r][n->nu + c] * rb[r];
+                    t2[c] = v;
+                }
+                for (int r = 0; r < NX; r++) {
+                    double v = 0;
+                    for (int c = 0; c <= r; c++) v += n->L[n->nu + r][n->nu + c] * t2[c];
+                    tmp[r] = v + ndux[n->nu + r];
+                }
+            }
+            for (int r = 0; r < s->nv; r++) {
+                double v = 0;
+                for (int c = 0; c < NX; c++) v += s->M[r][c] * tmp[c];
+                dux[r] += v;
+            }
+        }
+        /* TRSV_LNN_MN(nv, nu) */
+        for (int i = 0; i < s->nu; i++) {
+            double v = dux[i];
+            for (int c = 0; c < i; c++) v -= s->L[i][c] * dux[c];
+            dux[i] = v * (1.0 / s->L[i][i]);
+        }
+        for (int i = s->nu; i < s->nv; i++) {
+            double v = dux[i];
+            for (int c = 0; c < s->nu; c++) v -= s->L[i][c] * dux[c];
+            dux[i] = v;
+        }
+    }
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w->s[k];
+        double *dux = itref ? s->dux2 : s->dux;
+        for (int i = 0; i < s->nx; i++) pl[k][i] = dux[s->nu + i];
+        for (int i = 0; i < s->nu; i++) dux[i] = -dux[i];
+    }
+    ric_forward(w, pl, itref, 0);
+    compute_lam_t(w, itref);
+    free(pl);
+}
+
+/* OCP_QP_RES_COMPUTE: x_ocp_qp_res.c:334-470 */
+static void res_compute(ipm *w)
+{
+    int N = w->N;
+    double mu = 0;
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < s->nv; i++) s->res_g[i] = s->H[i] * s->ux[i] + s->rq[i];
+        if (k > 0) for (int i = 0; i < s->nx; i++) s->res_g[s->nu + i] -= w->s[k - 1].pi[i];
+        for (int i = 0; i < s->nb; i++) {
+            s->res_g[i] += s->lam[s->nb + i] - s->lam[i];
+            s->res_d[i] = s->d[i] + s->t[i] - s->ux[i];
+            s->res_d[s->nb + i] = s->d[s->nb + i] + s->t[s->nb + i] + s->ux[i];
+        }
+        if (k < N) {
+            stage *n = &w->s[k + 1];
+            for (int c = 0; c < NX; c++) {
+                double v = s->b[c] - n->ux[n->nu + c];
+                for (int r = 0; r < s->nv; r++) v += s->M[r][c] * s->ux[r];
+                s->res_b[c] = v;
+            }
+            for (int r = 0; r < s->nv; r++) {
+                double v = 0;
+                for (int c = 0; c < NX; c++) v += s->M[r][c] * s->pi[c];
+                s->res_g[r] += v;
+            }
+        }
+        for (int i = 0; i < 2 * s->nb; i++) { s->res_m[i] = s->lam[i] * s->t[i]; mu += s->res_m[i]; }
+    }
+    w->mu = mu * (1.0 / w->nc);
+}
+
+/* OCP_QP_RES_COMPUTE_LIN: x_ocp_qp_res.c:474-598; rhs = qp_step (= current res_*),
+ * solution = current step, result in r*2 */
+static void res_compute_lin(ipm *w)
+{
+    int N = w->N;
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < s->nv; i++) s->rg2[i] = s->H[i] * s->dux[i] + s->res_g[i];
+        if (k > 0) for (int i = 0; i < s->nx; i++) s->rg2[s->nu + i] -= w->s[k - 1].dpi[i];
+        for (int i = 0; i < s->nb; i++) {
+            s->rg2[i] += s->dlam[s->nb + i] - s->dlam[i];
+            s->rd2[i] = s->res_d[i] + s->dt[i] - s->dux[i];
+            s->rd2[s->nb + i] = s->res_d[s->nb + i] + s->dt[s->nb + i] + s->dux[i];
+        }
+        if (k < N) {
+            stage *n = &w->s[k + 1];
+            for (int c = 0; c < NX; c++) {
+                double v = s->res_b[c] - n->dux[n->nu + c];
+                for (int r = 0; r < s->nv; r++) v += s->M[r][c] * s->dux[r];
+                s->rb2[c] = v;
+            }
+            for (int r = 0; r < s->nv; r++) {
+                double v = 0;
+                for (int c = 0; c < NX; c++) v += s->M[r][c] * s->dpi[c];
+                s->rg2[r] += v;
+            }
+        }
+        for (int i = 0; i < 2 * s->nb; i++)
+            s->rm2[i] = s->res_m[i] + s->lam[i] * s->dt[i] + s->dlam[i] * s->t[i];
+    }
+}
+
+static void inf_norms(ipm *w, int itref, double *out)
+{
+    double g = 0, b = 0, d = 0, m = 0;
+    for (int k = 0; k <= w->N; k++) {
+        stage *s = &w->s[k];
+        const double *rg = itref ? s->rg2 : s->res_g, *rb = itref ? s->rb2 : s->res_b;
+        const double *rd = itref ? s->rd2 : s->res_d, *rm = itref ? s->rm2 : s->res_m;
+        for (int i = 0; i < s->nv; i++) g = fmax(g, fabs(rg[i]));
+        if (k < w->N) for (int i = 0; i < NX; i++) b = fmax(b, fabs(rb[i]));
+        for (int i = 0; i < 2 * s->nb; i++) { d = fmax(d, fabs(rd[i])); m = fmax(m, fabs(rm[i])); }
+    }
+    out[0] = g; out[1] = b; out[2] = d; out[3] = m;
+}
+
+/* COMPUTE_ALPHA_QP: x_core_qp_ipm_aux.c:146-216 (single step length, split_step 0) */
+static void compute_alpha(ipm *w)
+{
+    double ap = -1.0, ad = -1.0;
+    for (int k = 0; k <= w->N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < 2 * s->nb; i++) {
+            if (ad * s->dlam[i] > s->lam[i]) ad = s->lam[i] / s->dlam[i];
+            if (ap * s->dt[i] > s->t[i]) ap = s->t[i] / s->dt[i];
+        }
+    }
+    double a = ap > ad ? ap : ad;
+    w->alpha = -a;
+}
+
+static void compute_mu_aff(ipm *w)
+{
+    double mu = 0;
+    for (int k = 0; k <= w->N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < 2 * s->nb; i++)
+            mu += (s->lam[i] + w->alpha * s->dlam[i]) * (s->t[i] + w->alpha * s->dt[i]);
+    }
+    w->mu_aff = mu * (1.0 / w->nc);
+}
+
+static int itref_converged(const ipm *w)
+{
+    const double *n = w->res2_max, *r = w->res_max;
+    return (n[0] < RES_G_MAX || n[0] < 1e-3 * r[0]) && (n[1] < RES_B_MAX || n[1] < 1e-3 * r[1]) &&
+           (n[2] < RES_D_MAX || n[2] < 1e-3 * r[2]) && (n[3] < RES_M_MAX || n[3] < 1e-3 * r[3]);
+}
+
+/* OCP_QP_IPM_DELTA_STEP: x_ocp_qp_ipm.c:1943-2405 */
+static void delta_step(ipm *w, cfo_info *info)
+{
+    int N = w->N;
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < 2 * s->nb; i++) { s->res_m_bkp[i] = s->res_m[i]; s->res_m[i] = s->res_m_bkp[i] - TAU_MIN; }
+    }
+    fact_solve_kkt_step(w);
+    /* lq_fact==1: linear-system residual decides on an LQ refactorisation (:2011-2059).
+     * Never taken on this OCP; detected and counted, not restated. */
+    res_compute_lin(w);
+    inf_norms(w, 1, w->res2_max);
+    if ((w->res2_max[0] == 0.0 && isnan(w->s[0].rg2[0])) || w->res2_max[0] > 1e-5 || w->res2_max[1] > 1e-5 ||
+        w->res2_max[2] > 1e-5 || w->res2_max[3] > 1e-5)
+        info->n_lq_flag++;
+
+    compute_alpha(w);
+    compute_mu_aff(w);
+    double tmp = w->mu_aff / w->mu;
+    w->sigma = tmp * tmp * tmp;
+    double sigma_mu = w->sigma * w->mu;
+    sigma_mu = sigma_mu > TAU_MIN ? sigma_mu : TAU_MIN;
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < 2 * s->nb; i++) s->res_m[i] = s->res_m_bkp[i] + s->dt[i] * s->dlam[i] - sigma_mu;
+    }
+    solve_kkt_step(w, 1, 0);
+    compute_alpha(w);
+    /* conditional predictor-corrector (:2230-2273) */
+    double mu_aff0 = w->mu_aff;
+    compute_mu_aff(w);
+    if (w->mu_aff > 2.0 * mu_aff0) {
+        for (int k = 0; k <= N; k++) {
+            stage *s = &w->s[k];
+            for (int i = 0; i < 2 * s->nb; i++) s->res_m[i] = s->res_m_bkp[i] - sigma_mu;
+        }
+        solve_kkt_step(w, 1, 0);
+        compute_alpha(w);
+    }
+    /* iterative refinement on the corrector (:2275-2366) */
+    int refined = 0, it;
+    for (it = 0; it < ITREF_CORR_MAX; it++) {
+        res_compute_lin(w);
+        inf_norms(w, 1, w->res2_max);
+        if (itref_converged(w)) break;
+        solve_kkt_step(w, 0, 1);
+        refined = 1;
+        info->n_itref++;
+        for (int k = 0; k <= N; k++) {
+            stage *s = &w->s[k];
+            for (int i = 0; i < s->nv; i++) s->dux[i] += s->dux2[i];
+            if (k < N) for (int i = 0; i < NX; i++) s->dpi[i] += s->dpi2[i];
+            for (int i = 0; i < 2 * s->nb; i++) { s->dlam[i] += s->dlam2[i]; s->dt[i] += s->dt2[i]; }
+        }
+    }
+    if (refined) compute_alpha(w);
+    /* UPDATE_VAR_QP: x_core_qp_ipm_aux.c:220-325 */
+    double alpha = w->alpha;
+    if (alpha < 1.0) alpha = alpha * ((1.0 - alpha) * 0.99 + alpha * 0.9999999);
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < s->nv; i++) s->ux[i] += alpha * s->dux[i];
+        if (k < N) for (int i = 0; i < NX; i++) s->pi[i] += alpha * s->dpi[i];
+        for (int i = 0; i < 2 * s->nb; i++) {
+            s->lam[i] += alpha * s->dlam[i];
+            s->lam[i] = s->lam[i] <= LAM_MIN ? LAM_MIN : s->lam[i];
+            s->t[i] += alpha * s->dt[i];
+            s->t[i] = s->t[i] <= T_MIN ? T_MIN : s->t[i];
+        }
+    }
+}
+
+/* OCP_QP_INIT_VAR, scheme 1: x_ocp_qp_ipm.c:1491-1530,1636-1769 */
+static void init_var(ipm *w)
+{
+    const double thr0 = 1e-1;
+    for (int k = 0; k <= w->N; k++) {
+        stage *s = &w->s[k];
+        for (int i = 0; i < s->nv; i++) s->ux[i] = 0.0;
+        for (int i = 0; i < NX; i++) s->pi[i] = 0.0;
+        for (int i = 0; i < s->nb; i++) {
+            double *tl = &s->t[i], *tu = &s->t[s->nb + i];
+            *tl = s->ux[i] - s->d[i];
+            *tu = -s->ux[i] - s->d[s->nb + i];
+            if (*tl < thr0) {
+                if (*tu < thr0) {
+                    s->ux[i] = 0.5 * (s->d[i] - s->d[s->nb + i]);
+                    *tl = thr0;
+                    *tu = thr0;
+                } else {
+                    *tl = thr0;
+                    s->ux[i] = s->d[i] + thr0;
+                }
+            } else if (*tu < thr0) {
+                *tu = thr0;
+                s->ux[i] = -s->d[s->nb + i] - thr0;
+            }
+        }
+        for (int i = 0; i < 2 * s->nb; i++) s->lam[i] = MU0 / s->t[i];
+    }
+}
+
+/* OCP_QP_IPM_SOLVE, delta formulation: x_ocp_qp_ipm.c:2409-2759 */
+static void ipm_solve(ipm *w, cfo_info *info)
+{
+    init_var(w);
+    w->alpha = 1.0;
+    res_compute(w);
+    inf_norms(w, 0, w->res_max);
+    int kk;
+    for (kk = 0; kk < ITER_MAX && w->alpha > ALPHA_MIN &&
+                 (w->res_max[0] > RES_G_MAX || w->res_max[1] > RES_B_MAX || w->res_max[2] > RES_D_MAX ||
+                  fabs(w->res_max[3] - TAU_MIN) > RES_M_MAX);
+         kk++) {
+        delta_step(w, info);
+        res_compute(w);
+        inf_norms(w, 0, w->res_max);
+    }
+    info->qp_iter = kk;
+    if (kk == ITER_MAX) info->qp_status = 1;
+    else if (w->alpha <= ALPHA_MIN) info->qp_status = 2;
+    else if (isnan(w->mu)) info->qp_status = 3;
+    else info->qp_status = 0;
+    for (int i = 0; i < 4; i++) info->res[i] = w->res_max[i];
+}
+
+int cfo_rti(int N, double Ts, const cfo_params *p_, const double *x0, const double *yref,
+            const double *yref_e, double *x, double *u, cfo_info *info_, double *dux_out, double *dpi_out)
+{
+    cfo_params pd;
+    cfo_info li;
+    cfo_info *info = info_ ? info_ : &li;
+    memset(info, 0, sizeof *info);
+    if (!p_) { cfo_default_params(&pd); p_ = &pd; }
+
+    /* --- preparation + QP vectors */
+    double *BAbt = malloc(sizeof(double) * N * NV * NX), *b = malloc(sizeof(double) * N * NX);
+    double *rqz = malloc(sizeof(double) * (N * NV + NX));
+    double *dl = malloc(sizeof(double) * (NV + NU * N)), *du = malloc(sizeof(double) * (NV + NU * N));
+    cfo_linearize(N, Ts, p_, x0, yref, yref_e, x, u, BAbt, b, rqz, dl, du);
+
+    /* --- reduce: eliminate the 13 equality-bounded x0 (x_ocp_qp_red.c:268-455) */
+    ipm w;
+    w.N = N;
+    w.nc = 2 * NU * N;
+    w.s = calloc(N + 1, sizeof(stage));
+    double xbar[NX];
+    for (int i = 0; i < NX; i++) xbar[i] = dl[NU + i]; /* lower-bound entry is the value (:310-315) */
+    for (int k = 0; k <= N; k++) {
+        stage *s = &w.s[k];
+        s->nu = k < N ? NU : 0;
+        s->nx = k == 0 ? 0 : NX;
+        s->nv = s->nu + s->nx;
+        s->nb = k < N ? NU : 0;
+        /* Hessian: scaling * (sqrt(w))^2, cost_ls.c:739-772 */
+        for (int i = 0; i < s->nu; i++) { double r = sqrt(p_->Wdiag[NX + i]); s->H[i] = Ts * (r * r); }
+        for (int i = 0; i < s->nx; i++) {
+            double r = sqrt(k < N ? p_->Wdiag[i] : p_->WNdiag[i]);
+            s->H[s->nu + i] = (k < N ? Ts : 1.0) * (r * r);
+        }
+        const double *g = rqz + NV * k;
+        if (k == 0) {
+            for (int i = 0; i < NU; i++) s->rq[i] = g[i]; /* diagonal RSQ: no cross term from xbar (:354) */
+        } else {
+            for (int i = 0; i < s->nv; i++) s->rq[i] = g[i];
+        }
+        if (k < N) {
+            const double *M = BAbt + (size_t) k * NV * NX;
+            if (k == 0) {
+                for (int r = 0; r < NU; r++) for (int c = 0; c < NX; c++) s->M[r][c] = M[r * NX + c];
+                for (int c = 0; c < NX; c++) {
+                    double v = 0; /* b0 += A0 xbar  (GEMV_T over the masked vector, :330) */
+                    for (int r = 0; r < NX; r++) v += M[(NU + r) * NX + c] * xbar[r];
+                    s->b[c] = v + b[c];
+                }
+            } else {
+                for (int r = 0; r < NV; r++) for (int c = 0; c < NX; c++) s->M[r][c] = M[r * NX + c];
+                for (int c = 0; c < NX; c++) s->b[c] = b[NX * k + c];
+            }
+            int od = k == 0 ? 0 : NV + NU * (k - 1);
+            for (int i = 0; i < NU; i++) { s->d[i] = dl[od + i]; s->d[NU + i] = du[od + i]; }
+        }
+    }
+
+    ipm_solve(&w, info);
+
+    /* --- restore (x_ocp_qp_red.c:723-871) + primal update (ocp_nlp_common.c:2900-2952) */
+    if (dux_out) {
+        for (int i = 0; i < NU; i++) dux_out[i] = w.s[0].ux[i];
+        for (int i = 0; i < NX; i++) dux_out[NU + i] = xbar[i];
+        for (int k = 1; k <= N; k++) for (int i = 0; i < w.s[k].nv; i++) dux_out[NV * k + i] = w.s[k].ux[i];
+    }
+    if (dpi_out) for (int k = 0; k < N; k++) for (int i = 0; i < NX; i++) dpi_out[NX * k + i] = w.s[k].pi[i];
+    int status = 0;
+    if (info->qp_status == 0 || info->qp_status == 1) {
+        for (int i = 0; i < NU; i++) u[i] += w.s[0].ux[i];
+        for (int i = 0; i < NX; i++) x[i] += xbar[i];
+        for (int k = 1; k <= N; k++) {
+            if (k < N) for (int i = 0; i < NU; i++) u[NU * k + i] += w.s[k].ux[i];
+            for (int i = 0; i < NX; i++) x[NX * k + i] += w.s[k].ux[w.s[k].nu + i];
+        }
+    } else {
+        status = 4; /* ACADOS_QP_FAILURE, iterate untouched (ocp_nlp_sqp_rti.c:651-664) */
+    }
+    free(w.s); free(BAbt); free(b); free(rqz); free(dl); free(du);
+    return status;
+}
+
+void cfo_batch(int N, double Ts, const cfo_params *p, int n_rti, int n, const double *x0,
+               const double *yref, const double *yref_e, double *x, double *u, int *status, int *qp_iter)
+{
+    for (int i = 0; i < n; i++) {
+        cfo_info info;
+        int st = 0;
+        for (int r = 0; r < n_rti; r++)
+            st = cfo_rti(N, Ts, p, x0 + NX * (size_t) i, yref + (size_t) N * NV * i, yref_e + NX * (size_t) i,
+                         x + (size_t) (N + 1) * NX * i, u + (size_t) N * NU * i, &info, NULL, NULL);
+        if (status) status[i] = st;
+        if (qp_iter) qp_iter[i] = info.qp_iter;
+    }
+}

@@ -1,0 +1,197 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes access to the two CPU checkers.
+
+* ``Port``  : oracle/liboracle.so, our plain-C restatement (cfnmpc_oracle.c).
+* ``Ref``   : oracle/_ref/libcfref.so, the reference's own acados/HPIPM/BLASFEO
+              code compiled from /root/reference (oracle/Makefile, ref_harness.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product package
+(crazyflie_nmpc_b200) never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NX, NU, NV = 13, 4, 17
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+def _P(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _I(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def build(ref=True, quiet=True):
+    """Compile the checkers (idempotent). `ref` is skipped where /root/reference is absent."""
+    targets = ["oracle"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-s", "-j8", "-C", HERE] + targets, check=True,
+                   stdout=subprocess.DEVNULL if quiet else None, stderr=subprocess.DEVNULL if quiet else None)
+
+
+class CfoParams(ctypes.Structure):
+    _fields_ = [("Wdiag", ctypes.c_double * 17), ("WNdiag", ctypes.c_double * 13),
+                ("lbu", ctypes.c_double * 4), ("ubu", ctypes.c_double * 4)]
+
+
+class CfoInfo(ctypes.Structure):
+    _fields_ = [("qp_iter", ctypes.c_int), ("qp_status", ctypes.c_int), ("n_lq_flag", ctypes.c_int),
+                ("n_itref", ctypes.c_int), ("res", ctypes.c_double * 4)]
+
+
+class Port:
+    """Plain-C restatement."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        L = self.lib = ctypes.CDLL(path)
+        L.cfo_rti.restype = ctypes.c_int
+        L.cfo_rti.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), _dp, _dp, _dp, _dp, _dp,
+                              ctypes.POINTER(CfoInfo), _dp, _dp]
+        L.cfo_linearize.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams)] + [_dp] * 10
+        L.cfo_batch.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), ctypes.c_int, ctypes.c_int,
+                                _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+        L.cfo_erk4.argtypes = [_dp, _dp, ctypes.c_double, _dp, _dp, _dp]
+        L.cfo_sim.argtypes = [_dp, _dp, ctypes.c_double, ctypes.c_int, _dp]
+        L.cfo_ode.argtypes = [_dp, _dp, _dp]
+        L.cfo_default_params.argtypes = [ctypes.POINTER(CfoParams)]
+
+    def params(self, Wdiag=None, WNdiag=None, lbu=None, ubu=None):
+        p = CfoParams()
+        self.lib.cfo_default_params(ctypes.byref(p))
+        for name, v in (("Wdiag", Wdiag), ("WNdiag", WNdiag), ("lbu", lbu), ("ubu", ubu)):
+            if v is not None:
+                arr = getattr(p, name)
+                for i, e in enumerate(v):
+                    arr[i] = float(e)
+        return p
+
+    def ode(self, x, u):
+        f = np.zeros(NX)
+        self.lib.cfo_ode(_P(np.ascontiguousarray(x, float)), _P(np.ascontiguousarray(u, float)), _P(f))
+        return f
+
+    def erk4(self, x, u, h):
+        xn, A, B = np.zeros(NX), np.zeros((NX, NX)), np.zeros((NX, NU))
+        self.lib.cfo_erk4(_P(np.ascontiguousarray(x, float)), _P(np.ascontiguousarray(u, float)), h, _P(xn), _P(A), _P(B))
+        return xn, A, B
+
+    def sim(self, x, u, T, n_steps=1):
+        xn = np.zeros(NX)
+        self.lib.cfo_sim(_P(np.ascontiguousarray(x, float)), _P(np.ascontiguousarray(u, float)), T, n_steps, _P(xn))
+        return xn
+
+    def linearize(self, N, Ts, x0, yref, yref_e, x, u, params=None):
+        BAbt, b = np.zeros((N, NV, NX)), np.zeros((N, NX))
+        rqz, dl, du = np.zeros(N * NV + NX), np.zeros(NV + NU * (N - 1)), np.zeros(NV + NU * (N - 1))
+        a = [np.ascontiguousarray(v, float) for v in (x0, yref, yref_e, x, u)]
+        self.lib.cfo_linearize(N, Ts, ctypes.byref(params) if params else None, *[_P(v) for v in a],
+                               _P(BAbt), _P(b), _P(rqz), _P(dl), _P(du))
+        return dict(BAbt=BAbt, b=b, rqz=rqz, d_lb=dl, d_ub=du)
+
+    def rti(self, N, Ts, x0, yref, yref_e, x, u, params=None, want_step=False):
+        """One RTI step; x,u are updated in place. Returns (status, info[, dux, dpi])."""
+        info = CfoInfo()
+        dux = np.zeros(N * NV + NX) if want_step else None
+        dpi = np.zeros(N * NX) if want_step else None
+        a = [np.ascontiguousarray(v, float) for v in (x0, yref, yref_e)]
+        st = self.lib.cfo_rti(N, Ts, ctypes.byref(params) if params else None, *[_P(v) for v in a], _P(x), _P(u),
+                              ctypes.byref(info), _P(dux), _P(dpi))
+        return (st, info, dux, dpi) if want_step else (st, info)
+
+    def batch(self, N, Ts, x0, yref, yref_e, x, u, n_rti=1, params=None):
+        n = x0.shape[0]
+        status, qp_iter = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.lib.cfo_batch(N, Ts, ctypes.byref(params) if params else None, n_rti, n, _P(x0), _P(yref), _P(yref_e),
+                           _P(x), _P(u), _I(status), _I(qp_iter))
+        return status, qp_iter
+
+
+def ref_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libcfref.so"))
+
+
+class Ref:
+    """The reference's own implementation (needs oracle/_ref/libcfref.so)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libcfref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError("oracle/_ref/libcfref.so missing: run `make -C oracle ref` where /root/reference exists")
+        L = self.lib = ctypes.CDLL(path)
+        L.cfref_create.restype = ctypes.c_void_p
+        L.cfref_create.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        L.cfref_destroy.argtypes = [ctypes.c_void_p]
+        L.cfref_rti.restype = ctypes.c_int
+        L.cfref_rti.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
+        L.cfref_get_qp.argtypes = [ctypes.c_void_p] + [_dp] * 7
+        L.cfref_get_ipm_stat.restype = ctypes.c_int
+        L.cfref_get_ipm_stat.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, _ip]
+        L.cfref_set_weights.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.cfref_set_input_bounds.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.cfref_batch.restype = ctypes.c_int
+        L.cfref_batch.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
+
+    def solver(self, N=50, Ts=0.015, cond_N=0):
+        return RefSolver(self, N, Ts, cond_N)
+
+    def batch(self, N, Ts, x0, yref, yref_e, x, u, n_rti=1, nthreads=1, cond_N=0):
+        n = x0.shape[0]
+        status, qp_iter, t = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n)
+        fail = self.lib.cfref_batch(N, Ts, cond_N, nthreads, n_rti, n, _P(x0), _P(yref), _P(yref_e), _P(x), _P(u),
+                                    _I(status), _I(qp_iter), _P(t))
+        if fail:
+            raise RuntimeError("reference solver creation failed")
+        return status, qp_iter, t
+
+
+class RefSolver:
+    def __init__(self, ref, N, Ts, cond_N):
+        self.lib, self.N, self.Ts = ref.lib, N, Ts
+        self.h = self.lib.cfref_create(N, Ts, cond_N)
+        if not self.h:
+            raise RuntimeError("cfref_create failed")
+
+    def close(self):
+        if self.h:
+            self.lib.cfref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_weights(self, Wdiag, WNdiag):
+        self.lib.cfref_set_weights(self.h, _P(np.ascontiguousarray(Wdiag, float)), _P(np.ascontiguousarray(WNdiag, float)))
+
+    def set_input_bounds(self, lbu, ubu):
+        self.lib.cfref_set_input_bounds(self.h, _P(np.ascontiguousarray(lbu, float)), _P(np.ascontiguousarray(ubu, float)))
+
+    def rti(self, x0, yref, yref_e, x, u):
+        """One RTI step; x,u updated in place. Returns (status, qp_iter, qp_status, times[5])."""
+        qi, qs, t = ctypes.c_int(), ctypes.c_int(), np.zeros(5)
+        a = [np.ascontiguousarray(v, float) for v in (x0, yref, yref_e)]
+        st = self.lib.cfref_rti(self.h, *[_P(v) for v in a], _P(x), _P(u), ctypes.byref(qi), ctypes.byref(qs), _P(t))
+        return st, qi.value, qs.value, t
+
+    def qp(self):
+        N = self.N
+        BAbt, b = np.zeros((N, NV, NX)), np.zeros((N, NX))
+        rqz, dl, du = np.zeros(N * NV + NX), np.zeros(NV + NU * (N - 1)), np.zeros(NV + NU * (N - 1))
+        dux, dpi = np.zeros(N * NV + NX), np.zeros(N * NX)
+        self.lib.cfref_get_qp(self.h, _P(BAbt), _P(b), _P(rqz), _P(dl), _P(du), _P(dux), _P(dpi))
+        return dict(BAbt=BAbt, b=b, rqz=rqz, d_lb=dl, d_ub=du, dux=dux, dpi=dpi)
+
+    def ipm_stat(self):
+        m = ctypes.c_int()
+        buf = np.zeros(64 * 32)
+        rows = self.lib.cfref_get_ipm_stat(self.h, _P(buf), 64, ctypes.byref(m))
+        return buf[: rows * m.value].reshape(rows, m.value)
