@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched real-time-iteration NMPC steps for the Crazyflie OCP.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+A step = one RTI solve (preparation + feedback = one acados_solve()) of every instance of the batch from the
+same seeded initial iterate.  Workload = BASELINE.json configs[1] per GPU: 65,536 hover-regulation OCPs,
+N=50, nx=13, nu=4, random feasible x0 (crazyflie_nmpc_b200.workloads.hover_batch).  Weak scaling: the per-GPU
+batch is fixed, ranks are independent (no collective inside the solve); with N>1 ranks the solved first
+controls u0 are all-gathered over NCCL after each step (BASELINE config 4), inside the timed region.
+
+Prints ONE JSON line (rank 0). Contract keys: see the task description; extra objects: roofline, cpu_baseline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "NMPC solves/sec (batch, device-timed) N=50 nx=13 nu=4"
+UNIT = "solves/s"
+TS = 0.015
+
+
+def alg_bytes(N):
+    """Algorithmic (compulsory) bytes per solve, SURVEY.md 8(d): read x0, read yref, read + write the iterate."""
+    return 8 * (51 * N + 52)
+
+
+def make_workload(name, B, N, seed):
+    from crazyflie_nmpc_b200 import workloads as wl
+    if name == "helix":
+        return wl.helix_batch(B, N, seed=seed)
+    return wl.hover_batch(B, N, seed=seed)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                r = [c.strip() for c in r]
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, c in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if c.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------ reference / CPU arm
+def cpu_solver():
+    """(callable, kind): the reference's own acados/HPIPM/BLASFEO build when it travelled with the repo
+    (oracle/_ref), else the plain-C port oracle."""
+    from oracle import oracle as orc
+    if orc.ref_available():
+        ref = orc.Ref()
+
+        def run(N, w, nthreads):
+            x, u = w["x_init"].copy(), w["u_init"].copy()
+            st, it, tt = ref.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u, nthreads=nthreads)
+            return x, u, st, float(tt.sum())
+        return run, "reference"
+    port = orc.Port()
+
+    def run(N, w, nthreads):
+        x, u = w["x_init"].copy(), w["u_init"].copy()
+        st, it = port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u)
+        return x, u, st, float("nan")
+    return run, "port"
+
+
+def time_cpu(N, workload, sample, nthreads, seed):
+    run, kind = cpu_solver()
+    if kind == "port":
+        nthreads = 1
+    w = make_workload(workload, sample, N, seed)
+    t0 = time.perf_counter()
+    _, _, st, t_own = run(N, w, nthreads)
+    dt = time.perf_counter() - t0
+    return dict(value=sample / dt, unit=UNIT, cores=nthreads, kind=kind,
+                sample=f"{sample} seeded instances of the same workload, one RTI step each, wall clock over {nthreads} host threads"
+                       + (f"; acados' own time_tot sums to {t_own / sample * 1e3:.3f} ms/solve/core" if t_own == t_own else ""),
+                failures=int((st != 0).sum()))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.ref_sample or 192 * cores
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = time_cpu(args.horizon, args.workload, sample, cores, seed=args.seed + i)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals])) if vals else 0.0
+    cb = dict(vals[-1]) if vals else {}
+    cb["value"] = v
+    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=(sample / v * 1e3) if v else None, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic",
+                config=dict(workload=f"{args.workload} regulation OCPs, N={args.horizon}, nx=13, nu=4, bounded sample of {sample} instances per step",
+                            batch_per_step=sample, horizon=args.horizon, host_threads=cores),
+                cpu_baseline=cb, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import crazyflie_nmpc_b200 as cf
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the solve path has no CPU implementation")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, B = args.horizon, args.batch
+    w = make_workload(args.workload, B, N, args.seed + rank)
+    stream = torch.cuda.current_stream()
+    s = cf.BatchSolver(B, N, TS, device=local)
+    s.set_stream(stream.cuda_stream)
+
+    dev = torch.device("cuda", local)
+    d_in = {k: torch.from_numpy(w[k]).to(dev) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
+    pin = {k: torch.from_numpy(w[k]).pin_memory() for k in ("x0", "yref", "yref_e")}
+    u0_dev = torch.empty(B, 4, dtype=torch.float64, device=dev)
+    u0_all = torch.empty(world * B, 4, dtype=torch.float64, device=dev) if world > 1 else None
+    u0_host = torch.empty(B, 4, dtype=torch.float64).pin_memory()
+    st_host = torch.empty(B, dtype=torch.int32).pin_memory()
+    s.set("x0", d_in["x0"]).set("yref", d_in["yref"]).set("yref_e", d_in["yref_e"])
+
+    def step_device():
+        # inputs resident in HBM: restore the seeded initial iterate (device copy), solve, gather u0
+        s.set("x", d_in["x_init"]).set("u", d_in["u_init"])
+        s.solve(1)
+        if world > 1:
+            s.get("u", 0, out=u0_dev)
+            dist.all_gather_into_tensor(u0_all, u0_dev)
+
+    def step_e2e():
+        # what a caller of the reference API does per tick, with host buffers: x0 + yref in, u0 + status out
+        s.set("x0", pin["x0"]).set("yref", pin["yref"]).set("yref_e", pin["yref_e"])
+        s.set("x", d_in["x_init"]).set("u", d_in["u_init"])
+        s.solve(1)
+        s.get("u", 0, out=u0_dev)
+        u0_host.copy_(u0_dev, non_blocking=True)
+        s.get("status", 0, out=st_host)   # host destination: synchronises the stream
+        if world > 1:
+            dist.all_gather_into_tensor(u0_all, u0_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = s.info("launches")
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, s.info("launches") - l0
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    # kernel-only time of the dominant kernel, CUDA events on its own stream, averaged over the timed steps
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches = timed(step_device, args.steps)
+    kern_ms = []
+    for _ in range(min(args.steps, 5)):
+        s.set("x", d_in["x_init"]).set("u", d_in["u_init"])
+        s.solve(1)
+        kern_ms.append(s.last_solve_ms())
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # sanity: the timed work really solved the batch
+    status = s.get("status")
+    iters = s.get("qp_iter")
+    ok = int((status == 0).sum())
+    if world > 1:
+        t = torch.tensor([ok], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        ok = int(t.item())
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = world * B / (ms_step * 1e-3)
+        e2e_v = world * B / (ms_e2e / args.steps * 1e-3)
+        peaks, how = measured_peaks()
+        k_ms = float(np.mean(kern_ms))
+        achieved = B * alg_bytes(N) / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(f"bytes_per_launch_B{B}_N{N}")
+            except Exception:
+                traffic = None
+        roofline = dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
+                        traffic=traffic, kernel="cf_rti_kernel", kernel_ms=k_ms, peak_source=how,
+                        alg_bytes_per_solve=alg_bytes(N),
+                        note="algorithmic bytes = x0 + yref + iterate in/out (SURVEY 8d); real traffic is dominated by factor/linearisation spill")
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cpu = time_cpu(N, args.workload, args.ref_sample or min(B, 512 * cores), cores, args.seed)
+        h2d = sum(pin[k].numel() * 8 for k in pin)
+        d2h = u0_host.numel() * 8 + st_host.numel() * 4
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload=f"BASELINE configs[{2 if args.workload == 'helix' else 1}]: batch={B} {args.workload} "
+                                         f"OCPs per GPU, N={N}, nx=13, nu=4, random feasible x0, 1 RTI step per step",
+                                batch_per_gpu=B, global_batch=world * B, horizon=N, parallelism=f"dp{world} (independent shards"
+                                + (", NCCL all-gather of u0)" if world > 1 else ")"),
+                                l2="inputs larger than L2 (iterate+yref 900 MB, scratch %d MB per GPU)" % (s.info("scratch_bytes") >> 20),
+                                occupancy=dict(warps_per_sm=s.info("blocks_per_sm") * s.info("warps_per_block"), regs=s.info("regs_per_thread"),
+                                               grid=s.info("grid"))),
+                    clocks=clocks, e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                                            ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
+                    solved=dict(status_ok=ok, of=world * B, ipm_iter_mean=float(iters.mean()), ipm_iter_max=int(iters.max())))
+        print(json.dumps(line))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hover", choices=["hover", "helix"])
+    ap.add_argument("--batch", type=int, default=65536, help="instances per GPU")
+    ap.add_argument("--horizon", type=int, default=50)
+    ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--ref-sample", type=int, default=0, help="instances per CPU step (default: scaled to the core count)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

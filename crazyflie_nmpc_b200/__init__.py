@@ -1,0 +1,180 @@
+"""crazyflie_nmpc_b200 -- batched real-time-iteration NMPC for the Crazyflie OCP on B200.
+
+Host-side Python mirror of the batch C-ABI in include/cfnmpc.h (which itself mirrors the
+reference's per-tick call sequence, crazyflie_controller/src/acados_mpc.cpp:581-625).
+All compute happens in the CUDA library crazyflie_nmpc_b200/libcfnmpc.so; there is no CPU
+path -- if the library or a GPU is missing, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import workloads  # noqa: F401
+
+NX, NU, NY = 13, 4, 17
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_PKG, "libcfnmpc.so")
+_lib = None
+
+# acados status codes, acados/acados/utils/types.h:75-83
+ACADOS_SUCCESS, ACADOS_NAN_DETECTED, ACADOS_MAXITER, ACADOS_MINSTEP, ACADOS_QP_FAILURE = 0, 1, 2, 3, 4
+
+
+class CfnmpcError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library (once). Raises if it has not been built: no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise CfnmpcError(f"{_LIB_PATH} is missing: build it with `python -m crazyflie_nmpc_b200.build` "
+                              "(nvcc, sm_100a). There is no CPU implementation of the solve path.")
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, cp, ci, cd = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_double
+        L.cfnmpc_batch_create.argtypes = [ci, ci, cd, ci, ctypes.POINTER(vp)]
+        L.cfnmpc_batch_destroy.argtypes = [vp]
+        L.cfnmpc_batch_set_stream.argtypes = [vp, vp]
+        L.cfnmpc_batch_set.argtypes = [vp, cp, vp, ci]
+        L.cfnmpc_batch_solve.argtypes = [vp, ci]
+        L.cfnmpc_batch_sync.argtypes = [vp]
+        L.cfnmpc_batch_get.argtypes = [vp, cp, ci, vp, ci]
+        L.cfnmpc_batch_device_ptr.argtypes = [vp, cp, ctypes.POINTER(vp)]
+        L.cfnmpc_batch_info.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_longlong)]
+        L.cfnmpc_batch_last_solve_ms.argtypes = [vp, ctypes.POINTER(cd)]
+        L.cfnmpc_debug_scratch.argtypes = [vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_longlong)]
+        L.cfnmpc_debug_max_ipm_iter.argtypes = [vp, ci]
+        L.cfnmpc_last_error.restype = cp
+        L.cfnmpc_version.restype = cp
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise CfnmpcError(f"cfnmpc error {rc}: {lib().cfnmpc_last_error().decode()}")
+
+
+def _ptr(a):
+    """(address, on_device, keepalive) for a numpy array or a torch tensor."""
+    if hasattr(a, "data_ptr"):  # torch tensor (duck-typed; torch is not a dependency of this module)
+        if not a.is_contiguous():
+            a = a.contiguous()
+        return a.data_ptr(), 1 if a.is_cuda else 0, a
+    a = np.ascontiguousarray(a)
+    return a.ctypes.data, 0, a
+
+
+class BatchSolver:
+    """B independent Crazyflie NMPC instances advanced together, one warp per instance.
+
+    set(field, array)   "x0" [B,13] | "yref" [B,N,17] | "yref_e" [B,13] | "x" [B,N+1,13] | "u" [B,N,4]
+                        | "W" [17] | "W_e" [13] | "lbu" | "ubu" [4]
+    solve(n_rti=1)      enqueue RTI steps (asynchronous)
+    get(field, stage)   "u"/"x" at a stage, "u_all", "x_all", "status", "qp_iter", "qp_status", "flags", "res"
+    """
+    _SHAPES = {"status": np.int32, "qp_iter": np.int32, "qp_status": np.int32, "flags": np.int32}
+
+    def __init__(self, batch, N=50, Ts=0.015, device=0):
+        self._h = ctypes.c_void_p()
+        self.B, self.N, self.Ts, self.device = int(batch), int(N), float(Ts), int(device)
+        _check(lib().cfnmpc_batch_create(self.B, self.N, self.Ts, self.device, ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().cfnmpc_batch_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_handle):
+        """Run on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None = own stream."""
+        _check(lib().cfnmpc_batch_set_stream(self._h, ctypes.c_void_p(cuda_stream_handle or 0)))
+
+    def _expected(self, field):
+        B, N = self.B, self.N
+        return {"x0": (B, NX), "yref": (B, N, NY), "yref_e": (B, NX), "x": (B, N + 1, NX), "u": (B, N, NU),
+                "W": (NY,), "W_e": (NX,), "lbu": (NU,), "ubu": (NU,)}[field]
+
+    def set(self, field, a):
+        if field not in ("x0", "yref", "yref_e", "x", "u", "W", "W_e", "lbu", "ubu"):
+            raise CfnmpcError(f"unknown field '{field}'")
+        n = int(np.prod(self._expected(field)))
+        if hasattr(a, "data_ptr"):
+            if a.numel() != n or a.element_size() != 8:
+                raise CfnmpcError(f"'{field}' needs {n} float64 values")
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.size != n:
+                raise CfnmpcError(f"'{field}' needs {n} float64 values, got {a.size}")
+        p, dev, keep = _ptr(a)
+        _check(lib().cfnmpc_batch_set(self._h, field.encode(), ctypes.c_void_p(p), dev))
+        if not dev and not (hasattr(a, "is_pinned") and a.is_pinned()):
+            self.sync()  # pageable host memory: make the copy complete before the caller may reuse it
+        return self
+
+    def set_problem(self, w):
+        """Load a workload dict as produced by crazyflie_nmpc_b200.workloads."""
+        self.set("x0", w["x0"]).set("yref", w["yref"]).set("yref_e", w["yref_e"])
+        self.set("x", w["x_init"]).set("u", w["u_init"])
+        return self
+
+    def solve(self, n_rti=1):
+        _check(lib().cfnmpc_batch_solve(self._h, int(n_rti)))
+        return self
+
+    def sync(self):
+        _check(lib().cfnmpc_batch_sync(self._h))
+
+    def get(self, field, stage=0, out=None):
+        B, N = self.B, self.N
+        shapes = {"u": ((B, NU), np.float64), "x": ((B, NX), np.float64), "u_all": ((B, N, NU), np.float64),
+                  "x_all": ((B, N + 1, NX), np.float64), "status": ((B,), np.int32), "qp_iter": ((B,), np.int32),
+                  "qp_status": ((B,), np.int32), "flags": ((B,), np.int32), "res": ((B, 4), np.float64)}
+        if field not in shapes:
+            raise CfnmpcError(f"unknown field '{field}'")
+        shape, dt = shapes[field]
+        if out is None:
+            out = np.empty(shape, dt)
+        p, dev, keep = _ptr(out)
+        _check(lib().cfnmpc_batch_get(self._h, field.encode(), int(stage), ctypes.c_void_p(p), dev))
+        return out
+
+    def device_ptr(self, field):
+        p = ctypes.c_void_p()
+        _check(lib().cfnmpc_batch_device_ptr(self._h, field.encode(), ctypes.byref(p)))
+        return p.value
+
+    def info(self, what):
+        v = ctypes.c_longlong()
+        _check(lib().cfnmpc_batch_info(self._h, what.encode(), ctypes.byref(v)))
+        return v.value
+
+    def last_solve_ms(self):
+        v = ctypes.c_double()
+        _check(lib().cfnmpc_batch_last_solve_ms(self._h, ctypes.byref(v)))
+        return v.value
+
+    # ---- test hooks
+    def debug_scratch(self):
+        n, offs = ctypes.c_size_t(), (ctypes.c_longlong * 12)()
+        _check(lib().cfnmpc_debug_scratch(self._h, None, 0, ctypes.byref(n), offs))
+        buf = np.empty(n.value)
+        _check(lib().cfnmpc_debug_scratch(self._h, ctypes.c_void_p(buf.ctypes.data), n.value, None, None))
+        names = ["M", "L", "b", "rq", "ux", "pi", "res_g", "dux", "dpi", "Pb", "bnd", "total"]
+        return buf, dict(zip(names, list(offs)))
+
+    def debug_max_ipm_iter(self, n):
+        _check(lib().cfnmpc_debug_max_ipm_iter(self._h, int(n)))

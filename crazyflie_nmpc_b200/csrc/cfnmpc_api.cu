@@ -1,0 +1,367 @@
+// Host side of the batch C-ABI (include/cfnmpc.h) and the sm_100a kernels behind it.
+// C++ above a C boundary, as the reference's solver glue is C
+// (acados_template/c_templates_tera/acados_solver.in.c).  No torch types, no CPU path:
+// every compute call ends in a kernel launch or returns CFNMPC_ECUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/cfnmpc.h"
+#include "cf_rti_warp.h"
+
+#define CF_WARPS_PER_BLOCK 4
+
+// ------------------------------------------------------------------ kernels
+// Persistent warps: each warp owns a scratch slot and pulls instance ids from a global
+// counter until the batch is exhausted (IPM trip counts differ per instance: 4..11).
+// MINB = resident blocks per SM the register allocation is bounded for (2: 255 regs, 3: 168, 4: 128).
+template <int MINB>
+__global__ void __launch_bounds__(CF_WARPS_PER_BLOCK * 32, MINB)
+cf_rti_kernel(const __grid_constant__ CfParams P, const __grid_constant__ CfBatchView bv)
+{
+    extern __shared__ double cf_smem[];
+    const int warp = threadIdx.x >> 5;
+    double *sm = cf_smem + warp * CF_SM_DOUBLES;
+    double *slot = bv.scratch + (long) (blockIdx.x * CF_WARPS_PER_BLOCK + warp) * bv.scratch_stride;
+    for (;;) {
+        int inst = 0;
+        if ((threadIdx.x & 31) == 0) inst = atomicAdd(bv.counter, 1);
+        inst = __shfl_sync(0xffffffffu, inst, 0);
+        if (inst >= bv.B) break;
+        cf_rti_instance(&P, bv, inst, slot, sm);
+    }
+}
+
+// out[i][0:w] = src[i][stage*w : stage*w + w]   (ocp_nlp_out_get for every instance at once)
+__global__ void cf_gather_stage_kernel(const double *__restrict__ src, double *__restrict__ out, int B, int per_inst, int stage, int w)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < B * w) {
+        const int i = t / w, j = t - i * w;
+        out[t] = src[(long) i * per_inst + stage * w + j];
+    }
+}
+
+// iterate initialisation of the generated solver (acados_solver.in.c:2323-2352)
+__global__ void cf_init_iterate_kernel(double *x, double *u, long nx_tot, long nu_tot)
+{
+    const long t = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nx_tot) x[t] = ((t % CF_NX) == 3) ? 1.0 : 0.0;
+    if (t < nu_tot) u[t] = 0.0;
+}
+
+// ------------------------------------------------------------------ host state
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(CFNMPC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+struct cfnmpc_batch
+{
+    int B = 0, N = 0, device = 0;
+    CfParams P;
+    CfBatchView bv;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *d_x0 = nullptr, *d_yref = nullptr, *d_yref_e = nullptr, *d_x = nullptr, *d_u = nullptr, *d_res = nullptr;
+    double *d_scratch = nullptr, *d_stage = nullptr;
+    int *d_status = nullptr, *d_qp_iter = nullptr, *d_qp_status = nullptr, *d_flags = nullptr, *d_counter = nullptr;
+    int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 4;
+    void (*kernel)(const CfParams, const CfBatchView) = nullptr;
+    size_t smem = 0;
+    long long launches = 0;
+    bool timed = false;
+};
+
+static void default_params(CfParams &P, int N, double Ts)
+{
+    // generate_c_code.py:61-84 (Q, R), :113 (W_e = 50 Q), :133-134 (0 <= u <= 22)
+    static const double Q[CF_NX] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
+    for (int i = 0; i < CF_NX; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
+    for (int i = 0; i < CF_NU; i++) { P.Wdiag[CF_NX + i] = 0.06; P.lbu[i] = 0.0; P.ubu[i] = 22.0; }
+    P.Ts = Ts; P.N = N; P.max_ipm_iter = CF_ITER_MAX;
+}
+
+extern "C" const char *cfnmpc_last_error(void) { return g_err.c_str(); }
+extern "C" const char *cfnmpc_version(void) { return "crazyflie_nmpc_b200 0.1 (sm_100a)"; }
+
+extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
+{
+    if (!h) return CFNMPC_OK;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
+                    h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnmpc_batch **out)
+{
+    if (!out) return fail(CFNMPC_EINVAL, "cfnmpc_batch_create: out is NULL");
+    *out = nullptr;
+    if (batch < 1 || N < 1 || N > 4096 || !(Ts > 0)) return fail(CFNMPC_EINVAL, "cfnmpc_batch_create: need batch >= 1, 1 <= N <= 4096, Ts > 0");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(CFNMPC_EINVAL, "cfnmpc_batch_create: no such CUDA device");
+    CK(cudaSetDevice(device));
+    cfnmpc_batch *h = new cfnmpc_batch();
+    h->B = batch; h->N = N; h->device = device;
+    default_params(h->P, N, Ts);
+#define CKH(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            cfnmpc_batch_destroy(h);                                                                \
+            return fail(CFNMPC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+        }                                                                                           \
+    } while (0)
+    CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CKH(cudaEventCreate(&h->ev0));
+    CKH(cudaEventCreate(&h->ev1));
+    cudaDeviceProp prop;
+    CKH(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem = (size_t) CF_WARPS_PER_BLOCK * CF_SM_DOUBLES * sizeof(double);
+    // occupancy variant: CFNMPC_MIN_BLOCKS = 2 | 3 | 4 (default 4 -> 16 warps per SM)
+    if (const char *e = getenv("CFNMPC_MIN_BLOCKS")) h->minb = atoi(e);
+    if (h->minb == 2) h->kernel = cf_rti_kernel<2>;
+    else if (h->minb == 3) h->kernel = cf_rti_kernel<3>;
+    else { h->minb = 4; h->kernel = cf_rti_kernel<4>; }
+    CKH(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem));
+    cudaFuncAttributes fa;
+    CKH(cudaFuncGetAttributes(&fa, h->kernel));
+    h->regs = fa.numRegs;
+    CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, h->kernel, CF_WARPS_PER_BLOCK * 32, h->smem));
+    if (h->blocks_per_sm < 1) { cfnmpc_batch_destroy(h); return fail(CFNMPC_ECUDA, "kernel does not fit on an SM"); }
+    // persistent grid: every SM fully occupied, but never more warps than instances
+    long want = (long) h->sm_count * h->blocks_per_sm;
+    long need = ((long) batch + CF_WARPS_PER_BLOCK - 1) / CF_WARPS_PER_BLOCK;
+    h->grid = (int) (want < need ? want : need);
+    h->n_slots = h->grid * CF_WARPS_PER_BLOCK;
+    const long stride = cf_scratch_layout(N).total;
+    const size_t B = batch;
+    CKH(cudaMalloc(&h->d_x0, B * CF_NX * 8));
+    CKH(cudaMalloc(&h->d_yref, B * N * CF_NY * 8));
+    CKH(cudaMalloc(&h->d_yref_e, B * CF_NX * 8));
+    CKH(cudaMalloc(&h->d_x, B * (N + 1) * CF_NX * 8));
+    CKH(cudaMalloc(&h->d_u, B * N * CF_NU * 8));
+    CKH(cudaMalloc(&h->d_res, B * 4 * 8));
+    CKH(cudaMalloc(&h->d_stage, B * CF_NX * 8));
+    CKH(cudaMalloc(&h->d_status, B * 4));
+    CKH(cudaMalloc(&h->d_qp_iter, B * 4));
+    CKH(cudaMalloc(&h->d_qp_status, B * 4));
+    CKH(cudaMalloc(&h->d_flags, B * 4));
+    CKH(cudaMalloc(&h->d_counter, 4));
+    CKH(cudaMalloc(&h->d_scratch, (size_t) h->n_slots * stride * 8));
+    CKH(cudaMemsetAsync(h->d_scratch, 0, (size_t) h->n_slots * stride * 8, h->stream));
+    CKH(cudaMemsetAsync(h->d_x0, 0, B * CF_NX * 8, h->stream));
+    CKH(cudaMemsetAsync(h->d_yref, 0, B * N * CF_NY * 8, h->stream));
+    CKH(cudaMemsetAsync(h->d_yref_e, 0, B * CF_NX * 8, h->stream));
+    CKH(cudaMemsetAsync(h->d_status, 0, B * 4, h->stream));
+    CKH(cudaMemsetAsync(h->d_qp_iter, 0, B * 4, h->stream));
+    CKH(cudaMemsetAsync(h->d_qp_status, 0, B * 4, h->stream));
+    CKH(cudaMemsetAsync(h->d_flags, 0, B * 4, h->stream));
+    CKH(cudaMemsetAsync(h->d_res, 0, B * 4 * 8, h->stream));
+    {
+        const long nx_tot = (long) B * (N + 1) * CF_NX, nu_tot = (long) B * N * CF_NU;
+        const long n = nx_tot > nu_tot ? nx_tot : nu_tot;
+        cf_init_iterate_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, h->stream>>>(h->d_x, h->d_u, nx_tot, nu_tot);
+        CKH(cudaGetLastError());
+        h->launches++;
+    }
+    CfBatchView &bv = h->bv;
+    bv.B = batch; bv.x0 = h->d_x0; bv.yref = h->d_yref; bv.yref_e = h->d_yref_e; bv.x = h->d_x; bv.u = h->d_u;
+    bv.status = h->d_status; bv.qp_iter = h->d_qp_iter; bv.qp_status = h->d_qp_status; bv.flags = h->d_flags;
+    bv.res = h->d_res; bv.scratch = h->d_scratch; bv.scratch_stride = stride; bv.counter = h->d_counter;
+    CKH(cudaStreamSynchronize(h->stream));
+#undef CKH
+    *out = h;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_set_stream(cfnmpc_batch *h, void *cuda_stream)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t) cuda_stream : h->own_stream;
+    return CFNMPC_OK;
+}
+
+struct FieldRef
+{
+    void *dev;
+    size_t bytes;
+};
+static bool batch_field(cfnmpc_batch *h, const char *f, FieldRef &r)
+{
+    const size_t B = h->B, N = h->N;
+    if (!strcmp(f, "x0")) r = {h->d_x0, B * CF_NX * 8};
+    else if (!strcmp(f, "yref")) r = {h->d_yref, B * N * CF_NY * 8};
+    else if (!strcmp(f, "yref_e")) r = {h->d_yref_e, B * CF_NX * 8};
+    else if (!strcmp(f, "x") || !strcmp(f, "x_all")) r = {h->d_x, B * (N + 1) * CF_NX * 8};
+    else if (!strcmp(f, "u") || !strcmp(f, "u_all")) r = {h->d_u, B * N * CF_NU * 8};
+    else if (!strcmp(f, "status")) r = {h->d_status, B * 4};
+    else if (!strcmp(f, "qp_iter")) r = {h->d_qp_iter, B * 4};
+    else if (!strcmp(f, "qp_status")) r = {h->d_qp_status, B * 4};
+    else if (!strcmp(f, "flags")) r = {h->d_flags, B * 4};
+    else if (!strcmp(f, "res")) r = {h->d_res, B * 4 * 8};
+    else return false;
+    return true;
+}
+
+extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *src, int src_on_device)
+{
+    if (!h || !field || !src) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set: null argument");
+    CK(cudaSetDevice(h->device));
+    // solver-wide parameters travel as kernel arguments
+    double *pdst = nullptr;
+    int pn = 0;
+    if (!strcmp(field, "W")) { pdst = h->P.Wdiag; pn = CF_NY; }
+    else if (!strcmp(field, "W_e")) { pdst = h->P.WNdiag; pn = CF_NX; }
+    else if (!strcmp(field, "lbu")) { pdst = h->P.lbu; pn = CF_NU; }
+    else if (!strcmp(field, "ubu")) { pdst = h->P.ubu; pn = CF_NU; }
+    if (pdst) {
+        if (src_on_device) CK(cudaMemcpy(pdst, src, pn * 8, cudaMemcpyDeviceToHost));
+        else memcpy(pdst, src, pn * 8);
+        return CFNMPC_OK;
+    }
+    FieldRef r;
+    if (!strcmp(field, "x0") || !strcmp(field, "yref") || !strcmp(field, "yref_e") || !strcmp(field, "x") || !strcmp(field, "u")) {
+        batch_field(h, field, r);
+        CK(cudaMemcpyAsync(r.dev, src, r.bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        return CFNMPC_OK;
+    }
+    return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_set: unknown field '") + field + "'");
+}
+
+extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    if (n_rti < 1) return fail(CFNMPC_EINVAL, "cfnmpc_batch_solve: n_rti must be >= 1");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int r = 0; r < n_rti; r++) {
+        CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+        h->kernel<<<h->grid, CF_WARPS_PER_BLOCK * 32, h->smem, h->stream>>>(h->P, h->bv);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_sync(cfnmpc_batch *h)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_get(cfnmpc_batch *h, const char *field, int stage, void *dst, int dst_on_device)
+{
+    if (!h || !field || !dst) return fail(CFNMPC_EINVAL, "cfnmpc_batch_get: null argument");
+    CK(cudaSetDevice(h->device));
+    const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const bool is_u = !strcmp(field, "u"), is_x = !strcmp(field, "x");
+    if (is_u || is_x) {
+        const int w = is_u ? CF_NU : CF_NX, nst = is_u ? h->N : h->N + 1;
+        if (stage < 0 || stage >= nst) return fail(CFNMPC_EINVAL, "cfnmpc_batch_get: stage out of range");
+        const int n = h->B * w;
+        cf_gather_stage_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(is_u ? h->d_u : h->d_x, h->d_stage, h->B, nst * w, stage, w);
+        CK(cudaGetLastError());
+        h->launches++;
+        CK(cudaMemcpyAsync(dst, h->d_stage, (size_t) n * 8, kind, h->stream));
+    } else {
+        FieldRef r;
+        if (!batch_field(h, field, r) || !strcmp(field, "x0") || !strcmp(field, "yref") || !strcmp(field, "yref_e"))
+            return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_get: unknown field '") + field + "'");
+        CK(cudaMemcpyAsync(dst, r.dev, r.bytes, kind, h->stream));
+    }
+    if (!dst_on_device) CK(cudaStreamSynchronize(h->stream));
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_device_ptr(cfnmpc_batch *h, const char *field, void **ptr)
+{
+    if (!h || !field || !ptr) return fail(CFNMPC_EINVAL, "cfnmpc_batch_device_ptr: null argument");
+    FieldRef r;
+    if (!batch_field(h, field, r)) return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_device_ptr: unknown field '") + field + "'");
+    *ptr = r.dev;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_info(cfnmpc_batch *h, const char *what, long long *value)
+{
+    if (!h || !what || !value) return fail(CFNMPC_EINVAL, "cfnmpc_batch_info: null argument");
+    if (!strcmp(what, "batch")) *value = h->B;
+    else if (!strcmp(what, "N")) *value = h->N;
+    else if (!strcmp(what, "n_slots")) *value = h->n_slots;
+    else if (!strcmp(what, "sm_count")) *value = h->sm_count;
+    else if (!strcmp(what, "warps_per_block")) *value = CF_WARPS_PER_BLOCK;
+    else if (!strcmp(what, "blocks_per_sm")) *value = h->blocks_per_sm;
+    else if (!strcmp(what, "grid")) *value = h->grid;
+    else if (!strcmp(what, "regs_per_thread")) *value = h->regs;
+    else if (!strcmp(what, "smem_per_block")) *value = (long long) h->smem;
+    else if (!strcmp(what, "scratch_bytes")) *value = (long long) h->n_slots * h->bv.scratch_stride * 8;
+    else if (!strcmp(what, "launches")) *value = h->launches;
+    else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_info: unknown property '") + what + "'");
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_last_solve_ms(cfnmpc_batch *h, double *ms)
+{
+    if (!h || !ms) return fail(CFNMPC_EINVAL, "null argument");
+    if (!h->timed) return fail(CFNMPC_ESTATE, "cfnmpc_batch_last_solve_ms: no solve has been enqueued");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    *ms = f;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_doubles, size_t *n_doubles, long long *offsets12)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    CfScratchLayout s = cf_scratch_layout(h->N);
+    if (offsets12) {
+        long long v[12] = {s.M, s.L, s.b, s.rq, s.ux, s.pi, s.res_g, s.dux, s.dpi, s.Pb, s.bnd, s.total};
+        memcpy(offsets12, v, sizeof v);
+    }
+    if (n_doubles) *n_doubles = (size_t) s.total;
+    if (dst) {
+        if (h->B != 1) return fail(CFNMPC_ESTATE, "cfnmpc_debug_scratch: only meaningful for batch == 1");
+        if (max_doubles < (size_t) s.total) return fail(CFNMPC_EINVAL, "cfnmpc_debug_scratch: buffer too small");
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(dst, h->d_scratch, (size_t) s.total * 8, cudaMemcpyDeviceToHost));
+    }
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_debug_max_ipm_iter(cfnmpc_batch *h, int max_iter)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    h->P.max_ipm_iter = (max_iter > 0 && max_iter < CF_ITER_MAX) ? max_iter : CF_ITER_MAX;
+    return CFNMPC_OK;
+}

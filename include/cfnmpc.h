@@ -1,0 +1,120 @@
+/* cfnmpc.h -- batch C-ABI of the B200-native Crazyflie NMPC solver.
+ *
+ * One handle owns B independent instances of the OCP that
+ * `crazyflie_controller` solves (N shooting intervals, nx = 13, nu = 4) and
+ * advances all of them by one real-time-iteration SQP step per
+ * cfnmpc_batch_solve() on one GPU, one warp per instance.
+ *
+ * Reference interface this replaces.  The reference has no batch notion; per
+ * instance and per control tick its ROS node does
+ *   ocp_nlp_constraints_model_set(.., 0, "lbx"/"ubx", x0)   crazyflie_controller/src/acados_mpc.cpp:581-582
+ *   ocp_nlp_cost_model_set(.., k, "yref", ..) k = 0..N      :590-594
+ *   acados_solve()                                           :611
+ *   ocp_nlp_out_get(.., 0, "u"), (1,"u"), (4,"x")            :619-625
+ * against acados/interfaces/acados_c/ocp_nlp_interface.h:221-234,274-275,352.
+ * The calls below are the same operations with a leading batch dimension:
+ * cfnmpc_batch_set("x0"|"yref"|...) <-> the two *_model_set calls,
+ * cfnmpc_batch_solve <-> acados_solve / ocp_nlp_solve,
+ * cfnmpc_batch_get("u"|"x", stage) <-> ocp_nlp_out_get.
+ * The single-instance surfaces (acados_solver_crazyflie.h, acados_c/...) are thin
+ * B = 1 wrappers over this file.
+ *
+ * Conventions (same as the reference): plain pointers and sizes,
+ * fp64, vectors contiguous, the library copies in setters and copies out in
+ * getters and owns all solver memory.  No call aborts the process: errors are
+ * negative return values and cfnmpc_last_error() has the text.  Not re-entrant
+ * per handle; different handles may be used from different threads.
+ */
+#ifndef CFNMPC_H
+#define CFNMPC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFNMPC_NX 13
+#define CFNMPC_NU 4
+#define CFNMPC_NY 17
+
+/* return codes */
+#define CFNMPC_OK 0
+#define CFNMPC_EINVAL (-1)  /* bad argument / unknown field */
+#define CFNMPC_ECUDA (-2)   /* CUDA runtime error (no device, launch failure, out of memory) */
+#define CFNMPC_ESTATE (-3)  /* call sequence error */
+
+/* per-instance status values written by a solve: acados/acados/utils/types.h:75-83 */
+#define CFNMPC_SUCCESS 0
+#define CFNMPC_NAN_DETECTED 1
+#define CFNMPC_MAXITER 2
+#define CFNMPC_MINSTEP 3
+#define CFNMPC_QP_FAILURE 4
+
+typedef struct cfnmpc_batch cfnmpc_batch;
+
+/* Create a solver for `batch` instances with horizon N and grid step Ts [s]
+ * on CUDA device `device`.  Weights and bounds start at the values of
+ * crazyflie_controller/scripts/crazyflie_full_model/generate_c_code.py:61-136; the
+ * iterate starts as the generated solver's does (x_k = [0,0,0,1,0..], u_k = 0,
+ * acados_solver.in.c:2323-2352). */
+int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnmpc_batch **out);
+int cfnmpc_batch_destroy(cfnmpc_batch *h);
+
+/* Run all work of this handle on an existing CUDA stream (a cudaStream_t passed as
+ * void*); NULL returns to the handle's own stream. */
+int cfnmpc_batch_set_stream(cfnmpc_batch *h, void *cuda_stream);
+
+/* Copy caller data into the solver.  `src_on_device` != 0 means `src` is a device
+ * pointer on the handle's GPU.  Fields and shapes (row-major, instance-major):
+ *   "x0"      double [B][13]        measured state -> lbx_0 = ubx_0
+ *   "yref"    double [B][N][17]     stage references, y = [x(13); u(4)]
+ *   "yref_e"  double [B][13]        terminal reference
+ *   "x"       double [B][N+1][13]   iterate (states)
+ *   "u"       double [B][N][4]      iterate (inputs)
+ *   "W"       double [17]           diagonal of the stage weight matrix (all instances)
+ *   "W_e"     double [13]           diagonal of the terminal weight matrix
+ *   "lbu","ubu" double [4]          input bounds, stages 0..N-1
+ * Copies are asynchronous on the handle's stream. */
+int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *src, int src_on_device);
+
+/* Enqueue n_rti consecutive RTI steps (preparation + feedback) for every instance,
+ * inputs frozen between steps.  Asynchronous; pair with cfnmpc_batch_sync or a
+ * getter to a host pointer. */
+int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti);
+int cfnmpc_batch_sync(cfnmpc_batch *h);
+
+/* Copy results out.  Fields:
+ *   "u"        stage k in [0,N)   double [B][4]
+ *   "x"        stage k in [0,N]   double [B][13]
+ *   "u_all"    double [B][N][4]      "x_all"  double [B][N+1][13]      (stage ignored)
+ *   "status"   int [B]   acados status of the last step (0 ok, 4 QP failure)
+ *   "qp_iter"  int [B]   interior-point iterations of the last step
+ *   "qp_status" int [B]  HPIPM status 0 ok / 1 max-iter / 2 min-step / 3 NaN
+ *   "flags"    int [B]   bit 0/1: the reference's LQ / iterative-refinement safety nets would have fired
+ *   "res"      double [B][4]  final QP residual inf-norms (stationarity, dynamics, bounds, complementarity)
+ * Copies to host pointers synchronise the stream before returning. */
+int cfnmpc_batch_get(cfnmpc_batch *h, const char *field, int stage, void *dst, int dst_on_device);
+
+/* Device pointer of a batch array ("x0","yref","yref_e","x","u","status","qp_iter"), for
+ * callers that produce inputs / consume outputs on the GPU without staging copies. */
+int cfnmpc_batch_device_ptr(cfnmpc_batch *h, const char *field, void **ptr);
+
+/* Integer properties: "batch","N","n_slots","sm_count","warps_per_block","blocks_per_sm",
+ * "regs_per_thread","smem_per_block","launches" (kernels launched so far). */
+int cfnmpc_batch_info(cfnmpc_batch *h, const char *what, long long *value);
+/* Device time of the last cfnmpc_batch_solve in ms (CUDA events on the stream); syncs. */
+int cfnmpc_batch_last_solve_ms(cfnmpc_batch *h, double *ms);
+
+/* Test hook: copy the scratch slot that solved instance 0 when batch == 1 (QP data,
+ * factors, IPM vectors) and limit the IPM iteration count; see tests/test_gpu_parity.py. */
+int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_doubles, size_t *n_doubles, long long *offsets12);
+int cfnmpc_debug_max_ipm_iter(cfnmpc_batch *h, int max_iter);
+
+const char *cfnmpc_last_error(void);
+const char *cfnmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFNMPC_H */

@@ -1,0 +1,23 @@
+"""Build tests/simt_emu/libcfemu.so: the CUDA warp program compiled for the host with its 32
+lanes run as lock-step fibers (TEST HARNESS ONLY, see emu.cpp)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "crazyflie_nmpc_b200", "csrc")
+LIB = os.path.join(HERE, "libcfemu.so")
+
+
+def build(force=False):
+    deps = [os.path.join(HERE, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("cf_simt.h", "cf_model.h", "cf_rti_warp.h")]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, os.path.join(HERE, "emu.cpp"),
+                    "-o", LIB, "-lpthread"], check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

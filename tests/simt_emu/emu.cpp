@@ -1,0 +1,175 @@
+// TEST HARNESS ONLY: runs the CUDA warp program (crazyflie_nmpc_b200/csrc/cf_rti_warp.h)
+// on the host by executing the 32 lanes of a warp as lock-step fibers.  Every warp
+// primitive (shuffle, __syncwarp) is a rendez-vous of all 32 fibers, so data races and
+// divergent-barrier bugs in the kernel source show up here without a GPU.  This file is
+// compiled only by tests/ (see tests/simt_emu/build.py); the product library never
+// contains it and has no CPU path.
+#define CF_SIMT_EMU 1
+#include <ucontext.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "cf_rti_warp.h"
+
+namespace cfemu {
+struct Warp
+{
+    ucontext_t ctx[32], main_ctx;
+    char *stacks[32];
+    int cur = 0;
+    int done[32];
+    int line0 = 0;
+    double xch[32];
+    void (*fn)(void *) = nullptr;
+    void *arg = nullptr;
+};
+static thread_local Warp *W = nullptr;
+static const size_t STACK = 512 * 1024;
+
+int lane() { return W->cur; }
+
+static void switch_next()
+{
+    Warp *w = W;
+    int from = w->cur;
+    for (int step = 1; step <= 32; step++) {
+        int to = (from + step) & 31;
+        if (!w->done[to]) {
+            if (to == from) return;
+            w->cur = to;
+            swapcontext(&w->ctx[from], &w->ctx[to]);
+            return;
+        }
+    }
+}
+
+void barrier(int line)
+{
+    Warp *w = W;
+    if (w->cur == 0) w->line0 = line;
+    else if (line != w->line0) {
+        fprintf(stderr, "cfemu: divergent warp barrier: lane %d at line %d, lane 0 at line %d\n", w->cur, line, w->line0);
+        abort();
+    }
+    switch_next();
+}
+
+double exch(double v, int src, int line)
+{
+    Warp *w = W;
+    w->xch[w->cur] = v;
+    barrier(line);
+    double r = w->xch[src & 31];
+    barrier(-line);
+    return r;
+}
+
+int atomic_add(int *p, int v)
+{
+    int old = *p;
+    *p += v;
+    return old;
+}
+
+static void trampoline()
+{
+    Warp *w = W;
+    w->fn(w->arg);
+    w->done[w->cur] = 1;
+    int from = w->cur;
+    for (int step = 1; step < 32; step++) {
+        int to = (from + step) & 31;
+        if (!w->done[to]) { w->cur = to; setcontext(&w->ctx[to]); }
+    }
+    setcontext(&w->main_ctx);
+}
+
+static void run_warp(void (*fn)(void *), void *arg)
+{
+    Warp *w = new Warp();
+    W = w;
+    w->fn = fn;
+    w->arg = arg;
+    for (int i = 0; i < 32; i++) {
+        w->done[i] = 0;
+        w->stacks[i] = (char *) malloc(STACK);
+        getcontext(&w->ctx[i]);
+        w->ctx[i].uc_stack.ss_sp = w->stacks[i];
+        w->ctx[i].uc_stack.ss_size = STACK;
+        w->ctx[i].uc_link = nullptr;
+        makecontext(&w->ctx[i], trampoline, 0);
+    }
+    w->cur = 0;
+    swapcontext(&w->main_ctx, &w->ctx[0]);
+    for (int i = 0; i < 32; i++) free(w->stacks[i]);
+    delete w;
+    W = nullptr;
+}
+}  // namespace cfemu
+
+struct Job
+{
+    const CfParams *P;
+    CfBatchView bv;
+    int inst;
+    double *slot;
+    double *sm;
+};
+static void job_fn(void *a)
+{
+    Job *j = (Job *) a;
+    cf_rti_instance(j->P, j->bv, j->inst, j->slot, j->sm);
+}
+
+extern "C" long cfemu_scratch_doubles(int N) { return cf_scratch_layout(N).total; }
+extern "C" void cfemu_scratch_offsets(int N, long *out)
+{
+    CfScratchLayout s = cf_scratch_layout(N);
+    long v[12] = {s.M, s.L, s.b, s.rq, s.ux, s.pi, s.res_g, s.dux, s.dpi, s.Pb, s.bnd, s.total};
+    memcpy(out, v, sizeof v);
+}
+
+// params: Wdiag[17], WNdiag[13], lbu[4], ubu[4] (38 doubles) or NULL for the reference values
+extern "C" int cfemu_rti_batch(int B, int N, double Ts, const double *params, int max_ipm_iter, const double *x0,
+                               const double *yref, const double *yref_e, double *x, double *u, int *status,
+                               int *qp_iter, int *qp_status, int *flags, double *res, double *scratch_out,
+                               int nthreads)
+{
+    CfParams P;
+    static const double Q[13] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
+    for (int i = 0; i < 13; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
+    for (int i = 0; i < 4; i++) { P.Wdiag[13 + i] = 0.06; P.lbu[i] = 0; P.ubu[i] = 22; }
+    if (params) {
+        memcpy(P.Wdiag, params, 17 * 8); memcpy(P.WNdiag, params + 17, 13 * 8);
+        memcpy(P.lbu, params + 30, 4 * 8); memcpy(P.ubu, params + 34, 4 * 8);
+    }
+    P.Ts = Ts; P.N = N; P.max_ipm_iter = max_ipm_iter > 0 ? max_ipm_iter : CF_ITER_MAX;
+    const long stride = cf_scratch_layout(N).total;
+    CfBatchView bv;
+    bv.B = B; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
+    bv.qp_iter = qp_iter; bv.qp_status = qp_status; bv.flags = flags; bv.res = res; bv.scratch = nullptr;
+    bv.scratch_stride = stride; bv.counter = nullptr;
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&]() {
+            std::vector<double> slot(stride, 0.0), sm(CF_SM_DOUBLES, 0.0);
+            for (;;) {
+                int i = next.fetch_add(1);
+                if (i >= B) break;
+                // poison the scratch so that reads of never-written data are visible
+                for (auto &v : slot) v = std::nan("");
+                Job j{&P, bv, i, slot.data(), sm.data()};
+                cfemu::run_warp(job_fn, &j);
+                if (scratch_out) memcpy(scratch_out + (size_t) i * stride, slot.data(), stride * 8);
+            }
+        });
+    for (auto &t : th) t.join();
+    return 0;
+}
