@@ -171,7 +171,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, B = args.horizon, args.batch
     w = make_workload(args.workload, B, N, args.seed + rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated torch stream carries every copy, kernel and event of the benchmark
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     s = cf.BatchSolver(B, N, TS, device=local)
     s.set_stream(stream.cuda_stream)
 

@@ -354,7 +354,16 @@ extern "C" int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_dou
         if (max_doubles < (size_t) s.total) return fail(CFNMPC_EINVAL, "cfnmpc_debug_scratch: buffer too small");
         CK(cudaSetDevice(h->device));
         CK(cudaStreamSynchronize(h->stream));
-        CK(cudaMemcpy(dst, h->d_scratch, (size_t) s.total * 8, cudaMemcpyDeviceToHost));
+        // any warp of the (single) block may have pulled instance 0: find the slot that was written
+        int slot = 0;
+        for (int w = 0; w < h->n_slots; w++) {
+            double probe[CF_MSZ];
+            CK(cudaMemcpy(probe, h->d_scratch + (size_t) w * s.total + s.M, sizeof probe, cudaMemcpyDeviceToHost));
+            bool used = false;
+            for (int i = 0; i < CF_MSZ; i++) used |= probe[i] != 0.0;
+            if (used) { slot = w; break; }
+        }
+        CK(cudaMemcpy(dst, h->d_scratch + (size_t) slot * s.total, (size_t) s.total * 8, cudaMemcpyDeviceToHost));
     }
     return CFNMPC_OK;
 }
