@@ -13,18 +13,20 @@
 //                  x_ocp_qp_res.c:334-637, ipm_core/x_core_qp_ipm_aux.c:36-457)
 //
 // Mapping.  Stage variables are [u(4); x(13)] -> lanes 0..16; lane 17 carries the extra
-// "gradient / b" row of the (nv+1) x nv square-root Riccati blocks.  Lane r owns ROW r of
-// the stage matrices it works on ([B';A';b'] is 18 x 13, the factor L is 18 x 17), so the
-// dense per-stage kernels (TRMM, SYRK, Cholesky) are rank-1 register updates with the
-// broadcast operand read from shared memory, and triangular/GEMV sweeps use either the row
-// layout or a column-per-lane layout loaded from the same packed global block.  Lanes 18..31
-// help only in the element-wise passes.
+// "gradient / b" row of the (nv+1) x nv square-root Riccati blocks.  Lane r owns ROW r of the
+// stage matrices ([B';A';b'] is 18 x 13, the factor L is 18 x 17).  Stage blocks are staged in
+// shared memory by the TMA bulk-copy engine one stage ahead of the arithmetic (double
+// buffered, mbarrier-tracked); the dense per-stage kernels (TRMM, SYRK, Cholesky, GEMV,
+// TRSV) are short ROLLED loops over shared-memory rows with 128-bit broadcast loads, so the
+// whole warp program stays resident in the instruction caches (a fully unrolled register
+// formulation was 300 KB of SASS and spent half its cycles waiting for instruction fetch,
+// profiles/README.md).  Lanes 18..31 help only in the element-wise passes.
 //
 // All stages use the uniform nv = 17 layout: stage 0 keeps 13 decoupled dummy x-variables
 // (its A-rows are zeroed after the x0 elimination folded A0*xbar into b0) and stage N keeps 4
 // decoupled dummy inputs; both stay exactly zero and cost 2/51 of the work.
 //
-// The per-instance working set (linearisation [B';A';b'] 94 KB, factors 69 KB, IPM vectors)
+// The per-instance working set (linearisation [B';A';b'] 94 KB, factors 72 KB, IPM vectors)
 // does not fit on chip; it lives in a per-warp scratch slot in global memory (L2/HBM).
 #pragma once
 #include "cf_model.h"
@@ -32,7 +34,9 @@
 // ------------------------------------------------------------------ sizes / layout
 #define CF_MROWS 18                       // rows of [B';A';res_b'] held per stage
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
-#define CF_LSZ 170                        // packed lower-trapezoid 18x17, column-major
+#define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
+#define CF_LX 104                         // factor, state block: packed lower rows (91) + last row l~x (13)
+#define CF_LFSZ (CF_LU + CF_LX)           // 176 doubles per stage
 #define CF_BND 64                         // doubles per stage of bound data: 8 fields x [lb4 | ub4]
 enum { CF_F_D = 0, CF_F_LAM, CF_F_T, CF_F_RESD, CF_F_RESM, CF_F_BKP, CF_F_DLAM, CF_F_DT };
 
@@ -86,7 +90,8 @@ struct CfBatchView
     int *counter;          // work queue
 };
 
-// offsets (in doubles) of the arrays inside one scratch slot
+// offsets (in doubles) of the arrays inside one scratch slot; every block that the TMA engine
+// touches (M, LF) starts on a 16-byte boundary
 struct CfScratchLayout
 {
     long M, L, b, rq, ux, pi, res_g, dux, dpi, Pb, bnd, total;
@@ -101,7 +106,7 @@ static inline
     CfScratchLayout s;
     long o = 0;
     s.M = o;     o += (long) N * CF_MSZ;
-    s.L = o;     o += (long) (N + 1) * CF_LSZ;
+    s.L = o;     o += (long) (N + 1) * CF_LFSZ;
     s.b = o;     o += (long) N * CF_NX + 1;
     s.rq = o;    o += (long) (N + 1) * CF_NV + 1;
     s.ux = o;    o += (long) (N + 1) * CF_NV + 1;
@@ -110,20 +115,28 @@ static inline
     s.dux = o;   o += (long) (N + 1) * CF_NV + 1;
     s.dpi = o;   o += (long) (N + 1) * CF_NX + 1;
     s.Pb = o;    o += (long) N * CF_NX + 1;
+    o = (o + 1) & ~1L;
     s.bnd = o;   o += (long) (N + 1) * CF_BND;
     s.total = (o + 15) & ~15L;  // keep every slot 128-byte aligned
     return s;
 }
 
-// per-warp shared memory (doubles)
-#define CF_SM_LROWS 0                          // 17 x 17 finished factor rows (stride 17)
-#define CF_SM_AL (CF_SM_LROWS + 17 * 17 + 1)   // 18 x 14 AL rows (stride 14 -> 16-byte aligned rows)
-#define CF_SM_V0 (CF_SM_AL + 18 * 14)          // small broadcast vectors, 32 each
+// per-warp shared memory (doubles); every region starts on a 16-byte boundary
+#define CF_SM_MS0 0                            // [B';A';res_b']_k staging, double buffered (234 used of 240)
+#define CF_SM_MS1 240
+#define CF_SM_W 480                            // 576-double work region:
+#define CF_SM_LS CF_SM_W                       //   factorisation: 18 x 18 factor rows (stride 18) ...
+#define CF_SM_ALS (CF_SM_W + 324)              //   ... and 18 x 14 AL rows (stride 14)
+#define CF_SM_LB0 CF_SM_W                      //   sweeps: factor block staging [LU 72 | LX 104], double buffered
+#define CF_SM_LB1 (CF_SM_W + CF_LFSZ)
+#define CF_SM_V0 (CF_SM_W + 576)               // four 32-double broadcast vectors
 #define CF_SM_V1 (CF_SM_V0 + 32)
 #define CF_SM_V2 (CF_SM_V1 + 32)
-#define CF_SM_DOUBLES (CF_SM_V2 + 32)          // 638 doubles = 5104 bytes per warp
+#define CF_SM_V3 (CF_SM_V2 + 32)
+#define CF_SM_BAR (CF_SM_V3 + 32)              // two mbarriers
+#define CF_SM_DOUBLES (CF_SM_BAR + 4)          // 1188 doubles = 9504 bytes per warp
 
-CF_DEV int cf_loff(int c) { return 18 * c - (c * (c - 1)) / 2; }  // start of column c in a packed factor
+CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
 struct CfWarp
 {
@@ -131,8 +144,10 @@ struct CfWarp
     const CfParams *P;
     int lane, N;
     double *sm;  // per-warp shared memory
+    uint64_t *bar;
+    unsigned par;  // phase parity of the two mbarriers
     // scratch arrays
-    double *M, *L, *b, *rq, *ux, *pi, *res_g, *dux, *dpi, *Pb, *bnd;
+    double *M, *LF, *b, *rq, *ux, *pi, *res_g, *dux, *dpi, *Pb, *bnd;
     // lane constants
     double Hs, HN;     // Hessian diagonal for this lane's variable (stage / terminal)
     // IPM scalars (warp-uniform)
@@ -144,8 +159,10 @@ struct CfWarp
     CF_MEM void bind(const CfParams *P_, double *slot, double *sm_)
     {
         P = P_; N = P_->N; sm = sm_; lane = cf_lane();
+        bar = reinterpret_cast<uint64_t *>(sm_ + CF_SM_BAR);
+        par = 0;
         CfScratchLayout s = cf_scratch_layout(N);
-        M = slot + s.M; L = slot + s.L; b = slot + s.b; rq = slot + s.rq; ux = slot + s.ux; pi = slot + s.pi;
+        M = slot + s.M; LF = slot + s.L; b = slot + s.b; rq = slot + s.rq; ux = slot + s.ux; pi = slot + s.pi;
         res_g = slot + s.res_g; dux = slot + s.dux; dpi = slot + s.dpi; Pb = slot + s.Pb; bnd = slot + s.bnd;
         // hess = scaling * (sqrt(W))^2 : ocp_nlp_cost_ls.c:739-772 (terminal scaling stays 1.0, :265)
         double w = 1.0, wN = 1.0;
@@ -156,18 +173,43 @@ struct CfWarp
         HN = (lane < CF_NU) ? Hs : (rN * rN);
     }
 
+    // ---- TMA staging: one mbarrier per buffer; lane 0 issues, every lane waits
+    CF_MEM void pass_begin()
+    {
+        cf_syncwarp();                            // all generic stores of the previous pass are ordered ...
+        if (lane == 0) cf_fence_proxy_async();    // ... before the bulk (async-proxy) reads of this pass
+    }
+    // fetch into buffer `bf`: [B';A';res_b']_km (if km >= 0), LU_ku (if ku >= 0), LX_kx (if kx >= 0)
+    CF_MEM void fetch(int bf, int km, int ku, int kx)
+    {
+        if (lane == 0) {
+            const int bytes = (km >= 0 ? CF_MSZ * 8 : 0) + (ku >= 0 ? CF_LU * 8 : 0) + (kx >= 0 ? CF_LX * 8 : 0);
+            cf_bulk_expect(bar + bf, bytes);
+            double *ms = sm + (bf ? CF_SM_MS1 : CF_SM_MS0), *lb = sm + (bf ? CF_SM_LB1 : CF_SM_LB0);
+            if (km >= 0) cf_bulk_g2s_raw(ms, M + (long) km * CF_MSZ, CF_MSZ * 8, bar + bf);
+            if (ku >= 0) cf_bulk_g2s_raw(lb, LF + (long) ku * CF_LFSZ, CF_LU * 8, bar + bf);
+            if (kx >= 0) cf_bulk_g2s_raw(lb + CF_LU, LF + (long) kx * CF_LFSZ + CF_LU, CF_LX * 8, bar + bf);
+        }
+    }
+    CF_MEM void wait(int bf)
+    {
+        cf_bulk_wait(bar + bf, (par >> bf) & 1u);
+        par ^= 1u << bf;
+    }
+
     // =============================================================== preparation
     // ERK4 with forward sensitivities for stage k; lane c pushes sensitivity column c
     // ([Su(4) | Sx(13)] -> rows of [B';A']), the nominal state is advanced once per warp in
-    // shared memory.  Writes M_k (rows 0..16), b_k, rq_k, d_k.
-    CF_MEM void linearize_stage(int k, const double *xg, const double *ug, const double *x0g,
-                                const double *yrefg, const double *yref_eg)
+    // shared memory.  Writes M_k (rows 0..16 + b row) by bulk store, b_k, rq_k, d_k.
+    CF_MEM void linearize_stage(int k, const double *xg, const double *ug, const double *x0g, const double *yrefg)
     {
-        double *X0 = sm + CF_SM_V0, *ACC = sm + CF_SM_V1, *XS = sm + CF_SM_V2, *UU = sm + CF_SM_V2 + 16;
+        double *X0 = sm + CF_SM_V0, *ACC = sm + CF_SM_V1, *XS = sm + CF_SM_V2, *UU = sm + CF_SM_V3;
+        double *MS = sm + ((k & 1) ? CF_SM_MS1 : CF_SM_MS0);
         const double h = P->Ts;
         cf_syncwarp();
         if (lane < CF_NX) { double v = xg[k * CF_NX + lane]; X0[lane] = v; ACC[lane] = v; XS[lane] = v; }
         if (lane < CF_NU) UU[lane] = ug[k * CF_NU + lane];
+        if (lane == 0) cf_bulk_s2g_wait_read1();  // the bulk store that last read this MS buffer (stage k-2) is done
         cf_syncwarp();
         double uu[CF_NU];
         CF_UNROLL
@@ -175,7 +217,7 @@ struct CfWarp
         double Ss[CF_NX], acc[CF_NX];
         CF_UNROLL
         for (int i = 0; i < CF_NX; i++) { Ss[i] = (lane - CF_NU == i) ? 1.0 : 0.0; acc[i] = Ss[i]; }
-        CF_UNROLL
+        CF_NOUNROLL
         for (int s = 0; s < 4; s++) {
             // tableau: sim_collocation_utils.c:611-640 (classic RK4)
             const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
@@ -191,13 +233,13 @@ struct CfWarp
             CF_UNROLL
             for (int i = 0; i < CF_NX; i++) {
                 acc[i] += bh * ks[i];
-                if (s < 3) Ss[i] = ((lane - CF_NU == i) ? 1.0 : 0.0) + ah * ks[i];
+                Ss[i] = ((lane - CF_NU == i) ? 1.0 : 0.0) + ah * ks[i];
             }
             if (lane == 17) {
                 CF_UNROLL
                 for (int i = 0; i < CF_NX; i++) {
                     ACC[i] += bh * f[i];
-                    if (s < 3) XS[i] = X0[i] + ah * f[i];
+                    XS[i] = X0[i] + ah * f[i];
                 }
             }
             cf_syncwarp();
@@ -209,19 +251,18 @@ struct CfWarp
         }
         if (k == 0) {
             // x0 elimination (x_ocp_qp_red.c:310-330): xbar = lbx - x_0 ; b_0 += A_0 xbar ; drop the A rows
-            double xbar = (lane >= CF_NU && lane < CF_NV) ? (x0g[lane - CF_NU] - xg[lane - CF_NU]) : 0.0;
+            const bool xl = lane >= CF_NU && lane < CF_NV;
+            const double xbar = xl ? (x0g[lane - CF_NU] - xg[lane - CF_NU]) : 0.0;
             CF_UNROLL
             for (int i = 0; i < CF_NX; i++) {
-                double contrib = (lane >= CF_NU && lane < CF_NV) ? acc[i] * xbar : 0.0;
-                double tot = cf_warp_sum(contrib);
+                const double tot = cf_warp_sum(xl ? acc[i] * xbar : 0.0);
                 if (lane == 17) acc[i] = tot + acc[i];
                 else if (lane >= CF_NU) acc[i] = 0.0;
             }
         }
-        double *Mk = M + (long) k * CF_MSZ;
         if (lane < CF_MROWS) {
             CF_UNROLL
-            for (int c = 0; c < CF_NX; c++) Mk[c * CF_MROWS + lane] = acc[c];
+            for (int c = 0; c < CF_NX; c++) MS[c * CF_MROWS + lane] = acc[c];
         }
         if (lane == 17) {
             CF_UNROLL
@@ -240,7 +281,8 @@ struct CfWarp
             bk[CF_F_D * 8 + lane] = P->lbu[lane] - UU[lane];
             bk[CF_F_D * 8 + 4 + lane] = UU[lane] - P->ubu[lane];
         }
-        (void) yref_eg;
+        cf_syncwarp();
+        if (lane == 0) cf_bulk_s2g(M + (long) k * CF_MSZ, MS, CF_MSZ * 8);
     }
 
     CF_MEM void terminal_gradient(const double *xg, const double *yref_eg)
@@ -250,6 +292,7 @@ struct CfWarp
             if (lane >= CF_NU) g = P->WNdiag[lane - CF_NU] * (xg[N * CF_NX + lane - CF_NU] - yref_eg[lane - CF_NU]);
             rq[N * CF_NV + lane] = g;
         }
+        if (lane == 0) cf_bulk_s2g_wait_all();  // every M_k has landed in global memory
     }
 
     // =============================================================== IPM pieces
@@ -282,6 +325,8 @@ struct CfWarp
         if (do_update && a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
         double ng = 0, nb = 0, nd = 0, nm = 0, mus = 0;
         double *UXS = sm + CF_SM_V0, *PIS = sm + CF_SM_V1;
+        pass_begin();
+        fetch(0, 0, -1, -1);
         // prologue: ux_0
         double uxc = 0.0;
         if (lane < CF_NV) {
@@ -289,6 +334,7 @@ struct CfWarp
             if (do_update) { uxc += a * dux[lane]; ux[lane] = uxc; }
         }
         double pi_prev = 0.0;
+        CF_NOUNROLL
         for (int k = 0; k <= N; k++) {
             double uxn = 0.0, pik = 0.0;
             if (k < N) {
@@ -301,11 +347,12 @@ struct CfWarp
                     if (do_update) { pik += a * dpi[k * CF_NX + lane - CF_NU]; pi[k * CF_NX + lane - CF_NU] = pik; }
                 }
             }
-            double rg = 0.0;
+            double rg = 0.0, bkc = 0.0;
             if (lane < CF_NV) {
                 rg = ((k == N) ? HN : Hs) * uxc + rq[k * CF_NV + lane];
                 if (k > 0 && lane >= CF_NU) rg -= pi_prev;
             }
+            if (k < N && lane >= CF_NU && lane < CF_NV) bkc = b[k * CF_NX + lane - CF_NU];
             if (lane < CF_NU && k < N) {
                 double *bk = bnd + (long) k * CF_BND;
                 double ll = bk[CF_F_LAM * 8 + lane], lu = bk[CF_F_LAM * 8 + 4 + lane];
@@ -328,25 +375,41 @@ struct CfWarp
                 nm = fmax(nm, fmax(fabs(rml), fabs(rmu)));
             }
             if (k < N) {
-                cf_syncwarp();
+                const int bf = k & 1;
+                cf_syncwarp();  // previous stage's reads of UXS/PIS and of buffer bf^1 are complete
+                if (k + 1 < N) fetch(bf ^ 1, k + 1, -1, -1);
                 if (lane < CF_NV) UXS[lane] = uxc;
+                if (lane == 17) UXS[17] = 0.0;
                 if (lane >= CF_NU && lane < CF_NV) PIS[lane - CF_NU] = pik;
+                if (lane == 17) PIS[13] = 0.0;
+                wait(bf);
                 cf_syncwarp();
-                double *Mk = M + (long) k * CF_MSZ;
-                if (lane < CF_NV) {  // res_g += [B';A'] pi_k   (row layout)
-                    double s = 0.0;
+                const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
+                if (lane < CF_NV) {  // res_g += [B';A'] pi_k   (row layout: own elements stride 18)
+                    double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
-                    for (int c = 0; c < CF_NX; c++) s += Mk[c * CF_MROWS + lane] * PIS[c];
-                    rg += s;
+                    for (int cp = 0; cp < 6; cp++) {
+                        const cf_d2 p2 = cf_ld2(PIS + 2 * cp);
+                        s0 += Mk[(2 * cp) * CF_MROWS + lane] * p2.x;
+                        s1 += Mk[(2 * cp + 1) * CF_MROWS + lane] * p2.y;
+                    }
+                    s0 += Mk[12 * CF_MROWS + lane] * PIS[12];
+                    rg += s0 + s1;
                 }
-                if (lane >= CF_NU && lane < CF_NV) {  // res_b = b - x+ + [A B] ux   (column layout)
+                if (lane >= CF_NU && lane < CF_NV) {  // res_b = b - x+ + [A B] ux   (column layout: contiguous)
                     const int c = lane - CF_NU;
-                    double s = 0.0;
+                    const double *Mc = Mk + c * CF_MROWS;
+                    double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
-                    for (int r = 0; r < CF_NV; r++) s += Mk[c * CF_MROWS + r] * UXS[r];
-                    double rb = (b[k * CF_NX + c] - uxn) + s;
+                    for (int rp = 0; rp < 8; rp++) {
+                        const cf_d2 m2 = cf_ld2(Mc + 2 * rp), u2 = cf_ld2(UXS + 2 * rp);
+                        s0 += m2.x * u2.x;
+                        s1 += m2.y * u2.y;
+                    }
+                    s0 += Mc[16] * UXS[16];
+                    const double rb = (bkc - uxn) + (s0 + s1);
                     nb = fmax(nb, fabs(rb));
-                    Mk[c * CF_MROWS + 17] = rb;  // ROWIN(res_b) of x_ocp_qp_kkt.c:490
+                    M[(long) k * CF_MSZ + c * CF_MROWS + 17] = rb;  // ROWIN(res_b) of x_ocp_qp_kkt.c:490
                 }
             }
             if (lane < CF_NV) { res_g[k * CF_NV + lane] = rg; ng = fmax(ng, fabs(rg)); }
@@ -385,101 +448,127 @@ struct CfWarp
 
     // OCP_QP_FACT_SOLVE_KKT_STEP, backward factorisation (x_ocp_qp_kkt.c:445-528):
     //   L_k = chol( [H_k + Gamma ; (res_g + gamma)'] + AL AL' ),  AL = [B';A';res_b']_k Lxx_{k+1}
+    // The factor rows of the stage just finished stay in shared memory (LS) for the next TRMM.
     CF_MEM void factorize()
     {
-        double *LS = sm + CF_SM_LROWS, *ALS = sm + CF_SM_AL, *V = sm + CF_SM_V0;
-        double Lp[CF_NV];  // this lane's row of L_{k+1}
-        CF_UNROLL
-        for (int c = 0; c < CF_NV; c++) Lp[c] = 0.0;
+        double *LS = sm + CF_SM_LS, *ALS = sm + CF_SM_ALS, *V = sm + CF_SM_V0, *G = sm + CF_SM_V1;
+        pass_begin();
+        if (N > 0) fetch(0, N - 1, -1, -1);
+        for (int i = lane; i < 18 * 18; i += 32) LS[i] = 0.0;
+        const bool row = lane < CF_MROWS;
+        const int rl = row ? lane : 0;
+        double *own = LS + rl * 18;
+        CF_NOUNROLL
         for (int k = N; k >= 0; k--) {
-            double s[CF_NV];
+            double out[CF_NX + 1];
             CF_UNROLL
-            for (int j = 0; j < CF_NV; j++) s[j] = 0.0;
+            for (int c = 0; c <= CF_NX; c++) out[c] = 0.0;
+            // gradient row and diagonal of the stage Hessian; bound data are independent of the matrices
+            double Gam = 0.0, gam = 0.0;
+            if (lane < CF_NU && k < N) bound_terms(k, 0, 0.0, Gam, gam);
+            const double g = (lane < CF_NV) ? res_g[k * CF_NV + lane] + gam : 0.0;
+            const double hd = ((k == N) ? HN : Hs) + CF_REG_PRIM + Gam;
             if (k < N) {
-                const double *Mk = M + (long) k * CF_MSZ;
-                double m[CF_NX];
-                CF_UNROLL
-                for (int c = 0; c < CF_NX; c++) m[c] = (lane < CF_MROWS) ? Mk[c * CF_MROWS + lane] : 0.0;
-                // TRMM_RLNN in place: m[c] <- sum_{j>=c} m[j] * Lxx[j][c]
-                CF_UNROLL
-                for (int c = 0; c < CF_NX; c++) {
-                    double v = 0.0;
+                const int bf = (N - 1 - k) & 1;
+                wait(bf);
+                cf_syncwarp();  // every lane is done with buffer bf^1 and with V/G of the previous stage
+                if (k > 0) fetch(bf ^ 1, k - 1, -1, -1);
+                const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
+                // TRMM_RLNN: out[c] = sum_{j>=c} M[r][j] * Lxx[j][c]; the strict upper part of LS is kept
+                // zero so whole 128-bit pairs can be used
+                CF_NOUNROLL
+                for (int j = 0; j < CF_NX; j++) {
+                    const double mj = row ? Mk[j * CF_MROWS + lane] : 0.0;
+                    const double *Lj = LS + (CF_NU + j) * 18 + CF_NU;
                     CF_UNROLL
-                    for (int j = c; j < CF_NX; j++) v += m[j] * LS[(CF_NU + j) * 17 + CF_NU + c];
-                    m[c] = v;
+                    for (int cp = 0; cp < 7; cp++) {
+                        if (2 * cp > j) break;
+                        const cf_d2 l2 = cf_ld2(Lj + 2 * cp);
+                        out[2 * cp] += mj * l2.x;
+                        out[2 * cp + 1] += mj * l2.y;
+                    }
                 }
-                cf_syncwarp();
                 if (lane == 17) {
                     CF_UNROLL
-                    for (int c = 0; c < CF_NX; c++) V[c] = m[c];
+                    for (int cp = 0; cp < 7; cp++) cf_st2(V + 2 * cp, out[2 * cp], cp < 6 ? out[2 * cp + 1] : 0.0);
                 }
                 cf_syncwarp();
-                // Pb = Lxx * (Lxx' res_b)  (TRMV_LNN, :492-493): lane 4+r uses its own factor row
+                // Pb = Lxx * (Lxx' res_b)  (TRMV_LNN, :492-493): lane 4+i uses its own factor row
                 if (lane >= CF_NU && lane < CF_NV) {
-                    double v = 0.0;
+                    double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
-                    for (int c = 0; c < CF_NX; c++)
-                        if (c <= lane - CF_NU) v += Lp[CF_NU + c] * V[c];
-                    Pb[k * CF_NX + lane - CF_NU] = v;
+                    for (int cp = 0; cp < 7; cp++) {
+                        const cf_d2 l2 = cf_ld2(own + CF_NU + 2 * cp), v2 = cf_ld2(V + 2 * cp);
+                        s0 += l2.x * v2.x;
+                        s1 += l2.y * v2.y;
+                    }
+                    Pb[k * CF_NX + lane - CF_NU] = s0 + s1;
                 }
-                if (lane == 17) {
+                if (lane == 17) {  // + l~x of stage k+1 (GEAD, :494)
                     CF_UNROLL
-                    for (int c = 0; c < CF_NX; c++) m[c] += Lp[CF_NU + c];
+                    for (int c = 0; c < CF_NX; c++) out[c] += own[CF_NU + c];
                 }
-                if (lane < CF_MROWS) {
+                if (row) {
                     CF_UNROLL
-                    for (int c = 0; c < CF_NX; c++) ALS[lane * 14 + c] = m[c];
+                    for (int cp = 0; cp < 7; cp++) cf_st2(ALS + lane * 14 + 2 * cp, out[2 * cp], cp < 6 ? out[2 * cp + 1] : 0.0);
                 }
-                cf_syncwarp();
-                // SYRK: s[j] = sum_c AL[r][c] * AL[j][c]
-                CF_UNROLL
+            }
+            G[lane] = g;
+            cf_syncwarp();  // ALS and G visible; all reads of the old LS are complete
+            // SYRK_LN: S[r][j] = D[r][j] + sum_c AL[r][c] AL[j][c], written over this lane's row of LS
+            if (row) {
+                CF_NOUNROLL
                 for (int j = 0; j < CF_NV; j++) {
-                    double v = 0.0;
-                    CF_UNROLL
-                    for (int c = 0; c < CF_NX; c++) v += m[c] * ALS[j * 14 + c];
-                    s[j] = v;
+                    double s0 = (lane == 17) ? G[j] : ((lane == j) ? hd : 0.0), s1 = 0.0;
+                    if (k < N) {
+                        const double *Aj = ALS + j * 14;
+                        CF_UNROLL
+                        for (int cp = 0; cp < 7; cp++) {
+                            const cf_d2 a2 = cf_ld2(Aj + 2 * cp);
+                            s0 += out[2 * cp] * a2.x;
+                            s1 += out[2 * cp + 1] * a2.y;
+                        }
+                    }
+                    own[j] = s0 + s1;
                 }
             }
-            // diagonal / gradient row
             cf_syncwarp();
-            {
-                double Gam = 0.0, gam = 0.0;
-                if (lane < CF_NU && k < N) bound_terms(k, 0, 0.0, Gam, gam);
-                double g = 0.0;
-                if (lane < CF_NV) g = res_g[k * CF_NV + lane] + gam;
-                V[lane] = g;
-                const double hd = ((k == N) ? HN : Hs) + CF_REG_PRIM + Gam;
-                CF_UNROLL
-                for (int j = 0; j < CF_NV; j++)
-                    if (lane == j) s[j] += hd;
-            }
-            cf_syncwarp();
-            if (lane == 17) {
-                CF_UNROLL
-                for (int j = 0; j < CF_NV; j++) s[j] += V[j];
-            }
-            // right-looking Cholesky of the 18 x 17 block, one column per step
-            // (POTRF_L_MN; non-positive pivot -> 0, BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
-            CF_UNROLL
+            // POTRF_L_MN, left-looking, one column per step; non-positive pivot -> 0
+            // (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
+            CF_NOUNROLL
             for (int j = 0; j < CF_NV; j++) {
-                const double piv = cf_shfl(s[j], j);
+                const double *Lj = LS + j * 18;
+                double v0 = own[j], v1 = 0.0;
+                CF_UNROLL
+                for (int cp = 0; cp < 8; cp++) {
+                    if (2 * cp + 1 >= j) break;
+                    const cf_d2 a2 = cf_ld2(own + 2 * cp), b2 = cf_ld2(Lj + 2 * cp);
+                    v0 -= a2.x * b2.x;
+                    v1 -= a2.y * b2.y;
+                }
+                if (j & 1) v0 -= own[j - 1] * Lj[j - 1];
+                const double v = v0 + v1;
+                const double piv = cf_shfl(v, j);
                 double dj = 0.0, inv = 0.0;
                 if (piv > 0.0) { dj = sqrt(piv); inv = 1.0 / dj; }
-                s[j] = (lane == j) ? dj : ((lane > j) ? s[j] * inv : 0.0);
-                if (lane < CF_NV) LS[lane * 17 + j] = s[j];
+                if (row) own[j] = (lane == j) ? dj : ((lane > j) ? v * inv : 0.0);
                 cf_syncwarp();
-                CF_UNROLL
-                for (int jj = j + 1; jj < CF_NV; jj++) s[jj] -= s[j] * LS[jj * 17 + j];
             }
-            // store packed factor (column-major lower trapezoid)
-            double *Lk = L + (long) k * CF_LSZ;
-            if (lane < CF_MROWS) {
-                CF_UNROLL
-                for (int c = 0; c < CF_NV; c++)
-                    if (lane >= c) Lk[cf_loff(c) + lane - c] = s[c];
+            // store the factor: LU block 18 x 4, LX packed rows + last row
+            double *LFk = LF + (long) k * CF_LFSZ;
+            if (row) {
+                const cf_d2 a2 = cf_ld2(own), b2 = cf_ld2(own + 2);
+                cf_st2(LFk + lane * 4, a2.x, a2.y);
+                cf_st2(LFk + lane * 4 + 2, b2.x, b2.y);
             }
-            CF_UNROLL
-            for (int c = 0; c < CF_NV; c++) Lp[c] = s[c];
+            if (lane >= CF_NU && lane < CF_NV) {
+                const int i = lane - CF_NU;
+                double *dst = LFk + CF_LU + cf_tri(i);
+                CF_UNROLL
+                for (int c = 0; c < CF_NX; c++)
+                    if (c <= i) dst[c] = own[CF_NU + c];
+                LFk[CF_LU + 91 + i] = LS[17 * 18 + CF_NU + i];
+            }
         }
         cf_syncwarp();
     }
@@ -491,54 +580,66 @@ struct CfWarp
     // rm_mode selects which complementarity rhs the step was computed for (see bound_terms).
     CF_MEM void forward(int mode, int rm_mode)
     {
-        double *XS = sm + CF_SM_V0, *DS = sm + CF_SM_V1, *YS = sm + CF_SM_V2;
+        double *XS = sm + CF_SM_V0, *DS = sm + CF_SM_V1, *YS = sm + CF_SM_V2, *PS = sm + CF_SM_V3;
         double a_p = -1.0, a_d = -1.0;            // running alpha_prim / alpha_dual (negated)
         double lg = 0, lb = 0, ld = 0, lm = 0;    // linear residual norms
-        // column layout of L_0
-        double col[CF_MROWS];
-        load_factor_cols(0, col);
         double dxk = 0.0;        // lanes 4..16: dx_k ; stage 0 has none
         double dpi_prev = 0.0;   // lanes 4..16: dpi_{k-1}
-        cf_syncwarp();
-        if (lane < 32) XS[lane] = 0.0;
-        cf_syncwarp();
-        for (int k = 0; k <= N; k++) {
-            // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu)
-            double v = 0.0;
+        pass_begin();
+        if (N > 0) fetch(0, 0, 0, 1);
+        XS[lane] = 0.0; YS[lane] = 0.0; PS[lane] = 0.0;
+        const bool xl = lane >= CF_NU && lane < CF_NV;
+        const int ci = xl ? lane - CF_NU : 0;
+        CF_NOUNROLL
+        for (int k = 0; k < N; k++) {
+            const int bf = k & 1;
+            // early, independent global loads
+            double rgk = 0.0, du_in = 0.0;
+            if (lane < CF_NV) rgk = res_g[k * CF_NV + lane];
+            if (mode == 1 && lane < CF_NU) du_in = dux[k * CF_NV + lane];
+            double ll = 1, lu = 1, tl = 1, tu = 1, rdl = 0, rdu = 0, rml = 0, rmu = 0;
             if (lane < CF_NU) {
-                if (mode == 1) v = -dux[k * CF_NV + lane];
-                CF_UNROLL
-                for (int t = 1; t < CF_MROWS; t++) {
-                    const int i = lane + t;
-                    if (i >= CF_NU && i < CF_NV) v -= col[t] * XS[i - CF_NU];
-                    if (mode == 0 && i == 17) v -= col[t];  // - l~_u (last row of L_k)
-                }
+                const double *bk = bnd + (long) k * CF_BND;
+                ll = bk[CF_F_LAM * 8 + lane]; lu = bk[CF_F_LAM * 8 + 4 + lane];
+                tl = bk[CF_F_T * 8 + lane]; tu = bk[CF_F_T * 8 + 4 + lane];
+                rdl = bk[CF_F_RESD * 8 + lane]; rdu = bk[CF_F_RESD * 8 + 4 + lane];
+                if (rm_mode == 0) { rml = bk[CF_F_BKP * 8 + lane] - CF_TAU_MIN; rmu = bk[CF_F_BKP * 8 + 4 + lane] - CF_TAU_MIN; }
+                else { rml = bk[CF_F_RESM * 8 + lane]; rmu = bk[CF_F_RESM * 8 + 4 + lane]; }
             }
-            const double invd = 1.0 / col[0];
+            const double pnext = (mode == 1 && xl) ? dux[(k + 1) * CF_NV + lane] : 0.0;  // p_{k+1} of the backward sweep
+            wait(bf);
+            cf_syncwarp();  // every lane is done with buffer bf^1
+            if (k + 1 < N) fetch(bf ^ 1, k + 1, k + 1, k + 2);
+            const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
+            const double *LU = sm + (bf ? CF_SM_LB1 : CF_SM_LB0), *LX = LU + CF_LU;
+            // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu)
+            double v = 0.0, invd = 1.0;
+            if (lane < CF_NU) {
+                double v0 = (mode == 0) ? -LU[17 * 4 + lane] : -du_in, v1 = 0.0;
+                CF_UNROLL
+                for (int ip = 0; ip < 6; ip++) {
+                    const cf_d2 x2 = cf_ld2(XS + 2 * ip);
+                    v0 -= LU[(CF_NU + 2 * ip) * 4 + lane] * x2.x;
+                    v1 -= LU[(CF_NU + 2 * ip + 1) * 4 + lane] * x2.y;
+                }
+                v0 -= LU[16 * 4 + lane] * XS[12];
+                v = v0 + v1;
+                invd = 1.0 / LU[lane * 4 + lane];
+            }
             double du = 0.0;
             CF_UNROLL
             for (int j = CF_NU - 1; j >= 0; j--) {
                 const double duj = cf_shfl(v * invd, j);
                 if (lane == j) du = duj;
-                if (lane < j) {
-                    const int t = j - lane;
-                    const double lj = (t == 1) ? col[1] : ((t == 2) ? col[2] : col[3]);
-                    v -= lj * duj;
-                }
+                if (lane < j) v -= LU[j * 4 + lane] * duj;
             }
             const double duxk = (lane < CF_NU) ? du : dxk;  // lane r: dux_k[r]
             if (lane < CF_NV) dux[k * CF_NV + lane] = duxk;
             // ---- dlam, dt, alpha (lanes 0..3)
             double dlam_l = 0, dlam_u = 0;
-            if (lane < CF_NU && k < N) {
+            if (lane < CF_NU) {
                 double *bk = bnd + (long) k * CF_BND;
-                double ll = bk[CF_F_LAM * 8 + lane], lu = bk[CF_F_LAM * 8 + 4 + lane];
-                double tl = bk[CF_F_T * 8 + lane], tu = bk[CF_F_T * 8 + 4 + lane];
-                double til = 1.0 / tl, tiu = 1.0 / tu;
-                double rdl = bk[CF_F_RESD * 8 + lane], rdu = bk[CF_F_RESD * 8 + 4 + lane];
-                double rml, rmu;
-                if (rm_mode == 0) { rml = bk[CF_F_BKP * 8 + lane] - CF_TAU_MIN; rmu = bk[CF_F_BKP * 8 + 4 + lane] - CF_TAU_MIN; }
-                else { rml = bk[CF_F_RESM * 8 + lane]; rmu = bk[CF_F_RESM * 8 + 4 + lane]; }
+                const double til = 1.0 / tl, tiu = 1.0 / tu;
                 double dtl = du, dtu = -du;
                 dlam_l = -til * (rml + (ll * dtl) - (ll * rdl));
                 dlam_u = -tiu * (rmu + (lu * dtu) - (lu * rdu));
@@ -556,72 +657,80 @@ struct CfWarp
             // stationarity residual, part 1: H dux + rhs_g - dpi_{k-1} + dlam_ub - dlam_lb
             double rgl = 0.0;
             if (lane < CF_NV) {
-                rgl = ((k == N) ? HN : Hs) * duxk + res_g[k * CF_NV + lane];
+                rgl = Hs * duxk + rgk;
                 if (k > 0 && lane >= CF_NU) rgl -= dpi_prev;
                 rgl += dlam_u - dlam_l;
             }
-            if (k == N) { if (lane < CF_NV) lg = fmax(lg, fabs(rgl)); break; }
-            // ---- dx+ = [A B] dux + res_b        GEMV_T, column layout of M_k
-            cf_syncwarp();
+            // ---- dx+ = [A B] dux + res_b        GEMV_T, column layout of M_k (contiguous)
             if (lane < CF_NV) DS[lane] = duxk;
             cf_syncwarp();
-            const double *Mk = M + (long) k * CF_MSZ;
-            double dxn = 0.0, rbk = 0.0;
-            if (lane >= CF_NU && lane < CF_NV) {
-                const int c = lane - CF_NU;
-                double sacc = 0.0;
+            double dxn = 0.0;
+            if (xl) {
+                const double *Mc = Mk + ci * CF_MROWS;
+                double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
-                for (int r = 0; r < CF_NV; r++) sacc += Mk[c * CF_MROWS + r] * DS[r];
-                rbk = Mk[c * CF_MROWS + 17];
-                dxn = sacc + rbk;
-                lb = fmax(lb, fabs((rbk - dxn) + sacc));
+                for (int rp = 0; rp < 8; rp++) {
+                    const cf_d2 m2 = cf_ld2(Mc + 2 * rp), d2 = cf_ld2(DS + 2 * rp);
+                    s0 += m2.x * d2.x;
+                    s1 += m2.y * d2.y;
+                }
+                const cf_d2 m2 = cf_ld2(Mc + 16);  // [M[16][c], res_b[c]]
+                s0 += m2.x * DS[16];
+                const double sacc = s0 + s1;
+                dxn = sacc + m2.y;
+                lb = fmax(lb, fabs((m2.y - dxn) + sacc));
+                XS[ci] = dxn;
             }
             cf_syncwarp();
-            if (lane >= CF_NU && lane < CF_NV) XS[lane - CF_NU] = dxn;
-            cf_syncwarp();
-            // ---- dpi: needs L_{k+1} in column layout (Lxx' dx+) and row layout (Lxx * .)
-            double coln[CF_MROWS];
-            load_factor_cols(k + 1, coln);
-            double y = 0.0;
-            if (lane >= CF_NU && lane < CF_NV) {
+            // ---- dpi = Lxx (Lxx' dx+ + l~x)  [mode 0]   |   p_{k+1} + Lxx Lxx' dx+  [mode 1]
+            if (xl) {
+                double y0 = (mode == 0) ? LX[91 + ci] : 0.0, y1 = 0.0;
                 CF_UNROLL
-                for (int t = 0; t < CF_MROWS; t++) {
-                    const int i = lane + t;
-                    if (i < CF_NV) y += coln[t] * XS[i - CF_NU];
-                }
-                if (mode == 0) {  // + l~_x  (last row of L_{k+1})
-                    CF_UNROLL
-                    for (int t = 1; t < CF_MROWS; t++)
-                        if (lane + t == 17) y += coln[t];
-                }
-                YS[lane - CF_NU] = y;
+                for (int i = 0; i < CF_NX; i++)  // column ci of the packed rows: entries i >= ci
+                    if (i >= ci) {
+                        if (i & 1) y1 += LX[(i * (i + 1)) / 2 + ci] * XS[i];
+                        else y0 += LX[(i * (i + 1)) / 2 + ci] * XS[i];
+                    }
+                YS[ci] = y0 + y1;
             }
             cf_syncwarp();
             double dpik = 0.0;
-            if (lane >= CF_NU && lane < CF_NV) {
-                const double *Ln = L + (long) (k + 1) * CF_LSZ;
-                double z = 0.0;
+            if (xl) {
+                const double *Li = LX + cf_tri(ci);  // row ci: entries c <= ci
+                double z0 = 0.0, z1 = 0.0;
                 CF_UNROLL
-                for (int c = CF_NU; c < CF_NV; c++)
-                    if (lane >= c) z += Ln[cf_loff(c) + lane - c] * YS[c - CF_NU];
-                if (mode == 1) z += dux[(k + 1) * CF_NV + lane];  // p_{k+1} from the backward sweep
-                dpik = z;
-                dpi[k * CF_NX + lane - CF_NU] = dpik;
+                for (int c = 0; c < CF_NX; c++)
+                    if (c <= ci) {
+                        if (c & 1) z1 += Li[c] * YS[c];
+                        else z0 += Li[c] * YS[c];
+                    }
+                dpik = (z0 + z1) + pnext;
+                dpi[k * CF_NX + ci] = dpik;
+                PS[ci] = dpik;
             }
+            cf_syncwarp();
             // stationarity residual, part 2: + [B';A'] dpi_k   (row layout)
-            cf_syncwarp();
-            if (lane >= CF_NU && lane < CF_NV) YS[lane - CF_NU] = dpik;
-            cf_syncwarp();
             if (lane < CF_NV) {
-                double sacc = 0.0;
+                double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
-                for (int c = 0; c < CF_NX; c++) sacc += Mk[c * CF_MROWS + lane] * YS[c];
-                lg = fmax(lg, fabs(rgl + sacc));
+                for (int cp = 0; cp < 6; cp++) {
+                    const cf_d2 p2 = cf_ld2(PS + 2 * cp);
+                    s0 += Mk[(2 * cp) * CF_MROWS + lane] * p2.x;
+                    s1 += Mk[(2 * cp + 1) * CF_MROWS + lane] * p2.y;
+                }
+                s0 += Mk[12 * CF_MROWS + lane] * PS[12];
+                lg = fmax(lg, fabs(rgl + (s0 + s1)));
             }
             dpi_prev = dpik;
             dxk = dxn;
-            CF_UNROLL
-            for (int t = 0; t < CF_MROWS; t++) col[t] = coln[t];
+        }
+        // terminal stage: no inputs, no bounds, no dynamics
+        if (lane < CF_NV) {
+            const double duxN = (lane < CF_NU) ? 0.0 : dxk;
+            dux[N * CF_NV + lane] = duxN;
+            double rgl = HN * duxN + res_g[N * CF_NV + lane];
+            if (N > 0 && lane >= CF_NU) rgl -= dpi_prev;
+            lg = fmax(lg, fabs(rgl));
         }
         lin[0] = cf_warp_max(lg); lin[1] = cf_warp_max(lb); lin[2] = cf_warp_max(ld); lin[3] = cf_warp_max(lm);
         a_p = cf_warp_max(a_p); a_d = cf_warp_max(a_d);
@@ -629,50 +738,56 @@ struct CfWarp
         cf_syncwarp();
     }
 
-    // lane c (0..16) loads column c of the packed factor of stage k: col[t] = L[c+t][c]
-    CF_MEM void load_factor_cols(int k, double *col)
-    {
-        const double *Lk = L + (long) k * CF_LSZ;
-        const int off = cf_loff(lane < CF_NV ? lane : 0);
-        CF_UNROLL
-        for (int t = 0; t < CF_MROWS; t++) col[t] = (lane < CF_NV && lane + t < CF_MROWS) ? Lk[off + t] : ((t == 0) ? 1.0 : 0.0);
-    }
-
     // OCP_QP_SOLVE_KKT_STEP, backward vector recursion with cached Pb (x_ocp_qp_kkt.c:1147-1245):
     // leaves l_k = [L^-1 rhs]_u ; p_k in dux_k for the forward sweep.
     CF_MEM void backward_rhs(int rm_mode, double sigma_mu)
     {
         double *TS = sm + CF_SM_V0;
+        pass_begin();
+        if (N > 0) fetch(0, N - 1, N - 1, -1);
+        // terminal stage: rhs = res_g_N, nothing to eliminate (dummy inputs are zero)
         double pn = 0.0;  // lanes 4..16: p_{k+1}
-        for (int k = N; k >= 0; k--) {
+        if (lane < CF_NV) {
+            pn = res_g[N * CF_NV + lane];
+            dux[N * CF_NV + lane] = pn;
+        }
+        if (lane == 13) TS[13] = 0.0;
+        CF_NOUNROLL
+        for (int k = N - 1; k >= 0; k--) {
+            const int bf = (N - 1 - k) & 1;
             double Gam = 0.0, gam = 0.0;
-            if (lane < CF_NU && k < N) bound_terms(k, rm_mode, sigma_mu, Gam, gam);
-            double rhs = 0.0;
+            if (lane < CF_NU) bound_terms(k, rm_mode, sigma_mu, Gam, gam);
+            double rhs = 0.0, pbk = 0.0;
             if (lane < CF_NV) rhs = res_g[k * CF_NV + lane] + gam;
-            if (k < N) {
-                cf_syncwarp();
-                if (lane >= CF_NU && lane < CF_NV) TS[lane - CF_NU] = pn + Pb[k * CF_NX + lane - CF_NU];
-                cf_syncwarp();
-                const double *Mk = M + (long) k * CF_MSZ;
-                if (lane < CF_NV) {
-                    double sacc = 0.0;
-                    CF_UNROLL
-                    for (int c = 0; c < CF_NX; c++) sacc += Mk[c * CF_MROWS + lane] * TS[c];
-                    rhs += sacc;
+            if (lane >= CF_NU && lane < CF_NV) pbk = Pb[k * CF_NX + lane - CF_NU];
+            cf_syncwarp();  // previous stage's reads of TS and of buffer bf^1 are complete
+            if (k > 0) fetch(bf ^ 1, k - 1, k - 1, -1);
+            if (lane >= CF_NU && lane < CF_NV) TS[lane - CF_NU] = pn + pbk;
+            wait(bf);
+            cf_syncwarp();
+            const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
+            const double *LU = sm + (bf ? CF_SM_LB1 : CF_SM_LB0);
+            if (lane < CF_NV) {
+                double s0 = 0.0, s1 = 0.0;
+                CF_UNROLL
+                for (int cp = 0; cp < 6; cp++) {
+                    const cf_d2 t2 = cf_ld2(TS + 2 * cp);
+                    s0 += Mk[(2 * cp) * CF_MROWS + lane] * t2.x;
+                    s1 += Mk[(2 * cp + 1) * CF_MROWS + lane] * t2.y;
                 }
+                s0 += Mk[12 * CF_MROWS + lane] * TS[12];
+                rhs += s0 + s1;
             }
-            // TRSV_LNN_MN(nv, nu): row layout of the 4 input columns of L_k
-            const double *Lk = L + (long) k * CF_LSZ;
-            double Lr[CF_NU];
-            CF_UNROLL
-            for (int j = 0; j < CF_NU; j++) Lr[j] = (lane < CF_NV && lane >= j) ? Lk[cf_loff(j) + lane - j] : 0.0;
-            const double dg = (lane == 0) ? Lr[0] : ((lane == 1) ? Lr[1] : ((lane == 2) ? Lr[2] : ((lane == 3) ? Lr[3] : 1.0)));
-            const double invd = 1.0 / dg;
+            // TRSV_LNN_MN(nv, nu): rows of the 4 input columns of L_k
+            const int rl = lane < CF_NV ? lane : 0;
+            const cf_d2 l01 = cf_ld2(LU + rl * 4), l23 = cf_ld2(LU + rl * 4 + 2);
+            const double Lr[CF_NU] = {l01.x, l01.y, l23.x, l23.y};
+            const double invd = (lane < CF_NU) ? 1.0 / LU[rl * 4 + rl] : 1.0;
             CF_UNROLL
             for (int j = 0; j < CF_NU; j++) {
                 const double zj = cf_shfl(rhs * invd, j);
                 if (lane == j) rhs = zj;
-                else if (lane > j) rhs -= Lr[j] * zj;
+                else if (lane > j && lane < CF_NV) rhs -= Lr[j] * zj;
             }
             if (lane < CF_NV) dux[k * CF_NV + lane] = rhs;
             pn = rhs;
@@ -685,6 +800,7 @@ struct CfWarp
     {
         double s = 0.0;
         const int e = lane & 7;
+        CF_NOUNROLL
         for (int k = lane >> 3; k < N; k += 4) {
             const double *bk = bnd + (long) k * CF_BND;
             s += (bk[CF_F_LAM * 8 + e] + alpha * bk[CF_F_DLAM * 8 + e]) * (bk[CF_F_T * 8 + e] + alpha * bk[CF_F_DT * 8 + e]);
@@ -701,71 +817,99 @@ struct CfWarp
         return (lin[0] < CF_RES_G_MAX || lin[0] < 1e-3 * nrm[0]) && (lin[1] < CF_RES_B_MAX || lin[1] < 1e-3 * nrm[1]) &&
                (lin[2] < CF_RES_D_MAX || lin[2] < 1e-3 * nrm[2]) && (lin[3] < CF_RES_M_MAX || lin[3] < 1e-3 * nrm[3]);
     }
-
-    // OCP_QP_IPM_SOLVE, delta formulation (x_ocp_qp_ipm.c:2409-2759). Returns HPIPM status.
-    CF_MEM int ipm_solve(int &iters)
-    {
-        init_var();
-        alpha = 1.0;
-        flags = 0;
-        cf_syncwarp();
-        update_and_residuals(false);
-        int kk = 0;
-        const int itmax = P->max_ipm_iter < CF_ITER_MAX ? P->max_ipm_iter : CF_ITER_MAX;
-        for (; kk < itmax && alpha > CF_ALPHA_MIN &&
-               (nrm[0] > CF_RES_G_MAX || nrm[1] > CF_RES_B_MAX || nrm[2] > CF_RES_D_MAX ||
-                fabs(nrm[3] - CF_TAU_MIN) > CF_RES_M_MAX);
-             kk++) {
-            // ---- OCP_QP_IPM_DELTA_STEP (:1943-2405)
-            factorize();
-            forward(0, 0);
-            if (!lin_res_ok_fact()) flags |= CF_FLAG_LIN_RES_FACT;
-            compute_mu_aff();
-            const double tmp = mu_aff / mu;
-            sigma = tmp * tmp * tmp;
-            double sigma_mu = sigma * mu;
-            sigma_mu = sigma_mu > CF_TAU_MIN ? sigma_mu : CF_TAU_MIN;
-            backward_rhs(1, sigma_mu);
-            forward(1, 3);
-            // conditional predictor-corrector (:2230-2273)
-            const double mu_aff0 = mu_aff;
-            compute_mu_aff();
-            if (mu_aff > 2.0 * mu_aff0) {
-                backward_rhs(2, sigma_mu);
-                forward(1, 3);
-            }
-            if (!lin_res_ok_corr()) flags |= CF_FLAG_LIN_RES_CORR;
-            update_and_residuals(true);
-        }
-        iters = kk;
-        if (kk == itmax) return 1;
-        if (alpha <= CF_ALPHA_MIN) return 2;
-        if (mu != mu) return 3;
-        return 0;
-    }
 };
 
+// The passes are compiled once each (not inlined at their several call sites): the code of
+// the whole warp program has to stay small enough for the instruction caches.
+#if defined(CF_SIMT_EMU)
+#define CF_PASS static CF_NOINLINE
+#else
+#define CF_PASS static __device__ CF_NOINLINE
+#endif
+CF_PASS void cf_pass_residuals(CfWarp &w, bool do_update) { w.update_and_residuals(do_update); }
+CF_PASS void cf_pass_factorize(CfWarp &w) { w.factorize(); }
+CF_PASS void cf_pass_forward(CfWarp &w, int mode, int rm_mode) { w.forward(mode, rm_mode); }
+CF_PASS void cf_pass_backward(CfWarp &w, int rm_mode, double sigma_mu) { w.backward_rhs(rm_mode, sigma_mu); }
+CF_PASS void cf_pass_linearize(CfWarp &w, const double *xg, const double *ug, const double *x0g, const double *yrefg,
+                               const double *yref_eg)
+{
+    CF_NOUNROLL
+    for (int k = 0; k < w.N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg);
+    w.terminal_gradient(xg, yref_eg);
+    cf_syncwarp();
+}
+
+// OCP_QP_IPM_SOLVE, delta formulation (x_ocp_qp_ipm.c:2409-2759). Returns HPIPM status.
+CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
+{
+    w.init_var();
+    w.alpha = 1.0;
+    w.flags = 0;
+    cf_syncwarp();
+    cf_pass_residuals(w, false);
+    int kk = 0;
+    const int itmax = w.P->max_ipm_iter < CF_ITER_MAX ? w.P->max_ipm_iter : CF_ITER_MAX;
+    for (; kk < itmax && w.alpha > CF_ALPHA_MIN &&
+           (w.nrm[0] > CF_RES_G_MAX || w.nrm[1] > CF_RES_B_MAX || w.nrm[2] > CF_RES_D_MAX ||
+            fabs(w.nrm[3] - CF_TAU_MIN) > CF_RES_M_MAX);
+         kk++) {
+        // ---- OCP_QP_IPM_DELTA_STEP (:1943-2405)
+        cf_pass_factorize(w);
+        cf_pass_forward(w, 0, 0);
+        if (!w.lin_res_ok_fact()) w.flags |= CF_FLAG_LIN_RES_FACT;
+        w.compute_mu_aff();
+        const double tmp = w.mu_aff / w.mu;
+        w.sigma = tmp * tmp * tmp;
+        double sigma_mu = w.sigma * w.mu;
+        sigma_mu = sigma_mu > CF_TAU_MIN ? sigma_mu : CF_TAU_MIN;
+        cf_pass_backward(w, 1, sigma_mu);
+        cf_pass_forward(w, 1, 3);
+        // conditional predictor-corrector (:2230-2273)
+        const double mu_aff0 = w.mu_aff;
+        w.compute_mu_aff();
+        if (w.mu_aff > 2.0 * mu_aff0) {
+            cf_pass_backward(w, 2, sigma_mu);
+            cf_pass_forward(w, 1, 3);
+        }
+        if (!w.lin_res_ok_corr()) w.flags |= CF_FLAG_LIN_RES_CORR;
+        cf_pass_residuals(w, true);
+    }
+    iters = kk;
+    if (kk == itmax) return 1;
+    if (w.alpha <= CF_ALPHA_MIN) return 2;
+    if (w.mu != w.mu) return 3;
+    return 0;
+}
+
 // The whole RTI step for instance `inst` (what acados_solve() does, ocp_nlp_sqp_rti.c:1232-1237).
-CF_DEV void cf_rti_instance(const CfParams *P, const CfBatchView &bv, int inst, double *slot, double *sm)
+// `sm` must be 16-byte aligned and its two mbarriers initialised (cf_warp_init_smem).
+CF_DEV void cf_warp_init_smem(double *sm)
+{
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + CF_SM_BAR);
+    if (cf_lane() == 0) { cf_mbar_init(bar); cf_mbar_init(bar + 1); }
+    cf_syncwarp();
+}
+
+CF_DEV void cf_rti_instance(const CfParams *P, const CfBatchView &bv, int inst, double *slot, double *sm, unsigned &par)
 {
     CfWarp w;
     w.bind(P, slot, sm);
+    w.par = par;
     const int N = P->N;
     double *xg = bv.x + (long) inst * (N + 1) * CF_NX;
     double *ug = bv.u + (long) inst * N * CF_NU;
     const double *x0g = bv.x0 + (long) inst * CF_NX;
     const double *yrefg = bv.yref + (long) inst * N * CF_NY;
     const double *yref_eg = bv.yref_e + (long) inst * CF_NX;
-    for (int k = 0; k < N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg, yref_eg);
-    w.terminal_gradient(xg, yref_eg);
-    cf_syncwarp();
+    cf_pass_linearize(w, xg, ug, x0g, yrefg, yref_eg);
     int iters = 0;
-    const int qp_status = w.ipm_solve(iters);
+    const int qp_status = cf_ipm_solve(w, iters);
     // ocp_nlp_sqp_rti.c:651-674: QP max-iter is not fatal; anything else leaves the iterate untouched
     int status = CF_ACADOS_SUCCESS;
     if (qp_status == 0 || qp_status == 1) {
         // primal update, full step (ocp_nlp_common.c:2900-2952); x_0 takes the eliminated step xbar
         const int lane = w.lane;
+        CF_NOUNROLL
         for (int k = 0; k <= N; k++) {
             if (lane < CF_NU && k < N) ug[k * CF_NU + lane] += w.ux[k * CF_NV + lane];
             if (lane >= CF_NU && lane < CF_NV) {
@@ -784,5 +928,6 @@ CF_DEV void cf_rti_instance(const CfParams *P, const CfBatchView &bv, int inst, 
         bv.flags[inst] = w.flags;
         if (bv.res) { for (int i = 0; i < 4; i++) bv.res[inst * 4 + i] = w.nrm[i]; }
     }
+    par = w.par;
     cf_syncwarp();
 }

@@ -18,21 +18,23 @@
 // ------------------------------------------------------------------ kernels
 // Persistent warps: each warp owns a scratch slot and pulls instance ids from a global
 // counter until the batch is exhausted (IPM trip counts differ per instance: 4..11).
-// MINB = resident blocks per SM the register allocation is bounded for (2: 255 regs, 3: 168, 4: 128).
+// MINB = resident blocks per SM the register allocation is bounded for (blocks of 4 warps).
 template <int MINB>
 __global__ void __launch_bounds__(CF_WARPS_PER_BLOCK * 32, MINB)
 cf_rti_kernel(const __grid_constant__ CfParams P, const __grid_constant__ CfBatchView bv)
 {
-    extern __shared__ double cf_smem[];
+    extern __shared__ __align__(128) double cf_smem[];
     const int warp = threadIdx.x >> 5;
     double *sm = cf_smem + warp * CF_SM_DOUBLES;
     double *slot = bv.scratch + (long) (blockIdx.x * CF_WARPS_PER_BLOCK + warp) * bv.scratch_stride;
+    cf_warp_init_smem(sm);
+    unsigned par = 0;
     for (;;) {
         int inst = 0;
         if ((threadIdx.x & 31) == 0) inst = atomicAdd(bv.counter, 1);
         inst = __shfl_sync(0xffffffffu, inst, 0);
         if (inst >= bv.B) break;
-        cf_rti_instance(&P, bv, inst, slot, sm);
+        cf_rti_instance(&P, bv, inst, slot, sm, par);
     }
 }
 
@@ -78,7 +80,7 @@ struct cfnmpc_batch
     double *d_x0 = nullptr, *d_yref = nullptr, *d_yref_e = nullptr, *d_x = nullptr, *d_u = nullptr, *d_res = nullptr;
     double *d_scratch = nullptr, *d_stage = nullptr;
     int *d_status = nullptr, *d_qp_iter = nullptr, *d_qp_status = nullptr, *d_flags = nullptr, *d_counter = nullptr;
-    int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 4;
+    int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 5;
     void (*kernel)(const CfParams, const CfBatchView) = nullptr;
     size_t smem = 0;
     long long launches = 0;
@@ -139,11 +141,12 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     CKH(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
     h->smem = (size_t) CF_WARPS_PER_BLOCK * CF_SM_DOUBLES * sizeof(double);
-    // occupancy variant: CFNMPC_MIN_BLOCKS = 2 | 3 | 4 (default 4 -> 16 warps per SM)
+    // occupancy variant: CFNMPC_MIN_BLOCKS = 3 | 4 | 5 | 6 blocks of 4 warps per SM (default 5 -> 20 warps per SM)
     if (const char *e = getenv("CFNMPC_MIN_BLOCKS")) h->minb = atoi(e);
-    if (h->minb == 2) h->kernel = cf_rti_kernel<2>;
-    else if (h->minb == 3) h->kernel = cf_rti_kernel<3>;
-    else { h->minb = 4; h->kernel = cf_rti_kernel<4>; }
+    if (h->minb == 3) h->kernel = cf_rti_kernel<3>;
+    else if (h->minb == 4) h->kernel = cf_rti_kernel<4>;
+    else if (h->minb == 6) h->kernel = cf_rti_kernel<6>;
+    else { h->minb = 5; h->kernel = cf_rti_kernel<5>; }
     CKH(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem));
     cudaFuncAttributes fa;
     CKH(cudaFuncGetAttributes(&fa, h->kernel));

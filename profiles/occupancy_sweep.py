@@ -19,5 +19,5 @@ with cf.BatchSolver({B}, {N}, 0.015) as s:
     print("minb", s.info("blocks_per_sm"), "regs", s.info("regs_per_thread"), "grid", s.info("grid"),
           "ms", [round(t, 2) for t in ts], "solves/s %.0f" % ({B} / (min(ts) * 1e-3)), "iters", s.get("qp_iter").mean())
 """
-for mb in (2, 3, 4):
+for mb in (3, 4, 5, 6):
     subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CFNMPC_MIN_BLOCKS=str(mb)))

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -76,6 +77,72 @@ int atomic_add(int *p, int v)
     return old;
 }
 
+// ---- TMA bulk copies.  global->shared: the destination is poisoned when the copy is issued and
+// filled only when the warp waits on the mbarrier, so reading a staged block before waiting,
+// or waiting on the wrong barrier/parity, produces NaNs instead of silently working.
+struct PendingLoad { void *dst; const void *src; int bytes; uint64_t *bar; };
+struct PendingStore { const void *src; std::vector<char> snapshot; };
+static thread_local std::vector<PendingLoad> g_loads;
+static thread_local std::vector<PendingStore> g_stores;
+static thread_local std::vector<std::pair<uint64_t *, int>> g_expect;
+
+void bulk_expect(uint64_t *bar, int bytes, int line)
+{
+    for (auto &e : g_expect)
+        if (e.first == bar) { fprintf(stderr, "cfemu: line %d: mbarrier re-armed while a phase is pending\n", line); abort(); }
+    g_expect.push_back({bar, bytes});
+}
+void bulk_g2s(void *dst, const void *src, int bytes, uint64_t *bar, int line)
+{
+    if ((((uintptr_t) dst) & 15) || (((uintptr_t) src) & 15) || (bytes & 15)) {
+        fprintf(stderr, "cfemu: line %d: bulk copy needs 16-byte aligned addresses and size\n", line); abort();
+    }
+    double *d = (double *) dst;
+    for (int i = 0; i < bytes / 8; i++) d[i] = std::nan("");
+    g_loads.push_back({dst, src, bytes, bar});
+}
+void bulk_wait(uint64_t *bar, unsigned parity, int line)
+{
+    // phase bit lives in the barrier word: completed phases counted modulo 2
+    barrier(line);
+    if (W->cur == 0 || true) {
+        // the first lane to arrive completes the phase; later lanes see it done
+        if ((*bar & 1u) == parity) {
+            int expect = -1, got = 0;
+            for (size_t i = 0; i < g_expect.size(); i++)
+                if (g_expect[i].first == bar) { expect = g_expect[i].second; g_expect.erase(g_expect.begin() + i); break; }
+            if (expect < 0) { fprintf(stderr, "cfemu: line %d: wait on an mbarrier that was never armed (deadlock on the GPU)\n", line); abort(); }
+            for (size_t i = 0; i < g_loads.size();) {
+                if (g_loads[i].bar == bar) { memcpy(g_loads[i].dst, g_loads[i].src, g_loads[i].bytes); got += g_loads[i].bytes; g_loads.erase(g_loads.begin() + i); }
+                else i++;
+            }
+            if (got != expect) { fprintf(stderr, "cfemu: line %d: expect_tx %d bytes but %d were copied\n", line, expect, got); abort(); }
+            *bar ^= 1u;
+        }
+    }
+    barrier(-line);
+}
+void bulk_s2g(void *dst, const void *src, int bytes, int line)
+{
+    if ((((uintptr_t) dst) & 15) || (((uintptr_t) src) & 15) || (bytes & 15)) {
+        fprintf(stderr, "cfemu: line %d: bulk copy needs 16-byte aligned addresses and size\n", line); abort();
+    }
+    memcpy(dst, src, bytes);
+    PendingStore p; p.src = src; p.snapshot.assign((const char *) src, (const char *) src + bytes);
+    g_stores.push_back(std::move(p));
+}
+void bulk_s2g_wait(int max_pending, int line)
+{
+    // the shared source of a store that may still be in flight must not have been modified
+    while ((int) g_stores.size() > max_pending) {
+        PendingStore &p = g_stores.front();
+        if (memcmp(p.src, p.snapshot.data(), p.snapshot.size()) != 0) {
+            fprintf(stderr, "cfemu: line %d: shared source of a bulk store was overwritten before wait_group\n", line); abort();
+        }
+        g_stores.erase(g_stores.begin());
+    }
+}
+
 static void trampoline()
 {
     Warp *w = W;
@@ -123,7 +190,9 @@ struct Job
 static void job_fn(void *a)
 {
     Job *j = (Job *) a;
-    cf_rti_instance(j->P, j->bv, j->inst, j->slot, j->sm);
+    cf_warp_init_smem(j->sm);
+    unsigned par = 0;
+    cf_rti_instance(j->P, j->bv, j->inst, j->slot, j->sm, par);
 }
 
 extern "C" long cfemu_scratch_doubles(int N) { return cf_scratch_layout(N).total; }
@@ -159,15 +228,17 @@ extern "C" int cfemu_rti_batch(int B, int N, double Ts, const double *params, in
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; t++)
         th.emplace_back([&]() {
-            std::vector<double> slot(stride, 0.0), sm(CF_SM_DOUBLES, 0.0);
+            std::vector<double> slot(stride + 2, 0.0), sm(CF_SM_DOUBLES + 2, 0.0);
             for (;;) {
                 int i = next.fetch_add(1);
                 if (i >= B) break;
                 // poison the scratch so that reads of never-written data are visible
                 for (auto &v : slot) v = std::nan("");
-                Job j{&P, bv, i, slot.data(), sm.data()};
+                double *slot_a = (double *) ((((uintptr_t) slot.data()) + 15) & ~(uintptr_t) 15), *sm_a = (double *) ((((uintptr_t) sm.data()) + 15) & ~(uintptr_t) 15);
+                for (int q = 0; q < CF_SM_DOUBLES; q++) sm_a[q] = std::nan("");
+                Job j{&P, bv, i, slot_a, sm_a};
                 cfemu::run_warp(job_fn, &j);
-                if (scratch_out) memcpy(scratch_out + (size_t) i * stride, slot.data(), stride * 8);
+                if (scratch_out) memcpy(scratch_out + (size_t) i * stride, slot_a, stride * 8);
             }
         });
     for (auto &t : th) t.join();
