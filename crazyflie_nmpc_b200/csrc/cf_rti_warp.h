@@ -819,60 +819,65 @@ struct CfWarp
     }
 };
 
-// The passes are compiled once each (not inlined at their several call sites): the code of
-// the whole warp program has to stay small enough for the instruction caches.
-#if defined(CF_SIMT_EMU)
-#define CF_PASS static CF_NOINLINE
-#else
-#define CF_PASS static __device__ CF_NOINLINE
-#endif
-CF_PASS void cf_pass_residuals(CfWarp &w, bool do_update) { w.update_and_residuals(do_update); }
-CF_PASS void cf_pass_factorize(CfWarp &w) { w.factorize(); }
-CF_PASS void cf_pass_forward(CfWarp &w, int mode, int rm_mode) { w.forward(mode, rm_mode); }
-CF_PASS void cf_pass_backward(CfWarp &w, int rm_mode, double sigma_mu) { w.backward_rhs(rm_mode, sigma_mu); }
-CF_PASS void cf_pass_linearize(CfWarp &w, const double *xg, const double *ug, const double *x0g, const double *yrefg,
-                               const double *yref_eg)
-{
-    CF_NOUNROLL
-    for (int k = 0; k < w.N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg);
-    w.terminal_gradient(xg, yref_eg);
-    cf_syncwarp();
-}
-
-// OCP_QP_IPM_SOLVE, delta formulation (x_ocp_qp_ipm.c:2409-2759). Returns HPIPM status.
+// OCP_QP_IPM_SOLVE, delta formulation (x_ocp_qp_ipm.c:2409-2759), written as a small state
+// machine so that every pass has exactly ONE call site: each pass is inlined once into the
+// kernel (address spaces of all pointers known, warp context in registers) and the code of
+// the whole warp program stays small enough for the instruction caches.  Returns HPIPM status.
 CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
 {
     w.init_var();
     w.alpha = 1.0;
     w.flags = 0;
     cf_syncwarp();
-    cf_pass_residuals(w, false);
-    int kk = 0;
     const int itmax = w.P->max_ipm_iter < CF_ITER_MAX ? w.P->max_ipm_iter : CF_ITER_MAX;
-    for (; kk < itmax && w.alpha > CF_ALPHA_MIN &&
-           (w.nrm[0] > CF_RES_G_MAX || w.nrm[1] > CF_RES_B_MAX || w.nrm[2] > CF_RES_D_MAX ||
-            fabs(w.nrm[3] - CF_TAU_MIN) > CF_RES_M_MAX);
-         kk++) {
-        // ---- OCP_QP_IPM_DELTA_STEP (:1943-2405)
-        cf_pass_factorize(w);
-        cf_pass_forward(w, 0, 0);
-        if (!w.lin_res_ok_fact()) w.flags |= CF_FLAG_LIN_RES_FACT;
-        w.compute_mu_aff();
-        const double tmp = w.mu_aff / w.mu;
-        w.sigma = tmp * tmp * tmp;
-        double sigma_mu = w.sigma * w.mu;
-        sigma_mu = sigma_mu > CF_TAU_MIN ? sigma_mu : CF_TAU_MIN;
-        cf_pass_backward(w, 1, sigma_mu);
-        cf_pass_forward(w, 1, 3);
-        // conditional predictor-corrector (:2230-2273)
-        const double mu_aff0 = w.mu_aff;
-        w.compute_mu_aff();
-        if (w.mu_aff > 2.0 * mu_aff0) {
-            cf_pass_backward(w, 2, sigma_mu);
-            cf_pass_forward(w, 1, 3);
+    enum { ST_RES, ST_FACT, ST_FWD, ST_BWD };
+    int st = ST_RES, kk = 0, fmode = 0, frm = 0, brm = 1;
+    bool upd = false;
+    double sigma_mu = 0.0, mu_aff0 = 0.0;
+    for (;;) {
+        if (st == ST_RES) {
+            w.update_and_residuals(upd);
+            if (upd) kk++;
+            const bool go = kk < itmax && w.alpha > CF_ALPHA_MIN &&
+                            (w.nrm[0] > CF_RES_G_MAX || w.nrm[1] > CF_RES_B_MAX || w.nrm[2] > CF_RES_D_MAX ||
+                             fabs(w.nrm[3] - CF_TAU_MIN) > CF_RES_M_MAX);
+            if (!go) break;
+            st = ST_FACT;
+        } else if (st == ST_FACT) {
+            // ---- OCP_QP_IPM_DELTA_STEP (:1943-2405): affine (predictor) direction
+            w.factorize();
+            fmode = 0; frm = 0;
+            st = ST_FWD;
+        } else if (st == ST_FWD) {
+            w.forward(fmode, frm);
+            if (fmode == 0) {
+                if (!w.lin_res_ok_fact()) w.flags |= CF_FLAG_LIN_RES_FACT;
+                w.compute_mu_aff();
+                const double tmp = w.mu_aff / w.mu;
+                w.sigma = tmp * tmp * tmp;
+                sigma_mu = w.sigma * w.mu;
+                sigma_mu = sigma_mu > CF_TAU_MIN ? sigma_mu : CF_TAU_MIN;
+                brm = 1;            // centering-corrector rhs
+                st = ST_BWD;
+            } else {
+                bool recenter = false;
+                if (brm == 1) {     // conditional predictor-corrector (:2230-2273)
+                    mu_aff0 = w.mu_aff;
+                    w.compute_mu_aff();
+                    recenter = w.mu_aff > 2.0 * mu_aff0;
+                }
+                if (recenter) { brm = 2; st = ST_BWD; }
+                else {
+                    if (!w.lin_res_ok_corr()) w.flags |= CF_FLAG_LIN_RES_CORR;
+                    upd = true;
+                    st = ST_RES;
+                }
+            }
+        } else {
+            w.backward_rhs(brm, sigma_mu);
+            fmode = 1; frm = 3;
+            st = ST_FWD;
         }
-        if (!w.lin_res_ok_corr()) w.flags |= CF_FLAG_LIN_RES_CORR;
-        cf_pass_residuals(w, true);
     }
     iters = kk;
     if (kk == itmax) return 1;
@@ -901,7 +906,10 @@ CF_DEV void cf_rti_instance(const CfParams *P, const CfBatchView &bv, int inst, 
     const double *x0g = bv.x0 + (long) inst * CF_NX;
     const double *yrefg = bv.yref + (long) inst * N * CF_NY;
     const double *yref_eg = bv.yref_e + (long) inst * CF_NX;
-    cf_pass_linearize(w, xg, ug, x0g, yrefg, yref_eg);
+    CF_NOUNROLL
+    for (int k = 0; k < N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg);
+    w.terminal_gradient(xg, yref_eg);
+    cf_syncwarp();
     int iters = 0;
     const int qp_status = cf_ipm_solve(w, iters);
     // ocp_nlp_sqp_rti.c:651-674: QP max-iter is not fatal; anything else leaves the iterate untouched
