@@ -122,9 +122,9 @@ static inline
 }
 
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
-#define CF_SM_MS0 0                            // [B';A';res_b']_k staging, double buffered (234 used of 240)
-#define CF_SM_MS1 240
-#define CF_SM_W 480                            // 576-double work region:
+#define CF_SM_MS0 0                            // [B';A';res_b']_k staging, double buffered
+#define CF_SM_MS1 CF_MSZ
+#define CF_SM_W (2 * CF_MSZ)                            // 576-double work region:
 #define CF_SM_LS CF_SM_W                       //   factorisation: 18 x 18 factor rows (stride 18) ...
 #define CF_SM_ALS (CF_SM_W + 324)              //   ... and 18 x 14 AL rows (stride 14)
 #define CF_SM_LB0 CF_SM_W                      //   sweeps: factor block staging [LU 72 | LX 104], double buffered
@@ -134,7 +134,7 @@ static inline
 #define CF_SM_V2 (CF_SM_V1 + 32)
 #define CF_SM_V3 (CF_SM_V2 + 32)
 #define CF_SM_BAR (CF_SM_V3 + 32)              // two mbarriers
-#define CF_SM_DOUBLES (CF_SM_BAR + 4)          // 1188 doubles = 9504 bytes per warp
+#define CF_SM_DOUBLES (CF_SM_BAR + 4)          // 1176 doubles = 9408 bytes per warp (6 blocks of 4 warps per SM)
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
@@ -455,8 +455,10 @@ struct CfWarp
         pass_begin();
         if (N > 0) fetch(0, N - 1, -1, -1);
         for (int i = lane; i < 18 * 18; i += 32) LS[i] = 0.0;
+        // lanes 17..31 all act as row 17 (they compute and store identical values), so the dense
+        // loops below run without lane predicates
         const bool row = lane < CF_MROWS;
-        const int rl = row ? lane : 0;
+        const int rl = lane < 17 ? lane : 17;
         double *own = LS + rl * 18;
         CF_NOUNROLL
         for (int k = N; k >= 0; k--) {
@@ -478,7 +480,7 @@ struct CfWarp
                 // zero so whole 128-bit pairs can be used
                 CF_NOUNROLL
                 for (int j = 0; j < CF_NX; j++) {
-                    const double mj = row ? Mk[j * CF_MROWS + lane] : 0.0;
+                    const double mj = Mk[j * CF_MROWS + rl];
                     const double *Lj = LS + (CF_NU + j) * 18 + CF_NU;
                     CF_UNROLL
                     for (int cp = 0; cp < 7; cp++) {
@@ -504,33 +506,29 @@ struct CfWarp
                     }
                     Pb[k * CF_NX + lane - CF_NU] = s0 + s1;
                 }
-                if (lane == 17) {  // + l~x of stage k+1 (GEAD, :494)
+                if (lane >= 17) {  // + l~x of stage k+1 (GEAD, :494)
                     CF_UNROLL
                     for (int c = 0; c < CF_NX; c++) out[c] += own[CF_NU + c];
                 }
-                if (row) {
-                    CF_UNROLL
-                    for (int cp = 0; cp < 7; cp++) cf_st2(ALS + lane * 14 + 2 * cp, out[2 * cp], cp < 6 ? out[2 * cp + 1] : 0.0);
-                }
+                CF_UNROLL
+                for (int cp = 0; cp < 7; cp++) cf_st2(ALS + rl * 14 + 2 * cp, out[2 * cp], cp < 6 ? out[2 * cp + 1] : 0.0);
             }
             G[lane] = g;
             cf_syncwarp();  // ALS and G visible; all reads of the old LS are complete
             // SYRK_LN: S[r][j] = D[r][j] + sum_c AL[r][c] AL[j][c], written over this lane's row of LS
-            if (row) {
-                CF_NOUNROLL
-                for (int j = 0; j < CF_NV; j++) {
-                    double s0 = (lane == 17) ? G[j] : ((lane == j) ? hd : 0.0), s1 = 0.0;
-                    if (k < N) {
-                        const double *Aj = ALS + j * 14;
-                        CF_UNROLL
-                        for (int cp = 0; cp < 7; cp++) {
-                            const cf_d2 a2 = cf_ld2(Aj + 2 * cp);
-                            s0 += out[2 * cp] * a2.x;
-                            s1 += out[2 * cp + 1] * a2.y;
-                        }
+            CF_NOUNROLL
+            for (int j = 0; j < CF_NV; j++) {
+                double s0 = (lane >= 17) ? G[j] : ((lane == j) ? hd : 0.0), s1 = 0.0;
+                if (k < N) {
+                    const double *Aj = ALS + j * 14;
+                    CF_UNROLL
+                    for (int cp = 0; cp < 7; cp++) {
+                        const cf_d2 a2 = cf_ld2(Aj + 2 * cp);
+                        s0 += out[2 * cp] * a2.x;
+                        s1 += out[2 * cp + 1] * a2.y;
                     }
-                    own[j] = s0 + s1;
                 }
+                own[j] = s0 + s1;
             }
             cf_syncwarp();
             // POTRF_L_MN, left-looking, one column per step; non-positive pivot -> 0
@@ -549,9 +547,10 @@ struct CfWarp
                 if (j & 1) v0 -= own[j - 1] * Lj[j - 1];
                 const double v = v0 + v1;
                 const double piv = cf_shfl(v, j);
-                double dj = 0.0, inv = 0.0;
-                if (piv > 0.0) { dj = sqrt(piv); inv = 1.0 / dj; }
-                if (row) own[j] = (lane == j) ? dj : ((lane > j) ? v * inv : 0.0);
+                double dj, inv;
+                cf_sqrt_rsqrt(piv, dj, inv);
+                if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; }
+                own[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
                 cf_syncwarp();
             }
             // store the factor: LU block 18 x 4, LX packed rows + last row
