@@ -160,6 +160,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import crazyflie_nmpc_b200 as cf
+    from crazyflie_nmpc_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,7 +182,6 @@ def run_ours(args):
     d_in = {k: torch.from_numpy(w[k]).to(dev) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
     pin = {k: torch.from_numpy(w[k]).pin_memory() for k in ("x0", "yref", "yref_e")}
     u0_dev = torch.empty(B, 4, dtype=torch.float64, device=dev)
-    u0_all = torch.empty(world * B, 4, dtype=torch.float64, device=dev) if world > 1 else None
     u0_host = torch.empty(B, 4, dtype=torch.float64).pin_memory()
     st_host = torch.empty(B, dtype=torch.int32).pin_memory()
     s.set("x0", d_in["x0"]).set("yref", d_in["yref"]).set("yref_e", d_in["yref_e"])
@@ -192,7 +192,7 @@ def run_ours(args):
         s.solve(1)
         if world > 1:
             s.get("u", 0, out=u0_dev)
-            dist.all_gather_into_tensor(u0_all, u0_dev)
+            sharding.gather_u0(u0_dev, world * B)
 
     def step_e2e():
         # what a caller of the reference API does per tick, with host buffers: x0 + yref in, u0 + status out
@@ -203,7 +203,7 @@ def run_ours(args):
         u0_host.copy_(u0_dev, non_blocking=True)
         s.get("status", 0, out=st_host)   # host destination: synchronises the stream
         if world > 1:
-            dist.all_gather_into_tensor(u0_all, u0_dev)
+            sharding.gather_u0(u0_dev, world * B)
 
     def barrier():
         if world > 1:

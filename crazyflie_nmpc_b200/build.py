@@ -9,7 +9,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcfnmpc.so")
-SOURCES = ["cfnmpc_api.cu"]
+SOURCES = ["cfnmpc_api.cu", "acados_shim.cpp"]
 HEADERS = ["cf_simt.h", "cf_model.h", "cf_rti_warp.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

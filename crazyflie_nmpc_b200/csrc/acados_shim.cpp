@@ -1,0 +1,310 @@
+// Single-instance drop-in surfaces (include/acados_solver_crazyflie.h, include/acados_c/ocp_nlp_interface.h):
+// the entry points `crazyflie_controller`'s NMPC node binds, implemented as a batch of ONE instance over the
+// batch C-ABI (include/cfnmpc.h).  Host logic only; every solve is a GPU kernel launch.
+//
+// Reference behaviour mirrored here:
+//   setters copy caller arrays, getters copy out        ocp_nlp_cost_ls.c:357-361, ocp_nlp_interface.c:549-557
+//   the iterate persists between solves                  SURVEY.md fact 5
+//   initial iterate x_k = lbx_0 (= [0,0,0,1,0..]), u = 0 acados_solver.in.c:2323-2352
+//   status codes                                         acados/utils/types.h:75-83
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/acados_solver_crazyflie.h"
+#include "../../include/cfnmpc.h"
+
+struct crazyflie_solver_capsule
+{
+    cfnmpc_batch *batch = nullptr;
+    int N = 0;
+    double Ts = 0.015;
+    std::vector<double> x0, yref, yref_e, x, u;
+    bool in_dirty = true, iterate_dirty = true;
+    int status = 0, qp_iter = 0, qp_status = 0, cond_N = 0;
+    double time_tot = 0.0;
+    ocp_nlp_plan_t plan;
+    ocp_nlp_config config;
+    ocp_nlp_dims dims;
+    ocp_nlp_in in;
+    ocp_nlp_out out;
+    ocp_nlp_solver solver;
+    int opts_dummy = 0;
+};
+
+static void reset_iterate(crazyflie_solver_capsule *c)
+{
+    const int N = c->N;
+    c->x.assign((size_t) (N + 1) * 13, 0.0);
+    for (int k = 0; k <= N; k++) c->x[(size_t) k * 13 + 3] = 1.0;
+    c->u.assign((size_t) N * 4, 0.0);
+    c->iterate_dirty = true;
+}
+
+extern "C" {
+
+crazyflie_solver_capsule *crazyflie_acados_create_capsule(void) { return new crazyflie_solver_capsule(); }
+
+int crazyflie_acados_free_capsule(crazyflie_solver_capsule *c)
+{
+    delete c;
+    return 0;
+}
+
+int crazyflie_acados_free(crazyflie_solver_capsule *c)
+{
+    if (!c) return 1;
+    if (c->batch) cfnmpc_batch_destroy(c->batch);
+    c->batch = nullptr;
+    return 0;
+}
+
+int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int N, double *new_time_steps)
+{
+    if (!c || N < 1) return 1;
+    double Ts = 0.75 / 50.0;  // Tf / N of generate_c_code.py:41-42
+    if (new_time_steps) {
+        Ts = new_time_steps[0];
+        for (int i = 1; i < N; i++)
+            if (new_time_steps[i] != Ts) {
+                fprintf(stderr, "crazyflie_acados_create_with_discretization: only uniform time grids are supported\n");
+                return 1;
+            }
+    } else if (N != CRAZYFLIE_N) {
+        fprintf(stderr, "crazyflie_acados_create_with_discretization: new_time_steps is required when N != %d\n", CRAZYFLIE_N);
+        return 1;
+    }
+    crazyflie_acados_free(c);
+    if (cfnmpc_batch_create(1, N, Ts, 0, &c->batch) != CFNMPC_OK) {
+        fprintf(stderr, "crazyflie_acados_create: %s\n", cfnmpc_last_error());
+        c->batch = nullptr;
+        return 1;
+    }
+    c->N = N;
+    c->Ts = Ts;
+    // generate_c_code.py:128-129 reference, :135 x0
+    const double g0 = 9.8066, mq = 33e-3, Ct = 3.25e-4;
+    const double hov = __builtin_sqrt((mq * g0) / (4 * Ct));
+    const double y[17] = {0, 0, 0.5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, hov, hov, hov, hov};
+    c->x0.assign(13, 0.0);
+    c->x0[3] = 1.0;
+    c->yref.resize((size_t) N * 17);
+    for (int k = 0; k < N; k++) memcpy(&c->yref[(size_t) k * 17], y, sizeof y);
+    c->yref_e.assign(y, y + 13);
+    reset_iterate(c);
+    c->in_dirty = true;
+    c->plan.N = N;
+    c->config.N = N; c->config.capsule = c;
+    c->dims.N = N; c->dims.nx = 13; c->dims.nu = 4; c->dims.ny = 17; c->dims.ny_e = 13; c->dims.capsule = c;
+    c->in.capsule = c;
+    c->out.capsule = c; c->out.inf_norm_res = 0.0; c->out.total_time = 0.0;
+    c->solver.capsule = c;
+    c->cond_N = N;
+    return 0;
+}
+
+int crazyflie_acados_create(crazyflie_solver_capsule *c) { return crazyflie_acados_create_with_discretization(c, CRAZYFLIE_N, nullptr); }
+
+int crazyflie_acados_update_time_steps(crazyflie_solver_capsule *c, int N, double *new_time_steps)
+{
+    if (!c || !c->batch || N != c->N || !new_time_steps) return 1;
+    // keep inputs and iterate, rebuild the device solver with the new (uniform) step
+    std::vector<double> x0 = c->x0, yref = c->yref, yref_e = c->yref_e, x = c->x, u = c->u;
+    if (crazyflie_acados_create_with_discretization(c, N, new_time_steps)) return 1;
+    c->x0 = x0; c->yref = yref; c->yref_e = yref_e; c->x = x; c->u = u;
+    c->in_dirty = c->iterate_dirty = true;
+    return 0;
+}
+
+int crazyflie_acados_update_qp_solver_cond_N(crazyflie_solver_capsule *c, int cond_N)
+{
+    if (!c || cond_N < 1) return 1;
+    c->cond_N = cond_N;  // partial condensing changes nothing in the result for this OCP
+    return 0;
+}
+
+int crazyflie_acados_reset(crazyflie_solver_capsule *c, int)
+{
+    if (!c || !c->batch) return 1;
+    // acados_solver.in.c:2467-2520 zeroes the iterate
+    c->x.assign(c->x.size(), 0.0);
+    c->u.assign(c->u.size(), 0.0);
+    c->iterate_dirty = true;
+    return 0;
+}
+
+int crazyflie_acados_solve(crazyflie_solver_capsule *c)
+{
+    if (!c || !c->batch) return ACADOS_QP_FAILURE;
+    cfnmpc_batch *b = c->batch;
+    int rc = 0;
+    if (c->in_dirty) {
+        rc |= cfnmpc_batch_set(b, "x0", c->x0.data(), 0);
+        rc |= cfnmpc_batch_set(b, "yref", c->yref.data(), 0);
+        rc |= cfnmpc_batch_set(b, "yref_e", c->yref_e.data(), 0);
+        c->in_dirty = false;
+    }
+    if (c->iterate_dirty) {
+        rc |= cfnmpc_batch_set(b, "x", c->x.data(), 0);
+        rc |= cfnmpc_batch_set(b, "u", c->u.data(), 0);
+        c->iterate_dirty = false;
+    }
+    rc |= cfnmpc_batch_solve(b, 1);
+    rc |= cfnmpc_batch_get(b, "x_all", 0, c->x.data(), 0);
+    rc |= cfnmpc_batch_get(b, "u_all", 0, c->u.data(), 0);
+    rc |= cfnmpc_batch_get(b, "status", 0, &c->status, 0);
+    rc |= cfnmpc_batch_get(b, "qp_iter", 0, &c->qp_iter, 0);
+    rc |= cfnmpc_batch_get(b, "qp_status", 0, &c->qp_status, 0);
+    double ms = 0.0;
+    rc |= cfnmpc_batch_last_solve_ms(b, &ms);
+    if (rc) {
+        fprintf(stderr, "crazyflie_acados_solve: %s\n", cfnmpc_last_error());
+        return ACADOS_QP_FAILURE;
+    }
+    c->time_tot = ms * 1e-3;
+    c->out.total_time = c->time_tot;
+    return c->status;
+}
+
+void crazyflie_acados_print_stats(crazyflie_solver_capsule *c)
+{
+    if (!c) return;
+    printf("iter\tqp_stat\tqp_iter\n%d\t%d\t%d\n", 1, c->qp_status, c->qp_iter);
+}
+
+ocp_nlp_in *crazyflie_acados_get_nlp_in(crazyflie_solver_capsule *c) { return &c->in; }
+ocp_nlp_out *crazyflie_acados_get_nlp_out(crazyflie_solver_capsule *c) { return &c->out; }
+ocp_nlp_solver *crazyflie_acados_get_nlp_solver(crazyflie_solver_capsule *c) { return &c->solver; }
+ocp_nlp_config *crazyflie_acados_get_nlp_config(crazyflie_solver_capsule *c) { return &c->config; }
+void *crazyflie_acados_get_nlp_opts(crazyflie_solver_capsule *c) { return &c->opts_dummy; }
+ocp_nlp_dims *crazyflie_acados_get_nlp_dims(crazyflie_solver_capsule *c) { return &c->dims; }
+ocp_nlp_plan_t *crazyflie_acados_get_nlp_plan(crazyflie_solver_capsule *c) { return &c->plan; }
+
+// ------------------------------------------------------------------ acados_c subset
+int ocp_nlp_constraints_model_set(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_in *in, int stage, const char *field, void *value)
+{
+    if (!in || !in->capsule || !field || !value) return 1;
+    crazyflie_solver_capsule *c = in->capsule;
+    if (!strcmp(field, "lbx") || !strcmp(field, "ubx")) {
+        if (stage != 0) return 1;
+        memcpy(c->x0.data(), value, 13 * sizeof(double));  // lbx_0 = ubx_0 = measured state (acados_mpc.cpp:581-582)
+        c->in_dirty = true;
+        return 0;
+    }
+    if (!strcmp(field, "lbu") || !strcmp(field, "ubu")) {
+        if (stage < 0 || stage >= c->N || !c->batch) return 1;
+        return cfnmpc_batch_set(c->batch, field, value, 0) != CFNMPC_OK;
+    }
+    return 1;
+}
+
+int ocp_nlp_cost_model_set(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_in *in, int stage, const char *field, void *value)
+{
+    if (!in || !in->capsule || !field || !value) return 1;
+    crazyflie_solver_capsule *c = in->capsule;
+    if (stage < 0 || stage > c->N) return 1;
+    if (!strcmp(field, "yref") || !strcmp(field, "y_ref")) {
+        if (stage < c->N) memcpy(&c->yref[(size_t) stage * 17], value, 17 * sizeof(double));
+        else memcpy(c->yref_e.data(), value, 13 * sizeof(double));
+        c->in_dirty = true;
+        return 0;
+    }
+    if (!strcmp(field, "W")) {
+        // column-major ny x ny as the node fills it (acados_mpc.cpp:526-542); only diagonal weights are supported
+        const int n = stage < c->N ? 17 : 13;
+        const double *W = static_cast<const double *>(value);
+        double d[17];
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                if (i == j) d[i] = W[i + n * j];
+                else if (W[i + n * j] != 0.0) return 1;
+            }
+        if (!c->batch) return 1;
+        return cfnmpc_batch_set(c->batch, stage < c->N ? "W" : "W_e", d, 0) != CFNMPC_OK;
+    }
+    return 1;
+}
+
+void ocp_nlp_out_set(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_out *out, int stage, const char *field, void *value)
+{
+    if (!out || !out->capsule || !field || !value) return;
+    crazyflie_solver_capsule *c = out->capsule;
+    if (!strcmp(field, "x") && stage >= 0 && stage <= c->N) memcpy(&c->x[(size_t) stage * 13], value, 13 * sizeof(double));
+    else if (!strcmp(field, "u") && stage >= 0 && stage < c->N) memcpy(&c->u[(size_t) stage * 4], value, 4 * sizeof(double));
+    else return;
+    c->iterate_dirty = true;
+}
+
+void ocp_nlp_out_get(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_out *out, int stage, const char *field, void *value)
+{
+    if (!out || !out->capsule || !field || !value) return;
+    crazyflie_solver_capsule *c = out->capsule;
+    if (!strcmp(field, "x") && stage >= 0 && stage <= c->N) memcpy(value, &c->x[(size_t) stage * 13], 13 * sizeof(double));
+    else if (!strcmp(field, "u") && stage >= 0 && stage < c->N) memcpy(value, &c->u[(size_t) stage * 4], 4 * sizeof(double));
+}
+
+void ocp_nlp_solver_opts_set(ocp_nlp_config *config, void *, const char *field, void *value)
+{
+    if (!config || !config->capsule || !field || !value) return;
+    if (!strcmp(field, "qp_cond_N")) config->capsule->cond_N = *static_cast<int *>(value);
+    else if (!strcmp(field, "rti_phase") && *static_cast<int *>(value) != 0)
+        fprintf(stderr, "ocp_nlp_solver_opts_set: rti_phase %d is not supported (preparation and feedback are fused)\n",
+                *static_cast<int *>(value));
+}
+
+int ocp_nlp_solve(ocp_nlp_solver *solver, ocp_nlp_in *, ocp_nlp_out *)
+{
+    if (!solver || !solver->capsule) return ACADOS_QP_FAILURE;
+    return crazyflie_acados_solve(solver->capsule);
+}
+
+void ocp_nlp_get(ocp_nlp_config *, ocp_nlp_solver *solver, const char *field, void *ret)
+{
+    if (!solver || !solver->capsule || !field || !ret) return;
+    crazyflie_solver_capsule *c = solver->capsule;
+    if (!strcmp(field, "time_tot") || !strcmp(field, "tot_time")) *static_cast<double *>(ret) = c->time_tot;
+    else if (!strcmp(field, "qp_iter")) *static_cast<int *>(ret) = c->qp_iter;
+    else if (!strcmp(field, "sqp_iter")) *static_cast<int *>(ret) = 1;
+    else if (!strcmp(field, "status")) *static_cast<int *>(ret) = c->status;
+    else if (!strcmp(field, "qp_status")) *static_cast<int *>(ret) = c->qp_status;
+}
+
+// ------------------------------------------------------------------ legacy surface (process globals)
+__attribute__((weak)) ocp_nlp_in *nlp_in;
+__attribute__((weak)) ocp_nlp_out *nlp_out;
+__attribute__((weak)) ocp_nlp_solver *nlp_solver;
+__attribute__((weak)) void *nlp_opts;
+__attribute__((weak)) ocp_nlp_plan *nlp_solver_plan;
+__attribute__((weak)) ocp_nlp_config *nlp_config;
+__attribute__((weak)) ocp_nlp_dims *nlp_dims;
+static crazyflie_solver_capsule *g_capsule = nullptr;
+
+int acados_create(void)
+{
+    if (g_capsule) acados_free();
+    g_capsule = crazyflie_acados_create_capsule();
+    if (crazyflie_acados_create(g_capsule)) {
+        crazyflie_acados_free_capsule(g_capsule);
+        g_capsule = nullptr;
+        return 1;
+    }
+    nlp_in = &g_capsule->in; nlp_out = &g_capsule->out; nlp_solver = &g_capsule->solver;
+    nlp_opts = &g_capsule->opts_dummy; nlp_solver_plan = &g_capsule->plan; nlp_config = &g_capsule->config;
+    nlp_dims = &g_capsule->dims;
+    return 0;
+}
+
+int acados_solve(void) { return g_capsule ? crazyflie_acados_solve(g_capsule) : ACADOS_QP_FAILURE; }
+
+int acados_free(void)
+{
+    if (!g_capsule) return 0;
+    crazyflie_acados_free(g_capsule);
+    crazyflie_acados_free_capsule(g_capsule);
+    g_capsule = nullptr;
+    nlp_in = nullptr; nlp_out = nullptr; nlp_solver = nullptr; nlp_opts = nullptr; nlp_solver_plan = nullptr;
+    nlp_config = nullptr; nlp_dims = nullptr;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,6 @@
+/* Source-compatibility stub.  The reference node includes this path
+ * (crazyflie_controller/src/acados_mpc.cpp:61-73) but uses nothing from it on the NMPC path;
+ * the drop-in library has no BLASFEO / module-level objects to expose. */
+#ifndef CFNMPC_STUB_ACADOS_OCP_NLP_OCP_NLP_CONSTRAINTS_BGH_H
+#define CFNMPC_STUB_ACADOS_OCP_NLP_OCP_NLP_CONSTRAINTS_BGH_H
+#endif

@@ -1,0 +1,113 @@
+"""Drop-in boundary: the node's own call sequence against the shipped headers and library.
+
+CPU part: tests/dropin/node_sequence.cpp -- written like NMPC::iteration() of the reference
+(crazyflie_controller/src/acados_mpc.cpp:61-84,427-718) -- compiles and links against include/ and
+libcfnmpc.so, and fails loudly without a GPU.  GPU part: its printed u0/u1/x4 match the oracle.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import crazyflie_nmpc_b200 as cf
+from crazyflie_nmpc_b200 import workloads as wl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "dropin", "node_sequence.cpp")
+EXE = os.path.join(ROOT, "tests", "dropin", "node_sequence")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    cf.lib()
+    subprocess.run(["g++", "-O1", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
+                    "-L", os.path.join(ROOT, "crazyflie_nmpc_b200"), "-lcfnmpc",
+                    "-Wl,-rpath," + os.path.join(ROOT, "crazyflie_nmpc_b200")], check=True)
+    return EXE
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_node_sequence_compiles_links_and_fails_loudly_without_gpu(exe):
+    if _has_gpu():
+        pytest.skip("GPU present")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 3 and "acados_create() returned status" in r.stderr
+
+
+@pytest.mark.gpu
+def test_node_sequence_matches_oracle(exe, port):
+    ticks, N, TS = 4, 50, 0.015
+    r = subprocess.run([exe, str(ticks)], capture_output=True, text=True, check=True)
+    rows = [l.split() for l in r.stdout.splitlines() if l.startswith("tick")]
+    assert len(rows) == ticks
+    x0 = np.array([0.1, -0.05, 0.3, 1, 0, 0, 0, 0.1, 0, -0.1, 0, 0, 0])
+    w = wl.single_hover(N, template_iterate=True, node_yref=True, x0=x0)
+    x, u = w["x_init"][0].copy(), w["u_init"][0].copy()
+    for t, row in enumerate(rows):
+        st, info = port.rti(N, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], x, u)
+        vals = np.array(row[6:], float)
+        assert int(row[3]) == st
+        assert np.abs(vals[0:4] - u[0]).max() < 1e-7 and np.abs(vals[4:8] - u[1]).max() < 1e-7
+        assert np.abs(vals[8:21] - x[4]).max() < 1e-7
+        assert float(row[5]) > 0.0     # nlp_out->total_time is filled (acados_mpc.cpp:616)
+
+
+@pytest.mark.gpu
+def test_capsule_api_through_ctypes(port):
+    """Surface B: crazyflie_acados_* with a non-default horizon via create_with_discretization."""
+    import ctypes
+    L = cf.lib()
+    vp, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)
+    L.crazyflie_acados_create_capsule.restype = vp
+    for f in ("crazyflie_acados_get_nlp_in", "crazyflie_acados_get_nlp_out", "crazyflie_acados_get_nlp_config",
+              "crazyflie_acados_get_nlp_dims", "crazyflie_acados_get_nlp_solver"):
+        getattr(L, f).restype = vp
+        getattr(L, f).argtypes = [vp]
+    L.crazyflie_acados_create_with_discretization.argtypes = [vp, ctypes.c_int, dp]
+    L.crazyflie_acados_solve.argtypes = [vp]
+    L.crazyflie_acados_free.argtypes = [vp]
+    L.crazyflie_acados_free_capsule.argtypes = [vp]
+    L.ocp_nlp_constraints_model_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_cost_model_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_out_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_out_get.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_get.argtypes = [vp, vp, ctypes.c_char_p, vp]
+    N, TS = 20, 0.015
+    w = wl.helix_batch(1, N, seed=5)
+    cap = L.crazyflie_acados_create_capsule()
+    steps = (ctypes.c_double * N)(*([TS] * N))
+    assert L.crazyflie_acados_create_with_discretization(cap, N, steps) == 0
+    cfg, dims, nin, nout, sol = (L.crazyflie_acados_get_nlp_config(cap), L.crazyflie_acados_get_nlp_dims(cap),
+                                 L.crazyflie_acados_get_nlp_in(cap), L.crazyflie_acados_get_nlp_out(cap),
+                                 L.crazyflie_acados_get_nlp_solver(cap))
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"lbx", P(w["x0"][0])) == 0
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"ubx", P(w["x0"][0])) == 0
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"bogus", P(w["x0"][0])) != 0
+    for k in range(N):
+        assert L.ocp_nlp_cost_model_set(cfg, dims, nin, k, b"yref", P(w["yref"][0, k])) == 0
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"u", P(w["u_init"][0, k]))
+    assert L.ocp_nlp_cost_model_set(cfg, dims, nin, N, b"yref", P(w["yref_e"][0])) == 0
+    for k in range(N + 1):
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"x", P(w["x_init"][0, k]))
+    assert L.crazyflie_acados_solve(cap) == 0
+    x, u = np.zeros((N + 1, 13)), np.zeros((N, 4))
+    for k in range(N + 1):
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"x", P(x[k]))
+    for k in range(N):
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"u", P(u[k]))
+    qi = ctypes.c_int()
+    L.ocp_nlp_get(cfg, sol, b"qp_iter", ctypes.byref(qi))
+    xo, uo = w["x_init"][0].copy(), w["u_init"][0].copy()
+    st, info = port.rti(N, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], xo, uo)
+    assert np.abs(x - xo).max() < 1e-8 and np.abs(u - uo).max() < 1e-8 and abs(qi.value - info.qp_iter) <= 1
+    L.crazyflie_acados_free(cap)
+    L.crazyflie_acados_free_capsule(cap)

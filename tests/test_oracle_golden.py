@@ -1,0 +1,142 @@
+"""The oracles against the golden vectors minted by the reference's own implementation.
+
+tests/golden/crazyflie_rti_golden.npz was produced by tests/golden/make_golden.py with
+oracle/_ref/libcfref.so = acados + HPIPM + BLASFEO compiled from /root/reference.  These tests pin
+the plain-C restatement (oracle/cfnmpc_oracle.c) to it on any machine, and re-check the reference
+library itself where it is available.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from crazyflie_nmpc_b200 import workloads as wl
+from conftest import rel_err
+
+TS = 0.015
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "crazyflie_rti_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def batch(gold, name):
+    return {k: gold[f"{name}_{k}"] for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
+
+
+def test_known_answer_sequence_matches_survey_values(gold):
+    """Values reproduced by the survey with an independent build of the reference."""
+    ka = gold["ka_seq"]
+    assert (ka[:, 0] == 0).all()
+    assert list(ka[:5, 1].astype(int)) == [6, 7, 5, 4, 4]
+    assert abs(ka[0, 2] - 15.777730167250) < 5e-13
+    assert abs(ka[1, 2] - 21.999999999667) < 5e-13
+    assert abs(ka[2, 2] - 22.0) < 5e-13
+    assert abs(ka[3, 2] - 21.999999997941) < 5e-13
+    assert abs(ka[0, 6 + 2] + 0.0011032425) < 5e-13        # x1.z
+    assert abs(ka[0, 19 + 2] + 0.01765188) < 5e-11         # x4.z
+    assert abs(ka[0, 19 + 9] + 0.588396) < 5e-9            # x4.vbz
+
+
+def test_port_oracle_known_answer_sequence(port, gold):
+    N = 50
+    w = wl.single_hover(N)
+    x, u = w["x_init"][0].copy(), w["u_init"][0].copy()
+    for r in range(6):
+        st, info = port.rti(N, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], x, u)
+        row = gold["ka_seq"][r]
+        assert st == row[0] and info.qp_iter == row[1] and info.n_lq_flag == 0 and info.n_itref == 0
+        assert np.abs(u[0] - row[2:6]).max() < 1e-10
+        assert np.abs(x[1] - row[6:19]).max() < 1e-11 and np.abs(x[4] - row[19:32]).max() < 1e-11
+    assert rel_err(x, gold["ka_x_final"]) < 1e-10 and rel_err(u, gold["ka_u_final"]) < 1e-10
+
+
+@pytest.mark.parametrize("name,N", [("hover", 50), ("helix", 50), ("hover20", 20), ("hover100", 100)])
+def test_port_oracle_batches(port, gold, name, N):
+    w = batch(gold, name)
+    x, u = w["x_init"].copy(), w["u_init"].copy()
+    st, it = port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u)
+    assert (st == gold[f"{name}_status"]).all() and (it == gold[f"{name}_qp_iter"]).all()
+    assert rel_err(x, gold[f"{name}_x"]) < 1e-11 and rel_err(u, gold[f"{name}_u"]) < 1e-11
+    if f"{name}_x5" in gold:
+        x, u = w["x_init"].copy(), w["u_init"].copy()
+        port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u, n_rti=5)
+        # five steps with frozen inputs: consecutive calls move active-bound controls by ~2e-9
+        assert rel_err(x, gold[f"{name}_x5"]) < 1e-7 and rel_err(u, gold[f"{name}_u5"]) < 1e-7
+
+
+def test_port_oracle_config1(port, gold):
+    N = 50
+    for c in range(int(gold["cfg1_count"])):
+        w = {k: gold[f"cfg1_{c}_{k}"] for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
+        for n_rti in (1, 5):
+            x, u = w["x_init"].copy(), w["u_init"].copy()
+            port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u, n_rti=n_rti)
+            tol = 1e-11 if n_rti == 1 else 1e-7
+            assert rel_err(x, gold[f"cfg1_{c}_x{n_rti}"]) < tol and rel_err(u, gold[f"cfg1_{c}_u{n_rti}"]) < tol
+
+
+def test_port_oracle_qp_intermediates(port, gold):
+    """BAbt, b, rqz, d and the QP step against the reference's qp_in / qp_out (1e-11 relative)."""
+    N = 50
+    w = batch(gold, "hover")
+    lin = port.linearize(N, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], w["x_init"][0], w["u_init"][0])
+    for k in ("BAbt", "b", "rqz", "d_lb", "d_ub"):
+        ref = gold[f"qp_{k}"]
+        assert np.abs(lin[k] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), k
+    x, u = w["x_init"][0].copy(), w["u_init"][0].copy()
+    st, info, dux, dpi = port.rti(N, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], x, u, want_step=True)
+    assert np.abs(dux - gold["qp_dux"]).max() < 1e-10 and rel_err(dpi, gold["qp_dpi"]) < 1e-10
+    stat = gold["qp_ipm_stat"]
+    assert info.qp_iter == stat.shape[0] - 1
+    assert (stat[1:, 11] == 0).all() and (stat[1:, 13] == 0).all()   # no LQ refactorisation, no refinement solve
+    assert abs(info.res[0] - stat[-1, 6]) < 1e-9 and abs(info.res[3] - stat[-1, 9]) < 1e-12
+
+
+def test_port_oracle_runtime_weights_and_bounds(port, gold):
+    N = 50
+    w = {k: v[:4] for k, v in batch(gold, "hover").items()}
+    p = port.params(Wdiag=gold["par_W"], WNdiag=gold["par_WN"], lbu=gold["par_lbu"], ubu=gold["par_ubu"])
+    x, u = w["x_init"].copy(), w["u_init"].copy()
+    port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u, params=p)
+    assert rel_err(x, gold["par_x"]) < 1e-11 and rel_err(u, gold["par_u"]) < 1e-11
+
+
+def test_reference_library_reproduces_golden(ref, gold):
+    """Where oracle/_ref is built, the golden file is reproducible bit-for-bit-ish."""
+    w = batch(gold, "helix")
+    x, u = w["x_init"].copy(), w["u_init"].copy()
+    st, it, _ = ref.batch(50, TS, w["x0"], w["yref"], w["yref_e"], x, u, nthreads=2)
+    assert (it == gold["helix_qp_iter"]).all()
+    assert rel_err(x, gold["helix_x"]) < 1e-13 and rel_err(u, gold["helix_u"]) < 1e-13
+    # partial condensing is a pure optimisation knob for this OCP: identical results
+    x2, u2 = w["x_init"].copy(), w["u_init"].copy()
+    ref.batch(50, TS, w["x0"], w["yref"], w["yref_e"], x2, u2, nthreads=2, cond_N=10)
+    assert rel_err(x2, x) < 1e-8 and rel_err(u2, u) < 1e-8
+
+
+def test_model_jacobian_against_finite_differences(port):
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        x = rng.normal(size=13) * 0.5
+        x[3:7] /= np.linalg.norm(x[3:7])
+        u = wl.hover_speed() + rng.uniform(-1, 1, 4)
+        xn, A, B = port.erk4(x, u, TS)
+        h = 1e-6
+        for j in range(13):
+            e = np.zeros(13); e[j] = h
+            fd = (port.erk4(x + e, u, TS)[0] - port.erk4(x - e, u, TS)[0]) / (2 * h)
+            assert np.abs(fd - A[:, j]).max() < 1e-7
+        for j in range(4):
+            e = np.zeros(4); e[j] = h
+            fd = (port.erk4(x, u + e, TS)[0] - port.erk4(x, u - e, TS)[0]) / (2 * h)
+            assert np.abs(fd - B[:, j]).max() < 1e-6
+        # one RK4 step against 64 substeps of the same scheme (truncation error of the 15 ms grid)
+        assert np.abs(port.sim(x, u, TS, 64) - xn).max() < 1e-6
+        assert np.abs(port.sim(x, u, TS, 1) - xn).max() < 1e-15
+    # hover is an equilibrium of the model with the model's own gravity constant
+    uss = wl.hover_speed()
+    f = port.ode(np.array([0, 0, 0.5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.]), np.full(4, uss))
+    assert np.abs(f).max() < 1e-12
