@@ -124,17 +124,18 @@ static inline
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
 #define CF_SM_MS0 0                            // [B';A';res_b']_k staging, double buffered
 #define CF_SM_MS1 CF_MSZ
-#define CF_SM_W (2 * CF_MSZ)                            // 576-double work region:
+#define CF_SM_W (2 * CF_MSZ)                   // 684-double work region:
 #define CF_SM_LS CF_SM_W                       //   factorisation: 18 x 18 factor rows (stride 18) ...
-#define CF_SM_ALS (CF_SM_W + 324)              //   ... and 18 x 14 AL rows (stride 14)
+#define CF_SM_ALS (CF_SM_W + 324)              //   ... and 18 x 20 AL rows (stride 20: conflict-free DMMA fragment loads)
+#define CF_ALST 20
 #define CF_SM_LB0 CF_SM_W                      //   sweeps: factor block staging [LU 72 | LX 104], double buffered
 #define CF_SM_LB1 (CF_SM_W + CF_LFSZ)
-#define CF_SM_V0 (CF_SM_W + 576)               // four 32-double broadcast vectors
+#define CF_SM_V0 (CF_SM_W + 324 + 18 * CF_ALST) // four 32-double broadcast vectors
 #define CF_SM_V1 (CF_SM_V0 + 32)
 #define CF_SM_V2 (CF_SM_V1 + 32)
 #define CF_SM_V3 (CF_SM_V2 + 32)
 #define CF_SM_BAR (CF_SM_V3 + 32)              // two mbarriers
-#define CF_SM_DOUBLES (CF_SM_BAR + 4)          // 1176 doubles = 9408 bytes per warp (6 blocks of 4 warps per SM)
+#define CF_SM_DOUBLES (CF_SM_BAR + 4)          // 1284 doubles = 10272 bytes per warp (5 blocks of 4 warps per SM)
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
@@ -451,20 +452,19 @@ struct CfWarp
     // The factor rows of the stage just finished stay in shared memory (LS) for the next TRMM.
     CF_MEM void factorize()
     {
-        double *LS = sm + CF_SM_LS, *ALS = sm + CF_SM_ALS, *V = sm + CF_SM_V0, *G = sm + CF_SM_V1;
+        double *LS = sm + CF_SM_LS, *ALS = sm + CF_SM_ALS, *V = sm + CF_SM_V0, *G = sm + CF_SM_V1, *HD = sm + CF_SM_V2;
         pass_begin();
         if (N > 0) fetch(0, N - 1, -1, -1);
         for (int i = lane; i < 18 * 18; i += 32) LS[i] = 0.0;
-        // lanes 17..31 all act as row 17 (they compute and store identical values), so the dense
-        // loops below run without lane predicates
+        // lanes 17..31 all act as row 17 (they compute and store identical values), so the Cholesky
+        // loop below runs without lane predicates
         const bool row = lane < CF_MROWS;
         const int rl = lane < 17 ? lane : 17;
         double *own = LS + rl * 18;
+        // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
+        const int fg = lane >> 2, fq = lane & 3;
         CF_NOUNROLL
         for (int k = N; k >= 0; k--) {
-            double out[CF_NX + 1];
-            CF_UNROLL
-            for (int c = 0; c <= CF_NX; c++) out[c] = 0.0;
             // gradient row and diagonal of the stage Hessian; bound data are independent of the matrices
             double Gam = 0.0, gam = 0.0;
             if (lane < CF_NU && k < N) bound_terms(k, 0, 0.0, Gam, gam);
@@ -473,26 +473,48 @@ struct CfWarp
             if (k < N) {
                 const int bf = (N - 1 - k) & 1;
                 wait(bf);
-                cf_syncwarp();  // every lane is done with buffer bf^1 and with V/G of the previous stage
+                cf_syncwarp();  // every lane is done with buffer bf^1 and with V/G/HD of the previous stage
                 if (k > 0) fetch(bf ^ 1, k - 1, -1, -1);
                 const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
-                // TRMM_RLNN: out[c] = sum_{j>=c} M[r][j] * Lxx[j][c]; the strict upper part of LS is kept
-                // zero so whole 128-bit pairs can be used
-                CF_NOUNROLL
-                for (int j = 0; j < CF_NX; j++) {
-                    const double mj = Mk[j * CF_MROWS + rl];
-                    const double *Lj = LS + (CF_NU + j) * 18 + CF_NU;
+                G[lane] = g;
+                HD[lane] = hd;
+                // ---- TRMM_RLNN on the fp64 tensor cores: AL(18x13) = [B';A';res_b'](18x13) * Lxx(13x13, lower).
+                // Row tiles t = 0..2 (rows 8t+fg), column tiles 0..1 (columns 8t'+2fq+{0,1}), K padded to 16.
+                // Lxx is lower triangular: for column tile 1 (n >= 8) only k >= 8 contributes.
+                double al[3][2][2];
+                CF_UNROLL
+                for (int t = 0; t < 3; t++) { al[t][0][0] = al[t][0][1] = al[t][1][0] = al[t][1][1] = 0.0; }
+                CF_UNROLL
+                for (int kk = 0; kk < 4; kk++) {
+                    const int kc = 4 * kk + fq;                 // k index: column of M, row of Lxx
+                    const bool kv = kc < CF_NX;
+                    const double *Lk = LS + (CF_NU + (kv ? kc : 0)) * 18 + CF_NU;
+                    const double b0 = kv ? Lk[fg] : 0.0;       // Lxx[kc][fg]
+                    const double b1 = (kk >= 2 && kv && fg < CF_NX - 8) ? Lk[8 + fg] : 0.0;   // Lxx[kc][8+fg]
                     CF_UNROLL
-                    for (int cp = 0; cp < 7; cp++) {
-                        if (2 * cp > j) break;
-                        const cf_d2 l2 = cf_ld2(Lj + 2 * cp);
-                        out[2 * cp] += mj * l2.x;
-                        out[2 * cp + 1] += mj * l2.y;
+                    for (int t = 0; t < 3; t++) {
+                        const int r = 8 * t + fg;
+                        const double a = (kv && r < CF_MROWS) ? Mk[kc * CF_MROWS + r] : 0.0;
+                        cf_dmma(al[t][0][0], al[t][0][1], a, b0);
+                        if (kk >= 2) cf_dmma(al[t][1][0], al[t][1][1], a, b1);
                     }
                 }
-                if (lane == 17) {
-                    CF_UNROLL
-                    for (int cp = 0; cp < 7; cp++) cf_st2(V + 2 * cp, out[2 * cp], cp < 6 ? out[2 * cp + 1] : 0.0);
+                // row 17 (tile 2, fg == 1): V = res_b' Lxx for Pb, then + l~x of stage k+1 (GEAD, :494)
+                if (fg == 1) {
+                    cf_st2(V + 2 * fq, al[2][0][0], al[2][0][1]);
+                    cf_st2(V + 8 + 2 * fq, al[2][1][0], al[2][1][1]);
+                    const double *lt = LS + 17 * 18 + CF_NU;
+                    al[2][0][0] += lt[2 * fq]; al[2][0][1] += lt[2 * fq + 1];
+                    if (8 + 2 * fq < CF_NX) al[2][1][0] += lt[8 + 2 * fq];
+                    if (9 + 2 * fq < CF_NX) al[2][1][1] += lt[9 + 2 * fq];
+                }
+                CF_UNROLL
+                for (int t = 0; t < 3; t++) {
+                    const int r = 8 * t + fg;
+                    if (r < CF_MROWS) {
+                        cf_st2(ALS + r * CF_ALST + 2 * fq, al[t][0][0], al[t][0][1]);
+                        cf_st2(ALS + r * CF_ALST + 8 + 2 * fq, al[t][1][0], al[t][1][1]);
+                    }
                 }
                 cf_syncwarp();
                 // Pb = Lxx * (Lxx' res_b)  (TRMV_LNN, :492-493): lane 4+i uses its own factor row
@@ -506,29 +528,38 @@ struct CfWarp
                     }
                     Pb[k * CF_NX + lane - CF_NU] = s0 + s1;
                 }
-                if (lane >= 17) {  // + l~x of stage k+1 (GEAD, :494)
-                    CF_UNROLL
-                    for (int c = 0; c < CF_NX; c++) out[c] += own[CF_NU + c];
-                }
+                // ---- SYRK_LN on the tensor cores: S = D + AL * AL'; the same fragment serves as A and as B
+                double fr[3][4];
                 CF_UNROLL
-                for (int cp = 0; cp < 7; cp++) cf_st2(ALS + rl * 14 + 2 * cp, out[2 * cp], cp < 6 ? out[2 * cp + 1] : 0.0);
-            }
-            G[lane] = g;
-            cf_syncwarp();  // ALS and G visible; all reads of the old LS are complete
-            // SYRK_LN: S[r][j] = D[r][j] + sum_c AL[r][c] AL[j][c], written over this lane's row of LS
-            CF_NOUNROLL
-            for (int j = 0; j < CF_NV; j++) {
-                double s0 = (lane >= 17) ? G[j] : ((lane == j) ? hd : 0.0), s1 = 0.0;
-                if (k < N) {
-                    const double *Aj = ALS + j * 14;
+                for (int t = 0; t < 3; t++) {
+                    const int r = 8 * t + fg;
                     CF_UNROLL
-                    for (int cp = 0; cp < 7; cp++) {
-                        const cf_d2 a2 = cf_ld2(Aj + 2 * cp);
-                        s0 += out[2 * cp] * a2.x;
-                        s1 += out[2 * cp + 1] * a2.y;
+                    for (int kk = 0; kk < 4; kk++) fr[t][kk] = (r < CF_MROWS) ? ALS[r * CF_ALST + 4 * kk + fq] : 0.0;
+                }
+                cf_syncwarp();  // all reads of the old factor rows (TRMM, Pb) are complete: LS may be overwritten
+                CF_UNROLL
+                for (int t = 0; t < 3; t++) {
+                    CF_UNROLL
+                    for (int tp = 0; tp <= t; tp++) {
+                        double s0 = 0.0, s1 = 0.0;
+                        CF_UNROLL
+                        for (int kk = 0; kk < 4; kk++) cf_dmma(s0, s1, fr[t][kk], fr[tp][kk]);
+                        const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
+                        if (r == 17) { s0 += G[c0 < 17 ? c0 : 0]; s1 += G[c0 + 1 < 17 ? c0 + 1 : 0]; }
+                        if (r == c0) s0 += HD[r];
+                        if (r == c0 + 1) s1 += HD[r];
+                        if (r < CF_MROWS) {
+                            if (tp < 2) cf_st2(LS + r * 18 + c0, s0, s1);
+                            else if (fq == 0) LS[r * 18 + 16] = s0;   // column 16; column 17 is padding and stays 0
+                        }
                     }
                 }
-                own[j] = s0 + s1;
+            } else {
+                // terminal stage: no dynamics, S = [diag(H) ; g']
+                G[lane] = g;
+                cf_syncwarp();
+                CF_NOUNROLL
+                for (int j = 0; j < CF_NV; j++) own[j] = (lane >= 17) ? G[j] : ((lane == j) ? hd : 0.0);
             }
             cf_syncwarp();
             // POTRF_L_MN, left-looking, one column per step; non-positive pivot -> 0

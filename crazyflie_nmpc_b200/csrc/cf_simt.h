@@ -34,6 +34,7 @@ void bulk_g2s(void *dst, const void *src, int bytes, uint64_t *bar, int line);
 void bulk_wait(uint64_t *bar, unsigned parity, int line);
 void bulk_s2g(void *dst, const void *src, int bytes, int line);
 void bulk_s2g_wait(int max_pending, int line);
+void dmma(double &d0, double &d1, double a, double b, int line);
 }  // namespace cfemu
 CF_DEV int cf_lane() { return cfemu::lane(); }
 #define cf_syncwarp() cfemu::barrier(__LINE__)
@@ -59,6 +60,7 @@ CF_DEV double cf_rsqrt_seed(double x) { return (double) (float) (1.0 / sqrt(x));
 #define cf_bulk_s2g_wait_all() cfemu::bulk_s2g_wait(0, __LINE__)
 #define cf_bulk_s2g_wait_read1() cfemu::bulk_s2g_wait(1, __LINE__)
 CF_DEV void cf_fence_proxy_async() {}
+#define cf_dmma(d0, d1, a, b) cfemu::dmma((d0), (d1), (a), (b), __LINE__)
 #else
 // ---------------------------------------------------------------- CUDA (sm_100a)
 #define CF_DEV __device__ __forceinline__
@@ -127,6 +129,12 @@ CF_DEV void cf_bulk_s2g(void *dst, const void *src, int bytes)
 CF_DEV void cf_bulk_s2g_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // Issuing lane: all but the most recent bulk store have finished READING their shared source.
 CF_DEV void cf_bulk_s2g_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// fp64 tensor-core tile product D(8x8) += A(8x4) * B(4x8), fragments as in the PTX ISA for m8n8k4:
+// a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], d0/d1 = D[lane>>2][2*(lane&3) + {0,1}]   (SASS DMMA)
+CF_DEV void cf_dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 // Order earlier generic-proxy accesses before later async-proxy (TMA) accesses.
 CF_DEV void cf_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 #endif

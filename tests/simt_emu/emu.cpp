@@ -143,6 +143,24 @@ void bulk_s2g_wait(int max_pending, int line)
     }
 }
 
+// fp64 mma.sync.m8n8k4: every lane publishes its A and B fragment element, then computes its two outputs
+static thread_local double g_fa[32], g_fb[32];
+void dmma(double &d0, double &d1, double a, double b, int line)
+{
+    Warp *w = W;
+    g_fa[w->cur] = a; g_fb[w->cur] = b;
+    barrier(line);
+    const int g = w->cur >> 2, q = w->cur & 3;
+    double s0 = d0, s1 = d1;
+    for (int k = 0; k < 4; k++) {
+        const double A = g_fa[g * 4 + k];
+        s0 = std::fma(A, g_fb[(2 * q) * 4 + k], s0);
+        s1 = std::fma(A, g_fb[(2 * q + 1) * 4 + k], s1);
+    }
+    barrier(-line);
+    d0 = s0; d1 = s1;
+}
+
 static void trampoline()
 {
     Warp *w = W;
