@@ -202,16 +202,21 @@ struct CfWarp
     // ERK4 with forward sensitivities for stage k; lane c pushes sensitivity column c
     // ([Su(4) | Sx(13)] -> rows of [B';A']), the nominal state is advanced once per warp in
     // shared memory.  Writes M_k (rows 0..16 + b row) by bulk store, b_k, rq_k, d_k.
-    CF_MEM void linearize_stage(int k, const double *xg, const double *ug, const double *x0g, const double *yrefg)
+    CF_MEM void linearize_stage(int k, const double *xg, const double *ug, const double *x0g, const double *yrefg,
+                                double &xk_pre, double &uk_pre)
     {
         double *X0 = sm + CF_SM_V0, *ACC = sm + CF_SM_V1, *XS = sm + CF_SM_V2, *UU = sm + CF_SM_V3;
         double *MS = sm + ((k & 1) ? CF_SM_MS1 : CF_SM_MS0);
         const double h = P->Ts;
         cf_syncwarp();
-        if (lane < CF_NX) { double v = xg[k * CF_NX + lane]; X0[lane] = v; ACC[lane] = v; XS[lane] = v; }
-        if (lane < CF_NU) UU[lane] = ug[k * CF_NU + lane];
+        if (lane < CF_NX) { const double v = xk_pre; X0[lane] = v; ACC[lane] = v; XS[lane] = v; }
+        if (lane < CF_NU) UU[lane] = uk_pre;
         if (lane == 0) cf_bulk_s2g_wait_read1();  // the bulk store that last read this MS buffer (stage k-2) is done
         cf_syncwarp();
+        // software prefetch: x_{k+1} (needed for b_k and as the next stage's state), u_{k+1}, and this stage's reference
+        const double xn_pre = (lane < CF_NX) ? xg[(k + 1) * CF_NX + lane] : 0.0;
+        const double un_pre = (lane < CF_NU && k + 1 < N) ? ug[(k + 1) * CF_NU + lane] : 0.0;
+        const double yr_pre = (lane < CF_NU) ? yrefg[k * CF_NY + CF_NX + lane] : ((lane < CF_NV) ? yrefg[k * CF_NY + lane - CF_NU] : 0.0);
         double uu[CF_NU];
         CF_UNROLL
         for (int i = 0; i < CF_NU; i++) uu[i] = UU[i];
@@ -246,9 +251,12 @@ struct CfWarp
             cf_syncwarp();
         }
         // lane 17: b_k = phi(x_k,u_k) - x_{k+1}   (ocp_nlp_dynamics_cont.c:822-823)
+        cf_syncwarp();
+        if (lane < CF_NX) XS[lane] = xn_pre;   // broadcast x_{k+1} to lane 17 (XS is free after the last RK stage)
+        cf_syncwarp();
         if (lane == 17) {
             CF_UNROLL
-            for (int i = 0; i < CF_NX; i++) acc[i] = ACC[i] - xg[(k + 1) * CF_NX + i];
+            for (int i = 0; i < CF_NX; i++) acc[i] = ACC[i] - XS[i];
         }
         if (k == 0) {
             // x0 elimination (x_ocp_qp_red.c:310-330): xbar = lbx - x_0 ; b_0 += A_0 xbar ; drop the A rows
@@ -272,8 +280,8 @@ struct CfWarp
         // gradient: scaling * W * (y - yref), [u;x] order (ocp_nlp_cost_ls.c:883-912)
         if (lane < CF_NV) {
             double g;
-            if (lane < CF_NU) g = (P->Wdiag[CF_NX + lane] * (UU[lane] - yrefg[k * CF_NY + CF_NX + lane])) * h;
-            else g = (k == 0) ? 0.0 : (P->Wdiag[lane - CF_NU] * (X0[lane - CF_NU] - yrefg[k * CF_NY + lane - CF_NU])) * h;
+            if (lane < CF_NU) g = (P->Wdiag[CF_NX + lane] * (UU[lane] - yr_pre)) * h;
+            else g = (k == 0) ? 0.0 : (P->Wdiag[lane - CF_NU] * (X0[lane - CF_NU] - yr_pre)) * h;
             rq[k * CF_NV + lane] = g;
         }
         // bounds (ocp_nlp_constraints_bgh.c:1634-1636): d = [lb - u ; u - ub]
@@ -284,6 +292,8 @@ struct CfWarp
         }
         cf_syncwarp();
         if (lane == 0) cf_bulk_s2g(M + (long) k * CF_MSZ, MS, CF_MSZ * 8);
+        xk_pre = xn_pre;
+        uk_pre = un_pre;
     }
 
     CF_MEM void terminal_gradient(const double *xg, const double *yref_eg)
@@ -328,32 +338,47 @@ struct CfWarp
         double *UXS = sm + CF_SM_V0, *PIS = sm + CF_SM_V1;
         pass_begin();
         fetch(0, 0, -1, -1);
-        // prologue: ux_0
+        // prologue: ux_0 and the vectors of stage 0; inside the loop the vectors of stage k+1 are loaded
+        // before the arithmetic of stage k (software pipelining of the global-load latency)
+        const bool xl = lane >= CF_NU && lane < CF_NV;
+        const int ci = xl ? lane - CF_NU : 0;
         double uxc = 0.0;
         if (lane < CF_NV) {
             uxc = ux[lane];
             if (do_update) { uxc += a * dux[lane]; ux[lane] = uxc; }
         }
+        double rq_c = (lane < CF_NV) ? rq[lane] : 0.0;
+        double b_c = (xl && N > 0) ? b[ci] : 0.0;
+        double pi_c = (xl && N > 0) ? pi[ci] : 0.0;
+        double dpi_c = (xl && N > 0 && do_update) ? dpi[ci] : 0.0;
         double pi_prev = 0.0;
         CF_NOUNROLL
         for (int k = 0; k <= N; k++) {
             double uxn = 0.0, pik = 0.0;
+            double rq_n = 0.0, b_n = 0.0, pi_n = 0.0, dpi_n = 0.0;
             if (k < N) {
                 if (lane < CF_NV) {
                     uxn = ux[(k + 1) * CF_NV + lane];
-                    if (do_update) { uxn += a * dux[(k + 1) * CF_NV + lane]; ux[(k + 1) * CF_NV + lane] = uxn; }
+                    if (do_update) uxn += a * dux[(k + 1) * CF_NV + lane];
+                    rq_n = rq[(k + 1) * CF_NV + lane];
                 }
-                if (lane >= CF_NU && lane < CF_NV) {
-                    pik = pi[k * CF_NX + lane - CF_NU];
-                    if (do_update) { pik += a * dpi[k * CF_NX + lane - CF_NU]; pi[k * CF_NX + lane - CF_NU] = pik; }
+                if (xl && k + 1 < N) {
+                    b_n = b[(k + 1) * CF_NX + ci];
+                    pi_n = pi[(k + 1) * CF_NX + ci];
+                    if (do_update) dpi_n = dpi[(k + 1) * CF_NX + ci];
+                }
+                if (do_update && lane < CF_NV) ux[(k + 1) * CF_NV + lane] = uxn;
+                if (xl) {
+                    pik = pi_c;
+                    if (do_update) { pik += a * dpi_c; pi[k * CF_NX + ci] = pik; }
                 }
             }
-            double rg = 0.0, bkc = 0.0;
+            double rg = 0.0;
+            const double bkc = b_c;
             if (lane < CF_NV) {
-                rg = ((k == N) ? HN : Hs) * uxc + rq[k * CF_NV + lane];
+                rg = ((k == N) ? HN : Hs) * uxc + rq_c;
                 if (k > 0 && lane >= CF_NU) rg -= pi_prev;
             }
-            if (k < N && lane >= CF_NU && lane < CF_NV) bkc = b[k * CF_NX + lane - CF_NU];
             if (lane < CF_NU && k < N) {
                 double *bk = bnd + (long) k * CF_BND;
                 double ll = bk[CF_F_LAM * 8 + lane], lu = bk[CF_F_LAM * 8 + 4 + lane];
@@ -416,6 +441,7 @@ struct CfWarp
             if (lane < CF_NV) { res_g[k * CF_NV + lane] = rg; ng = fmax(ng, fabs(rg)); }
             pi_prev = pik;
             uxc = uxn;
+            rq_c = rq_n; b_c = b_n; pi_c = pi_n; dpi_c = dpi_n;
         }
         nrm[0] = cf_warp_max(ng); nrm[1] = cf_warp_max(nb); nrm[2] = cf_warp_max(nd); nrm[3] = cf_warp_max(nm);
         mu = cf_warp_sum(mus) * (1.0 / (double) (2 * CF_NU * N));
@@ -476,8 +502,6 @@ struct CfWarp
                 cf_syncwarp();  // every lane is done with buffer bf^1 and with V/G/HD of the previous stage
                 if (k > 0) fetch(bf ^ 1, k - 1, -1, -1);
                 const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
-                G[lane] = g;
-                HD[lane] = hd;
                 // ---- TRMM_RLNN on the fp64 tensor cores: AL(18x13) = [B';A';res_b'](18x13) * Lxx(13x13, lower).
                 // Row tiles t = 0..2 (rows 8t+fg), column tiles 0..1 (columns 8t'+2fq+{0,1}), K padded to 16.
                 // Lxx is lower triangular: for column tile 1 (n >= 8) only k >= 8 contributes.
@@ -516,6 +540,8 @@ struct CfWarp
                         cf_st2(ALS + r * CF_ALST + 8 + 2 * fq, al[t][1][0], al[t][1][1]);
                     }
                 }
+                G[lane] = g;      // published only now: the global loads behind g / hd overlap the TRMM
+                HD[lane] = hd;
                 cf_syncwarp();
                 // Pb = Lxx * (Lxx' res_b)  (TRMV_LNN, :492-493): lane 4+i uses its own factor row
                 if (lane >= CF_NU && lane < CF_NV) {
@@ -936,8 +962,9 @@ CF_DEV void cf_rti_instance(const CfParams *P, const CfBatchView &bv, int inst, 
     const double *x0g = bv.x0 + (long) inst * CF_NX;
     const double *yrefg = bv.yref + (long) inst * N * CF_NY;
     const double *yref_eg = bv.yref_e + (long) inst * CF_NX;
+    double xk_pre = (w.lane < CF_NX) ? xg[w.lane] : 0.0, uk_pre = (w.lane < CF_NU) ? ug[w.lane] : 0.0;
     CF_NOUNROLL
-    for (int k = 0; k < N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg);
+    for (int k = 0; k < N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg, xk_pre, uk_pre);
     w.terminal_gradient(xg, yref_eg);
     cf_syncwarp();
     int iters = 0;
