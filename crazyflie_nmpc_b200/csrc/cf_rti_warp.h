@@ -220,63 +220,63 @@ struct CfWarp
         double uu[CF_NU];
         CF_UNROLL
         for (int i = 0; i < CF_NU; i++) uu[i] = UU[i];
-        double Ss[CF_NX], acc[CF_NX];
+        // the accumulated sensitivity column of this lane lives in its row of the staging block (MS[c*18+lane]),
+        // not in registers: the RK stage below is register-hungry enough
+        const bool col = lane < CF_NV;
+        double *Mrow = MS + (col ? lane : 17);
+        double Ss[CF_NX];
         CF_UNROLL
-        for (int i = 0; i < CF_NX; i++) { Ss[i] = (lane - CF_NU == i) ? 1.0 : 0.0; acc[i] = Ss[i]; }
+        for (int i = 0; i < CF_NX; i++) {
+            Ss[i] = (lane - CF_NU == i) ? 1.0 : 0.0;
+            if (col) Mrow[i * CF_MROWS] = Ss[i];
+        }
         CF_NOUNROLL
         for (int s = 0; s < 4; s++) {
             // tableau: sim_collocation_utils.c:611-640 (classic RK4)
             const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
             const double a_next = (s == 2) ? 1.0 : 0.5;
-            double xs[CF_NX], f[CF_NX], ks[CF_NX];
+            const double bh = h * bw, ah = a_next * h;
+            double xs[CF_NX];
             CF_UNROLL
             for (int i = 0; i < CF_NX; i++) xs[i] = XS[i];
-            cf_ode(xs, uu, f);
+            cf_syncwarp();  // everyone has read XS
+            {
+                double f[CF_NX];
+                cf_ode(xs, uu, f);
+                if (lane == 17) {
+                    CF_UNROLL
+                    for (int i = 0; i < CF_NX; i++) {
+                        ACC[i] += bh * f[i];
+                        XS[i] = X0[i] + ah * f[i];
+                    }
+                }
+            }
+            double ks[CF_NX];
             cf_jvp_x(xs, Ss, ks);
             if (lane < CF_NU) cf_add_ju_col(uu, lane, ks);
-            cf_syncwarp();  // everyone has read XS
-            const double bh = h * bw, ah = a_next * h;
             CF_UNROLL
             for (int i = 0; i < CF_NX; i++) {
-                acc[i] += bh * ks[i];
+                if (col) Mrow[i * CF_MROWS] += bh * ks[i];
                 Ss[i] = ((lane - CF_NU == i) ? 1.0 : 0.0) + ah * ks[i];
-            }
-            if (lane == 17) {
-                CF_UNROLL
-                for (int i = 0; i < CF_NX; i++) {
-                    ACC[i] += bh * f[i];
-                    XS[i] = X0[i] + ah * f[i];
-                }
             }
             cf_syncwarp();
         }
-        // lane 17: b_k = phi(x_k,u_k) - x_{k+1}   (ocp_nlp_dynamics_cont.c:822-823)
+        // row 17: b_k = phi(x_k,u_k) - x_{k+1}   (ocp_nlp_dynamics_cont.c:822-823)
+        if (lane < CF_NX) MS[lane * CF_MROWS + 17] = ACC[lane] - xn_pre;
         cf_syncwarp();
-        if (lane < CF_NX) XS[lane] = xn_pre;   // broadcast x_{k+1} to lane 17 (XS is free after the last RK stage)
-        cf_syncwarp();
-        if (lane == 17) {
-            CF_UNROLL
-            for (int i = 0; i < CF_NX; i++) acc[i] = ACC[i] - XS[i];
-        }
         if (k == 0) {
             // x0 elimination (x_ocp_qp_red.c:310-330): xbar = lbx - x_0 ; b_0 += A_0 xbar ; drop the A rows
             const bool xl = lane >= CF_NU && lane < CF_NV;
             const double xbar = xl ? (x0g[lane - CF_NU] - xg[lane - CF_NU]) : 0.0;
-            CF_UNROLL
+            CF_NOUNROLL
             for (int i = 0; i < CF_NX; i++) {
-                const double tot = cf_warp_sum(xl ? acc[i] * xbar : 0.0);
-                if (lane == 17) acc[i] = tot + acc[i];
-                else if (lane >= CF_NU) acc[i] = 0.0;
+                const double tot = cf_warp_sum(xl ? Mrow[i * CF_MROWS] * xbar : 0.0);
+                if (lane == 17) MS[i * CF_MROWS + 17] = tot + MS[i * CF_MROWS + 17];
+                else if (xl) Mrow[i * CF_MROWS] = 0.0;
             }
+            cf_syncwarp();
         }
-        if (lane < CF_MROWS) {
-            CF_UNROLL
-            for (int c = 0; c < CF_NX; c++) MS[c * CF_MROWS + lane] = acc[c];
-        }
-        if (lane == 17) {
-            CF_UNROLL
-            for (int c = 0; c < CF_NX; c++) b[k * CF_NX + c] = acc[c];
-        }
+        if (lane < CF_NX) b[k * CF_NX + lane] = MS[lane * CF_MROWS + 17];
         // gradient: scaling * W * (y - yref), [u;x] order (ocp_nlp_cost_ls.c:883-912)
         if (lane < CF_NV) {
             double g;
