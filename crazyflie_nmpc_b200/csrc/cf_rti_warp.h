@@ -37,8 +37,13 @@
 #define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
 #define CF_LX 104                         // factor, state block: packed lower rows (91) + last row l~x (13)
 #define CF_LFSZ (CF_LU + CF_LX)           // 176 doubles per stage
-#define CF_BND 64                         // doubles per stage of bound data: 8 fields x [lb4 | ub4]
-enum { CF_F_D = 0, CF_F_LAM, CF_F_T, CF_F_RESD, CF_F_RESM, CF_F_BKP, CF_F_DLAM, CF_F_DT };
+// Per-stage record of all IPM vectors (192 doubles).  The field order makes what each sweep reads one
+// contiguous, 16-byte aligned range, so it is staged by a single TMA bulk copy one stage ahead:
+//   residual sweep  [R_UX, R_RESD)  (+ R_DUX)      forward sweep  [R_LAM, end)      backward sweep  [R_DLAM, R_DUX)
+// 17-vectors are padded to 18, 13-vectors to 14; bound fields are [lb(4) | ub(4)].
+#define CF_REC 192
+enum { R_UX = 0, R_PI = 18, R_DPI = 32, R_RQ = 46, R_B = 64, R_D = 78, R_DLAM = 86, R_DT = 94, R_LAM = 102, R_T = 110,
+       R_RESD = 118, R_BKP = 126, R_RESM = 134, R_RESG = 142, R_PB = 160, R_DUX = 174 };
 
 // HPIPM arguments in effect for the reference configuration (BALANCE mode + acados
 // overrides): acados/acados/ocp_qp/ocp_qp_hpipm.c:96-108, x_ocp_qp_ipm.c:133-161
@@ -94,7 +99,7 @@ struct CfBatchView
 // touches (M, LF) starts on a 16-byte boundary
 struct CfScratchLayout
 {
-    long M, L, b, rq, ux, pi, res_g, dux, dpi, Pb, bnd, total;
+    long M, L, rec, total;
 };
 static inline
 #if !defined(CF_SIMT_EMU)
@@ -107,16 +112,7 @@ static inline
     long o = 0;
     s.M = o;     o += (long) N * CF_MSZ;
     s.L = o;     o += (long) (N + 1) * CF_LFSZ;
-    s.b = o;     o += (long) N * CF_NX + 1;
-    s.rq = o;    o += (long) (N + 1) * CF_NV + 1;
-    s.ux = o;    o += (long) (N + 1) * CF_NV + 1;
-    s.pi = o;    o += (long) (N + 1) * CF_NX + 1;
-    s.res_g = o; o += (long) (N + 1) * CF_NV + 1;
-    s.dux = o;   o += (long) (N + 1) * CF_NV + 1;
-    s.dpi = o;   o += (long) (N + 1) * CF_NX + 1;
-    s.Pb = o;    o += (long) N * CF_NX + 1;
-    o = (o + 1) & ~1L;
-    s.bnd = o;   o += (long) (N + 1) * CF_BND;
+    s.rec = o;   o += (long) (N + 1) * CF_REC;
     s.total = (o + 15) & ~15L;  // keep every slot 128-byte aligned
     return s;
 }
@@ -130,6 +126,8 @@ static inline
 #define CF_ALST 20
 #define CF_SM_LB0 CF_SM_W                      //   sweeps: factor block staging [LU 72 | LX 104], double buffered
 #define CF_SM_LB1 (CF_SM_W + CF_LFSZ)
+#define CF_SM_VS0 (CF_SM_W + 2 * CF_LFSZ)      //   sweeps: staged part of the stage record, double buffered (<= 136 doubles)
+#define CF_SM_VS1 (CF_SM_VS0 + 136)
 #define CF_SM_V0 (CF_SM_W + 324 + 18 * CF_ALST) // four 32-double broadcast vectors
 #define CF_SM_V1 (CF_SM_V0 + 32)
 #define CF_SM_V2 (CF_SM_V1 + 32)
@@ -148,7 +146,7 @@ struct CfWarp
     uint64_t *bar;
     unsigned par;  // phase parity of the two mbarriers
     // scratch arrays
-    double *M, *LF, *b, *rq, *ux, *pi, *res_g, *dux, *dpi, *Pb, *bnd;
+    double *M, *LF, *REC;
     // lane constants
     double Hs, HN;     // Hessian diagonal for this lane's variable (stage / terminal)
     // IPM scalars (warp-uniform)
@@ -163,8 +161,7 @@ struct CfWarp
         bar = reinterpret_cast<uint64_t *>(sm_ + CF_SM_BAR);
         par = 0;
         CfScratchLayout s = cf_scratch_layout(N);
-        M = slot + s.M; LF = slot + s.L; b = slot + s.b; rq = slot + s.rq; ux = slot + s.ux; pi = slot + s.pi;
-        res_g = slot + s.res_g; dux = slot + s.dux; dpi = slot + s.dpi; Pb = slot + s.Pb; bnd = slot + s.bnd;
+        M = slot + s.M; LF = slot + s.L; REC = slot + s.rec;
         // hess = scaling * (sqrt(W))^2 : ocp_nlp_cost_ls.c:739-772 (terminal scaling stays 1.0, :265)
         double w = 1.0, wN = 1.0;
         if (lane < CF_NU) w = P->Wdiag[CF_NX + lane];
@@ -180,16 +177,24 @@ struct CfWarp
         cf_syncwarp();                            // all generic stores of the previous pass are ordered ...
         if (lane == 0) cf_fence_proxy_async();    // ... before the bulk (async-proxy) reads of this pass
     }
-    // fetch into buffer `bf`: [B';A';res_b']_km (if km >= 0), LU_ku (if ku >= 0), LX_kx (if kx >= 0)
-    CF_MEM void fetch(int bf, int km, int ku, int kx)
+    CF_MEM double *rec(int k) const { return REC + (long) k * CF_REC; }
+    // fetch into buffer `bf`: [B';A';res_b']_km (if km >= 0), LU_ku (if ku >= 0), LX_kx (if kx >= 0) and up to two
+    // ranges [o1, o1+n1), [o2, o2+n2) of the stage record kv (if kv >= 0), packed back to back in VS
+    CF_MEM void fetch(int bf, int km, int ku, int kx, int kv = -1, int o1 = 0, int n1 = 0, int o2 = 0, int n2 = 0)
     {
         if (lane == 0) {
-            const int bytes = (km >= 0 ? CF_MSZ * 8 : 0) + (ku >= 0 ? CF_LU * 8 : 0) + (kx >= 0 ? CF_LX * 8 : 0);
+            const int bytes = (km >= 0 ? CF_MSZ * 8 : 0) + (ku >= 0 ? CF_LU * 8 : 0) + (kx >= 0 ? CF_LX * 8 : 0) +
+                              (kv >= 0 ? (n1 + n2) * 8 : 0);
             cf_bulk_expect(bar + bf, bytes);
             double *ms = sm + (bf ? CF_SM_MS1 : CF_SM_MS0), *lb = sm + (bf ? CF_SM_LB1 : CF_SM_LB0);
+            double *vs = sm + (bf ? CF_SM_VS1 : CF_SM_VS0);
             if (km >= 0) cf_bulk_g2s_raw(ms, M + (long) km * CF_MSZ, CF_MSZ * 8, bar + bf);
             if (ku >= 0) cf_bulk_g2s_raw(lb, LF + (long) ku * CF_LFSZ, CF_LU * 8, bar + bf);
             if (kx >= 0) cf_bulk_g2s_raw(lb + CF_LU, LF + (long) kx * CF_LFSZ + CF_LU, CF_LX * 8, bar + bf);
+            if (kv >= 0) {
+                cf_bulk_g2s_raw(vs, rec(kv) + o1, n1 * 8, bar + bf);
+                if (n2 > 0) cf_bulk_g2s_raw(vs + n1, rec(kv) + o2, n2 * 8, bar + bf);
+            }
         }
     }
     CF_MEM void wait(int bf)
@@ -276,19 +281,18 @@ struct CfWarp
             }
             cf_syncwarp();
         }
-        if (lane < CF_NX) b[k * CF_NX + lane] = MS[lane * CF_MROWS + 17];
+        if (lane < CF_NX) rec(k)[R_B + lane] = MS[lane * CF_MROWS + 17];
         // gradient: scaling * W * (y - yref), [u;x] order (ocp_nlp_cost_ls.c:883-912)
         if (lane < CF_NV) {
             double g;
             if (lane < CF_NU) g = (P->Wdiag[CF_NX + lane] * (UU[lane] - yr_pre)) * h;
             else g = (k == 0) ? 0.0 : (P->Wdiag[lane - CF_NU] * (X0[lane - CF_NU] - yr_pre)) * h;
-            rq[k * CF_NV + lane] = g;
+            rec(k)[R_RQ + lane] = g;
         }
         // bounds (ocp_nlp_constraints_bgh.c:1634-1636): d = [lb - u ; u - ub]
         if (lane < CF_NU) {
-            double *bk = bnd + (long) k * CF_BND;
-            bk[CF_F_D * 8 + lane] = P->lbu[lane] - UU[lane];
-            bk[CF_F_D * 8 + 4 + lane] = UU[lane] - P->ubu[lane];
+            rec(k)[R_D + lane] = P->lbu[lane] - UU[lane];
+            rec(k)[R_D + 4 + lane] = UU[lane] - P->ubu[lane];
         }
         cf_syncwarp();
         if (lane == 0) cf_bulk_s2g(M + (long) k * CF_MSZ, MS, CF_MSZ * 8);
@@ -301,7 +305,7 @@ struct CfWarp
         if (lane < CF_NV) {
             double g = 0.0;
             if (lane >= CF_NU) g = P->WNdiag[lane - CF_NU] * (xg[N * CF_NX + lane - CF_NU] - yref_eg[lane - CF_NU]);
-            rq[N * CF_NV + lane] = g;
+            rec(N)[R_RQ + lane] = g;
         }
         if (lane == 0) cf_bulk_s2g_wait_all();  // every M_k has landed in global memory
     }
@@ -310,21 +314,22 @@ struct CfWarp
     // OCP_QP_INIT_VAR scheme 1 (x_ocp_qp_ipm.c:1491-1530,1636-1769)
     CF_MEM void init_var()
     {
+        CF_NOUNROLL
         for (int k = 0; k <= N; k++) {
+            double *rk = rec(k);
             double v = 0.0;
             if (lane < CF_NU && k < N) {
-                double *bk = bnd + (long) k * CF_BND;
-                double dl = bk[CF_F_D * 8 + lane], du = bk[CF_F_D * 8 + 4 + lane];
+                double dl = rk[R_D + lane], du = rk[R_D + 4 + lane];
                 double tl = -dl, tu = -du;
                 if (tl < CF_THR0) {
                     if (tu < CF_THR0) { v = 0.5 * (dl - du); tl = CF_THR0; tu = CF_THR0; }
                     else { tl = CF_THR0; v = dl + CF_THR0; }
                 } else if (tu < CF_THR0) { tu = CF_THR0; v = -du - CF_THR0; }
-                bk[CF_F_T * 8 + lane] = tl; bk[CF_F_T * 8 + 4 + lane] = tu;
-                bk[CF_F_LAM * 8 + lane] = CF_MU0 / tl; bk[CF_F_LAM * 8 + 4 + lane] = CF_MU0 / tu;
+                rk[R_T + lane] = tl; rk[R_T + 4 + lane] = tu;
+                rk[R_LAM + lane] = CF_MU0 / tl; rk[R_LAM + 4 + lane] = CF_MU0 / tu;
             }
-            if (lane < CF_NV) ux[k * CF_NV + lane] = v;
-            if (lane < CF_NX) pi[k * CF_NX + lane] = 0.0;
+            if (lane < CF_NV) rk[R_UX + lane] = v;
+            if (lane < CF_NX) rk[R_PI + lane] = 0.0;
         }
     }
 
@@ -336,79 +341,64 @@ struct CfWarp
         if (do_update && a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
         double ng = 0, nb = 0, nd = 0, nm = 0, mus = 0;
         double *UXS = sm + CF_SM_V0, *PIS = sm + CF_SM_V1;
+        const int n2 = do_update ? 18 : 0;   // the step dux is needed only when the variables are updated
         pass_begin();
-        fetch(0, 0, -1, -1);
-        // prologue: ux_0 and the vectors of stage 0; inside the loop the vectors of stage k+1 are loaded
-        // before the arithmetic of stage k (software pipelining of the global-load latency)
+        fetch(0, N > 0 ? 0 : -1, -1, -1, 0, R_UX, R_RESD - R_UX, R_DUX, n2);
         const bool xl = lane >= CF_NU && lane < CF_NV;
         const int ci = xl ? lane - CF_NU : 0;
-        double uxc = 0.0;
-        if (lane < CF_NV) {
-            uxc = ux[lane];
-            if (do_update) { uxc += a * dux[lane]; ux[lane] = uxc; }
-        }
-        double rq_c = (lane < CF_NV) ? rq[lane] : 0.0;
-        double b_c = (xl && N > 0) ? b[ci] : 0.0;
-        double pi_c = (xl && N > 0) ? pi[ci] : 0.0;
-        double dpi_c = (xl && N > 0 && do_update) ? dpi[ci] : 0.0;
-        double pi_prev = 0.0;
+        double pi_prev = 0.0;            // lanes 4..16: pi_{k-1}
+        double sb_prev = 0.0, b_prev = 0.0;  // lanes 4..16: ([A B] ux)_{k-1} and b_{k-1}; res_b_{k-1} is finished at stage k
         CF_NOUNROLL
         for (int k = 0; k <= N; k++) {
-            double uxn = 0.0, pik = 0.0;
-            double rq_n = 0.0, b_n = 0.0, pi_n = 0.0, dpi_n = 0.0;
-            if (k < N) {
-                if (lane < CF_NV) {
-                    uxn = ux[(k + 1) * CF_NV + lane];
-                    if (do_update) uxn += a * dux[(k + 1) * CF_NV + lane];
-                    rq_n = rq[(k + 1) * CF_NV + lane];
-                }
-                if (xl && k + 1 < N) {
-                    b_n = b[(k + 1) * CF_NX + ci];
-                    pi_n = pi[(k + 1) * CF_NX + ci];
-                    if (do_update) dpi_n = dpi[(k + 1) * CF_NX + ci];
-                }
-                if (do_update && lane < CF_NV) ux[(k + 1) * CF_NV + lane] = uxn;
-                if (xl) {
-                    pik = pi_c;
-                    if (do_update) { pik += a * dpi_c; pi[k * CF_NX + ci] = pik; }
-                }
+            const int bf = k & 1;
+            cf_syncwarp();  // previous stage's reads of UXS/PIS and of buffer bf^1 are complete
+            if (k < N) fetch(bf ^ 1, k + 1 < N ? k + 1 : -1, -1, -1, k + 1, R_UX, R_RESD - R_UX, R_DUX, n2);
+            wait(bf);
+            const double *VS = sm + (bf ? CF_SM_VS1 : CF_SM_VS0);
+            double *rk = rec(k);
+            double uxc = 0.0, pik = 0.0;
+            if (lane < CF_NV) {
+                uxc = VS[R_UX + lane];
+                if (do_update) { uxc += a * VS[R_RESD + lane]; rk[R_UX + lane] = uxc; }
+            }
+            if (k > 0 && xl) {  // res_b_{k-1} = (b - x+) + [A B] ux, stored as row 17 of M_{k-1} (ROWIN of x_ocp_qp_kkt.c:490)
+                const double rb = (b_prev - uxc) + sb_prev;
+                nb = fmax(nb, fabs(rb));
+                M[(long) (k - 1) * CF_MSZ + ci * CF_MROWS + 17] = rb;
+            }
+            if (k < N && xl) {
+                pik = VS[R_PI + ci];
+                if (do_update) { pik += a * VS[R_DPI + ci]; rk[R_PI + ci] = pik; }
             }
             double rg = 0.0;
-            const double bkc = b_c;
             if (lane < CF_NV) {
-                rg = ((k == N) ? HN : Hs) * uxc + rq_c;
+                rg = ((k == N) ? HN : Hs) * uxc + VS[R_RQ + lane];
                 if (k > 0 && lane >= CF_NU) rg -= pi_prev;
             }
             if (lane < CF_NU && k < N) {
-                double *bk = bnd + (long) k * CF_BND;
-                double ll = bk[CF_F_LAM * 8 + lane], lu = bk[CF_F_LAM * 8 + 4 + lane];
-                double tl = bk[CF_F_T * 8 + lane], tu = bk[CF_F_T * 8 + 4 + lane];
+                double ll = VS[R_LAM + lane], lu = VS[R_LAM + 4 + lane];
+                double tl = VS[R_T + lane], tu = VS[R_T + 4 + lane];
                 if (do_update) {
-                    ll += a * bk[CF_F_DLAM * 8 + lane]; lu += a * bk[CF_F_DLAM * 8 + 4 + lane];
-                    tl += a * bk[CF_F_DT * 8 + lane]; tu += a * bk[CF_F_DT * 8 + 4 + lane];
+                    ll += a * VS[R_DLAM + lane]; lu += a * VS[R_DLAM + 4 + lane];
+                    tl += a * VS[R_DT + lane]; tu += a * VS[R_DT + 4 + lane];
                     ll = ll <= CF_LAM_MIN ? CF_LAM_MIN : ll; lu = lu <= CF_LAM_MIN ? CF_LAM_MIN : lu;
                     tl = tl <= CF_T_MIN ? CF_T_MIN : tl; tu = tu <= CF_T_MIN ? CF_T_MIN : tu;
-                    bk[CF_F_LAM * 8 + lane] = ll; bk[CF_F_LAM * 8 + 4 + lane] = lu;
-                    bk[CF_F_T * 8 + lane] = tl; bk[CF_F_T * 8 + 4 + lane] = tu;
+                    rk[R_LAM + lane] = ll; rk[R_LAM + 4 + lane] = lu;
+                    rk[R_T + lane] = tl; rk[R_T + 4 + lane] = tu;
                 }
                 rg += lu - ll;
-                double rdl = bk[CF_F_D * 8 + lane] + tl - uxc, rdu = bk[CF_F_D * 8 + 4 + lane] + tu + uxc;
+                double rdl = VS[R_D + lane] + tl - uxc, rdu = VS[R_D + 4 + lane] + tu + uxc;
                 double rml = ll * tl, rmu = lu * tu;
-                bk[CF_F_RESD * 8 + lane] = rdl; bk[CF_F_RESD * 8 + 4 + lane] = rdu;
-                bk[CF_F_BKP * 8 + lane] = rml; bk[CF_F_BKP * 8 + 4 + lane] = rmu;
+                rk[R_RESD + lane] = rdl; rk[R_RESD + 4 + lane] = rdu;
+                rk[R_BKP + lane] = rml; rk[R_BKP + 4 + lane] = rmu;
                 mus += rml + rmu;
                 nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
                 nm = fmax(nm, fmax(fabs(rml), fabs(rmu)));
             }
+            double sbk = 0.0;
             if (k < N) {
-                const int bf = k & 1;
-                cf_syncwarp();  // previous stage's reads of UXS/PIS and of buffer bf^1 are complete
-                if (k + 1 < N) fetch(bf ^ 1, k + 1, -1, -1);
                 if (lane < CF_NV) UXS[lane] = uxc;
-                if (lane == 17) UXS[17] = 0.0;
-                if (lane >= CF_NU && lane < CF_NV) PIS[lane - CF_NU] = pik;
-                if (lane == 17) PIS[13] = 0.0;
-                wait(bf);
+                if (xl) PIS[ci] = pik;
                 cf_syncwarp();
                 const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
                 if (lane < CF_NV) {  // res_g += [B';A'] pi_k   (row layout: own elements stride 18)
@@ -422,9 +412,8 @@ struct CfWarp
                     s0 += Mk[12 * CF_MROWS + lane] * PIS[12];
                     rg += s0 + s1;
                 }
-                if (lane >= CF_NU && lane < CF_NV) {  // res_b = b - x+ + [A B] ux   (column layout: contiguous)
-                    const int c = lane - CF_NU;
-                    const double *Mc = Mk + c * CF_MROWS;
+                if (xl) {  // [A B] ux   (column layout: contiguous)
+                    const double *Mc = Mk + ci * CF_MROWS;
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
                     for (int rp = 0; rp < 8; rp++) {
@@ -433,15 +422,13 @@ struct CfWarp
                         s1 += m2.y * u2.y;
                     }
                     s0 += Mc[16] * UXS[16];
-                    const double rb = (bkc - uxn) + (s0 + s1);
-                    nb = fmax(nb, fabs(rb));
-                    M[(long) k * CF_MSZ + c * CF_MROWS + 17] = rb;  // ROWIN(res_b) of x_ocp_qp_kkt.c:490
+                    sbk = s0 + s1;
                 }
             }
-            if (lane < CF_NV) { res_g[k * CF_NV + lane] = rg; ng = fmax(ng, fabs(rg)); }
+            if (lane < CF_NV) { rk[R_RESG + lane] = rg; ng = fmax(ng, fabs(rg)); }
             pi_prev = pik;
-            uxc = uxn;
-            rq_c = rq_n; b_c = b_n; pi_c = pi_n; dpi_c = dpi_n;
+            sb_prev = sbk;
+            b_prev = (k < N && xl) ? VS[R_B + ci] : 0.0;
         }
         nrm[0] = cf_warp_max(ng); nrm[1] = cf_warp_max(nb); nrm[2] = cf_warp_max(nd); nrm[3] = cf_warp_max(nm);
         mu = cf_warp_sum(mus) * (1.0 / (double) (2 * CF_NU * N));
@@ -451,24 +438,25 @@ struct CfWarp
     // gamma for the condensed right-hand side (x_core_qp_ipm_aux.c:38-111); lanes 0..3 of stage k<N.
     // rm_mode: 0 predictor (bkp - tau_min), 1 corrector (bkp + dt*dlam - sigma_mu, stored),
     //          2 re-centering (bkp - sigma_mu, stored), 3 use the stored RESM as is.
-    CF_MEM void bound_terms(int k, int rm_mode, double sigma_mu, double &Gam, double &gam)
+    // `q` points at field R_DLAM of stage k's record, either in global memory or in its staged copy.
+    CF_MEM void bound_terms(int k, const double *q, int rm_mode, double sigma_mu, double &Gam, double &gam)
     {
-        double *bk = bnd + (long) k * CF_BND;
-        double ll = bk[CF_F_LAM * 8 + lane], lu = bk[CF_F_LAM * 8 + 4 + lane];
-        double til = 1.0 / bk[CF_F_T * 8 + lane], tiu = 1.0 / bk[CF_F_T * 8 + 4 + lane];
+        const double *f = q - R_DLAM;
+        double ll = f[R_LAM + lane], lu = f[R_LAM + 4 + lane];
+        double til = 1.0 / f[R_T + lane], tiu = 1.0 / f[R_T + 4 + lane];
         double rml, rmu;
-        if (rm_mode == 3) { rml = bk[CF_F_RESM * 8 + lane]; rmu = bk[CF_F_RESM * 8 + 4 + lane]; }
+        if (rm_mode == 3) { rml = f[R_RESM + lane]; rmu = f[R_RESM + 4 + lane]; }
         else {
-            rml = bk[CF_F_BKP * 8 + lane]; rmu = bk[CF_F_BKP * 8 + 4 + lane];
+            rml = f[R_BKP + lane]; rmu = f[R_BKP + 4 + lane];
             if (rm_mode == 0) { rml -= CF_TAU_MIN; rmu -= CF_TAU_MIN; }
             else if (rm_mode == 1) {
-                rml = rml + bk[CF_F_DT * 8 + lane] * bk[CF_F_DLAM * 8 + lane] - sigma_mu;
-                rmu = rmu + bk[CF_F_DT * 8 + 4 + lane] * bk[CF_F_DLAM * 8 + 4 + lane] - sigma_mu;
+                rml = rml + f[R_DT + lane] * f[R_DLAM + lane] - sigma_mu;
+                rmu = rmu + f[R_DT + 4 + lane] * f[R_DLAM + 4 + lane] - sigma_mu;
             } else { rml -= sigma_mu; rmu -= sigma_mu; }
-            bk[CF_F_RESM * 8 + lane] = rml; bk[CF_F_RESM * 8 + 4 + lane] = rmu;
+            if (rm_mode != 0) { rec(k)[R_RESM + lane] = rml; rec(k)[R_RESM + 4 + lane] = rmu; }
         }
-        double gl = til * (rml - ll * bk[CF_F_RESD * 8 + lane]);
-        double gu = tiu * (rmu - lu * bk[CF_F_RESD * 8 + 4 + lane]);
+        double gl = til * (rml - ll * f[R_RESD + lane]);
+        double gu = tiu * (rmu - lu * f[R_RESD + 4 + lane]);
         Gam = til * ll + tiu * lu;
         gam = gl - gu;
     }
@@ -493,8 +481,8 @@ struct CfWarp
         for (int k = N; k >= 0; k--) {
             // gradient row and diagonal of the stage Hessian; bound data are independent of the matrices
             double Gam = 0.0, gam = 0.0;
-            if (lane < CF_NU && k < N) bound_terms(k, 0, 0.0, Gam, gam);
-            const double g = (lane < CF_NV) ? res_g[k * CF_NV + lane] + gam : 0.0;
+            if (lane < CF_NU && k < N) bound_terms(k, rec(k) + R_DLAM, 0, 0.0, Gam, gam);
+            const double g = (lane < CF_NV) ? rec(k)[R_RESG + lane] + gam : 0.0;
             const double hd = ((k == N) ? HN : Hs) + CF_REG_PRIM + Gam;
             if (k < N) {
                 const int bf = (N - 1 - k) & 1;
@@ -552,7 +540,7 @@ struct CfWarp
                         s0 += l2.x * v2.x;
                         s1 += l2.y * v2.y;
                     }
-                    Pb[k * CF_NX + lane - CF_NU] = s0 + s1;
+                    rec(k)[R_PB + lane - CF_NU] = s0 + s1;
                 }
                 // ---- SYRK_LN on the tensor cores: S = D + AL * AL'; the same fragment serves as A and as B
                 double fr[3][4];
@@ -641,37 +629,27 @@ struct CfWarp
         double lg = 0, lb = 0, ld = 0, lm = 0;    // linear residual norms
         double dxk = 0.0;        // lanes 4..16: dx_k ; stage 0 has none
         double dpi_prev = 0.0;   // lanes 4..16: dpi_{k-1}
+        const int VO = R_LAM, VN = CF_REC - R_LAM;   // staged part of the stage record: [R_LAM, end)
         pass_begin();
-        if (N > 0) fetch(0, 0, 0, 1);
+        if (N > 0) fetch(0, 0, 0, 1, 0, VO, VN);
         XS[lane] = 0.0; YS[lane] = 0.0; PS[lane] = 0.0;
         const bool xl = lane >= CF_NU && lane < CF_NV;
         const int ci = xl ? lane - CF_NU : 0;
         CF_NOUNROLL
         for (int k = 0; k < N; k++) {
             const int bf = k & 1;
-            // early, independent global loads
-            double rgk = 0.0, du_in = 0.0;
-            if (lane < CF_NV) rgk = res_g[k * CF_NV + lane];
-            if (mode == 1 && lane < CF_NU) du_in = dux[k * CF_NV + lane];
-            double ll = 1, lu = 1, tl = 1, tu = 1, rdl = 0, rdu = 0, rml = 0, rmu = 0;
-            if (lane < CF_NU) {
-                const double *bk = bnd + (long) k * CF_BND;
-                ll = bk[CF_F_LAM * 8 + lane]; lu = bk[CF_F_LAM * 8 + 4 + lane];
-                tl = bk[CF_F_T * 8 + lane]; tu = bk[CF_F_T * 8 + 4 + lane];
-                rdl = bk[CF_F_RESD * 8 + lane]; rdu = bk[CF_F_RESD * 8 + 4 + lane];
-                if (rm_mode == 0) { rml = bk[CF_F_BKP * 8 + lane] - CF_TAU_MIN; rmu = bk[CF_F_BKP * 8 + 4 + lane] - CF_TAU_MIN; }
-                else { rml = bk[CF_F_RESM * 8 + lane]; rmu = bk[CF_F_RESM * 8 + 4 + lane]; }
-            }
-            const double pnext = (mode == 1 && xl) ? dux[(k + 1) * CF_NV + lane] : 0.0;  // p_{k+1} of the backward sweep
+            double *rk = rec(k);
+            const double pnext = (mode == 1 && xl) ? rec(k + 1)[R_DUX + lane] : 0.0;  // p_{k+1} of the backward sweep
             wait(bf);
             cf_syncwarp();  // every lane is done with buffer bf^1
-            if (k + 1 < N) fetch(bf ^ 1, k + 1, k + 1, k + 2);
+            if (k + 1 < N) fetch(bf ^ 1, k + 1, k + 1, k + 2, k + 1, VO, VN);
             const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
             const double *LU = sm + (bf ? CF_SM_LB1 : CF_SM_LB0), *LX = LU + CF_LU;
+            const double *VS = sm + (bf ? CF_SM_VS1 : CF_SM_VS0) - VO;   // VS[R_x] = staged field R_x
             // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu)
             double v = 0.0, invd = 1.0;
             if (lane < CF_NU) {
-                double v0 = (mode == 0) ? -LU[17 * 4 + lane] : -du_in, v1 = 0.0;
+                double v0 = (mode == 0) ? -LU[17 * 4 + lane] : -VS[R_DUX + lane], v1 = 0.0;
                 CF_UNROLL
                 for (int ip = 0; ip < 6; ip++) {
                     const cf_d2 x2 = cf_ld2(XS + 2 * ip);
@@ -690,18 +668,23 @@ struct CfWarp
                 if (lane < j) v -= LU[j * 4 + lane] * duj;
             }
             const double duxk = (lane < CF_NU) ? du : dxk;  // lane r: dux_k[r]
-            if (lane < CF_NV) dux[k * CF_NV + lane] = duxk;
+            if (lane < CF_NV) rk[R_DUX + lane] = duxk;
             // ---- dlam, dt, alpha (lanes 0..3)
             double dlam_l = 0, dlam_u = 0;
             if (lane < CF_NU) {
-                double *bk = bnd + (long) k * CF_BND;
+                const double ll = VS[R_LAM + lane], lu = VS[R_LAM + 4 + lane];
+                const double tl = VS[R_T + lane], tu = VS[R_T + 4 + lane];
+                const double rdl = VS[R_RESD + lane], rdu = VS[R_RESD + 4 + lane];
+                double rml, rmu;
+                if (rm_mode == 0) { rml = VS[R_BKP + lane] - CF_TAU_MIN; rmu = VS[R_BKP + 4 + lane] - CF_TAU_MIN; }
+                else { rml = VS[R_RESM + lane]; rmu = VS[R_RESM + 4 + lane]; }
                 const double til = 1.0 / tl, tiu = 1.0 / tu;
                 double dtl = du, dtu = -du;
                 dlam_l = -til * (rml + (ll * dtl) - (ll * rdl));
                 dlam_u = -tiu * (rmu + (lu * dtu) - (lu * rdu));
                 dtl -= rdl; dtu -= rdu;
-                bk[CF_F_DLAM * 8 + lane] = dlam_l; bk[CF_F_DLAM * 8 + 4 + lane] = dlam_u;
-                bk[CF_F_DT * 8 + lane] = dtl; bk[CF_F_DT * 8 + 4 + lane] = dtu;
+                rk[R_DLAM + lane] = dlam_l; rk[R_DLAM + 4 + lane] = dlam_u;
+                rk[R_DT + lane] = dtl; rk[R_DT + 4 + lane] = dtu;
                 if (a_d * dlam_l > ll) a_d = ll / dlam_l;
                 if (a_p * dtl > tl) a_p = tl / dtl;
                 if (a_d * dlam_u > lu) a_d = lu / dlam_u;
@@ -713,7 +696,7 @@ struct CfWarp
             // stationarity residual, part 1: H dux + rhs_g - dpi_{k-1} + dlam_ub - dlam_lb
             double rgl = 0.0;
             if (lane < CF_NV) {
-                rgl = Hs * duxk + rgk;
+                rgl = Hs * duxk + VS[R_RESG + lane];
                 if (k > 0 && lane >= CF_NU) rgl -= dpi_prev;
                 rgl += dlam_u - dlam_l;
             }
@@ -761,7 +744,7 @@ struct CfWarp
                         else z0 += Li[c] * YS[c];
                     }
                 dpik = (z0 + z1) + pnext;
-                dpi[k * CF_NX + ci] = dpik;
+                rk[R_DPI + ci] = dpik;
                 PS[ci] = dpik;
             }
             cf_syncwarp();
@@ -783,8 +766,8 @@ struct CfWarp
         // terminal stage: no inputs, no bounds, no dynamics
         if (lane < CF_NV) {
             const double duxN = (lane < CF_NU) ? 0.0 : dxk;
-            dux[N * CF_NV + lane] = duxN;
-            double rgl = HN * duxN + res_g[N * CF_NV + lane];
+            double rgl = HN * duxN + rec(N)[R_RESG + lane];
+            rec(N)[R_DUX + lane] = duxN;
             if (N > 0 && lane >= CF_NU) rgl -= dpi_prev;
             lg = fmax(lg, fabs(rgl));
         }
@@ -799,30 +782,31 @@ struct CfWarp
     CF_MEM void backward_rhs(int rm_mode, double sigma_mu)
     {
         double *TS = sm + CF_SM_V0;
+        const int VO = R_DLAM, VN = R_DUX - R_DLAM;   // staged part of the stage record: [R_DLAM, R_DUX)
         pass_begin();
-        if (N > 0) fetch(0, N - 1, N - 1, -1);
+        if (N > 0) fetch(0, N - 1, N - 1, -1, N - 1, VO, VN);
         // terminal stage: rhs = res_g_N, nothing to eliminate (dummy inputs are zero)
         double pn = 0.0;  // lanes 4..16: p_{k+1}
         if (lane < CF_NV) {
-            pn = res_g[N * CF_NV + lane];
-            dux[N * CF_NV + lane] = pn;
+            pn = rec(N)[R_RESG + lane];
+            rec(N)[R_DUX + lane] = pn;
         }
         if (lane == 13) TS[13] = 0.0;
         CF_NOUNROLL
         for (int k = N - 1; k >= 0; k--) {
             const int bf = (N - 1 - k) & 1;
-            double Gam = 0.0, gam = 0.0;
-            if (lane < CF_NU) bound_terms(k, rm_mode, sigma_mu, Gam, gam);
-            double rhs = 0.0, pbk = 0.0;
-            if (lane < CF_NV) rhs = res_g[k * CF_NV + lane] + gam;
-            if (lane >= CF_NU && lane < CF_NV) pbk = Pb[k * CF_NX + lane - CF_NU];
             cf_syncwarp();  // previous stage's reads of TS and of buffer bf^1 are complete
-            if (k > 0) fetch(bf ^ 1, k - 1, k - 1, -1);
-            if (lane >= CF_NU && lane < CF_NV) TS[lane - CF_NU] = pn + pbk;
+            if (k > 0) fetch(bf ^ 1, k - 1, k - 1, -1, k - 1, VO, VN);
             wait(bf);
-            cf_syncwarp();
             const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
             const double *LU = sm + (bf ? CF_SM_LB1 : CF_SM_LB0);
+            const double *VS = sm + (bf ? CF_SM_VS1 : CF_SM_VS0) - VO;   // VS[R_x] = staged field R_x
+            double Gam = 0.0, gam = 0.0;
+            if (lane < CF_NU) bound_terms(k, VS + R_DLAM, rm_mode, sigma_mu, Gam, gam);
+            double rhs = 0.0;
+            if (lane < CF_NV) rhs = VS[R_RESG + lane] + gam;
+            if (lane >= CF_NU && lane < CF_NV) TS[lane - CF_NU] = pn + VS[R_PB + lane - CF_NU];
+            cf_syncwarp();
             if (lane < CF_NV) {
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
@@ -845,7 +829,7 @@ struct CfWarp
                 if (lane == j) rhs = zj;
                 else if (lane > j && lane < CF_NV) rhs -= Lr[j] * zj;
             }
-            if (lane < CF_NV) dux[k * CF_NV + lane] = rhs;
+            if (lane < CF_NV) rec(k)[R_DUX + lane] = rhs;
             pn = rhs;
         }
         cf_syncwarp();
@@ -858,8 +842,8 @@ struct CfWarp
         const int e = lane & 7;
         CF_NOUNROLL
         for (int k = lane >> 3; k < N; k += 4) {
-            const double *bk = bnd + (long) k * CF_BND;
-            s += (bk[CF_F_LAM * 8 + e] + alpha * bk[CF_F_DLAM * 8 + e]) * (bk[CF_F_T * 8 + e] + alpha * bk[CF_F_DT * 8 + e]);
+            const double *rk = rec(k);
+            s += (rk[R_LAM + e] + alpha * rk[R_DLAM + e]) * (rk[R_T + e] + alpha * rk[R_DT + e]);
         }
         mu_aff = cf_warp_sum(s) * (1.0 / (double) (2 * CF_NU * N));
     }
@@ -976,11 +960,11 @@ CF_DEV void cf_rti_instance(const CfParams *P, const CfBatchView &bv, int inst, 
         const int lane = w.lane;
         CF_NOUNROLL
         for (int k = 0; k <= N; k++) {
-            if (lane < CF_NU && k < N) ug[k * CF_NU + lane] += w.ux[k * CF_NV + lane];
+            if (lane < CF_NU && k < N) ug[k * CF_NU + lane] += w.rec(k)[R_UX + lane];
             if (lane >= CF_NU && lane < CF_NV) {
                 const int i = lane - CF_NU;
                 if (k == 0) xg[i] += x0g[i] - xg[i];
-                else xg[k * CF_NX + i] += w.ux[k * CF_NV + lane];
+                else xg[k * CF_NX + i] += w.rec(k)[R_UX + lane];
             }
         }
     } else {

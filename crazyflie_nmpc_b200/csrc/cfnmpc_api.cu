@@ -348,7 +348,7 @@ extern "C" int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_dou
     if (!h) return fail(CFNMPC_EINVAL, "null handle");
     CfScratchLayout s = cf_scratch_layout(h->N);
     if (offsets12) {
-        long long v[12] = {s.M, s.L, s.b, s.rq, s.ux, s.pi, s.res_g, s.dux, s.dpi, s.Pb, s.bnd, s.total};
+        long long v[12] = {s.M, s.L, s.rec, s.total, CF_REC, R_UX, R_PI, R_RQ, R_B, R_RESG, R_DUX, R_D};
         memcpy(offsets12, v, sizeof v);
     }
     if (n_doubles) *n_doubles = (size_t) s.total;

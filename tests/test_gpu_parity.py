@@ -119,27 +119,33 @@ def test_qp_data_intermediates(port):
         ref_BAbt = lin["BAbt"].copy()
         ref_BAbt[0, 4:, :] = 0.0                                       # A0 rows dropped by the x0 elimination
         assert np.abs(BAbt - ref_BAbt).max() <= 1e-11 * np.abs(ref_BAbt).max()
-        b = buf[off["b"]: off["b"] + N * 13].reshape(N, 13)
+        rec = buf[off["rec"]: off["rec"] + (N + 1) * off["rec_stride"]].reshape(N + 1, off["rec_stride"])
+        b = rec[:N, off["r_b"]: off["r_b"] + 13]
         xbar = wi["x0"][0] - wi["x_init"][0, 0]
         ref_b = lin["b"].copy()
         ref_b[0] += lin["BAbt"][0, 4:, :].T @ xbar
         assert np.abs(b - ref_b).max() <= 1e-11 * max(1.0, np.abs(ref_b).max())
-        rq = buf[off["rq"]: off["rq"] + (N + 1) * 17].reshape(N + 1, 17)
+        rq = rec[:, off["r_rq"]: off["r_rq"] + 17]
         ref_rq = np.zeros((N + 1, 17))
         ref_rq[:N] = lin["rqz"][:N * 17].reshape(N, 17)
         ref_rq[N, 4:] = lin["rqz"][N * 17:]
         ref_rq[0, 4:] = 0.0
         assert np.abs(rq - ref_rq).max() <= 1e-11 * np.abs(ref_rq).max()
+        d = rec[:N, off["r_d"]: off["r_d"] + 8]
+        ref_d = np.concatenate([np.r_[lin["d_lb"][:4], lin["d_ub"][:4]][None]] +
+                               [np.r_[lin["d_lb"][17 + 4 * (k - 1): 21 + 4 * (k - 1)], lin["d_ub"][17 + 4 * (k - 1): 21 + 4 * (k - 1)]][None]
+                                for k in range(1, N)])
+        assert np.abs(d - ref_d).max() <= 1e-12
         # QP solution (the step) against the oracle's
         x, u = wi["x_init"][0].copy(), wi["u_init"][0].copy()
         st, info, dux, dpi = port.rti(N, TS, wi["x0"][0], wi["yref"][0], wi["yref_e"][0], x, u, want_step=True)
-        ux = buf[off["ux"]: off["ux"] + (N + 1) * 17].reshape(N + 1, 17)
+        ux = rec[:, off["r_ux"]: off["r_ux"] + 17]
         ref_ux = np.zeros((N + 1, 17))
         ref_ux[:N] = dux[:N * 17].reshape(N, 17)
         ref_ux[N, 4:] = dux[N * 17:]
         ref_ux[0, 4:] = 0.0
         assert np.abs(ux - ref_ux).max() <= 1e-9 * (1 + np.abs(ref_ux).max())
-        pi = buf[off["pi"]: off["pi"] + N * 13]
+        pi = rec[:N, off["r_pi"]: off["r_pi"] + 13].ravel()
         assert np.abs(pi - dpi).max() <= 1e-9 * (1 + np.abs(dpi).max())
 
 
