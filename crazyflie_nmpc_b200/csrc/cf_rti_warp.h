@@ -35,7 +35,7 @@
 #define CF_MROWS 18                       // rows of [B';A';res_b'] held per stage
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
 #define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
-#define CF_LX 104                         // factor, state block: packed lower rows (91) + last row l~x (13)
+#define CF_LX 104                         // cost-to-go of the state block: packed lower triangle of P (91) + p (13)
 #define CF_LFSZ (CF_LU + CF_LX)           // 176 doubles per stage
 // Per-stage record of all IPM vectors (192 doubles).  The field order makes what each sweep reads one
 // contiguous, 16-byte aligned range, so it is staged by a single TMA bulk copy one stage ahead:
@@ -461,157 +461,189 @@ struct CfWarp
         gam = gl - gu;
     }
 
-    // OCP_QP_FACT_SOLVE_KKT_STEP, backward factorisation (x_ocp_qp_kkt.c:445-528):
-    //   L_k = chol( [H_k + Gamma ; (res_g + gamma)'] + AL AL' ),  AL = [B';A';res_b']_k Lxx_{k+1}
-    // The factor rows of the stage just finished stay in shared memory (LS) for the next TRMM.
+    // OCP_QP_FACT_SOLVE_KKT_STEP, backward factorisation.  HPIPM's classical Riccati recursion
+    // (square_root_alg = 0, x_ocp_qp_kkt.c:573-740) instead of the square-root variant the reference selects
+    // (:445-528): only the 4 input columns of each stage block are Cholesky-factorised, the state block is kept as the
+    // symmetric cost-to-go Hessian P_k.  Same arithmetic cost, but 4 instead of 17 strictly sequential pivot steps per
+    // stage and every matrix product is a tensor-core tile product; on this OCP the two recursions agree to 1e-14
+    // (oracle/cfnmpc_oracle.c: cfo_set_classical_riccati, tests/test_oracle_golden.py).  Per stage k < N:
+    //   W   = [B';A';res_b']_k P_{k+1}                      GEMM_NT :621   (row 17: Pb_k = P res_b, then += p_{k+1}')
+    //   S   = [H_k + Gamma ; (res_g + gamma)'] + W [B';A']'  SYRK_LN_MN :652
+    //   L   = chol of the 4 input columns of S               POTRF_L_MN(nv+1, nu) :653
+    //   P_k = S_xx - Ls Ls',  p_k = s_x - Ls l_u             SYRK -1 :655
+    // Stored per stage: LU (18 x 4 factor columns) and the packed lower triangle of P_k followed by p_k.
     CF_MEM void factorize()
     {
-        double *LS = sm + CF_SM_LS, *ALS = sm + CF_SM_ALS, *V = sm + CF_SM_V0, *G = sm + CF_SM_V1, *HD = sm + CF_SM_V2;
+        double *PS = sm + CF_SM_W;                 // P_{k+1}, full symmetric 13 x 13, stride 20
+        double *WS = sm + CF_SM_W + 13 * CF_ALST;  // W rows 18 x 16 (stride 20); later the 18 x 4 input-column block
+        double *PV = sm + CF_SM_V0, *G = sm + CF_SM_V1, *HD = sm + CF_SM_V2;
         pass_begin();
         if (N > 0) fetch(0, N - 1, -1, -1);
-        for (int i = lane; i < 18 * 18; i += 32) LS[i] = 0.0;
-        // lanes 17..31 all act as row 17 (they compute and store identical values), so the Cholesky
-        // loop below runs without lane predicates
-        const bool row = lane < CF_MROWS;
-        const int rl = lane < 17 ? lane : 17;
-        double *own = LS + rl * 18;
         // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
         const int fg = lane >> 2, fq = lane & 3;
+        const int rl = lane < CF_MROWS ? lane : 17;
+        // ---- terminal stage: no dynamics. P_N = diag(H_N) + reg, p_N = res_g_N; dummy inputs decoupled.
+        {
+            double *LFN = LF + (long) N * CF_LFSZ;
+            for (int i = lane; i < 13 * CF_ALST; i += 32) PS[i] = 0.0;
+            for (int i = lane; i < CF_LFSZ; i += 32) LFN[i] = 0.0;
+            cf_syncwarp();
+            const double hN = HN + CF_REG_PRIM;
+            if (lane < CF_NU) LFN[lane * 4 + lane] = sqrt(hN);
+            if (lane >= CF_NU && lane < CF_NV) {
+                const int i = lane - CF_NU;
+                const double gN = rec(N)[R_RESG + lane];
+                PS[i * CF_ALST + i] = hN;
+                PV[i] = gN;
+                LFN[CF_LU + cf_tri(i) + i] = hN;
+                LFN[CF_LU + 91 + i] = gN;
+            }
+        }
         CF_NOUNROLL
-        for (int k = N; k >= 0; k--) {
-            // gradient row and diagonal of the stage Hessian; bound data are independent of the matrices
+        for (int k = N - 1; k >= 0; k--) {
+            // gradient row and diagonal of the stage Hessian; their global loads overlap the first product
             double Gam = 0.0, gam = 0.0;
-            if (lane < CF_NU && k < N) bound_terms(k, rec(k) + R_DLAM, 0, 0.0, Gam, gam);
+            if (lane < CF_NU) bound_terms(k, rec(k) + R_DLAM, 0, 0.0, Gam, gam);
             const double g = (lane < CF_NV) ? rec(k)[R_RESG + lane] + gam : 0.0;
-            const double hd = ((k == N) ? HN : Hs) + CF_REG_PRIM + Gam;
-            if (k < N) {
-                const int bf = (N - 1 - k) & 1;
-                wait(bf);
-                cf_syncwarp();  // every lane is done with buffer bf^1 and with V/G/HD of the previous stage
-                if (k > 0) fetch(bf ^ 1, k - 1, -1, -1);
-                const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
-                // ---- TRMM_RLNN on the fp64 tensor cores: AL(18x13) = [B';A';res_b'](18x13) * Lxx(13x13, lower).
-                // Row tiles t = 0..2 (rows 8t+fg), column tiles 0..1 (columns 8t'+2fq+{0,1}), K padded to 16.
-                // Lxx is lower triangular: for column tile 1 (n >= 8) only k >= 8 contributes.
-                double al[3][2][2];
-                CF_UNROLL
-                for (int t = 0; t < 3; t++) { al[t][0][0] = al[t][0][1] = al[t][1][0] = al[t][1][1] = 0.0; }
-                CF_UNROLL
-                for (int kk = 0; kk < 4; kk++) {
-                    const int kc = 4 * kk + fq;                 // k index: column of M, row of Lxx
-                    const bool kv = kc < CF_NX;
-                    const double *Lk = LS + (CF_NU + (kv ? kc : 0)) * 18 + CF_NU;
-                    const double b0 = kv ? Lk[fg] : 0.0;       // Lxx[kc][fg]
-                    const double b1 = (kk >= 2 && kv && fg < CF_NX - 8) ? Lk[8 + fg] : 0.0;   // Lxx[kc][8+fg]
-                    CF_UNROLL
-                    for (int t = 0; t < 3; t++) {
-                        const int r = 8 * t + fg;
-                        const double a = (kv && r < CF_MROWS) ? Mk[kc * CF_MROWS + r] : 0.0;
-                        cf_dmma(al[t][0][0], al[t][0][1], a, b0);
-                        if (kk >= 2) cf_dmma(al[t][1][0], al[t][1][1], a, b1);
-                    }
-                }
-                // row 17 (tile 2, fg == 1): V = res_b' Lxx for Pb, then + l~x of stage k+1 (GEAD, :494)
-                if (fg == 1) {
-                    cf_st2(V + 2 * fq, al[2][0][0], al[2][0][1]);
-                    cf_st2(V + 8 + 2 * fq, al[2][1][0], al[2][1][1]);
-                    const double *lt = LS + 17 * 18 + CF_NU;
-                    al[2][0][0] += lt[2 * fq]; al[2][0][1] += lt[2 * fq + 1];
-                    if (8 + 2 * fq < CF_NX) al[2][1][0] += lt[8 + 2 * fq];
-                    if (9 + 2 * fq < CF_NX) al[2][1][1] += lt[9 + 2 * fq];
-                }
+            const double hd = Hs + CF_REG_PRIM + Gam;
+            const int bf = (N - 1 - k) & 1;
+            wait(bf);
+            cf_syncwarp();  // every lane is done with buffer bf^1, PS/PV of stage k+1 are complete
+            if (k > 0) fetch(bf ^ 1, k - 1, -1, -1);
+            const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
+            // ---- W(18x13) = M(18x13) * P(13x13): row tiles t (rows 8t+fg), column tiles 0..1, K padded to 16
+            double a[3][4];     // a[t][kk] = M[8t+fg][4kk+fq]: A fragment here, B fragment (M') of the second product
+            double wt[3][2][2];
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) { wt[t][0][0] = wt[t][0][1] = wt[t][1][0] = wt[t][1][1] = 0.0; }
+            CF_UNROLL
+            for (int kk = 0; kk < 4; kk++) {
+                const int kc = 4 * kk + fq;
+                const bool kv = kc < CF_NX;
+                const double *Pk = PS + (kv ? kc : 0) * CF_ALST;
+                const double b0 = kv ? Pk[fg] : 0.0;                          // P[kc][fg]
+                const double b1 = (kv && fg < CF_NX - 8) ? Pk[8 + fg] : 0.0;  // P[kc][8+fg]
                 CF_UNROLL
                 for (int t = 0; t < 3; t++) {
                     const int r = 8 * t + fg;
-                    if (r < CF_MROWS) {
-                        cf_st2(ALS + r * CF_ALST + 2 * fq, al[t][0][0], al[t][0][1]);
-                        cf_st2(ALS + r * CF_ALST + 8 + 2 * fq, al[t][1][0], al[t][1][1]);
-                    }
+                    a[t][kk] = (kv && r < CF_MROWS) ? Mk[kc * CF_MROWS + r] : 0.0;
+                    cf_dmma(wt[t][0][0], wt[t][0][1], a[t][kk], b0);
+                    cf_dmma(wt[t][1][0], wt[t][1][1], a[t][kk], b1);
                 }
-                G[lane] = g;      // published only now: the global loads behind g / hd overlap the TRMM
-                HD[lane] = hd;
-                cf_syncwarp();
-                // Pb = Lxx * (Lxx' res_b)  (TRMV_LNN, :492-493): lane 4+i uses its own factor row
-                if (lane >= CF_NU && lane < CF_NV) {
+            }
+            // row 17 (tile 2, fg == 1): Pb_k = P res_b (ROWEX :622), then + p_{k+1}' (GEAD :623)
+            if (fg == 1) {
+                double *pb = rec(k) + R_PB;
+                CF_UNROLL
+                for (int tp = 0; tp < 2; tp++)
+                    CF_UNROLL
+                    for (int e = 0; e < 2; e++) {
+                        const int c = 8 * tp + 2 * fq + e;
+                        if (c < CF_NX) { pb[c] = wt[2][tp][e]; wt[2][tp][e] += PV[c]; }
+                    }
+            }
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                const int r = 8 * t + fg;
+                if (r < CF_MROWS) {
+                    cf_st2(WS + r * CF_ALST + 2 * fq, wt[t][0][0], wt[t][0][1]);
+                    cf_st2(WS + r * CF_ALST + 8 + 2 * fq, wt[t][1][0], wt[t][1][1]);
+                }
+            }
+            G[lane] = g;      // published only now: the global loads behind g / hd overlapped the first product
+            HD[lane] = hd;
+            cf_syncwarp();
+            // ---- S = D + W * M': A fragments from W, B fragments are the M fragments already in registers
+            double wf[3][4];
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                const int r = 8 * t + fg;
+                CF_UNROLL
+                for (int kk = 0; kk < 4; kk++) wf[t][kk] = (r < CF_MROWS) ? WS[r * CF_ALST + 4 * kk + fq] : 0.0;
+            }
+            double s[3][3][2];  // lower tiles (t, tp <= t): S[8t+fg][8tp+2fq+{0,1}]
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                CF_UNROLL
+                for (int tp = 0; tp <= t; tp++) {
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
-                    for (int cp = 0; cp < 7; cp++) {
-                        const cf_d2 l2 = cf_ld2(own + CF_NU + 2 * cp), v2 = cf_ld2(V + 2 * cp);
-                        s0 += l2.x * v2.x;
-                        s1 += l2.y * v2.y;
-                    }
-                    rec(k)[R_PB + lane - CF_NU] = s0 + s1;
+                    for (int kk = 0; kk < 4; kk++) cf_dmma(s0, s1, wf[t][kk], a[tp][kk]);
+                    const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
+                    if (r == 17) { s0 += G[c0 < 17 ? c0 : 0]; s1 += G[c0 + 1 < 17 ? c0 + 1 : 0]; }
+                    if (r == c0) s0 += HD[r];
+                    if (r == c0 + 1) s1 += HD[r];
+                    s[t][tp][0] = s0; s[t][tp][1] = s1;
                 }
-                // ---- SYRK_LN on the tensor cores: S = D + AL * AL'; the same fragment serves as A and as B
-                double fr[3][4];
+            }
+            cf_syncwarp();  // every lane has its W fragments: WS is reused for the 18 x 4 input-column block
+            double *LUs = WS;
+            if (fq < 2) {
                 CF_UNROLL
                 for (int t = 0; t < 3; t++) {
                     const int r = 8 * t + fg;
-                    CF_UNROLL
-                    for (int kk = 0; kk < 4; kk++) fr[t][kk] = (r < CF_MROWS) ? ALS[r * CF_ALST + 4 * kk + fq] : 0.0;
+                    if (r < CF_MROWS) cf_st2(LUs + r * 4 + 2 * fq, s[t][0][0], s[t][0][1]);
                 }
-                cf_syncwarp();  // all reads of the old factor rows (TRMM, Pb) are complete: LS may be overwritten
+            }
+            cf_syncwarp();
+            // ---- POTRF_L_MN(nv+1, nu): the 4 input columns, one per step, lane = row; non-positive pivot -> 0
+            // (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
+            {
+                const cf_d2 o01 = cf_ld2(LUs + rl * 4), o23 = cf_ld2(LUs + rl * 4 + 2);
+                double o[CF_NU] = {o01.x, o01.y, o23.x, o23.y};
+                CF_UNROLL
+                for (int j = 0; j < CF_NU; j++) {
+                    double v = o[j];
+                    CF_UNROLL
+                    for (int c = 0; c < j; c++) v -= o[c] * LUs[j * 4 + c];
+                    const double piv = cf_shfl(v, j);
+                    double dj, inv;
+                    cf_sqrt_rsqrt(piv, dj, inv);
+                    if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; }
+                    o[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
+                    LUs[rl * 4 + j] = o[j];
+                    cf_syncwarp();
+                }
+                // factor columns to global memory (LU block of stage k)
+                double *LFk = LF + (long) k * CF_LFSZ;
+                if (lane < CF_MROWS) {
+                    cf_st2(LFk + lane * 4, o[0], o[1]);
+                    cf_st2(LFk + lane * 4 + 2, o[2], o[3]);
+                }
+            }
+            // ---- Schur complement on the tensor cores (K = 4 = the input columns): S -= Ls Ls'
+            double la[3];
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                const int r = 8 * t + fg;
+                la[t] = (r < CF_MROWS) ? LUs[r * 4 + fq] : 0.0;
+            }
+            cf_syncwarp();  // all reads of PS/PV (first product) are long complete; they are rewritten below
+            {
+                double *LFk = LF + (long) k * CF_LFSZ + CF_LU;
                 CF_UNROLL
                 for (int t = 0; t < 3; t++) {
                     CF_UNROLL
                     for (int tp = 0; tp <= t; tp++) {
-                        double s0 = 0.0, s1 = 0.0;
+                        cf_dmma(s[t][tp][0], s[t][tp][1], -la[t], la[tp]);
+                        const int r = 8 * t + fg;
                         CF_UNROLL
-                        for (int kk = 0; kk < 4; kk++) cf_dmma(s0, s1, fr[t][kk], fr[tp][kk]);
-                        const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
-                        if (r == 17) { s0 += G[c0 < 17 ? c0 : 0]; s1 += G[c0 + 1 < 17 ? c0 + 1 : 0]; }
-                        if (r == c0) s0 += HD[r];
-                        if (r == c0 + 1) s1 += HD[r];
-                        if (r < CF_MROWS) {
-                            if (tp < 2) cf_st2(LS + r * 18 + c0, s0, s1);
-                            else if (fq == 0) LS[r * 18 + 16] = s0;   // column 16; column 17 is padding and stays 0
+                        for (int e = 0; e < 2; e++) {
+                            const int c = 8 * tp + 2 * fq + e;
+                            const double val = s[t][tp][e];
+                            if (c >= CF_NU && c < CF_NV) {
+                                const int jx = c - CF_NU;
+                                if (r == 17) { PV[jx] = val; LFk[91 + jx] = val; }           // p_k
+                                else if (r >= c && r < CF_NV) {                             // P_k, lower part + mirror
+                                    const int ix = r - CF_NU;
+                                    PS[ix * CF_ALST + jx] = val;
+                                    PS[jx * CF_ALST + ix] = val;
+                                    LFk[cf_tri(ix) + jx] = val;
+                                }
+                            }
                         }
                     }
                 }
-            } else {
-                // terminal stage: no dynamics, S = [diag(H) ; g']
-                G[lane] = g;
-                cf_syncwarp();
-                CF_NOUNROLL
-                for (int j = 0; j < CF_NV; j++) own[j] = (lane >= 17) ? G[j] : ((lane == j) ? hd : 0.0);
-            }
-            cf_syncwarp();
-            // POTRF_L_MN, left-looking, one column per step; non-positive pivot -> 0
-            // (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
-            CF_NOUNROLL
-            for (int j = 0; j < CF_NV; j++) {
-                const double *Lj = LS + j * 18;
-                double v0 = own[j], v1 = 0.0;
-                CF_UNROLL
-                for (int cp = 0; cp < 8; cp++) {
-                    if (2 * cp + 1 >= j) break;
-                    const cf_d2 a2 = cf_ld2(own + 2 * cp), b2 = cf_ld2(Lj + 2 * cp);
-                    v0 -= a2.x * b2.x;
-                    v1 -= a2.y * b2.y;
-                }
-                if (j & 1) v0 -= own[j - 1] * Lj[j - 1];
-                const double v = v0 + v1;
-                const double piv = cf_shfl(v, j);
-                double dj, inv;
-                cf_sqrt_rsqrt(piv, dj, inv);
-                if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; }
-                own[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
-                cf_syncwarp();
-            }
-            // store the factor: LU block 18 x 4, LX packed rows + last row
-            double *LFk = LF + (long) k * CF_LFSZ;
-            if (row) {
-                const cf_d2 a2 = cf_ld2(own), b2 = cf_ld2(own + 2);
-                cf_st2(LFk + lane * 4, a2.x, a2.y);
-                cf_st2(LFk + lane * 4 + 2, b2.x, b2.y);
-            }
-            if (lane >= CF_NU && lane < CF_NV) {
-                const int i = lane - CF_NU;
-                double *dst = LFk + CF_LU + cf_tri(i);
-                CF_UNROLL
-                for (int c = 0; c < CF_NX; c++)
-                    if (c <= i) dst[c] = own[CF_NU + c];
-                LFk[CF_LU + 91 + i] = LS[17 * 18 + CF_NU + i];
             }
         }
         cf_syncwarp();
@@ -624,7 +656,7 @@ struct CfWarp
     // rm_mode selects which complementarity rhs the step was computed for (see bound_terms).
     CF_MEM void forward(int mode, int rm_mode)
     {
-        double *XS = sm + CF_SM_V0, *DS = sm + CF_SM_V1, *YS = sm + CF_SM_V2, *PS = sm + CF_SM_V3;
+        double *XS = sm + CF_SM_V0, *DS = sm + CF_SM_V1, *PS = sm + CF_SM_V3;
         double a_p = -1.0, a_d = -1.0;            // running alpha_prim / alpha_dual (negated)
         double lg = 0, lb = 0, ld = 0, lm = 0;    // linear residual norms
         double dxk = 0.0;        // lanes 4..16: dx_k ; stage 0 has none
@@ -632,7 +664,7 @@ struct CfWarp
         const int VO = R_LAM, VN = CF_REC - R_LAM;   // staged part of the stage record: [R_LAM, end)
         pass_begin();
         if (N > 0) fetch(0, 0, 0, 1, 0, VO, VN);
-        XS[lane] = 0.0; YS[lane] = 0.0; PS[lane] = 0.0;
+        XS[lane] = 0.0; PS[lane] = 0.0;
         const bool xl = lane >= CF_NU && lane < CF_NV;
         const int ci = xl ? lane - CF_NU : 0;
         CF_NOUNROLL
@@ -721,29 +753,19 @@ struct CfWarp
                 XS[ci] = dxn;
             }
             cf_syncwarp();
-            // ---- dpi = Lxx (Lxx' dx+ + l~x)  [mode 0]   |   p_{k+1} + Lxx Lxx' dx+  [mode 1]
-            if (xl) {
-                double y0 = (mode == 0) ? LX[91 + ci] : 0.0, y1 = 0.0;
-                CF_UNROLL
-                for (int i = 0; i < CF_NX; i++)  // column ci of the packed rows: entries i >= ci
-                    if (i >= ci) {
-                        if (i & 1) y1 += LX[(i * (i + 1)) / 2 + ci] * XS[i];
-                        else y0 += LX[(i * (i + 1)) / 2 + ci] * XS[i];
-                    }
-                YS[ci] = y0 + y1;
-            }
-            cf_syncwarp();
+            // ---- dpi = P_{k+1} dx+ + p_{k+1}   (GEMV_N :712,729); P packed lower, p from the factorisation (mode 0)
+            // or from the backward rhs sweep (mode 1)
             double dpik = 0.0;
             if (xl) {
-                const double *Li = LX + cf_tri(ci);  // row ci: entries c <= ci
-                double z0 = 0.0, z1 = 0.0;
+                const double *Li = LX + cf_tri(ci);   // row ci: entries c <= ci; entries c > ci come from column ci
+                double z0 = (mode == 0) ? LX[91 + ci] : pnext, z1 = 0.0;
                 CF_UNROLL
-                for (int c = 0; c < CF_NX; c++)
-                    if (c <= ci) {
-                        if (c & 1) z1 += Li[c] * YS[c];
-                        else z0 += Li[c] * YS[c];
-                    }
-                dpik = (z0 + z1) + pnext;
+                for (int c = 0; c < CF_NX; c++) {
+                    const double pc = (c <= ci) ? Li[c] : LX[(c * (c + 1)) / 2 + ci];
+                    if (c & 1) z1 += pc * XS[c];
+                    else z0 += pc * XS[c];
+                }
+                dpik = z0 + z1;
                 rk[R_DPI + ci] = dpik;
                 PS[ci] = dpik;
             }

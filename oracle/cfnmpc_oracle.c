@@ -230,6 +230,7 @@ typedef struct
     double rg2[NV], rb2[NX], rd2[2 * NU], rm2[2 * NU];                /* res_itref */
     double dux2[NV], dpi2[NX], dlam2[2 * NU], dt2[2 * NU];            /* sol_itref */
     double L[NV + 1][NV];
+    double Pm[NX][NX], pv[NX]; /* classical Riccati: cost-to-go Hessian / gradient of this stage */
     double Gamma[2 * NU], gamma[2 * NU], t_inv[2 * NU], Pb[NX];
 } stage;
 
@@ -246,6 +247,12 @@ typedef struct
 static const double RES_G_MAX = 1e-6, RES_B_MAX = 1e-8, RES_D_MAX = 1e-8, RES_M_MAX = 1e-8;
 static const double ALPHA_MIN = 1e-8, MU0 = 1.0, REG_PRIM = 1e-15, LAM_MIN = 1e-16, T_MIN = 1e-16, TAU_MIN = 1e-16;
 static const int ITER_MAX = 50, ITREF_CORR_MAX = 2;
+
+/* 0: square-root Riccati (the reference configuration, x_ocp_qp_kkt.c:445-572);
+ * 1: HPIPM's classical Riccati (square_root_alg = 0, x_ocp_qp_kkt.c:573-740) -- the variant the CUDA
+ * factorisation uses; kept here so that tests can quantify the difference between the two. */
+static int g_classical = 0;
+void cfo_set_classical_riccati(int on) { g_classical = on; }
 
 /* lower Cholesky of the n x n top of an m x n block, remaining rows solved;
  * non-positive pivot -> 0 (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714) */
@@ -320,6 +327,14 @@ static void ric_forward(ipm *w, double (*pl)[NX], int itref, int l_is_scaled)
             ndux[n->nu + c] = v + rb[c];
         }
         /* dpi: x_ocp_qp_kkt.c:545-547 (factorise) / :1262-1266 (solve) */
+        if (g_classical) { /* dpi = P dx+ + p   (GEMV_N, x_ocp_qp_kkt.c:712,729) */
+            for (int r = 0; r < NX; r++) {
+                double v = pl[k + 1][r];
+                for (int c = 0; c < NX; c++) v += n->Pm[r][c] * ndux[n->nu + c];
+                dpi[r] = v;
+            }
+            continue;
+        }
         double tmp[NX];
         for (int c = 0; c < NX; c++) {
             double v = 0;
@@ -340,7 +355,46 @@ static void fact_solve_kkt_step(ipm *w)
     int N = w->N;
     double(*pl)[NX] = malloc(sizeof(double[NX]) * (N + 1));
     compute_Gamma_gamma(w, 1, 0);
-    for (int k = N; k >= 0; k--) {
+    for (int k = N; k >= 0 && g_classical; k--) {
+        stage *s = &w->s[k];
+        double AL[NV + 1][NX];
+        if (k < N) {
+            stage *n = &w->s[k + 1];
+            for (int r = 0; r <= s->nv; r++) /* AL = [B';A';res_b'] * P(k+1)   (GEMM_NT, :621) */
+                for (int c = 0; c < NX; c++) {
+                    double v = 0;
+                    for (int j = 0; j < NX; j++) v += (r < s->nv ? s->M[r][j] : s->res_b[j]) * n->Pm[j][c];
+                    AL[r][c] = v;
+                }
+            for (int c = 0; c < NX; c++) { s->Pb[c] = AL[s->nv][c]; AL[s->nv][c] += n->pv[c]; }
+        }
+        memset(s->L, 0, sizeof s->L);
+        for (int i = 0; i < s->nv; i++) { s->L[i][i] = s->H[i] + REG_PRIM; s->L[s->nv][i] = s->res_g[i]; }
+        for (int i = 0; i < s->nb; i++) {
+            s->L[i][i] += s->Gamma[i] + s->Gamma[s->nb + i];
+            s->L[s->nv][i] += s->gamma[i] - s->gamma[s->nb + i];
+        }
+        if (k < N)
+            for (int r = 0; r <= s->nv; r++) /* SYRK_LN_MN(AL, BAbt) :652 */
+                for (int c = 0; c <= r && c < s->nv; c++) {
+                    double v = 0;
+                    for (int j = 0; j < NX; j++) v += AL[r][j] * s->M[c][j];
+                    s->L[r][c] += v;
+                }
+        potrf_l_mn(s->nv + 1, s->nu, s->L); /* only the nu input columns are factorised :653 */
+        for (int r = 0; r < s->nx; r++) /* P = Sxx - Ls Ls' (SYRK -1, :655), symmetrised (TRTR_L) */
+            for (int c = 0; c <= r; c++) {
+                double v = s->L[s->nu + r][s->nu + c];
+                for (int j = 0; j < s->nu; j++) v -= s->L[s->nu + r][j] * s->L[s->nu + c][j];
+                s->Pm[r][c] = s->Pm[c][r] = v;
+            }
+        for (int c = 0; c < s->nx; c++) {
+            double v = s->L[s->nv][s->nu + c];
+            for (int j = 0; j < s->nu; j++) v -= s->L[s->nv][j] * s->L[s->nu + c][j];
+            s->pv[c] = v;
+        }
+    }
+    for (int k = N; k >= 0 && !g_classical; k--) {
         stage *s = &w->s[k];
         double AL[NV + 1][NX];
         if (k < N) {
@@ -379,7 +433,7 @@ static void fact_solve_kkt_step(ipm *w)
     for (int k = 0; k <= N; k++) {
         stage *s = &w->s[k];
         for (int i = 0; i < s->nu; i++) s->dux[i] = -s->L[s->nv][i];
-        for (int i = 0; i < s->nx; i++) pl[k][i] = s->L[s->nv][s->nu + i];
+        for (int i = 0; i < s->nx; i++) pl[k][i] = g_classical ? s->pv[i] : s->L[s->nv][s->nu + i];
     }
     ric_forward(w, pl, 0, 1);
     compute_lam_t(w, 0);
@@ -406,6 +460,12 @@ static void solve_kkt_step(ipm *w, int use_Pb, int itref)
             double tmp[NX];
             if (use_Pb) {
                 for (int i = 0; i < NX; i++) tmp[i] = ndux[n->nu + i] + s->Pb[i];
+            } else if (g_classical) {
+                for (int r = 0; r < NX; r++) {
+                    double v = ndux[n->nu + r];
+                    for (int c = 0; c < NX; c++) v += n->Pm[r][c] * rb[c];
+                    tmp[r] = v;
+                }
             } else {
                 double t2[NX];
                 for (int c = 0; c < NX; c++) {
