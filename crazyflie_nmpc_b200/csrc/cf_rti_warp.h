@@ -499,13 +499,24 @@ struct CfWarp
                 LFN[CF_LU + 91 + i] = gN;
             }
         }
+        // gradient row and diagonal of the stage Hessian are computed one stage ahead (software pipelining:
+        // the global loads behind them complete during the previous stage's tile products)
+        double g_nx = 0.0, hd_nx = 0.0;
+        if (N > 0) {
+            double Gam = 0.0, gam = 0.0;
+            if (lane < CF_NU) bound_terms(N - 1, rec(N - 1) + R_DLAM, 0, 0.0, Gam, gam);
+            g_nx = (lane < CF_NV) ? rec(N - 1)[R_RESG + lane] + gam : 0.0;
+            hd_nx = Hs + CF_REG_PRIM + Gam;
+        }
         CF_NOUNROLL
         for (int k = N - 1; k >= 0; k--) {
-            // gradient row and diagonal of the stage Hessian; their global loads overlap the first product
-            double Gam = 0.0, gam = 0.0;
-            if (lane < CF_NU) bound_terms(k, rec(k) + R_DLAM, 0, 0.0, Gam, gam);
-            const double g = (lane < CF_NV) ? rec(k)[R_RESG + lane] + gam : 0.0;
-            const double hd = Hs + CF_REG_PRIM + Gam;
+            const double g = g_nx, hd = hd_nx;
+            if (k > 0) {
+                double Gam = 0.0, gam = 0.0;
+                if (lane < CF_NU) bound_terms(k - 1, rec(k - 1) + R_DLAM, 0, 0.0, Gam, gam);
+                g_nx = (lane < CF_NV) ? rec(k - 1)[R_RESG + lane] + gam : 0.0;
+                hd_nx = Hs + CF_REG_PRIM + Gam;
+            }
             const int bf = (N - 1 - k) & 1;
             wait(bf);
             cf_syncwarp();  // every lane is done with buffer bf^1, PS/PV of stage k+1 are complete
@@ -550,7 +561,7 @@ struct CfWarp
                     cf_st2(WS + r * CF_ALST + 8 + 2 * fq, wt[t][1][0], wt[t][1][1]);
                 }
             }
-            G[lane] = g;      // published only now: the global loads behind g / hd overlapped the first product
+            G[lane] = g;
             HD[lane] = hd;
             cf_syncwarp();
             // ---- S = D + W * M': A fragments from W, B fragments are the M fragments already in registers
@@ -860,14 +871,22 @@ struct CfWarp
     // COMPUTE_MU_AFF_QP (x_core_qp_ipm_aux.c:329-352): all 32 lanes sweep the bound records
     CF_MEM void compute_mu_aff()
     {
-        double s = 0.0;
+        double s0 = 0.0, s1 = 0.0;
         const int e = lane & 7;
+        int k = lane >> 3;
         CF_NOUNROLL
-        for (int k = lane >> 3; k < N; k += 4) {
-            const double *rk = rec(k);
-            s += (rk[R_LAM + e] + alpha * rk[R_DLAM + e]) * (rk[R_T + e] + alpha * rk[R_DT + e]);
+        for (; k + 4 < N; k += 8) {   // two stages per trip: eight independent loads in flight per lane
+            const double *ra = rec(k), *rb = rec(k + 4);
+            const double la = ra[R_LAM + e], da = ra[R_DLAM + e], ta = ra[R_T + e], ua = ra[R_DT + e];
+            const double lb = rb[R_LAM + e], db = rb[R_DLAM + e], tb = rb[R_T + e], ub = rb[R_DT + e];
+            s0 += (la + alpha * da) * (ta + alpha * ua);
+            s1 += (lb + alpha * db) * (tb + alpha * ub);
         }
-        mu_aff = cf_warp_sum(s) * (1.0 / (double) (2 * CF_NU * N));
+        if (k < N) {
+            const double *ra = rec(k);
+            s0 += (ra[R_LAM + e] + alpha * ra[R_DLAM + e]) * (ra[R_T + e] + alpha * ra[R_DT + e]);
+        }
+        mu_aff = cf_warp_sum(s0 + s1) * (1.0 / (double) (2 * CF_NU * N));
     }
 
     CF_MEM bool lin_res_ok_fact() const
