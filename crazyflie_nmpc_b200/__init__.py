@@ -173,7 +173,7 @@ class BatchSolver:
         _check(lib().cfnmpc_debug_scratch(self._h, None, 0, ctypes.byref(n), offs))
         buf = np.empty(n.value)
         _check(lib().cfnmpc_debug_scratch(self._h, ctypes.c_void_p(buf.ctypes.data), n.value, None, None))
-        names = ["M", "L", "rec", "total", "rec_stride", "r_ux", "r_pi", "r_rq", "r_b", "r_resg", "r_dux", "r_d"]
+        names = ["total", "blk_stride", "b_m", "b_lu", "b_px", "r_ux", "r_pi", "r_rq", "r_b", "r_resg", "r_dux", "r_d"]
         return buf, dict(zip(names, list(offs)))
 
     def debug_max_ipm_iter(self, n):

@@ -42,6 +42,15 @@
 //   residual sweep  [R_UX, R_RESD)  (+ R_DUX)      forward sweep  [R_LAM, end)      backward sweep  [R_DLAM, R_DUX)
 // 17-vectors are padded to 18, 13-vectors to 14; bound fields are [lb(4) | ub(4)].
 #define CF_REC 192
+// One contiguous block per stage in the scratch slot: [ record | [B';A';res_b'] | LU | PX ], so that whatever a
+// sweep needs of a stage is ONE contiguous, 16-byte aligned range = one TMA bulk copy:
+//   residual [0, B_LU)   backward [R_DLAM, B_PX)   forward [R_LAM, CF_SB)   factorisation [B_M, B_LU)
+// PX of block k holds P_{k+1} | p_{k+1} (what the forward sweep of stage k multiplies with); it is written by the
+// factorisation of stage k+1.
+#define B_M CF_REC
+#define B_LU (B_M + CF_MSZ)
+#define B_PX (B_LU + CF_LU)
+#define CF_SB (B_PX + CF_LX)              // 602 doubles per stage
 enum { R_UX = 0, R_PI = 18, R_DPI = 32, R_RQ = 46, R_B = 64, R_D = 78, R_DLAM = 86, R_DT = 94, R_LAM = 102, R_T = 110,
        R_RESD = 118, R_BKP = 126, R_RESM = 134, R_RESG = 142, R_PB = 160, R_DUX = 174 };
 
@@ -99,7 +108,7 @@ struct CfBatchView
 // touches (M, LF) starts on a 16-byte boundary
 struct CfScratchLayout
 {
-    long M, L, rec, total;
+    long blk, total;
 };
 static inline
 #if !defined(CF_SIMT_EMU)
@@ -109,31 +118,24 @@ static inline
     cf_scratch_layout(int N)
 {
     CfScratchLayout s;
-    long o = 0;
-    s.M = o;     o += (long) N * CF_MSZ;
-    s.L = o;     o += (long) (N + 1) * CF_LFSZ;
-    s.rec = o;   o += (long) (N + 1) * CF_REC;
-    s.total = (o + 15) & ~15L;  // keep every slot 128-byte aligned
+    s.blk = 0;
+    s.total = ((long) (N + 1) * CF_SB + 15) & ~15L;  // keep every slot 128-byte aligned
     return s;
 }
 
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
-#define CF_SM_MS0 0                            // [B';A';res_b']_k staging, double buffered
+#define CF_SM_BUF0 0                           // sweeps: staged range of a stage block, double buffered (<= 500 doubles)
+#define CF_SM_BUF1 500
+#define CF_SM_MS0 0                            // factorisation / linearisation: [B';A';res_b'] staging, double buffered
 #define CF_SM_MS1 CF_MSZ
-#define CF_SM_W (2 * CF_MSZ)                   // 684-double work region:
-#define CF_SM_LS CF_SM_W                       //   factorisation: 18 x 18 factor rows (stride 18) ...
-#define CF_SM_ALS (CF_SM_W + 324)              //   ... and 18 x 20 AL rows (stride 20: conflict-free DMMA fragment loads)
-#define CF_ALST 20
-#define CF_SM_LB0 CF_SM_W                      //   sweeps: factor block staging [LU 72 | LX 104], double buffered
-#define CF_SM_LB1 (CF_SM_W + CF_LFSZ)
-#define CF_SM_VS0 (CF_SM_W + 2 * CF_LFSZ)      //   sweeps: staged part of the stage record, double buffered (<= 136 doubles)
-#define CF_SM_VS1 (CF_SM_VS0 + 136)
-#define CF_SM_V0 (CF_SM_W + 324 + 18 * CF_ALST) // four 32-double broadcast vectors
+#define CF_SM_W (2 * CF_MSZ)                   // factorisation: P_{k+1} (13 x 20) and W / input-column block (18 x 20)
+#define CF_ALST 20                             //   row stride 20: conflict-free fp64 tensor-core fragment loads
+#define CF_SM_V0 (CF_SM_W + 31 * CF_ALST)      // four 32-double broadcast vectors (after the larger of 2*500 and 468+620)
 #define CF_SM_V1 (CF_SM_V0 + 32)
 #define CF_SM_V2 (CF_SM_V1 + 32)
 #define CF_SM_V3 (CF_SM_V2 + 32)
 #define CF_SM_BAR (CF_SM_V3 + 32)              // two mbarriers
-#define CF_SM_DOUBLES (CF_SM_BAR + 4)          // 1284 doubles = 10272 bytes per warp (5 blocks of 4 warps per SM)
+#define CF_SM_DOUBLES (CF_SM_BAR + 4)          // 1220 doubles = 9760 bytes per warp (5 blocks of 4 warps per SM)
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
@@ -146,7 +148,7 @@ struct CfWarp
     uint64_t *bar;
     unsigned par;  // phase parity of the two mbarriers
     // scratch arrays
-    double *M, *LF, *REC;
+    double *SLOT;
     // lane constants
     double Hs, HN;     // Hessian diagonal for this lane's variable (stage / terminal)
     // IPM scalars (warp-uniform)
@@ -161,7 +163,7 @@ struct CfWarp
         bar = reinterpret_cast<uint64_t *>(sm_ + CF_SM_BAR);
         par = 0;
         CfScratchLayout s = cf_scratch_layout(N);
-        M = slot + s.M; LF = slot + s.L; REC = slot + s.rec;
+        SLOT = slot + s.blk;
         // hess = scaling * (sqrt(W))^2 : ocp_nlp_cost_ls.c:739-772 (terminal scaling stays 1.0, :265)
         double w = 1.0, wN = 1.0;
         if (lane < CF_NU) w = P->Wdiag[CF_NX + lane];
@@ -177,26 +179,18 @@ struct CfWarp
         cf_syncwarp();                            // all generic stores of the previous pass are ordered ...
         if (lane == 0) cf_fence_proxy_async();    // ... before the bulk (async-proxy) reads of this pass
     }
-    CF_MEM double *rec(int k) const { return REC + (long) k * CF_REC; }
-    // fetch into buffer `bf`: [B';A';res_b']_km (if km >= 0), LU_ku (if ku >= 0), LX_kx (if kx >= 0) and up to two
-    // ranges [o1, o1+n1), [o2, o2+n2) of the stage record kv (if kv >= 0), packed back to back in VS
-    CF_MEM void fetch(int bf, int km, int ku, int kx, int kv = -1, int o1 = 0, int n1 = 0, int o2 = 0, int n2 = 0)
+    CF_MEM double *blk(int k) const { return SLOT + (long) k * CF_SB; }
+    CF_MEM double *rec(int k) const { return blk(k); }
+    CF_MEM double *buf(int bf) const { return sm + (bf ? CF_SM_BUF1 : CF_SM_BUF0); }
+    // stage doubles [start, start+len) of stage block k into buffer `bf` (one bulk copy, lane 0 issues)
+    CF_MEM void fetch_to(double *dst, int bf, int k, int start, int len)
     {
         if (lane == 0) {
-            const int bytes = (km >= 0 ? CF_MSZ * 8 : 0) + (ku >= 0 ? CF_LU * 8 : 0) + (kx >= 0 ? CF_LX * 8 : 0) +
-                              (kv >= 0 ? (n1 + n2) * 8 : 0);
-            cf_bulk_expect(bar + bf, bytes);
-            double *ms = sm + (bf ? CF_SM_MS1 : CF_SM_MS0), *lb = sm + (bf ? CF_SM_LB1 : CF_SM_LB0);
-            double *vs = sm + (bf ? CF_SM_VS1 : CF_SM_VS0);
-            if (km >= 0) cf_bulk_g2s_raw(ms, M + (long) km * CF_MSZ, CF_MSZ * 8, bar + bf);
-            if (ku >= 0) cf_bulk_g2s_raw(lb, LF + (long) ku * CF_LFSZ, CF_LU * 8, bar + bf);
-            if (kx >= 0) cf_bulk_g2s_raw(lb + CF_LU, LF + (long) kx * CF_LFSZ + CF_LU, CF_LX * 8, bar + bf);
-            if (kv >= 0) {
-                cf_bulk_g2s_raw(vs, rec(kv) + o1, n1 * 8, bar + bf);
-                if (n2 > 0) cf_bulk_g2s_raw(vs + n1, rec(kv) + o2, n2 * 8, bar + bf);
-            }
+            cf_bulk_expect(bar + bf, len * 8);
+            cf_bulk_g2s_raw(dst, blk(k) + start, len * 8, bar + bf);
         }
     }
+    CF_MEM void fetch(int bf, int k, int start, int len) { fetch_to(buf(bf), bf, k, start, len); }
     CF_MEM void wait(int bf)
     {
         cf_bulk_wait(bar + bf, (par >> bf) & 1u);
@@ -295,7 +289,7 @@ struct CfWarp
             rec(k)[R_D + 4 + lane] = UU[lane] - P->ubu[lane];
         }
         cf_syncwarp();
-        if (lane == 0) cf_bulk_s2g(M + (long) k * CF_MSZ, MS, CF_MSZ * 8);
+        if (lane == 0) cf_bulk_s2g(blk(k) + B_M, MS, CF_MSZ * 8);
         xk_pre = xn_pre;
         uk_pre = un_pre;
     }
@@ -341,9 +335,8 @@ struct CfWarp
         if (do_update && a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
         double ng = 0, nb = 0, nd = 0, nm = 0, mus = 0;
         double *UXS = sm + CF_SM_V0, *PIS = sm + CF_SM_V1;
-        const int n2 = do_update ? 18 : 0;   // the step dux is needed only when the variables are updated
         pass_begin();
-        fetch(0, N > 0 ? 0 : -1, -1, -1, 0, R_UX, R_RESD - R_UX, R_DUX, n2);
+        fetch(0, 0, 0, B_LU);
         const bool xl = lane >= CF_NU && lane < CF_NV;
         const int ci = xl ? lane - CF_NU : 0;
         double pi_prev = 0.0;            // lanes 4..16: pi_{k-1}
@@ -352,19 +345,19 @@ struct CfWarp
         for (int k = 0; k <= N; k++) {
             const int bf = k & 1;
             cf_syncwarp();  // previous stage's reads of UXS/PIS and of buffer bf^1 are complete
-            if (k < N) fetch(bf ^ 1, k + 1 < N ? k + 1 : -1, -1, -1, k + 1, R_UX, R_RESD - R_UX, R_DUX, n2);
+            if (k < N) fetch(bf ^ 1, k + 1, 0, k + 1 < N ? B_LU : CF_REC);
             wait(bf);
-            const double *VS = sm + (bf ? CF_SM_VS1 : CF_SM_VS0);
+            const double *VS = buf(bf);   // block k from offset 0: record fields at their own offsets, M at B_M
             double *rk = rec(k);
             double uxc = 0.0, pik = 0.0;
             if (lane < CF_NV) {
                 uxc = VS[R_UX + lane];
-                if (do_update) { uxc += a * VS[R_RESD + lane]; rk[R_UX + lane] = uxc; }
+                if (do_update) { uxc += a * VS[R_DUX + lane]; rk[R_UX + lane] = uxc; }
             }
             if (k > 0 && xl) {  // res_b_{k-1} = (b - x+) + [A B] ux, stored as row 17 of M_{k-1} (ROWIN of x_ocp_qp_kkt.c:490)
                 const double rb = (b_prev - uxc) + sb_prev;
                 nb = fmax(nb, fabs(rb));
-                M[(long) (k - 1) * CF_MSZ + ci * CF_MROWS + 17] = rb;
+                blk(k - 1)[B_M + ci * CF_MROWS + 17] = rb;
             }
             if (k < N && xl) {
                 pik = VS[R_PI + ci];
@@ -400,7 +393,7 @@ struct CfWarp
                 if (lane < CF_NV) UXS[lane] = uxc;
                 if (xl) PIS[ci] = pik;
                 cf_syncwarp();
-                const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
+                const double *Mk = VS + B_M;
                 if (lane < CF_NV) {  // res_g += [B';A'] pi_k   (row layout: own elements stride 18)
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
@@ -478,25 +471,24 @@ struct CfWarp
         double *WS = sm + CF_SM_W + 13 * CF_ALST;  // W rows 18 x 16 (stride 20); later the 18 x 4 input-column block
         double *PV = sm + CF_SM_V0, *G = sm + CF_SM_V1, *HD = sm + CF_SM_V2;
         pass_begin();
-        if (N > 0) fetch(0, N - 1, -1, -1);
+        if (N > 0) fetch_to(sm + CF_SM_MS0, 0, N - 1, B_M, CF_MSZ);
         // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
         const int fg = lane >> 2, fq = lane & 3;
         const int rl = lane < CF_MROWS ? lane : 17;
         // ---- terminal stage: no dynamics. P_N = diag(H_N) + reg, p_N = res_g_N; dummy inputs decoupled.
         {
-            double *LFN = LF + (long) N * CF_LFSZ;
+            double *PXN = blk(N > 0 ? N - 1 : 0) + B_PX;   // P_N | p_N belong to the block of stage N-1
             for (int i = lane; i < 13 * CF_ALST; i += 32) PS[i] = 0.0;
-            for (int i = lane; i < CF_LFSZ; i += 32) LFN[i] = 0.0;
+            for (int i = lane; i < CF_LX; i += 32) PXN[i] = 0.0;
             cf_syncwarp();
             const double hN = HN + CF_REG_PRIM;
-            if (lane < CF_NU) LFN[lane * 4 + lane] = sqrt(hN);
             if (lane >= CF_NU && lane < CF_NV) {
                 const int i = lane - CF_NU;
                 const double gN = rec(N)[R_RESG + lane];
                 PS[i * CF_ALST + i] = hN;
                 PV[i] = gN;
-                LFN[CF_LU + cf_tri(i) + i] = hN;
-                LFN[CF_LU + 91 + i] = gN;
+                PXN[cf_tri(i) + i] = hN;
+                PXN[91 + i] = gN;
             }
         }
         // gradient row and diagonal of the stage Hessian are computed one stage ahead (software pipelining:
@@ -520,7 +512,7 @@ struct CfWarp
             const int bf = (N - 1 - k) & 1;
             wait(bf);
             cf_syncwarp();  // every lane is done with buffer bf^1, PS/PV of stage k+1 are complete
-            if (k > 0) fetch(bf ^ 1, k - 1, -1, -1);
+            if (k > 0) fetch_to(sm + ((bf ^ 1) ? CF_SM_MS1 : CF_SM_MS0), bf ^ 1, k - 1, B_M, CF_MSZ);
             const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
             // ---- W(18x13) = M(18x13) * P(13x13): row tiles t (rows 8t+fg), column tiles 0..1, K padded to 16
             double a[3][4];     // a[t][kk] = M[8t+fg][4kk+fq]: A fragment here, B fragment (M') of the second product
@@ -616,7 +608,7 @@ struct CfWarp
                     cf_syncwarp();
                 }
                 // factor columns to global memory (LU block of stage k)
-                double *LFk = LF + (long) k * CF_LFSZ;
+                double *LFk = blk(k) + B_LU;
                 if (lane < CF_MROWS) {
                     cf_st2(LFk + lane * 4, o[0], o[1]);
                     cf_st2(LFk + lane * 4 + 2, o[2], o[3]);
@@ -631,7 +623,7 @@ struct CfWarp
             }
             cf_syncwarp();  // all reads of PS/PV (first product) are long complete; they are rewritten below
             {
-                double *LFk = LF + (long) k * CF_LFSZ + CF_LU;
+                double *LFk = blk(k > 0 ? k - 1 : 0) + B_PX;   // P_k | p_k go to the block of stage k-1 (no consumer for k = 0)
                 CF_UNROLL
                 for (int t = 0; t < 3; t++) {
                     CF_UNROLL
@@ -644,12 +636,12 @@ struct CfWarp
                             const double val = s[t][tp][e];
                             if (c >= CF_NU && c < CF_NV) {
                                 const int jx = c - CF_NU;
-                                if (r == 17) { PV[jx] = val; LFk[91 + jx] = val; }           // p_k
+                                if (r == 17) { PV[jx] = val; if (k > 0) LFk[91 + jx] = val; }   // p_k
                                 else if (r >= c && r < CF_NV) {                             // P_k, lower part + mirror
                                     const int ix = r - CF_NU;
                                     PS[ix * CF_ALST + jx] = val;
                                     PS[jx * CF_ALST + ix] = val;
-                                    LFk[cf_tri(ix) + jx] = val;
+                                    if (k > 0) LFk[cf_tri(ix) + jx] = val;
                                 }
                             }
                         }
@@ -672,9 +664,9 @@ struct CfWarp
         double lg = 0, lb = 0, ld = 0, lm = 0;    // linear residual norms
         double dxk = 0.0;        // lanes 4..16: dx_k ; stage 0 has none
         double dpi_prev = 0.0;   // lanes 4..16: dpi_{k-1}
-        const int VO = R_LAM, VN = CF_REC - R_LAM;   // staged part of the stage record: [R_LAM, end)
+        const int VO = R_LAM, VN = CF_SB - R_LAM;   // staged part of the stage block: [R_LAM, end)
         pass_begin();
-        if (N > 0) fetch(0, 0, 0, 1, 0, VO, VN);
+        if (N > 0) fetch(0, 0, VO, VN);
         XS[lane] = 0.0; PS[lane] = 0.0;
         const bool xl = lane >= CF_NU && lane < CF_NV;
         const int ci = xl ? lane - CF_NU : 0;
@@ -685,10 +677,9 @@ struct CfWarp
             const double pnext = (mode == 1 && xl) ? rec(k + 1)[R_DUX + lane] : 0.0;  // p_{k+1} of the backward sweep
             wait(bf);
             cf_syncwarp();  // every lane is done with buffer bf^1
-            if (k + 1 < N) fetch(bf ^ 1, k + 1, k + 1, k + 2, k + 1, VO, VN);
-            const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
-            const double *LU = sm + (bf ? CF_SM_LB1 : CF_SM_LB0), *LX = LU + CF_LU;
-            const double *VS = sm + (bf ? CF_SM_VS1 : CF_SM_VS0) - VO;   // VS[R_x] = staged field R_x
+            if (k + 1 < N) fetch(bf ^ 1, k + 1, VO, VN);
+            const double *VS = buf(bf) - VO;   // VS[offset within the stage block]
+            const double *Mk = VS + B_M, *LU = VS + B_LU, *LX = VS + B_PX;
             // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu)
             double v = 0.0, invd = 1.0;
             if (lane < CF_NU) {
@@ -815,9 +806,9 @@ struct CfWarp
     CF_MEM void backward_rhs(int rm_mode, double sigma_mu)
     {
         double *TS = sm + CF_SM_V0;
-        const int VO = R_DLAM, VN = R_DUX - R_DLAM;   // staged part of the stage record: [R_DLAM, R_DUX)
+        const int VO = R_DLAM, VN = B_PX - R_DLAM;   // staged part of the stage block: [R_DLAM, B_PX)
         pass_begin();
-        if (N > 0) fetch(0, N - 1, N - 1, -1, N - 1, VO, VN);
+        if (N > 0) fetch(0, N - 1, VO, VN);
         // terminal stage: rhs = res_g_N, nothing to eliminate (dummy inputs are zero)
         double pn = 0.0;  // lanes 4..16: p_{k+1}
         if (lane < CF_NV) {
@@ -829,11 +820,10 @@ struct CfWarp
         for (int k = N - 1; k >= 0; k--) {
             const int bf = (N - 1 - k) & 1;
             cf_syncwarp();  // previous stage's reads of TS and of buffer bf^1 are complete
-            if (k > 0) fetch(bf ^ 1, k - 1, k - 1, -1, k - 1, VO, VN);
+            if (k > 0) fetch(bf ^ 1, k - 1, VO, VN);
             wait(bf);
-            const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
-            const double *LU = sm + (bf ? CF_SM_LB1 : CF_SM_LB0);
-            const double *VS = sm + (bf ? CF_SM_VS1 : CF_SM_VS0) - VO;   // VS[R_x] = staged field R_x
+            const double *VS = buf(bf) - VO;   // VS[offset within the stage block]
+            const double *Mk = VS + B_M, *LU = VS + B_LU;
             double Gam = 0.0, gam = 0.0;
             if (lane < CF_NU) bound_terms(k, VS + R_DLAM, rm_mode, sigma_mu, Gam, gam);
             double rhs = 0.0;

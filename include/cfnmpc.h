@@ -108,7 +108,8 @@ int cfnmpc_batch_last_solve_ms(cfnmpc_batch *h, double *ms);
 
 /* Test hook: copy the scratch slot that solved instance 0 when batch == 1 (QP data,
  * factors, IPM vectors) and limit the IPM iteration count; see tests/test_gpu_parity.py. */
-/* offsets12 = {M, L, rec, total, rec_stride, r_ux, r_pi, r_rq, r_b, r_resg, r_dux, r_d} in doubles */
+/* offsets12 = {slot size, stage-block stride, b_m, b_lu, b_px, r_ux, r_pi, r_rq, r_b, r_resg, r_dux, r_d} in doubles
+ * (layout of a stage block: crazyflie_nmpc_b200/csrc/cf_rti_warp.h) */
 int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_doubles, size_t *n_doubles, long long *offsets12);
 int cfnmpc_debug_max_ipm_iter(cfnmpc_batch *h, int max_iter);
 

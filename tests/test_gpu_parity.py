@@ -114,12 +114,13 @@ def test_qp_data_intermediates(port):
             s.set_problem(wi).solve(1)
             buf, off = s.debug_scratch()
         lin = port.linearize(N, TS, wi["x0"][0], wi["yref"][0], wi["yref_e"][0], wi["x_init"][0], wi["u_init"][0])
-        M = buf[off["M"]: off["M"] + N * 234].reshape(N, 13, 18)       # [k][c][r]
+        blocks = buf[: (N + 1) * off["blk_stride"]].reshape(N + 1, off["blk_stride"])
+        M = blocks[:N, off["b_m"]: off["b_m"] + 234].reshape(N, 13, 18)   # [k][c][r]
         BAbt = np.transpose(M[:, :, :17], (0, 2, 1))                   # [k][r][c]
         ref_BAbt = lin["BAbt"].copy()
         ref_BAbt[0, 4:, :] = 0.0                                       # A0 rows dropped by the x0 elimination
         assert np.abs(BAbt - ref_BAbt).max() <= 1e-11 * np.abs(ref_BAbt).max()
-        rec = buf[off["rec"]: off["rec"] + (N + 1) * off["rec_stride"]].reshape(N + 1, off["rec_stride"])
+        rec = blocks
         b = rec[:N, off["r_b"]: off["r_b"] + 13]
         xbar = wi["x0"][0] - wi["x_init"][0, 0]
         ref_b = lin["b"].copy()
