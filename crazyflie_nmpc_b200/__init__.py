@@ -38,6 +38,7 @@ def lib():
         L.cfnmpc_batch_destroy.argtypes = [vp]
         L.cfnmpc_batch_set_stream.argtypes = [vp, vp]
         L.cfnmpc_batch_set.argtypes = [vp, cp, vp, ci]
+        L.cfnmpc_batch_clear.argtypes = [vp, cp]
         L.cfnmpc_batch_solve.argtypes = [vp, ci]
         L.cfnmpc_batch_sync.argtypes = [vp]
         L.cfnmpc_batch_get.argtypes = [vp, cp, ci, vp, ci]
@@ -71,7 +72,9 @@ class BatchSolver:
     """B independent Crazyflie NMPC instances advanced together, one warp per instance.
 
     set(field, array)   "x0" [B,13] | "yref" [B,N,17] | "yref_e" [B,13] | "x" [B,N+1,13] | "u" [B,N,4]
-                        | "W" [17] | "W_e" [13] | "lbu" | "ubu" [4]
+                        | "W" [17] | "W_e" [13] | "lbu" | "ubu" | "lbu0" | "ubu0" [4]   (solver-wide)
+                        | "W_batch" [B,17] | "W_e_batch" [B,13] | "lbu_batch" | "ubu_batch" | "lbu0_batch"
+                        | "ubu0_batch" [B,4]   (per instance; clear(field) returns to the solver-wide value)
     solve(n_rti=1)      enqueue RTI steps (asynchronous)
     get(field, stage)   "u"/"x" at a stage, "u_all", "x_all", "status", "qp_iter", "qp_status", "flags", "res"
     """
@@ -106,10 +109,16 @@ class BatchSolver:
     def _expected(self, field):
         B, N = self.B, self.N
         return {"x0": (B, NX), "yref": (B, N, NY), "yref_e": (B, NX), "x": (B, N + 1, NX), "u": (B, N, NU),
-                "W": (NY,), "W_e": (NX,), "lbu": (NU,), "ubu": (NU,)}[field]
+                "W": (NY,), "W_e": (NX,), "lbu": (NU,), "ubu": (NU,), "lbu0": (NU,), "ubu0": (NU,),
+                "W_batch": (B, NY), "W_e_batch": (B, NX), "lbu_batch": (B, NU), "ubu_batch": (B, NU),
+                "lbu0_batch": (B, NU), "ubu0_batch": (B, NU)}.get(field)
+
+    def clear(self, field):
+        _check(lib().cfnmpc_batch_clear(self._h, field.encode()))
+        return self
 
     def set(self, field, a):
-        if field not in ("x0", "yref", "yref_e", "x", "u", "W", "W_e", "lbu", "ubu"):
+        if self._expected(field) is None:
             raise CfnmpcError(f"unknown field '{field}'")
         n = int(np.prod(self._expected(field)))
         if hasattr(a, "data_ptr"):

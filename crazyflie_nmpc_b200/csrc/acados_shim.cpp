@@ -22,6 +22,7 @@ struct crazyflie_solver_capsule
     std::vector<double> x0, yref, yref_e, x, u;
     bool in_dirty = true, iterate_dirty = true;
     int status = 0, qp_iter = 0, qp_status = 0, cond_N = 0;
+    double lbu[4] = {0, 0, 0, 0}, ubu[4] = {22, 22, 22, 22}, lbu0[4] = {0, 0, 0, 0}, ubu0[4] = {22, 22, 22, 22};
     double time_tot = 0.0;
     ocp_nlp_plan_t plan;
     ocp_nlp_config config;
@@ -82,6 +83,7 @@ int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int
     }
     c->N = N;
     c->Ts = Ts;
+    for (int i = 0; i < 4; i++) { c->lbu[i] = c->lbu0[i] = 0.0; c->ubu[i] = c->ubu0[i] = 22.0; }  // generate_c_code.py:133-134
     // generate_c_code.py:128-129 reference, :135 x0
     const double g0 = 9.8066, mq = 33e-3, Ct = 3.25e-4;
     const double hov = __builtin_sqrt((mq * g0) / (4 * Ct));
@@ -192,8 +194,15 @@ int ocp_nlp_constraints_model_set(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_in *
         return 0;
     }
     if (!strcmp(field, "lbu") || !strcmp(field, "ubu")) {
+        // per-stage in the reference (ocp_nlp_constraints_bgh.c:653-674).  Supported granularity: stage 0 on its own
+        // (the node's FIXED_U0 branch, acados_mpc.cpp:604-608) and stages 1..N-1 together.
         if (stage < 0 || stage >= c->N || !c->batch) return 1;
-        return cfnmpc_batch_set(c->batch, field, value, 0) != CFNMPC_OK;
+        const bool lower = field[0] == 'l';
+        double *path = lower ? c->lbu : c->ubu, *first = lower ? c->lbu0 : c->ubu0;
+        memcpy(stage == 0 ? first : path, value, 4 * sizeof(double));
+        int rc = cfnmpc_batch_set(c->batch, lower ? "lbu" : "ubu", path, 0);
+        rc |= cfnmpc_batch_set(c->batch, lower ? "lbu0" : "ubu0", first, 0);
+        return rc != CFNMPC_OK;
     }
     return 1;
 }

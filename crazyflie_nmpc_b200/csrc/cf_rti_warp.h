@@ -80,11 +80,14 @@ struct CfParams
 {
     double Wdiag[CF_NY];   // stage weights, cost order y = [x;u] (generate_c_code.py:61-84)
     double WNdiag[CF_NX];  // terminal weights (:113)
-    double lbu[CF_NU], ubu[CF_NU];
+    double lbu[CF_NU], ubu[CF_NU];    // input box, stages 1..N-1
+    double lbu0[CF_NU], ubu0[CF_NU];  // input box of stage 0 (the node's FIXED_U0 branch pins it, acados_mpc.cpp:604-608)
     double Ts;
     int N;
     int max_ipm_iter;      // CF_ITER_MAX unless a test truncates the loop
 };
+#define CF_PAR_DOUBLES 48  // sizeof(CfParams) / 8: the per-warp copy in shared memory
+static_assert(sizeof(CfParams) == CF_PAR_DOUBLES * 8, "CfParams layout");
 
 struct CfBatchView
 {
@@ -102,6 +105,9 @@ struct CfBatchView
     double *scratch;       // n_slots * scratch_stride doubles
     long scratch_stride;
     int *counter;          // work queue
+    // optional per-instance overrides of the solver-wide CfParams (null = not given), SET_WEIGHTS / FIXED_U0 of the
+    // node with one value set per vehicle: W [B][17], W_e [B][13], lbu/ubu [B][4] (stages 1..N-1), lbu0/ubu0 [B][4]
+    const double *W_b, *WN_b, *lbu_b, *ubu_b, *lbu0_b, *ubu0_b;
 };
 
 // offsets (in doubles) of the arrays inside one scratch slot; every block that the TMA engine
@@ -135,7 +141,8 @@ static inline
 #define CF_SM_V2 (CF_SM_V1 + 32)
 #define CF_SM_V3 (CF_SM_V2 + 32)
 #define CF_SM_BAR (CF_SM_V3 + 32)              // two mbarriers
-#define CF_SM_DOUBLES (CF_SM_BAR + 4)          // 1220 doubles = 9760 bytes per warp (5 blocks of 4 warps per SM)
+#define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
+#define CF_SM_DOUBLES (CF_SM_PAR + CF_PAR_DOUBLES)  // 1268 doubles = 10144 bytes per warp (5 blocks of 4 warps per SM)
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
@@ -285,8 +292,8 @@ struct CfWarp
         }
         // bounds (ocp_nlp_constraints_bgh.c:1634-1636): d = [lb - u ; u - ub]
         if (lane < CF_NU) {
-            rec(k)[R_D + lane] = P->lbu[lane] - UU[lane];
-            rec(k)[R_D + 4 + lane] = UU[lane] - P->ubu[lane];
+            rec(k)[R_D + lane] = ((k == 0) ? P->lbu0[lane] : P->lbu[lane]) - UU[lane];
+            rec(k)[R_D + 4 + lane] = UU[lane] - ((k == 0) ? P->ubu0[lane] : P->ubu[lane]);
         }
         cf_syncwarp();
         if (lane == 0) cf_bulk_s2g(blk(k) + B_M, MS, CF_MSZ * 8);
@@ -966,8 +973,27 @@ CF_DEV void cf_warp_init_smem(double *sm)
     cf_syncwarp();
 }
 
-CF_DEV void cf_rti_instance(const CfParams *P, const CfBatchView &bv, int inst, double *slot, double *sm, unsigned &par)
+CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst, double *slot, double *sm, unsigned &par)
 {
+    // this instance's parameters: the solver-wide set, overridden by whatever per-instance arrays the caller gave
+    CfParams *P = reinterpret_cast<CfParams *>(sm + CF_SM_PAR);
+    {
+        const int lane = cf_lane();
+        const double *src = reinterpret_cast<const double *>(Pg);
+        double *dst = sm + CF_SM_PAR;
+        dst[lane] = src[lane];
+        if (lane + 32 < CF_PAR_DOUBLES) dst[lane + 32] = src[lane + 32];
+        cf_syncwarp();
+        if (bv.W_b && lane < CF_NY) P->Wdiag[lane] = bv.W_b[(long) inst * CF_NY + lane];
+        if (bv.WN_b && lane < CF_NX) P->WNdiag[lane] = bv.WN_b[(long) inst * CF_NX + lane];
+        if (lane < CF_NU) {
+            if (bv.lbu_b) P->lbu[lane] = P->lbu0[lane] = bv.lbu_b[(long) inst * CF_NU + lane];
+            if (bv.ubu_b) P->ubu[lane] = P->ubu0[lane] = bv.ubu_b[(long) inst * CF_NU + lane];
+            if (bv.lbu0_b) P->lbu0[lane] = bv.lbu0_b[(long) inst * CF_NU + lane];
+            if (bv.ubu0_b) P->ubu0[lane] = bv.ubu0_b[(long) inst * CF_NU + lane];
+        }
+        cf_syncwarp();
+    }
     CfWarp w;
     w.bind(P, slot, sm);
     w.par = par;

@@ -79,6 +79,7 @@ struct cfnmpc_batch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double *d_x0 = nullptr, *d_yref = nullptr, *d_yref_e = nullptr, *d_x = nullptr, *d_u = nullptr, *d_res = nullptr;
     double *d_scratch = nullptr, *d_stage = nullptr;
+    double *d_Wb = nullptr, *d_WNb = nullptr, *d_lbub = nullptr, *d_ubub = nullptr, *d_lbu0b = nullptr, *d_ubu0b = nullptr;
     int *d_status = nullptr, *d_qp_iter = nullptr, *d_qp_status = nullptr, *d_flags = nullptr, *d_counter = nullptr;
     int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 5;
     void (*kernel)(const CfParams, const CfBatchView) = nullptr;
@@ -92,7 +93,7 @@ static void default_params(CfParams &P, int N, double Ts)
     // generate_c_code.py:61-84 (Q, R), :113 (W_e = 50 Q), :133-134 (0 <= u <= 22)
     static const double Q[CF_NX] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
     for (int i = 0; i < CF_NX; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
-    for (int i = 0; i < CF_NU; i++) { P.Wdiag[CF_NX + i] = 0.06; P.lbu[i] = 0.0; P.ubu[i] = 22.0; }
+    for (int i = 0; i < CF_NU; i++) { P.Wdiag[CF_NX + i] = 0.06; P.lbu[i] = P.lbu0[i] = 0.0; P.ubu[i] = P.ubu0[i] = 22.0; }
     P.Ts = Ts; P.N = N; P.max_ipm_iter = CF_ITER_MAX;
 }
 
@@ -104,7 +105,8 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     if (!h) return CFNMPC_OK;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
-                    h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter};
+                    h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter,
+                    h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -193,6 +195,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     bv.B = batch; bv.x0 = h->d_x0; bv.yref = h->d_yref; bv.yref_e = h->d_yref_e; bv.x = h->d_x; bv.u = h->d_u;
     bv.status = h->d_status; bv.qp_iter = h->d_qp_iter; bv.qp_status = h->d_qp_status; bv.flags = h->d_flags;
     bv.res = h->d_res; bv.scratch = h->d_scratch; bv.scratch_stride = stride; bv.counter = h->d_counter;
+    bv.W_b = bv.WN_b = bv.lbu_b = bv.ubu_b = bv.lbu0_b = bv.ubu0_b = nullptr;
     CKH(cudaStreamSynchronize(h->stream));
 #undef CKH
     *out = h;
@@ -241,10 +244,34 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
     else if (!strcmp(field, "W_e")) { pdst = h->P.WNdiag; pn = CF_NX; }
     else if (!strcmp(field, "lbu")) { pdst = h->P.lbu; pn = CF_NU; }
     else if (!strcmp(field, "ubu")) { pdst = h->P.ubu; pn = CF_NU; }
+    else if (!strcmp(field, "lbu0")) { pdst = h->P.lbu0; pn = CF_NU; }
+    else if (!strcmp(field, "ubu0")) { pdst = h->P.ubu0; pn = CF_NU; }
     if (pdst) {
         if (src_on_device) CK(cudaMemcpy(pdst, src, pn * 8, cudaMemcpyDeviceToHost));
         else memcpy(pdst, src, pn * 8);
+        // "lbu"/"ubu" address every stage 0..N-1; "lbu0"/"ubu0" afterwards single out stage 0
+        if (pdst == h->P.lbu) memcpy(h->P.lbu0, h->P.lbu, sizeof h->P.lbu);
+        if (pdst == h->P.ubu) memcpy(h->P.ubu0, h->P.ubu, sizeof h->P.ubu);
         return CFNMPC_OK;
+    }
+    // per-instance parameter arrays: allocated on first use, then passed to the kernel instead of the solver-wide value
+    {
+        double **slot = nullptr;
+        const double **view = nullptr;
+        int w = 0;
+        if (!strcmp(field, "W_batch")) { slot = &h->d_Wb; view = &h->bv.W_b; w = CF_NY; }
+        else if (!strcmp(field, "W_e_batch")) { slot = &h->d_WNb; view = &h->bv.WN_b; w = CF_NX; }
+        else if (!strcmp(field, "lbu_batch")) { slot = &h->d_lbub; view = &h->bv.lbu_b; w = CF_NU; }
+        else if (!strcmp(field, "ubu_batch")) { slot = &h->d_ubub; view = &h->bv.ubu_b; w = CF_NU; }
+        else if (!strcmp(field, "lbu0_batch")) { slot = &h->d_lbu0b; view = &h->bv.lbu0_b; w = CF_NU; }
+        else if (!strcmp(field, "ubu0_batch")) { slot = &h->d_ubu0b; view = &h->bv.ubu0_b; w = CF_NU; }
+        if (slot) {
+            const size_t bytes = (size_t) h->B * w * 8;
+            if (!*slot) CK(cudaMalloc(slot, bytes));
+            CK(cudaMemcpyAsync(*slot, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+            *view = *slot;
+            return CFNMPC_OK;
+        }
     }
     FieldRef r;
     if (!strcmp(field, "x0") || !strcmp(field, "yref") || !strcmp(field, "yref_e") || !strcmp(field, "x") || !strcmp(field, "u")) {
@@ -253,6 +280,19 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         return CFNMPC_OK;
     }
     return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_set: unknown field '") + field + "'");
+}
+
+extern "C" int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field)
+{
+    if (!h || !field) return fail(CFNMPC_EINVAL, "cfnmpc_batch_clear: null argument");
+    if (!strcmp(field, "W_batch")) h->bv.W_b = nullptr;
+    else if (!strcmp(field, "W_e_batch")) h->bv.WN_b = nullptr;
+    else if (!strcmp(field, "lbu_batch")) h->bv.lbu_b = nullptr;
+    else if (!strcmp(field, "ubu_batch")) h->bv.ubu_b = nullptr;
+    else if (!strcmp(field, "lbu0_batch")) h->bv.lbu0_b = nullptr;
+    else if (!strcmp(field, "ubu0_batch")) h->bv.ubu0_b = nullptr;
+    else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_clear: '") + field + "' is not a per-instance parameter array");
+    return CFNMPC_OK;
 }
 
 extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)

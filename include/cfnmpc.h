@@ -75,8 +75,18 @@ int cfnmpc_batch_set_stream(cfnmpc_batch *h, void *cuda_stream);
  *   "W"       double [17]           diagonal of the stage weight matrix (all instances)
  *   "W_e"     double [13]           diagonal of the terminal weight matrix
  *   "lbu","ubu" double [4]          input bounds, stages 0..N-1
+ *   "lbu0","ubu0" double [4]        input bounds of stage 0 only (set after "lbu"/"ubu"): the node's FIXED_U0
+ *                                   branch pins u_0 this way, acados_mpc.cpp:604-608
+ * Per-instance parameter arrays (one value set per vehicle; the reference expresses this as one solver object per
+ * vehicle, each with its own ocp_nlp_cost_model_set(..,"W",..) / ocp_nlp_constraints_model_set(..,"lbu"|"ubu",..)
+ * calls, acados_mpc.cpp:596-608).  Once given they take precedence over the solver-wide value until cleared:
+ *   "W_batch"    double [B][17]     "W_e_batch"  double [B][13]
+ *   "lbu_batch","ubu_batch"   double [B][4]   stages 0..N-1
+ *   "lbu0_batch","ubu0_batch" double [B][4]   stage 0 only
  * Copies are asynchronous on the handle's stream. */
 int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *src, int src_on_device);
+/* Stop using a per-instance parameter array ("W_batch", ...): back to the solver-wide value. */
+int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field);
 
 /* Enqueue n_rti consecutive RTI steps (preparation + feedback) for every instance,
  * inputs frozen between steps.  Asynchronous; pair with cfnmpc_batch_sync or a

@@ -21,7 +21,8 @@ void cfo_default_params(cfo_params *p)
     /* generate_c_code.py:61-84,113,133-134 */
     static const double Q[NX] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
     for (int i = 0; i < NX; i++) { p->Wdiag[i] = Q[i]; p->WNdiag[i] = 50 * Q[i]; }
-    for (int i = 0; i < NU; i++) { p->Wdiag[NX + i] = 0.06; p->lbu[i] = 0.0; p->ubu[i] = 22.0; }
+    for (int i = 0; i < NU; i++) { p->Wdiag[NX + i] = 0.06; p->lbu[i] = p->lbu0[i] = 0.0; p->ubu[i] = p->ubu0[i] = 22.0; }
+    p->has_u0 = 0;
 }
 
 void cfo_ode(const double *x, const double *u, double *f)
@@ -199,8 +200,10 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
             }
             int nb = k == 0 ? NV : NU;
             for (int i = 0; i < NU; i++) {
-                if (d_lb) d_lb[od + i] = p_->lbu[i] - uk[i];
-                if (d_ub) d_ub[od + i] = uk[i] - p_->ubu[i];
+                /* per-stage bounds: ocp_nlp_constraints_bgh.c:653-674 (model_set copies into stage k only) */
+                const int s0 = (k == 0 && p_->has_u0);
+                if (d_lb) d_lb[od + i] = (s0 ? p_->lbu0[i] : p_->lbu[i]) - uk[i];
+                if (d_ub) d_ub[od + i] = uk[i] - (s0 ? p_->ubu0[i] : p_->ubu[i]);
             }
             if (k == 0)
                 for (int i = 0; i < NX; i++) {

@@ -37,7 +37,8 @@ def build(ref=True, quiet=True):
 
 class CfoParams(ctypes.Structure):
     _fields_ = [("Wdiag", ctypes.c_double * 17), ("WNdiag", ctypes.c_double * 13),
-                ("lbu", ctypes.c_double * 4), ("ubu", ctypes.c_double * 4)]
+                ("lbu", ctypes.c_double * 4), ("ubu", ctypes.c_double * 4), ("has_u0", ctypes.c_int),
+                ("lbu0", ctypes.c_double * 4), ("ubu0", ctypes.c_double * 4)]
 
 
 class CfoInfo(ctypes.Structure):
@@ -64,10 +65,14 @@ class Port:
         L.cfo_ode.argtypes = [_dp, _dp, _dp]
         L.cfo_default_params.argtypes = [ctypes.POINTER(CfoParams)]
 
-    def params(self, Wdiag=None, WNdiag=None, lbu=None, ubu=None):
+    def params(self, Wdiag=None, WNdiag=None, lbu=None, ubu=None, lbu0=None, ubu0=None):
         p = CfoParams()
         self.lib.cfo_default_params(ctypes.byref(p))
-        for name, v in (("Wdiag", Wdiag), ("WNdiag", WNdiag), ("lbu", lbu), ("ubu", ubu)):
+        if lbu0 is not None or ubu0 is not None:   # stage-0 bounds default to the path bounds
+            p.has_u0 = 1
+            lbu0 = lbu0 if lbu0 is not None else (lbu if lbu is not None else list(p.lbu))
+            ubu0 = ubu0 if ubu0 is not None else (ubu if ubu is not None else list(p.ubu))
+        for name, v in (("Wdiag", Wdiag), ("WNdiag", WNdiag), ("lbu", lbu), ("ubu", ubu), ("lbu0", lbu0), ("ubu0", ubu0)):
             if v is not None:
                 arr = getattr(p, name)
                 for i, e in enumerate(v):
@@ -137,6 +142,7 @@ class Ref:
         L.cfref_get_ipm_stat.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int, _ip]
         L.cfref_set_weights.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.cfref_set_input_bounds.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.cfref_set_input_bounds_stage0.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.cfref_batch.restype = ctypes.c_int
         L.cfref_batch.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
@@ -174,6 +180,9 @@ class RefSolver:
 
     def set_input_bounds(self, lbu, ubu):
         self.lib.cfref_set_input_bounds(self.h, _P(np.ascontiguousarray(lbu, float)), _P(np.ascontiguousarray(ubu, float)))
+
+    def set_input_bounds_stage0(self, lbu0, ubu0):
+        self.lib.cfref_set_input_bounds_stage0(self.h, _P(np.ascontiguousarray(lbu0, float)), _P(np.ascontiguousarray(ubu0, float)))
 
     def rti(self, x0, yref, yref_e, x, u):
         """One RTI step; x,u updated in place. Returns (status, qp_iter, qp_status, times[5])."""

@@ -209,6 +209,14 @@ void cfref_set_input_bounds(void *h_, const double *lbu, const double *ubu)
     }
 }
 
+/* stage-0 input box only: what the node's FIXED_U0 branch does (acados_mpc.cpp:604-608) */
+void cfref_set_input_bounds_stage0(void *h_, const double *lbu0, const double *ubu0)
+{
+    cfref *h = h_;
+    ocp_nlp_constraints_model_set(h->config, h->dims, h->in, 0, "lbu", (void *) lbu0);
+    ocp_nlp_constraints_model_set(h->config, h->dims, h->in, 0, "ubu", (void *) ubu0);
+}
+
 /* One RTI step exactly as NMPC::iteration does it (acados_mpc.cpp:581-625):
  * set x0 as lbx=ubx, set yref per stage, solve, read the iterate back.
  * x[(N+1)*13], u[N*4] are in/out (iterate before -> iterate after).

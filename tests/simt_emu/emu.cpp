@@ -222,10 +222,23 @@ extern "C" void cfemu_scratch_offsets(int N, long *out)
 }
 
 // params: Wdiag[17], WNdiag[13], lbu[4], ubu[4] (38 doubles) or NULL for the reference values
+// per_inst: six pointers {W [B][17], W_e [B][13], lbu, ubu, lbu0, ubu0 [B][4]}, any of them (or the array) NULL
+extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, int max_ipm_iter, const double *x0,
+                                const double *yref, const double *yref_e, double *x, double *u, int *status,
+                                int *qp_iter, int *qp_status, int *flags, double *res, double *scratch_out,
+                                int nthreads, const double *const *per_inst);
 extern "C" int cfemu_rti_batch(int B, int N, double Ts, const double *params, int max_ipm_iter, const double *x0,
                                const double *yref, const double *yref_e, double *x, double *u, int *status,
                                int *qp_iter, int *qp_status, int *flags, double *res, double *scratch_out,
                                int nthreads)
+{
+    return cfemu_rti_batch2(B, N, Ts, params, max_ipm_iter, x0, yref, yref_e, x, u, status, qp_iter, qp_status, flags, res,
+                            scratch_out, nthreads, nullptr);
+}
+extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, int max_ipm_iter, const double *x0,
+                                const double *yref, const double *yref_e, double *x, double *u, int *status,
+                                int *qp_iter, int *qp_status, int *flags, double *res, double *scratch_out,
+                                int nthreads, const double *const *per_inst)
 {
     CfParams P;
     static const double Q[13] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
@@ -235,12 +248,16 @@ extern "C" int cfemu_rti_batch(int B, int N, double Ts, const double *params, in
         memcpy(P.Wdiag, params, 17 * 8); memcpy(P.WNdiag, params + 17, 13 * 8);
         memcpy(P.lbu, params + 30, 4 * 8); memcpy(P.ubu, params + 34, 4 * 8);
     }
+    memcpy(P.lbu0, P.lbu, sizeof P.lbu); memcpy(P.ubu0, P.ubu, sizeof P.ubu);
     P.Ts = Ts; P.N = N; P.max_ipm_iter = max_ipm_iter > 0 ? max_ipm_iter : CF_ITER_MAX;
     const long stride = cf_scratch_layout(N).total;
     CfBatchView bv;
     bv.B = B; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
     bv.qp_iter = qp_iter; bv.qp_status = qp_status; bv.flags = flags; bv.res = res; bv.scratch = nullptr;
     bv.scratch_stride = stride; bv.counter = nullptr;
+    bv.W_b = per_inst ? per_inst[0] : nullptr; bv.WN_b = per_inst ? per_inst[1] : nullptr;
+    bv.lbu_b = per_inst ? per_inst[2] : nullptr; bv.ubu_b = per_inst ? per_inst[3] : nullptr;
+    bv.lbu0_b = per_inst ? per_inst[4] : nullptr; bv.ubu0_b = per_inst ? per_inst[5] : nullptr;
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(0);
     std::vector<std::thread> th;

@@ -163,6 +163,45 @@ def test_runtime_weights_and_bounds(port):
     assert (g["u"] >= lbu - 1e-6).all() and (g["u"] <= ubu + 1e-6).all()
 
 
+def test_per_instance_weights_and_bounds(port, ref):
+    """One weight set / input box / stage-0 box per vehicle ("W_batch", ... in cfnmpc.h): the batched form of the
+    node's SET_WEIGHTS and FIXED_U0 branches (acados_mpc.cpp:596-608).  Checked per instance against the port oracle
+    and, for a few instances, against the reference's own code with the same per-stage setter calls."""
+    from test_simt_emu import per_instance_params
+    N, B = 50, 48
+    w = wl.helix_batch(B, N, seed=41)
+    pp = per_instance_params(B, seed=9)
+    with cf.BatchSolver(B, N, TS) as s:
+        for k, v in pp.items():
+            s.set(k + "_batch", v)
+        s.set_problem(w).solve(1)
+        x, u, st, it = s.get("x_all"), s.get("u_all"), s.get("status"), s.get("qp_iter")
+        # clearing returns to the solver-wide values
+        for k in pp:
+            s.clear(k + "_batch")
+        s.set_problem(w).solve(1)
+        x_def, u_def = s.get("x_all"), s.get("u_all")
+    for i in range(B):
+        xo, uo = w["x_init"][i].copy(), w["u_init"][i].copy()
+        p = port.params(Wdiag=pp["W"][i], WNdiag=pp["W_e"][i], lbu=pp["lbu"][i], ubu=pp["ubu"][i], lbu0=pp["lbu0"][i], ubu0=pp["ubu0"][i])
+        sto, info = port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], xo, uo, params=p)
+        assert sto == st[i] and abs(info.qp_iter - it[i]) <= 1
+        assert rel_err(x[i], xo) <= TIGHT and rel_err(u[i], uo) <= TIGHT
+        assert (u[i, 0] >= pp["lbu0"][i] - 1e-6).all() and (u[i, 0] <= pp["ubu0"][i] + 1e-6).all()
+        assert (u[i, 1:] >= pp["lbu"][i] - 1e-6).all() and (u[i, 1:] <= pp["ubu"][i] + 1e-6).all()
+    for i in (0, B // 2, B - 1):
+        r = ref.solver(N, TS)
+        r.set_weights(pp["W"][i], pp["W_e"][i])
+        r.set_input_bounds(pp["lbu"][i], pp["ubu"][i])
+        r.set_input_bounds_stage0(pp["lbu0"][i], pp["ubu0"][i])
+        xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+        r.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)
+        r.close()
+        assert rel_err(x[i], xr) <= TIGHT and rel_err(u[i], ur) <= TIGHT
+    o = oracle_solve(port, w, N)
+    assert rel_err(x_def, o["x"]) <= TIGHT and rel_err(u_def, o["u"]) <= TIGHT
+
+
 def test_ragged_and_tiny_batches(port):
     N = 20
     for B in (1, 3, 5, 33):

@@ -27,7 +27,9 @@ def emu():
     L.cfemu_rti_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, ctypes.c_int, _dp, _dp, _dp, _dp, _dp,
                                   _ip, _ip, _ip, _ip, _dp, _dp, ctypes.c_int]
 
-    def run(w, N, n_rti=1, params=None):
+    L.cfemu_rti_batch2.argtypes = L.cfemu_rti_batch.argtypes + [ctypes.POINTER(_dp)]
+
+    def run(w, N, n_rti=1, params=None, per_inst=None):
         B = w["x0"].shape[0]
         x, u = w["x_init"].copy(), w["u_init"].copy()
         st, it, qs, fl = [np.zeros(B, np.int32) for _ in range(4)]
@@ -35,9 +37,14 @@ def emu():
         P = lambda a: a.ctypes.data_as(_dp)
         I = lambda a: a.ctypes.data_as(_ip)
         par = None if params is None else np.ascontiguousarray(np.concatenate(params), float)
+        pi = None
+        if per_inst is not None:   # dict with any of W, W_e, lbu, ubu, lbu0, ubu0 -> [B, width] arrays
+            keep = [None if per_inst.get(k) is None else np.ascontiguousarray(per_inst[k], float)
+                    for k in ("W", "W_e", "lbu", "ubu", "lbu0", "ubu0")]
+            pi = (_dp * 6)(*[P(a) if a is not None else None for a in keep])
         for _ in range(n_rti):
-            L.cfemu_rti_batch(B, N, TS, P(par) if par is not None else None, 0, P(w["x0"]), P(w["yref"]), P(w["yref_e"]),
-                              P(x), P(u), I(st), I(it), I(qs), I(fl), P(res), None, 4)
+            L.cfemu_rti_batch2(B, N, TS, P(par) if par is not None else None, 0, P(w["x0"]), P(w["yref"]), P(w["yref_e"]),
+                               P(x), P(u), I(st), I(it), I(qs), I(fl), P(res), None, 4, pi)
         return dict(x=x, u=u, status=st, qp_iter=it, qp_status=qs, flags=fl, res=res)
     return run
 
@@ -84,3 +91,46 @@ def test_emulated_kernel_tiny_horizons(emu, port):
         x, u = w["x_init"].copy(), w["u_init"].copy()
         port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u)
         assert rel_err(r["x"], x) < 1e-9 and rel_err(r["u"], u) < 1e-9
+
+
+def per_instance_params(B, seed=5):
+    """One weight / bound set per vehicle (SET_WEIGHTS / FIXED_U0 of the node, acados_mpc.cpp:596-608)."""
+    rng = np.random.default_rng(seed)
+    Q = np.array([120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0, 0.06, 0.06, 0.06, 0.06])
+    W = Q * rng.uniform(0.5, 2.0, (B, 17))
+    WN = W[:, :13] * rng.uniform(20, 60, (B, 1))
+    lbu = rng.uniform(0.0, 3.0, (B, 4))
+    ubu = rng.uniform(19.0, 22.0, (B, 4))
+    lbu0 = rng.uniform(10.0, 14.0, (B, 4))   # a narrow stage-0 box around hover
+    ubu0 = lbu0 + rng.uniform(1.0, 6.0, (B, 4))
+    return dict(W=W, W_e=WN, lbu=lbu, ubu=ubu, lbu0=lbu0, ubu0=ubu0)
+
+
+def test_emulated_kernel_per_instance_parameters(emu, port, ref):
+    """Per-instance W, W_e, input box and a separate stage-0 box, against the port and the reference's own code."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    N, B = 20, 6
+    w = wl.hover_batch(B, N, seed=31)
+    pp = per_instance_params(B)
+    r = emu(w, N, per_inst=pp)
+    for i in range(B):
+        x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+        p = port.params(Wdiag=pp["W"][i], WNdiag=pp["W_e"][i], lbu=pp["lbu"][i], ubu=pp["ubu"][i], lbu0=pp["lbu0"][i], ubu0=pp["ubu0"][i])
+        st, info = port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u, params=p)
+        assert st == r["status"][i] and abs(info.qp_iter - r["qp_iter"][i]) <= 1
+        assert rel_err(r["x"][i], x) < 1e-9 and rel_err(r["u"][i], u) < 1e-9
+        assert (r["u"][i, 0] >= pp["lbu0"][i] - 1e-6).all() and (r["u"][i, 0] <= pp["ubu0"][i] + 1e-6).all()
+        s = ref.solver(N, TS)
+        s.set_weights(pp["W"][i], pp["W_e"][i])
+        s.set_input_bounds(pp["lbu"][i], pp["ubu"][i])
+        s.set_input_bounds_stage0(pp["lbu0"][i], pp["ubu0"][i])
+        xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+        s.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)
+        s.close()
+        assert rel_err(r["x"][i], xr) < 1e-9 and rel_err(r["u"][i], ur) < 1e-9
+    # only some arrays given: the rest stays solver-wide
+    r2 = emu(w, N, per_inst=dict(lbu0=pp["lbu0"], ubu0=pp["ubu0"]))
+    for i in range(2):
+        x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+        port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u, params=port.params(lbu0=pp["lbu0"][i], ubu0=pp["ubu0"][i]))
+        assert rel_err(r2["x"][i], x) < 1e-9 and rel_err(r2["u"][i], u) < 1e-9
