@@ -21,6 +21,10 @@ _lib = None
 ACADOS_SUCCESS, ACADOS_NAN_DETECTED, ACADOS_MAXITER, ACADOS_MINSTEP, ACADOS_QP_FAILURE = 0, 1, 2, 3, 4
 
 
+# enum order of the node's `policy` (crazyflie_controller/src/acados_mpc.cpp:129-133)
+POLICY_REGULATION, POLICY_TRACKING, POLICY_HOLD = 0, 1, 2
+
+
 class CfnmpcError(RuntimeError):
     pass
 
@@ -47,6 +51,19 @@ def lib():
         L.cfnmpc_batch_last_solve_ms.argtypes = [vp, ctypes.POINTER(cd)]
         L.cfnmpc_debug_scratch.argtypes = [vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_longlong)]
         L.cfnmpc_debug_max_ipm_iter.argtypes = [vp, ci]
+        L.cfnmpc_batch_set_trajectory.argtypes = [vp, vp, ci, ci]
+        L.cfnmpc_batch_update_reference.argtypes = [vp]
+        L.cfnmpc_batch_commands.argtypes = [vp, ci]
+        L.cfnmpc_batch_tick.argtypes = [vp, ci]
+        L.cfnmpc_batch_plant_step.argtypes = [vp, cd, ci, ci]
+        L.cfnmpc_sim_create.argtypes = [ci, ci, ctypes.POINTER(vp)]
+        L.cfnmpc_sim_destroy.argtypes = [vp]
+        L.cfnmpc_sim_set_stream.argtypes = [vp, vp]
+        L.cfnmpc_sim_opts_set.argtypes = [vp, cp, ci]
+        L.cfnmpc_sim_set.argtypes = [vp, cp, vp, ci]
+        L.cfnmpc_sim_solve.argtypes = [vp]
+        L.cfnmpc_sim_get.argtypes = [vp, cp, vp, ci]
+        L.cfnmpc_sim_launches.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
         L.cfnmpc_last_error.restype = cp
         L.cfnmpc_version.restype = cp
         _lib = L
@@ -111,7 +128,8 @@ class BatchSolver:
         return {"x0": (B, NX), "yref": (B, N, NY), "yref_e": (B, NX), "x": (B, N + 1, NX), "u": (B, N, NU),
                 "W": (NY,), "W_e": (NX,), "lbu": (NU,), "ubu": (NU,), "lbu0": (NU,), "ubu0": (NU,),
                 "W_batch": (B, NY), "W_e_batch": (B, NX), "lbu_batch": (B, NU), "ubu_batch": (B, NU),
-                "lbu0_batch": (B, NU), "ubu0_batch": (B, NU)}.get(field)
+                "lbu0_batch": (B, NU), "ubu0_batch": (B, NU), "setpoint": (B, 3), "uss": (1,),
+                "policy": (B,), "traj_iter": (B,)}.get(field)
 
     def clear(self, field):
         _check(lib().cfnmpc_batch_clear(self._h, field.encode()))
@@ -121,13 +139,14 @@ class BatchSolver:
         if self._expected(field) is None:
             raise CfnmpcError(f"unknown field '{field}'")
         n = int(np.prod(self._expected(field)))
+        is_int = field in ("policy", "traj_iter")
         if hasattr(a, "data_ptr"):
-            if a.numel() != n or a.element_size() != 8:
-                raise CfnmpcError(f"'{field}' needs {n} float64 values")
+            if a.numel() != n or a.element_size() != (4 if is_int else 8):
+                raise CfnmpcError(f"'{field}' needs {n} {'int32' if is_int else 'float64'} values")
         else:
-            a = np.ascontiguousarray(a, dtype=np.float64)
+            a = np.ascontiguousarray(a, dtype=np.int32 if is_int else np.float64)
             if a.size != n:
-                raise CfnmpcError(f"'{field}' needs {n} float64 values, got {a.size}")
+                raise CfnmpcError(f"'{field}' needs {n} values, got {a.size}")
         p, dev, keep = _ptr(a)
         _check(lib().cfnmpc_batch_set(self._h, field.encode(), ctypes.c_void_p(p), dev))
         if not dev and not (hasattr(a, "is_pinned") and a.is_pinned()):
@@ -151,7 +170,10 @@ class BatchSolver:
         B, N = self.B, self.N
         shapes = {"u": ((B, NU), np.float64), "x": ((B, NX), np.float64), "u_all": ((B, N, NU), np.float64),
                   "x_all": ((B, N + 1, NX), np.float64), "status": ((B,), np.int32), "qp_iter": ((B,), np.int32),
-                  "qp_status": ((B,), np.int32), "flags": ((B,), np.int32), "res": ((B, 4), np.float64)}
+                  "qp_status": ((B,), np.int32), "flags": ((B,), np.int32), "res": ((B, 4), np.float64),
+                  "policy": ((B,), np.int32), "traj_iter": ((B,), np.int32), "motors": ((B, NU), np.int32),
+                  "euler": ((B, 3), np.float64), "twist": ((B, 4), np.float64), "x0": ((B, NX), np.float64),
+                  "yref": ((B, N, NY), np.float64), "yref_e": ((B, NX), np.float64), "setpoint": ((B, 3), np.float64)}
         if field not in shapes:
             raise CfnmpcError(f"unknown field '{field}'")
         shape, dt = shapes[field]
@@ -160,6 +182,40 @@ class BatchSolver:
         p, dev, keep = _ptr(out)
         _check(lib().cfnmpc_batch_get(self._h, field.encode(), int(stage), ctypes.c_void_p(p), dev))
         return out
+
+    # ---- closed-loop driver (the rest of NMPC::iteration, acados_mpc.cpp:430-516,619-670)
+    def set_trajectory(self, table):
+        """Trajectory table [rows,17] (crazyflie_controller/traj/*.txt format) for the Tracking / Hold policies."""
+        if hasattr(table, "data_ptr"):
+            rows = table.shape[0]
+        else:
+            table = np.ascontiguousarray(table, dtype=np.float64)
+            rows = table.shape[0]
+            if table.ndim != 2 or table.shape[1] != NY:
+                raise CfnmpcError("trajectory table must be [rows, 17]")
+        p, dev, keep = _ptr(table)
+        _check(lib().cfnmpc_batch_set_trajectory(self._h, ctypes.c_void_p(p), int(rows), dev))
+        if not dev:
+            self.sync()
+        return self
+
+    def update_reference(self):
+        _check(lib().cfnmpc_batch_update_reference(self._h))
+        return self
+
+    def commands(self, motors_from_u1=False):
+        _check(lib().cfnmpc_batch_commands(self._h, 1 if motors_from_u1 else 0))
+        return self
+
+    def tick(self, motors_from_u1=False):
+        """update_reference + one RTI step + commands."""
+        _check(lib().cfnmpc_batch_tick(self._h, 1 if motors_from_u1 else 0))
+        return self
+
+    def plant_step(self, dt, n_steps=1, truncated_motors=False):
+        """x0 <- ERK4(x0, u_0 or int32 motors, dt): simulated vehicle for closed-loop runs on the device."""
+        _check(lib().cfnmpc_batch_plant_step(self._h, float(dt), int(n_steps), 1 if truncated_motors else 0))
+        return self
 
     def device_ptr(self, field):
         p = ctypes.c_void_p()
@@ -187,3 +243,78 @@ class BatchSolver:
 
     def debug_max_ipm_iter(self, n):
         _check(lib().cfnmpc_debug_max_ipm_iter(self._h, int(n)))
+
+
+class SimBatch:
+    """B independent state predictions x+ = ERK4(x, u, T): the estimator node's delay compensation
+    (crazyflie_controller/src/acados_estimator.cpp:573-593), mirror of cfnmpc_sim_* in include/cfnmpc.h."""
+
+    def __init__(self, batch, device=0, num_steps=1, sens_forw=False):
+        self._h = ctypes.c_void_p()
+        self.B = int(batch)
+        _check(lib().cfnmpc_sim_create(self.B, int(device), ctypes.byref(self._h)))
+        self.opts_set("num_steps", num_steps)
+        self.opts_set("sens_forw", 1 if sens_forw else 0)
+        self.sens_forw = bool(sens_forw)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().cfnmpc_sim_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_handle):
+        _check(lib().cfnmpc_sim_set_stream(self._h, ctypes.c_void_p(cuda_stream_handle or 0)))
+
+    def opts_set(self, field, value):
+        _check(lib().cfnmpc_sim_opts_set(self._h, field.encode(), int(value)))
+        if field == "sens_forw":
+            self.sens_forw = bool(value)
+        return self
+
+    def set(self, field, a):
+        n = {"x": self.B * NX, "u": self.B * NU, "T": 1, "T_batch": self.B}.get(field)
+        if n is None:
+            raise CfnmpcError(f"unknown field '{field}'")
+        if hasattr(a, "data_ptr"):
+            if a.numel() != n or a.element_size() != 8:
+                raise CfnmpcError(f"'{field}' needs {n} float64 values")
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.size != n:
+                raise CfnmpcError(f"'{field}' needs {n} float64 values, got {a.size}")
+        p, dev, keep = _ptr(a)
+        _check(lib().cfnmpc_sim_set(self._h, field.encode(), ctypes.c_void_p(p), dev))
+        if not dev:
+            self.get("xn")  # pageable host source: drain the stream before the caller may reuse the buffer
+        return self
+
+    def solve(self):
+        _check(lib().cfnmpc_sim_solve(self._h))
+        return self
+
+    def get(self, field, out=None):
+        shape = {"xn": (self.B, NX), "S_forw": (self.B, NX + NU, NX)}.get(field)
+        if shape is None:
+            raise CfnmpcError(f"unknown field '{field}'")
+        if out is None:
+            out = np.empty(shape)
+        p, dev, keep = _ptr(out)
+        _check(lib().cfnmpc_sim_get(self._h, field.encode(), ctypes.c_void_p(p), dev))
+        return out
+
+    def launches(self):
+        v = ctypes.c_longlong()
+        _check(lib().cfnmpc_sim_launches(self._h, ctypes.byref(v)))
+        return v.value

@@ -317,3 +317,157 @@ int acados_free(void)
 }
 
 }  // extern "C"
+
+// ================================================================== state predictor surfaces
+// include/acados_sim_solver_crazyflie.h + include/acados_c/sim_interface.h: one-instance wrappers over cfnmpc_sim.
+#include "../../include/acados_sim_solver_crazyflie.h"
+
+struct crazyflie_sim_solver_capsule
+{
+    cfnmpc_sim *sim = nullptr;
+    double x[13] = {0}, u[4] = {0}, T = 0.015, xn[13] = {0}, S[13 * 17] = {0};
+    bool sens_forw = true;   // the generated sim solver keeps forward sensitivities on (acados_sim_solver.in.c:280-281)
+    bool have_S = false;
+    sim_config config;
+    sim_in in;
+    sim_out out;
+    sim_opts opts;
+    sim_solver solver;
+    int dims_dummy = 0;
+};
+
+extern "C" {
+
+crazyflie_sim_solver_capsule *crazyflie_acados_sim_solver_create_capsule(void) { return new crazyflie_sim_solver_capsule(); }
+
+int crazyflie_acados_sim_free_capsule_solver(crazyflie_sim_solver_capsule *c)
+{
+    if (!c) return 1;
+    if (c->sim) cfnmpc_sim_destroy(c->sim);
+    c->sim = nullptr;
+    return 0;
+}
+
+int crazyflie_acados_sim_solver_free_capsule(crazyflie_sim_solver_capsule *c)
+{
+    if (c) crazyflie_acados_sim_free_capsule_solver(c);
+    delete c;
+    return 0;
+}
+
+int crazyflie_acados_sim_create_capsule_solver(crazyflie_sim_solver_capsule *c)
+{
+    if (!c) return 1;
+    crazyflie_acados_sim_free_capsule_solver(c);
+    if (cfnmpc_sim_create(1, 0, &c->sim) != CFNMPC_OK) {
+        fprintf(stderr, "crazyflie_acados_sim_create: %s\n", cfnmpc_last_error());
+        c->sim = nullptr;
+        return 1;
+    }
+    cfnmpc_sim_opts_set(c->sim, "sens_forw", c->sens_forw ? 1 : 0);
+    c->config.capsule = c; c->in.capsule = c; c->out.capsule = c; c->opts.capsule = c; c->solver.capsule = c;
+    c->T = 0.015;  // Tsim = the shooting interval (acados_sim_solver.in.c:306-307)
+    return 0;
+}
+
+int crazyflie_acados_sim_solve_capsule(crazyflie_sim_solver_capsule *c)
+{
+    if (!c || !c->sim) return ACADOS_QP_FAILURE;
+    int rc = cfnmpc_sim_set(c->sim, "x", c->x, 0);
+    rc |= cfnmpc_sim_set(c->sim, "u", c->u, 0);
+    rc |= cfnmpc_sim_set(c->sim, "T", &c->T, 0);
+    rc |= cfnmpc_sim_solve(c->sim);
+    rc |= cfnmpc_sim_get(c->sim, "xn", c->xn, 0);
+    c->have_S = false;
+    if (!rc && c->sens_forw) { rc |= cfnmpc_sim_get(c->sim, "S_forw", c->S, 0); c->have_S = !rc; }
+    if (rc) {
+        fprintf(stderr, "crazyflie_acados_sim_solve: %s\n", cfnmpc_last_error());
+        return ACADOS_QP_FAILURE;
+    }
+    for (int i = 0; i < 13; i++) if (c->xn[i] != c->xn[i]) return ACADOS_NAN_DETECTED;  // sim_erk reports NaNs the same way
+    return ACADOS_SUCCESS;
+}
+
+sim_config *crazyflie_acados_get_sim_config(crazyflie_sim_solver_capsule *c) { return &c->config; }
+sim_in *crazyflie_acados_get_sim_in(crazyflie_sim_solver_capsule *c) { return &c->in; }
+sim_out *crazyflie_acados_get_sim_out(crazyflie_sim_solver_capsule *c) { return &c->out; }
+void *crazyflie_acados_get_sim_dims(crazyflie_sim_solver_capsule *c) { return &c->dims_dummy; }
+sim_opts *crazyflie_acados_get_sim_opts(crazyflie_sim_solver_capsule *c) { return &c->opts; }
+sim_solver *crazyflie_acados_get_sim_solver(crazyflie_sim_solver_capsule *c) { return &c->solver; }
+
+int sim_in_set(void *, void *, sim_in *in, const char *field, void *value)
+{
+    if (!in || !in->capsule || !field || !value) return 1;
+    crazyflie_sim_solver_capsule *c = in->capsule;
+    if (!strcmp(field, "T")) c->T = *static_cast<double *>(value);
+    else if (!strcmp(field, "x")) memcpy(c->x, value, sizeof c->x);
+    else if (!strcmp(field, "u")) memcpy(c->u, value, sizeof c->u);
+    else return 1;
+    return 0;
+}
+
+int sim_out_get(void *, void *, sim_out *out, const char *field, void *value)
+{
+    if (!out || !out->capsule || !field || !value) return 1;
+    crazyflie_sim_solver_capsule *c = out->capsule;
+    if (!strcmp(field, "xn") || !strcmp(field, "x")) memcpy(value, c->xn, sizeof c->xn);
+    else if (!strcmp(field, "S_forw") && c->have_S) memcpy(value, c->S, sizeof c->S);
+    else return 1;
+    return 0;
+}
+
+void sim_opts_set(sim_config *config, void *, const char *field, void *value)
+{
+    if (!config || !config->capsule || !field || !value) return;
+    crazyflie_sim_solver_capsule *c = config->capsule;
+    if (!strcmp(field, "sens_forw")) {
+        c->sens_forw = *static_cast<bool *>(value);
+        if (c->sim) cfnmpc_sim_opts_set(c->sim, "sens_forw", c->sens_forw ? 1 : 0);
+    } else if (!strcmp(field, "num_steps") || !strcmp(field, "num_stages")) {
+        if (c->sim && cfnmpc_sim_opts_set(c->sim, field, *static_cast<int *>(value)) != CFNMPC_OK)
+            fprintf(stderr, "sim_opts_set: %s\n", cfnmpc_last_error());
+    }
+}
+
+int sim_solve(sim_solver *solver, sim_in *, sim_out *)
+{
+    if (!solver || !solver->capsule) return ACADOS_QP_FAILURE;
+    return crazyflie_acados_sim_solve_capsule(solver->capsule);
+}
+
+__attribute__((weak)) sim_config *crazyflie_sim_config;
+__attribute__((weak)) void *crazyflie_sim_dims;
+__attribute__((weak)) sim_in *crazyflie_sim_in;
+__attribute__((weak)) sim_out *crazyflie_sim_out;
+__attribute__((weak)) sim_opts *crazyflie_sim_opts;
+__attribute__((weak)) sim_solver *crazyflie_sim_solver;
+static crazyflie_sim_solver_capsule *g_sim_capsule = nullptr;
+
+int crazyflie_acados_sim_free_legacy(void)
+{
+    if (!g_sim_capsule) return 0;
+    crazyflie_acados_sim_solver_free_capsule(g_sim_capsule);
+    g_sim_capsule = nullptr;
+    crazyflie_sim_config = nullptr; crazyflie_sim_dims = nullptr; crazyflie_sim_in = nullptr; crazyflie_sim_out = nullptr;
+    crazyflie_sim_opts = nullptr; crazyflie_sim_solver = nullptr;
+    return 0;
+}
+
+int crazyflie_acados_sim_create_legacy(void)
+{
+    crazyflie_acados_sim_free_legacy();
+    g_sim_capsule = crazyflie_acados_sim_solver_create_capsule();
+    if (crazyflie_acados_sim_create_capsule_solver(g_sim_capsule)) {
+        crazyflie_acados_sim_solver_free_capsule(g_sim_capsule);
+        g_sim_capsule = nullptr;
+        return 1;
+    }
+    crazyflie_sim_config = &g_sim_capsule->config; crazyflie_sim_dims = &g_sim_capsule->dims_dummy;
+    crazyflie_sim_in = &g_sim_capsule->in; crazyflie_sim_out = &g_sim_capsule->out;
+    crazyflie_sim_opts = &g_sim_capsule->opts; crazyflie_sim_solver = &g_sim_capsule->solver;
+    return 0;
+}
+
+int crazyflie_acados_sim_solve_legacy(void) { return g_sim_capsule ? crazyflie_acados_sim_solve_capsule(g_sim_capsule) : ACADOS_QP_FAILURE; }
+
+}  // extern "C"

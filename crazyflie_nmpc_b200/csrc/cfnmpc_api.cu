@@ -12,6 +12,7 @@
 
 #include "../../include/cfnmpc.h"
 #include "cf_rti_warp.h"
+#include "cf_loop_kernels.h"
 
 #define CF_WARPS_PER_BLOCK 4
 
@@ -79,6 +80,11 @@ struct cfnmpc_batch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double *d_x0 = nullptr, *d_yref = nullptr, *d_yref_e = nullptr, *d_x = nullptr, *d_u = nullptr, *d_res = nullptr;
     double *d_scratch = nullptr, *d_stage = nullptr;
+    // closed-loop driver state (cf_loop_kernels.h)
+    int *d_policy = nullptr, *d_titer = nullptr, *d_motors = nullptr;
+    double *d_setpoint = nullptr, *d_traj = nullptr, *d_euler = nullptr, *d_twist = nullptr;
+    int n_traj = 0;
+    double uss = 0.0;
     double *d_Wb = nullptr, *d_WNb = nullptr, *d_lbub = nullptr, *d_ubub = nullptr, *d_lbu0b = nullptr, *d_ubu0b = nullptr;
     int *d_status = nullptr, *d_qp_iter = nullptr, *d_qp_status = nullptr, *d_flags = nullptr, *d_counter = nullptr;
     int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 5;
@@ -106,6 +112,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
                     h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter,
+                    h->d_policy, h->d_titer, h->d_motors, h->d_setpoint, h->d_traj, h->d_euler, h->d_twist,
                     h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -174,6 +181,20 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     CKH(cudaMalloc(&h->d_qp_status, B * 4));
     CKH(cudaMalloc(&h->d_flags, B * 4));
     CKH(cudaMalloc(&h->d_counter, 4));
+    CKH(cudaMalloc(&h->d_policy, B * 4));
+    CKH(cudaMalloc(&h->d_titer, B * 4));
+    CKH(cudaMalloc(&h->d_motors, B * CF_NU * 4));
+    CKH(cudaMalloc(&h->d_setpoint, B * 3 * 8));
+    CKH(cudaMalloc(&h->d_euler, B * 3 * 8));
+    CKH(cudaMalloc(&h->d_twist, B * 4 * 8));
+    CKH(cudaMemsetAsync(h->d_policy, 0, B * 4, h->stream));      // Regulation at (0, 0, 0) until told otherwise
+    CKH(cudaMemsetAsync(h->d_titer, 0, B * 4, h->stream));
+    CKH(cudaMemsetAsync(h->d_motors, 0, B * CF_NU * 4, h->stream));
+    CKH(cudaMemsetAsync(h->d_setpoint, 0, B * 3 * 8, h->stream));
+    CKH(cudaMemsetAsync(h->d_euler, 0, B * 3 * 8, h->stream));
+    CKH(cudaMemsetAsync(h->d_twist, 0, B * 4 * 8, h->stream));
+    // uss as the node computes it: float arithmetic, g0 = 9.80665 (acados_mpc.cpp:107,189,253)
+    h->uss = (double) sqrtf((0.033f * 9.80665f) / (4.0f * 3.25e-4f));
     CKH(cudaMalloc(&h->d_scratch, (size_t) h->n_slots * stride * 8));
     CKH(cudaMemsetAsync(h->d_scratch, 0, (size_t) h->n_slots * stride * 8, h->stream));
     CKH(cudaMemsetAsync(h->d_x0, 0, B * CF_NX * 8, h->stream));
@@ -229,6 +250,12 @@ static bool batch_field(cfnmpc_batch *h, const char *f, FieldRef &r)
     else if (!strcmp(f, "qp_status")) r = {h->d_qp_status, B * 4};
     else if (!strcmp(f, "flags")) r = {h->d_flags, B * 4};
     else if (!strcmp(f, "res")) r = {h->d_res, B * 4 * 8};
+    else if (!strcmp(f, "policy")) r = {h->d_policy, B * 4};
+    else if (!strcmp(f, "traj_iter")) r = {h->d_titer, B * 4};
+    else if (!strcmp(f, "setpoint")) r = {h->d_setpoint, B * 3 * 8};
+    else if (!strcmp(f, "motors")) r = {h->d_motors, B * CF_NU * 4};
+    else if (!strcmp(f, "euler")) r = {h->d_euler, B * 3 * 8};
+    else if (!strcmp(f, "twist")) r = {h->d_twist, B * 4 * 8};
     else return false;
     return true;
 }
@@ -274,7 +301,13 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         }
     }
     FieldRef r;
-    if (!strcmp(field, "x0") || !strcmp(field, "yref") || !strcmp(field, "yref_e") || !strcmp(field, "x") || !strcmp(field, "u")) {
+    if (!strcmp(field, "uss")) {
+        if (src_on_device) CK(cudaMemcpy(&h->uss, src, 8, cudaMemcpyDeviceToHost));
+        else memcpy(&h->uss, src, 8);
+        return CFNMPC_OK;
+    }
+    if (!strcmp(field, "x0") || !strcmp(field, "yref") || !strcmp(field, "yref_e") || !strcmp(field, "x") || !strcmp(field, "u") ||
+        !strcmp(field, "policy") || !strcmp(field, "traj_iter") || !strcmp(field, "setpoint")) {
         batch_field(h, field, r);
         CK(cudaMemcpyAsync(r.dev, src, r.bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
         return CFNMPC_OK;
@@ -336,11 +369,206 @@ extern "C" int cfnmpc_batch_get(cfnmpc_batch *h, const char *field, int stage, v
         CK(cudaMemcpyAsync(dst, h->d_stage, (size_t) n * 8, kind, h->stream));
     } else {
         FieldRef r;
-        if (!batch_field(h, field, r) || !strcmp(field, "x0") || !strcmp(field, "yref") || !strcmp(field, "yref_e"))
+        if (!batch_field(h, field, r))
             return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_get: unknown field '") + field + "'");
         CK(cudaMemcpyAsync(dst, r.dev, r.bytes, kind, h->stream));
     }
     if (!dst_on_device) CK(cudaStreamSynchronize(h->stream));
+    return CFNMPC_OK;
+}
+
+// ------------------------------------------------------------------ closed-loop driver
+extern "C" int cfnmpc_batch_set_trajectory(cfnmpc_batch *h, const double *table, int n_rows, int src_on_device)
+{
+    if (!h || !table) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set_trajectory: null argument");
+    if (n_rows <= h->N) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set_trajectory: the table needs more than N rows");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_traj) { CK(cudaFree(h->d_traj)); h->d_traj = nullptr; }
+    const size_t bytes = (size_t) n_rows * CF_NY * 8;
+    CK(cudaMalloc(&h->d_traj, bytes));
+    CK(cudaMemcpyAsync(h->d_traj, table, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    h->n_traj = n_rows;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_update_reference(cfnmpc_batch *h)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    const long n = (long) h->B * (h->N + 1) * CF_NY;
+    cf_reference_window_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, h->stream>>>(h->B, h->N, h->d_policy, h->d_titer, h->d_setpoint,
+                                                                                h->d_traj, h->n_traj, h->uss, h->d_yref, h->d_yref_e);
+    CK(cudaGetLastError());
+    cf_policy_advance_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->N, h->d_policy, h->d_titer, h->n_traj);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_commands(cfnmpc_batch *h, int motors_from_u1)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    cf_command_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, h->N, h->d_x, h->d_u, motors_from_u1, h->d_motors, h->d_euler, h->d_twist);
+    CK(cudaGetLastError());
+    h->launches++;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_plant_step(cfnmpc_batch *h, double dt, int n_steps, int truncated_motors)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    if (!(dt > 0) || n_steps < 1) return fail(CFNMPC_EINVAL, "cfnmpc_batch_plant_step: need dt > 0 and n_steps >= 1");
+    CK(cudaSetDevice(h->device));
+    // input of the plant: the first control of the current solution (u_0 of every instance), or the int32 motor command
+    if (!truncated_motors) {
+        cf_gather_stage_kernel<<<(h->B * CF_NU + 255) / 256, 256, 0, h->stream>>>(h->d_u, h->d_stage, h->B, h->N * CF_NU, 0, CF_NU);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    cf_predict_kernel<<<(h->B + CF_PRED_THREADS - 1) / CF_PRED_THREADS, CF_PRED_THREADS, 0, h->stream>>>(
+        h->d_x0, h->d_stage, truncated_motors ? h->d_motors : nullptr, nullptr, dt, n_steps, h->B, h->d_x0);
+    CK(cudaGetLastError());
+    h->launches++;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti);
+extern "C" int cfnmpc_batch_tick(cfnmpc_batch *h, int motors_from_u1)
+{
+    int rc = cfnmpc_batch_update_reference(h);
+    if (rc == CFNMPC_OK) rc = cfnmpc_batch_solve(h, 1);
+    if (rc == CFNMPC_OK) rc = cfnmpc_batch_commands(h, motors_from_u1);
+    return rc;
+}
+
+// ------------------------------------------------------------------ batched state predictor object
+struct cfnmpc_sim
+{
+    int B = 0, device = 0, n_steps = 1, sens_forw = 0;
+    bool T_per_instance = false;
+    double T_all = 0.015;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    double *d_x = nullptr, *d_u = nullptr, *d_T = nullptr, *d_xn = nullptr, *d_S = nullptr;
+    long long launches = 0;
+};
+
+extern "C" int cfnmpc_sim_destroy(cfnmpc_sim *s)
+{
+    if (!s) return CFNMPC_OK;
+    cudaSetDevice(s->device);
+    void *ptrs[] = {s->d_x, s->d_u, s->d_T, s->d_xn, s->d_S};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_sim_create(int batch, int device, cfnmpc_sim **out)
+{
+    if (!out) return fail(CFNMPC_EINVAL, "cfnmpc_sim_create: out is NULL");
+    *out = nullptr;
+    if (batch < 1) return fail(CFNMPC_EINVAL, "cfnmpc_sim_create: need batch >= 1");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(CFNMPC_EINVAL, "cfnmpc_sim_create: no such CUDA device");
+    CK(cudaSetDevice(device));
+    cfnmpc_sim *s = new cfnmpc_sim();
+    s->B = batch; s->device = device;
+    const size_t B = batch;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_x, B * CF_NX * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_u, B * CF_NU * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_T, B * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_xn, B * CF_NX * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->d_x, 0, B * CF_NX * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->d_u, 0, B * CF_NU * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->d_xn, 0, B * CF_NX * 8);
+    if (e != cudaSuccess) {
+        cfnmpc_sim_destroy(s);
+        return fail(CFNMPC_ECUDA, std::string("cfnmpc_sim_create: ") + cudaGetErrorString(e));
+    }
+    s->stream = s->own_stream;
+    *out = s;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_sim_set_stream(cfnmpc_sim *s, void *cuda_stream)
+{
+    if (!s) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    s->stream = cuda_stream ? (cudaStream_t) cuda_stream : s->own_stream;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_sim_opts_set(cfnmpc_sim *s, const char *field, int value)
+{
+    if (!s || !field) return fail(CFNMPC_EINVAL, "cfnmpc_sim_opts_set: null argument");
+    if (!strcmp(field, "num_steps")) {
+        if (value < 1) return fail(CFNMPC_EINVAL, "cfnmpc_sim_opts_set: num_steps must be >= 1");
+        s->n_steps = value;
+    } else if (!strcmp(field, "sens_forw")) s->sens_forw = value != 0;
+    else if (!strcmp(field, "num_stages")) {
+        if (value != 4) return fail(CFNMPC_EINVAL, "cfnmpc_sim_opts_set: only the 4-stage ERK of the reference configuration is implemented");
+    } else return fail(CFNMPC_EINVAL, std::string("cfnmpc_sim_opts_set: unknown option '") + field + "'");
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_sim_set(cfnmpc_sim *s, const char *field, const void *src, int src_on_device)
+{
+    if (!s || !field || !src) return fail(CFNMPC_EINVAL, "cfnmpc_sim_set: null argument");
+    CK(cudaSetDevice(s->device));
+    const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const size_t B = s->B;
+    if (!strcmp(field, "x")) CK(cudaMemcpyAsync(s->d_x, src, B * CF_NX * 8, kind, s->stream));
+    else if (!strcmp(field, "u")) CK(cudaMemcpyAsync(s->d_u, src, B * CF_NU * 8, kind, s->stream));
+    else if (!strcmp(field, "T_batch")) { CK(cudaMemcpyAsync(s->d_T, src, B * 8, kind, s->stream)); s->T_per_instance = true; }
+    else if (!strcmp(field, "T")) {
+        if (src_on_device) CK(cudaMemcpy(&s->T_all, src, 8, cudaMemcpyDeviceToHost));
+        else memcpy(&s->T_all, src, 8);
+        s->T_per_instance = false;
+    } else return fail(CFNMPC_EINVAL, std::string("cfnmpc_sim_set: unknown field '") + field + "'");
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_sim_solve(cfnmpc_sim *s)
+{
+    if (!s) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(s->device));
+    const double *T_b = s->T_per_instance ? s->d_T : nullptr;
+    if (s->sens_forw) {
+        if (!s->d_S) CK(cudaMalloc(&s->d_S, (size_t) s->B * CF_NX * CF_NV * 8));
+        const long threads = (long) s->B * 32;
+        cf_predict_sens_kernel<<<(unsigned) ((threads + 127) / 128), 128, 0, s->stream>>>(s->d_x, s->d_u, T_b, s->T_all, s->n_steps, s->B, s->d_xn, s->d_S);
+    } else {
+        cf_predict_kernel<<<(s->B + CF_PRED_THREADS - 1) / CF_PRED_THREADS, CF_PRED_THREADS, 0, s->stream>>>(s->d_x, s->d_u, nullptr, T_b, s->T_all,
+                                                                                                     s->n_steps, s->B, s->d_xn);
+    }
+    CK(cudaGetLastError());
+    s->launches++;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_sim_get(cfnmpc_sim *s, const char *field, void *dst, int dst_on_device)
+{
+    if (!s || !field || !dst) return fail(CFNMPC_EINVAL, "cfnmpc_sim_get: null argument");
+    CK(cudaSetDevice(s->device));
+    const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (!strcmp(field, "xn")) CK(cudaMemcpyAsync(dst, s->d_xn, (size_t) s->B * CF_NX * 8, kind, s->stream));
+    else if (!strcmp(field, "S_forw")) {
+        if (!s->sens_forw || !s->d_S) return fail(CFNMPC_ESTATE, "cfnmpc_sim_get: S_forw needs the option sens_forw = 1 and a solve");
+        CK(cudaMemcpyAsync(dst, s->d_S, (size_t) s->B * CF_NX * CF_NV * 8, kind, s->stream));
+    } else return fail(CFNMPC_EINVAL, std::string("cfnmpc_sim_get: unknown field '") + field + "'");
+    if (!dst_on_device) CK(cudaStreamSynchronize(s->stream));
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_sim_launches(cfnmpc_sim *s, long long *n)
+{
+    if (!s || !n) return fail(CFNMPC_EINVAL, "null argument");
+    *n = s->launches;
     return CFNMPC_OK;
 }
 

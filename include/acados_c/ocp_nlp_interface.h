@@ -56,8 +56,9 @@ typedef struct ocp_nlp_solver
     struct crazyflie_solver_capsule *capsule;
 } ocp_nlp_solver;
 
-/* field: "lbx" | "ubx" (stage 0, 13 doubles: the measured state), "lbu" | "ubu" (4 doubles; one box for all
- * stages, the last value set wins).  Returns 0, or 1 for an unknown field / bad stage. */
+/* field: "lbx" | "ubx" (stage 0, 13 doubles: the measured state), "lbu" | "ubu" (4 doubles; stage 0 has its own box
+ * -- the node's FIXED_U0 branch, acados_mpc.cpp:604-608 -- stages 1..N-1 share one, the last value set wins).
+ * Returns 0, or 1 for an unknown field / bad stage. */
 int ocp_nlp_constraints_model_set(ocp_nlp_config *config, ocp_nlp_dims *dims, ocp_nlp_in *in, int stage,
                                   const char *field, void *value);
 /* field: "yref" | "y_ref" (17 doubles for stage < N, 13 at stage N), "W" (column-major ny x ny; must be diagonal,

@@ -106,6 +106,51 @@ int cfnmpc_batch_sync(cfnmpc_batch *h);
  * Copies to host pointers synchronise the stream before returning. */
 int cfnmpc_batch_get(cfnmpc_batch *h, const char *field, int stage, void *dst, int dst_on_device);
 
+/* ---- closed-loop driver: the rest of the node's control tick, on the device ----------------
+ * Reference: NMPC::iteration, crazyflie_controller/src/acados_mpc.cpp:430-516 (reference window by policy),
+ * :619-670 (what is published from the solution).  Additional cfnmpc_batch_set fields:
+ *   "policy"    int    [B]      0 Regulation, 1 Tracking, 2 Position_Hold (enum order of acados_mpc.cpp:129-133)
+ *   "traj_iter" int    [B]      row of the trajectory table the tracking window starts at (`iter` of the node)
+ *   "setpoint"  double [B][3]   regulation point (xq_des, yq_des, zq_des)
+ *   "uss"       double [1]      hover speed written into regulation / hold references; default = the node's float
+ *                               computation sqrt(mq*g0/(4*Ct)) with g0 = 9.80665 (:107,189,253)
+ * and cfnmpc_batch_get fields "policy", "traj_iter", "yref", "yref_e", "x0",
+ *   "motors" int [B][4]      motor speeds truncated to int32 as PropellerSpeedsStamped carries them (:632-640)
+ *   "euler"  double [B][3]   (phi, theta, psi) of the normalised quaternion of x_4 (quatern2euler :384-404)
+ *   "twist"  double [B][4]   linear.x = pitch [deg], linear.y = -roll [deg], linear.z = krpm2pwm(mean(u_1)),
+ *                            angular.z = yaw rate of x_4 [deg/s]  (:641-668) */
+/* Trajectory table, n_rows x 17 row-major = the file format of crazyflie_controller/traj (acados_mpc.cpp:258-283). */
+int cfnmpc_batch_set_trajectory(cfnmpc_batch *h, const double *table, int n_rows, int src_on_device);
+/* yref / yref_e of every instance from its policy, then iter++ (tracking) or the switch to position hold. */
+int cfnmpc_batch_update_reference(cfnmpc_batch *h);
+/* "motors", "euler", "twist" from the current solution; motors_from_u1 != 0 selects u_1 (the FIXED_U0 variant). */
+int cfnmpc_batch_commands(cfnmpc_batch *h, int motors_from_u1);
+/* One control tick = update_reference + one RTI step + commands (three launches + the solve kernel). */
+int cfnmpc_batch_tick(cfnmpc_batch *h, int motors_from_u1);
+/* Simulated plant for closed-loop studies: x0 <- ERK4(x0, u_applied, dt) in n_steps steps with the model of the
+ * OCP; u_applied = u_0 of the current solution, or the int32 "motors" of the last cfnmpc_batch_commands when
+ * truncated_motors != 0 (what the real vehicle and the estimator see, acados_estimator.cpp:463-471). */
+int cfnmpc_batch_plant_step(cfnmpc_batch *h, double dt, int n_steps, int truncated_motors);
+
+/* ---- batched state predictor ---------------------------------------------------------------
+ * Reference: the estimator node's delay compensation, acados_estimator.cpp:573-593:
+ *   sim_in_set(.., "T", &delay); sim_in_set(.., "x", x0); sim_in_set(.., "u", u0);
+ *   crazyflie_acados_sim_solve(); sim_out_get(.., "xn", xn);
+ * against acados/interfaces/acados_c/sim_interface.h:96-127 and the generated acados_sim_solver_crazyflie.h
+ * (c_templates_tera/acados_sim_solver.in.h:81-95).  Same integrator as the OCP (ERK, 4 stages). */
+typedef struct cfnmpc_sim cfnmpc_sim;
+int cfnmpc_sim_create(int batch, int device, cfnmpc_sim **out);
+int cfnmpc_sim_destroy(cfnmpc_sim *s);
+int cfnmpc_sim_set_stream(cfnmpc_sim *s, void *cuda_stream);
+/* options: "num_steps" (default 1), "sens_forw" (0/1, default 0; the estimator only reads xn), "num_stages" (4) */
+int cfnmpc_sim_opts_set(cfnmpc_sim *s, const char *field, int value);
+/* fields: "x" double [B][13], "u" double [B][4], "T" double [1] (all instances) or "T_batch" double [B] */
+int cfnmpc_sim_set(cfnmpc_sim *s, const char *field, const void *src, int src_on_device);
+int cfnmpc_sim_solve(cfnmpc_sim *s);
+/* fields: "xn" double [B][13]; "S_forw" double [B][13*17] column-major 13 x 17, columns [x | u] (sim_out "S_forw") */
+int cfnmpc_sim_get(cfnmpc_sim *s, const char *field, void *dst, int dst_on_device);
+int cfnmpc_sim_launches(cfnmpc_sim *s, long long *n);
+
 /* Device pointer of a batch array ("x0","yref","yref_e","x","u","status","qp_iter"), for
  * callers that produce inputs / consume outputs on the GPU without staging copies. */
 int cfnmpc_batch_device_ptr(cfnmpc_batch *h, const char *field, void **ptr);

@@ -362,3 +362,83 @@ int cfref_batch(int N, double Ts, int cond_N, int nthreads, int n_rti, int n,
     free(th); free(sl);
     return fail;
 }
+
+/* ------------------------------------------------------------------ state predictor
+ * The reference's own ERK integrator driven the way acados_sim_solver_crazyflie.c does it
+ * (c_templates_tera/acados_sim_solver.in.c:236-396): plan ERK, dims nx/nu, 4 stages, num_steps, sens_forw,
+ * S_forw seeded with [I 0], then per call sim_in_set "T","x","u" -> sim_solve -> sim_out_get "xn"
+ * (crazyflie_controller/src/acados_estimator.cpp:573-593). */
+#include "acados_c/sim_interface.h"
+
+typedef struct
+{
+    sim_config *config;
+    void *dims, *opts;
+    sim_in *in;
+    sim_out *out;
+    sim_solver *solver;
+    external_function_generic vde, ode;
+    int sens_forw;
+} cfsim;
+
+void cfref_sim_destroy(void *h_)
+{
+    cfsim *h = h_;
+    if (!h) return;
+    if (h->solver) sim_solver_destroy(h->solver);
+    if (h->in) sim_in_destroy(h->in);
+    if (h->out) sim_out_destroy(h->out);
+    if (h->opts) sim_opts_destroy(h->opts);
+    if (h->dims) sim_dims_destroy(h->dims);
+    if (h->config) sim_config_destroy(h->config);
+    free(h);
+}
+
+void *cfref_sim_create(int num_steps, int sens_forw)
+{
+    cfsim *h = calloc(1, sizeof *h);
+    sim_solver_plan_t plan;
+    plan.sim_solver = ERK;
+    h->config = sim_config_create(plan);
+    h->dims = sim_dims_create(h->config);
+    int nx = NX, nu = NU, nz = 0;
+    sim_dims_set(h->config, h->dims, "nx", &nx);
+    sim_dims_set(h->config, h->dims, "nu", &nu);
+    sim_dims_set(h->config, h->dims, "nz", &nz);
+    h->opts = sim_opts_create(h->config, h->dims);
+    int ns = 4;
+    bool sf = sens_forw != 0, no = false;
+    sim_opts_set(h->config, h->opts, "num_stages", &ns);
+    sim_opts_set(h->config, h->opts, "num_steps", &num_steps);
+    sim_opts_set(h->config, h->opts, "sens_forw", &sf);
+    sim_opts_set(h->config, h->opts, "sens_adj", &no);
+    sim_opts_set(h->config, h->opts, "sens_hess", &no);
+    h->sens_forw = sens_forw;
+    h->in = sim_in_create(h->config, h->dims);
+    h->out = sim_out_create(h->config, h->dims);
+    h->vde.evaluate = &vde_eval;
+    h->ode.evaluate = &ode_eval;
+    h->config->model_set(h->in->model, "expl_vde_forw", &h->vde);
+    h->config->model_set(h->in->model, "expl_ode_fun", &h->ode);
+    h->solver = sim_solver_create(h->config, h->dims, h->opts);
+    double S[NX * (NX + NU)] = {0};
+    for (int i = 0; i < NX; i++) S[i + NX * i] = 1.0;
+    sim_in_set(h->config, h->dims, h->in, "S_forw", S);
+    double T = 0.015;
+    sim_in_set(h->config, h->dims, h->in, "T", &T);
+    if (sim_precompute(h->solver, h->in, h->out)) { cfref_sim_destroy(h); return NULL; }
+    return h;
+}
+
+/* xn[13]; S_forw[13*17] column-major, columns [x(13) | u(4)] (may be NULL) */
+int cfref_sim_solve(void *h_, const double *x, const double *u, double T, double *xn, double *S_forw)
+{
+    cfsim *h = h_;
+    sim_in_set(h->config, h->dims, h->in, "T", &T);
+    sim_in_set(h->config, h->dims, h->in, "x", (void *) x);
+    sim_in_set(h->config, h->dims, h->in, "u", (void *) u);
+    int status = sim_solve(h->solver, h->in, h->out);
+    sim_out_get(h->config, h->dims, h->out, "xn", xn);
+    if (S_forw && h->sens_forw) sim_out_get(h->config, h->dims, h->out, "S_forw", S_forw);
+    return status;
+}

@@ -42,6 +42,20 @@ def test_node_sequence_compiles_links_and_fails_loudly_without_gpu(exe):
     assert r.returncode == 3 and "acados_create() returned status" in r.stderr
 
 
+def test_estimator_sequence_compiles_links_and_fails_loudly_without_gpu():
+    """acados_estimator.cpp's predictor calls against include/acados_sim_solver_crazyflie.h."""
+    cf.lib()
+    src = os.path.join(ROOT, "tests", "dropin", "estimator_sequence.cpp")
+    out = os.path.join(ROOT, "tests", "dropin", "estimator_sequence")
+    subprocess.run(["g++", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", out,
+                    "-L", os.path.join(ROOT, "crazyflie_nmpc_b200"), "-lcfnmpc",
+                    "-Wl,-rpath," + os.path.join(ROOT, "crazyflie_nmpc_b200")], check=True)
+    if _has_gpu():
+        pytest.skip("GPU present")
+    r = subprocess.run([out], capture_output=True, text=True)
+    assert r.returncode == 3 and "acados_sim_create() returned status" in r.stderr
+
+
 @pytest.mark.gpu
 def test_node_sequence_matches_oracle(exe, port):
     ticks, N, TS = 4, 50, 0.015
