@@ -207,6 +207,32 @@ def run_ours(args):
         if world > 1:
             sharding.gather_u0(u0_dev, world * B)
 
+    # the same tick through the closed-loop driver: only the measured states travel to the device, the
+    # reference window is built there from (policy, trajectory row | set-point); motor commands and twist travel back
+    from crazyflie_nmpc_b200 import workloads as wl
+    motors_host = torch.empty(B, 4, dtype=torch.int32).pin_memory()
+    twist_host = torch.empty(B, 4, dtype=torch.float64).pin_memory()
+    if args.workload == "helix":
+        s.set_trajectory(wl.helix_table())
+        d_pol = torch.full((B,), cf.POLICY_TRACKING, dtype=torch.int32, device=dev)
+        d_it = torch.from_numpy(np.ascontiguousarray(w["i0"], dtype=np.int32)).to(dev)
+    else:
+        d_pol = torch.full((B,), cf.POLICY_REGULATION, dtype=torch.int32, device=dev)
+        d_it = torch.zeros(B, dtype=torch.int32, device=dev)
+        s.set("setpoint", np.ascontiguousarray(w["yref"][:, 0, :3]))
+    s.set("uss", [wl.hover_speed() if args.workload == "hover" else 15.7777])
+
+    def step_tick():
+        s.set("x0", pin["x0"])
+        s.set("policy", d_pol).set("traj_iter", d_it)            # same window every step (device-side, 0.5 MB)
+        s.set("x", d_in["x_init"]).set("u", d_in["u_init"])
+        s.tick()
+        s.get("motors", out=motors_host)
+        s.get("twist", out=twist_host)                           # host destination: synchronises the stream
+        if world > 1:
+            s.get("u", 0, out=u0_dev)
+            sharding.gather_u0(u0_dev, world * B)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -242,6 +268,12 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    u0_e2e = u0_host.clone()
+    for _ in range(2):
+        step_tick()
+    ms_tick, _ = timed(step_tick, args.steps)
+    # the driver built the same references: same first controls as the host-fed path (motors = trunc(u0))
+    tick_consistent = bool((motors_host.numpy() == u0_e2e.numpy().astype(np.int32)).all())
 
     # sanity: the timed work really solved the batch
     status = s.get("status")
@@ -287,6 +319,12 @@ def run_ours(args):
                                                grid=s.info("grid"))),
                     clocks=clocks, e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                             ms_per_step=ms_e2e / args.steps),
+                    e2e_closed_loop=dict(value=world * B / (ms_tick / args.steps * 1e-3), unit=UNIT, ms_per_step=ms_tick / args.steps,
+                                         h2d_bytes_per_step=pin["x0"].numel() * 8,
+                                         d2h_bytes_per_step=motors_host.numel() * 4 + twist_host.numel() * 8,
+                                         consistent_with_e2e=tick_consistent,
+                                         note="cfnmpc_batch_tick: reference window from (policy, set-point | trajectory row) on the device, "
+                                              "RTI step, motor/twist commands; only x0 goes up"),
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                     solved=dict(status_ok=ok, of=world * B, ipm_iter_mean=float(iters.mean()), ipm_iter_max=int(iters.max())))
         print(json.dumps(line))

@@ -35,7 +35,7 @@
 #define CF_MROWS 18                       // rows of [B';A';res_b'] held per stage
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
 #define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
-#define CF_LX 104                         // cost-to-go of the state block: packed lower triangle of P (91) + p (13)
+#define CF_LX 92                          // cost-to-go Hessian of the state block: packed lower triangle of P (91) + pad
 #define CF_LFSZ (CF_LU + CF_LX)           // 176 doubles per stage
 // Per-stage record of all IPM vectors (192 doubles).  The field order makes what each sweep reads one
 // contiguous, 16-byte aligned range, so it is staged by a single TMA bulk copy one stage ahead:
@@ -45,12 +45,14 @@
 // One contiguous block per stage in the scratch slot: [ record | [B';A';res_b'] | LU | PX ], so that whatever a
 // sweep needs of a stage is ONE contiguous, 16-byte aligned range = one TMA bulk copy:
 //   residual [0, B_LU)   backward [R_DLAM, B_PX)   forward [R_LAM, CF_SB)   factorisation [B_M, B_LU)
-// PX of block k holds P_{k+1} | p_{k+1} (what the forward sweep of stage k multiplies with); it is written by the
-// factorisation of stage k+1.
+// PX of block k holds P_{k+1} (what the forward sweep of stage k multiplies with); it is written by the factorisation
+// of stage k+1.  The gradient parts of the factorisation (l_u of stage k, p_k) go to R_DUX of stage k's record, the place
+// where the rhs-only backward sweep leaves them too, so the forward sweep is the same code for both.  The diagonal of
+// the stored LU block holds the INVERSE pivots (like BLASFEO's dA), the only form the substitutions need.
 #define B_M CF_REC
 #define B_LU (B_M + CF_MSZ)
 #define B_PX (B_LU + CF_LU)
-#define CF_SB (B_PX + CF_LX)              // 602 doubles per stage
+#define CF_SB (B_PX + CF_LX)              // 590 doubles per stage
 enum { R_UX = 0, R_PI = 18, R_DPI = 32, R_RQ = 46, R_B = 64, R_D = 78, R_DLAM = 86, R_DT = 94, R_LAM = 102, R_T = 110,
        R_RESD = 118, R_BKP = 126, R_RESM = 134, R_RESG = 142, R_PB = 160, R_DUX = 174 };
 
@@ -149,7 +151,8 @@ CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 struct CfWarp
 {
     // ---- per-warp context
-    const CfParams *P;
+    const CfParams *P;    // this instance's weights and bounds (per-warp copy in shared memory)
+    const CfParams *PG;   // solver-wide scalars Ts, N, max_ipm_iter (kernel parameter, constant bank)
     int lane, N;
     double *sm;  // per-warp shared memory
     uint64_t *bar;
@@ -164,9 +167,9 @@ struct CfWarp
     double lin[4];     // inf-norms of the linear-system residual of the last solve
     int flags;
 
-    CF_MEM void bind(const CfParams *P_, double *slot, double *sm_)
+    CF_MEM void bind(const CfParams *P_, const CfParams *PG_, double *slot, double *sm_)
     {
-        P = P_; N = P_->N; sm = sm_; lane = cf_lane();
+        P = P_; PG = PG_; N = PG_->N; sm = sm_; lane = cf_lane();
         bar = reinterpret_cast<uint64_t *>(sm_ + CF_SM_BAR);
         par = 0;
         CfScratchLayout s = cf_scratch_layout(N);
@@ -176,7 +179,7 @@ struct CfWarp
         if (lane < CF_NU) w = P->Wdiag[CF_NX + lane];
         else if (lane < CF_NV) { w = P->Wdiag[lane - CF_NU]; wN = P->WNdiag[lane - CF_NU]; }
         double r = sqrt(w), rN = sqrt(wN);
-        Hs = P->Ts * (r * r);
+        Hs = PG->Ts * (r * r);
         HN = (lane < CF_NU) ? Hs : (rN * rN);
     }
 
@@ -213,7 +216,7 @@ struct CfWarp
     {
         double *X0 = sm + CF_SM_V0, *ACC = sm + CF_SM_V1, *XS = sm + CF_SM_V2, *UU = sm + CF_SM_V3;
         double *MS = sm + ((k & 1) ? CF_SM_MS1 : CF_SM_MS0);
-        const double h = P->Ts;
+        const double h = PG->Ts;
         cf_syncwarp();
         if (lane < CF_NX) { const double v = xk_pre; X0[lane] = v; ACC[lane] = v; XS[lane] = v; }
         if (lane < CF_NU) UU[lane] = uk_pre;
@@ -329,90 +332,85 @@ struct CfWarp
                 rk[R_T + lane] = tl; rk[R_T + 4 + lane] = tu;
                 rk[R_LAM + lane] = CF_MU0 / tl; rk[R_LAM + 4 + lane] = CF_MU0 / tu;
             }
-            if (lane < CF_NV) rk[R_UX + lane] = v;
-            if (lane < CF_NX) rk[R_PI + lane] = 0.0;
+            if (lane < CF_NV) { rk[R_UX + lane] = v; rk[R_DUX + lane] = 0.0; }
+            if (lane < CF_NX) { rk[R_PI + lane] = 0.0; rk[R_DPI + lane] = 0.0; }
+            if (lane < 2 * CF_NU) { rk[R_DLAM + lane] = 0.0; rk[R_DT + lane] = 0.0; }
         }
     }
 
     // UPDATE_VAR_QP (x_core_qp_ipm_aux.c:220-325) fused with OCP_QP_RES_COMPUTE +
-    // _INF_NORM (x_ocp_qp_res.c:334-470,602-637): one forward pass over the stages.
-    CF_MEM void update_and_residuals(bool do_update)
+    // _INF_NORM (x_ocp_qp_res.c:334-470,602-637): one forward pass over the stages.  `a_raw` is the step length of the
+    // direction to apply; the very first pass runs with 0 on the zeroed directions of init_var (ux + 0*0 is exact), so
+    // there is a single copy of this code.  Written branch-free: every lane computes (with clamped indices), only
+    // the stores and the norm contributions are predicated.
+    CF_MEM void update_and_residuals(const double a_raw)
     {
-        double a = alpha;
-        if (do_update && a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
+        double a = a_raw;
+        if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
         double ng = 0, nb = 0, nd = 0, nm = 0, mus = 0;
         double *UXS = sm + CF_SM_V0, *PIS = sm + CF_SM_V1;
         pass_begin();
         fetch(0, 0, 0, B_LU);
-        const bool xl = lane >= CF_NU && lane < CF_NV;
-        const int ci = xl ? lane - CF_NU : 0;
+        const bool ul = lane < CF_NU, vl = lane < CF_NV;
+        const bool xl = lane >= CF_NU && vl;
+        const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
         double pi_prev = 0.0;            // lanes 4..16: pi_{k-1}
         double sb_prev = 0.0, b_prev = 0.0;  // lanes 4..16: ([A B] ux)_{k-1} and b_{k-1}; res_b_{k-1} is finished at stage k
         CF_NOUNROLL
         for (int k = 0; k <= N; k++) {
             const int bf = k & 1;
+            const bool kl = k < N;
             cf_syncwarp();  // previous stage's reads of UXS/PIS and of buffer bf^1 are complete
-            if (k < N) fetch(bf ^ 1, k + 1, 0, k + 1 < N ? B_LU : CF_REC);
+            if (kl) fetch(bf ^ 1, k + 1, 0, k + 1 < N ? B_LU : CF_REC);
             wait(bf);
             const double *VS = buf(bf);   // block k from offset 0: record fields at their own offsets, M at B_M
             double *rk = rec(k);
-            double uxc = 0.0, pik = 0.0;
-            if (lane < CF_NV) {
-                uxc = VS[R_UX + lane];
-                if (do_update) { uxc += a * VS[R_DUX + lane]; rk[R_UX + lane] = uxc; }
-            }
-            if (k > 0 && xl) {  // res_b_{k-1} = (b - x+) + [A B] ux, stored as row 17 of M_{k-1} (ROWIN of x_ocp_qp_kkt.c:490)
+            const double uxc = vl ? VS[R_UX + lv] + a * VS[R_DUX + lv] : 0.0;
+            if (vl) rk[R_UX + lane] = uxc;
+            {   // res_b_{k-1} = (b - x+) + [A B] ux, stored as row 17 of M_{k-1} (ROWIN of x_ocp_qp_kkt.c:490)
                 const double rb = (b_prev - uxc) + sb_prev;
-                nb = fmax(nb, fabs(rb));
-                blk(k - 1)[B_M + ci * CF_MROWS + 17] = rb;
+                if (k > 0 && xl) { nb = fmax(nb, fabs(rb)); blk(k - 1)[B_M + ci * CF_MROWS + 17] = rb; }
             }
-            if (k < N && xl) {
-                pik = VS[R_PI + ci];
-                if (do_update) { pik += a * VS[R_DPI + ci]; rk[R_PI + ci] = pik; }
-            }
-            double rg = 0.0;
-            if (lane < CF_NV) {
-                rg = ((k == N) ? HN : Hs) * uxc + VS[R_RQ + lane];
-                if (k > 0 && lane >= CF_NU) rg -= pi_prev;
-            }
-            if (lane < CF_NU && k < N) {
-                double ll = VS[R_LAM + lane], lu = VS[R_LAM + 4 + lane];
-                double tl = VS[R_T + lane], tu = VS[R_T + 4 + lane];
-                if (do_update) {
-                    ll += a * VS[R_DLAM + lane]; lu += a * VS[R_DLAM + 4 + lane];
-                    tl += a * VS[R_DT + lane]; tu += a * VS[R_DT + 4 + lane];
-                    ll = ll <= CF_LAM_MIN ? CF_LAM_MIN : ll; lu = lu <= CF_LAM_MIN ? CF_LAM_MIN : lu;
-                    tl = tl <= CF_T_MIN ? CF_T_MIN : tl; tu = tu <= CF_T_MIN ? CF_T_MIN : tu;
+            const double pik = (kl && xl) ? VS[R_PI + ci] + a * VS[R_DPI + ci] : 0.0;
+            if (kl && xl) rk[R_PI + ci] = pik;
+            double rg = ((k == N) ? HN : Hs) * uxc + VS[R_RQ + lv] - pi_prev;
+            {   // bounds of input l4 (lanes >= 4 compute duplicates that are never stored nor counted)
+                double ll = VS[R_LAM + l4] + a * VS[R_DLAM + l4], lu = VS[R_LAM + 4 + l4] + a * VS[R_DLAM + 4 + l4];
+                double tl = VS[R_T + l4] + a * VS[R_DT + l4], tu = VS[R_T + 4 + l4] + a * VS[R_DT + 4 + l4];
+                ll = ll <= CF_LAM_MIN ? CF_LAM_MIN : ll; lu = lu <= CF_LAM_MIN ? CF_LAM_MIN : lu;
+                tl = tl <= CF_T_MIN ? CF_T_MIN : tl; tu = tu <= CF_T_MIN ? CF_T_MIN : tu;
+                const double rdl = VS[R_D + l4] + tl - uxc, rdu = VS[R_D + 4 + l4] + tu + uxc;
+                const double rml = ll * tl, rmu = lu * tu;
+                if (ul && kl) {
                     rk[R_LAM + lane] = ll; rk[R_LAM + 4 + lane] = lu;
                     rk[R_T + lane] = tl; rk[R_T + 4 + lane] = tu;
+                    rk[R_RESD + lane] = rdl; rk[R_RESD + 4 + lane] = rdu;
+                    rk[R_BKP + lane] = rml; rk[R_BKP + 4 + lane] = rmu;
+                    rk[R_RESM + lane] = rml - CF_TAU_MIN; rk[R_RESM + 4 + lane] = rmu - CF_TAU_MIN;  // predictor rhs
+                    rg += lu - ll;
+                    mus += rml + rmu;
+                    nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
+                    nm = fmax(nm, fmax(fabs(rml), fabs(rmu)));
                 }
-                rg += lu - ll;
-                double rdl = VS[R_D + lane] + tl - uxc, rdu = VS[R_D + 4 + lane] + tu + uxc;
-                double rml = ll * tl, rmu = lu * tu;
-                rk[R_RESD + lane] = rdl; rk[R_RESD + 4 + lane] = rdu;
-                rk[R_BKP + lane] = rml; rk[R_BKP + 4 + lane] = rmu;
-                mus += rml + rmu;
-                nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
-                nm = fmax(nm, fmax(fabs(rml), fabs(rmu)));
             }
             double sbk = 0.0;
-            if (k < N) {
-                if (lane < CF_NV) UXS[lane] = uxc;
+            if (kl) {   // warp-uniform
+                if (vl) UXS[lane] = uxc;
                 if (xl) PIS[ci] = pik;
                 cf_syncwarp();
                 const double *Mk = VS + B_M;
-                if (lane < CF_NV) {  // res_g += [B';A'] pi_k   (row layout: own elements stride 18)
+                {   // res_g += [B';A'] pi_k   (row layout: own elements stride 18)
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
                     for (int cp = 0; cp < 6; cp++) {
                         const cf_d2 p2 = cf_ld2(PIS + 2 * cp);
-                        s0 += Mk[(2 * cp) * CF_MROWS + lane] * p2.x;
-                        s1 += Mk[(2 * cp + 1) * CF_MROWS + lane] * p2.y;
+                        s0 += Mk[(2 * cp) * CF_MROWS + lv] * p2.x;
+                        s1 += Mk[(2 * cp + 1) * CF_MROWS + lv] * p2.y;
                     }
-                    s0 += Mk[12 * CF_MROWS + lane] * PIS[12];
+                    s0 += Mk[12 * CF_MROWS + lv] * PIS[12];
                     rg += s0 + s1;
                 }
-                if (xl) {  // [A B] ux   (column layout: contiguous)
+                {   // [A B] ux   (column layout: contiguous)
                     const double *Mc = Mk + ci * CF_MROWS;
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
@@ -422,13 +420,13 @@ struct CfWarp
                         s1 += m2.y * u2.y;
                     }
                     s0 += Mc[16] * UXS[16];
-                    sbk = s0 + s1;
+                    sbk = xl ? s0 + s1 : 0.0;
                 }
             }
-            if (lane < CF_NV) { rk[R_RESG + lane] = rg; ng = fmax(ng, fabs(rg)); }
+            if (vl) { rk[R_RESG + lane] = rg; ng = fmax(ng, fabs(rg)); }
             pi_prev = pik;
             sb_prev = sbk;
-            b_prev = (k < N && xl) ? VS[R_B + ci] : 0.0;
+            b_prev = (kl && xl) ? VS[R_B + ci] : 0.0;
         }
         nrm[0] = cf_warp_max(ng); nrm[1] = cf_warp_max(nb); nrm[2] = cf_warp_max(nd); nrm[3] = cf_warp_max(nm);
         mu = cf_warp_sum(mus) * (1.0 / (double) (2 * CF_NU * N));
@@ -443,7 +441,7 @@ struct CfWarp
     {
         const double *f = q - R_DLAM;
         double ll = f[R_LAM + lane], lu = f[R_LAM + 4 + lane];
-        double til = 1.0 / f[R_T + lane], tiu = 1.0 / f[R_T + 4 + lane];
+        const double til = cf_rcp(f[R_T + lane]), tiu = cf_rcp(f[R_T + 4 + lane]);
         double rml, rmu;
         if (rm_mode == 3) { rml = f[R_RESM + lane]; rmu = f[R_RESM + 4 + lane]; }
         else {
@@ -471,7 +469,8 @@ struct CfWarp
     //   S   = [H_k + Gamma ; (res_g + gamma)'] + W [B';A']'  SYRK_LN_MN :652
     //   L   = chol of the 4 input columns of S               POTRF_L_MN(nv+1, nu) :653
     //   P_k = S_xx - Ls Ls',  p_k = s_x - Ls l_u             SYRK -1 :655
-    // Stored per stage: LU (18 x 4 factor columns) and the packed lower triangle of P_k followed by p_k.
+    // Stored per stage: LU (18 x 4 factor columns, inverse pivots on the diagonal), the packed lower triangle of P_k, and
+    // the gradient parts l_u | p_k in R_DUX of the stage record.
     CF_MEM void factorize()
     {
         double *PS = sm + CF_SM_W;                 // P_{k+1}, full symmetric 13 x 13, stride 20
@@ -495,7 +494,7 @@ struct CfWarp
                 PS[i * CF_ALST + i] = hN;
                 PV[i] = gN;
                 PXN[cf_tri(i) + i] = hN;
-                PXN[91 + i] = gN;
+                rec(N)[R_DUX + lane] = gN;   // p_N for the forward sweep
             }
         }
         // gradient row and diagonal of the stage Hessian are computed one stage ahead (software pipelining:
@@ -600,7 +599,7 @@ struct CfWarp
             // (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
             {
                 const cf_d2 o01 = cf_ld2(LUs + rl * 4), o23 = cf_ld2(LUs + rl * 4 + 2);
-                double o[CF_NU] = {o01.x, o01.y, o23.x, o23.y};
+                double o[CF_NU] = {o01.x, o01.y, o23.x, o23.y}, og[CF_NU];
                 CF_UNROLL
                 for (int j = 0; j < CF_NU; j++) {
                     double v = o[j];
@@ -612,13 +611,19 @@ struct CfWarp
                     if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; }
                     o[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
                     LUs[rl * 4 + j] = o[j];
+                    og[j] = (rl == j) ? inv : o[j];
                     cf_syncwarp();
                 }
-                // factor columns to global memory (LU block of stage k)
+                // factor columns to global memory (LU block of stage k), inverse pivots on the diagonal; the gradient row
+                // l_u goes where the forward sweep picks it up
                 double *LFk = blk(k) + B_LU;
                 if (lane < CF_MROWS) {
-                    cf_st2(LFk + lane * 4, o[0], o[1]);
-                    cf_st2(LFk + lane * 4 + 2, o[2], o[3]);
+                    cf_st2(LFk + lane * 4, og[0], og[1]);
+                    cf_st2(LFk + lane * 4 + 2, og[2], og[3]);
+                }
+                if (lane == 17) {
+                    cf_st2(rec(k) + R_DUX, o[0], o[1]);
+                    cf_st2(rec(k) + R_DUX + 2, o[2], o[3]);
                 }
             }
             // ---- Schur complement on the tensor cores (K = 4 = the input columns): S -= Ls Ls'
@@ -643,7 +648,7 @@ struct CfWarp
                             const double val = s[t][tp][e];
                             if (c >= CF_NU && c < CF_NV) {
                                 const int jx = c - CF_NU;
-                                if (r == 17) { PV[jx] = val; if (k > 0) LFk[91 + jx] = val; }   // p_k
+                                if (r == 17) { PV[jx] = val; rec(k)[R_DUX + c] = val; }   // p_k
                                 else if (r >= c && r < CF_NV) {                             // P_k, lower part + mirror
                                     const int ix = r - CF_NU;
                                     PS[ix * CF_ALST + jx] = val;
@@ -659,15 +664,17 @@ struct CfWarp
         cf_syncwarp();
     }
 
-    // Forward substitution shared by the factorise-and-solve (mode 0, :536-570) and the
-    // rhs-only solve (mode 1, :1250-1290); computes dux, dpi, then dlam, dt (:741-758,
-    // x_core_qp_ipm_aux.c:117-142), the step length ingredients (:146-216) and the inf-norms of
-    // the linear-system residual (OCP_QP_RES_COMPUTE_LIN, x_ocp_qp_res.c:474-598) on the fly.
-    // rm_mode selects which complementarity rhs the step was computed for (see bound_terms).
-    CF_MEM void forward(int mode, int rm_mode)
+    // Forward substitution shared by the factorise-and-solve (:536-570) and the rhs-only solve (:1250-1290): the
+    // backward sweep before it (factorize or backward_rhs) left l_u of stage k and p_k in R_DUX of stage k's record and
+    // the complementarity rhs in R_RESM.  Computes dux, dpi, then dlam, dt (:741-758, x_core_qp_ipm_aux.c:117-142), the
+    // step length ingredients (:146-216) and the inf-norms of the linear-system residual (OCP_QP_RES_COMPUTE_LIN,
+    // x_ocp_qp_res.c:474-598) on the fly.  Branch-free: every lane computes with clamped indices (lanes with equal
+    // lane & 3 hold identical input/bound quantities), stores and norm contributions are predicated.
+    CF_MEM void forward()
     {
         double *XS = sm + CF_SM_V0, *DS = sm + CF_SM_V1, *PS = sm + CF_SM_V3;
-        double a_p = -1.0, a_d = -1.0;            // running alpha_prim / alpha_dual (negated)
+        // running step lengths to the boundary kept as ratios num/den (den < 0): alpha = min(1, min -lam/dlam, -t/dt)
+        double dn = 1.0, dd = -1.0, pn_ = 1.0, pd_ = -1.0;
         double lg = 0, lb = 0, ld = 0, lm = 0;    // linear residual norms
         double dxk = 0.0;        // lanes 4..16: dx_k ; stage 0 has none
         double dpi_prev = 0.0;   // lanes 4..16: dpi_{k-1}
@@ -675,77 +682,77 @@ struct CfWarp
         pass_begin();
         if (N > 0) fetch(0, 0, VO, VN);
         XS[lane] = 0.0; PS[lane] = 0.0;
-        const bool xl = lane >= CF_NU && lane < CF_NV;
-        const int ci = xl ? lane - CF_NU : 0;
+        const bool ul = lane < CF_NU, vl = lane < CF_NV;
+        const bool xl = lane >= CF_NU && vl;
+        const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
         CF_NOUNROLL
         for (int k = 0; k < N; k++) {
             const int bf = k & 1;
             double *rk = rec(k);
-            const double pnext = (mode == 1 && xl) ? rec(k + 1)[R_DUX + lane] : 0.0;  // p_{k+1} of the backward sweep
+            const double pnext = rec(k + 1)[R_DUX + lv];  // p_{k+1} left by the backward sweep (x lanes)
             wait(bf);
             cf_syncwarp();  // every lane is done with buffer bf^1
             if (k + 1 < N) fetch(bf ^ 1, k + 1, VO, VN);
             const double *VS = buf(bf) - VO;   // VS[offset within the stage block]
             const double *Mk = VS + B_M, *LU = VS + B_LU, *LX = VS + B_PX;
-            // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu)
-            double v = 0.0, invd = 1.0;
-            if (lane < CF_NU) {
-                double v0 = (mode == 0) ? -LU[17 * 4 + lane] : -VS[R_DUX + lane], v1 = 0.0;
+            // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu); input l4 on every lane
+            double v;
+            {
+                double v0 = -VS[R_DUX + l4], v1 = 0.0;
                 CF_UNROLL
                 for (int ip = 0; ip < 6; ip++) {
                     const cf_d2 x2 = cf_ld2(XS + 2 * ip);
-                    v0 -= LU[(CF_NU + 2 * ip) * 4 + lane] * x2.x;
-                    v1 -= LU[(CF_NU + 2 * ip + 1) * 4 + lane] * x2.y;
+                    v0 -= LU[(CF_NU + 2 * ip) * 4 + l4] * x2.x;
+                    v1 -= LU[(CF_NU + 2 * ip + 1) * 4 + l4] * x2.y;
                 }
-                v0 -= LU[16 * 4 + lane] * XS[12];
+                v0 -= LU[16 * 4 + l4] * XS[12];
                 v = v0 + v1;
-                invd = 1.0 / LU[lane * 4 + lane];
             }
+            const double invd = LU[l4 * 4 + l4];   // inverse pivot
             double du = 0.0;
             CF_UNROLL
             for (int j = CF_NU - 1; j >= 0; j--) {
                 const double duj = cf_shfl(v * invd, j);
-                if (lane == j) du = duj;
-                if (lane < j) v -= LU[j * 4 + lane] * duj;
+                const double vn = v - LU[j * 4 + l4] * duj;
+                du = (l4 == j) ? duj : du;
+                v = (l4 < j) ? vn : v;
             }
-            const double duxk = (lane < CF_NU) ? du : dxk;  // lane r: dux_k[r]
-            if (lane < CF_NV) rk[R_DUX + lane] = duxk;
-            // ---- dlam, dt, alpha (lanes 0..3)
-            double dlam_l = 0, dlam_u = 0;
-            if (lane < CF_NU) {
-                const double ll = VS[R_LAM + lane], lu = VS[R_LAM + 4 + lane];
-                const double tl = VS[R_T + lane], tu = VS[R_T + 4 + lane];
-                const double rdl = VS[R_RESD + lane], rdu = VS[R_RESD + 4 + lane];
-                double rml, rmu;
-                if (rm_mode == 0) { rml = VS[R_BKP + lane] - CF_TAU_MIN; rmu = VS[R_BKP + 4 + lane] - CF_TAU_MIN; }
-                else { rml = VS[R_RESM + lane]; rmu = VS[R_RESM + 4 + lane]; }
-                const double til = 1.0 / tl, tiu = 1.0 / tu;
+            const double duxk = ul ? du : dxk;  // lane r: dux_k[r]
+            if (vl) rk[R_DUX + lane] = duxk;
+            // ---- dlam, dt, alpha for the bounds of input l4
+            double dlam_l, dlam_u;
+            {
+                const double ll = VS[R_LAM + l4], lu = VS[R_LAM + 4 + l4];
+                const double tl = VS[R_T + l4], tu = VS[R_T + 4 + l4];
+                const double rdl = VS[R_RESD + l4], rdu = VS[R_RESD + 4 + l4];
+                const double rml = VS[R_RESM + l4], rmu = VS[R_RESM + 4 + l4];
+                const double til = cf_rcp(tl), tiu = cf_rcp(tu);
                 double dtl = du, dtu = -du;
                 dlam_l = -til * (rml + (ll * dtl) - (ll * rdl));
                 dlam_u = -tiu * (rmu + (lu * dtu) - (lu * rdu));
                 dtl -= rdl; dtu -= rdu;
-                rk[R_DLAM + lane] = dlam_l; rk[R_DLAM + 4 + lane] = dlam_u;
-                rk[R_DT + lane] = dtl; rk[R_DT + 4 + lane] = dtu;
-                if (a_d * dlam_l > ll) a_d = ll / dlam_l;
-                if (a_p * dtl > tl) a_p = tl / dtl;
-                if (a_d * dlam_u > lu) a_d = lu / dlam_u;
-                if (a_p * dtu > tu) a_p = tu / dtu;
+                if (ul) {
+                    rk[R_DLAM + lane] = dlam_l; rk[R_DLAM + 4 + lane] = dlam_u;
+                    rk[R_DT + lane] = dtl; rk[R_DT + 4 + lane] = dtu;
+                }
+                // a*d > v with a = n/dd, dd < 0  <=>  n*d < v*dd ; then the new ratio is v/d (d < 0)
+                bool c;
+                c = dn * dlam_l < ll * dd; dn = c ? ll : dn; dd = c ? dlam_l : dd;
+                c = pn_ * dtl < tl * pd_; pn_ = c ? tl : pn_; pd_ = c ? dtl : pd_;
+                c = dn * dlam_u < lu * dd; dn = c ? lu : dn; dd = c ? dlam_u : dd;
+                c = pn_ * dtu < tu * pd_; pn_ = c ? tu : pn_; pd_ = c ? dtu : pd_;
                 // linear residuals of the complementarity / bound rows
                 ld = fmax(ld, fmax(fabs(rdl + dtl - du), fabs(rdu + dtu + du)));
                 lm = fmax(lm, fmax(fabs(rml + ll * dtl + dlam_l * tl), fabs(rmu + lu * dtu + dlam_u * tu)));
             }
             // stationarity residual, part 1: H dux + rhs_g - dpi_{k-1} + dlam_ub - dlam_lb
-            double rgl = 0.0;
-            if (lane < CF_NV) {
-                rgl = Hs * duxk + VS[R_RESG + lane];
-                if (k > 0 && lane >= CF_NU) rgl -= dpi_prev;
-                rgl += dlam_u - dlam_l;
-            }
+            double rgl = Hs * duxk + VS[R_RESG + lv] - dpi_prev;
+            rgl += ul ? dlam_u - dlam_l : 0.0;
             // ---- dx+ = [A B] dux + res_b        GEMV_T, column layout of M_k (contiguous)
-            if (lane < CF_NV) DS[lane] = duxk;
+            if (vl) DS[lane] = duxk;
             cf_syncwarp();
-            double dxn = 0.0;
-            if (xl) {
+            double dxn;
+            {
                 const double *Mc = Mk + ci * CF_MROWS;
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
@@ -757,53 +764,51 @@ struct CfWarp
                 const cf_d2 m2 = cf_ld2(Mc + 16);  // [M[16][c], res_b[c]]
                 s0 += m2.x * DS[16];
                 const double sacc = s0 + s1;
-                dxn = sacc + m2.y;
-                lb = fmax(lb, fabs((m2.y - dxn) + sacc));
-                XS[ci] = dxn;
+                dxn = xl ? sacc + m2.y : 0.0;
+                lb = fmax(lb, xl ? fabs((m2.y - dxn) + sacc) : 0.0);
+                if (xl) XS[ci] = dxn;
             }
             cf_syncwarp();
-            // ---- dpi = P_{k+1} dx+ + p_{k+1}   (GEMV_N :712,729); P packed lower, p from the factorisation (mode 0)
-            // or from the backward rhs sweep (mode 1)
-            double dpik = 0.0;
-            if (xl) {
+            // ---- dpi = P_{k+1} dx+ + p_{k+1}   (GEMV_N :712,729); P packed lower
+            double dpik;
+            {
                 const double *Li = LX + cf_tri(ci);   // row ci: entries c <= ci; entries c > ci come from column ci
-                double z0 = (mode == 0) ? LX[91 + ci] : pnext, z1 = 0.0;
+                double z0 = pnext, z1 = 0.0;
                 CF_UNROLL
                 for (int c = 0; c < CF_NX; c++) {
                     const double pc = (c <= ci) ? Li[c] : LX[(c * (c + 1)) / 2 + ci];
                     if (c & 1) z1 += pc * XS[c];
                     else z0 += pc * XS[c];
                 }
-                dpik = z0 + z1;
-                rk[R_DPI + ci] = dpik;
-                PS[ci] = dpik;
+                dpik = xl ? z0 + z1 : 0.0;
+                if (xl) { rk[R_DPI + ci] = dpik; PS[ci] = dpik; }
             }
             cf_syncwarp();
             // stationarity residual, part 2: + [B';A'] dpi_k   (row layout)
-            if (lane < CF_NV) {
+            {
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
                 for (int cp = 0; cp < 6; cp++) {
                     const cf_d2 p2 = cf_ld2(PS + 2 * cp);
-                    s0 += Mk[(2 * cp) * CF_MROWS + lane] * p2.x;
-                    s1 += Mk[(2 * cp + 1) * CF_MROWS + lane] * p2.y;
+                    s0 += Mk[(2 * cp) * CF_MROWS + lv] * p2.x;
+                    s1 += Mk[(2 * cp + 1) * CF_MROWS + lv] * p2.y;
                 }
-                s0 += Mk[12 * CF_MROWS + lane] * PS[12];
-                lg = fmax(lg, fabs(rgl + (s0 + s1)));
+                s0 += Mk[12 * CF_MROWS + lv] * PS[12];
+                lg = fmax(lg, vl ? fabs(rgl + (s0 + s1)) : 0.0);
             }
             dpi_prev = dpik;
             dxk = dxn;
         }
         // terminal stage: no inputs, no bounds, no dynamics
-        if (lane < CF_NV) {
-            const double duxN = (lane < CF_NU) ? 0.0 : dxk;
-            double rgl = HN * duxN + rec(N)[R_RESG + lane];
+        if (vl) {
+            const double duxN = ul ? 0.0 : dxk;
+            const double rgl = HN * duxN + rec(N)[R_RESG + lane] - dpi_prev;
             rec(N)[R_DUX + lane] = duxN;
-            if (N > 0 && lane >= CF_NU) rgl -= dpi_prev;
             lg = fmax(lg, fabs(rgl));
         }
         lin[0] = cf_warp_max(lg); lin[1] = cf_warp_max(lb); lin[2] = cf_warp_max(ld); lin[3] = cf_warp_max(lm);
-        a_p = cf_warp_max(a_p); a_d = cf_warp_max(a_d);
+        // alpha = min(1, prim, dual) as in x_core_qp_ipm_aux.c:146-216 (running values are negative)
+        const double a_p = cf_warp_max(pn_ / pd_), a_d = cf_warp_max(dn / dd);
         alpha = -(a_p > a_d ? a_p : a_d);
         cf_syncwarp();
     }
@@ -852,7 +857,7 @@ struct CfWarp
             const int rl = lane < CF_NV ? lane : 0;
             const cf_d2 l01 = cf_ld2(LU + rl * 4), l23 = cf_ld2(LU + rl * 4 + 2);
             const double Lr[CF_NU] = {l01.x, l01.y, l23.x, l23.y};
-            const double invd = (lane < CF_NU) ? 1.0 / LU[rl * 4 + rl] : 1.0;
+            const double invd = LU[(lane & 3) * 5];   // inverse pivot (only lanes 0..3 feed the shuffles)
             CF_UNROLL
             for (int j = 0; j < CF_NU; j++) {
                 const double zj = cf_shfl(rhs * invd, j);
@@ -907,15 +912,16 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
     w.alpha = 1.0;
     w.flags = 0;
     cf_syncwarp();
-    const int itmax = w.P->max_ipm_iter < CF_ITER_MAX ? w.P->max_ipm_iter : CF_ITER_MAX;
+    const int itmax = w.PG->max_ipm_iter < CF_ITER_MAX ? w.PG->max_ipm_iter : CF_ITER_MAX;
     enum { ST_RES, ST_FACT, ST_FWD, ST_BWD };
-    int st = ST_RES, kk = 0, fmode = 0, frm = 0, brm = 1;
-    bool upd = false;
+    int st = ST_RES, kk = 0, brm = 1;
+    bool first = true, predictor = true;
     double sigma_mu = 0.0, mu_aff0 = 0.0;
     for (;;) {
         if (st == ST_RES) {
-            w.update_and_residuals(upd);
-            if (upd) kk++;
+            w.update_and_residuals(first ? 0.0 : w.alpha);
+            if (first) { first = false; w.alpha = 1.0; }
+            else kk++;
             const bool go = kk < itmax && w.alpha > CF_ALPHA_MIN &&
                             (w.nrm[0] > CF_RES_G_MAX || w.nrm[1] > CF_RES_B_MAX || w.nrm[2] > CF_RES_D_MAX ||
                              fabs(w.nrm[3] - CF_TAU_MIN) > CF_RES_M_MAX);
@@ -924,11 +930,11 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
         } else if (st == ST_FACT) {
             // ---- OCP_QP_IPM_DELTA_STEP (:1943-2405): affine (predictor) direction
             w.factorize();
-            fmode = 0; frm = 0;
+            predictor = true;
             st = ST_FWD;
         } else if (st == ST_FWD) {
-            w.forward(fmode, frm);
-            if (fmode == 0) {
+            w.forward();
+            if (predictor) {
                 if (!w.lin_res_ok_fact()) w.flags |= CF_FLAG_LIN_RES_FACT;
                 w.compute_mu_aff();
                 const double tmp = w.mu_aff / w.mu;
@@ -947,13 +953,12 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
                 if (recenter) { brm = 2; st = ST_BWD; }
                 else {
                     if (!w.lin_res_ok_corr()) w.flags |= CF_FLAG_LIN_RES_CORR;
-                    upd = true;
                     st = ST_RES;
                 }
             }
         } else {
             w.backward_rhs(brm, sigma_mu);
-            fmode = 1; frm = 3;
+            predictor = false;
             st = ST_FWD;
         }
     }
@@ -995,9 +1000,9 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
         cf_syncwarp();
     }
     CfWarp w;
-    w.bind(P, slot, sm);
+    w.bind(P, Pg, slot, sm);
     w.par = par;
-    const int N = P->N;
+    const int N = Pg->N;
     double *xg = bv.x + (long) inst * (N + 1) * CF_NX;
     double *ug = bv.u + (long) inst * N * CF_NU;
     const double *x0g = bv.x0 + (long) inst * CF_NX;

@@ -53,6 +53,7 @@ CF_DEV void cf_st2(double *p, double a, double b)
 }
 CF_DEV void cf_mbar_init(uint64_t *bar) { *bar = 0; }
 CF_DEV double cf_rsqrt_seed(double x) { return (double) (float) (1.0 / sqrt(x)); }  // ~2^-23, like MUFU.RSQ64H
+CF_DEV double cf_rcp_seed(double x) { return (double) (float) (1.0 / x); }            // ~2^-23, like MUFU.RCP64H
 #define cf_bulk_expect(bar, bytes) cfemu::bulk_expect((bar), (bytes), __LINE__)
 #define cf_bulk_g2s_raw(dst, src, bytes, bar) cfemu::bulk_g2s((dst), (src), (bytes), (bar), __LINE__)
 #define cf_bulk_wait(bar, parity) cfemu::bulk_wait((bar), (parity), __LINE__)
@@ -85,6 +86,12 @@ CF_DEV double cf_rsqrt_seed(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+CF_DEV double cf_rcp_seed(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
 }
 CF_DEV uint32_t cf_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -153,6 +160,17 @@ CF_DEV void cf_sqrt_rsqrt(double x, double &root, double &inv)
     const double d = fma(-g, g, x);
     root = fma(d, h, g);
     inv = h + h;
+}
+
+// 1/x for x in the normal range (slacks, multipliers, pivots): hardware seed (2^-23) + two Newton steps; branch-free,
+// no slow-path call, within 1 ulp of the IEEE quotient.
+CF_DEV double cf_rcp(double x)
+{
+    double y = cf_rcp_seed(x);
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
 }
 
 // butterfly reductions (all lanes get the result)
