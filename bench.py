@@ -169,8 +169,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the solve path has no CPU implementation")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]        # those levels print "NCCL version ..." on stdout: keep it to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, B = args.horizon, args.batch
     w = make_workload(args.workload, B, N, args.seed + rank)
