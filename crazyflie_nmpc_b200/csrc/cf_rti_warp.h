@@ -36,25 +36,24 @@
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
 #define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
 #define CF_LX 92                          // cost-to-go Hessian of the state block: packed lower triangle of P (91) + pad
-#define CF_LFSZ (CF_LU + CF_LX)           // 176 doubles per stage
-// Per-stage record of all IPM vectors (192 doubles).  The field order makes what each sweep reads one
-// contiguous, 16-byte aligned range, so it is staged by a single TMA bulk copy one stage ahead:
-//   residual sweep  [R_UX, R_RESD)  (+ R_DUX)      forward sweep  [R_LAM, end)      backward sweep  [R_DLAM, R_DUX)
+// One contiguous block per stage in the scratch slot.  The field order makes whatever a sweep needs of a stage ONE
+// contiguous, 16-byte aligned range = one TMA bulk copy, issued one stage ahead of the arithmetic:
+//   residual+factorisation sweep [0, B_RD)      rhs-only backward sweep [R_BKP, B_PX)      forward sweep [R_LAM, CF_SB)
 // 17-vectors are padded to 18, 13-vectors to 14; bound fields are [lb(4) | ub(4)].
-#define CF_REC 192
-// One contiguous block per stage in the scratch slot: [ record | [B';A';res_b'] | LU | PX ], so that whatever a
-// sweep needs of a stage is ONE contiguous, 16-byte aligned range = one TMA bulk copy:
-//   residual [0, B_LU)   backward [R_DLAM, B_PX)   forward [R_LAM, CF_SB)   factorisation [B_M, B_LU)
-// PX of block k holds P_{k+1} (what the forward sweep of stage k multiplies with); it is written by the factorisation
-// of stage k+1.  The gradient parts of the factorisation (l_u of stage k, p_k) go to R_DUX of stage k's record, the place
-// where the rhs-only backward sweep leaves them too, so the forward sweep is the same code for both.  The diagonal of
-// the stored LU block holds the INVERSE pivots (like BLASFEO's dA), the only form the substitutions need.
-#define B_M CF_REC
-#define B_LU (B_M + CF_MSZ)
-#define B_PX (B_LU + CF_LU)
-#define CF_SB (B_PX + CF_LX)              // 590 doubles per stage
-enum { R_UX = 0, R_PI = 18, R_DPI = 32, R_RQ = 46, R_B = 64, R_D = 78, R_DLAM = 86, R_DT = 94, R_LAM = 102, R_T = 110,
-       R_RESD = 118, R_BKP = 126, R_RESM = 134, R_RESG = 142, R_PB = 160, R_DUX = 174 };
+//   R_UX  ux_k            R_PI  pi_{k-1} (multiplier of the dynamics ENTERING stage k)   R_DPI  its step
+//   R_RQ  gradient        R_D   bound data [lb - u ; u - ub]
+//   R_BKP lam*t of the iterate (res_m backup)          R_PB   P_{k+1} res_b (cached for the rhs-only sweeps)
+//   R_DLAM, R_DT steps    R_LAM, R_T multipliers / slacks
+//   R_DUX  in: l_u | p_k left by a backward sweep, out: the step dux_k
+//   B_M    [B';A'] rows 0..16, row 17 = b_k (linearisation, never changes inside the IPM), element (r,c) at c*18 + r
+//   R_RESD, R_RESM, R_RESG, R_RESB residuals (R_RESM = the complementarity rhs of the next solve)
+//   B_LU   factor of the 4 input columns (18 x 4), INVERSE pivots on the diagonal (like BLASFEO's dA)
+//   B_PX   packed lower triangle of P_{k+1} (what the forward sweep of stage k multiplies with; written by the
+//          factorisation of stage k+1)
+enum { R_UX = 0, R_PI = 18, R_DPI = 32, R_RQ = 46, R_D = 64, R_BKP = 72, R_PB = 80, R_DLAM = 94, R_DT = 102, R_LAM = 110,
+       R_T = 118, R_DUX = 126, B_M = 144, B_RD = B_M + CF_MSZ, R_RESD = B_RD, R_RESM = B_RD + 8, R_RESG = B_RD + 16,
+       R_RESB = B_RD + 34, B_LU = B_RD + 48, B_PX = B_LU + CF_LU, CF_SB = B_PX + CF_LX };   // 590 doubles per stage
+static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 && CF_SB % 2 == 0, "16-byte alignment of TMA ranges");
 
 // HPIPM arguments in effect for the reference configuration (BALANCE mode + acados
 // overrides): acados/acados/ocp_qp/ocp_qp_hpipm.c:96-108, x_ocp_qp_ipm.c:133-161
@@ -132,19 +131,21 @@ static inline
 }
 
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
-#define CF_SM_BUF0 0                           // sweeps: staged range of a stage block, double buffered (<= 500 doubles)
-#define CF_SM_BUF1 500
-#define CF_SM_MS0 0                            // factorisation / linearisation: [B';A';res_b'] staging, double buffered
+#define CF_SM_BUF0 0                           // sweeps: staged range of a stage block, double buffered (<= 480 doubles)
+#define CF_SM_BUF1 480
+#define CF_SM_MS0 0                            // linearisation: [B';A';b'] staging, double buffered
 #define CF_SM_MS1 CF_MSZ
-#define CF_SM_W (2 * CF_MSZ)                   // factorisation: P_{k+1} (13 x 20) and W / input-column block (18 x 20)
-#define CF_ALST 20                             //   row stride 20: conflict-free fp64 tensor-core fragment loads
-#define CF_SM_V0 (CF_SM_W + 31 * CF_ALST)      // four 32-double broadcast vectors (after the larger of 2*500 and 468+620)
-#define CF_SM_V1 (CF_SM_V0 + 32)
-#define CF_SM_V2 (CF_SM_V1 + 32)
-#define CF_SM_V3 (CF_SM_V2 + 32)
-#define CF_SM_BAR (CF_SM_V3 + 32)              // two mbarriers
+#define CF_ALST 20                             // row stride 20: conflict-free fp64 tensor-core fragment loads
+#define CF_SM_P (2 * 480)                      // factorisation: P_{k+1}, 13 x 20 (the W / input-column block, 18 x 20,
+                                               //   overlays the staged block of the stage being factorised)
+#define CF_SM_V0 (CF_SM_P + 13 * CF_ALST)      // four 20-double broadcast vectors
+#define CF_SM_V1 (CF_SM_V0 + 20)
+#define CF_SM_V2 (CF_SM_V1 + 20)
+#define CF_SM_V3 (CF_SM_V2 + 20)
+#define CF_SM_BAR (CF_SM_V3 + 20)              // two mbarriers
 #define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
-#define CF_SM_DOUBLES (CF_SM_PAR + CF_PAR_DOUBLES)  // 1268 doubles = 10144 bytes per warp (5 blocks of 4 warps per SM)
+#define CF_SM_DOUBLES (CF_SM_PAR + CF_PAR_DOUBLES)  // 1352 doubles = 10816 bytes per warp (5 blocks of 4 warps per SM)
+static_assert(B_RD <= 480 && CF_SB - R_LAM <= 480 && B_PX - R_BKP <= 480 && 18 * CF_ALST <= 480, "staging buffers");
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
@@ -190,7 +191,7 @@ struct CfWarp
         if (lane == 0) cf_fence_proxy_async();    // ... before the bulk (async-proxy) reads of this pass
     }
     CF_MEM double *blk(int k) const { return SLOT + (long) k * CF_SB; }
-    CF_MEM double *rec(int k) const { return blk(k); }
+    CF_MEM double *rec(int k) const { return blk(k); }   // record fields are addressed from the block start
     CF_MEM double *buf(int bf) const { return sm + (bf ? CF_SM_BUF1 : CF_SM_BUF0); }
     // stage doubles [start, start+len) of stage block k into buffer `bf` (one bulk copy, lane 0 issues)
     CF_MEM void fetch_to(double *dst, int bf, int k, int start, int len)
@@ -285,7 +286,6 @@ struct CfWarp
             }
             cf_syncwarp();
         }
-        if (lane < CF_NX) rec(k)[R_B + lane] = MS[lane * CF_MROWS + 17];
         // gradient: scaling * W * (y - yref), [u;x] order (ocp_nlp_cost_ls.c:883-912)
         if (lane < CF_NV) {
             double g;
@@ -294,18 +294,41 @@ struct CfWarp
             rec(k)[R_RQ + lane] = g;
         }
         // bounds (ocp_nlp_constraints_bgh.c:1634-1636): d = [lb - u ; u - ub]
+        double v0 = 0.0;
         if (lane < CF_NU) {
-            rec(k)[R_D + lane] = ((k == 0) ? P->lbu0[lane] : P->lbu[lane]) - UU[lane];
-            rec(k)[R_D + 4 + lane] = UU[lane] - ((k == 0) ? P->ubu0[lane] : P->ubu[lane]);
+            const double dl = ((k == 0) ? P->lbu0[lane] : P->lbu[lane]) - UU[lane];
+            const double du = UU[lane] - ((k == 0) ? P->ubu0[lane] : P->ubu[lane]);
+            rec(k)[R_D + lane] = dl;
+            rec(k)[R_D + 4 + lane] = du;
+            // OCP_QP_INIT_VAR scheme 1 (x_ocp_qp_ipm.c:1491-1530,1636-1769): slacks at ux = 0, pushed 0.1 inside
+            double tl = -dl, tu = -du;
+            if (tl < CF_THR0) {
+                if (tu < CF_THR0) { v0 = 0.5 * (dl - du); tl = CF_THR0; tu = CF_THR0; }
+                else { tl = CF_THR0; v0 = dl + CF_THR0; }
+            } else if (tu < CF_THR0) { tu = CF_THR0; v0 = -du - CF_THR0; }
+            rec(k)[R_T + lane] = tl; rec(k)[R_T + 4 + lane] = tu;
+            rec(k)[R_LAM + lane] = CF_MU0 / tl; rec(k)[R_LAM + 4 + lane] = CF_MU0 / tu;
         }
+        init_stage_vectors(k, v0);
         cf_syncwarp();
         if (lane == 0) cf_bulk_s2g(blk(k) + B_M, MS, CF_MSZ * 8);
         xk_pre = xn_pre;
         uk_pre = un_pre;
     }
 
+    // ux = v (0 unless a bound had to be respected), pi = 0 and zero steps, so that the first residual pass can be an
+    // "update with step 0" (one code copy of that sweep)
+    CF_MEM void init_stage_vectors(int k, double v)
+    {
+        double *rk = rec(k);
+        if (lane < CF_NV) { rk[R_UX + lane] = v; rk[R_DUX + lane] = 0.0; }
+        if (lane < CF_NX) { rk[R_PI + lane] = 0.0; rk[R_DPI + lane] = 0.0; }
+        if (lane < 2 * CF_NU) { rk[R_DLAM + lane] = 0.0; rk[R_DT + lane] = 0.0; }
+    }
+
     CF_MEM void terminal_gradient(const double *xg, const double *yref_eg)
     {
+        init_stage_vectors(N, 0.0);
         if (lane < CF_NV) {
             double g = 0.0;
             if (lane >= CF_NU) g = P->WNdiag[lane - CF_NU] * (xg[N * CF_NX + lane - CF_NU] - yref_eg[lane - CF_NU]);
@@ -315,65 +338,62 @@ struct CfWarp
     }
 
     // =============================================================== IPM pieces
-    // OCP_QP_INIT_VAR scheme 1 (x_ocp_qp_ipm.c:1491-1530,1636-1769)
-    CF_MEM void init_var()
-    {
-        CF_NOUNROLL
-        for (int k = 0; k <= N; k++) {
-            double *rk = rec(k);
-            double v = 0.0;
-            if (lane < CF_NU && k < N) {
-                double dl = rk[R_D + lane], du = rk[R_D + 4 + lane];
-                double tl = -dl, tu = -du;
-                if (tl < CF_THR0) {
-                    if (tu < CF_THR0) { v = 0.5 * (dl - du); tl = CF_THR0; tu = CF_THR0; }
-                    else { tl = CF_THR0; v = dl + CF_THR0; }
-                } else if (tu < CF_THR0) { tu = CF_THR0; v = -du - CF_THR0; }
-                rk[R_T + lane] = tl; rk[R_T + 4 + lane] = tu;
-                rk[R_LAM + lane] = CF_MU0 / tl; rk[R_LAM + 4 + lane] = CF_MU0 / tu;
-            }
-            if (lane < CF_NV) { rk[R_UX + lane] = v; rk[R_DUX + lane] = 0.0; }
-            if (lane < CF_NX) { rk[R_PI + lane] = 0.0; rk[R_DPI + lane] = 0.0; }
-            if (lane < 2 * CF_NU) { rk[R_DLAM + lane] = 0.0; rk[R_DT + lane] = 0.0; }
-        }
-    }
-
-    // UPDATE_VAR_QP (x_core_qp_ipm_aux.c:220-325) fused with OCP_QP_RES_COMPUTE +
-    // _INF_NORM (x_ocp_qp_res.c:334-470,602-637): one forward pass over the stages.  `a_raw` is the step length of the
-    // direction to apply; the very first pass runs with 0 on the zeroed directions of init_var (ux + 0*0 is exact), so
-    // there is a single copy of this code.  Written branch-free: every lane computes (with clamped indices), only
-    // the stores and the norm contributions are predicated.
-    CF_MEM void update_and_residuals(const double a_raw)
+    // One BACKWARD sweep that does, per stage, everything the reference spreads over three passes:
+    //   UPDATE_VAR_QP            x_core_qp_ipm_aux.c:220-325   (variables += step length * direction, clipping)
+    //   OCP_QP_RES_COMPUTE + _INF_NORM   x_ocp_qp_res.c:334-470,602-637   (residuals of the new iterate, norms, mu)
+    //   OCP_QP_FACT_SOLVE_KKT_STEP, backward part   x_ocp_qp_kkt.c:401-762   (Riccati factorisation for the next direction)
+    // The residuals of a stage are local (they couple stage k only to ux_{k+1} and pi_{k-1}, pi_k), so they can be
+    // evaluated in the order the factorisation runs; the factorisation of the final iterate is wasted (1 of ~7 sweeps)
+    // in exchange for one sweep less per interior-point iteration.  `a_raw` is the step length of the direction to
+    // apply; the first pass applies 0 to the zeroed directions of the initialisation.
+    //
+    // Factorisation: HPIPM's classical Riccati recursion (square_root_alg = 0, x_ocp_qp_kkt.c:573-740) instead of the
+    // square-root variant the reference selects (:445-528): only the 4 input columns of each stage block are
+    // Cholesky-factorised, the state block is kept as the symmetric cost-to-go Hessian P_k.  Same arithmetic cost, but
+    // 4 instead of 17 strictly sequential pivot steps per stage and every matrix product is a tensor-core tile product;
+    // on this OCP the two recursions agree to 1e-14 (oracle/cfnmpc_oracle.c: cfo_set_classical_riccati,
+    // tests/test_oracle_golden.py).  Per stage k < N:
+    //   W   = [B';A';res_b']_k P_{k+1}                      GEMM_NT :621   (row 17: Pb_k = P res_b, then += p_{k+1}')
+    //   S   = [H_k + Gamma ; (res_g + gamma)'] + W [B';A']'  SYRK_LN_MN :652
+    //   L   = chol of the 4 input columns of S               POTRF_L_MN(nv+1, nu) :653
+    //   P_k = S_xx - Ls Ls',  p_k = s_x - Ls l_u             SYRK -1 :655
+    // Stored per stage: LU (18 x 4 factor columns, inverse pivots on the diagonal), the packed lower triangle of P_k, and
+    // the gradient parts l_u | p_k in R_DUX of the stage record.
+    CF_MEM void residual_factorize(const double a_raw)
     {
         double a = a_raw;
         if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
         double ng = 0, nb = 0, nd = 0, nm = 0, mus = 0;
-        double *UXS = sm + CF_SM_V0, *PIS = sm + CF_SM_V1;
+        double *PS = sm + CF_SM_P;                 // P_{k+1}, full symmetric 13 x 13, stride 20
+        double *PV = sm + CF_SM_V0;                // p_{k+1}
+        double *UXS = sm + CF_SM_V1, *PIS = sm + CF_SM_V2;   // residual part: ux_k, pi_k broadcast
+        double *G = sm + CF_SM_V1, *HD = sm + CF_SM_V2;      // factor part: gradient row / Hessian diagonal
         pass_begin();
-        fetch(0, 0, 0, B_LU);
+        fetch(N & 1, N, 0, B_M);
         const bool ul = lane < CF_NU, vl = lane < CF_NV;
         const bool xl = lane >= CF_NU && vl;
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
-        double pi_prev = 0.0;            // lanes 4..16: pi_{k-1}
-        double sb_prev = 0.0, b_prev = 0.0;  // lanes 4..16: ([A B] ux)_{k-1} and b_{k-1}; res_b_{k-1} is finished at stage k
+        // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
+        const int fg = lane >> 2, fq = lane & 3;
+        const int rl = lane < CF_MROWS ? lane : 17;
+        double ux_next = 0.0;   // lanes 4..16: x-part of ux_{k+1} (new iterate)
+        double pi_k = 0.0;      // lanes 4..16: pi_k (new iterate), read from the record of stage k+1
         CF_NOUNROLL
-        for (int k = 0; k <= N; k++) {
+        for (int k = N; k >= 0; k--) {
             const int bf = k & 1;
             const bool kl = k < N;
-            cf_syncwarp();  // previous stage's reads of UXS/PIS and of buffer bf^1 are complete
-            if (kl) fetch(bf ^ 1, k + 1, 0, k + 1 < N ? B_LU : CF_REC);
             wait(bf);
-            const double *VS = buf(bf);   // block k from offset 0: record fields at their own offsets, M at B_M
+            cf_syncwarp();  // every lane is done with buffer bf^1 (incl. the W block of stage k+1), PS/PV are complete
+            if (k > 0) fetch(bf ^ 1, k - 1, 0, B_RD);
+            double *VS = buf(bf);   // block k from offset 0
             double *rk = rec(k);
+            // ---------------- update + residuals of stage k
             const double uxc = vl ? VS[R_UX + lv] + a * VS[R_DUX + lv] : 0.0;
             if (vl) rk[R_UX + lane] = uxc;
-            {   // res_b_{k-1} = (b - x+) + [A B] ux, stored as row 17 of M_{k-1} (ROWIN of x_ocp_qp_kkt.c:490)
-                const double rb = (b_prev - uxc) + sb_prev;
-                if (k > 0 && xl) { nb = fmax(nb, fabs(rb)); blk(k - 1)[B_M + ci * CF_MROWS + 17] = rb; }
-            }
-            const double pik = (kl && xl) ? VS[R_PI + ci] + a * VS[R_DPI + ci] : 0.0;
-            if (kl && xl) rk[R_PI + ci] = pik;
-            double rg = ((k == N) ? HN : Hs) * uxc + VS[R_RQ + lv] - pi_prev;
+            const double pim = (k > 0 && xl) ? VS[R_PI + ci] + a * VS[R_DPI + ci] : 0.0;   // pi_{k-1}
+            if (k > 0 && xl) rk[R_PI + ci] = pim;
+            double rg = ((k == N) ? HN : Hs) * uxc + VS[R_RQ + lv] - pim;
+            double Gam = 0.0, gam = 0.0;
             {   // bounds of input l4 (lanes >= 4 compute duplicates that are never stored nor counted)
                 double ll = VS[R_LAM + l4] + a * VS[R_DLAM + l4], lu = VS[R_LAM + 4 + l4] + a * VS[R_DLAM + 4 + l4];
                 double tl = VS[R_T + l4] + a * VS[R_DT + l4], tu = VS[R_T + 4 + l4] + a * VS[R_DT + 4 + l4];
@@ -391,14 +411,17 @@ struct CfWarp
                     mus += rml + rmu;
                     nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
                     nm = fmax(nm, fmax(fabs(rml), fabs(rmu)));
+                    // Gamma, gamma of the predictor system (x_core_qp_ipm_aux.c:38-111)
+                    const double til = cf_rcp(tl), tiu = cf_rcp(tu);
+                    Gam = til * ll + tiu * lu;
+                    gam = til * ((rml - CF_TAU_MIN) - ll * rdl) - tiu * ((rmu - CF_TAU_MIN) - lu * rdu);
                 }
             }
-            double sbk = 0.0;
             if (kl) {   // warp-uniform
                 if (vl) UXS[lane] = uxc;
-                if (xl) PIS[ci] = pik;
+                if (xl) PIS[ci] = pi_k;
                 cf_syncwarp();
-                const double *Mk = VS + B_M;
+                double *Mk = VS + B_M;
                 {   // res_g += [B';A'] pi_k   (row layout: own elements stride 18)
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
@@ -410,7 +433,7 @@ struct CfWarp
                     s0 += Mk[12 * CF_MROWS + lv] * PIS[12];
                     rg += s0 + s1;
                 }
-                {   // [A B] ux   (column layout: contiguous)
+                {   // res_b_k = (b_k - x_{k+1}) + [A B] ux_k   (column layout: contiguous; b_k is row 17 of the column)
                     const double *Mc = Mk + ci * CF_MROWS;
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
@@ -419,14 +442,180 @@ struct CfWarp
                         s0 += m2.x * u2.x;
                         s1 += m2.y * u2.y;
                     }
-                    s0 += Mc[16] * UXS[16];
-                    sbk = xl ? s0 + s1 : 0.0;
+                    const cf_d2 m2 = cf_ld2(Mc + 16);
+                    s0 += m2.x * UXS[16];
+                    const double rb = (m2.y - ux_next) + (s0 + s1);
+                    cf_syncwarp();   // every lane has read its column: row 17 of the staged block becomes res_b (ROWIN :490)
+                    if (xl) {
+                        nb = fmax(nb, fabs(rb));
+                        rk[R_RESB + ci] = rb;
+                        Mk[ci * CF_MROWS + 17] = rb;
+                    }
                 }
             }
             if (vl) { rk[R_RESG + lane] = rg; ng = fmax(ng, fabs(rg)); }
-            pi_prev = pik;
-            sb_prev = sbk;
-            b_prev = (kl && xl) ? VS[R_B + ci] : 0.0;
+            ux_next = uxc;
+            pi_k = pim;
+            // ---------------- factorisation of stage k
+            if (!kl) {
+                // terminal stage: no dynamics. P_N = diag(H_N) + reg, p_N = res_g_N; dummy inputs decoupled.
+                double *PXN = blk(N > 0 ? N - 1 : 0) + B_PX;   // P_N belongs to the block of stage N-1
+                for (int i = lane; i < 13 * CF_ALST; i += 32) PS[i] = 0.0;
+                for (int i = lane; i < CF_LX; i += 32) PXN[i] = 0.0;
+                cf_syncwarp();
+                const double hN = HN + CF_REG_PRIM;
+                if (xl) {
+                    PS[ci * CF_ALST + ci] = hN;
+                    PV[ci] = rg;
+                    PXN[cf_tri(ci) + ci] = hN;
+                    rk[R_DUX + lane] = rg;   // p_N for the forward sweep
+                }
+                continue;
+            }
+            const double g = vl ? rg + gam : 0.0, hd = Hs + CF_REG_PRIM + Gam;
+            cf_syncwarp();  // row 17 of M_k is complete
+            const double *Mk = VS + B_M;
+            double *WS = VS;   // W rows 18 x 16 (stride 20) overlay the staged block once M is in registers
+            // ---- W(18x13) = M(18x13) * P(13x13): row tiles t (rows 8t+fg), column tiles 0..1, K padded to 16
+            double am[3][4];     // am[t][kk] = M[8t+fg][4kk+fq]: A fragment here, B fragment (M') of the second product
+            double wt[3][2][2];
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) { wt[t][0][0] = wt[t][0][1] = wt[t][1][0] = wt[t][1][1] = 0.0; }
+            CF_UNROLL
+            for (int kk = 0; kk < 4; kk++) {
+                const int kc = 4 * kk + fq;
+                const bool kv = kc < CF_NX;
+                const double *Pk = PS + (kv ? kc : 0) * CF_ALST;
+                const double b0 = kv ? Pk[fg] : 0.0;                          // P[kc][fg]
+                const double b1 = (kv && fg < CF_NX - 8) ? Pk[8 + fg] : 0.0;  // P[kc][8+fg]
+                CF_UNROLL
+                for (int t = 0; t < 3; t++) {
+                    const int r = 8 * t + fg;
+                    am[t][kk] = (kv && r < CF_MROWS) ? Mk[kc * CF_MROWS + r] : 0.0;
+                    cf_dmma(wt[t][0][0], wt[t][0][1], am[t][kk], b0);
+                    cf_dmma(wt[t][1][0], wt[t][1][1], am[t][kk], b1);
+                }
+            }
+            // row 17 (tile 2, fg == 1): Pb_k = P res_b (ROWEX :622), then + p_{k+1}' (GEAD :623)
+            if (fg == 1) {
+                double *pb = rk + R_PB;
+                CF_UNROLL
+                for (int tp = 0; tp < 2; tp++)
+                    CF_UNROLL
+                    for (int e = 0; e < 2; e++) {
+                        const int c = 8 * tp + 2 * fq + e;
+                        if (c < CF_NX) { pb[c] = wt[2][tp][e]; wt[2][tp][e] += PV[c]; }
+                    }
+            }
+            cf_syncwarp();  // every lane holds its M fragments: the staged block may be overwritten by W
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                const int r = 8 * t + fg;
+                if (r < CF_MROWS) {
+                    cf_st2(WS + r * CF_ALST + 2 * fq, wt[t][0][0], wt[t][0][1]);
+                    cf_st2(WS + r * CF_ALST + 8 + 2 * fq, wt[t][1][0], wt[t][1][1]);
+                }
+            }
+            if (lane < CF_MROWS) { G[lane] = g; HD[lane] = hd; }
+            cf_syncwarp();
+            // ---- S = D + W * M': A fragments from W, B fragments are the M fragments already in registers
+            double wf[3][4];
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                const int r = 8 * t + fg;
+                CF_UNROLL
+                for (int kk = 0; kk < 4; kk++) wf[t][kk] = (r < CF_MROWS) ? WS[r * CF_ALST + 4 * kk + fq] : 0.0;
+            }
+            double sx[3][3][2];  // lower tiles (t, tp <= t): S[8t+fg][8tp+2fq+{0,1}]
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                CF_UNROLL
+                for (int tp = 0; tp <= t; tp++) {
+                    double s0 = 0.0, s1 = 0.0;
+                    CF_UNROLL
+                    for (int kk = 0; kk < 4; kk++) cf_dmma(s0, s1, wf[t][kk], am[tp][kk]);
+                    const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
+                    if (r == 17) { s0 += G[c0 < 17 ? c0 : 0]; s1 += G[c0 + 1 < 17 ? c0 + 1 : 0]; }
+                    if (r == c0) s0 += HD[r];
+                    if (r == c0 + 1) s1 += HD[r];
+                    sx[t][tp][0] = s0; sx[t][tp][1] = s1;
+                }
+            }
+            cf_syncwarp();  // every lane has its W fragments: WS is reused for the 18 x 4 input-column block
+            double *LUs = WS;
+            if (fq < 2) {
+                CF_UNROLL
+                for (int t = 0; t < 3; t++) {
+                    const int r = 8 * t + fg;
+                    if (r < CF_MROWS) cf_st2(LUs + r * 4 + 2 * fq, sx[t][0][0], sx[t][0][1]);
+                }
+            }
+            cf_syncwarp();
+            // ---- POTRF_L_MN(nv+1, nu): the 4 input columns, one per step, lane = row; non-positive pivot -> 0
+            // (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
+            {
+                const cf_d2 o01 = cf_ld2(LUs + rl * 4), o23 = cf_ld2(LUs + rl * 4 + 2);
+                double o[CF_NU] = {o01.x, o01.y, o23.x, o23.y}, og[CF_NU];
+                CF_UNROLL
+                for (int j = 0; j < CF_NU; j++) {
+                    double v = o[j];
+                    CF_UNROLL
+                    for (int c = 0; c < j; c++) v -= o[c] * LUs[j * 4 + c];
+                    const double piv = cf_shfl(v, j);
+                    double dj, inv;
+                    cf_sqrt_rsqrt(piv, dj, inv);
+                    if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; }
+                    o[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
+                    LUs[rl * 4 + j] = o[j];
+                    og[j] = (rl == j) ? inv : o[j];
+                    cf_syncwarp();
+                }
+                // factor columns to global memory (LU block of stage k), inverse pivots on the diagonal; the gradient row
+                // l_u goes where the forward sweep picks it up
+                double *LFk = blk(k) + B_LU;
+                if (lane < CF_MROWS) {
+                    cf_st2(LFk + lane * 4, og[0], og[1]);
+                    cf_st2(LFk + lane * 4 + 2, og[2], og[3]);
+                }
+                if (lane == 17) {
+                    cf_st2(rk + R_DUX, o[0], o[1]);
+                    cf_st2(rk + R_DUX + 2, o[2], o[3]);
+                }
+            }
+            // ---- Schur complement on the tensor cores (K = 4 = the input columns): S -= Ls Ls'
+            double la[3];
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                const int r = 8 * t + fg;
+                la[t] = (r < CF_MROWS) ? LUs[r * 4 + fq] : 0.0;
+            }
+            cf_syncwarp();  // all reads of PS/PV (first product) are long complete; they are rewritten below
+            {
+                double *LFk = blk(k > 0 ? k - 1 : 0) + B_PX;   // P_k goes to the block of stage k-1 (no consumer for k = 0)
+                CF_UNROLL
+                for (int t = 0; t < 3; t++) {
+                    CF_UNROLL
+                    for (int tp = 0; tp <= t; tp++) {
+                        cf_dmma(sx[t][tp][0], sx[t][tp][1], -la[t], la[tp]);
+                        const int r = 8 * t + fg;
+                        CF_UNROLL
+                        for (int e = 0; e < 2; e++) {
+                            const int c = 8 * tp + 2 * fq + e;
+                            const double val = sx[t][tp][e];
+                            if (c >= CF_NU && c < CF_NV) {
+                                const int jx = c - CF_NU;
+                                if (r == 17) { PV[jx] = val; rk[R_DUX + c] = val; }   // p_k
+                                else if (r >= c && r < CF_NV) {                             // P_k, lower part + mirror
+                                    const int ix = r - CF_NU;
+                                    PS[ix * CF_ALST + jx] = val;
+                                    PS[jx * CF_ALST + ix] = val;
+                                    if (k > 0) LFk[cf_tri(ix) + jx] = val;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
         }
         nrm[0] = cf_warp_max(ng); nrm[1] = cf_warp_max(nb); nrm[2] = cf_warp_max(nd); nrm[3] = cf_warp_max(nm);
         mu = cf_warp_sum(mus) * (1.0 / (double) (2 * CF_NU * N));
@@ -459,211 +648,6 @@ struct CfWarp
         gam = gl - gu;
     }
 
-    // OCP_QP_FACT_SOLVE_KKT_STEP, backward factorisation.  HPIPM's classical Riccati recursion
-    // (square_root_alg = 0, x_ocp_qp_kkt.c:573-740) instead of the square-root variant the reference selects
-    // (:445-528): only the 4 input columns of each stage block are Cholesky-factorised, the state block is kept as the
-    // symmetric cost-to-go Hessian P_k.  Same arithmetic cost, but 4 instead of 17 strictly sequential pivot steps per
-    // stage and every matrix product is a tensor-core tile product; on this OCP the two recursions agree to 1e-14
-    // (oracle/cfnmpc_oracle.c: cfo_set_classical_riccati, tests/test_oracle_golden.py).  Per stage k < N:
-    //   W   = [B';A';res_b']_k P_{k+1}                      GEMM_NT :621   (row 17: Pb_k = P res_b, then += p_{k+1}')
-    //   S   = [H_k + Gamma ; (res_g + gamma)'] + W [B';A']'  SYRK_LN_MN :652
-    //   L   = chol of the 4 input columns of S               POTRF_L_MN(nv+1, nu) :653
-    //   P_k = S_xx - Ls Ls',  p_k = s_x - Ls l_u             SYRK -1 :655
-    // Stored per stage: LU (18 x 4 factor columns, inverse pivots on the diagonal), the packed lower triangle of P_k, and
-    // the gradient parts l_u | p_k in R_DUX of the stage record.
-    CF_MEM void factorize()
-    {
-        double *PS = sm + CF_SM_W;                 // P_{k+1}, full symmetric 13 x 13, stride 20
-        double *WS = sm + CF_SM_W + 13 * CF_ALST;  // W rows 18 x 16 (stride 20); later the 18 x 4 input-column block
-        double *PV = sm + CF_SM_V0, *G = sm + CF_SM_V1, *HD = sm + CF_SM_V2;
-        pass_begin();
-        if (N > 0) fetch_to(sm + CF_SM_MS0, 0, N - 1, B_M, CF_MSZ);
-        // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
-        const int fg = lane >> 2, fq = lane & 3;
-        const int rl = lane < CF_MROWS ? lane : 17;
-        // ---- terminal stage: no dynamics. P_N = diag(H_N) + reg, p_N = res_g_N; dummy inputs decoupled.
-        {
-            double *PXN = blk(N > 0 ? N - 1 : 0) + B_PX;   // P_N | p_N belong to the block of stage N-1
-            for (int i = lane; i < 13 * CF_ALST; i += 32) PS[i] = 0.0;
-            for (int i = lane; i < CF_LX; i += 32) PXN[i] = 0.0;
-            cf_syncwarp();
-            const double hN = HN + CF_REG_PRIM;
-            if (lane >= CF_NU && lane < CF_NV) {
-                const int i = lane - CF_NU;
-                const double gN = rec(N)[R_RESG + lane];
-                PS[i * CF_ALST + i] = hN;
-                PV[i] = gN;
-                PXN[cf_tri(i) + i] = hN;
-                rec(N)[R_DUX + lane] = gN;   // p_N for the forward sweep
-            }
-        }
-        // gradient row and diagonal of the stage Hessian are computed one stage ahead (software pipelining:
-        // the global loads behind them complete during the previous stage's tile products)
-        double g_nx = 0.0, hd_nx = 0.0;
-        if (N > 0) {
-            double Gam = 0.0, gam = 0.0;
-            if (lane < CF_NU) bound_terms(N - 1, rec(N - 1) + R_DLAM, 0, 0.0, Gam, gam);
-            g_nx = (lane < CF_NV) ? rec(N - 1)[R_RESG + lane] + gam : 0.0;
-            hd_nx = Hs + CF_REG_PRIM + Gam;
-        }
-        CF_NOUNROLL
-        for (int k = N - 1; k >= 0; k--) {
-            const double g = g_nx, hd = hd_nx;
-            if (k > 0) {
-                double Gam = 0.0, gam = 0.0;
-                if (lane < CF_NU) bound_terms(k - 1, rec(k - 1) + R_DLAM, 0, 0.0, Gam, gam);
-                g_nx = (lane < CF_NV) ? rec(k - 1)[R_RESG + lane] + gam : 0.0;
-                hd_nx = Hs + CF_REG_PRIM + Gam;
-            }
-            const int bf = (N - 1 - k) & 1;
-            wait(bf);
-            cf_syncwarp();  // every lane is done with buffer bf^1, PS/PV of stage k+1 are complete
-            if (k > 0) fetch_to(sm + ((bf ^ 1) ? CF_SM_MS1 : CF_SM_MS0), bf ^ 1, k - 1, B_M, CF_MSZ);
-            const double *Mk = sm + (bf ? CF_SM_MS1 : CF_SM_MS0);
-            // ---- W(18x13) = M(18x13) * P(13x13): row tiles t (rows 8t+fg), column tiles 0..1, K padded to 16
-            double a[3][4];     // a[t][kk] = M[8t+fg][4kk+fq]: A fragment here, B fragment (M') of the second product
-            double wt[3][2][2];
-            CF_UNROLL
-            for (int t = 0; t < 3; t++) { wt[t][0][0] = wt[t][0][1] = wt[t][1][0] = wt[t][1][1] = 0.0; }
-            CF_UNROLL
-            for (int kk = 0; kk < 4; kk++) {
-                const int kc = 4 * kk + fq;
-                const bool kv = kc < CF_NX;
-                const double *Pk = PS + (kv ? kc : 0) * CF_ALST;
-                const double b0 = kv ? Pk[fg] : 0.0;                          // P[kc][fg]
-                const double b1 = (kv && fg < CF_NX - 8) ? Pk[8 + fg] : 0.0;  // P[kc][8+fg]
-                CF_UNROLL
-                for (int t = 0; t < 3; t++) {
-                    const int r = 8 * t + fg;
-                    a[t][kk] = (kv && r < CF_MROWS) ? Mk[kc * CF_MROWS + r] : 0.0;
-                    cf_dmma(wt[t][0][0], wt[t][0][1], a[t][kk], b0);
-                    cf_dmma(wt[t][1][0], wt[t][1][1], a[t][kk], b1);
-                }
-            }
-            // row 17 (tile 2, fg == 1): Pb_k = P res_b (ROWEX :622), then + p_{k+1}' (GEAD :623)
-            if (fg == 1) {
-                double *pb = rec(k) + R_PB;
-                CF_UNROLL
-                for (int tp = 0; tp < 2; tp++)
-                    CF_UNROLL
-                    for (int e = 0; e < 2; e++) {
-                        const int c = 8 * tp + 2 * fq + e;
-                        if (c < CF_NX) { pb[c] = wt[2][tp][e]; wt[2][tp][e] += PV[c]; }
-                    }
-            }
-            CF_UNROLL
-            for (int t = 0; t < 3; t++) {
-                const int r = 8 * t + fg;
-                if (r < CF_MROWS) {
-                    cf_st2(WS + r * CF_ALST + 2 * fq, wt[t][0][0], wt[t][0][1]);
-                    cf_st2(WS + r * CF_ALST + 8 + 2 * fq, wt[t][1][0], wt[t][1][1]);
-                }
-            }
-            G[lane] = g;
-            HD[lane] = hd;
-            cf_syncwarp();
-            // ---- S = D + W * M': A fragments from W, B fragments are the M fragments already in registers
-            double wf[3][4];
-            CF_UNROLL
-            for (int t = 0; t < 3; t++) {
-                const int r = 8 * t + fg;
-                CF_UNROLL
-                for (int kk = 0; kk < 4; kk++) wf[t][kk] = (r < CF_MROWS) ? WS[r * CF_ALST + 4 * kk + fq] : 0.0;
-            }
-            double s[3][3][2];  // lower tiles (t, tp <= t): S[8t+fg][8tp+2fq+{0,1}]
-            CF_UNROLL
-            for (int t = 0; t < 3; t++) {
-                CF_UNROLL
-                for (int tp = 0; tp <= t; tp++) {
-                    double s0 = 0.0, s1 = 0.0;
-                    CF_UNROLL
-                    for (int kk = 0; kk < 4; kk++) cf_dmma(s0, s1, wf[t][kk], a[tp][kk]);
-                    const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
-                    if (r == 17) { s0 += G[c0 < 17 ? c0 : 0]; s1 += G[c0 + 1 < 17 ? c0 + 1 : 0]; }
-                    if (r == c0) s0 += HD[r];
-                    if (r == c0 + 1) s1 += HD[r];
-                    s[t][tp][0] = s0; s[t][tp][1] = s1;
-                }
-            }
-            cf_syncwarp();  // every lane has its W fragments: WS is reused for the 18 x 4 input-column block
-            double *LUs = WS;
-            if (fq < 2) {
-                CF_UNROLL
-                for (int t = 0; t < 3; t++) {
-                    const int r = 8 * t + fg;
-                    if (r < CF_MROWS) cf_st2(LUs + r * 4 + 2 * fq, s[t][0][0], s[t][0][1]);
-                }
-            }
-            cf_syncwarp();
-            // ---- POTRF_L_MN(nv+1, nu): the 4 input columns, one per step, lane = row; non-positive pivot -> 0
-            // (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
-            {
-                const cf_d2 o01 = cf_ld2(LUs + rl * 4), o23 = cf_ld2(LUs + rl * 4 + 2);
-                double o[CF_NU] = {o01.x, o01.y, o23.x, o23.y}, og[CF_NU];
-                CF_UNROLL
-                for (int j = 0; j < CF_NU; j++) {
-                    double v = o[j];
-                    CF_UNROLL
-                    for (int c = 0; c < j; c++) v -= o[c] * LUs[j * 4 + c];
-                    const double piv = cf_shfl(v, j);
-                    double dj, inv;
-                    cf_sqrt_rsqrt(piv, dj, inv);
-                    if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; }
-                    o[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
-                    LUs[rl * 4 + j] = o[j];
-                    og[j] = (rl == j) ? inv : o[j];
-                    cf_syncwarp();
-                }
-                // factor columns to global memory (LU block of stage k), inverse pivots on the diagonal; the gradient row
-                // l_u goes where the forward sweep picks it up
-                double *LFk = blk(k) + B_LU;
-                if (lane < CF_MROWS) {
-                    cf_st2(LFk + lane * 4, og[0], og[1]);
-                    cf_st2(LFk + lane * 4 + 2, og[2], og[3]);
-                }
-                if (lane == 17) {
-                    cf_st2(rec(k) + R_DUX, o[0], o[1]);
-                    cf_st2(rec(k) + R_DUX + 2, o[2], o[3]);
-                }
-            }
-            // ---- Schur complement on the tensor cores (K = 4 = the input columns): S -= Ls Ls'
-            double la[3];
-            CF_UNROLL
-            for (int t = 0; t < 3; t++) {
-                const int r = 8 * t + fg;
-                la[t] = (r < CF_MROWS) ? LUs[r * 4 + fq] : 0.0;
-            }
-            cf_syncwarp();  // all reads of PS/PV (first product) are long complete; they are rewritten below
-            {
-                double *LFk = blk(k > 0 ? k - 1 : 0) + B_PX;   // P_k | p_k go to the block of stage k-1 (no consumer for k = 0)
-                CF_UNROLL
-                for (int t = 0; t < 3; t++) {
-                    CF_UNROLL
-                    for (int tp = 0; tp <= t; tp++) {
-                        cf_dmma(s[t][tp][0], s[t][tp][1], -la[t], la[tp]);
-                        const int r = 8 * t + fg;
-                        CF_UNROLL
-                        for (int e = 0; e < 2; e++) {
-                            const int c = 8 * tp + 2 * fq + e;
-                            const double val = s[t][tp][e];
-                            if (c >= CF_NU && c < CF_NV) {
-                                const int jx = c - CF_NU;
-                                if (r == 17) { PV[jx] = val; rec(k)[R_DUX + c] = val; }   // p_k
-                                else if (r >= c && r < CF_NV) {                             // P_k, lower part + mirror
-                                    const int ix = r - CF_NU;
-                                    PS[ix * CF_ALST + jx] = val;
-                                    PS[jx * CF_ALST + ix] = val;
-                                    if (k > 0) LFk[cf_tri(ix) + jx] = val;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        cf_syncwarp();
-    }
-
     // Forward substitution shared by the factorise-and-solve (:536-570) and the rhs-only solve (:1250-1290): the
     // backward sweep before it (factorize or backward_rhs) left l_u of stage k and p_k in R_DUX of stage k's record and
     // the complementarity rhs in R_RESM.  Computes dux, dpi, then dlam, dt (:741-758, x_core_qp_ipm_aux.c:117-142), the
@@ -681,7 +665,7 @@ struct CfWarp
         const int VO = R_LAM, VN = CF_SB - R_LAM;   // staged part of the stage block: [R_LAM, end)
         pass_begin();
         if (N > 0) fetch(0, 0, VO, VN);
-        XS[lane] = 0.0; PS[lane] = 0.0;
+        if (lane < 20) { XS[lane] = 0.0; PS[lane] = 0.0; }
         const bool ul = lane < CF_NU, vl = lane < CF_NV;
         const bool xl = lane >= CF_NU && vl;
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
@@ -761,11 +745,10 @@ struct CfWarp
                     s0 += m2.x * d2.x;
                     s1 += m2.y * d2.y;
                 }
-                const cf_d2 m2 = cf_ld2(Mc + 16);  // [M[16][c], res_b[c]]
-                s0 += m2.x * DS[16];
-                const double sacc = s0 + s1;
-                dxn = xl ? sacc + m2.y : 0.0;
-                lb = fmax(lb, xl ? fabs((m2.y - dxn) + sacc) : 0.0);
+                s0 += Mc[16] * DS[16];
+                const double sacc = s0 + s1, rbk = VS[R_RESB + ci];
+                dxn = xl ? sacc + rbk : 0.0;
+                lb = fmax(lb, xl ? fabs((rbk - dxn) + sacc) : 0.0);
                 if (xl) XS[ci] = dxn;
             }
             cf_syncwarp();
@@ -781,7 +764,7 @@ struct CfWarp
                     else z0 += pc * XS[c];
                 }
                 dpik = xl ? z0 + z1 : 0.0;
-                if (xl) { rk[R_DPI + ci] = dpik; PS[ci] = dpik; }
+                if (xl) { rec(k + 1)[R_DPI + ci] = dpik; PS[ci] = dpik; }   // the record of stage k+1 holds pi_k
             }
             cf_syncwarp();
             // stationarity residual, part 2: + [B';A'] dpi_k   (row layout)
@@ -818,7 +801,7 @@ struct CfWarp
     CF_MEM void backward_rhs(int rm_mode, double sigma_mu)
     {
         double *TS = sm + CF_SM_V0;
-        const int VO = R_DLAM, VN = B_PX - R_DLAM;   // staged part of the stage block: [R_DLAM, B_PX)
+        const int VO = R_BKP, VN = B_PX - R_BKP;   // staged part of the stage block: [R_BKP, B_PX)
         pass_begin();
         if (N > 0) fetch(0, N - 1, VO, VN);
         // terminal stage: rhs = res_g_N, nothing to eliminate (dummy inputs are zero)
@@ -827,7 +810,6 @@ struct CfWarp
             pn = rec(N)[R_RESG + lane];
             rec(N)[R_DUX + lane] = pn;
         }
-        if (lane == 13) TS[13] = 0.0;
         CF_NOUNROLL
         for (int k = N - 1; k >= 0; k--) {
             const int bf = (N - 1 - k) & 1;
@@ -908,28 +890,25 @@ struct CfWarp
 // the whole warp program stays small enough for the instruction caches.  Returns HPIPM status.
 CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
 {
-    w.init_var();
     w.alpha = 1.0;
     w.flags = 0;
     cf_syncwarp();
     const int itmax = w.PG->max_ipm_iter < CF_ITER_MAX ? w.PG->max_ipm_iter : CF_ITER_MAX;
-    enum { ST_RES, ST_FACT, ST_FWD, ST_BWD };
-    int st = ST_RES, kk = 0, brm = 1;
+    enum { ST_RF, ST_FWD, ST_BWD };
+    int st = ST_RF, kk = 0, brm = 1;
     bool first = true, predictor = true;
     double sigma_mu = 0.0, mu_aff0 = 0.0;
     for (;;) {
-        if (st == ST_RES) {
-            w.update_and_residuals(first ? 0.0 : w.alpha);
+        if (st == ST_RF) {
+            // variables += alpha * direction, residuals of the new iterate, and (speculatively) the factorisation of the
+            // next affine system, OCP_QP_IPM_DELTA_STEP (:1943-2405)
+            w.residual_factorize(first ? 0.0 : w.alpha);
             if (first) { first = false; w.alpha = 1.0; }
             else kk++;
             const bool go = kk < itmax && w.alpha > CF_ALPHA_MIN &&
                             (w.nrm[0] > CF_RES_G_MAX || w.nrm[1] > CF_RES_B_MAX || w.nrm[2] > CF_RES_D_MAX ||
                              fabs(w.nrm[3] - CF_TAU_MIN) > CF_RES_M_MAX);
             if (!go) break;
-            st = ST_FACT;
-        } else if (st == ST_FACT) {
-            // ---- OCP_QP_IPM_DELTA_STEP (:1943-2405): affine (predictor) direction
-            w.factorize();
             predictor = true;
             st = ST_FWD;
         } else if (st == ST_FWD) {
@@ -953,7 +932,7 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
                 if (recenter) { brm = 2; st = ST_BWD; }
                 else {
                     if (!w.lin_res_ok_corr()) w.flags |= CF_FLAG_LIN_RES_CORR;
-                    st = ST_RES;
+                    st = ST_RF;
                 }
             }
         } else {

@@ -616,7 +616,7 @@ extern "C" int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_dou
     if (!h) return fail(CFNMPC_EINVAL, "null handle");
     CfScratchLayout s = cf_scratch_layout(h->N);
     if (offsets12) {
-        long long v[12] = {s.total, CF_SB, B_M, B_LU, B_PX, R_UX, R_PI, R_RQ, R_B, R_RESG, R_DUX, R_D};
+        long long v[12] = {s.total, CF_SB, B_M, B_LU, B_PX, R_UX, R_PI, R_RQ, -1, R_RESG, R_DUX, R_D};
         memcpy(offsets12, v, sizeof v);
     }
     if (n_doubles) *n_doubles = (size_t) s.total;

@@ -121,7 +121,7 @@ def test_qp_data_intermediates(port):
         ref_BAbt[0, 4:, :] = 0.0                                       # A0 rows dropped by the x0 elimination
         assert np.abs(BAbt - ref_BAbt).max() <= 1e-11 * np.abs(ref_BAbt).max()
         rec = blocks
-        b = rec[:N, off["r_b"]: off["r_b"] + 13]
+        b = M[:, :, 17]                                                # row 17 of the stage block holds b_k
         xbar = wi["x0"][0] - wi["x_init"][0, 0]
         ref_b = lin["b"].copy()
         ref_b[0] += lin["BAbt"][0, 4:, :].T @ xbar
@@ -146,7 +146,7 @@ def test_qp_data_intermediates(port):
         ref_ux[N, 4:] = dux[N * 17:]
         ref_ux[0, 4:] = 0.0
         assert np.abs(ux - ref_ux).max() <= 1e-9 * (1 + np.abs(ref_ux).max())
-        pi = rec[:N, off["r_pi"]: off["r_pi"] + 13].ravel()
+        pi = rec[1:N + 1, off["r_pi"]: off["r_pi"] + 13].ravel()         # the record of stage k+1 holds pi_k
         assert np.abs(pi - dpi).max() <= 1e-9 * (1 + np.abs(dpi).max())
 
 
