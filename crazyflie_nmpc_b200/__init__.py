@@ -51,6 +51,7 @@ def lib():
         L.cfnmpc_batch_last_solve_ms.argtypes = [vp, ctypes.POINTER(cd)]
         L.cfnmpc_debug_scratch.argtypes = [vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_longlong)]
         L.cfnmpc_debug_max_ipm_iter.argtypes = [vp, ci]
+        L.cfnmpc_debug_pass_cycles.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
         L.cfnmpc_batch_set_trajectory.argtypes = [vp, vp, ci, ci]
         L.cfnmpc_batch_update_reference.argtypes = [vp]
         L.cfnmpc_batch_commands.argtypes = [vp, ci]
@@ -240,6 +241,13 @@ class BatchSolver:
         _check(lib().cfnmpc_debug_scratch(self._h, ctypes.c_void_p(buf.ctypes.data), n.value, None, None))
         names = ["total", "blk_stride", "b_m", "b_lu", "b_px", "r_ux", "r_pi", "r_rq", "r_b", "r_resg", "r_dux", "r_d"]
         return buf, dict(zip(names, list(offs)))
+
+    def debug_pass_cycles(self, read=True):
+        """Per-pass warp cycles / call counts since the last read (first call enables the counters)."""
+        buf = (ctypes.c_ulonglong * 12)()
+        _check(lib().cfnmpc_debug_pass_cycles(self._h, buf if read else None))
+        names = ["linearize", "residual_factorize", "forward", "backward_rhs", "mu_aff", "update"]
+        return {n: (buf[2 * i], buf[2 * i + 1]) for i, n in enumerate(names)}
 
     def debug_max_ipm_iter(self, n):
         _check(lib().cfnmpc_debug_max_ipm_iter(self._h, int(n)))

@@ -109,7 +109,10 @@ struct CfBatchView
     // optional per-instance overrides of the solver-wide CfParams (null = not given), SET_WEIGHTS / FIXED_U0 of the
     // node with one value set per vehicle: W [B][17], W_e [B][13], lbu/ubu [B][4] (stages 1..N-1), lbu0/ubu0 [B][4]
     const double *W_b, *WN_b, *lbu_b, *ubu_b, *lbu0_b, *ubu0_b;
+    // optional profiling counters (null = off): per-pass warp cycles and call counts, see cfnmpc_debug_pass_cycles
+    unsigned long long *prof;
 };
+enum { CF_PROF_LIN = 0, CF_PROF_RF, CF_PROF_FWD, CF_PROF_BWD, CF_PROF_MUAFF, CF_PROF_UPDATE, CF_PROF_N };
 
 // offsets (in doubles) of the arrays inside one scratch slot; every block that the TMA engine
 // touches (M, LF) starts on a 16-byte boundary
@@ -409,8 +412,8 @@ struct CfWarp
                     rk[R_RESM + lane] = rml - CF_TAU_MIN; rk[R_RESM + 4 + lane] = rmu - CF_TAU_MIN;  // predictor rhs
                     rg += lu - ll;
                     mus += rml + rmu;
-                    nd = fmax(nd, fmax(fabs(rdl), fabs(rdu)));
-                    nm = fmax(nm, fmax(fabs(rml), fabs(rmu)));
+                    cf_amax(nd, rdl); cf_amax(nd, rdu);
+                    cf_amax(nm, rml); cf_amax(nm, rmu);
                     // Gamma, gamma of the predictor system (x_core_qp_ipm_aux.c:38-111)
                     const double til = cf_rcp(tl), tiu = cf_rcp(tu);
                     Gam = til * ll + tiu * lu;
@@ -447,13 +450,13 @@ struct CfWarp
                     const double rb = (m2.y - ux_next) + (s0 + s1);
                     cf_syncwarp();   // every lane has read its column: row 17 of the staged block becomes res_b (ROWIN :490)
                     if (xl) {
-                        nb = fmax(nb, fabs(rb));
+                        cf_amax(nb, rb);
                         rk[R_RESB + ci] = rb;
                         Mk[ci * CF_MROWS + 17] = rb;
                     }
                 }
             }
-            if (vl) { rk[R_RESG + lane] = rg; ng = fmax(ng, fabs(rg)); }
+            if (vl) { rk[R_RESG + lane] = rg; cf_amax(ng, rg); }
             ux_next = uxc;
             pi_k = pim;
             // ---------------- factorisation of stage k
@@ -726,8 +729,8 @@ struct CfWarp
                 c = dn * dlam_u < lu * dd; dn = c ? lu : dn; dd = c ? dlam_u : dd;
                 c = pn_ * dtu < tu * pd_; pn_ = c ? tu : pn_; pd_ = c ? dtu : pd_;
                 // linear residuals of the complementarity / bound rows
-                ld = fmax(ld, fmax(fabs(rdl + dtl - du), fabs(rdu + dtu + du)));
-                lm = fmax(lm, fmax(fabs(rml + ll * dtl + dlam_l * tl), fabs(rmu + lu * dtu + dlam_u * tu)));
+                cf_amax(ld, rdl + dtl - du); cf_amax(ld, rdu + dtu + du);
+                cf_amax(lm, rml + ll * dtl + dlam_l * tl); cf_amax(lm, rmu + lu * dtu + dlam_u * tu);
             }
             // stationarity residual, part 1: H dux + rhs_g - dpi_{k-1} + dlam_ub - dlam_lb
             double rgl = Hs * duxk + VS[R_RESG + lv] - dpi_prev;
@@ -748,7 +751,7 @@ struct CfWarp
                 s0 += Mc[16] * DS[16];
                 const double sacc = s0 + s1, rbk = VS[R_RESB + ci];
                 dxn = xl ? sacc + rbk : 0.0;
-                lb = fmax(lb, xl ? fabs((rbk - dxn) + sacc) : 0.0);
+                cf_amax(lb, xl ? (rbk - dxn) + sacc : 0.0);
                 if (xl) XS[ci] = dxn;
             }
             cf_syncwarp();
@@ -777,7 +780,7 @@ struct CfWarp
                     s1 += Mk[(2 * cp + 1) * CF_MROWS + lv] * p2.y;
                 }
                 s0 += Mk[12 * CF_MROWS + lv] * PS[12];
-                lg = fmax(lg, vl ? fabs(rgl + (s0 + s1)) : 0.0);
+                cf_amax(lg, vl ? rgl + (s0 + s1) : 0.0);
             }
             dpi_prev = dpik;
             dxk = dxn;
@@ -787,7 +790,7 @@ struct CfWarp
             const double duxN = ul ? 0.0 : dxk;
             const double rgl = HN * duxN + rec(N)[R_RESG + lane] - dpi_prev;
             rec(N)[R_DUX + lane] = duxN;
-            lg = fmax(lg, fabs(rgl));
+            cf_amax(lg, rgl);
         }
         lin[0] = cf_warp_max(lg); lin[1] = cf_warp_max(lb); lin[2] = cf_warp_max(ld); lin[3] = cf_warp_max(lm);
         // alpha = min(1, prim, dual) as in x_core_qp_ipm_aux.c:146-216 (running values are negative)
@@ -888,7 +891,14 @@ struct CfWarp
 // machine so that every pass has exactly ONE call site: each pass is inlined once into the
 // kernel (address spaces of all pointers known, warp context in registers) and the code of
 // the whole warp program stays small enough for the instruction caches.  Returns HPIPM status.
-CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
+#if defined(CF_SIMT_EMU)
+#define CF_PROF_BEGIN()
+#define CF_PROF_END(id)
+#else
+#define CF_PROF_BEGIN() const long long cf_t0_ = prof ? clock64() : 0
+#define CF_PROF_END(id) do { if (prof && cf_lane() == 0) { atomicAdd(prof + 2 * (id), (unsigned long long) (clock64() - cf_t0_)); atomicAdd(prof + 2 * (id) + 1, 1ull); } } while (0)
+#endif
+CF_DEV int cf_ipm_solve(CfWarp &w, int &iters, unsigned long long *prof)
 {
     w.alpha = 1.0;
     w.flags = 0;
@@ -902,7 +912,9 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
         if (st == ST_RF) {
             // variables += alpha * direction, residuals of the new iterate, and (speculatively) the factorisation of the
             // next affine system, OCP_QP_IPM_DELTA_STEP (:1943-2405)
+            CF_PROF_BEGIN();
             w.residual_factorize(first ? 0.0 : w.alpha);
+            CF_PROF_END(CF_PROF_RF);
             if (first) { first = false; w.alpha = 1.0; }
             else kk++;
             const bool go = kk < itmax && w.alpha > CF_ALPHA_MIN &&
@@ -912,10 +924,14 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
             predictor = true;
             st = ST_FWD;
         } else if (st == ST_FWD) {
+            CF_PROF_BEGIN();
             w.forward();
+            CF_PROF_END(CF_PROF_FWD);
             if (predictor) {
                 if (!w.lin_res_ok_fact()) w.flags |= CF_FLAG_LIN_RES_FACT;
+                CF_PROF_BEGIN();
                 w.compute_mu_aff();
+                CF_PROF_END(CF_PROF_MUAFF);
                 const double tmp = w.mu_aff / w.mu;
                 w.sigma = tmp * tmp * tmp;
                 sigma_mu = w.sigma * w.mu;
@@ -936,7 +952,9 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters)
                 }
             }
         } else {
+            CF_PROF_BEGIN();
             w.backward_rhs(brm, sigma_mu);
+            CF_PROF_END(CF_PROF_BWD);
             predictor = false;
             st = ST_FWD;
         }
@@ -988,12 +1006,18 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     const double *yrefg = bv.yref + (long) inst * N * CF_NY;
     const double *yref_eg = bv.yref_e + (long) inst * CF_NX;
     double xk_pre = (w.lane < CF_NX) ? xg[w.lane] : 0.0, uk_pre = (w.lane < CF_NU) ? ug[w.lane] : 0.0;
-    CF_NOUNROLL
-    for (int k = 0; k < N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg, xk_pre, uk_pre);
-    w.terminal_gradient(xg, yref_eg);
-    cf_syncwarp();
+    unsigned long long *prof = bv.prof;
+    {
+        CF_PROF_BEGIN();
+        CF_NOUNROLL
+        for (int k = 0; k < N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg, xk_pre, uk_pre);
+        w.terminal_gradient(xg, yref_eg);
+        cf_syncwarp();
+        CF_PROF_END(CF_PROF_LIN);
+    }
     int iters = 0;
-    const int qp_status = cf_ipm_solve(w, iters);
+    const int qp_status = cf_ipm_solve(w, iters, prof);
+    CF_PROF_BEGIN();
     // ocp_nlp_sqp_rti.c:651-674: QP max-iter is not fatal; anything else leaves the iterate untouched
     int status = CF_ACADOS_SUCCESS;
     if (qp_status == 0 || qp_status == 1) {
@@ -1020,4 +1044,5 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     }
     par = w.par;
     cf_syncwarp();
+    CF_PROF_END(CF_PROF_UPDATE);
 }

@@ -173,6 +173,13 @@ CF_DEV double cf_rcp(double x)
     return fma(y, e, y);
 }
 
+// acc = max(acc, |x|) as a compare + select (fmax costs a NaN-aware sequence per call); a NaN in x is ignored, as by fmax
+CF_DEV void cf_amax(double &acc, double x)
+{
+    const double ax = fabs(x);
+    acc = (ax > acc) ? ax : acc;
+}
+
 // butterfly reductions (all lanes get the result)
 CF_DEV double cf_warp_sum(double v)
 {

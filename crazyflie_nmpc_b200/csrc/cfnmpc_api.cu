@@ -14,20 +14,19 @@
 #include "cf_rti_warp.h"
 #include "cf_loop_kernels.h"
 
-#define CF_WARPS_PER_BLOCK 4
 
 // ------------------------------------------------------------------ kernels
 // Persistent warps: each warp owns a scratch slot and pulls instance ids from a global
 // counter until the batch is exhausted (IPM trip counts differ per instance: 4..11).
-// MINB = resident blocks per SM the register allocation is bounded for (blocks of 4 warps).
-template <int MINB>
-__global__ void __launch_bounds__(CF_WARPS_PER_BLOCK * 32, MINB)
-cf_rti_kernel(const __grid_constant__ CfParams P, const __grid_constant__ CfBatchView bv)
+// Launch shape <WPB, MINB>: WPB warps per block (warps never cooperate, the block is only a container), MINB resident
+// blocks per SM the register allocation is bounded for: warps per SM = WPB * MINB, registers <= 65536 / (32 * WPB * MINB).
+template <int WPB>
+__device__ __forceinline__ void cf_rti_kernel_body(const CfParams &P, const CfBatchView &bv)
 {
     extern __shared__ __align__(128) double cf_smem[];
     const int warp = threadIdx.x >> 5;
     double *sm = cf_smem + warp * CF_SM_DOUBLES;
-    double *slot = bv.scratch + (long) (blockIdx.x * CF_WARPS_PER_BLOCK + warp) * bv.scratch_stride;
+    double *slot = bv.scratch + (long) (blockIdx.x * WPB + warp) * bv.scratch_stride;
     cf_warp_init_smem(sm);
     unsigned par = 0;
     for (;;) {
@@ -38,7 +37,12 @@ cf_rti_kernel(const __grid_constant__ CfParams P, const __grid_constant__ CfBatc
         cf_rti_instance(&P, bv, inst, slot, sm, par);
     }
 }
-
+template <int WPB, int MINB>
+__global__ void __launch_bounds__(WPB * 32, MINB)
+cf_rti_kernel(const __grid_constant__ CfParams P, const __grid_constant__ CfBatchView bv)
+{
+    cf_rti_kernel_body<WPB>(P, bv);
+}
 // out[i][0:w] = src[i][stage*w : stage*w + w]   (ocp_nlp_out_get for every instance at once)
 __global__ void cf_gather_stage_kernel(const double *__restrict__ src, double *__restrict__ out, int B, int per_inst, int stage, int w)
 {
@@ -85,9 +89,10 @@ struct cfnmpc_batch
     double *d_setpoint = nullptr, *d_traj = nullptr, *d_euler = nullptr, *d_twist = nullptr;
     int n_traj = 0;
     double uss = 0.0;
+    unsigned long long *d_prof = nullptr;
     double *d_Wb = nullptr, *d_WNb = nullptr, *d_lbub = nullptr, *d_ubub = nullptr, *d_lbu0b = nullptr, *d_ubu0b = nullptr;
     int *d_status = nullptr, *d_qp_iter = nullptr, *d_qp_status = nullptr, *d_flags = nullptr, *d_counter = nullptr;
-    int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 5;
+    int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 4, wpb = 4;
     void (*kernel)(const CfParams, const CfBatchView) = nullptr;
     size_t smem = 0;
     long long launches = 0;
@@ -113,7 +118,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
                     h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter,
                     h->d_policy, h->d_titer, h->d_motors, h->d_setpoint, h->d_traj, h->d_euler, h->d_twist,
-                    h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b};
+                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -149,24 +154,30 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     cudaDeviceProp prop;
     CKH(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    h->smem = (size_t) CF_WARPS_PER_BLOCK * CF_SM_DOUBLES * sizeof(double);
-    // occupancy variant: CFNMPC_MIN_BLOCKS = 3 | 4 | 5 | 6 blocks of 4 warps per SM (default 5 -> 20 warps per SM)
+    // launch shape: CFNMPC_WARPS_PER_BLOCK x CFNMPC_MIN_BLOCKS (default 4 x 4 = 16 warps per SM at 128 registers, the
+    // measured optimum: profiles/README.md)
     if (const char *e = getenv("CFNMPC_MIN_BLOCKS")) h->minb = atoi(e);
-    if (h->minb == 3) h->kernel = cf_rti_kernel<3>;
-    else if (h->minb == 4) h->kernel = cf_rti_kernel<4>;
-    else if (h->minb == 6) h->kernel = cf_rti_kernel<6>;
-    else { h->minb = 5; h->kernel = cf_rti_kernel<5>; }
+    if (const char *e = getenv("CFNMPC_WARPS_PER_BLOCK")) h->wpb = atoi(e);
+    const int shape = h->wpb * 100 + h->minb;
+    switch (shape) {
+    case 403: h->kernel = cf_rti_kernel<4, 3>; break;
+    case 405: h->kernel = cf_rti_kernel<4, 5>; break;
+    case 209: h->kernel = cf_rti_kernel<2, 9>; break;
+
+    default: h->wpb = 4; h->minb = 4; h->kernel = cf_rti_kernel<4, 4>; break;
+    }
+    h->smem = (size_t) h->wpb * CF_SM_DOUBLES * sizeof(double);
     CKH(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem));
     cudaFuncAttributes fa;
     CKH(cudaFuncGetAttributes(&fa, h->kernel));
     h->regs = fa.numRegs;
-    CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, h->kernel, CF_WARPS_PER_BLOCK * 32, h->smem));
+    CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, h->kernel, h->wpb * 32, h->smem));
     if (h->blocks_per_sm < 1) { cfnmpc_batch_destroy(h); return fail(CFNMPC_ECUDA, "kernel does not fit on an SM"); }
     // persistent grid: every SM fully occupied, but never more warps than instances
     long want = (long) h->sm_count * h->blocks_per_sm;
-    long need = ((long) batch + CF_WARPS_PER_BLOCK - 1) / CF_WARPS_PER_BLOCK;
+    long need = ((long) batch + h->wpb - 1) / h->wpb;
     h->grid = (int) (want < need ? want : need);
-    h->n_slots = h->grid * CF_WARPS_PER_BLOCK;
+    h->n_slots = h->grid * h->wpb;
     const long stride = cf_scratch_layout(N).total;
     const size_t B = batch;
     CKH(cudaMalloc(&h->d_x0, B * CF_NX * 8));
@@ -217,6 +228,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     bv.status = h->d_status; bv.qp_iter = h->d_qp_iter; bv.qp_status = h->d_qp_status; bv.flags = h->d_flags;
     bv.res = h->d_res; bv.scratch = h->d_scratch; bv.scratch_stride = stride; bv.counter = h->d_counter;
     bv.W_b = bv.WN_b = bv.lbu_b = bv.ubu_b = bv.lbu0_b = bv.ubu0_b = nullptr;
+    bv.prof = nullptr;
     CKH(cudaStreamSynchronize(h->stream));
 #undef CKH
     *out = h;
@@ -336,7 +348,7 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
     CK(cudaEventRecord(h->ev0, h->stream));
     for (int r = 0; r < n_rti; r++) {
         CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
-        h->kernel<<<h->grid, CF_WARPS_PER_BLOCK * 32, h->smem, h->stream>>>(h->P, h->bv);
+        h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, h->bv);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -588,7 +600,7 @@ extern "C" int cfnmpc_batch_info(cfnmpc_batch *h, const char *what, long long *v
     else if (!strcmp(what, "N")) *value = h->N;
     else if (!strcmp(what, "n_slots")) *value = h->n_slots;
     else if (!strcmp(what, "sm_count")) *value = h->sm_count;
-    else if (!strcmp(what, "warps_per_block")) *value = CF_WARPS_PER_BLOCK;
+    else if (!strcmp(what, "warps_per_block")) *value = h->wpb;
     else if (!strcmp(what, "blocks_per_sm")) *value = h->blocks_per_sm;
     else if (!strcmp(what, "grid")) *value = h->grid;
     else if (!strcmp(what, "regs_per_thread")) *value = h->regs;
@@ -635,6 +647,26 @@ extern "C" int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_dou
             if (used) { slot = w; break; }
         }
         CK(cudaMemcpy(dst, h->d_scratch + (size_t) slot * s.total, (size_t) s.total * 8, cudaMemcpyDeviceToHost));
+    }
+    return CFNMPC_OK;
+}
+
+// Profiling aid: enable (cycles_calls != NULL) per-pass counters and read them back: for each of the passes
+// {linearisation, residual+factorisation, forward, rhs-backward, mu_aff, primal update} the sum over warps of elapsed SM
+// cycles and the number of calls since the counters were enabled.  Costs two clock reads per pass while enabled.
+extern "C" int cfnmpc_debug_pass_cycles(cfnmpc_batch *h, unsigned long long *cycles_calls12)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!h->d_prof) {
+        CK(cudaMalloc(&h->d_prof, 2 * CF_PROF_N * 8));
+        CK(cudaMemset(h->d_prof, 0, 2 * CF_PROF_N * 8));
+        h->bv.prof = h->d_prof;
+    }
+    if (cycles_calls12) {
+        CK(cudaMemcpy(cycles_calls12, h->d_prof, 2 * CF_PROF_N * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(h->d_prof, 0, 2 * CF_PROF_N * 8));
     }
     return CFNMPC_OK;
 }

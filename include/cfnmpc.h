@@ -167,6 +167,10 @@ int cfnmpc_batch_last_solve_ms(cfnmpc_batch *h, double *ms);
  * (layout of a stage block: crazyflie_nmpc_b200/csrc/cf_rti_warp.h) */
 int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_doubles, size_t *n_doubles, long long *offsets12);
 int cfnmpc_debug_max_ipm_iter(cfnmpc_batch *h, int max_iter);
+/* Profiling aid: the first call switches per-pass cycle counters on; later calls copy out and reset them:
+ * cycles_calls12[2*p] = warp cycles summed over all warps, [2*p+1] = calls, p = linearisation, residual+factorisation
+ * sweep, forward sweep, rhs-only backward sweep, mu_aff, primal update. */
+int cfnmpc_debug_pass_cycles(cfnmpc_batch *h, unsigned long long *cycles_calls12);
 
 const char *cfnmpc_last_error(void);
 const char *cfnmpc_version(void);

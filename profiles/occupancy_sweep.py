@@ -16,8 +16,9 @@ with cf.BatchSolver({B}, {N}, 0.015) as s:
     ts = []
     for r in range(4):
         s.set_problem(w).solve(1); ts.append(s.last_solve_ms())
-    print("minb", s.info("blocks_per_sm"), "regs", s.info("regs_per_thread"), "grid", s.info("grid"),
+    print("warps/block", s.info("warps_per_block"), "blocks/SM", s.info("blocks_per_sm"), "regs", s.info("regs_per_thread"), "grid", s.info("grid"),
           "ms", [round(t, 2) for t in ts], "solves/s %.0f" % ({B} / (min(ts) * 1e-3)), "iters", s.get("qp_iter").mean())
 """
-for mb in (3, 4, 5, 6):
-    subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CFNMPC_MIN_BLOCKS=str(mb)))
+for wpb, mb in ((4, 3), (4, 4), (4, 5), (2, 9)):
+    subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CFNMPC_MIN_BLOCKS=str(mb), CFNMPC_WARPS_PER_BLOCK=str(wpb)))
+

@@ -258,6 +258,7 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
     bv.W_b = per_inst ? per_inst[0] : nullptr; bv.WN_b = per_inst ? per_inst[1] : nullptr;
     bv.lbu_b = per_inst ? per_inst[2] : nullptr; bv.ubu_b = per_inst ? per_inst[3] : nullptr;
     bv.lbu0_b = per_inst ? per_inst[4] : nullptr; bv.ubu0_b = per_inst ? per_inst[5] : nullptr;
+    bv.prof = nullptr;
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(0);
     std::vector<std::thread> th;
