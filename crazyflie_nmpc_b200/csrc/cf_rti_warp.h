@@ -35,7 +35,8 @@
 #define CF_MROWS 18                       // rows of [B';A';res_b'] held per stage
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
 #define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
-#define CF_LX 92                          // cost-to-go Hessian of the state block: packed lower triangle of P (91) + pad
+#define CF_PST 14                         // row stride of the stored cost-to-go Hessian
+#define CF_LX (CF_NX * CF_PST)            // cost-to-go Hessian P of the state block, full symmetric 13 x 13 (rows padded to 14)
 // One contiguous block per stage in the scratch slot.  The field order makes whatever a sweep needs of a stage ONE
 // contiguous, 16-byte aligned range = one TMA bulk copy, issued one stage ahead of the arithmetic:
 //   residual+factorisation sweep [0, B_RD)      rhs-only backward sweep [R_BKP, B_PX)      forward sweep [R_LAM, CF_SB)
@@ -48,11 +49,11 @@
 //   B_M    [B';A'] rows 0..16, row 17 = b_k (linearisation, never changes inside the IPM), element (r,c) at c*18 + r
 //   R_RESD, R_RESM, R_RESG, R_RESB residuals (R_RESM = the complementarity rhs of the next solve)
 //   B_LU   factor of the 4 input columns (18 x 4), INVERSE pivots on the diagonal (like BLASFEO's dA)
-//   B_PX   packed lower triangle of P_{k+1} (what the forward sweep of stage k multiplies with; written by the
-//          factorisation of stage k+1)
+//   B_PX   P_{k+1}, full symmetric (what the forward sweep of stage k multiplies with, row-wise with 128-bit loads;
+//          written by the factorisation of stage k+1)
 enum { R_UX = 0, R_PI = 18, R_DPI = 32, R_RQ = 46, R_D = 64, R_BKP = 72, R_PB = 80, R_DLAM = 94, R_DT = 102, R_LAM = 110,
        R_T = 118, R_DUX = 126, B_M = 144, B_RD = B_M + CF_MSZ, R_RESD = B_RD, R_RESM = B_RD + 8, R_RESG = B_RD + 16,
-       R_RESB = B_RD + 34, B_LU = B_RD + 48, B_PX = B_LU + CF_LU, CF_SB = B_PX + CF_LX };   // 590 doubles per stage
+       R_RESB = B_RD + 34, B_LU = B_RD + 48, B_PX = B_LU + CF_LU, CF_SB = B_PX + CF_LX };   // 680 doubles per stage
 static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 && CF_SB % 2 == 0, "16-byte alignment of TMA ranges");
 
 // HPIPM arguments in effect for the reference configuration (BALANCE mode + acados
@@ -134,12 +135,13 @@ static inline
 }
 
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
-#define CF_SM_BUF0 0                           // sweeps: staged range of a stage block, double buffered (<= 480 doubles)
-#define CF_SM_BUF1 480
+#define CF_SM_BUFSZ 576                        // sweeps: staged range of a stage block, double buffered
+#define CF_SM_BUF0 0
+#define CF_SM_BUF1 CF_SM_BUFSZ
 #define CF_SM_MS0 0                            // linearisation: [B';A';b'] staging, double buffered
 #define CF_SM_MS1 CF_MSZ
 #define CF_ALST 20                             // row stride 20: conflict-free fp64 tensor-core fragment loads
-#define CF_SM_P (2 * 480)                      // factorisation: P_{k+1}, 13 x 20 (the W / input-column block, 18 x 20,
+#define CF_SM_P (2 * CF_SM_BUFSZ)              // factorisation: P_{k+1}, 13 x 20 (the W / input-column block, 18 x 20,
                                                //   overlays the staged block of the stage being factorised)
 #define CF_SM_V0 (CF_SM_P + 13 * CF_ALST)      // four 20-double broadcast vectors
 #define CF_SM_V1 (CF_SM_V0 + 20)
@@ -147,8 +149,9 @@ static inline
 #define CF_SM_V3 (CF_SM_V2 + 20)
 #define CF_SM_BAR (CF_SM_V3 + 20)              // two mbarriers
 #define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
-#define CF_SM_DOUBLES (CF_SM_PAR + CF_PAR_DOUBLES)  // 1352 doubles = 10816 bytes per warp (5 blocks of 4 warps per SM)
-static_assert(B_RD <= 480 && CF_SB - R_LAM <= 480 && B_PX - R_BKP <= 480 && 18 * CF_ALST <= 480, "staging buffers");
+#define CF_SM_DOUBLES (CF_SM_PAR + CF_PAR_DOUBLES)  // 1544 doubles = 12352 bytes per warp (4 blocks of 4 warps per SM)
+static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && 18 * CF_ALST <= CF_SM_BUFSZ,
+              "staging buffers");
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
@@ -470,7 +473,7 @@ struct CfWarp
                 if (xl) {
                     PS[ci * CF_ALST + ci] = hN;
                     PV[ci] = rg;
-                    PXN[cf_tri(ci) + ci] = hN;
+                    PXN[ci * CF_PST + ci] = hN;
                     rk[R_DUX + lane] = rg;   // p_N for the forward sweep
                 }
                 continue;
@@ -603,18 +606,16 @@ struct CfWarp
                         const int r = 8 * t + fg;
                         CF_UNROLL
                         for (int e = 0; e < 2; e++) {
+                            // flat predicates (predicated stores, no nested branches): element (r, c) of the Schur complement
                             const int c = 8 * tp + 2 * fq + e;
                             const double val = sx[t][tp][e];
-                            if (c >= CF_NU && c < CF_NV) {
-                                const int jx = c - CF_NU;
-                                if (r == 17) { PV[jx] = val; rk[R_DUX + c] = val; }   // p_k
-                                else if (r >= c && r < CF_NV) {                             // P_k, lower part + mirror
-                                    const int ix = r - CF_NU;
-                                    PS[ix * CF_ALST + jx] = val;
-                                    PS[jx * CF_ALST + ix] = val;
-                                    if (k > 0) LFk[cf_tri(ix) + jx] = val;
-                                }
-                            }
+                            const bool cx = c >= CF_NU && c < CF_NV;
+                            const int jx = cx ? c - CF_NU : 0, ix = (r >= CF_NU && r < CF_NV) ? r - CF_NU : 0;
+                            const bool isP = cx && r >= c && r < CF_NV;   // P_k, lower part (mirrored on the fly)
+                            const bool isp = cx && r == 17;               // p_k
+                            if (isP) { PS[ix * CF_ALST + jx] = val; PS[jx * CF_ALST + ix] = val; }
+                            if (isP && k > 0) { LFk[ix * CF_PST + jx] = val; LFk[jx * CF_PST + ix] = val; }
+                            if (isp) { PV[jx] = val; rk[R_DUX + CF_NU + jx] = val; }
                         }
                     }
                 }
@@ -755,17 +756,18 @@ struct CfWarp
                 if (xl) XS[ci] = dxn;
             }
             cf_syncwarp();
-            // ---- dpi = P_{k+1} dx+ + p_{k+1}   (GEMV_N :712,729); P packed lower
+            // ---- dpi = P_{k+1} dx+ + p_{k+1}   (GEMV_N :712,729)
             double dpik;
             {
-                const double *Li = LX + cf_tri(ci);   // row ci: entries c <= ci; entries c > ci come from column ci
+                const double *Li = LX + ci * CF_PST;   // row ci of the symmetric P_{k+1}
                 double z0 = pnext, z1 = 0.0;
                 CF_UNROLL
-                for (int c = 0; c < CF_NX; c++) {
-                    const double pc = (c <= ci) ? Li[c] : LX[(c * (c + 1)) / 2 + ci];
-                    if (c & 1) z1 += pc * XS[c];
-                    else z0 += pc * XS[c];
+                for (int cp = 0; cp < 6; cp++) {
+                    const cf_d2 p2 = cf_ld2(Li + 2 * cp), x2 = cf_ld2(XS + 2 * cp);
+                    z0 += p2.x * x2.x;
+                    z1 += p2.y * x2.y;
                 }
+                z0 += Li[12] * XS[12];
                 dpik = xl ? z0 + z1 : 0.0;
                 if (xl) { rec(k + 1)[R_DPI + ci] = dpik; PS[ci] = dpik; }   // the record of stage k+1 holds pi_k
             }
