@@ -43,6 +43,7 @@ def lib():
         L.cfnmpc_batch_set_stream.argtypes = [vp, vp]
         L.cfnmpc_batch_set.argtypes = [vp, cp, vp, ci]
         L.cfnmpc_batch_clear.argtypes = [vp, cp]
+        L.cfnmpc_batch_set_option.argtypes = [vp, cp, ci]
         L.cfnmpc_batch_solve.argtypes = [vp, ci]
         L.cfnmpc_batch_sync.argtypes = [vp]
         L.cfnmpc_batch_get.argtypes = [vp, cp, ci, vp, ci]
@@ -131,6 +132,11 @@ class BatchSolver:
                 "W_batch": (B, NY), "W_e_batch": (B, NX), "lbu_batch": (B, NU), "ubu_batch": (B, NU),
                 "lbu0_batch": (B, NU), "ubu0_batch": (B, NU), "setpoint": (B, 3), "uss": (1,),
                 "policy": (B,), "traj_iter": (B,)}.get(field)
+
+    def set_option(self, option, value):
+        """"lin_res_check" (0/1: the reference's linear-system residual diagnostics -> "flags"), "max_ipm_iter"."""
+        _check(lib().cfnmpc_batch_set_option(self._h, option.encode(), int(value)))
+        return self
 
     def clear(self, field):
         _check(lib().cfnmpc_batch_clear(self._h, field.encode()))

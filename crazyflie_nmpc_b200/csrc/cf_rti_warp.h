@@ -87,8 +87,10 @@ struct CfParams
     double Ts;
     int N;
     int max_ipm_iter;      // CF_ITER_MAX unless a test truncates the loop
+    int lin_res_check;     // != 0: evaluate the linear-system residuals of every solve (sets the CF_FLAG_LIN_RES_* bits)
+    int pad_;
 };
-#define CF_PAR_DOUBLES 48  // sizeof(CfParams) / 8: the per-warp copy in shared memory
+#define CF_PAR_DOUBLES 49  // sizeof(CfParams) / 8: the per-warp copy in shared memory
 static_assert(sizeof(CfParams) == CF_PAR_DOUBLES * 8, "CfParams layout");
 
 struct CfBatchView
@@ -149,7 +151,8 @@ static inline
 #define CF_SM_V3 (CF_SM_V2 + 20)
 #define CF_SM_BAR (CF_SM_V3 + 20)              // two mbarriers
 #define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
-#define CF_SM_DOUBLES (CF_SM_PAR + CF_PAR_DOUBLES)  // 1544 doubles = 12352 bytes per warp (4 blocks of 4 warps per SM)
+#define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1546 doubles = 12368 bytes per warp (4 blocks of 4 warps per SM)
+static_assert(CF_SM_DOUBLES % 2 == 0, "every warp's shared-memory slice must start on a 16-byte boundary");
 static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && 18 * CF_ALST <= CF_SM_BUFSZ,
               "staging buffers");
 
@@ -673,6 +676,7 @@ struct CfWarp
         const bool ul = lane < CF_NU, vl = lane < CF_NV;
         const bool xl = lane >= CF_NU && vl;
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
+        const bool chk = PG->lin_res_check != 0;   // the reference's linear-system residual checks (diagnostic flags only)
         CF_NOUNROLL
         for (int k = 0; k < N; k++) {
             const int bf = k & 1;
@@ -729,13 +733,17 @@ struct CfWarp
                 c = pn_ * dtl < tl * pd_; pn_ = c ? tl : pn_; pd_ = c ? dtl : pd_;
                 c = dn * dlam_u < lu * dd; dn = c ? lu : dn; dd = c ? dlam_u : dd;
                 c = pn_ * dtu < tu * pd_; pn_ = c ? tu : pn_; pd_ = c ? dtu : pd_;
-                // linear residuals of the complementarity / bound rows
-                cf_amax(ld, rdl + dtl - du); cf_amax(ld, rdu + dtu + du);
-                cf_amax(lm, rml + ll * dtl + dlam_l * tl); cf_amax(lm, rmu + lu * dtu + dlam_u * tu);
+                if (chk) {   // linear residuals of the complementarity / bound rows
+                    cf_amax(ld, rdl + dtl - du); cf_amax(ld, rdu + dtu + du);
+                    cf_amax(lm, rml + ll * dtl + dlam_l * tl); cf_amax(lm, rmu + lu * dtu + dlam_u * tu);
+                }
             }
             // stationarity residual, part 1: H dux + rhs_g - dpi_{k-1} + dlam_ub - dlam_lb
-            double rgl = Hs * duxk + VS[R_RESG + lv] - dpi_prev;
-            rgl += ul ? dlam_u - dlam_l : 0.0;
+            double rgl = 0.0;
+            if (chk) {
+                rgl = Hs * duxk + VS[R_RESG + lv] - dpi_prev;
+                rgl += ul ? dlam_u - dlam_l : 0.0;
+            }
             // ---- dx+ = [A B] dux + res_b        GEMV_T, column layout of M_k (contiguous)
             if (vl) DS[lane] = duxk;
             cf_syncwarp();
@@ -752,7 +760,7 @@ struct CfWarp
                 s0 += Mc[16] * DS[16];
                 const double sacc = s0 + s1, rbk = VS[R_RESB + ci];
                 dxn = xl ? sacc + rbk : 0.0;
-                cf_amax(lb, xl ? (rbk - dxn) + sacc : 0.0);
+                if (chk) cf_amax(lb, xl ? (rbk - dxn) + sacc : 0.0);
                 if (xl) XS[ci] = dxn;
             }
             cf_syncwarp();
@@ -771,9 +779,9 @@ struct CfWarp
                 dpik = xl ? z0 + z1 : 0.0;
                 if (xl) { rec(k + 1)[R_DPI + ci] = dpik; PS[ci] = dpik; }   // the record of stage k+1 holds pi_k
             }
+            if (chk) {   // warp-uniform
             cf_syncwarp();
             // stationarity residual, part 2: + [B';A'] dpi_k   (row layout)
-            {
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
                 for (int cp = 0; cp < 6; cp++) {
@@ -790,11 +798,11 @@ struct CfWarp
         // terminal stage: no inputs, no bounds, no dynamics
         if (vl) {
             const double duxN = ul ? 0.0 : dxk;
-            const double rgl = HN * duxN + rec(N)[R_RESG + lane] - dpi_prev;
             rec(N)[R_DUX + lane] = duxN;
-            cf_amax(lg, rgl);
+            if (chk) cf_amax(lg, HN * duxN + rec(N)[R_RESG + lane] - dpi_prev);
         }
-        lin[0] = cf_warp_max(lg); lin[1] = cf_warp_max(lb); lin[2] = cf_warp_max(ld); lin[3] = cf_warp_max(lm);
+        if (chk) { lin[0] = cf_warp_max(lg); lin[1] = cf_warp_max(lb); lin[2] = cf_warp_max(ld); lin[3] = cf_warp_max(lm); }
+        else { lin[0] = lin[1] = lin[2] = lin[3] = 0.0; }
         // alpha = min(1, prim, dual) as in x_core_qp_ipm_aux.c:146-216 (running values are negative)
         const double a_p = cf_warp_max(pn_ / pd_), a_d = cf_warp_max(dn / dd);
         alpha = -(a_p > a_d ? a_p : a_d);

@@ -105,7 +105,7 @@ static void default_params(CfParams &P, int N, double Ts)
     static const double Q[CF_NX] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
     for (int i = 0; i < CF_NX; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
     for (int i = 0; i < CF_NU; i++) { P.Wdiag[CF_NX + i] = 0.06; P.lbu[i] = P.lbu0[i] = 0.0; P.ubu[i] = P.ubu0[i] = 22.0; }
-    P.Ts = Ts; P.N = N; P.max_ipm_iter = CF_ITER_MAX;
+    P.Ts = Ts; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = 0; P.pad_ = 0;
 }
 
 extern "C" const char *cfnmpc_last_error(void) { return g_err.c_str(); }
@@ -325,6 +325,15 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         return CFNMPC_OK;
     }
     return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_set: unknown field '") + field + "'");
+}
+
+extern "C" int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int value)
+{
+    if (!h || !option) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set_option: null argument");
+    if (!strcmp(option, "lin_res_check")) h->P.lin_res_check = value != 0;
+    else if (!strcmp(option, "max_ipm_iter")) h->P.max_ipm_iter = (value > 0 && value < CF_ITER_MAX) ? value : CF_ITER_MAX;
+    else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_set_option: unknown option '") + option + "'");
+    return CFNMPC_OK;
 }
 
 extern "C" int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field)

@@ -88,6 +88,14 @@ int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *src, int sr
 /* Stop using a per-instance parameter array ("W_batch", ...): back to the solver-wide value. */
 int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field);
 
+/* Integer options:
+ *   "lin_res_check" (default 0)  1: evaluate, after every Riccati solve, the linear-system residuals HPIPM evaluates for
+ *                   its safety nets (x_ocp_qp_ipm.c:2029-2059 LQ re-factorisation, :2311-2318 iterative refinement) and
+ *                   report in "flags" where the reference would have taken one of them.  Diagnostic only: the nets
+ *                   themselves are not implemented (they never fire on this OCP), results do not depend on the option.
+ *   "max_ipm_iter"  (default 50 = qp_solver_iter_max of the reference configuration) */
+int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int value);
+
 /* Enqueue n_rti consecutive RTI steps (preparation + feedback) for every instance,
  * inputs frozen between steps.  Asynchronous; pair with cfnmpc_batch_sync or a
  * getter to a host pointer. */
@@ -101,7 +109,8 @@ int cfnmpc_batch_sync(cfnmpc_batch *h);
  *   "status"   int [B]   acados status of the last step (0 ok, 4 QP failure)
  *   "qp_iter"  int [B]   interior-point iterations of the last step
  *   "qp_status" int [B]  HPIPM status 0 ok / 1 max-iter / 2 min-step / 3 NaN
- *   "flags"    int [B]   bit 0/1: the reference's LQ / iterative-refinement safety nets would have fired
+ *   "flags"    int [B]   bit 0/1: the reference's LQ / iterative-refinement safety nets would have fired (needs the option
+ *                        "lin_res_check"; 0 otherwise)
  *   "res"      double [B][4]  final QP residual inf-norms (stationarity, dynamics, bounds, complementarity)
  * Copies to host pointers synchronise the stream before returning. */
 int cfnmpc_batch_get(cfnmpc_batch *h, const char *field, int stage, void *dst, int dst_on_device);

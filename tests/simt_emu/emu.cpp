@@ -250,6 +250,7 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
     }
     memcpy(P.lbu0, P.lbu, sizeof P.lbu); memcpy(P.ubu0, P.ubu, sizeof P.ubu);
     P.Ts = Ts; P.N = N; P.max_ipm_iter = max_ipm_iter > 0 ? max_ipm_iter : CF_ITER_MAX;
+    P.lin_res_check = 1; P.pad_ = 0;
     const long stride = cf_scratch_layout(N).total;
     CfBatchView bv;
     bv.B = B; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;

@@ -22,6 +22,7 @@ TS = 0.015
 def gpu_solve(w, N, n_rti=1, **params):
     B = w["x0"].shape[0]
     with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("lin_res_check", 1)   # "flags" reports where the reference's safety nets would have fired
         for k, v in params.items():
             s.set(k, v)
         s.set_problem(w).solve(n_rti)
@@ -202,6 +203,20 @@ def test_per_instance_weights_and_bounds(port, ref):
     assert rel_err(x_def, o["x"]) <= TIGHT and rel_err(u_def, o["u"]) <= TIGHT
 
 
+def test_lin_res_check_is_diagnostic_only():
+    """The linear-system residual diagnostics (option "lin_res_check") never change a result."""
+    N, B = 50, 256
+    w = wl.hover_batch(B, N, seed=5)
+    out = []
+    for chk in (0, 1):
+        with cf.BatchSolver(B, N, TS) as s:
+            s.set_option("lin_res_check", chk)
+            s.set_problem(w).solve(2)
+            out.append((s.get("x_all"), s.get("u_all"), s.get("qp_iter"), s.get("flags")))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2]) and (out[0][3] == 0).all() and (out[1][3] == 0).all()
+
+
 def test_ragged_and_tiny_batches(port):
     N = 20
     for B in (1, 3, 5, 33):
@@ -214,6 +229,7 @@ def test_full_size_properties(port):
     N, B = 50, 65536
     w = wl.hover_batch(B, N)
     with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("lin_res_check", 1)
         s.set_problem(w).solve(1)
         x, u, st, it, fl = s.get("x_all"), s.get("u_all"), s.get("status"), s.get("qp_iter"), s.get("flags")
         assert s.info("n_slots") < B  # persistent warps really re-used their scratch slots
