@@ -218,27 +218,81 @@ struct CfWarp
     }
 
     // =============================================================== preparation
-    // ERK4 with forward sensitivities for stage k; lane c pushes sensitivity column c
-    // ([Su(4) | Sx(13)] -> rows of [B';A']), the nominal state is advanced once per warp in
-    // shared memory.  Writes M_k (rows 0..16 + b row) by bulk store, b_k, rq_k, d_k.
-    CF_MEM void linearize_stage(int k, const double *xg, const double *ug, const double *x0g, const double *yrefg,
-                                double &xk_pre, double &uk_pre)
+    // Multiple shooting makes the N intervals independent, so the NOMINAL integration is done first, one interval per
+    // lane (two rounds of 32 lanes at N = 50) instead of redundantly on every lane of every stage: classic RK4
+    // (tableau sim_collocation_utils.c:611-640, operation order of sim_erk_integrator.c:658-731).  Leaves, per interval,
+    // the four RK stage states, b_k = phi(x_k,u_k) - x_{k+1} (ocp_nlp_dynamics_cont.c:822-823) and u_k in the (still
+    // unused) factor area of the stage block, from where the sensitivity pass stages them by TMA:
+    //   NOM = [ xs_0 (13+1) | xs_1 | xs_2 | xs_3 | b (13+1) | u (4) ]  at B_LU
+#define CF_NOM 74
+    CF_MEM void nominal_pass(const double *xg, const double *ug)
     {
-        double *X0 = sm + CF_SM_V0, *ACC = sm + CF_SM_V1, *XS = sm + CF_SM_V2, *UU = sm + CF_SM_V3;
+        const double h = PG->Ts;
+        CF_NOUNROLL
+        for (int k = lane; k < N; k += 32) {
+            double *nom = blk(k) + B_LU;
+            double x[CF_NX], xs[CF_NX], acc[CF_NX], uu[CF_NU];
+            CF_UNROLL
+            for (int i = 0; i < CF_NX; i++) { x[i] = xg[k * CF_NX + i]; xs[i] = x[i]; acc[i] = x[i]; }
+            CF_UNROLL
+            for (int i = 0; i < CF_NU; i++) uu[i] = ug[k * CF_NU + i];
+            cf_st2(nom + 5 * 14, uu[0], uu[1]);
+            cf_st2(nom + 5 * 14 + 2, uu[2], uu[3]);
+            CF_UNROLL
+            for (int s = 0; s < 4; s++) {
+                const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
+                const double a_next = (s == 2) ? 1.0 : 0.5;
+                const double bh = h * bw, ah = a_next * h;
+                CF_UNROLL
+                for (int i = 0; i < 12; i += 2) cf_st2(nom + s * 14 + i, xs[i], xs[i + 1]);
+                nom[s * 14 + 12] = xs[12];
+                double f[CF_NX];
+                cf_ode(xs, uu, f);
+                CF_UNROLL
+                for (int i = 0; i < CF_NX; i++) {
+                    acc[i] += bh * f[i];
+                    xs[i] = x[i] + ah * f[i];
+                }
+            }
+            CF_UNROLL
+            for (int i = 0; i < CF_NX; i++) acc[i] -= xg[(k + 1) * CF_NX + i];
+            CF_UNROLL
+            for (int i = 0; i < 12; i += 2) cf_st2(nom + 4 * 14 + i, acc[i], acc[i + 1]);
+            nom[4 * 14 + 12] = acc[12];
+        }
+        pass_begin();   // the generic stores above are read back by bulk copies
+        if (N > 0) fetch_nom(0, 0);
+    }
+    CF_MEM double *nom_buf(int bf) const { return sm + 480 + bf * 80; }
+    CF_MEM void fetch_nom(int bf, int k)
+    {
+        if (lane == 0) {
+            cf_bulk_expect(bar + bf, CF_NOM * 8);
+            cf_bulk_g2s_raw(nom_buf(bf), blk(k) + B_LU, CF_NOM * 8, bar + bf);
+        }
+    }
+
+    // Forward sensitivities of stage k along the stored nominal RK stages; lane c pushes sensitivity column c
+    // ([Su(4) | Sx(13)] -> rows of [B';A']).  Writes M_k (rows 0..16 + b row) by bulk store, rq_k, d_k and the initial
+    // IPM variables of the stage.
+    CF_MEM void linearize_stage(int k, const double *xg, const double *x0g, const double *yrefg)
+    {
         double *MS = sm + ((k & 1) ? CF_SM_MS1 : CF_SM_MS0);
         const double h = PG->Ts;
-        cf_syncwarp();
-        if (lane < CF_NX) { const double v = xk_pre; X0[lane] = v; ACC[lane] = v; XS[lane] = v; }
-        if (lane < CF_NU) UU[lane] = uk_pre;
-        if (lane == 0) cf_bulk_s2g_wait_read1();  // the bulk store that last read this MS buffer (stage k-2) is done
-        cf_syncwarp();
-        // software prefetch: x_{k+1} (needed for b_k and as the next stage's state), u_{k+1}, and this stage's reference
-        const double xn_pre = (lane < CF_NX) ? xg[(k + 1) * CF_NX + lane] : 0.0;
-        const double un_pre = (lane < CF_NU && k + 1 < N) ? ug[(k + 1) * CF_NU + lane] : 0.0;
+        const int bf = k & 1;
+        // this stage's reference (consumed at the end of the stage)
         const double yr_pre = (lane < CF_NU) ? yrefg[k * CF_NY + CF_NX + lane] : ((lane < CF_NV) ? yrefg[k * CF_NY + lane - CF_NU] : 0.0);
+        wait(bf);
+        cf_syncwarp();   // every lane is done with the other nominal buffer and with MS of stage k-2 ...
+        if (k + 1 < N) fetch_nom(bf ^ 1, k + 1);
+        if (lane == 0) cf_bulk_s2g_wait_read1();  // ... and the bulk store that last read this MS buffer (stage k-2) is done
+        cf_syncwarp();
+        const double *NOMS = nom_buf(bf);
         double uu[CF_NU];
-        CF_UNROLL
-        for (int i = 0; i < CF_NU; i++) uu[i] = UU[i];
+        {
+            const cf_d2 u01 = cf_ld2(NOMS + 5 * 14), u23 = cf_ld2(NOMS + 5 * 14 + 2);
+            uu[0] = u01.x; uu[1] = u01.y; uu[2] = u23.x; uu[3] = u23.y;
+        }
         // the accumulated sensitivity column of this lane lives in its row of the staging block (MS[c*18+lane]),
         // not in registers: the RK stage below is register-hungry enough
         const bool col = lane < CF_NV;
@@ -251,25 +305,13 @@ struct CfWarp
         }
         CF_NOUNROLL
         for (int s = 0; s < 4; s++) {
-            // tableau: sim_collocation_utils.c:611-640 (classic RK4)
             const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
             const double a_next = (s == 2) ? 1.0 : 0.5;
             const double bh = h * bw, ah = a_next * h;
             double xs[CF_NX];
             CF_UNROLL
-            for (int i = 0; i < CF_NX; i++) xs[i] = XS[i];
-            cf_syncwarp();  // everyone has read XS
-            {
-                double f[CF_NX];
-                cf_ode(xs, uu, f);
-                if (lane == 17) {
-                    CF_UNROLL
-                    for (int i = 0; i < CF_NX; i++) {
-                        ACC[i] += bh * f[i];
-                        XS[i] = X0[i] + ah * f[i];
-                    }
-                }
-            }
+            for (int i = 0; i < 12; i += 2) { const cf_d2 v = cf_ld2(NOMS + s * 14 + i); xs[i] = v.x; xs[i + 1] = v.y; }
+            xs[12] = NOMS[s * 14 + 12];
             double ks[CF_NX];
             cf_jvp_x(xs, Ss, ks);
             if (lane < CF_NU) cf_add_ju_col(uu, lane, ks);
@@ -278,10 +320,9 @@ struct CfWarp
                 if (col) Mrow[i * CF_MROWS] += bh * ks[i];
                 Ss[i] = ((lane - CF_NU == i) ? 1.0 : 0.0) + ah * ks[i];
             }
-            cf_syncwarp();
         }
-        // row 17: b_k = phi(x_k,u_k) - x_{k+1}   (ocp_nlp_dynamics_cont.c:822-823)
-        if (lane < CF_NX) MS[lane * CF_MROWS + 17] = ACC[lane] - xn_pre;
+        // row 17: b_k
+        if (lane < CF_NX) MS[lane * CF_MROWS + 17] = NOMS[4 * 14 + lane];
         cf_syncwarp();
         if (k == 0) {
             // x0 elimination (x_ocp_qp_red.c:310-330): xbar = lbx - x_0 ; b_0 += A_0 xbar ; drop the A rows
@@ -296,17 +337,18 @@ struct CfWarp
             cf_syncwarp();
         }
         // gradient: scaling * W * (y - yref), [u;x] order (ocp_nlp_cost_ls.c:883-912)
+        const double uk = (lane < CF_NU) ? NOMS[5 * 14 + lane] : 0.0;
         if (lane < CF_NV) {
             double g;
-            if (lane < CF_NU) g = (P->Wdiag[CF_NX + lane] * (UU[lane] - yr_pre)) * h;
-            else g = (k == 0) ? 0.0 : (P->Wdiag[lane - CF_NU] * (X0[lane - CF_NU] - yr_pre)) * h;
+            if (lane < CF_NU) g = (P->Wdiag[CF_NX + lane] * (uk - yr_pre)) * h;
+            else g = (k == 0) ? 0.0 : (P->Wdiag[lane - CF_NU] * (NOMS[lane - CF_NU] - yr_pre)) * h;
             rec(k)[R_RQ + lane] = g;
         }
         // bounds (ocp_nlp_constraints_bgh.c:1634-1636): d = [lb - u ; u - ub]
         double v0 = 0.0;
         if (lane < CF_NU) {
-            const double dl = ((k == 0) ? P->lbu0[lane] : P->lbu[lane]) - UU[lane];
-            const double du = UU[lane] - ((k == 0) ? P->ubu0[lane] : P->ubu[lane]);
+            const double dl = ((k == 0) ? P->lbu0[lane] : P->lbu[lane]) - uk;
+            const double du = uk - ((k == 0) ? P->ubu0[lane] : P->ubu[lane]);
             rec(k)[R_D + lane] = dl;
             rec(k)[R_D + 4 + lane] = du;
             // OCP_QP_INIT_VAR scheme 1 (x_ocp_qp_ipm.c:1491-1530,1636-1769): slacks at ux = 0, pushed 0.1 inside
@@ -321,8 +363,6 @@ struct CfWarp
         init_stage_vectors(k, v0);
         cf_syncwarp();
         if (lane == 0) cf_bulk_s2g(blk(k) + B_M, MS, CF_MSZ * 8);
-        xk_pre = xn_pre;
-        uk_pre = un_pre;
     }
 
     // ux = v (0 unless a bound had to be respected), pi = 0 and zero steps, so that the first residual pass can be an
@@ -1015,12 +1055,12 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     const double *x0g = bv.x0 + (long) inst * CF_NX;
     const double *yrefg = bv.yref + (long) inst * N * CF_NY;
     const double *yref_eg = bv.yref_e + (long) inst * CF_NX;
-    double xk_pre = (w.lane < CF_NX) ? xg[w.lane] : 0.0, uk_pre = (w.lane < CF_NU) ? ug[w.lane] : 0.0;
     unsigned long long *prof = bv.prof;
     {
         CF_PROF_BEGIN();
+        w.nominal_pass(xg, ug);
         CF_NOUNROLL
-        for (int k = 0; k < N; k++) w.linearize_stage(k, xg, ug, x0g, yrefg, xk_pre, uk_pre);
+        for (int k = 0; k < N; k++) w.linearize_stage(k, xg, x0g, yrefg);
         w.terminal_gradient(xg, yref_eg);
         cf_syncwarp();
         CF_PROF_END(CF_PROF_LIN);
