@@ -172,7 +172,7 @@ struct CfWarp
     // lane constants
     double Hs, HN;     // Hessian diagonal for this lane's variable (stage / terminal)
     // IPM scalars (warp-uniform)
-    double mu, alpha, mu_aff, sigma;
+    double mu, alpha, mu_aff, sigma, pm_max;
     double nrm[4];     // inf-norms of res_g, res_b, res_d, res_m
     double lin[4];     // inf-norms of the linear-system residual of the last solve
     int flags;
@@ -408,10 +408,10 @@ struct CfWarp
     //   P_k = S_xx - Ls Ls',  p_k = s_x - Ls l_u             SYRK -1 :655
     // Stored per stage: LU (18 x 4 factor columns, inverse pivots on the diagonal), the packed lower triangle of P_k, and
     // the gradient parts l_u | p_k in R_DUX of the stage record.
-    CF_MEM void residual_factorize(const double a_raw)
+    CF_MEM double step_adjust(double a) const { return (a < 1.0) ? a * ((1.0 - a) * 0.99 + a * 0.9999999) : a; }
+    CF_MEM void residual_factorize(const double a_raw, const bool do_factor)
     {
-        double a = a_raw;
-        if (a < 1.0) a = a * ((1.0 - a) * 0.99 + a * 0.9999999);
+        const double a = step_adjust(a_raw);
         double ng = 0, nb = 0, nd = 0, nm = 0, mus = 0;
         double *PS = sm + CF_SM_P;                 // P_{k+1}, full symmetric 13 x 13, stride 20
         double *PV = sm + CF_SM_V0;                // p_{k+1}
@@ -505,7 +505,8 @@ struct CfWarp
             if (vl) { rk[R_RESG + lane] = rg; cf_amax(ng, rg); }
             ux_next = uxc;
             pi_k = pim;
-            // ---------------- factorisation of stage k
+            // ---------------- factorisation of stage k (skipped when the caller predicts that this iterate is final)
+            if (!do_factor) continue;
             if (!kl) {
                 // terminal stage: no dynamics. P_N = diag(H_N) + reg, p_N = res_g_N; dummy inputs decoupled.
                 double *PXN = blk(N > 0 ? N - 1 : 0) + B_PX;   // P_N belongs to the block of stage N-1
@@ -905,10 +906,13 @@ struct CfWarp
         cf_syncwarp();
     }
 
-    // COMPUTE_MU_AFF_QP (x_core_qp_ipm_aux.c:329-352): all 32 lanes sweep the bound records
+    // COMPUTE_MU_AFF_QP (x_core_qp_ipm_aux.c:329-352): all 32 lanes sweep the bound records.  The same sweep predicts
+    // the complementarity residual norm of the iterate the adjusted step would produce (pm_max), used to decide whether
+    // the next residual sweep needs to factorise at all.
     CF_MEM void compute_mu_aff()
     {
-        double s0 = 0.0, s1 = 0.0;
+        double s0 = 0.0, s1 = 0.0, pm = 0.0;
+        const double aa = step_adjust(alpha);
         const int e = lane & 7;
         int k = lane >> 3;
         CF_NOUNROLL
@@ -918,12 +922,17 @@ struct CfWarp
             const double lb = rb[R_LAM + e], db = rb[R_DLAM + e], tb = rb[R_T + e], ub = rb[R_DT + e];
             s0 += (la + alpha * da) * (ta + alpha * ua);
             s1 += (lb + alpha * db) * (tb + alpha * ub);
+            cf_amax(pm, (la + aa * da) * (ta + aa * ua));
+            cf_amax(pm, (lb + aa * db) * (tb + aa * ub));
         }
         if (k < N) {
             const double *ra = rec(k);
-            s0 += (ra[R_LAM + e] + alpha * ra[R_DLAM + e]) * (ra[R_T + e] + alpha * ra[R_DT + e]);
+            const double la = ra[R_LAM + e], da = ra[R_DLAM + e], ta = ra[R_T + e], ua = ra[R_DT + e];
+            s0 += (la + alpha * da) * (ta + alpha * ua);
+            cf_amax(pm, (la + aa * da) * (ta + aa * ua));
         }
         mu_aff = cf_warp_sum(s0 + s1) * (1.0 / (double) (2 * CF_NU * N));
+        pm_max = cf_warp_max(pm);
     }
 
     CF_MEM bool lin_res_ok_fact() const
@@ -956,21 +965,25 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters, unsigned long long *prof)
     const int itmax = w.PG->max_ipm_iter < CF_ITER_MAX ? w.PG->max_ipm_iter : CF_ITER_MAX;
     enum { ST_RF, ST_FWD, ST_BWD };
     int st = ST_RF, kk = 0, brm = 1;
-    bool first = true, predictor = true;
+    bool first = true, predictor = true, do_factor = true, redo = false;
     double sigma_mu = 0.0, mu_aff0 = 0.0;
     for (;;) {
         if (st == ST_RF) {
-            // variables += alpha * direction, residuals of the new iterate, and (speculatively) the factorisation of the
-            // next affine system, OCP_QP_IPM_DELTA_STEP (:1943-2405)
+            // variables += alpha * direction, residuals of the new iterate, and the factorisation of the next affine
+            // system, OCP_QP_IPM_DELTA_STEP (:1943-2405).  The factorisation is skipped when the iterate is predicted to
+            // be the last one; a wrong prediction costs a second pass with step 0 (same residuals, now factorising).
             CF_PROF_BEGIN();
-            w.residual_factorize(first ? 0.0 : w.alpha);
+            w.residual_factorize((first || redo) ? 0.0 : w.alpha, do_factor);
             CF_PROF_END(CF_PROF_RF);
             if (first) { first = false; w.alpha = 1.0; }
-            else kk++;
+            else if (!redo) kk++;
             const bool go = kk < itmax && w.alpha > CF_ALPHA_MIN &&
                             (w.nrm[0] > CF_RES_G_MAX || w.nrm[1] > CF_RES_B_MAX || w.nrm[2] > CF_RES_D_MAX ||
                              fabs(w.nrm[3] - CF_TAU_MIN) > CF_RES_M_MAX);
             if (!go) break;
+            redo = !do_factor;
+            do_factor = true;
+            if (redo) continue;
             predictor = true;
             st = ST_FWD;
         } else if (st == ST_FWD) {
@@ -989,15 +1002,22 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters, unsigned long long *prof)
                 brm = 1;            // centering-corrector rhs
                 st = ST_BWD;
             } else {
-                bool recenter = false;
-                if (brm == 1) {     // conditional predictor-corrector (:2230-2273)
-                    mu_aff0 = w.mu_aff;
-                    w.compute_mu_aff();
-                    recenter = w.mu_aff > 2.0 * mu_aff0;
-                }
+                mu_aff0 = w.mu_aff;
+                CF_PROF_BEGIN();
+                w.compute_mu_aff();
+                CF_PROF_END(CF_PROF_MUAFF);
+                // conditional predictor-corrector (:2230-2273)
+                const bool recenter = brm == 1 && w.mu_aff > 2.0 * mu_aff0;
                 if (recenter) { brm = 2; st = ST_BWD; }
                 else {
                     if (!w.lin_res_ok_corr()) w.flags |= CF_FLAG_LIN_RES_CORR;
+                    // will the updated iterate pass the exit test?  The linear residuals shrink by (1 - step), the
+                    // complementarity products were just evaluated; half the tolerances as margin.
+                    const double r = 1.0 - w.step_adjust(w.alpha);
+                    const bool conv = r * w.nrm[0] < 0.5 * CF_RES_G_MAX && r * w.nrm[1] < 0.5 * CF_RES_B_MAX &&
+                                      r * w.nrm[2] < 0.5 * CF_RES_D_MAX && fabs(w.pm_max - CF_TAU_MIN) < 0.5 * CF_RES_M_MAX;
+                    do_factor = !(conv || kk + 1 >= itmax);
+                    redo = false;
                     st = ST_RF;
                 }
             }
@@ -1071,15 +1091,28 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     // ocp_nlp_sqp_rti.c:651-674: QP max-iter is not fatal; anything else leaves the iterate untouched
     int status = CF_ACADOS_SUCCESS;
     if (qp_status == 0 || qp_status == 1) {
-        // primal update, full step (ocp_nlp_common.c:2900-2952); x_0 takes the eliminated step xbar
+        // primal update, full step (ocp_nlp_common.c:2900-2952); x_0 takes the eliminated step xbar.  Four stages per
+        // trip so that the (independent) step loads of several stages are in flight together.
         const int lane = w.lane;
+        const bool ul = lane < CF_NU, xl = lane >= CF_NU && lane < CF_NV;
+        const int i = xl ? lane - CF_NU : 0;
+        if (xl) xg[i] += x0g[i] - xg[i];
+        if (ul && N > 0) ug[lane] += w.rec(0)[R_UX + lane];
         CF_NOUNROLL
-        for (int k = 0; k <= N; k++) {
-            if (lane < CF_NU && k < N) ug[k * CF_NU + lane] += w.rec(k)[R_UX + lane];
-            if (lane >= CF_NU && lane < CF_NV) {
-                const int i = lane - CF_NU;
-                if (k == 0) xg[i] += x0g[i] - xg[i];
-                else xg[k * CF_NX + i] += w.rec(k)[R_UX + lane];
+        for (int k = 1; k <= N; k += 4) {
+            double d[4], v[4];
+            CF_UNROLL
+            for (int q = 0; q < 4; q++) {
+                const bool on = k + q <= N && ((ul && k + q < N) || xl);
+                d[q] = on ? w.rec(k + q)[R_UX + lane] : 0.0;
+                v[q] = on ? (ul ? ug[(k + q) * CF_NU + lane] : xg[(k + q) * CF_NX + i]) : 0.0;
+            }
+            CF_UNROLL
+            for (int q = 0; q < 4; q++) {
+                if (k + q <= N) {
+                    if (ul && k + q < N) ug[(k + q) * CF_NU + lane] = v[q] + d[q];
+                    if (xl) xg[(k + q) * CF_NX + i] = v[q] + d[q];
+                }
             }
         }
     } else {
