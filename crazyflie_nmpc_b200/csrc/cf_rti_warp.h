@@ -35,8 +35,8 @@
 #define CF_MROWS 18                       // rows of [B';A';res_b'] held per stage
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
 #define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
-#define CF_PST 14                         // row stride of the stored cost-to-go Hessian
-#define CF_LX (CF_NX * CF_PST)            // cost-to-go Hessian P of the state block, full symmetric 13 x 13 (rows padded to 14)
+#define CF_PST 14                         // row stride of the cost-to-go Hessian once expanded in shared memory
+#define CF_LX 92                          // cost-to-go Hessian P of the state block in HBM: packed lower triangle (91) + pad
 // One contiguous block per stage in the scratch slot.  The field order makes whatever a sweep needs of a stage ONE
 // contiguous, 16-byte aligned range = one TMA bulk copy, issued one stage ahead of the arithmetic:
 //   residual+factorisation sweep [0, B_RD)      rhs-only backward sweep [R_BKP, B_PX)      forward sweep [R_LAM, CF_SB)
@@ -49,11 +49,11 @@
 //   B_M    [B';A'] rows 0..16, row 17 = b_k (linearisation, never changes inside the IPM), element (r,c) at c*18 + r
 //   R_RESD, R_RESM, R_RESG, R_RESB residuals (R_RESM = the complementarity rhs of the next solve)
 //   B_LU   factor of the 4 input columns (18 x 4), INVERSE pivots on the diagonal (like BLASFEO's dA)
-//   B_PX   P_{k+1}, full symmetric (what the forward sweep of stage k multiplies with, row-wise with 128-bit loads;
-//          written by the factorisation of stage k+1)
+//   B_PX   packed lower triangle of P_{k+1} (what the forward sweep of stage k multiplies with, after expanding it to
+//          full symmetric rows in shared memory; written by the factorisation of stage k+1)
 enum { R_UX = 0, R_PI = 18, R_DPI = 32, R_RQ = 46, R_D = 64, R_BKP = 72, R_PB = 80, R_DLAM = 94, R_DT = 102, R_LAM = 110,
        R_T = 118, R_DUX = 126, B_M = 144, B_RD = B_M + CF_MSZ, R_RESD = B_RD, R_RESM = B_RD + 8, R_RESG = B_RD + 16,
-       R_RESB = B_RD + 34, B_LU = B_RD + 48, B_PX = B_LU + CF_LU, CF_SB = B_PX + CF_LX };   // 680 doubles per stage
+       R_RESB = B_RD + 34, B_LU = B_RD + 48, B_PX = B_LU + CF_LU, CF_SB = B_PX + CF_LX };   // 590 doubles per stage
 static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 && CF_SB % 2 == 0, "16-byte alignment of TMA ranges");
 
 // HPIPM arguments in effect for the reference configuration (BALANCE mode + acados
@@ -137,21 +137,22 @@ static inline
 }
 
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
-#define CF_SM_BUFSZ 576                        // sweeps: staged range of a stage block, double buffered
+#define CF_SM_BUFSZ 480                        // sweeps: staged range of a stage block, double buffered
 #define CF_SM_BUF0 0
 #define CF_SM_BUF1 CF_SM_BUFSZ
 #define CF_SM_MS0 0                            // linearisation: [B';A';b'] staging, double buffered
 #define CF_SM_MS1 CF_MSZ
 #define CF_ALST 20                             // row stride 20: conflict-free fp64 tensor-core fragment loads
 #define CF_SM_P (2 * CF_SM_BUFSZ)              // factorisation: P_{k+1}, 13 x 20 (the W / input-column block, 18 x 20,
-                                               //   overlays the staged block of the stage being factorised)
+                                               //   overlays the staged block of the stage being factorised);
+                                               //   forward sweep: P_{k+1} expanded to full rows, 13 x 14
 #define CF_SM_V0 (CF_SM_P + 13 * CF_ALST)      // four 20-double broadcast vectors
 #define CF_SM_V1 (CF_SM_V0 + 20)
 #define CF_SM_V2 (CF_SM_V1 + 20)
 #define CF_SM_V3 (CF_SM_V2 + 20)
 #define CF_SM_BAR (CF_SM_V3 + 20)              // two mbarriers
 #define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
-#define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1546 doubles = 12368 bytes per warp (4 blocks of 4 warps per SM)
+#define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1354 doubles = 10832 bytes per warp (4 blocks of 4 warps per SM)
 static_assert(CF_SM_DOUBLES % 2 == 0, "every warp's shared-memory slice must start on a 16-byte boundary");
 static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && 18 * CF_ALST <= CF_SM_BUFSZ,
               "staging buffers");
@@ -517,7 +518,7 @@ struct CfWarp
                 if (xl) {
                     PS[ci * CF_ALST + ci] = hN;
                     PV[ci] = rg;
-                    PXN[ci * CF_PST + ci] = hN;
+                    PXN[cf_tri(ci) + ci] = hN;
                     rk[R_DUX + lane] = rg;   // p_N for the forward sweep
                 }
                 continue;
@@ -658,7 +659,7 @@ struct CfWarp
                             const bool isP = cx && r >= c && r < CF_NV;   // P_k, lower part (mirrored on the fly)
                             const bool isp = cx && r == 17;               // p_k
                             if (isP) { PS[ix * CF_ALST + jx] = val; PS[jx * CF_ALST + ix] = val; }
-                            if (isP && k > 0) { LFk[ix * CF_PST + jx] = val; LFk[jx * CF_PST + ix] = val; }
+                            if (isP && k > 0) LFk[cf_tri(ix) + jx] = val;
                             if (isp) { PV[jx] = val; rk[R_DUX + CF_NU + jx] = val; }
                         }
                     }
@@ -718,16 +719,38 @@ struct CfWarp
         const bool xl = lane >= CF_NU && vl;
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
         const bool chk = PG->lin_res_check != 0;   // the reference's linear-system residual checks (diagnostic flags only)
+        // P_{k+1} travels packed (lower triangle) and is expanded to full symmetric rows in shared memory: element
+        // e = lane + 32 t of the packed triangle goes to (i,j) and (j,i)
+        double *PE = sm + CF_SM_P;
+        int pe_a[3], pe_b[3];
+        CF_UNROLL
+        for (int t = 0; t < 3; t++) {
+            const int e = lane + 32 * t;
+            int i = 0;
+            CF_UNROLL
+            for (int q = 1; q < CF_NX; q++) i += (e >= cf_tri(q)) ? 1 : 0;
+            const int j = e - cf_tri(i);
+            pe_a[t] = (e < 91) ? i * CF_PST + j : -1;
+            pe_b[t] = j * CF_PST + i;
+        }
         CF_NOUNROLL
         for (int k = 0; k < N; k++) {
             const int bf = k & 1;
             double *rk = rec(k);
             const double pnext = rec(k + 1)[R_DUX + lv];  // p_{k+1} left by the backward sweep (x lanes)
             wait(bf);
-            cf_syncwarp();  // every lane is done with buffer bf^1
+            cf_syncwarp();  // every lane is done with buffer bf^1 and with the expanded P of the previous stage
             if (k + 1 < N) fetch(bf ^ 1, k + 1, VO, VN);
             const double *VS = buf(bf) - VO;   // VS[offset within the stage block]
-            const double *Mk = VS + B_M, *LU = VS + B_LU, *LX = VS + B_PX;
+            const double *Mk = VS + B_M, *LU = VS + B_LU, *LX = PE;
+            CF_UNROLL
+            for (int t = 0; t < 3; t++) {
+                if (pe_a[t] >= 0) {
+                    const double v = VS[B_PX + lane + 32 * t];
+                    PE[pe_a[t]] = v;
+                    PE[pe_b[t]] = v;
+                }
+            }
             // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu); input l4 on every lane
             double v;
             {
