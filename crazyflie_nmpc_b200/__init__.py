@@ -14,7 +14,7 @@ from . import workloads  # noqa: F401
 
 NX, NU, NY = 13, 4, 17
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "libcfnmpc.so")
+_LIB_PATH = os.environ.get("CFNMPC_LIB") or os.path.join(_PKG, "libcfnmpc.so")   # CFNMPC_LIB: A/B experiments only
 _lib = None
 
 # acados status codes, acados/acados/utils/types.h:75-83
