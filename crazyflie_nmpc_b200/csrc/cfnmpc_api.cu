@@ -92,7 +92,7 @@ struct cfnmpc_batch
     unsigned long long *d_prof = nullptr;
     double *d_Wb = nullptr, *d_WNb = nullptr, *d_lbub = nullptr, *d_ubub = nullptr, *d_lbu0b = nullptr, *d_ubu0b = nullptr;
     int *d_status = nullptr, *d_qp_iter = nullptr, *d_qp_status = nullptr, *d_flags = nullptr, *d_counter = nullptr;
-    int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 4, wpb = 4;
+    int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 3, wpb = 4;
     void (*kernel)(const CfParams, const CfBatchView) = nullptr;
     size_t smem = 0;
     long long launches = 0;
@@ -154,17 +154,17 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     cudaDeviceProp prop;
     CKH(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    // launch shape: CFNMPC_WARPS_PER_BLOCK x CFNMPC_MIN_BLOCKS (default 4 x 4 = 16 warps per SM at 128 registers, the
+    // launch shape: CFNMPC_WARPS_PER_BLOCK x CFNMPC_MIN_BLOCKS (default 4 x 3 = 12 warps per SM at 168 registers, the
     // measured optimum: profiles/README.md)
     if (const char *e = getenv("CFNMPC_MIN_BLOCKS")) h->minb = atoi(e);
     if (const char *e = getenv("CFNMPC_WARPS_PER_BLOCK")) h->wpb = atoi(e);
     const int shape = h->wpb * 100 + h->minb;
     switch (shape) {
-    case 403: h->kernel = cf_rti_kernel<4, 3>; break;
+    case 404: h->kernel = cf_rti_kernel<4, 4>; break;
     case 405: h->kernel = cf_rti_kernel<4, 5>; break;
     case 209: h->kernel = cf_rti_kernel<2, 9>; break;
 
-    default: h->wpb = 4; h->minb = 4; h->kernel = cf_rti_kernel<4, 4>; break;
+    default: h->wpb = 4; h->minb = 3; h->kernel = cf_rti_kernel<4, 3>; break;
     }
     h->smem = (size_t) h->wpb * CF_SM_DOUBLES * sizeof(double);
     CKH(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem));
