@@ -103,8 +103,8 @@ cf_predict_sens_kernel(const double *__restrict__ x, const double *__restrict__ 
             const double a_next = (s == 2) ? 1.0 : 0.5;
             double f[CF_NX], ks[CF_NX];
             cf_ode(xs, uu, f);
-            cf_jvp_x(xs, Ss, ks);
-            if (lane >= CF_NX && lane < CF_NV) cf_add_ju_col(uu, lane - CF_NX, ks);
+            cf_jvp_x(xs, uu, Ss, ks);
+            if (lane >= CF_NX && lane < CF_NV) cf_add_ju_col(xs, uu, lane - CF_NX, ks);
 #pragma unroll
             for (int i = 0; i < CF_NX; i++) {
                 xa[i] += (h * bw) * f[i];

@@ -5,8 +5,15 @@
 //   crazyflie_controller/scripts/crazyflie_full_model/export_ode_model.py:34-42,85-101
 // via acados_template/casadi_function_generation.py:137-151.
 // State x = [p(3), q(4: w,x,y,z), v_body(3), omega(3)], input u = 4 motor speeds [krpm].
+//
+// The functions the kernels call (cf_ode, cf_jvp_x, cf_add_ju_col) and the default weights / bounds / horizon come from
+// cf_spec_generated.h, which tools/gen_spec.py derives from those two reference files (sympy, common-subexpression
+// elimination).  The hand-derived versions below (*_hand) are kept as an independent cross-check
+// (tests/test_spec_generated.py).
 #pragma once
 #include "cf_simt.h"
+#include "cf_spec_generated.h"
+static_assert(CF_SPEC_NX == 13 && CF_SPEC_NU == 4, "the warp mapping is built for nx = 13, nu = 4");
 
 #define CF_NX 13
 #define CF_NU 4
@@ -21,7 +28,7 @@ struct CfModel
 };
 
 // xdot = f(x,u).  Only x[3..12] enter (the dynamics do not depend on position).
-CF_DEV void cf_ode(const double *x, const double *u, double *f)
+CF_DEV void cf_ode_hand(const double *x, const double *u, double *f)
 {
     const double q1 = x[3], q2 = x[4], q3 = x[5], q4 = x[6], vx = x[7], vy = x[8], vz = x[9];
     const double wx = x[10], wy = x[11], wz = x[12];
@@ -44,7 +51,7 @@ CF_DEV void cf_ode(const double *x, const double *u, double *f)
 // Directional derivative o = (df/dx)(x) * d.  The Jacobian is never formed: each lane
 // of the warp pushes one sensitivity column through this product (73 structural
 // non-zeros).  d[0..2] (position part) does not enter.
-CF_DEV void cf_jvp_x(const double *x, const double *d, double *o)
+CF_DEV void cf_jvp_x_hand(const double *x, const double *d, double *o)
 {
     const double q1 = x[3], q2 = x[4], q3 = x[5], q4 = x[6], vx = x[7], vy = x[8], vz = x[9];
     const double wx = x[10], wy = x[11], wz = x[12];
@@ -78,7 +85,7 @@ CF_DEV void cf_jvp_x(const double *x, const double *d, double *o)
 }
 
 // o += column j of df/du (only rows 9..12 are non-zero; zero at u = 0)
-CF_DEV void cf_add_ju_col(const double *u, int j, double *o)
+CF_DEV void cf_add_ju_col_hand(const double *u, int j, double *o)
 {
     const double uj = (j == 0) ? u[0] : (j == 1) ? u[1] : (j == 2) ? u[2] : u[3];
     const double s10 = (j < 2) ? 1.0 : -1.0;
@@ -89,3 +96,8 @@ CF_DEV void cf_add_ju_col(const double *u, int j, double *o)
     o[11] += -2 * CfModel::Ct * CfModel::arm * s11 * uj / CfModel::Iyy;
     o[12] += -2 * CfModel::Cd * s12 * uj / CfModel::Izz;
 }
+
+// ---- what the kernels call: the generated model
+CF_DEV void cf_ode(const double *x, const double *u, double *f) { cf_ode_gen(x, u, f); }
+CF_DEV void cf_jvp_x(const double *x, const double *u, const double *d, double *o) { cf_jvp_x_gen(x, u, d, o); }
+CF_DEV void cf_add_ju_col(const double *x, const double *u, int j, double *o) { cf_ju_col_gen(x, u, j, o); }

@@ -314,8 +314,8 @@ struct CfWarp
             for (int i = 0; i < 12; i += 2) { const cf_d2 v = cf_ld2(NOMS + s * 14 + i); xs[i] = v.x; xs[i + 1] = v.y; }
             xs[12] = NOMS[s * 14 + 12];
             double ks[CF_NX];
-            cf_jvp_x(xs, Ss, ks);
-            if (lane < CF_NU) cf_add_ju_col(uu, lane, ks);
+            cf_jvp_x(xs, uu, Ss, ks);
+            if (lane < CF_NU) cf_add_ju_col(xs, uu, lane, ks);
             CF_UNROLL
             for (int i = 0; i < CF_NX; i++) {
                 if (col) Mrow[i * CF_MROWS] += bh * ks[i];

@@ -101,10 +101,10 @@ struct cfnmpc_batch
 
 static void default_params(CfParams &P, int N, double Ts)
 {
-    // generate_c_code.py:61-84 (Q, R), :113 (W_e = 50 Q), :133-134 (0 <= u <= 22)
-    static const double Q[CF_NX] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
-    for (int i = 0; i < CF_NX; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
-    for (int i = 0; i < CF_NU; i++) { P.Wdiag[CF_NX + i] = 0.06; P.lbu[i] = P.lbu0[i] = 0.0; P.ubu[i] = P.ubu0[i] = 22.0; }
+    // generate_c_code.py:61-84 (Q, R), :113 (W_e = 50 Q), :133-134 (0 <= u <= 22), through tools/gen_spec.py
+    for (int i = 0; i < CF_NY; i++) P.Wdiag[i] = CfSpec::W[i];
+    for (int i = 0; i < CF_NX; i++) P.WNdiag[i] = CfSpec::W_e[i];
+    for (int i = 0; i < CF_NU; i++) { P.lbu[i] = P.lbu0[i] = CfSpec::lbu[i]; P.ubu[i] = P.ubu0[i] = CfSpec::ubu[i]; }
     P.Ts = Ts; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = 0; P.pad_ = 0;
 }
 
