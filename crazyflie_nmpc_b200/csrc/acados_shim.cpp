@@ -13,6 +13,9 @@
 
 #include "../../include/acados_solver_crazyflie.h"
 #include "../../include/cfnmpc.h"
+#define CF_DEV static inline   // host-only use of the generated OCP description (defaults below)
+#include "cf_spec_generated.h"
+static_assert(CF_SPEC_N == CRAZYFLIE_N, "include/acados_solver_crazyflie.h and the generated spec disagree on N");
 
 struct crazyflie_solver_capsule
 {
@@ -63,7 +66,7 @@ int crazyflie_acados_free(crazyflie_solver_capsule *c)
 int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int N, double *new_time_steps)
 {
     if (!c || N < 1) return 1;
-    double Ts = 0.75 / 50.0;  // Tf / N of generate_c_code.py:41-42
+    double Ts = CF_SPEC_TF / CF_SPEC_N;  // Tf / N of generate_c_code.py:41-42
     if (new_time_steps) {
         Ts = new_time_steps[0];
         for (int i = 1; i < N; i++)
@@ -83,16 +86,13 @@ int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int
     }
     c->N = N;
     c->Ts = Ts;
-    for (int i = 0; i < 4; i++) { c->lbu[i] = c->lbu0[i] = 0.0; c->ubu[i] = c->ubu0[i] = 22.0; }  // generate_c_code.py:133-134
-    // generate_c_code.py:128-129 reference, :135 x0
-    const double g0 = 9.8066, mq = 33e-3, Ct = 3.25e-4;
-    const double hov = __builtin_sqrt((mq * g0) / (4 * Ct));
-    const double y[17] = {0, 0, 0.5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, hov, hov, hov, hov};
-    c->x0.assign(13, 0.0);
-    c->x0[3] = 1.0;
+    for (int i = 0; i < 4; i++) { c->lbu[i] = c->lbu0[i] = CfSpec::lbu[i]; c->ubu[i] = c->ubu0[i] = CfSpec::ubu[i]; }  // generate_c_code.py:133-134
+    // generate_c_code.py:128-129 reference, :135 x0 (through tools/gen_spec.py)
+    const double *y = CfSpec::yref;
+    c->x0.assign(CfSpec::x0, CfSpec::x0 + 13);
     c->yref.resize((size_t) N * 17);
-    for (int k = 0; k < N; k++) memcpy(&c->yref[(size_t) k * 17], y, sizeof y);
-    c->yref_e.assign(y, y + 13);
+    for (int k = 0; k < N; k++) memcpy(&c->yref[(size_t) k * 17], y, 17 * sizeof(double));
+    c->yref_e.assign(CfSpec::yref_e, CfSpec::yref_e + 13);
     reset_iterate(c);
     c->in_dirty = true;
     c->plan.N = N;
