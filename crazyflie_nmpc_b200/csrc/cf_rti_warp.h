@@ -1,33 +1,34 @@
 // One real-time-iteration SQP step of the Crazyflie OCP executed by ONE WARP for ONE
 // problem instance.  Everything the reference does inside acados_solve() for this OCP:
 //
-//   preparation   ERK4 + forward sensitivities, Gauss-Newton gradient, bound residuals
+//   preparation   ERK4 + forward sensitivities, Gauss-Newton gradient, bound residuals, initial IPM variables
 //                 (acados/acados/ocp_nlp/ocp_nlp_sqp_rti.c:495-542,
 //                  acados/acados/sim/sim_erk_integrator.c:658-731,
 //                  acados/acados/ocp_nlp/ocp_nlp_cost_ls.c:810-916,
 //                  acados/acados/ocp_nlp/ocp_nlp_constraints_bgh.c:1613-1648)
 //   feedback      x0 elimination, Mehrotra predictor-corrector IPM on the stage-wise QP with a
-//                 square-root Riccati factorisation, primal update
+//                 Riccati factorisation, primal update
 //                 (ocp_nlp_sqp_rti.c:545-683, external/hpipm/ocp_qp/x_ocp_qp_red.c:268-455,
 //                  x_ocp_qp_ipm.c:1442-1774,1943-2759, x_ocp_qp_kkt.c:401-762,1108-1292,
 //                  x_ocp_qp_res.c:334-637, ipm_core/x_core_qp_ipm_aux.c:36-457)
 //
 // Mapping.  Stage variables are [u(4); x(13)] -> lanes 0..16; lane 17 carries the extra
-// "gradient / b" row of the (nv+1) x nv square-root Riccati blocks.  Lane r owns ROW r of the
-// stage matrices ([B';A';b'] is 18 x 13, the factor L is 18 x 17).  Stage blocks are staged in
-// shared memory by the TMA bulk-copy engine one stage ahead of the arithmetic (double
-// buffered, mbarrier-tracked); the dense per-stage kernels (TRMM, SYRK, Cholesky, GEMV,
-// TRSV) are short ROLLED loops over shared-memory rows with 128-bit broadcast loads, so the
-// whole warp program stays resident in the instruction caches (a fully unrolled register
-// formulation was 300 KB of SASS and spent half its cycles waiting for instruction fetch,
-// profiles/README.md).  Lanes 18..31 help only in the element-wise passes.
+// "gradient / b" row of the (nv+1) x nv Riccati blocks.  Lane r owns ROW r of the stage matrices
+// ([B';A';b'] is 18 x 13).  Per IPM iteration the warp runs four sweeps over the stages
+// (residual_factorize, forward, backward_rhs, forward); each sweep stages the part of a stage block it
+// needs in shared memory with ONE TMA bulk copy issued one stage ahead of the arithmetic (double
+// buffered, mbarrier-tracked).  Inside a sweep the code is straight-line and branch-free (clamped
+// indices, predicated stores); matrix products of the factorisation are fp64 tensor-core tiles,
+// GEMV-shaped work reads shared-memory rows / columns with 128-bit loads.  Lanes 18..31 help only
+// in element-wise passes and as tensor-core fragment holders.  DESIGN.md section 2 has the full story,
+// profiles/README.md the measurements behind each choice.
 //
 // All stages use the uniform nv = 17 layout: stage 0 keeps 13 decoupled dummy x-variables
 // (its A-rows are zeroed after the x0 elimination folded A0*xbar into b0) and stage N keeps 4
 // decoupled dummy inputs; both stay exactly zero and cost 2/51 of the work.
 //
-// The per-instance working set (linearisation [B';A';b'] 94 KB, factors 72 KB, IPM vectors)
-// does not fit on chip; it lives in a per-warp scratch slot in global memory (L2/HBM).
+// The per-instance working set (51 stage blocks of 590 doubles = 240 KB) does not fit on chip; it
+// lives in a per-warp scratch slot in global memory (L2/HBM).
 #pragma once
 #include "cf_model.h"
 
@@ -152,7 +153,7 @@ static inline
 #define CF_SM_V3 (CF_SM_V2 + 20)
 #define CF_SM_BAR (CF_SM_V3 + 20)              // two mbarriers
 #define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
-#define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1354 doubles = 10832 bytes per warp (4 blocks of 4 warps per SM)
+#define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1354 doubles = 10832 bytes per warp
 static_assert(CF_SM_DOUBLES % 2 == 0, "every warp's shared-memory slice must start on a 16-byte boundary");
 static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && 18 * CF_ALST <= CF_SM_BUFSZ,
               "staging buffers");
