@@ -427,6 +427,20 @@ struct CfWarp
         // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
         const int fg = lane >> 2, fq = lane & 3;
         const int rl = lane < CF_MROWS ? lane : 17;
+        // P_{k+1} is kept in shared memory as the lower triangle of a 13 x 20 array, row = state index, column = the
+        // state's index among the stage variables (4 + state index): exactly where the Schur-complement tiles fall, so
+        // they are stored as whole tiles; the fragment loads of the next stage's first product swap indices instead
+        // (addresses are loop-invariant): pa[kk][h] = address of P[4kk+fq][8h+fg]
+        int pa[4][2];
+        CF_UNROLL
+        for (int kk = 0; kk < 4; kk++)
+            CF_UNROLL
+            for (int hh = 0; hh < 2; hh++) {
+                const int i = 4 * kk + fq, j = 8 * hh + fg;
+                const bool ok = i < CF_NX && j < CF_NX;
+                const int hi = i > j ? i : j, lo = i > j ? j : i;
+                pa[kk][hh] = ok ? hi * CF_ALST + lo + CF_NU : -1;
+            }
         double ux_next = 0.0;   // lanes 4..16: x-part of ux_{k+1} (new iterate)
         double pi_k = 0.0;      // lanes 4..16: pi_k (new iterate), read from the record of stage k+1
         CF_NOUNROLL
@@ -517,7 +531,7 @@ struct CfWarp
                 cf_syncwarp();
                 const double hN = HN + CF_REG_PRIM;
                 if (xl) {
-                    PS[ci * CF_ALST + ci] = hN;
+                    PS[ci * CF_ALST + ci + CF_NU] = hN;
                     PV[ci] = rg;
                     PXN[cf_tri(ci) + ci] = hN;
                     rk[R_DUX + lane] = rg;   // p_N for the forward sweep
@@ -537,9 +551,8 @@ struct CfWarp
             for (int kk = 0; kk < 4; kk++) {
                 const int kc = 4 * kk + fq;
                 const bool kv = kc < CF_NX;
-                const double *Pk = PS + (kv ? kc : 0) * CF_ALST;
-                const double b0 = kv ? Pk[fg] : 0.0;                          // P[kc][fg]
-                const double b1 = (kv && fg < CF_NX - 8) ? Pk[8 + fg] : 0.0;  // P[kc][8+fg]
+                const double b0 = pa[kk][0] >= 0 ? PS[pa[kk][0]] : 0.0;   // P[kc][fg]
+                const double b1 = pa[kk][1] >= 0 ? PS[pa[kk][1]] : 0.0;   // P[kc][8+fg]
                 CF_UNROLL
                 for (int t = 0; t < 3; t++) {
                     const int r = 8 * t + fg;
@@ -649,19 +662,27 @@ struct CfWarp
                     CF_UNROLL
                     for (int tp = 0; tp <= t; tp++) {
                         cf_dmma(sx[t][tp][0], sx[t][tp][1], -la[t], la[tp]);
-                        const int r = 8 * t + fg;
-                        CF_UNROLL
-                        for (int e = 0; e < 2; e++) {
-                            // flat predicates (predicated stores, no nested branches): element (r, c) of the Schur complement
-                            const int c = 8 * tp + 2 * fq + e;
-                            const double val = sx[t][tp][e];
-                            const bool cx = c >= CF_NU && c < CF_NV;
-                            const int jx = cx ? c - CF_NU : 0, ix = (r >= CF_NU && r < CF_NV) ? r - CF_NU : 0;
-                            const bool isP = cx && r >= c && r < CF_NV;   // P_k, lower part (mirrored on the fly)
-                            const bool isp = cx && r == 17;               // p_k
-                            if (isP) { PS[ix * CF_ALST + jx] = val; PS[jx * CF_ALST + ix] = val; }
-                            if (isP && k > 0) LFk[cf_tri(ix) + jx] = val;
-                            if (isp) { PV[jx] = val; rk[R_DUX + CF_NU + jx] = val; }
+                        const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
+                        // P_k: whole tile rows into the shared-memory array (positions above the diagonal or in the input
+                        // columns are never read); the last tile has a single valid element (16,16)
+                        const bool xrow = r >= CF_NU && r < CF_NV;
+                        if (tp < 2) { if (xrow) cf_st2(PS + (r - CF_NU) * CF_ALST + c0, sx[t][tp][0], sx[t][tp][1]); }
+                        else if (r == 16 && fq == 0) PS[12 * CF_ALST + 16] = sx[t][tp][0];
+                        // p_k (row 17) for the next stage and for the forward sweep
+                        if (t == 2 && r == 17) {
+                            CF_UNROLL
+                            for (int e = 0; e < 2; e++) {
+                                const int c = c0 + e;
+                                if (c >= CF_NU && c < CF_NV) { PV[c - CF_NU] = sx[t][tp][e]; rk[R_DUX + c] = sx[t][tp][e]; }
+                            }
+                        }
+                        // packed lower triangle to the block of stage k-1
+                        if (k > 0 && xrow) {
+                            CF_UNROLL
+                            for (int e = 0; e < 2; e++) {
+                                const int c = c0 + e;
+                                if (c >= CF_NU && c <= r) LFk[cf_tri(r - CF_NU) + c - CF_NU] = sx[t][tp][e];
+                            }
                         }
                     }
                 }
