@@ -725,7 +725,9 @@ struct CfWarp
     // step length ingredients (:146-216) and the inf-norms of the linear-system residual (OCP_QP_RES_COMPUTE_LIN,
     // x_ocp_qp_res.c:474-598) on the fly.  Branch-free: every lane computes with clamped indices (lanes with equal
     // lane & 3 hold identical input/bound quantities), stores and norm contributions are predicated.
-    CF_MEM void forward()
+    // `need_pi`: the multiplier step dpi is only consumed by the variable update (and by the optional linear-residual
+    // check), never by the corrector -- the affine (predictor) solve skips it together with the P_{k+1} it would read.
+    CF_MEM void forward(const bool need_pi_)
     {
         double *XS = sm + CF_SM_V0, *DS = sm + CF_SM_V1, *PS = sm + CF_SM_V3;
         // running step lengths to the boundary kept as ratios num/den (den < 0): alpha = min(1, min -lam/dlam, -t/dt)
@@ -733,14 +735,15 @@ struct CfWarp
         double lg = 0, lb = 0, ld = 0, lm = 0;    // linear residual norms
         double dxk = 0.0;        // lanes 4..16: dx_k ; stage 0 has none
         double dpi_prev = 0.0;   // lanes 4..16: dpi_{k-1}
-        const int VO = R_LAM, VN = CF_SB - R_LAM;   // staged part of the stage block: [R_LAM, end)
+        const bool chk = PG->lin_res_check != 0;   // the reference's linear-system residual checks (diagnostic flags only)
+        const bool need_pi = need_pi_ || chk;
+        const int VO = R_LAM, VN = (need_pi ? CF_SB : B_PX) - R_LAM;   // staged part of the stage block: [R_LAM, end | B_PX)
         pass_begin();
         if (N > 0) fetch(0, 0, VO, VN);
         if (lane < 20) { XS[lane] = 0.0; PS[lane] = 0.0; }
         const bool ul = lane < CF_NU, vl = lane < CF_NV;
         const bool xl = lane >= CF_NU && vl;
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
-        const bool chk = PG->lin_res_check != 0;   // the reference's linear-system residual checks (diagnostic flags only)
         // P_{k+1} travels packed (lower triangle) and is expanded to full symmetric rows in shared memory: element
         // e = lane + 32 t of the packed triangle goes to (i,j) and (j,i)
         double *PE = sm + CF_SM_P;
@@ -759,18 +762,20 @@ struct CfWarp
         for (int k = 0; k < N; k++) {
             const int bf = k & 1;
             double *rk = rec(k);
-            const double pnext = rec(k + 1)[R_DUX + lv];  // p_{k+1} left by the backward sweep (x lanes)
+            const double pnext = need_pi ? rec(k + 1)[R_DUX + lv] : 0.0;  // p_{k+1} left by the backward sweep (x lanes)
             wait(bf);
             cf_syncwarp();  // every lane is done with buffer bf^1 and with the expanded P of the previous stage
             if (k + 1 < N) fetch(bf ^ 1, k + 1, VO, VN);
             const double *VS = buf(bf) - VO;   // VS[offset within the stage block]
             const double *Mk = VS + B_M, *LU = VS + B_LU, *LX = PE;
-            CF_UNROLL
-            for (int t = 0; t < 3; t++) {
-                if (pe_a[t] >= 0) {
-                    const double v = VS[B_PX + lane + 32 * t];
-                    PE[pe_a[t]] = v;
-                    PE[pe_b[t]] = v;
+            if (need_pi) {   // warp-uniform
+                CF_UNROLL
+                for (int t = 0; t < 3; t++) {
+                    if (pe_a[t] >= 0) {
+                        const double v = VS[B_PX + lane + 32 * t];
+                        PE[pe_a[t]] = v;
+                        PE[pe_b[t]] = v;
+                    }
                 }
             }
             // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu); input l4 on every lane
@@ -849,10 +854,10 @@ struct CfWarp
                 if (chk) cf_amax(lb, xl ? (rbk - dxn) + sacc : 0.0);
                 if (xl) XS[ci] = dxn;
             }
+            double dpik = 0.0;
+            if (need_pi) {   // warp-uniform
             cf_syncwarp();
             // ---- dpi = P_{k+1} dx+ + p_{k+1}   (GEMV_N :712,729)
-            double dpik;
-            {
                 const double *Li = LX + ci * CF_PST;   // row ci of the symmetric P_{k+1}
                 double z0 = pnext, z1 = 0.0;
                 CF_UNROLL
@@ -1033,7 +1038,7 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters, unsigned long long *prof)
             st = ST_FWD;
         } else if (st == ST_FWD) {
             CF_PROF_BEGIN();
-            w.forward();
+            w.forward(!predictor);
             CF_PROF_END(CF_PROF_FWD);
             if (predictor) {
                 if (!w.lin_res_ok_fact()) w.flags |= CF_FLAG_LIN_RES_FACT;
