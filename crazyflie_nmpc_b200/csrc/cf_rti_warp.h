@@ -801,7 +801,7 @@ struct CfWarp
                 v = (l4 < j) ? vn : v;
             }
             const double duxk = ul ? du : dxk;  // lane r: dux_k[r]
-            if (vl) rk[R_DUX + lane] = duxk;
+            if (vl && need_pi) rk[R_DUX + lane] = duxk;   // the affine primal step itself is never read again
             // ---- dlam, dt, alpha for the bounds of input l4
             double dlam_l, dlam_u;
             {
@@ -889,7 +889,7 @@ struct CfWarp
         // terminal stage: no inputs, no bounds, no dynamics
         if (vl) {
             const double duxN = ul ? 0.0 : dxk;
-            rec(N)[R_DUX + lane] = duxN;
+            if (need_pi) rec(N)[R_DUX + lane] = duxN;
             if (chk) cf_amax(lg, HN * duxN + rec(N)[R_RESG + lane] - dpi_prev);
         }
         if (chk) { lin[0] = cf_warp_max(lg); lin[1] = cf_warp_max(lb); lin[2] = cf_warp_max(ld); lin[3] = cf_warp_max(lm); }
