@@ -966,16 +966,22 @@ struct CfWarp
         const int e = lane & 7;
         int k = lane >> 3;
         CF_NOUNROLL
-        for (; k + 4 < N; k += 8) {   // two stages per trip: eight independent loads in flight per lane
-            const double *ra = rec(k), *rb = rec(k + 4);
-            const double la = ra[R_LAM + e], da = ra[R_DLAM + e], ta = ra[R_T + e], ua = ra[R_DT + e];
-            const double lb = rb[R_LAM + e], db = rb[R_DLAM + e], tb = rb[R_T + e], ub = rb[R_DT + e];
-            s0 += (la + alpha * da) * (ta + alpha * ua);
-            s1 += (lb + alpha * db) * (tb + alpha * ub);
-            cf_amax(pm, (la + aa * da) * (ta + aa * ua));
-            cf_amax(pm, (lb + aa * db) * (tb + aa * ub));
+        for (; k + 12 < N; k += 16) {   // four stages per trip: sixteen independent loads in flight per lane
+            double l[4], d[4], t[4], u[4];
+            CF_UNROLL
+            for (int q = 0; q < 4; q++) {
+                const double *r = rec(k + 4 * q);
+                l[q] = r[R_LAM + e]; d[q] = r[R_DLAM + e]; t[q] = r[R_T + e]; u[q] = r[R_DT + e];
+            }
+            CF_UNROLL
+            for (int q = 0; q < 4; q++) {
+                if (q & 1) s1 += (l[q] + alpha * d[q]) * (t[q] + alpha * u[q]);
+                else s0 += (l[q] + alpha * d[q]) * (t[q] + alpha * u[q]);
+                cf_amax(pm, (l[q] + aa * d[q]) * (t[q] + aa * u[q]));
+            }
         }
-        if (k < N) {
+        CF_NOUNROLL
+        for (; k < N; k += 4) {
             const double *ra = rec(k);
             const double la = ra[R_LAM + e], da = ra[R_DLAM + e], ta = ra[R_T + e], ua = ra[R_DT + e];
             s0 += (la + alpha * da) * (ta + alpha * ua);
