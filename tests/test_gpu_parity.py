@@ -28,7 +28,7 @@ def gpu_solve(w, N, n_rti=1, **params):
         s.set_problem(w).solve(n_rti)
         out = dict(x=s.get("x_all"), u=s.get("u_all"), status=s.get("status"), qp_iter=s.get("qp_iter"),
                    qp_status=s.get("qp_status"), flags=s.get("flags"), res=s.get("res"),
-                   u0=s.get("u", 0), u1=s.get("u", 1), x4=s.get("x", 4))
+                   u0=s.get("u", 0), u1=s.get("u", min(1, N - 1)), x4=s.get("x", min(4, N)))
     return out
 
 
@@ -45,8 +45,9 @@ def check(g, o, tight=TIGHT):
     assert ex <= tight and eu <= tight, ("numerics drifted", ex, eu)
     assert np.abs(g["qp_iter"] - o["qp_iter"]).max() <= 1
     # the node reads u0, u1, x4 (acados_mpc.cpp:619-625)
-    assert np.array_equal(g["u0"], g["u"][:, 0]) and np.array_equal(g["u1"], g["u"][:, 1])
-    assert np.array_equal(g["x4"], g["x"][:, 4])
+    n = g["u"].shape[1]
+    assert np.array_equal(g["u0"], g["u"][:, 0]) and np.array_equal(g["u1"], g["u"][:, min(1, n - 1)])
+    assert np.array_equal(g["x4"], g["x"][:, min(4, n)])
 
 
 @pytest.mark.parametrize("gen", [wl.hover_batch, wl.helix_batch])
@@ -215,6 +216,31 @@ def test_lin_res_check_is_diagnostic_only():
             out.append((s.get("x_all"), s.get("u_all"), s.get("qp_iter"), s.get("flags")))
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert np.array_equal(out[0][2], out[1][2]) and (out[0][3] == 0).all() and (out[1][3] == 0).all()
+
+
+def test_tiny_horizons(port):
+    for N in (1, 2, 3, 5):
+        w = wl.hover_batch(7, N, seed=40 + N)
+        check(gpu_solve(w, N), oracle_solve(port, w, N))
+
+
+def test_nan_input_is_reported_not_propagated(port, ref):
+    """A NaN measurement: the reference reports ACADOS_QP_FAILURE (HPIPM status 3 -> ocp_nlp_sqp_rti.c:651-664) and leaves
+    the iterate untouched; so must we, and the neighbouring instances must not be affected."""
+    N, B = 20, 9
+    w = wl.hover_batch(B, N, seed=77)
+    w["x0"][4, 2] = np.nan
+    g, o = gpu_solve(w, N), oracle_solve(port, w, N)
+    assert g["status"][4] == cf.ACADOS_QP_FAILURE == o["status"][4] and g["qp_status"][4] == 3
+    assert np.array_equal(g["x"][4], w["x_init"][4]) and np.array_equal(g["u"][4], w["u_init"][4])
+    ok = np.arange(B) != 4
+    assert (g["status"][ok] == 0).all()
+    assert rel_err(g["x"][ok], o["x"][ok]) <= TIGHT and rel_err(g["u"][ok], o["u"][ok]) <= TIGHT
+    x, u = w["x_init"][4].copy(), w["u_init"][4].copy()
+    s = ref.solver(N, TS)
+    st, _, qs, _ = s.rti(w["x0"][4], w["yref"][4], w["yref_e"][4], x, u)
+    s.close()
+    assert st == cf.ACADOS_QP_FAILURE and np.array_equal(x, w["x_init"][4])
 
 
 def test_ragged_and_tiny_batches(port):

@@ -134,3 +134,19 @@ def test_emulated_kernel_per_instance_parameters(emu, port, ref):
         x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
         port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u, params=port.params(lbu0=pp["lbu0"][i], ubu0=pp["ubu0"][i]))
         assert rel_err(r2["x"][i], x) < 1e-9 and rel_err(r2["u"][i], u) < 1e-9
+
+
+def test_emulated_kernel_nan_measurement(emu, port):
+    """A NaN in x0: status ACADOS_QP_FAILURE (4), HPIPM status 3 after one iteration, iterate untouched -- as the
+    reference does (ocp_nlp_sqp_rti.c:651-664, x_ocp_qp_ipm.c:2723-2750); other instances unaffected."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    N, B = 20, 5
+    w = wl.hover_batch(B, N, seed=77)
+    w["x0"][2, 2] = np.nan
+    r = emu(w, N)
+    x, u = w["x_init"].copy(), w["u_init"].copy()
+    st, it = port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u)
+    assert (r["status"] == st).all() and r["status"][2] == 4 and r["qp_status"][2] == 3 and r["qp_iter"][2] == it[2]
+    assert np.array_equal(r["x"][2], w["x_init"][2]) and np.array_equal(r["u"][2], w["u_init"][2])
+    ok = np.arange(B) != 2
+    assert rel_err(r["x"][ok], x[ok]) < 1e-9 and rel_err(r["u"][ok], u[ok]) < 1e-9
