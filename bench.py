@@ -104,14 +104,14 @@ def cpu_solver():
     if orc.ref_available():
         ref = orc.Ref()
 
-        def run(N, w, nthreads):
+        def run(N, w, nthreads, cond_N=0):
             x, u = w["x_init"].copy(), w["u_init"].copy()
-            st, it, tt = ref.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u, nthreads=nthreads)
+            st, it, tt = ref.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u, nthreads=nthreads, cond_N=cond_N)
             return x, u, st, float(tt.sum())
         return run, "reference"
     port = orc.Port()
 
-    def run(N, w, nthreads):
+    def run(N, w, nthreads, cond_N=0):
         x, u = w["x_init"].copy(), w["u_init"].copy()
         st, it = port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], x, u)
         return x, u, st, float("nan")
@@ -126,10 +126,22 @@ def time_cpu(N, workload, sample, nthreads, seed):
     t0 = time.perf_counter()
     _, _, st, t_own = run(N, w, nthreads)
     dt = time.perf_counter() - t0
-    return dict(value=sample / dt, unit=UNIT, cores=nthreads, kind=kind,
-                sample=f"{sample} seeded instances of the same workload, one RTI step each, wall clock over {nthreads} host threads"
-                       + (f"; acados' own time_tot sums to {t_own / sample * 1e3:.3f} ms/solve/core" if t_own == t_own else ""),
-                failures=int((st != 0).sum()))
+    out = dict(value=sample / dt, unit=UNIT, cores=nthreads, kind=kind,
+               sample=f"{sample} seeded instances of the same workload, one RTI step each, wall clock over {nthreads} host threads"
+                      + (f"; acados' own time_tot sums to {t_own / sample * 1e3:.3f} ms/solve/core" if t_own == t_own else ""),
+               failures=int((st != 0).sum()))
+    if kind == "reference" and N % 10 == 0:
+        # fair to the reference: the same solver with real partial condensing, which the reference's own
+        # configuration (qp_cond_N = N) does not use; `value` above stays the reference's configuration
+        best = None
+        for cn in (N // 5, N // 10):
+            t0 = time.perf_counter()
+            run(N, w, nthreads, cond_N=cn)
+            v = sample / (time.perf_counter() - t0)
+            if best is None or v > best[1]:
+                best = (cn, v)
+        out["with_partial_condensing"] = dict(qp_cond_N=best[0], value=best[1], unit=UNIT)
+    return out
 
 
 def run_reference(args):
