@@ -65,3 +65,28 @@ def test_python_mirror_rejects_bad_fields_before_touching_the_device():
         cf.BatchSolver.set(s, "x0", np.zeros(5))
     with pytest.raises(cf.CfnmpcError):
         cf.BatchSolver.get(s, "nonsense")
+
+
+def test_headers_compile_as_c99_and_cxx11(tmp_path):
+    """The boundary is a C ABI: every shipped header must be usable from plain C (and from C++11, the node's dialect)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text("""
+#include "cfnmpc.h"
+#include "acados_solver_crazyflie.h"
+#include "acados_sim_solver_crazyflie.h"
+#include "acados_c/ocp_nlp_interface.h"
+#include "acados_c/sim_interface.h"
+#include "acados_c/external_function_interface.h"
+#include "acados/utils/print.h"
+#include "acados/utils/types.h"
+#include "acados/ocp_nlp/ocp_nlp_constraints_bgh.h"
+#include "acados/ocp_nlp/ocp_nlp_cost_ls.h"
+#include "blasfeo/include/blasfeo_d_aux.h"
+#include "blasfeo/include/blasfeo_d_aux_ext_dep.h"
+#include "crazyflie_model/crazyflie_model.h"
+int main(void) { return CFNMPC_OK + CRAZYFLIE_N - 50; }
+""")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o", str(tmp_path / "a.o")], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I", inc, "-x", "c++", "-c", str(src), "-o", str(tmp_path / "b.o")], check=True)
