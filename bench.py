@@ -210,9 +210,8 @@ def run_ours(args):
 
     def step_e2e():
         # what a caller of the reference API does per tick, with host buffers: x0 + yref in, u0 + status out
-        s.set("x0", pin["x0"]).set("yref", pin["yref"]).set("yref_e", pin["yref_e"])
         s.set("x", d_in["x_init"]).set("u", d_in["u_init"])
-        s.solve(1)
+        s.solve_from_host(pin["x0"], pin["yref"], pin["yref_e"], n_chunks=args.e2e_chunks)   # upload overlapped with the solve
         s.get("u", 0, out=u0_dev)
         u0_host.copy_(u0_dev, non_blocking=True)
         s.get("status", 0, out=st_host)   # host destination: synchronises the stream
@@ -330,7 +329,7 @@ def run_ours(args):
                                 occupancy=dict(warps_per_sm=s.info("blocks_per_sm") * s.info("warps_per_block"), regs=s.info("regs_per_thread"),
                                                grid=s.info("grid"))),
                     clocks=clocks, e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                                            ms_per_step=ms_e2e / args.steps),
+                                            ms_per_step=ms_e2e / args.steps, upload_chunks=args.e2e_chunks),
                     e2e_closed_loop=dict(value=world * B / (ms_tick / args.steps * 1e-3), unit=UNIT, ms_per_step=ms_tick / args.steps,
                                          h2d_bytes_per_step=pin["x0"].numel() * 8,
                                          d2h_bytes_per_step=motors_host.numel() * 4 + twist_host.numel() * 8,
@@ -357,6 +356,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--ref-sample", type=int, default=0, help="instances per CPU step (default: scaled to the core count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks of the overlapped host-to-device upload in the e2e path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

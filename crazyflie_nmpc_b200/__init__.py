@@ -46,6 +46,7 @@ def lib():
         L.cfnmpc_batch_set_option.argtypes = [vp, cp, ci]
         L.cfnmpc_batch_solve.argtypes = [vp, ci]
         L.cfnmpc_batch_sync.argtypes = [vp]
+        L.cfnmpc_batch_solve_from_host.argtypes = [vp, vp, vp, vp, ci]
         L.cfnmpc_batch_get.argtypes = [vp, cp, ci, vp, ci]
         L.cfnmpc_batch_device_ptr.argtypes = [vp, cp, ctypes.POINTER(vp)]
         L.cfnmpc_batch_info.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_longlong)]
@@ -168,6 +169,24 @@ class BatchSolver:
 
     def solve(self, n_rti=1):
         _check(lib().cfnmpc_batch_solve(self._h, int(n_rti)))
+        return self
+
+    def solve_from_host(self, x0, yref, yref_e, n_chunks=4):
+        """One tick from host buffers (numpy arrays or pinned torch CPU tensors): chunked upload overlapped with the solve."""
+        ptrs = []
+        for a, n in ((x0, self.B * NX), (yref, self.B * self.N * NY), (yref_e, self.B * NX)):
+            if hasattr(a, "data_ptr"):
+                if a.is_cuda or a.numel() != n or a.element_size() != 8:
+                    raise CfnmpcError("solve_from_host needs float64 host tensors of the batch shapes")
+            else:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                if a.size != n:
+                    raise CfnmpcError("solve_from_host: wrong array size")
+            ptrs.append(_ptr(a))
+        _check(lib().cfnmpc_batch_solve_from_host(self._h, ctypes.c_void_p(ptrs[0][0]), ctypes.c_void_p(ptrs[1][0]),
+                                                  ctypes.c_void_p(ptrs[2][0]), int(n_chunks)))
+        if not all(hasattr(p[2], "is_pinned") and p[2].is_pinned() for p in ptrs):
+            self.sync()  # pageable host memory: the copies must be complete before the caller may reuse the buffers
         return self
 
     def sync(self):

@@ -96,7 +96,10 @@ static_assert(sizeof(CfParams) == CF_PAR_DOUBLES * 8, "CfParams layout");
 
 struct CfBatchView
 {
-    int B;
+    int B;                 // instances this launch solves: [first, first + B)
+    int first;
+    const int *ready;      // null, or a device counter: only instances < *ready have their inputs in place (host-fed ticks
+                           // whose upload overlaps the solve, cfnmpc_batch_solve_from_host)
     const double *x0;      // [B][13]
     const double *yref;    // [B][N][17]
     const double *yref_e;  // [B][13]

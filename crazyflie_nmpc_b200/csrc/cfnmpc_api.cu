@@ -34,7 +34,19 @@ __device__ __forceinline__ void cf_rti_kernel_body(const CfParams &P, const CfBa
         if ((threadIdx.x & 31) == 0) inst = atomicAdd(bv.counter, 1);
         inst = __shfl_sync(0xffffffffu, inst, 0);
         if (inst >= bv.B) break;
-        cf_rti_instance(&P, bv, inst, slot, sm, par);
+        if (bv.ready) {
+            // inputs of this instance may still be on their way from the host: wait for the upload front to pass it
+            if ((threadIdx.x & 31) == 0) {
+                int r;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(r) : "l"(bv.ready) : "memory");
+                    if (r > inst) break;
+                    __nanosleep(500);
+                }
+            }
+            __syncwarp();
+        }
+        cf_rti_instance(&P, bv, bv.first + inst, slot, sm, par);
     }
 }
 template <int WPB, int MINB>
@@ -80,8 +92,9 @@ struct cfnmpc_batch
     int B = 0, N = 0, device = 0;
     CfParams P;
     CfBatchView bv;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_free = nullptr;
+    int *d_ready = nullptr, *h_ready = nullptr;   // upload front of cfnmpc_batch_solve_from_host (device counter, pinned staging)
     double *d_x0 = nullptr, *d_yref = nullptr, *d_yref_e = nullptr, *d_x = nullptr, *d_u = nullptr, *d_res = nullptr;
     double *d_scratch = nullptr, *d_stage = nullptr;
     // closed-loop driver state (cf_loop_kernels.h)
@@ -122,6 +135,10 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_free) cudaEventDestroy(h->ev_free);
+    if (h->d_ready) cudaFree(h->d_ready);
+    if (h->h_ready) cudaFreeHost(h->h_ready);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return CFNMPC_OK;
@@ -224,7 +241,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
         h->launches++;
     }
     CfBatchView &bv = h->bv;
-    bv.B = batch; bv.x0 = h->d_x0; bv.yref = h->d_yref; bv.yref_e = h->d_yref_e; bv.x = h->d_x; bv.u = h->d_u;
+    bv.B = batch; bv.first = 0; bv.ready = nullptr; bv.x0 = h->d_x0; bv.yref = h->d_yref; bv.yref_e = h->d_yref_e; bv.x = h->d_x; bv.u = h->d_u;
     bv.status = h->d_status; bv.qp_iter = h->d_qp_iter; bv.qp_status = h->d_qp_status; bv.flags = h->d_flags;
     bv.res = h->d_res; bv.scratch = h->d_scratch; bv.scratch_stride = stride; bv.counter = h->d_counter;
     bv.W_b = bv.WN_b = bv.lbu_b = bv.ubu_b = bv.lbu0_b = bv.ubu0_b = nullptr;
@@ -363,6 +380,59 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
     }
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
+    return CFNMPC_OK;
+}
+
+// One control tick fed from HOST buffers: ONE launch of the persistent kernel starts at once; the inputs (x0, yref,
+// yref_e) follow in n_chunks contiguous chunks on a second stream, each chunk followed by a 4-byte copy that advances
+// the device-side "upload front"; a warp that pulls an instance beyond the front waits for it.  Upload and solve overlap
+// without the per-launch tails that chunked launches would add.
+#define CF_MAX_CHUNKS 32
+extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, const double *yref, const double *yref_e, int n_chunks)
+{
+    if (!h || !x0 || !yref || !yref_e) return fail(CFNMPC_EINVAL, "cfnmpc_batch_solve_from_host: null argument");
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > CF_MAX_CHUNKS) n_chunks = CF_MAX_CHUNKS;
+    if (n_chunks > h->B) n_chunks = h->B;
+    CK(cudaSetDevice(h->device));
+    if (!h->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
+        CK(cudaMalloc(&h->d_ready, 4));
+        CK(cudaHostAlloc(&h->h_ready, CF_MAX_CHUNKS * sizeof(int), cudaHostAllocDefault));
+    }
+    // the staging counters of the previous call must have been consumed before they are rewritten
+    CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaMemsetAsync(h->d_ready, 0, 4, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+    // the copies may only overwrite the inputs once everything enqueued so far on the solve stream is done with them
+    CK(cudaEventRecord(h->ev_free, h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
+    CfBatchView bv = h->bv;
+    bv.ready = h->d_ready;
+    h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, bv);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    const size_t N = h->N;
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < n_chunks && e == cudaSuccess; c++) {
+        const size_t first = (size_t) h->B * c / n_chunks, last = (size_t) h->B * (c + 1) / n_chunks, cnt = last - first;
+        e = cudaMemcpyAsync(h->d_x0 + first * CF_NX, x0 + first * CF_NX, cnt * CF_NX * 8, cudaMemcpyHostToDevice, h->copy_stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h->d_yref + first * N * CF_NY, yref + first * N * CF_NY, cnt * N * CF_NY * 8, cudaMemcpyHostToDevice, h->copy_stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h->d_yref_e + first * CF_NX, yref_e + first * CF_NX, cnt * CF_NX * 8, cudaMemcpyHostToDevice, h->copy_stream);
+        h->h_ready[c] = (int) last;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_ready, h->h_ready + c, 4, cudaMemcpyHostToDevice, h->copy_stream);
+    }
+    if (e != cudaSuccess) {
+        // never leave the running kernel waiting for inputs that will not come: open the front completely
+        cudaMemsetAsync(h->d_ready, 0x7f, 4, h->copy_stream);
+        return fail(CFNMPC_ECUDA, std::string("cfnmpc_batch_solve_from_host: upload failed: ") + cudaGetErrorString(e));
+    }
     return CFNMPC_OK;
 }
 

@@ -101,6 +101,13 @@ int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int value);
  * getter to a host pointer. */
 int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti);
 int cfnmpc_batch_sync(cfnmpc_batch *h);
+/* One tick fed from HOST buffers (pinned memory for real overlap): equivalent to cfnmpc_batch_set of "x0", "yref",
+ * "yref_e" followed by cfnmpc_batch_solve(h, 1), but the solve kernel starts at once and the inputs follow in n_chunks
+ * (1..32) contiguous chunks on a second stream; a warp that reaches an instance whose inputs have not arrived yet waits
+ * for the upload front.  This is the batched form of the node's per-tick ocp_nlp_constraints_model_set /
+ * ocp_nlp_cost_model_set / acados_solve sequence (acados_mpc.cpp:581-611).  Getters on the handle's stream see the
+ * results as after cfnmpc_batch_solve. */
+int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, const double *yref, const double *yref_e, int n_chunks);
 
 /* Copy results out.  Fields:
  *   "u"        stage k in [0,N)   double [B][4]

@@ -253,7 +253,7 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
     P.lin_res_check = 1; P.pad_ = 0;
     const long stride = cf_scratch_layout(N).total;
     CfBatchView bv;
-    bv.B = B; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
+    bv.B = B; bv.first = 0; bv.ready = nullptr; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
     bv.qp_iter = qp_iter; bv.qp_status = qp_status; bv.flags = flags; bv.res = res; bv.scratch = nullptr;
     bv.scratch_stride = stride; bv.counter = nullptr;
     bv.W_b = per_inst ? per_inst[0] : nullptr; bv.WN_b = per_inst ? per_inst[1] : nullptr;

@@ -243,6 +243,23 @@ def test_nan_input_is_reported_not_propagated(port, ref):
     assert st == cf.ACADOS_QP_FAILURE and np.array_equal(x, w["x_init"][4])
 
 
+def test_solve_from_host_chunks_match_plain_solve():
+    """The chunked, upload-overlapped tick (cfnmpc_batch_solve_from_host) gives bit-identical results."""
+    torch = pytest.importorskip("torch")
+    N, B = 20, 1001
+    w = wl.helix_batch(B, N, seed=3)
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_problem(w).solve(1)
+        x_ref, u_ref, st_ref = s.get("x_all"), s.get("u_all"), s.get("status")
+        for chunks, pinned in ((1, False), (3, True), (8, True), (50, False)):
+            host = [torch.from_numpy(w[k]).pin_memory() if pinned else w[k] for k in ("x0", "yref", "yref_e")]
+            s.set("x0", np.zeros_like(w["x0"])).set("yref", np.zeros_like(w["yref"])).set("yref_e", np.zeros_like(w["yref_e"]))
+            s.set("x", w["x_init"]).set("u", w["u_init"])
+            s.solve_from_host(*host, n_chunks=chunks)
+            assert np.array_equal(s.get("x_all"), x_ref) and np.array_equal(s.get("u_all"), u_ref)
+            assert np.array_equal(s.get("status"), st_ref)
+
+
 def test_ragged_and_tiny_batches(port):
     N = 20
     for B in (1, 3, 5, 33):
