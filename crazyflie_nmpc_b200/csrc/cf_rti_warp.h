@@ -78,6 +78,7 @@ static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 &&
 // flag bits OR-ed into the per-instance `flags` output (not part of the reference API)
 #define CF_FLAG_LIN_RES_FACT 1   // reference would have switched to the LQ factorisation (x_ocp_qp_ipm.c:2029-2059)
 #define CF_FLAG_LIN_RES_CORR 2   // reference would have run iterative refinement (:2311-2318)
+#define CF_FLAG_INPUT_LATE 4     // host-fed tick: the inputs of this instance had not arrived after 5 s (solved with stale data)
 
 struct CfParams
 {

@@ -36,15 +36,25 @@ __device__ __forceinline__ void cf_rti_kernel_body(const CfParams &P, const CfBa
         if (inst >= bv.B) break;
         if (bv.ready) {
             // inputs of this instance may still be on their way from the host: wait for the upload front to pass it
+            // (bounded: under a profiler that replays the kernel without the copies, or if the host died, give up after
+            // 5 s and mark the instance instead of hanging the device)
+            int late = 0;
             if ((threadIdx.x & 31) == 0) {
                 int r;
+                unsigned long long t0 = 0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                 for (;;) {
                     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(r) : "l"(bv.ready) : "memory");
                     if (r > inst) break;
                     __nanosleep(500);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 5000000000ull) { late = 1; break; }
                 }
             }
-            __syncwarp();
+            late = __shfl_sync(0xffffffffu, late, 0);
+            cf_rti_instance(&P, bv, bv.first + inst, slot, sm, par);
+            if (late && (threadIdx.x & 31) == 0) bv.flags[bv.first + inst] |= CF_FLAG_INPUT_LATE;
+            continue;
         }
         cf_rti_instance(&P, bv, bv.first + inst, slot, sm, par);
     }
@@ -409,13 +419,6 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
     // the copies may only overwrite the inputs once everything enqueued so far on the solve stream is done with them
     CK(cudaEventRecord(h->ev_free, h->stream));
     CK(cudaStreamWaitEvent(h->copy_stream, h->ev_free, 0));
-    CfBatchView bv = h->bv;
-    bv.ready = h->d_ready;
-    h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, bv);
-    CK(cudaGetLastError());
-    h->launches++;
-    CK(cudaEventRecord(h->ev1, h->stream));
-    h->timed = true;
     const size_t N = h->N;
     cudaError_t e = cudaSuccess;
     for (int c = 0; c < n_chunks && e == cudaSuccess; c++) {
@@ -428,11 +431,16 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
         h->h_ready[c] = (int) last;
         if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_ready, h->h_ready + c, 4, cudaMemcpyHostToDevice, h->copy_stream);
     }
-    if (e != cudaSuccess) {
-        // never leave the running kernel waiting for inputs that will not come: open the front completely
-        cudaMemsetAsync(h->d_ready, 0x7f, 4, h->copy_stream);
+    if (e != cudaSuccess)
         return fail(CFNMPC_ECUDA, std::string("cfnmpc_batch_solve_from_host: upload failed: ") + cudaGetErrorString(e));
-    }
+    // the copies are enqueued BEFORE the launch: a synchronous launch (profilers, CUDA_LAUNCH_BLOCKING) cannot dead-lock
+    CfBatchView bv = h->bv;
+    bv.ready = h->d_ready;
+    h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, bv);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
     return CFNMPC_OK;
 }
 

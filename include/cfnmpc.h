@@ -117,7 +117,8 @@ int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, const double
  *   "qp_iter"  int [B]   interior-point iterations of the last step
  *   "qp_status" int [B]  HPIPM status 0 ok / 1 max-iter / 2 min-step / 3 NaN
  *   "flags"    int [B]   bit 0/1: the reference's LQ / iterative-refinement safety nets would have fired (needs the option
- *                        "lin_res_check"; 0 otherwise)
+ *                        "lin_res_check"; 0 otherwise); bit 2: cfnmpc_batch_solve_from_host gave up waiting for this
+ *                        instance's inputs (5 s) and solved it with whatever was in device memory
  *   "res"      double [B][4]  final QP residual inf-norms (stationarity, dynamics, bounds, complementarity)
  * Copies to host pointers synchronise the stream before returning. */
 int cfnmpc_batch_get(cfnmpc_batch *h, const char *field, int stage, void *dst, int dst_on_device);
