@@ -46,6 +46,8 @@ def lib():
         L.cfnmpc_batch_set_option.argtypes = [vp, cp, ci]
         L.cfnmpc_batch_solve.argtypes = [vp, ci]
         L.cfnmpc_batch_sync.argtypes = [vp]
+        L.cfnmpc_batch_prepare.argtypes = [vp]
+        L.cfnmpc_batch_feedback.argtypes = [vp]
         L.cfnmpc_batch_solve_from_host.argtypes = [vp, vp, vp, vp, ci]
         L.cfnmpc_batch_get.argtypes = [vp, cp, ci, vp, ci]
         L.cfnmpc_batch_device_ptr.argtypes = [vp, cp, ctypes.POINTER(vp)]
@@ -132,7 +134,7 @@ class BatchSolver:
                 "W": (NY,), "W_e": (NX,), "lbu": (NU,), "ubu": (NU,), "lbu0": (NU,), "ubu0": (NU,),
                 "W_batch": (B, NY), "W_e_batch": (B, NX), "lbu_batch": (B, NU), "ubu_batch": (B, NU),
                 "lbu0_batch": (B, NU), "ubu0_batch": (B, NU), "setpoint": (B, 3), "uss": (1,),
-                "policy": (B,), "traj_iter": (B,)}.get(field)
+                "policy": (B,), "traj_iter": (B,), "time_steps": (N,)}.get(field)
 
     def set_option(self, option, value):
         """"lin_res_check" (0/1: the reference's linear-system residual diagnostics -> "flags"), "max_ipm_iter"."""
@@ -169,6 +171,16 @@ class BatchSolver:
 
     def solve(self, n_rti=1):
         _check(lib().cfnmpc_batch_solve(self._h, int(n_rti)))
+        return self
+
+    def prepare(self):
+        """Preparation phase of a split real-time iteration (the reference's rti_phase 1): linearise around the iterate."""
+        _check(lib().cfnmpc_batch_prepare(self._h))
+        return self
+
+    def feedback(self):
+        """Feedback phase (rti_phase 2): take the current "x0", solve the QP, update the iterate."""
+        _check(lib().cfnmpc_batch_feedback(self._h))
         return self
 
     def solve_from_host(self, x0, yref, yref_e, n_chunks=4):

@@ -25,6 +25,7 @@ struct crazyflie_solver_capsule
     std::vector<double> x0, yref, yref_e, x, u;
     bool in_dirty = true, iterate_dirty = true;
     int status = 0, qp_iter = 0, qp_status = 0, cond_N = 0;
+    int rti_phase = 0;   // 0 preparation + feedback, 1 preparation, 2 feedback (ocp_nlp_sqp_rti.c:189-198)
     double lbu[4] = {0, 0, 0, 0}, ubu[4] = {22, 22, 22, 22}, lbu0[4] = {0, 0, 0, 0}, ubu0[4] = {22, 22, 22, 22};
     double time_tot = 0.0;
     ocp_nlp_plan_t plan;
@@ -69,9 +70,9 @@ int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int
     double Ts = CF_SPEC_TF / CF_SPEC_N;  // Tf / N of generate_c_code.py:41-42
     if (new_time_steps) {
         Ts = new_time_steps[0];
-        for (int i = 1; i < N; i++)
-            if (new_time_steps[i] != Ts) {
-                fprintf(stderr, "crazyflie_acados_create_with_discretization: only uniform time grids are supported\n");
+        for (int i = 0; i < N; i++)
+            if (!(new_time_steps[i] > 0.0)) {
+                fprintf(stderr, "crazyflie_acados_create_with_discretization: time steps must be positive\n");
                 return 1;
             }
     } else if (N != CRAZYFLIE_N) {
@@ -84,8 +85,15 @@ int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int
         c->batch = nullptr;
         return 1;
     }
+    // one step per shooting interval = its cost scaling (acados_solver.in.c:133-153,879-892)
+    if (new_time_steps && cfnmpc_batch_set(c->batch, "time_steps", new_time_steps, 0) != CFNMPC_OK) {
+        fprintf(stderr, "crazyflie_acados_create: %s\n", cfnmpc_last_error());
+        crazyflie_acados_free(c);
+        return 1;
+    }
     c->N = N;
     c->Ts = Ts;
+    c->rti_phase = 0;
     for (int i = 0; i < 4; i++) { c->lbu[i] = c->lbu0[i] = CfSpec::lbu[i]; c->ubu[i] = c->ubu0[i] = CfSpec::ubu[i]; }  // generate_c_code.py:133-134
     // generate_c_code.py:128-129 reference, :135 x0 (through tools/gen_spec.py)
     const double *y = CfSpec::yref;
@@ -110,11 +118,12 @@ int crazyflie_acados_create(crazyflie_solver_capsule *c) { return crazyflie_acad
 int crazyflie_acados_update_time_steps(crazyflie_solver_capsule *c, int N, double *new_time_steps)
 {
     if (!c || !c->batch || N != c->N || !new_time_steps) return 1;
-    // keep inputs and iterate, rebuild the device solver with the new (uniform) step
-    std::vector<double> x0 = c->x0, yref = c->yref, yref_e = c->yref_e, x = c->x, u = c->u;
-    if (crazyflie_acados_create_with_discretization(c, N, new_time_steps)) return 1;
-    c->x0 = x0; c->yref = yref; c->yref_e = yref_e; c->x = x; c->u = u;
-    c->in_dirty = c->iterate_dirty = true;
+    // acados_solver.in.c:133-153: "Ts" and the cost "scaling" of every interval; inputs, weights and iterate stay
+    if (cfnmpc_batch_set(c->batch, "time_steps", new_time_steps, 0) != CFNMPC_OK) {
+        fprintf(stderr, "crazyflie_acados_update_time_steps: %s\n", cfnmpc_last_error());
+        return 1;
+    }
+    c->Ts = new_time_steps[0];
     return 0;
 }
 
@@ -151,7 +160,21 @@ int crazyflie_acados_solve(crazyflie_solver_capsule *c)
         rc |= cfnmpc_batch_set(b, "u", c->u.data(), 0);
         c->iterate_dirty = false;
     }
-    rc |= cfnmpc_batch_solve(b, 1);
+    // ocp_nlp_sqp_rti.c:1213-1237
+    if (c->rti_phase == 1) {
+        rc |= cfnmpc_batch_prepare(b);
+        rc |= cfnmpc_batch_sync(b);
+        double ms = 0.0;
+        rc |= cfnmpc_batch_last_solve_ms(b, &ms);
+        if (rc) {
+            fprintf(stderr, "crazyflie_acados_solve (preparation): %s\n", cfnmpc_last_error());
+            return ACADOS_QP_FAILURE;
+        }
+        c->time_tot = ms * 1e-3;
+        c->out.total_time = c->time_tot;
+        return c->status;   // mem->status is left as the last feedback set it
+    }
+    rc |= (c->rti_phase == 2) ? cfnmpc_batch_feedback(b) : cfnmpc_batch_solve(b, 1);
     rc |= cfnmpc_batch_get(b, "x_all", 0, c->x.data(), 0);
     rc |= cfnmpc_batch_get(b, "u_all", 0, c->u.data(), 0);
     rc |= cfnmpc_batch_get(b, "status", 0, &c->status, 0);
@@ -256,9 +279,11 @@ void ocp_nlp_solver_opts_set(ocp_nlp_config *config, void *, const char *field, 
 {
     if (!config || !config->capsule || !field || !value) return;
     if (!strcmp(field, "qp_cond_N")) config->capsule->cond_N = *static_cast<int *>(value);
-    else if (!strcmp(field, "rti_phase") && *static_cast<int *>(value) != 0)
-        fprintf(stderr, "ocp_nlp_solver_opts_set: rti_phase %d is not supported (preparation and feedback are fused)\n",
-                *static_cast<int *>(value));
+    else if (!strcmp(field, "rti_phase")) {
+        const int v = *static_cast<int *>(value);
+        if (v < 0 || v > 2) fprintf(stderr, "ocp_nlp_solver_opts_set: invalid value %d for rti_phase (0, 1, 2)\n", v);
+        else config->capsule->rti_phase = v;
+    }
 }
 
 int ocp_nlp_solve(ocp_nlp_solver *solver, ocp_nlp_in *, ocp_nlp_out *)

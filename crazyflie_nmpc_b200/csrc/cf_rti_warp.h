@@ -119,7 +119,22 @@ struct CfBatchView
     const double *W_b, *WN_b, *lbu_b, *ubu_b, *lbu0_b, *ubu0_b;
     // optional profiling counters (null = off): per-pass warp cycles and call counts, see cfnmpc_debug_pass_cycles
     unsigned long long *prof;
+    // non-uniform shooting grid (crazyflie_acados_create_with_discretization / _update_time_steps,
+    // c_templates_tera/acados_solver.in.c:133-153): dts[N] = length of every interval = its cost scaling; only read by
+    // the kernel variants compiled with VDT (null otherwise: CfParams::Ts applies to every interval)
+    const double *dts;
+    // split real-time iteration (rti_phase 1 / 2, ocp_nlp_sqp_rti.c:495-542,545-683): what the preparation phase leaves
+    // for the feedback phase, per INSTANCE: N stage records [ [B';A';b'] (234) | gradient (18) ] + the terminal gradient
+    double *prep;
+    long prep_stride;
 };
+// layout of the prepared linearisation of one instance (doubles)
+#define CF_PREP_STAGE (CF_MSZ + 18)
+static inline
+#if !defined(CF_SIMT_EMU)
+    __host__ __device__
+#endif
+    long cf_prep_stride(int N) { return ((long) N * CF_PREP_STAGE + 18 + 15) & ~15L; }
 enum { CF_PROF_LIN = 0, CF_PROF_RF, CF_PROF_FWD, CF_PROF_BWD, CF_PROF_MUAFF, CF_PROF_UPDATE, CF_PROF_N };
 
 // offsets (in doubles) of the arrays inside one scratch slot; every block that the TMA engine
@@ -164,7 +179,12 @@ static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BK
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
-struct CfWarp
+// PH: 0 = preparation + feedback in one go (what acados_solve() does with rti_phase 0), 1 = preparation only,
+//     2 = feedback only (ocp_nlp_sqp_rti.c:1213-1237).  VDT: per-interval time steps CfBatchView::dts instead of the
+//     uniform CfParams::Ts.  The benchmarked kernel is <0, false>; the other variants cost it nothing.
+enum { CF_PH_BOTH = 0, CF_PH_PREPARATION = 1, CF_PH_FEEDBACK = 2 };
+template <int PH, bool VDT>
+struct CfWarpT
 {
     // ---- per-warp context
     const CfParams *P;    // this instance's weights and bounds (per-warp copy in shared memory)
@@ -175,17 +195,21 @@ struct CfWarp
     unsigned par;  // phase parity of the two mbarriers
     // scratch arrays
     double *SLOT;
+    double *PREP;      // this instance's prepared linearisation (split phases only)
+    const double *DT;  // per-interval time steps (VDT only)
     // lane constants
     double Hs, HN;     // Hessian diagonal for this lane's variable (stage / terminal)
+    double W2;         // (sqrt(w))^2 of this lane's stage weight: the stage Hessian is dt_k * W2
     // IPM scalars (warp-uniform)
     double mu, alpha, mu_aff, sigma, pm_max;
     double nrm[4];     // inf-norms of res_g, res_b, res_d, res_m
     double lin[4];     // inf-norms of the linear-system residual of the last solve
     int flags;
 
-    CF_MEM void bind(const CfParams *P_, const CfParams *PG_, double *slot, double *sm_)
+    CF_MEM void bind(const CfParams *P_, const CfParams *PG_, double *slot, double *sm_, double *prep_, const double *dts_)
     {
         P = P_; PG = PG_; N = PG_->N; sm = sm_; lane = cf_lane();
+        PREP = prep_; DT = dts_;
         bar = reinterpret_cast<uint64_t *>(sm_ + CF_SM_BAR);
         par = 0;
         CfScratchLayout s = cf_scratch_layout(N);
@@ -195,8 +219,21 @@ struct CfWarp
         if (lane < CF_NU) w = P->Wdiag[CF_NX + lane];
         else if (lane < CF_NV) { w = P->Wdiag[lane - CF_NU]; wN = P->WNdiag[lane - CF_NU]; }
         double r = sqrt(w), rN = sqrt(wN);
-        Hs = PG->Ts * (r * r);
+        W2 = r * r;
+        Hs = PG->Ts * W2;
         HN = (lane < CF_NU) ? Hs : (rN * rN);
+    }
+    // length of shooting interval k = scaling of its cost term (ocp_nlp_in "Ts" / cost "scaling")
+    CF_MEM double dt(int k) const
+    {
+        if constexpr (VDT) return DT[k];
+        else return PG->Ts;
+    }
+    // Hessian diagonal of this lane's variable at stage k < N
+    CF_MEM double hess(int k) const
+    {
+        if constexpr (VDT) return DT[k] * W2;
+        else return Hs;
     }
 
     // ---- TMA staging: one mbarrier per buffer; lane 0 issues, every lane waits
@@ -233,9 +270,9 @@ struct CfWarp
 #define CF_NOM 74
     CF_MEM void nominal_pass(const double *xg, const double *ug)
     {
-        const double h = PG->Ts;
         CF_NOUNROLL
         for (int k = lane; k < N; k += 32) {
+            const double h = dt(k);
             double *nom = blk(k) + B_LU;
             double x[CF_NX], xs[CF_NX], acc[CF_NX], uu[CF_NU];
             CF_UNROLL
@@ -284,8 +321,11 @@ struct CfWarp
     CF_MEM void linearize_stage(int k, const double *xg, const double *x0g, const double *yrefg)
     {
         double *MS = sm + ((k & 1) ? CF_SM_MS1 : CF_SM_MS0);
-        const double h = PG->Ts;
+        const double h = dt(k);
         const int bf = k & 1;
+        // preparation-only: the linearisation goes to the instance's prepared record instead of the warp's scratch slot
+        double *mdst = (PH == CF_PH_PREPARATION) ? PREP + (long) k * CF_PREP_STAGE : blk(k) + B_M;
+        double *rqdst = (PH == CF_PH_PREPARATION) ? PREP + (long) k * CF_PREP_STAGE + CF_MSZ : rec(k) + R_RQ;
         // this stage's reference (consumed at the end of the stage)
         const double yr_pre = (lane < CF_NU) ? yrefg[k * CF_NY + CF_NX + lane] : ((lane < CF_NV) ? yrefg[k * CF_NY + lane - CF_NU] : 0.0);
         wait(bf);
@@ -330,26 +370,39 @@ struct CfWarp
         // row 17: b_k
         if (lane < CF_NX) MS[lane * CF_MROWS + 17] = NOMS[4 * 14 + lane];
         cf_syncwarp();
-        if (k == 0) {
-            // x0 elimination (x_ocp_qp_red.c:310-330): xbar = lbx - x_0 ; b_0 += A_0 xbar ; drop the A rows
-            const bool xl = lane >= CF_NU && lane < CF_NV;
-            const double xbar = xl ? (x0g[lane - CF_NU] - xg[lane - CF_NU]) : 0.0;
-            CF_NOUNROLL
-            for (int i = 0; i < CF_NX; i++) {
-                const double tot = cf_warp_sum(xl ? Mrow[i * CF_MROWS] * xbar : 0.0);
-                if (lane == 17) MS[i * CF_MROWS + 17] = tot + MS[i * CF_MROWS + 17];
-                else if (xl) Mrow[i * CF_MROWS] = 0.0;
-            }
-            cf_syncwarp();
-        }
+        if (PH != CF_PH_PREPARATION && k == 0) eliminate_x0(MS, xg, x0g);   // (the feedback phase does it otherwise)
         // gradient: scaling * W * (y - yref), [u;x] order (ocp_nlp_cost_ls.c:883-912)
         const double uk = (lane < CF_NU) ? NOMS[5 * 14 + lane] : 0.0;
         if (lane < CF_NV) {
             double g;
             if (lane < CF_NU) g = (P->Wdiag[CF_NX + lane] * (uk - yr_pre)) * h;
             else g = (k == 0) ? 0.0 : (P->Wdiag[lane - CF_NU] * (NOMS[lane - CF_NU] - yr_pre)) * h;
-            rec(k)[R_RQ + lane] = g;
+            rqdst[lane] = g;
         }
+        if (PH != CF_PH_PREPARATION) stage_bounds_init(k, uk);
+        cf_syncwarp();
+        if (lane == 0) cf_bulk_s2g(mdst, MS, CF_MSZ * 8);
+    }
+
+    // x0 elimination on the staged block of stage 0 (x_ocp_qp_red.c:310-330): xbar = lbx - x_0 ; b_0 += A_0 xbar ; drop
+    // the A rows
+    CF_MEM void eliminate_x0(double *MS, const double *xg, const double *x0g)
+    {
+        const bool xl = lane >= CF_NU && lane < CF_NV;
+        double *Mrow = MS + (lane < CF_NV ? lane : 17);
+        const double xbar = xl ? (x0g[lane - CF_NU] - xg[lane - CF_NU]) : 0.0;
+        CF_NOUNROLL
+        for (int i = 0; i < CF_NX; i++) {
+            const double tot = cf_warp_sum(xl ? Mrow[i * CF_MROWS] * xbar : 0.0);
+            if (lane == 17) MS[i * CF_MROWS + 17] = tot + MS[i * CF_MROWS + 17];
+            else if (xl) Mrow[i * CF_MROWS] = 0.0;
+        }
+        cf_syncwarp();
+    }
+
+    // bound data and the initial interior-point variables of stage k < N; uk = u_k[lane] on lanes 0..3
+    CF_MEM void stage_bounds_init(int k, double uk)
+    {
         // bounds (ocp_nlp_constraints_bgh.c:1634-1636): d = [lb - u ; u - ub]
         double v0 = 0.0;
         if (lane < CF_NU) {
@@ -367,8 +420,6 @@ struct CfWarp
             rec(k)[R_LAM + lane] = CF_MU0 / tl; rec(k)[R_LAM + 4 + lane] = CF_MU0 / tu;
         }
         init_stage_vectors(k, v0);
-        cf_syncwarp();
-        if (lane == 0) cf_bulk_s2g(blk(k) + B_M, MS, CF_MSZ * 8);
     }
 
     // ux = v (0 unless a bound had to be respected), pi = 0 and zero steps, so that the first residual pass can be an
@@ -383,13 +434,46 @@ struct CfWarp
 
     CF_MEM void terminal_gradient(const double *xg, const double *yref_eg)
     {
-        init_stage_vectors(N, 0.0);
+        if (PH != CF_PH_PREPARATION) init_stage_vectors(N, 0.0);
         if (lane < CF_NV) {
             double g = 0.0;
             if (lane >= CF_NU) g = P->WNdiag[lane - CF_NU] * (xg[N * CF_NX + lane - CF_NU] - yref_eg[lane - CF_NU]);
-            rec(N)[R_RQ + lane] = g;
+            if (PH == CF_PH_PREPARATION) PREP[(long) N * CF_PREP_STAGE + lane] = g;
+            else rec(N)[R_RQ + lane] = g;
         }
         if (lane == 0) cf_bulk_s2g_wait_all();  // every M_k has landed in global memory
+    }
+
+    // Feedback phase of a split real-time iteration (ocp_nlp_sqp_rti.c:545-683): the linearisation comes from the
+    // instance's prepared record; what depends on data that may have changed since the preparation -- the measured
+    // state (stage-0 elimination), the bound vectors (ocp_nlp_approximate_qp_vectors_sqp, ocp_nlp_common.c:2258-2292) --
+    // is evaluated now, together with the initial interior-point variables.
+    CF_MEM void load_prepared(const double *xg, const double *ug, const double *x0g)
+    {
+        double *MS = sm + CF_SM_MS0;
+        CF_NOUNROLL
+        for (int k = 0; k < N; k++) {
+            const double *src = PREP + (long) k * CF_PREP_STAGE;
+            double *dst = (k == 0) ? MS : blk(k) + B_M;
+            CF_UNROLL
+            for (int q = 0; q < 4; q++) {
+                const int i = lane + 32 * q;
+                if (i < CF_MSZ / 2) { const cf_d2 v = cf_ld2(src + 2 * i); cf_st2(dst + 2 * i, v.x, v.y); }
+            }
+            if (k == 0) {
+                cf_syncwarp();
+                eliminate_x0(MS, xg, x0g);
+                CF_UNROLL
+                for (int q = 0; q < 4; q++) {
+                    const int i = lane + 32 * q;
+                    if (i < CF_MSZ / 2) { const cf_d2 v = cf_ld2(MS + 2 * i); cf_st2(blk(0) + B_M + 2 * i, v.x, v.y); }
+                }
+            }
+            if (lane < CF_NV) rec(k)[R_RQ + lane] = src[CF_MSZ + lane];
+            stage_bounds_init(k, lane < CF_NU ? ug[k * CF_NU + lane] : 0.0);
+        }
+        init_stage_vectors(N, 0.0);
+        if (lane < CF_NV) rec(N)[R_RQ + lane] = PREP[(long) N * CF_PREP_STAGE + lane];
     }
 
     // =============================================================== IPM pieces
@@ -461,7 +545,8 @@ struct CfWarp
             if (vl) rk[R_UX + lane] = uxc;
             const double pim = (k > 0 && xl) ? VS[R_PI + ci] + a * VS[R_DPI + ci] : 0.0;   // pi_{k-1}
             if (k > 0 && xl) rk[R_PI + ci] = pim;
-            double rg = ((k == N) ? HN : Hs) * uxc + VS[R_RQ + lv] - pim;
+            const double Hk = hess(k < N ? k : 0);
+            double rg = ((k == N) ? HN : Hk) * uxc + VS[R_RQ + lv] - pim;
             double Gam = 0.0, gam = 0.0;
             {   // bounds of input l4 (lanes >= 4 compute duplicates that are never stored nor counted)
                 double ll = VS[R_LAM + l4] + a * VS[R_DLAM + l4], lu = VS[R_LAM + 4 + l4] + a * VS[R_DLAM + 4 + l4];
@@ -542,7 +627,7 @@ struct CfWarp
                 }
                 continue;
             }
-            const double g = vl ? rg + gam : 0.0, hd = Hs + CF_REG_PRIM + Gam;
+            const double g = vl ? rg + gam : 0.0, hd = Hk + CF_REG_PRIM + Gam;
             cf_syncwarp();  // row 17 of M_k is complete
             const double *Mk = VS + B_M;
             double *WS = VS;   // W rows 18 x 16 (stride 20) overlay the staged block once M is in registers
@@ -836,7 +921,7 @@ struct CfWarp
             // stationarity residual, part 1: H dux + rhs_g - dpi_{k-1} + dlam_ub - dlam_lb
             double rgl = 0.0;
             if (chk) {
-                rgl = Hs * duxk + VS[R_RESG + lv] - dpi_prev;
+                rgl = hess(k) * duxk + VS[R_RESG + lv] - dpi_prev;
                 rgl += ul ? dlam_u - dlam_l : 0.0;
             }
             // ---- dx+ = [A B] dux + res_b        GEMV_T, column layout of M_k (contiguous)
@@ -1017,6 +1102,7 @@ struct CfWarp
 #define CF_PROF_BEGIN() const long long cf_t0_ = prof ? clock64() : 0
 #define CF_PROF_END(id) do { if (prof && cf_lane() == 0) { atomicAdd(prof + 2 * (id), (unsigned long long) (clock64() - cf_t0_)); atomicAdd(prof + 2 * (id) + 1, 1ull); } } while (0)
 #endif
+template <class CfWarp>
 CF_DEV int cf_ipm_solve(CfWarp &w, int &iters, unsigned long long *prof)
 {
     w.alpha = 1.0;
@@ -1105,8 +1191,10 @@ CF_DEV void cf_warp_init_smem(double *sm)
     cf_syncwarp();
 }
 
+template <int PH = CF_PH_BOTH, bool VDT = false>
 CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst, double *slot, double *sm, unsigned &par)
 {
+    typedef CfWarpT<PH, VDT> CfWarp;
     // this instance's parameters: the solver-wide set, overridden by whatever per-instance arrays the caller gave
     CfParams *P = reinterpret_cast<CfParams *>(sm + CF_SM_PAR);
     {
@@ -1127,7 +1215,7 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
         cf_syncwarp();
     }
     CfWarp w;
-    w.bind(P, Pg, slot, sm);
+    w.bind(P, Pg, slot, sm, (PH != CF_PH_BOTH) ? bv.prep + (long) inst * bv.prep_stride : nullptr, VDT ? bv.dts : nullptr);
     w.par = par;
     const int N = Pg->N;
     double *xg = bv.x + (long) inst * (N + 1) * CF_NX;
@@ -1136,7 +1224,7 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     const double *yrefg = bv.yref + (long) inst * N * CF_NY;
     const double *yref_eg = bv.yref_e + (long) inst * CF_NX;
     unsigned long long *prof = bv.prof;
-    {
+    if (PH != CF_PH_FEEDBACK) {
         CF_PROF_BEGIN();
         w.nominal_pass(xg, ug);
         CF_NOUNROLL
@@ -1144,6 +1232,13 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
         w.terminal_gradient(xg, yref_eg);
         cf_syncwarp();
         CF_PROF_END(CF_PROF_LIN);
+    } else {
+        w.load_prepared(xg, ug, x0g);
+        cf_syncwarp();
+    }
+    if (PH == CF_PH_PREPARATION) {   // the solution, status and statistics of the instance are left as they are
+        par = w.par;
+        return;
     }
     int iters = 0;
     const int qp_status = cf_ipm_solve(w, iters, prof);

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/cfnmpc.h"
 #include "cf_rti_warp.h"
@@ -20,7 +21,7 @@
 // counter until the batch is exhausted (IPM trip counts differ per instance: 4..11).
 // Launch shape <WPB, MINB>: WPB warps per block (warps never cooperate, the block is only a container), MINB resident
 // blocks per SM the register allocation is bounded for: warps per SM = WPB * MINB, registers <= 65536 / (32 * WPB * MINB).
-template <int WPB>
+template <int WPB, int PH, bool VDT>
 __device__ __forceinline__ void cf_rti_kernel_body(const CfParams &P, const CfBatchView &bv)
 {
     extern __shared__ __align__(128) double cf_smem[];
@@ -52,18 +53,20 @@ __device__ __forceinline__ void cf_rti_kernel_body(const CfParams &P, const CfBa
                 }
             }
             late = __shfl_sync(0xffffffffu, late, 0);
-            cf_rti_instance(&P, bv, bv.first + inst, slot, sm, par);
+            cf_rti_instance<PH, VDT>(&P, bv, bv.first + inst, slot, sm, par);
             if (late && (threadIdx.x & 31) == 0) bv.flags[bv.first + inst] |= CF_FLAG_INPUT_LATE;
             continue;
         }
-        cf_rti_instance(&P, bv, bv.first + inst, slot, sm, par);
+        cf_rti_instance<PH, VDT>(&P, bv, bv.first + inst, slot, sm, par);
     }
 }
-template <int WPB, int MINB>
+// <PH, VDT>: preparation + feedback (0) / preparation (1) / feedback (2); uniform or per-interval time steps.  The
+// benchmarked path is <.., 0, false>.
+template <int WPB, int MINB, int PH = CF_PH_BOTH, bool VDT = false>
 __global__ void __launch_bounds__(WPB * 32, MINB)
 cf_rti_kernel(const __grid_constant__ CfParams P, const __grid_constant__ CfBatchView bv)
 {
-    cf_rti_kernel_body<WPB>(P, bv);
+    cf_rti_kernel_body<WPB, PH, VDT>(P, bv);
 }
 // out[i][0:w] = src[i][stage*w : stage*w + w]   (ocp_nlp_out_get for every instance at once)
 __global__ void cf_gather_stage_kernel(const double *__restrict__ src, double *__restrict__ out, int B, int per_inst, int stage, int w)
@@ -117,6 +120,15 @@ struct cfnmpc_batch
     int *d_status = nullptr, *d_qp_iter = nullptr, *d_qp_status = nullptr, *d_flags = nullptr, *d_counter = nullptr;
     int grid = 0, blocks_per_sm = 0, sm_count = 0, n_slots = 0, regs = 0, minb = 3, wpb = 4;
     void (*kernel)(const CfParams, const CfBatchView) = nullptr;
+    // general variants (default launch shape): per-interval time steps, split phases
+    void (*kernel_vdt)(const CfParams, const CfBatchView) = nullptr;
+    void (*kernel_prep)(const CfParams, const CfBatchView) = nullptr;
+    void (*kernel_fb)(const CfParams, const CfBatchView) = nullptr;
+    size_t smem_general = 0;
+    int grid_general = 0;
+    double *d_dts = nullptr, *d_prep = nullptr;
+    double *h_dts = nullptr;          // host copy of the time grid (N doubles)
+    bool vdt = false, prepared = false;
     size_t smem = 0;
     long long launches = 0;
     bool timed = false;
@@ -141,7 +153,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
                     h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter,
                     h->d_policy, h->d_titer, h->d_motors, h->d_setpoint, h->d_traj, h->d_euler, h->d_twist,
-                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b};
+                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -150,6 +162,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     if (h->h_ready) cudaFreeHost(h->h_ready);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    free(h->h_dts);
     delete h;
     return CFNMPC_OK;
 }
@@ -195,6 +208,13 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     }
     h->smem = (size_t) h->wpb * CF_SM_DOUBLES * sizeof(double);
     CKH(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem));
+    h->kernel_vdt = cf_rti_kernel<4, 3, CF_PH_BOTH, true>;
+    h->kernel_prep = cf_rti_kernel<4, 3, CF_PH_PREPARATION, true>;
+    h->kernel_fb = cf_rti_kernel<4, 3, CF_PH_FEEDBACK, true>;
+    h->smem_general = (size_t) 4 * CF_SM_DOUBLES * sizeof(double);
+    CKH(cudaFuncSetAttribute(h->kernel_vdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
+    CKH(cudaFuncSetAttribute(h->kernel_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
+    CKH(cudaFuncSetAttribute(h->kernel_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
     cudaFuncAttributes fa;
     CKH(cudaFuncGetAttributes(&fa, h->kernel));
     h->regs = fa.numRegs;
@@ -205,6 +225,9 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     long need = ((long) batch + h->wpb - 1) / h->wpb;
     h->grid = (int) (want < need ? want : need);
     h->n_slots = h->grid * h->wpb;
+    // the general variants run 4 warps per block on the same scratch slots: never more blocks than n_slots / 4
+    h->grid_general = h->n_slots / 4 > 0 ? h->n_slots / 4 : 1;
+    if (h->n_slots < 4) h->n_slots = 4;
     const long stride = cf_scratch_layout(N).total;
     const size_t B = batch;
     CKH(cudaMalloc(&h->d_x0, B * CF_NX * 8));
@@ -219,6 +242,10 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     CKH(cudaMalloc(&h->d_qp_status, B * 4));
     CKH(cudaMalloc(&h->d_flags, B * 4));
     CKH(cudaMalloc(&h->d_counter, 4));
+    CKH(cudaMalloc(&h->d_dts, (size_t) N * 8));
+    h->h_dts = (double *) malloc((size_t) N * 8);
+    for (int i = 0; i < N; i++) h->h_dts[i] = Ts;
+    CKH(cudaMemcpy(h->d_dts, h->h_dts, (size_t) N * 8, cudaMemcpyHostToDevice));
     CKH(cudaMalloc(&h->d_policy, B * 4));
     CKH(cudaMalloc(&h->d_titer, B * 4));
     CKH(cudaMalloc(&h->d_motors, B * CF_NU * 4));
@@ -256,6 +283,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     bv.res = h->d_res; bv.scratch = h->d_scratch; bv.scratch_stride = stride; bv.counter = h->d_counter;
     bv.W_b = bv.WN_b = bv.lbu_b = bv.ubu_b = bv.lbu0_b = bv.ubu0_b = nullptr;
     bv.prof = nullptr;
+    bv.dts = h->d_dts; bv.prep = nullptr; bv.prep_stride = cf_prep_stride(N);
     CKH(cudaStreamSynchronize(h->stream));
 #undef CKH
     *out = h;
@@ -340,6 +368,24 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         }
     }
     FieldRef r;
+    if (!strcmp(field, "time_steps")) {
+        // crazyflie_acados_update_time_steps (c_templates_tera/acados_solver.in.c:133-153): interval lengths = cost scalings
+        std::vector<double> dt(h->N);
+        if (src_on_device) CK(cudaMemcpy(dt.data(), src, (size_t) h->N * 8, cudaMemcpyDeviceToHost));
+        else memcpy(dt.data(), src, (size_t) h->N * 8);
+        bool uniform = true;
+        for (int i = 0; i < h->N; i++) {
+            if (!(dt[i] > 0)) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set: time steps must be positive");
+            uniform = uniform && dt[i] == dt[0];
+        }
+        CK(cudaStreamSynchronize(h->stream));   // a solve in flight still reads the old grid
+        memcpy(h->h_dts, dt.data(), (size_t) h->N * 8);
+        CK(cudaMemcpy(h->d_dts, h->h_dts, (size_t) h->N * 8, cudaMemcpyHostToDevice));
+        h->P.Ts = dt[0];
+        h->vdt = !uniform;
+        h->prepared = false;
+        return CFNMPC_OK;
+    }
     if (!strcmp(field, "uss")) {
         if (src_on_device) CK(cudaMemcpy(&h->uss, src, 8, cudaMemcpyDeviceToHost));
         else memcpy(&h->uss, src, 8);
@@ -384,12 +430,56 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
     CK(cudaEventRecord(h->ev0, h->stream));
     for (int r = 0; r < n_rti; r++) {
         CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
-        h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, h->bv);
+        if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+        else h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, h->bv);
         CK(cudaGetLastError());
         h->launches++;
     }
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
+    h->prepared = false;   // the iterate moved: an earlier preparation no longer belongs to it
+    return CFNMPC_OK;
+}
+
+// Split real-time iteration: rti_phase 1 / 2 of the reference (ocp_nlp_sqp_rti.c:189-198,1213-1237).
+extern "C" int cfnmpc_batch_prepare(cfnmpc_batch *h)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    if (!h->d_prep) {
+        const size_t bytes = (size_t) h->B * h->bv.prep_stride * 8;
+        cudaError_t e = cudaMalloc(&h->d_prep, bytes);
+        if (e != cudaSuccess) {
+            h->d_prep = nullptr;
+            return fail(CFNMPC_ECUDA, std::string("cfnmpc_batch_prepare: cannot allocate the prepared linearisations (") +
+                                          std::to_string(bytes >> 20) + " MiB): " + cudaGetErrorString(e));
+        }
+        h->bv.prep = h->d_prep;
+    }
+    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+    h->kernel_prep<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->prepared = true;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_feedback(cfnmpc_batch *h)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    if (!h->prepared) return fail(CFNMPC_ESTATE, "cfnmpc_batch_feedback: no preparation phase belongs to the current iterate");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+    h->kernel_fb<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->prepared = false;
     return CFNMPC_OK;
 }
 
@@ -436,9 +526,11 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
     // the copies are enqueued BEFORE the launch: a synchronous launch (profilers, CUDA_LAUNCH_BLOCKING) cannot dead-lock
     CfBatchView bv = h->bv;
     bv.ready = h->d_ready;
-    h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, bv);
+    if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, bv);
+    else h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, bv);
     CK(cudaGetLastError());
     h->launches++;
+    h->prepared = false;
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
     return CFNMPC_OK;

@@ -70,7 +70,8 @@ void ocp_nlp_out_set(ocp_nlp_config *config, ocp_nlp_dims *dims, ocp_nlp_out *ou
                      void *value);
 void ocp_nlp_out_get(ocp_nlp_config *config, ocp_nlp_dims *dims, ocp_nlp_out *out, int stage, const char *field,
                      void *value);
-/* field: "rti_phase" (only 0 = preparation + feedback), "qp_cond_N" (accepted; results do not depend on it),
+/* field: "rti_phase" (int 0 = preparation + feedback, 1 = preparation, 2 = feedback: ocp_nlp_sqp_rti.c:189-198,
+ * 1213-1237; the next ocp_nlp_solve / acados_solve runs that phase), "qp_cond_N" (accepted; results do not depend on it),
  * "print_level" (ignored) */
 void ocp_nlp_solver_opts_set(ocp_nlp_config *config, void *opts_, const char *field, void *value);
 /* One RTI step (ocp_nlp_sqp_rti.c:1232-1237). Returns the acados status. */

@@ -27,8 +27,9 @@ typedef struct crazyflie_solver_capsule crazyflie_solver_capsule;
 crazyflie_solver_capsule *crazyflie_acados_create_capsule(void);
 int crazyflie_acados_free_capsule(crazyflie_solver_capsule *capsule);
 int crazyflie_acados_create(crazyflie_solver_capsule *capsule);
-/* other horizons: n_time_steps intervals of equal length new_time_steps[0] (all entries must be equal);
- * NULL keeps Ts = 0.015 s (acados_solver.in.c:2381-2391) */
+/* other horizons / grids: n_time_steps shooting intervals of lengths new_time_steps[i] > 0, each also the scaling of its
+ * stage cost (acados_solver.in.c:133-153,879-892); NULL keeps Ts = 0.015 s and needs n_time_steps == CRAZYFLIE_N
+ * (:2381-2391).  crazyflie_acados_update_time_steps changes the grid of an existing solver (same N). */
 int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *capsule, int n_time_steps, double *new_time_steps);
 int crazyflie_acados_update_time_steps(crazyflie_solver_capsule *capsule, int N, double *new_time_steps);
 int crazyflie_acados_update_qp_solver_cond_N(crazyflie_solver_capsule *capsule, int qp_solver_cond_N);

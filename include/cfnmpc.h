@@ -77,6 +77,10 @@ int cfnmpc_batch_set_stream(cfnmpc_batch *h, void *cuda_stream);
  *   "lbu","ubu" double [4]          input bounds, stages 0..N-1
  *   "lbu0","ubu0" double [4]        input bounds of stage 0 only (set after "lbu"/"ubu"): the node's FIXED_U0
  *                                   branch pins u_0 this way, acados_mpc.cpp:604-608
+ *   "time_steps" double [N]         lengths of the shooting intervals (host or device pointer); each is also the
+ *                                   scaling of its stage cost, as crazyflie_acados_create_with_discretization /
+ *                                   crazyflie_acados_update_time_steps set them (c_templates_tera/acados_solver.in.c:
+ *                                   133-153).  A uniform grid runs the specialised kernel, anything else the general one.
  * Per-instance parameter arrays (one value set per vehicle; the reference expresses this as one solver object per
  * vehicle, each with its own ocp_nlp_cost_model_set(..,"W",..) / ocp_nlp_constraints_model_set(..,"lbu"|"ubu",..)
  * calls, acados_mpc.cpp:596-608).  Once given they take precedence over the solver-wide value until cleared:
@@ -100,6 +104,15 @@ int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int value);
  * inputs frozen between steps.  Asynchronous; pair with cfnmpc_batch_sync or a
  * getter to a host pointer. */
 int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti);
+/* The two halves of a real-time iteration as separate calls = rti_phase 1 (PREPARATION) and 2 (FEEDBACK) of the reference
+ * (ocp_nlp_solver_opts_set(.., "rti_phase", ..), acados/acados/ocp_nlp/ocp_nlp_sqp_rti.c:189-198,495-683,1213-1237).
+ * cfnmpc_batch_prepare linearises around the current iterate with the current "yref"/"yref_e"/weights (integration with
+ * sensitivities, gradients) and keeps the result per instance (8 * (252 N + 18) bytes each, allocated on first use);
+ * cfnmpc_batch_feedback then takes the "x0" (and bounds) of the moment, solves the QP and updates the iterate -- the
+ * latency-critical half.  prepare + feedback with unchanged inputs gives bit-identical results to cfnmpc_batch_solve(h, 1);
+ * feedback without a preparation that belongs to the current iterate returns CFNMPC_ESTATE. */
+int cfnmpc_batch_prepare(cfnmpc_batch *h);
+int cfnmpc_batch_feedback(cfnmpc_batch *h);
 int cfnmpc_batch_sync(cfnmpc_batch *h);
 /* One tick fed from HOST buffers (pinned memory for real overlap): equivalent to cfnmpc_batch_set of "x0", "yref",
  * "yref_e" followed by cfnmpc_batch_solve(h, 1), but the solve kernel starts at once and the inputs follow in n_chunks

@@ -169,6 +169,20 @@ void cfo_sim(const double *x, const double *u, double T, int n_steps, double *xn
     for (int i = 0; i < NX; i++) xn[i] = X[i];
 }
 
+/* Non-uniform shooting grid: interval lengths = cost scalings, as crazyflie_acados_update_time_steps sets them
+ * (acados_template/c_templates_tera/acados_solver.in.c:133-153).  Global, test use only; n = 0 returns to the
+ * uniform grid given by the Ts argument of the calls below. */
+#define CFO_MAX_N 4096
+static double g_dt[CFO_MAX_N];
+static int g_dt_n = 0;
+void cfo_set_time_steps(const double *dt, int n)
+{
+    if (!dt || n <= 0 || n > CFO_MAX_N) { g_dt_n = 0; return; }
+    memcpy(g_dt, dt, sizeof(double) * n);
+    g_dt_n = n;
+}
+#define DTK(k) ((k) < g_dt_n ? g_dt[k] : Ts)
+
 /* ------------------------------------------------------------ linearisation
  * ocp_nlp_common.c:2157-2292 calling dynamics_cont :755-884, cost_ls :810-916,
  * constraints_bgh :1613-1648.  Output layout = cfref_get_qp. */
@@ -184,7 +198,7 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
         if (k < N) {
             const double *uk = u + NU * k;
             double xn[NX], A[NX * NX], B[NX * NU];
-            cfo_erk4(xk, uk, Ts, xn, A, B);
+            cfo_erk4(xk, uk, DTK(k), xn, A, B);
             if (BAbt) {
                 double *M = BAbt + (size_t) k * NV * NX;
                 for (int j = 0; j < NU; j++) for (int i = 0; i < NX; i++) M[j * NX + i] = B[i * NU + j];
@@ -195,8 +209,8 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
                 /* grad = scaling * Cyt * W * (Cy ux - yref), [u;x] order */
                 double *g = rqz + NV * k;
                 const double *yr = yref + NV * k;
-                for (int i = 0; i < NU; i++) g[i] = (p_->Wdiag[NX + i] * (uk[i] - yr[NX + i])) * Ts;
-                for (int i = 0; i < NX; i++) g[NU + i] = (p_->Wdiag[i] * (xk[i] - yr[i])) * Ts;
+                for (int i = 0; i < NU; i++) g[i] = (p_->Wdiag[NX + i] * (uk[i] - yr[NX + i])) * DTK(k);
+                for (int i = 0; i < NX; i++) g[NU + i] = (p_->Wdiag[i] * (xk[i] - yr[i])) * DTK(k);
             }
             int nb = k == 0 ? NV : NU;
             for (int i = 0; i < NU; i++) {
@@ -778,10 +792,10 @@ int cfo_rti(int N, double Ts, const cfo_params *p_, const double *x0, const doub
         s->nv = s->nu + s->nx;
         s->nb = k < N ? NU : 0;
         /* Hessian: scaling * (sqrt(w))^2, cost_ls.c:739-772 */
-        for (int i = 0; i < s->nu; i++) { double r = sqrt(p_->Wdiag[NX + i]); s->H[i] = Ts * (r * r); }
+        for (int i = 0; i < s->nu; i++) { double r = sqrt(p_->Wdiag[NX + i]); s->H[i] = DTK(k) * (r * r); }
         for (int i = 0; i < s->nx; i++) {
             double r = sqrt(k < N ? p_->Wdiag[i] : p_->WNdiag[i]);
-            s->H[s->nu + i] = (k < N ? Ts : 1.0) * (r * r);
+            s->H[s->nu + i] = (k < N ? DTK(k) : 1.0) * (r * r);
         }
         const double *g = rqz + NV * k;
         if (k == 0) {
@@ -829,6 +843,18 @@ int cfo_rti(int N, double Ts, const cfo_params *p_, const double *x0, const doub
     }
     free(w.s); free(BAbt); free(b); free(rqz); free(dl); free(du);
     return status;
+}
+
+/* Split real-time iteration (rti_phase 1 then 2, ocp_nlp_sqp_rti.c:495-683): the preparation linearises around the
+ * iterate -- the measured state does not enter it -- and the feedback evaluates the bound vectors, i.e. the stage-0
+ * equality x_0 = x0, with the data of the moment (ocp_nlp_approximate_qp_vectors_sqp, ocp_nlp_common.c:2258-2292).  The
+ * pair therefore equals one full step with the feedback-time x0 (yref is consumed by the preparation and is the same for
+ * both); oracle/ref_harness.c:cfref_rti_split runs the reference's own two phases and the tests pin this equality. */
+int cfo_rti_split(int N, double Ts, const cfo_params *p, const double *x0_prep, const double *x0_fb, const double *yref,
+                  const double *yref_e, double *x, double *u, cfo_info *info)
+{
+    (void) x0_prep;
+    return cfo_rti(N, Ts, p, x0_fb, yref, yref_e, x, u, info, NULL, NULL);
 }
 
 void cfo_batch(int N, double Ts, const cfo_params *p, int n_rti, int n, const double *x0,

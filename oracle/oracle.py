@@ -64,6 +64,26 @@ class Port:
         L.cfo_sim.argtypes = [_dp, _dp, ctypes.c_double, ctypes.c_int, _dp]
         L.cfo_ode.argtypes = [_dp, _dp, _dp]
         L.cfo_default_params.argtypes = [ctypes.POINTER(CfoParams)]
+        L.cfo_set_time_steps.argtypes = [_dp, ctypes.c_int]
+        L.cfo_rti_split.restype = ctypes.c_int
+        L.cfo_rti_split.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), _dp, _dp, _dp, _dp, _dp, _dp,
+                                    ctypes.POINTER(CfoInfo)]
+
+    def set_time_steps(self, dt=None):
+        """Non-uniform shooting grid (global in the checker; None returns to the uniform grid)."""
+        if dt is None:
+            self.lib.cfo_set_time_steps(None, 0)
+        else:
+            dt = np.ascontiguousarray(dt, float)
+            self.lib.cfo_set_time_steps(_P(dt), dt.size)
+
+    def rti_split(self, N, Ts, x0_prep, x0_fb, yref, yref_e, x, u, params=None):
+        """Preparation with x0_prep, feedback with x0_fb; x,u updated in place."""
+        info = CfoInfo()
+        a = [np.ascontiguousarray(v, float) for v in (x0_prep, x0_fb, yref, yref_e)]
+        st = self.lib.cfo_rti_split(N, Ts, ctypes.byref(params) if params else None, *[_P(v) for v in a], _P(x), _P(u),
+                                    ctypes.byref(info))
+        return st, info
 
     def params(self, Wdiag=None, WNdiag=None, lbu=None, ubu=None, lbu0=None, ubu0=None):
         p = CfoParams()
@@ -143,12 +163,17 @@ class Ref:
         L.cfref_set_weights.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.cfref_set_input_bounds.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.cfref_set_input_bounds_stage0.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.cfref_create_dt.restype = ctypes.c_void_p
+        L.cfref_create_dt.argtypes = [ctypes.c_int, _dp, ctypes.c_int]
+        L.cfref_rti_split.restype = ctypes.c_int
+        L.cfref_rti_split.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
         L.cfref_batch.restype = ctypes.c_int
         L.cfref_batch.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
 
-    def solver(self, N=50, Ts=0.015, cond_N=0):
-        return RefSolver(self, N, Ts, cond_N)
+    def solver(self, N=50, Ts=0.015, cond_N=0, dt=None):
+        """dt: one time step per shooting interval (create_with_discretization) instead of the uniform Ts."""
+        return RefSolver(self, N, Ts, cond_N, dt)
 
     def batch(self, N, Ts, x0, yref, yref_e, x, u, n_rti=1, nthreads=1, cond_N=0):
         n = x0.shape[0]
@@ -161,9 +186,14 @@ class Ref:
 
 
 class RefSolver:
-    def __init__(self, ref, N, Ts, cond_N):
+    def __init__(self, ref, N, Ts, cond_N, dt=None):
         self.lib, self.N, self.Ts = ref.lib, N, Ts
-        self.h = self.lib.cfref_create(N, Ts, cond_N)
+        if dt is None:
+            self.h = self.lib.cfref_create(N, Ts, cond_N)
+        else:
+            dt = np.ascontiguousarray(dt, float)
+            assert dt.size == N
+            self.h = self.lib.cfref_create_dt(N, _P(dt), cond_N)
         if not self.h:
             raise RuntimeError("cfref_create failed")
 
@@ -190,6 +220,13 @@ class RefSolver:
         a = [np.ascontiguousarray(v, float) for v in (x0, yref, yref_e)]
         st = self.lib.cfref_rti(self.h, *[_P(v) for v in a], _P(x), _P(u), ctypes.byref(qi), ctypes.byref(qs), _P(t))
         return st, qi.value, qs.value, t
+
+    def rti_split(self, x0_prep, x0_fb, yref, yref_e, x, u):
+        """rti_phase 1 with x0_prep, then rti_phase 2 with x0_fb; x,u updated in place. Returns (status, qp_iter, qp_status)."""
+        qi, qs = ctypes.c_int(), ctypes.c_int()
+        a = [np.ascontiguousarray(v, float) for v in (x0_prep, x0_fb, yref, yref_e)]
+        st = self.lib.cfref_rti_split(self.h, *[_P(v) for v in a], _P(x), _P(u), ctypes.byref(qi), ctypes.byref(qs))
+        return st, qi.value, qs.value
 
     def qp(self):
         N = self.N

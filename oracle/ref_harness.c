@@ -76,8 +76,21 @@ void cfref_destroy(void *h_)
 }
 
 /* cond_N <= 0 means "what generate_c_code.py yields": qp_cond_N = N. */
+void *cfref_create_dt(int N, const double *dt, int cond_N);
 void *cfref_create(int N, double Ts, int cond_N)
 {
+    double *dt = malloc(sizeof(double) * N);
+    for (int i = 0; i < N; i++) dt[i] = Ts;
+    void *h = cfref_create_dt(N, dt, cond_N);
+    free(dt);
+    return h;
+}
+
+/* The same with one time step per shooting interval, as crazyflie_acados_create_with_discretization does it
+ * (acados_template/c_templates_tera/acados_solver.in.c:133-153,854-892): "Ts" and the cost "scaling" of interval i. */
+void *cfref_create_dt(int N, const double *dt, int cond_N)
+{
+    const double Ts = dt[0];
     cfref *h = calloc(1, sizeof(cfref));
     h->N = N;
     h->Ts = Ts;
@@ -118,8 +131,9 @@ void *cfref_create(int N, double Ts, int cond_N)
     h->ode.evaluate = &ode_eval;
     ocp_nlp_in *in = h->in = ocp_nlp_in_create(config, dims);
     for (int i = 0; i < N; i++) {
-        ocp_nlp_in_set(config, dims, in, i, "Ts", &Ts);
-        ocp_nlp_cost_model_set(config, dims, in, i, "scaling", &Ts);
+        double dti = dt[i];
+        ocp_nlp_in_set(config, dims, in, i, "Ts", &dti);
+        ocp_nlp_cost_model_set(config, dims, in, i, "scaling", &dti);
         ocp_nlp_dynamics_model_set(config, dims, in, i, "expl_vde_forw", &h->vde);
         ocp_nlp_dynamics_model_set(config, dims, in, i, "expl_ode_fun", &h->ode);
     }
@@ -250,6 +264,42 @@ int cfref_rti(void *h_, const double *x0, const double *yref, const double *yref
         ocp_nlp_get(c, h->solver, "time_qp_solver_call", times + 3);
         ocp_nlp_get(c, h->solver, "time_qp_xcond", times + 4);
     }
+    return status;
+}
+
+/* The real-time iteration as the reference's two phases: rti_phase 1 (PREPARATION) with x0_prep in place, then the new
+ * measurement x0_fb and rti_phase 2 (FEEDBACK); ocp_nlp_sqp_rti.c:189-198,1213-1237.  Leaves rti_phase at 0. */
+int cfref_rti_split(void *h_, const double *x0_prep, const double *x0_fb, const double *yref, const double *yref_e,
+                    double *x, double *u, int *qp_iter, int *qp_status)
+{
+    cfref *h = h_;
+    int N = h->N, phase;
+    ocp_nlp_config *c = h->config;
+    ocp_nlp_dims *d = h->dims;
+    ocp_nlp_constraints_model_set(c, d, h->in, 0, "lbx", (void *) x0_prep);
+    ocp_nlp_constraints_model_set(c, d, h->in, 0, "ubx", (void *) x0_prep);
+    for (int k = 0; k < N; k++) ocp_nlp_cost_model_set(c, d, h->in, k, "yref", (void *) (yref + NY * k));
+    ocp_nlp_cost_model_set(c, d, h->in, N, "yref", (void *) yref_e);
+    for (int k = 0; k <= N; k++) {
+        ocp_nlp_out_set(c, d, h->out, k, "x", x + NX * k);
+        if (k < N) ocp_nlp_out_set(c, d, h->out, k, "u", u + NU * k);
+    }
+    phase = 1;
+    ocp_nlp_solver_opts_set(c, h->opts, "rti_phase", &phase);
+    ocp_nlp_solve(h->solver, h->in, h->out);
+    ocp_nlp_constraints_model_set(c, d, h->in, 0, "lbx", (void *) x0_fb);
+    ocp_nlp_constraints_model_set(c, d, h->in, 0, "ubx", (void *) x0_fb);
+    phase = 2;
+    ocp_nlp_solver_opts_set(c, h->opts, "rti_phase", &phase);
+    int status = ocp_nlp_solve(h->solver, h->in, h->out);
+    phase = 0;
+    ocp_nlp_solver_opts_set(c, h->opts, "rti_phase", &phase);
+    for (int k = 0; k <= N; k++) {
+        ocp_nlp_out_get(c, d, h->out, k, "x", x + NX * k);
+        if (k < N) ocp_nlp_out_get(c, d, h->out, k, "u", u + NU * k);
+    }
+    if (qp_iter) ocp_nlp_get(c, h->solver, "qp_iter", qp_iter);
+    if (qp_status) ocp_nlp_get(c, h->solver, "qp_status", qp_status);
     return status;
 }
 

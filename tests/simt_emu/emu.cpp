@@ -212,6 +212,14 @@ static void job_fn(void *a)
     unsigned par = 0;
     cf_rti_instance(j->P, j->bv, j->inst, j->slot, j->sm, par);
 }
+template <int PH, bool VDT>
+static void job_fn_t(void *a)
+{
+    Job *j = (Job *) a;
+    cf_warp_init_smem(j->sm);
+    unsigned par = 0;
+    cf_rti_instance<PH, VDT>(j->P, j->bv, j->inst, j->slot, j->sm, par);
+}
 
 extern "C" long cfemu_scratch_doubles(int N) { return cf_scratch_layout(N).total; }
 extern "C" void cfemu_scratch_offsets(int N, long *out)
@@ -260,6 +268,7 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
     bv.lbu_b = per_inst ? per_inst[2] : nullptr; bv.ubu_b = per_inst ? per_inst[3] : nullptr;
     bv.lbu0_b = per_inst ? per_inst[4] : nullptr; bv.ubu0_b = per_inst ? per_inst[5] : nullptr;
     bv.prof = nullptr;
+    bv.dts = nullptr; bv.prep = nullptr; bv.prep_stride = 0;
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(0);
     std::vector<std::thread> th;
@@ -276,6 +285,58 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
                 Job j{&P, bv, i, slot_a, sm_a};
                 cfemu::run_warp(job_fn, &j);
                 if (scratch_out) memcpy(scratch_out + (size_t) i * stride, slot_a, stride * 8);
+            }
+        });
+    for (auto &t : th) t.join();
+    return 0;
+}
+
+// General variants of the warp program: per-interval time steps `dts` (NULL = uniform Ts) and, with split != 0, the
+// real-time iteration as two phases -- preparation with x0, then (scratch slot and shared memory poisoned in between, as
+// another instance would have used them) feedback with x0_fb (NULL = x0).
+extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int split, const double *x0, const double *x0_fb,
+                                 const double *yref, const double *yref_e, double *x, double *u, int *status, int *qp_iter,
+                                 int *qp_status, int *flags, double *res, int nthreads)
+{
+    CfParams P;
+    static const double Q[13] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
+    for (int i = 0; i < 13; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
+    for (int i = 0; i < 4; i++) { P.Wdiag[13 + i] = 0.06; P.lbu[i] = P.lbu0[i] = 0; P.ubu[i] = P.ubu0[i] = 22; }
+    std::vector<double> dtv(N, Ts);
+    if (dts) dtv.assign(dts, dts + N);
+    P.Ts = dtv[0]; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = 1; P.pad_ = 0;
+    const long stride = cf_scratch_layout(N).total, pstride = cf_prep_stride(N);
+    std::vector<double> prep((size_t) B * pstride + 2, std::nan(""));
+    CfBatchView bv;
+    memset(&bv, 0, sizeof bv);
+    bv.B = B; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
+    bv.qp_iter = qp_iter; bv.qp_status = qp_status; bv.flags = flags; bv.res = res; bv.scratch_stride = stride;
+    bv.dts = dtv.data();
+    bv.prep = (double *) ((((uintptr_t) prep.data()) + 15) & ~(uintptr_t) 15);
+    bv.prep_stride = pstride;
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&]() {
+            std::vector<double> slot(stride + 2, 0.0), sm(CF_SM_DOUBLES + 2, 0.0);
+            double *slot_a = (double *) ((((uintptr_t) slot.data()) + 15) & ~(uintptr_t) 15), *sm_a = (double *) ((((uintptr_t) sm.data()) + 15) & ~(uintptr_t) 15);
+            auto poison = [&]() {
+                for (long q = 0; q < stride; q++) slot_a[q] = std::nan("");
+                for (int q = 0; q < CF_SM_DOUBLES; q++) sm_a[q] = std::nan("");
+            };
+            for (;;) {
+                int i = next.fetch_add(1);
+                if (i >= B) break;
+                poison();
+                Job j{&P, bv, i, slot_a, sm_a};
+                if (!split) cfemu::run_warp(job_fn_t<CF_PH_BOTH, true>, &j);
+                else {
+                    cfemu::run_warp(job_fn_t<CF_PH_PREPARATION, true>, &j);
+                    poison();
+                    if (x0_fb) j.bv.x0 = x0_fb;
+                    cfemu::run_warp(job_fn_t<CF_PH_FEEDBACK, true>, &j);
+                }
             }
         });
     for (auto &t : th) t.join();

@@ -125,3 +125,93 @@ def test_capsule_api_through_ctypes(port):
     assert np.abs(x - xo).max() < 1e-8 and np.abs(u - uo).max() < 1e-8 and abs(qi.value - info.qp_iter) <= 1
     L.crazyflie_acados_free(cap)
     L.crazyflie_acados_free_capsule(cap)
+
+
+@pytest.mark.gpu
+def test_capsule_rti_phases_and_time_steps(port, ref):
+    """Surface B + acados_c: ocp_nlp_solver_opts_set(.., "rti_phase", ..) splits the iteration
+    (ocp_nlp_sqp_rti.c:189-198,1213-1237) and crazyflie_acados_update_time_steps changes the grid of a live solver
+    (acados_solver.in.c:133-153) -- against the reference doing the same."""
+    import ctypes
+    L = cf.lib()
+    vp, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)
+    L.crazyflie_acados_create_capsule.restype = vp
+    for f in ("crazyflie_acados_get_nlp_in", "crazyflie_acados_get_nlp_out", "crazyflie_acados_get_nlp_config",
+              "crazyflie_acados_get_nlp_dims", "crazyflie_acados_get_nlp_solver", "crazyflie_acados_get_nlp_opts"):
+        getattr(L, f).restype = vp
+        getattr(L, f).argtypes = [vp]
+    L.crazyflie_acados_create_with_discretization.argtypes = [vp, ctypes.c_int, dp]
+    L.crazyflie_acados_update_time_steps.argtypes = [vp, ctypes.c_int, dp]
+    L.crazyflie_acados_solve.argtypes = [vp]
+    L.crazyflie_acados_free.argtypes = [vp]
+    L.crazyflie_acados_free_capsule.argtypes = [vp]
+    L.ocp_nlp_constraints_model_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_cost_model_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_out_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_out_get.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_solver_opts_set.argtypes = [vp, vp, ctypes.c_char_p, vp]
+    N, TS = 20, 0.015
+    dt = TS * np.linspace(0.5, 2.0, N)
+    w = wl.helix_batch(1, N, seed=6)
+    x0_fb = w["x0"][0] + 0.01
+    x0_fb[3:7] /= np.linalg.norm(x0_fb[3:7])
+    cap = L.crazyflie_acados_create_capsule()
+    steps = (ctypes.c_double * N)(*dt)
+    assert L.crazyflie_acados_create_with_discretization(cap, N, steps) == 0
+    cfg, dims, nin, nout, opts = (L.crazyflie_acados_get_nlp_config(cap), L.crazyflie_acados_get_nlp_dims(cap),
+                                  L.crazyflie_acados_get_nlp_in(cap), L.crazyflie_acados_get_nlp_out(cap),
+                                  L.crazyflie_acados_get_nlp_opts(cap))
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+
+    def load(x0):
+        x0 = np.ascontiguousarray(x0)
+        assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"lbx", P(x0)) == 0
+        assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"ubx", P(x0)) == 0
+
+    def phase(v):
+        v = ctypes.c_int(v)
+        L.ocp_nlp_solver_opts_set(cfg, opts, b"rti_phase", ctypes.byref(v))
+
+    def read():
+        x, u = np.zeros((N + 1, 13)), np.zeros((N, 4))
+        for k in range(N + 1):
+            L.ocp_nlp_out_get(cfg, dims, nout, k, b"x", P(x[k]))
+        for k in range(N):
+            L.ocp_nlp_out_get(cfg, dims, nout, k, b"u", P(u[k]))
+        return x, u
+
+    for k in range(N):
+        assert L.ocp_nlp_cost_model_set(cfg, dims, nin, k, b"yref", P(w["yref"][0, k])) == 0
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"u", P(w["u_init"][0, k]))
+    assert L.ocp_nlp_cost_model_set(cfg, dims, nin, N, b"yref", P(w["yref_e"][0])) == 0
+    for k in range(N + 1):
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"x", P(w["x_init"][0, k]))
+    # preparation with the old measurement, feedback with the new one, on the non-uniform grid
+    load(w["x0"][0])
+    phase(1)
+    assert L.crazyflie_acados_solve(cap) == 0
+    xp, up = read()
+    assert np.array_equal(xp, w["x_init"][0]) and np.array_equal(up, w["u_init"][0])   # the preparation moves nothing
+    load(x0_fb)
+    phase(2)
+    assert L.crazyflie_acados_solve(cap) == 0
+    x, u = read()
+    sr = ref.solver(N, TS, dt=dt)
+    xr, ur = w["x_init"][0].copy(), w["u_init"][0].copy()
+    assert sr.rti_split(w["x0"][0], x0_fb, w["yref"][0], w["yref_e"][0], xr, ur)[0] == 0
+    sr.close()
+    assert np.abs(x - xr).max() < 1e-8 and np.abs(u - ur).max() < 1e-8
+    # a second feedback without a preparation fails loudly (the reference would silently re-use stale data)
+    assert L.crazyflie_acados_solve(cap) != 0
+    # back to the uniform grid on the live solver, fused phase: continues from the iterate above
+    phase(0)
+    steps_u = (ctypes.c_double * N)(*([TS] * N))
+    assert L.crazyflie_acados_update_time_steps(cap, N, steps_u) == 0
+    assert L.crazyflie_acados_update_time_steps(cap, N + 1, steps_u) != 0
+    assert L.crazyflie_acados_solve(cap) == 0
+    x2, u2 = read()
+    xo, uo = x.copy(), u.copy()
+    st, info = port.rti(N, TS, x0_fb, w["yref"][0], w["yref_e"][0], xo, uo)
+    assert st == 0 and np.abs(x2 - xo).max() < 1e-8 and np.abs(u2 - uo).max() < 1e-8
+    L.crazyflie_acados_free(cap)
+    L.crazyflie_acados_free_capsule(cap)

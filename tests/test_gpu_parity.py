@@ -320,3 +320,92 @@ def test_device_resident_inputs_with_torch(port):
         torch.cuda.synchronize()
         o = oracle_solve(port, w, N)
         assert rel_err(u0.cpu().numpy(), o["u"][:, 0]) <= TIGHT
+
+
+def _moved(x0, seed, scale=0.02):
+    x = x0 + scale * np.random.default_rng(seed).standard_normal(x0.shape)
+    x[..., 3:7] /= np.linalg.norm(x[..., 3:7], axis=-1, keepdims=True)
+    return np.ascontiguousarray(x)
+
+
+def _outputs(s):
+    return dict(x=s.get("x_all"), u=s.get("u_all"), status=s.get("status"), qp_iter=s.get("qp_iter"), flags=s.get("flags"))
+
+
+def test_split_phases_equal_the_fused_step():
+    """prepare + feedback with unchanged inputs is bit-identical to one cfnmpc_batch_solve; a feedback without a
+    preparation that belongs to the iterate is a call-sequence error."""
+    N, B = 50, 300
+    w = wl.helix_batch(B, N, seed=21)
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("lin_res_check", 1)
+        a = _outputs(s.set_problem(w).solve(1))
+        with pytest.raises(cf.CfnmpcError):
+            s.feedback()                       # the solve moved the iterate
+        b = _outputs(s.set_problem(w).prepare().feedback())
+        with pytest.raises(cf.CfnmpcError):
+            s.feedback()                       # consumed
+        # two consecutive split iterations = two fused ones
+        c = _outputs(s.prepare().feedback())
+        d = _outputs(s.set_problem(w).solve(2))
+    for k in ("x", "u", "status", "qp_iter"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(c[k], d[k]), k
+    assert (b["flags"] == 0).all() and (b["status"] == 0).all()
+
+
+def test_split_phases_match_reference(port, ref):
+    """rti_phase 1 with one measurement, rti_phase 2 with the next (ocp_nlp_sqp_rti.c:495-683,1213-1237): against the
+    reference's own two phases, and (whole batch) the port."""
+    N, B = 50, 160
+    w = wl.helix_batch(B, N, seed=22)
+    x0_fb = _moved(w["x0"], 23)
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("lin_res_check", 1)
+        s.set_problem(w).prepare()
+        g = _outputs(s.set("x0", x0_fb).feedback())
+    assert (g["status"] == 0).all() and (g["flags"] == 0).all()
+    w2 = dict(w, x0=x0_fb)
+    o = oracle_solve(port, w2, N)
+    assert rel_err(g["x"], o["x"]) <= TIGHT and rel_err(g["u"], o["u"]) <= TIGHT
+    for i in range(0, B, 20):
+        sr = ref.solver(N, TS)
+        xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+        st, qi, _ = sr.rti_split(w["x0"][i], x0_fb[i], w["yref"][i], w["yref_e"][i], xr, ur)
+        sr.close()
+        assert st == g["status"][i] and abs(qi - g["qp_iter"][i]) <= 1
+        assert rel_err(g["x"][i], xr) <= TIGHT and rel_err(g["u"][i], ur) <= TIGHT
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_nonuniform_time_grid(port, ref, split):
+    """One time step per shooting interval = its cost scaling (crazyflie_acados_create_with_discretization /
+    _update_time_steps, acados_solver.in.c:133-153): against the reference built with that grid, and the port."""
+    N, B = 30, 96
+    dt = TS * np.concatenate([np.full(8, 0.5), np.linspace(0.6, 2.5, N - 8)])
+    w = wl.hover_batch(B, N, seed=24)
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("lin_res_check", 1)
+        s.set("time_steps", dt).set_problem(w)
+        g = _outputs(s.prepare().feedback() if split else s.solve(1))
+        # back to a uniform grid: the specialised kernel again, same numbers as a solver created that way
+        h = _outputs(s.set("time_steps", np.full(N, TS)).set_problem(w).solve(1))
+        with pytest.raises(cf.CfnmpcError):
+            s.set("time_steps", np.zeros(N))
+    assert (g["status"] == 0).all() and (g["flags"] == 0).all()
+    port.set_time_steps(dt)
+    try:
+        o = oracle_solve(port, w, N)
+    finally:
+        port.set_time_steps(None)
+    assert rel_err(g["x"], o["x"]) <= TIGHT and rel_err(g["u"], o["u"]) <= TIGHT
+    for i in range(0, B, 16):
+        sr = ref.solver(N, TS, dt=dt)
+        xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+        st, qi, _, _ = sr.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)
+        sr.close()
+        assert st == g["status"][i] and abs(qi - g["qp_iter"][i]) <= 1
+        assert rel_err(g["x"][i], xr) <= TIGHT and rel_err(g["u"][i], ur) <= TIGHT
+    hu = gpu_solve(w, N)
+    assert np.array_equal(h["x"], hu["x"]) and np.array_equal(h["u"], hu["u"])
+    assert rel_err(g["u"], hu["u"]) > 1e-4      # and the grid matters

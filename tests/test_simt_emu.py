@@ -150,3 +150,93 @@ def test_emulated_kernel_nan_measurement(emu, port):
     assert np.array_equal(r["x"][2], w["x_init"][2]) and np.array_equal(r["u"][2], w["u_init"][2])
     ok = np.arange(B) != 2
     assert rel_err(r["x"][ok], x[ok]) < 1e-9 and rel_err(r["u"][ok], u[ok]) < 1e-9
+
+
+@pytest.fixture(scope="module")
+def emu_general():
+    """The general kernel variants (per-interval time steps, split phases) under the lock-step emulation."""
+    subprocess.run([sys.executable, os.path.join(HERE, "simt_emu", "build.py")], check=True)
+    L = ctypes.CDLL(os.path.join(HERE, "simt_emu", "libcfemu.so"))
+    L.cfemu_rti_general.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
+                                    _ip, _ip, _ip, _ip, _dp, ctypes.c_int]
+
+    def run(w, N, dts=None, split=False, x0_fb=None):
+        B = w["x0"].shape[0]
+        x, u = w["x_init"].copy(), w["u_init"].copy()
+        st, it, qs, fl = [np.full(B, -7, np.int32) for _ in range(4)]
+        res = np.zeros((B, 4))
+        P = lambda a: a.ctypes.data_as(_dp) if a is not None else None
+        I = lambda a: a.ctypes.data_as(_ip)
+        dts = None if dts is None else np.ascontiguousarray(dts, float)
+        x0_fb = None if x0_fb is None else np.ascontiguousarray(x0_fb, float)
+        L.cfemu_rti_general(B, N, TS, P(dts), int(split), P(w["x0"]), P(x0_fb), P(w["yref"]), P(w["yref_e"]), P(x), P(u),
+                            I(st), I(it), I(qs), I(fl), P(res), 4)
+        return dict(x=x, u=u, status=st, qp_iter=it, qp_status=qs, flags=fl, res=res)
+    return run
+
+
+def moved_measurement(x0, seed, scale=0.02):
+    """A second measurement a little away from the first (quaternion re-normalised)."""
+    x = x0 + scale * np.random.default_rng(seed).standard_normal(x0.shape)
+    x[..., 3:7] /= np.linalg.norm(x[..., 3:7], axis=-1, keepdims=True)
+    return np.ascontiguousarray(x)
+
+
+def test_emulated_general_variant_equals_specialised_kernel(emu, emu_general, gold):
+    """VDT variant on a uniform grid and prepare + feedback with an unchanged x0: bit-identical to the fused kernel."""
+    w = batch(gold, "helix", 3)
+    a = emu(w, 50)
+    for kw in (dict(), dict(split=True)):
+        b = emu_general(w, 50, **kw)
+        assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["u"], b["u"])
+        assert (a["status"] == b["status"]).all() and (a["qp_iter"] == b["qp_iter"]).all() and (b["flags"] == 0).all()
+
+
+def test_emulated_split_phases_match_reference(emu_general, port, ref):
+    """rti_phase 1 with one measurement, rti_phase 2 with the next one (ocp_nlp_sqp_rti.c:495-683), against the
+    reference's own two phases and the port."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    N, B = 20, 5
+    w = wl.helix_batch(B, N, seed=5)
+    x0_fb = moved_measurement(w["x0"], 11)
+    r = emu_general(w, N, split=True, x0_fb=x0_fb)
+    assert (r["status"] == 0).all() and (r["flags"] == 0).all()
+    for i in range(B):
+        s = ref.solver(N, TS)
+        xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+        st, qi, _ = s.rti_split(w["x0"][i], x0_fb[i], w["yref"][i], w["yref_e"][i], xr, ur)
+        s.close()
+        assert st == r["status"][i] and abs(qi - r["qp_iter"][i]) <= 1
+        assert rel_err(r["x"][i], xr) < 1e-9 and rel_err(r["u"][i], ur) < 1e-9
+        xp, up = w["x_init"][i].copy(), w["u_init"][i].copy()
+        port.rti_split(N, TS, w["x0"][i], x0_fb[i], w["yref"][i], w["yref_e"][i], xp, up)
+        assert rel_err(r["x"][i], xp) < 1e-9 and rel_err(r["u"][i], up) < 1e-9
+        assert np.allclose(r["x"][i, 0], x0_fb[i], rtol=0, atol=1e-15)   # x_0 lands on the feedback-time measurement
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_emulated_nonuniform_grid_matches_reference(emu_general, port, ref, split):
+    """One time step per shooting interval = its cost scaling (create_with_discretization,
+    acados_solver.in.c:133-153), against the reference built with that grid and the port."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    N, B = 20, 4
+    dt = TS * np.concatenate([np.full(6, 0.5), np.linspace(0.6, 2.5, N - 6)])
+    w = wl.hover_batch(B, N, seed=9)
+    r = emu_general(w, N, dts=dt, split=split)
+    assert (r["status"] == 0).all() and (r["flags"] == 0).all()
+    port.set_time_steps(dt)
+    try:
+        for i in range(B):
+            s = ref.solver(N, TS, dt=dt)
+            xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+            st, qi, _, _ = s.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)
+            s.close()
+            assert st == r["status"][i] and abs(qi - r["qp_iter"][i]) <= 1
+            assert rel_err(r["x"][i], xr) < 1e-9 and rel_err(r["u"][i], ur) < 1e-9
+            xp, up = w["x_init"][i].copy(), w["u_init"][i].copy()
+            port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], xp, up)
+            assert rel_err(r["x"][i], xp) < 1e-9 and rel_err(r["u"][i], up) < 1e-9
+    finally:
+        port.set_time_steps(None)
+    # and the grid matters: the uniform solution is different
+    assert rel_err(emu_general(w, N)["u"], r["u"]) > 1e-4
