@@ -270,11 +270,12 @@ def run_ours(args):
     # kernel-only time of the dominant kernel, CUDA events on its own stream, averaged over the timed steps
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, launches = timed(step_device, args.steps)
-    kern_ms = []
+    kern_ms, phase_ms = [], []
     for _ in range(min(args.steps, 5)):
         s.set("x", d_in["x_init"]).set("u", d_in["u_init"])
         s.solve(1)
         kern_ms.append(s.last_solve_ms())
+        phase_ms.append(s.last_phase_ms())
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         step_e2e()
@@ -300,7 +301,11 @@ def run_ours(args):
         value = world * B / (ms_step * 1e-3)
         e2e_v = world * B / (ms_e2e / args.steps * 1e-3)
         peaks, how = measured_peaks()
+        # the RTI step is two launches by default (preparation kernel, feedback kernel): the algorithmic bytes belong to
+        # the step, so they are set against the sum; the feedback kernel is the dominant one
         k_ms = float(np.mean(kern_ms))
+        prep_ms, fb_ms = (float(v) for v in np.mean(np.array(phase_ms), axis=0))
+        two = bool(s.info("two_kernels"))
         achieved = B * alg_bytes(N) / (k_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
@@ -310,7 +315,9 @@ def run_ours(args):
             except Exception:
                 traffic = None
         roofline = dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                        traffic=traffic, kernel="cf_rti_kernel", kernel_ms=k_ms, peak_source=how,
+                        traffic=traffic, kernel_ms=k_ms, peak_source=how,
+                        kernel="cf_rti_kernel<4,4,FEEDBACK> (dominant) after cf_rti_kernel<4,3,PREPARATION>" if two else "cf_rti_kernel<4,3> (fused)",
+                        kernels_ms=dict(preparation=prep_ms, feedback=fb_ms) if two else None,
                         alg_bytes_per_solve=alg_bytes(N),
                         note="algorithmic bytes = x0 + yref + iterate in/out (SURVEY 8d); real traffic is dominated by factor/linearisation spill")
         cpu = None
@@ -326,8 +333,12 @@ def run_ours(args):
                                 batch_per_gpu=B, global_batch=world * B, horizon=N, parallelism=f"dp{world} (independent shards"
                                 + (", NCCL all-gather of u0)" if world > 1 else ")"),
                                 l2="inputs larger than L2 (iterate+yref 900 MB, scratch %d MB per GPU)" % (s.info("scratch_bytes") >> 20),
-                                occupancy=dict(warps_per_sm=s.info("blocks_per_sm") * s.info("warps_per_block"), regs=s.info("regs_per_thread"),
-                                               grid=s.info("grid"))),
+                                occupancy=(dict(kernels="preparation + feedback", warps_per_sm=s.info("feedback_blocks_per_sm") * 4,
+                                                regs=s.info("feedback_regs_per_thread"), grid=s.info("feedback_grid"),
+                                                preparation=dict(warps_per_sm=12, grid=s.info("preparation_grid")),
+                                                prepared_mb=s.info("prepared_bytes") >> 20) if two else
+                                           dict(kernels="fused", warps_per_sm=s.info("blocks_per_sm") * s.info("warps_per_block"),
+                                                regs=s.info("regs_per_thread"), grid=s.info("grid")))),
                     clocks=clocks, e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                             ms_per_step=ms_e2e / args.steps, upload_chunks=args.e2e_chunks),
                     e2e_closed_loop=dict(value=world * B / (ms_tick / args.steps * 1e-3), unit=UNIT, ms_per_step=ms_tick / args.steps,

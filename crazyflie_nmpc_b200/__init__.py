@@ -53,6 +53,7 @@ def lib():
         L.cfnmpc_batch_device_ptr.argtypes = [vp, cp, ctypes.POINTER(vp)]
         L.cfnmpc_batch_info.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_longlong)]
         L.cfnmpc_batch_last_solve_ms.argtypes = [vp, ctypes.POINTER(cd)]
+        L.cfnmpc_batch_last_phase_ms.argtypes = [vp, ctypes.POINTER(cd)]
         L.cfnmpc_debug_scratch.argtypes = [vp, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_longlong)]
         L.cfnmpc_debug_max_ipm_iter.argtypes = [vp, ci]
         L.cfnmpc_debug_pass_cycles.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
@@ -269,6 +270,12 @@ class BatchSolver:
         v = ctypes.c_double()
         _check(lib().cfnmpc_batch_last_solve_ms(self._h, ctypes.byref(v)))
         return v.value
+
+    def last_phase_ms(self):
+        """(preparation kernel ms, feedback kernel ms) of the last step; (0, total) when it ran as one fused kernel."""
+        v = (ctypes.c_double * 2)()
+        _check(lib().cfnmpc_batch_last_phase_ms(self._h, v))
+        return v[0], v[1]
 
     # ---- test hooks
     def debug_scratch(self):

@@ -379,6 +379,7 @@ struct CfWarpT
             else g = (k == 0) ? 0.0 : (P->Wdiag[lane - CF_NU] * (NOMS[lane - CF_NU] - yr_pre)) * h;
             rqdst[lane] = g;
         }
+        if (PH == CF_PH_PREPARATION && lane == CF_NV) rqdst[lane] = 0.0;   // pad of the 18-double gradient record
         if (PH != CF_PH_PREPARATION) stage_bounds_init(k, uk);
         cf_syncwarp();
         if (lane == 0) cf_bulk_s2g(mdst, MS, CF_MSZ * 8);
@@ -450,30 +451,37 @@ struct CfWarpT
     // is evaluated now, together with the initial interior-point variables.
     CF_MEM void load_prepared(const double *xg, const double *ug, const double *x0g)
     {
-        double *MS = sm + CF_SM_MS0;
+        // Four stage records per trip travel prepared store -> shared memory -> scratch slot on the TMA engine (one bulk
+        // load of the contiguous records, two bulk stores per stage: [B';A';b'] and the gradient); the lanes meanwhile
+        // evaluate the bound vectors and the initial interior-point variables of those stages.
+        double *ST = sm;
+        static_assert(4 * CF_PREP_STAGE <= CF_SM_V0, "staging area of load_prepared");
+        pass_begin();   // generic accesses of the previous instance to this shared memory precede the bulk writes
         CF_NOUNROLL
-        for (int k = 0; k < N; k++) {
-            const double *src = PREP + (long) k * CF_PREP_STAGE;
-            double *dst = (k == 0) ? MS : blk(k) + B_M;
-            CF_UNROLL
-            for (int q = 0; q < 4; q++) {
-                const int i = lane + 32 * q;
-                if (i < CF_MSZ / 2) { const cf_d2 v = cf_ld2(src + 2 * i); cf_st2(dst + 2 * i, v.x, v.y); }
+        for (int k0 = 0; k0 < N; k0 += 4) {
+            const int n = (N - k0 < 4) ? N - k0 : 4;
+            if (lane == 0) {
+                cf_bulk_expect(bar, n * CF_PREP_STAGE * 8);
+                cf_bulk_g2s_raw(ST, PREP + (long) k0 * CF_PREP_STAGE, n * CF_PREP_STAGE * 8, bar);
             }
-            if (k == 0) {
-                cf_syncwarp();
-                eliminate_x0(MS, xg, x0g);
-                CF_UNROLL
-                for (int q = 0; q < 4; q++) {
-                    const int i = lane + 32 * q;
-                    if (i < CF_MSZ / 2) { const cf_d2 v = cf_ld2(MS + 2 * i); cf_st2(blk(0) + B_M + 2 * i, v.x, v.y); }
+            CF_NOUNROLL
+            for (int q = 0; q < n; q++) stage_bounds_init(k0 + q, lane < CF_NU ? ug[(k0 + q) * CF_NU + lane] : 0.0);
+            wait(0);
+            if (k0 == 0) eliminate_x0(ST, xg, x0g);
+            cf_syncwarp();
+            if (lane == 0) {
+                CF_NOUNROLL
+                for (int q = 0; q < n; q++) {
+                    cf_bulk_s2g(blk(k0 + q) + B_M, ST + q * CF_PREP_STAGE, CF_MSZ * 8);
+                    cf_bulk_s2g(rec(k0 + q) + R_RQ, ST + q * CF_PREP_STAGE + CF_MSZ, 18 * 8);
                 }
+                cf_bulk_s2g_wait_read0();   // the staging area may be refilled
             }
-            if (lane < CF_NV) rec(k)[R_RQ + lane] = src[CF_MSZ + lane];
-            stage_bounds_init(k, lane < CF_NU ? ug[k * CF_NU + lane] : 0.0);
+            cf_syncwarp();
         }
         init_stage_vectors(N, 0.0);
         if (lane < CF_NV) rec(N)[R_RQ + lane] = PREP[(long) N * CF_PREP_STAGE + lane];
+        if (lane == 0) cf_bulk_s2g_wait_all();   // every block has landed in the slot before the sweeps fetch it
     }
 
     // =============================================================== IPM pieces

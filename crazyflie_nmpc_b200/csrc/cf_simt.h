@@ -60,6 +60,7 @@ CF_DEV double cf_rcp_seed(double x) { return (double) (float) (1.0 / x); }      
 #define cf_bulk_s2g(dst, src, bytes) cfemu::bulk_s2g((dst), (src), (bytes), __LINE__)
 #define cf_bulk_s2g_wait_all() cfemu::bulk_s2g_wait(0, __LINE__)
 #define cf_bulk_s2g_wait_read1() cfemu::bulk_s2g_wait(1, __LINE__)
+#define cf_bulk_s2g_wait_read0() cfemu::bulk_s2g_wait(0, __LINE__)
 CF_DEV void cf_fence_proxy_async() {}
 #define cf_dmma(d0, d1, a, b) cfemu::dmma((d0), (d1), (a), (b), __LINE__)
 #else
@@ -136,6 +137,8 @@ CF_DEV void cf_bulk_s2g(void *dst, const void *src, int bytes)
 CF_DEV void cf_bulk_s2g_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // Issuing lane: all but the most recent bulk store have finished READING their shared source.
 CF_DEV void cf_bulk_s2g_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// Issuing lane: every bulk store has finished READING its shared source (the staging area may be refilled).
+CF_DEV void cf_bulk_s2g_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // fp64 tensor-core tile product D(8x8) += A(8x4) * B(4x8), fragments as in the PTX ISA for m8n8k4:
 // a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], d0/d1 = D[lane>>2][2*(lane&3) + {0,1}]   (SASS DMMA)
 CF_DEV void cf_dmma(double &d0, double &d1, double a, double b)

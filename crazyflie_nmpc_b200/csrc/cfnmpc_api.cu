@@ -124,6 +124,14 @@ struct cfnmpc_batch
     void (*kernel_vdt)(const CfParams, const CfBatchView) = nullptr;
     void (*kernel_prep)(const CfParams, const CfBatchView) = nullptr;
     void (*kernel_fb)(const CfParams, const CfBatchView) = nullptr;
+    // the two halves specialised for the uniform grid: cfnmpc_batch_solve as two launches (option "two_kernels")
+    void (*kernel_prep_u)(const CfParams, const CfBatchView) = nullptr;
+    void (*kernel_fb_u)(const CfParams, const CfBatchView) = nullptr;
+    bool two_kernels = true;
+    int grid_prep_u = 0, prep_minb = 3;
+    int grid_fb = 0, fb_minb = 4, fb_regs = 0, fb_blocks_per_sm = 0;
+    cudaEvent_t ev_mid = nullptr;     // between the two launches of a two-kernel step
+    bool mid_valid = false;
     size_t smem_general = 0;
     int grid_general = 0;
     double *d_dts = nullptr, *d_prep = nullptr;
@@ -158,6 +166,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_free) cudaEventDestroy(h->ev_free);
+    if (h->ev_mid) cudaEventDestroy(h->ev_mid);
     if (h->d_ready) cudaFree(h->d_ready);
     if (h->h_ready) cudaFreeHost(h->h_ready);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -191,6 +200,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     h->stream = h->own_stream;
     CKH(cudaEventCreate(&h->ev0));
     CKH(cudaEventCreate(&h->ev1));
+    CKH(cudaEventCreate(&h->ev_mid));
     cudaDeviceProp prop;
     CKH(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
@@ -211,7 +221,27 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     h->kernel_vdt = cf_rti_kernel<4, 3, CF_PH_BOTH, true>;
     h->kernel_prep = cf_rti_kernel<4, 3, CF_PH_PREPARATION, true>;
     h->kernel_fb = cf_rti_kernel<4, 3, CF_PH_FEEDBACK, true>;
+    h->kernel_prep_u = cf_rti_kernel<4, 3, CF_PH_PREPARATION, false>;
+    h->kernel_fb_u = cf_rti_kernel<4, 3, CF_PH_FEEDBACK, false>;
+    // Default step = two launches (profiles/README.md, "two kernels"): the preparation at 4 x 3 blocks per SM (168 registers,
+    // the linearisation needs them), the feedback at 4 x 4 (16 warps per SM at 128 registers).  CFNMPC_TWO_KERNELS=0 /
+    // option "two_kernels" 0 returns to the single fused kernel, CFNMPC_FB_MIN_BLOCKS=3 to a 4 x 3 feedback kernel.
+    if (const char *e = getenv("CFNMPC_FB_MIN_BLOCKS")) h->fb_minb = atoi(e);
+    if (h->fb_minb == 4) h->kernel_fb_u = cf_rti_kernel<4, 4, CF_PH_FEEDBACK, false>;
+    else h->fb_minb = 3;
+    if (const char *e = getenv("CFNMPC_PREP_MIN_BLOCKS"))
+        if (atoi(e) == 4) { h->kernel_prep_u = cf_rti_kernel<4, 4, CF_PH_PREPARATION, false>; h->prep_minb = 4; }
     h->smem_general = (size_t) 4 * CF_SM_DOUBLES * sizeof(double);
+    CKH(cudaFuncSetAttribute(h->kernel_prep_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
+    CKH(cudaFuncSetAttribute(h->kernel_fb_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
+    if (const char *e = getenv("CFNMPC_TWO_KERNELS")) h->two_kernels = atoi(e) != 0;
+    {
+        cudaFuncAttributes fb;
+        CKH(cudaFuncGetAttributes(&fb, h->kernel_fb_u));
+        h->fb_regs = fb.numRegs;
+        CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fb_blocks_per_sm, h->kernel_fb_u, 128, h->smem_general));
+        if (h->fb_blocks_per_sm < 1) { cfnmpc_batch_destroy(h); return fail(CFNMPC_ECUDA, "feedback kernel does not fit on an SM"); }
+    }
     CKH(cudaFuncSetAttribute(h->kernel_vdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
     CKH(cudaFuncSetAttribute(h->kernel_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
     CKH(cudaFuncSetAttribute(h->kernel_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
@@ -228,6 +258,14 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     // the general variants run 4 warps per block on the same scratch slots: never more blocks than n_slots / 4
     h->grid_general = h->n_slots / 4 > 0 ? h->n_slots / 4 : 1;
     if (h->n_slots < 4) h->n_slots = 4;
+    {
+        const long want_fb = (long) h->sm_count * h->fb_blocks_per_sm, need_fb = ((long) batch + 3) / 4;
+        h->grid_fb = (int) (want_fb < need_fb ? want_fb : need_fb);
+        if (h->grid_fb * 4 > h->n_slots) h->n_slots = h->grid_fb * 4;
+        const long want_p = (long) h->sm_count * h->prep_minb;
+        h->grid_prep_u = (int) (want_p < need_fb ? want_p : need_fb);
+        if (h->grid_prep_u * 4 > h->n_slots) h->n_slots = h->grid_prep_u * 4;
+    }
     const long stride = cf_scratch_layout(N).total;
     const size_t B = batch;
     CKH(cudaMalloc(&h->d_x0, B * CF_NX * 8));
@@ -404,6 +442,7 @@ extern "C" int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int 
 {
     if (!h || !option) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set_option: null argument");
     if (!strcmp(option, "lin_res_check")) h->P.lin_res_check = value != 0;
+    else if (!strcmp(option, "two_kernels")) h->two_kernels = value != 0;
     else if (!strcmp(option, "max_ipm_iter")) h->P.max_ipm_iter = (value > 0 && value < CF_ITER_MAX) ? value : CF_ITER_MAX;
     else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_set_option: unknown option '") + option + "'");
     return CFNMPC_OK;
@@ -422,16 +461,26 @@ extern "C" int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field)
     return CFNMPC_OK;
 }
 
+static int ensure_prep_store(cfnmpc_batch *h);
 extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
 {
     if (!h) return fail(CFNMPC_EINVAL, "null handle");
     if (n_rti < 1) return fail(CFNMPC_EINVAL, "cfnmpc_batch_solve: n_rti must be >= 1");
     CK(cudaSetDevice(h->device));
+    if (h->two_kernels && !h->vdt && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;   // no room: the fused kernel
+    h->mid_valid = false;
     CK(cudaEventRecord(h->ev0, h->stream));
     for (int r = 0; r < n_rti; r++) {
         CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
         if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
-        else h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, h->bv);
+        else if (h->two_kernels) {
+            h->kernel_prep_u<<<h->grid_prep_u, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+            if (r == n_rti - 1) { CK(cudaEventRecord(h->ev_mid, h->stream)); h->mid_valid = n_rti == 1; }
+            h->kernel_fb_u<<<h->grid_fb, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+            h->launches++;
+        } else h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, h->bv);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -442,20 +491,27 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
 }
 
 // Split real-time iteration: rti_phase 1 / 2 of the reference (ocp_nlp_sqp_rti.c:189-198,1213-1237).
-extern "C" int cfnmpc_batch_prepare(cfnmpc_batch *h)
+static int ensure_prep_store(cfnmpc_batch *h)
 {
-    if (!h) return fail(CFNMPC_EINVAL, "null handle");
-    CK(cudaSetDevice(h->device));
     if (!h->d_prep) {
         const size_t bytes = (size_t) h->B * h->bv.prep_stride * 8;
         cudaError_t e = cudaMalloc(&h->d_prep, bytes);
         if (e != cudaSuccess) {
             h->d_prep = nullptr;
-            return fail(CFNMPC_ECUDA, std::string("cfnmpc_batch_prepare: cannot allocate the prepared linearisations (") +
-                                          std::to_string(bytes >> 20) + " MiB): " + cudaGetErrorString(e));
+            return fail(CFNMPC_ECUDA, std::string("cannot allocate the prepared linearisations (") + std::to_string(bytes >> 20) +
+                                          " MiB): " + cudaGetErrorString(e));
         }
         h->bv.prep = h->d_prep;
     }
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_prepare(cfnmpc_batch *h)
+{
+    if (!h) return fail(CFNMPC_EINVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_prep_store(h)) return rc;
+    h->mid_valid = false;
     CK(cudaEventRecord(h->ev0, h->stream));
     CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
     h->kernel_prep<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
@@ -472,6 +528,7 @@ extern "C" int cfnmpc_batch_feedback(cfnmpc_batch *h)
     if (!h) return fail(CFNMPC_EINVAL, "null handle");
     if (!h->prepared) return fail(CFNMPC_ESTATE, "cfnmpc_batch_feedback: no preparation phase belongs to the current iterate");
     CK(cudaSetDevice(h->device));
+    h->mid_valid = false;
     CK(cudaEventRecord(h->ev0, h->stream));
     CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
     h->kernel_fb<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
@@ -495,6 +552,8 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
     if (n_chunks > CF_MAX_CHUNKS) n_chunks = CF_MAX_CHUNKS;
     if (n_chunks > h->B) n_chunks = h->B;
     CK(cudaSetDevice(h->device));
+    if (h->two_kernels && !h->vdt && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;
+    h->mid_valid = false;
     if (!h->copy_stream) {
         CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
@@ -527,7 +586,16 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
     CfBatchView bv = h->bv;
     bv.ready = h->d_ready;
     if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, bv);
-    else h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, bv);
+    else if (h->two_kernels) {
+        // the preparation follows the upload front; by the time it has finished every input is in place
+        bv.prep = h->d_prep;
+        h->kernel_prep_u<<<h->grid_prep_u, 128, h->smem_general, h->stream>>>(h->P, bv);
+        CK(cudaGetLastError());
+        CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+        bv.ready = nullptr;
+        h->kernel_fb_u<<<h->grid_fb, 128, h->smem_general, h->stream>>>(h->P, bv);
+        h->launches++;
+    } else h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, bv);
     CK(cudaGetLastError());
     h->launches++;
     h->prepared = false;
@@ -786,6 +854,12 @@ extern "C" int cfnmpc_batch_info(cfnmpc_batch *h, const char *what, long long *v
     else if (!strcmp(what, "smem_per_block")) *value = (long long) h->smem;
     else if (!strcmp(what, "scratch_bytes")) *value = (long long) h->n_slots * h->bv.scratch_stride * 8;
     else if (!strcmp(what, "launches")) *value = h->launches;
+    else if (!strcmp(what, "two_kernels")) *value = h->two_kernels && !h->vdt;
+    else if (!strcmp(what, "feedback_regs_per_thread")) *value = h->fb_regs;
+    else if (!strcmp(what, "feedback_blocks_per_sm")) *value = h->fb_blocks_per_sm;
+    else if (!strcmp(what, "feedback_grid")) *value = h->grid_fb;
+    else if (!strcmp(what, "preparation_grid")) *value = h->grid_prep_u;
+    else if (!strcmp(what, "prepared_bytes")) *value = h->d_prep ? (long long) h->B * h->bv.prep_stride * 8 : 0;
     else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_info: unknown property '") + what + "'");
     return CFNMPC_OK;
 }
@@ -799,6 +873,26 @@ extern "C" int cfnmpc_batch_last_solve_ms(cfnmpc_batch *h, double *ms)
     float f = 0;
     CK(cudaEventElapsedTime(&f, h->ev0, h->ev1));
     *ms = f;
+    return CFNMPC_OK;
+}
+
+extern "C" int cfnmpc_batch_last_phase_ms(cfnmpc_batch *h, double *ms2)
+{
+    if (!h || !ms2) return fail(CFNMPC_EINVAL, "null argument");
+    if (!h->timed) return fail(CFNMPC_ESTATE, "cfnmpc_batch_last_phase_ms: no solve has been enqueued");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev1));
+    float f = 0;
+    if (h->mid_valid) {
+        CK(cudaEventElapsedTime(&f, h->ev0, h->ev_mid));
+        ms2[0] = f;
+        CK(cudaEventElapsedTime(&f, h->ev_mid, h->ev1));
+        ms2[1] = f;
+    } else {
+        CK(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+        ms2[0] = 0.0;
+        ms2[1] = f;
+    }
     return CFNMPC_OK;
 }
 

@@ -97,7 +97,12 @@ int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field);
  *                   its safety nets (x_ocp_qp_ipm.c:2029-2059 LQ re-factorisation, :2311-2318 iterative refinement) and
  *                   report in "flags" where the reference would have taken one of them.  Diagnostic only: the nets
  *                   themselves are not implemented (they never fire on this OCP), results do not depend on the option.
- *   "max_ipm_iter"  (default 50 = qp_solver_iter_max of the reference configuration) */
+ *   "max_ipm_iter"  (default 50 = qp_solver_iter_max of the reference configuration)
+ *   "two_kernels"   (default 1) cfnmpc_batch_solve / _solve_from_host / _tick run the step as two launches -- preparation
+ *                   of every instance, then feedback of every instance, the linearisations travelling through a
+ *                   per-instance store of 8 * (252 N + 18) bytes -- instead of one fused kernel (0).  Same results bit for
+ *                   bit; 2 % faster on B200 (profiles/README.md).  Falls back to the fused kernel when the store cannot
+ *                   be allocated.  Also CFNMPC_TWO_KERNELS=0 in the environment. */
 int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int value);
 
 /* Enqueue n_rti consecutive RTI steps (preparation + feedback) for every instance,
@@ -186,10 +191,14 @@ int cfnmpc_sim_launches(cfnmpc_sim *s, long long *n);
 int cfnmpc_batch_device_ptr(cfnmpc_batch *h, const char *field, void **ptr);
 
 /* Integer properties: "batch","N","n_slots","sm_count","warps_per_block","blocks_per_sm",
- * "regs_per_thread","smem_per_block","launches" (kernels launched so far). */
+ * "regs_per_thread","smem_per_block" (fused kernel), "two_kernels", "feedback_regs_per_thread",
+ * "feedback_blocks_per_sm", "feedback_grid", "preparation_grid", "prepared_bytes", "scratch_bytes", "launches" (kernels launched so far). */
 int cfnmpc_batch_info(cfnmpc_batch *h, const char *what, long long *value);
 /* Device time of the last cfnmpc_batch_solve in ms (CUDA events on the stream); syncs. */
 int cfnmpc_batch_last_solve_ms(cfnmpc_batch *h, double *ms);
+/* The same split by launch when the step ran as two kernels (the default on a uniform grid: preparation kernel, then
+ * feedback kernel): ms2[0] = preparation, ms2[1] = feedback; a fused step reports {0, total}. */
+int cfnmpc_batch_last_phase_ms(cfnmpc_batch *h, double *ms2);
 
 /* Test hook: copy the scratch slot that solved instance 0 when batch == 1 (QP data,
  * factors, IPM vectors) and limit the IPM iteration count; see tests/test_gpu_parity.py. */

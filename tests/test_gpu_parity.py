@@ -409,3 +409,29 @@ def test_nonuniform_time_grid(port, ref, split):
     hu = gpu_solve(w, N)
     assert np.array_equal(h["x"], hu["x"]) and np.array_equal(h["u"], hu["u"])
     assert rel_err(g["u"], hu["u"]) > 1e-4      # and the grid matters
+
+
+def test_two_kernel_step_equals_fused_kernel(port):
+    """The default step (preparation kernel, then feedback kernel) against the single fused kernel (option
+    "two_kernels" 0): bit-identical, through cfnmpc_batch_solve, _solve_from_host and _tick."""
+    N, B = 50, 777
+    w = wl.hover_batch(B, N, seed=41)
+    out = {}
+    for two in (1, 0):
+        with cf.BatchSolver(B, N, TS) as s:
+            s.set_option("two_kernels", two).set_option("lin_res_check", 1)
+            assert s.info("two_kernels") == two
+            a = _outputs(s.set_problem(w).solve(2))
+            t_prep, t_fb = s.last_phase_ms()
+            assert t_fb > 0 and t_prep == 0          # two steps in one call: no per-kernel split is reported
+            s.set("x", w["x_init"]).set("u", w["u_init"])
+            b = _outputs(s.solve_from_host(w["x0"], w["yref"], w["yref_e"], n_chunks=5))
+            s.set_problem(w).solve(1)
+            t_prep, t_fb = s.last_phase_ms()
+            assert (t_prep > 0) == bool(two) and t_fb > 0
+            assert s.info("prepared_bytes") == (8 * B * ((252 * N + 18 + 15) // 16 * 16) if two else 0)
+            out[two] = (a, b)
+    for i in range(2):
+        for k in ("x", "u", "status", "qp_iter", "flags"):
+            assert np.array_equal(out[1][i][k], out[0][i][k]), (i, k)
+    check(dict(out[1][1], u0=out[1][1]["u"][:, 0], u1=out[1][1]["u"][:, 1], x4=out[1][1]["x"][:, 4]), oracle_solve(port, w, N))
