@@ -95,5 +95,47 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB,", len(g), "arrays")
 
 
+OUT_PHASES = os.path.join(ROOT, "tests", "golden", "crazyflie_rti_golden_phases.npz")
+
+
+def moved(x0, seed, scale=0.02):
+    """A second measurement a little away from the first (quaternion re-normalised)."""
+    x = x0 + scale * np.random.default_rng(seed).standard_normal(x0.shape)
+    x[..., 3:7] /= np.linalg.norm(x[..., 3:7], axis=-1, keepdims=True)
+    return np.ascontiguousarray(x)
+
+
+def main_phases():
+    """Split real-time iteration (rti_phase 1, new measurement, rti_phase 2: ocp_nlp_sqp_rti.c:189-198,1213-1237) and
+    non-uniform shooting grids (create_with_discretization, acados_solver.in.c:133-153) run by the reference itself."""
+    build(ref=True)
+    ref = Ref()
+    g = {}
+    N, n = 20, 6
+    dt = TS * np.concatenate([np.full(6, 0.5), np.linspace(0.6, 2.5, N - 6)])
+    g["dt"] = dt
+    for name, gen, seed, grid in (("split", wl.helix_batch, 201, None), ("dt", wl.hover_batch, 202, dt),
+                                  ("dtsplit", wl.hover_batch, 203, dt)):
+        w = gen(n, N, seed=seed)
+        x0_fb = moved(w["x0"], seed + 50)
+        x, u = w["x_init"].copy(), w["u_init"].copy()
+        st, it = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        for i in range(n):
+            s = ref.solver(N, TS, dt=grid)
+            if name == "dt":
+                st[i], it[i], _, _ = s.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], x[i], u[i])
+            else:
+                st[i], it[i], _ = s.rti_split(w["x0"][i], x0_fb[i], w["yref"][i], w["yref_e"][i], x[i], u[i])
+            s.close()
+        for k in ("x0", "yref", "yref_e", "x_init", "u_init"):
+            g[f"{name}_{k}"] = w[k]
+        g[f"{name}_x0_fb"] = x0_fb
+        g[f"{name}_x"], g[f"{name}_u"], g[f"{name}_status"], g[f"{name}_qp_iter"] = x, u, st, it
+    np.savez_compressed(OUT_PHASES, **g)
+    print("wrote", OUT_PHASES, os.path.getsize(OUT_PHASES) // 1024, "KiB,", len(g), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if "--phases-only" not in sys.argv:
+        main()
+    main_phases()

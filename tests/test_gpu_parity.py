@@ -435,3 +435,27 @@ def test_two_kernel_step_equals_fused_kernel(port):
         for k in ("x", "u", "status", "qp_iter", "flags"):
             assert np.array_equal(out[1][i][k], out[0][i][k]), (i, k)
     check(dict(out[1][1], u0=out[1][1]["u"][:, 0], u1=out[1][1]["u"][:, 1], x4=out[1][1]["x"][:, 4]), oracle_solve(port, w, N))
+
+
+@pytest.mark.parametrize("name", ["split", "dt", "dtsplit"])
+def test_phases_and_time_grids_against_golden(name):
+    """Fixtures minted by the reference's own rti_phase 1 / 2 and per-interval time steps
+    (tests/golden/crazyflie_rti_golden_phases.npz, make_golden.py::main_phases)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "crazyflie_rti_golden_phases.npz"))
+    N = 20
+    w = {k: np.ascontiguousarray(g[f"{name}_{k}"]) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
+    with cf.BatchSolver(w["x0"].shape[0], N, TS) as s:
+        s.set_option("lin_res_check", 1)
+        if name != "split":
+            s.set("time_steps", g["dt"])
+        s.set_problem(w)
+        if name == "dt":
+            s.solve(1)
+        else:
+            s.prepare().set("x0", np.ascontiguousarray(g[f"{name}_x0_fb"])).feedback()
+        r = _outputs(s)
+    assert (r["status"] == g[f"{name}_status"]).all() and np.abs(r["qp_iter"] - g[f"{name}_qp_iter"]).max() <= 1
+    assert (r["flags"] == 0).all()
+    ex, eu = rel_err(r["x"], g[f"{name}_x"]), rel_err(r["u"], g[f"{name}_u"])
+    assert ex <= TOL and eu <= TOL and ex <= TIGHT and eu <= TIGHT, (ex, eu)

@@ -140,3 +140,51 @@ def test_model_jacobian_against_finite_differences(port):
     uss = wl.hover_speed()
     f = port.ode(np.array([0, 0, 0.5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.]), np.full(4, uss))
     assert np.abs(f).max() < 1e-12
+
+
+# ---- split real-time iteration and non-uniform grids: fixtures minted by the reference's own two phases / per-interval
+# ---- time steps (tests/golden/make_golden.py::main_phases)
+GOLD_PHASES = os.path.join(os.path.dirname(__file__), "golden", "crazyflie_rti_golden_phases.npz")
+
+
+@pytest.fixture(scope="module")
+def gold_phases():
+    return np.load(GOLD_PHASES)
+
+
+@pytest.mark.parametrize("name", ["split", "dt", "dtsplit"])
+def test_port_oracle_phases_and_time_grids(port, gold_phases, name):
+    g, N = gold_phases, 20
+    w = {k: g[f"{name}_{k}"] for k in ("x0", "x0_fb", "yref", "yref_e", "x_init", "u_init")}
+    port.set_time_steps(g["dt"] if name != "split" else None)
+    try:
+        for i in range(w["x0"].shape[0]):
+            x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+            if name == "dt":
+                st, info = port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u)
+            else:
+                st, info = port.rti_split(N, TS, w["x0"][i], w["x0_fb"][i], w["yref"][i], w["yref_e"][i], x, u)
+            assert st == g[f"{name}_status"][i] and info.qp_iter == g[f"{name}_qp_iter"][i]
+            assert rel_err(x, g[f"{name}_x"][i]) < 1e-10 and rel_err(u, g[f"{name}_u"][i]) < 1e-10
+    finally:
+        port.set_time_steps(None)
+
+
+def test_reference_library_reproduces_phase_golden(ref, gold_phases):
+    """The fixtures are what the reference's own phases give, and its two phases equal one full step taken with the
+    feedback-time measurement (bit for bit)."""
+    g, N = gold_phases, 20
+    for name in ("split", "dtsplit"):
+        grid = g["dt"] if name == "dtsplit" else None
+        for i in range(3):
+            s = ref.solver(N, TS, dt=grid)
+            x, u = g[f"{name}_x_init"][i].copy(), g[f"{name}_u_init"][i].copy()
+            st, qi, _ = s.rti_split(g[f"{name}_x0"][i], g[f"{name}_x0_fb"][i], g[f"{name}_yref"][i], g[f"{name}_yref_e"][i], x, u)
+            s.close()
+            assert st == g[f"{name}_status"][i] and qi == g[f"{name}_qp_iter"][i]
+            assert np.array_equal(x, g[f"{name}_x"][i]) and np.array_equal(u, g[f"{name}_u"][i])
+            s = ref.solver(N, TS, dt=grid)
+            x2, u2 = g[f"{name}_x_init"][i].copy(), g[f"{name}_u_init"][i].copy()
+            s.rti(g[f"{name}_x0_fb"][i], g[f"{name}_yref"][i], g[f"{name}_yref_e"][i], x2, u2)
+            s.close()
+            assert np.array_equal(x, x2) and np.array_equal(u, u2)

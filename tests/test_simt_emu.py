@@ -240,3 +240,16 @@ def test_emulated_nonuniform_grid_matches_reference(emu_general, port, ref, spli
         port.set_time_steps(None)
     # and the grid matters: the uniform solution is different
     assert rel_err(emu_general(w, N)["u"], r["u"]) > 1e-4
+
+
+@pytest.mark.parametrize("name", ["split", "dt", "dtsplit"])
+def test_emulated_general_variants_match_phase_golden(emu_general, name):
+    """The general kernel variants against fixtures minted by the reference's own two phases / per-interval time steps
+    (tests/golden/crazyflie_rti_golden_phases.npz) -- no reference build needed."""
+    g = np.load(os.path.join(HERE, "golden", "crazyflie_rti_golden_phases.npz"))
+    w = {k: np.ascontiguousarray(g[f"{name}_{k}"]) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
+    r = emu_general(w, 20, dts=None if name == "split" else g["dt"], split=name != "dt",
+                    x0_fb=None if name == "dt" else g[f"{name}_x0_fb"])
+    assert (r["status"] == g[f"{name}_status"]).all() and np.abs(r["qp_iter"] - g[f"{name}_qp_iter"]).max() <= 1
+    assert (r["flags"] == 0).all()
+    assert rel_err(r["x"], g[f"{name}_x"]) < 1e-9 and rel_err(r["u"], g[f"{name}_u"]) < 1e-9
