@@ -459,3 +459,39 @@ def test_phases_and_time_grids_against_golden(name):
     assert (r["flags"] == 0).all()
     ex, eu = rel_err(r["x"], g[f"{name}_x"]), rel_err(r["u"], g[f"{name}_u"])
     assert ex <= TOL and eu <= TOL and ex <= TIGHT and eu <= TIGHT, (ex, eu)
+
+
+def test_split_phases_edge_cases(port):
+    """Tiny horizons (fewer stages than one staging trip of the feedback kernel, N not a multiple of 4) with their own
+    grids and a moved measurement, through both the general kernels (prepare / feedback) and the default two-kernel
+    step; a NaN measurement arriving for the feedback phase: QP failure, iterate untouched, neighbours unaffected."""
+    for N in (1, 2, 3, 5, 9):
+        B = 6
+        w = wl.hover_batch(B, N, seed=60 + N)
+        dt = TS * np.linspace(0.7, 1.6, N)
+        x0_fb = _moved(w["x0"], 70 + N)
+        with cf.BatchSolver(B, N, TS) as s:
+            g = _outputs(s.set("time_steps", dt).set_problem(w).prepare().set("x0", x0_fb).feedback())
+            h = _outputs(s.set("time_steps", np.full(N, TS)).set_problem(w).solve(1))     # two-kernel default, uniform grid
+        port.set_time_steps(dt)
+        try:
+            o = oracle_solve(port, dict(w, x0=x0_fb), N)
+        finally:
+            port.set_time_steps(None)
+        assert (g["status"] == o["status"]).all()
+        assert rel_err(g["x"], o["x"]) <= TIGHT and rel_err(g["u"], o["u"]) <= TIGHT
+        o = oracle_solve(port, w, N)
+        assert rel_err(h["x"], o["x"]) <= TIGHT and rel_err(h["u"], o["u"]) <= TIGHT
+    N, B = 10, 9
+    w = wl.hover_batch(B, N, seed=88)
+    x0_fb = w["x0"].copy()
+    x0_fb[4, 5] = np.nan
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_problem(w).prepare().set("x0", x0_fb).feedback()
+        g = dict(_outputs(s), qp_status=s.get("qp_status"))
+    assert g["status"][4] == cf.ACADOS_QP_FAILURE and g["qp_status"][4] == 3
+    assert np.array_equal(g["x"][4], w["x_init"][4]) and np.array_equal(g["u"][4], w["u_init"][4])
+    ok = np.arange(B) != 4
+    o = oracle_solve(port, w, N)
+    assert (g["status"][ok] == 0).all()
+    assert rel_err(g["x"][ok], o["x"][ok]) <= TIGHT and rel_err(g["u"][ok], o["u"][ok]) <= TIGHT

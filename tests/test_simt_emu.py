@@ -253,3 +253,40 @@ def test_emulated_general_variants_match_phase_golden(emu_general, name):
     assert (r["status"] == g[f"{name}_status"]).all() and np.abs(r["qp_iter"] - g[f"{name}_qp_iter"]).max() <= 1
     assert (r["flags"] == 0).all()
     assert rel_err(r["x"], g[f"{name}_x"]) < 1e-9 and rel_err(r["u"], g[f"{name}_u"]) < 1e-9
+
+
+def test_emulated_general_variants_edge_cases(emu_general, port, ref):
+    """Tiny horizons (fewer stages than one staging trip of the feedback kernel, N not a multiple of 4), each with its own
+    grid and a moved measurement; and a NaN measurement arriving for the feedback phase: QP failure, iterate untouched."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    for N in (1, 2, 3, 5, 9):
+        w = wl.hover_batch(3, N, seed=60 + N)
+        dt = TS * np.linspace(0.7, 1.6, N)
+        x0_fb = moved_measurement(w["x0"], 70 + N)
+        r = emu_general(w, N, dts=dt, split=True, x0_fb=x0_fb)
+        port.set_time_steps(dt)
+        try:
+            for i in range(3):
+                x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+                st, info = port.rti_split(N, TS, w["x0"][i], x0_fb[i], w["yref"][i], w["yref_e"][i], x, u)
+                assert st == r["status"][i] and abs(info.qp_iter - r["qp_iter"][i]) <= 1
+                assert rel_err(r["x"][i], x) < 1e-9 and rel_err(r["u"][i], u) < 1e-9
+        finally:
+            port.set_time_steps(None)
+    N, B = 10, 4
+    w = wl.hover_batch(B, N, seed=88)
+    x0_fb = w["x0"].copy()
+    x0_fb[1, 5] = np.nan
+    r = emu_general(w, N, split=True, x0_fb=x0_fb)
+    assert r["status"][1] == 4 and r["qp_status"][1] == 3
+    assert np.array_equal(r["x"][1], w["x_init"][1]) and np.array_equal(r["u"][1], w["u_init"][1])
+    s = ref.solver(N, TS)
+    x, u = w["x_init"][1].copy(), w["u_init"][1].copy()
+    st, _, qs = s.rti_split(w["x0"][1], x0_fb[1], w["yref"][1], w["yref_e"][1], x, u)
+    s.close()
+    assert st == 4 and qs == 3 and np.array_equal(x, w["x_init"][1])      # the reference does the same
+    ok = np.arange(B) != 1
+    assert (r["status"][ok] == 0).all()
+    xo, uo = w["x_init"].copy(), w["u_init"].copy()
+    port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], xo, uo)
+    assert rel_err(r["x"][ok], xo[ok]) < 1e-9 and rel_err(r["u"][ok], uo[ok]) < 1e-9
