@@ -26,7 +26,7 @@ struct crazyflie_solver_capsule
     bool in_dirty = true, iterate_dirty = true;
     int status = 0, qp_iter = 0, qp_status = 0, cond_N = 0;
     int rti_phase = 0;   // 0 preparation + feedback, 1 preparation, 2 feedback (ocp_nlp_sqp_rti.c:189-198)
-    double lbu[4] = {0, 0, 0, 0}, ubu[4] = {22, 22, 22, 22}, lbu0[4] = {0, 0, 0, 0}, ubu0[4] = {22, 22, 22, 22};
+    std::vector<double> bnd;   // input box per stage, [N][8] = lbu | ubu (ocp_nlp_constraints_bgh.c:653-674)
     double time_tot = 0.0;
     ocp_nlp_plan_t plan;
     ocp_nlp_config config;
@@ -94,7 +94,9 @@ int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int
     c->N = N;
     c->Ts = Ts;
     c->rti_phase = 0;
-    for (int i = 0; i < 4; i++) { c->lbu[i] = c->lbu0[i] = CfSpec::lbu[i]; c->ubu[i] = c->ubu0[i] = CfSpec::ubu[i]; }  // generate_c_code.py:133-134
+    c->bnd.assign((size_t) N * 8, 0.0);   // generate_c_code.py:133-134
+    for (int k = 0; k < N; k++)
+        for (int i = 0; i < 4; i++) { c->bnd[(size_t) k * 8 + i] = CfSpec::lbu[i]; c->bnd[(size_t) k * 8 + 4 + i] = CfSpec::ubu[i]; }
     // generate_c_code.py:128-129 reference, :135 x0 (through tools/gen_spec.py)
     const double *y = CfSpec::yref;
     c->x0.assign(CfSpec::x0, CfSpec::x0 + 13);
@@ -217,15 +219,11 @@ int ocp_nlp_constraints_model_set(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_in *
         return 0;
     }
     if (!strcmp(field, "lbu") || !strcmp(field, "ubu")) {
-        // per-stage in the reference (ocp_nlp_constraints_bgh.c:653-674).  Supported granularity: stage 0 on its own
-        // (the node's FIXED_U0 branch, acados_mpc.cpp:604-608) and stages 1..N-1 together.
+        // one stage at a time, as in the reference (ocp_nlp_constraints_bgh.c:653-674; the node's FIXED_U0 branch pins
+        // stage 0 this way, acados_mpc.cpp:604-608)
         if (stage < 0 || stage >= c->N || !c->batch) return 1;
-        const bool lower = field[0] == 'l';
-        double *path = lower ? c->lbu : c->ubu, *first = lower ? c->lbu0 : c->ubu0;
-        memcpy(stage == 0 ? first : path, value, 4 * sizeof(double));
-        int rc = cfnmpc_batch_set(c->batch, lower ? "lbu" : "ubu", path, 0);
-        rc |= cfnmpc_batch_set(c->batch, lower ? "lbu0" : "ubu0", first, 0);
-        return rc != CFNMPC_OK;
+        memcpy(&c->bnd[(size_t) stage * 8 + (field[0] == 'l' ? 0 : 4)], value, 4 * sizeof(double));
+        return cfnmpc_batch_set(c->batch, "bounds_stage", c->bnd.data(), 0) != CFNMPC_OK;
     }
     return 1;
 }

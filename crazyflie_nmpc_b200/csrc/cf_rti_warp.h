@@ -127,6 +127,10 @@ struct CfBatchView
     // for the feedback phase, per INSTANCE: N stage records [ [B';A';b'] (234) | gradient (18) ] + the terminal gradient
     double *prep;
     long prep_stride;
+    // input box per STAGE, [N][8] = lbu(4) | ubu(4) of stage k (ocp_nlp_constraints_model_set addresses one stage at a
+    // time, ocp_nlp_constraints_bgh.c:653-674); null = the stage-0 / path boxes of CfParams.  Takes precedence over them
+    // and over the per-instance arrays.
+    const double *bnd_stage;
 };
 // layout of the prepared linearisation of one instance (doubles)
 #define CF_PREP_STAGE (CF_MSZ + 18)
@@ -197,6 +201,7 @@ struct CfWarpT
     double *SLOT;
     double *PREP;      // this instance's prepared linearisation (split phases only)
     const double *DT;  // per-interval time steps (VDT only)
+    const double *BST; // per-stage input boxes (null: the boxes of P)
     // lane constants
     double Hs, HN;     // Hessian diagonal for this lane's variable (stage / terminal)
     double W2;         // (sqrt(w))^2 of this lane's stage weight: the stage Hessian is dt_k * W2
@@ -209,7 +214,7 @@ struct CfWarpT
     CF_MEM void bind(const CfParams *P_, const CfParams *PG_, double *slot, double *sm_, double *prep_, const double *dts_)
     {
         P = P_; PG = PG_; N = PG_->N; sm = sm_; lane = cf_lane();
-        PREP = prep_; DT = dts_;
+        PREP = prep_; DT = dts_; BST = nullptr;
         bar = reinterpret_cast<uint64_t *>(sm_ + CF_SM_BAR);
         par = 0;
         CfScratchLayout s = cf_scratch_layout(N);
@@ -407,8 +412,10 @@ struct CfWarpT
         // bounds (ocp_nlp_constraints_bgh.c:1634-1636): d = [lb - u ; u - ub]
         double v0 = 0.0;
         if (lane < CF_NU) {
-            const double dl = ((k == 0) ? P->lbu0[lane] : P->lbu[lane]) - uk;
-            const double du = uk - ((k == 0) ? P->ubu0[lane] : P->ubu[lane]);
+            double lb = (k == 0) ? P->lbu0[lane] : P->lbu[lane], ub = (k == 0) ? P->ubu0[lane] : P->ubu[lane];
+            if (BST) { lb = BST[k * 8 + lane]; ub = BST[k * 8 + 4 + lane]; }
+            const double dl = lb - uk;
+            const double du = uk - ub;
             rec(k)[R_D + lane] = dl;
             rec(k)[R_D + 4 + lane] = du;
             // OCP_QP_INIT_VAR scheme 1 (x_ocp_qp_ipm.c:1491-1530,1636-1769): slacks at ux = 0, pushed 0.1 inside
@@ -1225,6 +1232,7 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     CfWarp w;
     w.bind(P, Pg, slot, sm, (PH != CF_PH_BOTH) ? bv.prep + (long) inst * bv.prep_stride : nullptr, VDT ? bv.dts : nullptr);
     w.par = par;
+    w.BST = bv.bnd_stage;
     const int N = Pg->N;
     double *xg = bv.x + (long) inst * (N + 1) * CF_NX;
     double *ug = bv.u + (long) inst * N * CF_NU;

@@ -136,6 +136,7 @@ struct cfnmpc_batch
     int grid_general = 0;
     double *d_dts = nullptr, *d_prep = nullptr;
     double *h_dts = nullptr;          // host copy of the time grid (N doubles)
+    double *d_bst = nullptr;          // per-stage input boxes [N][8] (allocated on first use)
     bool vdt = false, prepared = false;
     size_t smem = 0;
     long long launches = 0;
@@ -161,7 +162,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
                     h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter,
                     h->d_policy, h->d_titer, h->d_motors, h->d_setpoint, h->d_traj, h->d_euler, h->d_twist,
-                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep};
+                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep, h->d_bst};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -321,7 +322,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     bv.res = h->d_res; bv.scratch = h->d_scratch; bv.scratch_stride = stride; bv.counter = h->d_counter;
     bv.W_b = bv.WN_b = bv.lbu_b = bv.ubu_b = bv.lbu0_b = bv.ubu0_b = nullptr;
     bv.prof = nullptr;
-    bv.dts = h->d_dts; bv.prep = nullptr; bv.prep_stride = cf_prep_stride(N);
+    bv.dts = h->d_dts; bv.prep = nullptr; bv.prep_stride = cf_prep_stride(N); bv.bnd_stage = nullptr;
     CKH(cudaStreamSynchronize(h->stream));
 #undef CKH
     *out = h;
@@ -406,6 +407,14 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         }
     }
     FieldRef r;
+    if (!strcmp(field, "bounds_stage")) {
+        // [N][8] = lbu(4) | ubu(4) of every stage: what a sequence of per-stage ocp_nlp_constraints_model_set calls builds
+        const size_t bytes = (size_t) h->N * 8 * 8;
+        if (!h->d_bst) CK(cudaMalloc(&h->d_bst, bytes));
+        CK(cudaMemcpyAsync(h->d_bst, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        h->bv.bnd_stage = h->d_bst;
+        return CFNMPC_OK;
+    }
     if (!strcmp(field, "time_steps")) {
         // crazyflie_acados_update_time_steps (c_templates_tera/acados_solver.in.c:133-153): interval lengths = cost scalings
         std::vector<double> dt(h->N);
@@ -457,6 +466,7 @@ extern "C" int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field)
     else if (!strcmp(field, "ubu_batch")) h->bv.ubu_b = nullptr;
     else if (!strcmp(field, "lbu0_batch")) h->bv.lbu0_b = nullptr;
     else if (!strcmp(field, "ubu0_batch")) h->bv.ubu0_b = nullptr;
+    else if (!strcmp(field, "bounds_stage")) h->bv.bnd_stage = nullptr;
     else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_clear: '") + field + "' is not a per-instance parameter array");
     return CFNMPC_OK;
 }

@@ -77,6 +77,10 @@ int cfnmpc_batch_set_stream(cfnmpc_batch *h, void *cuda_stream);
  *   "lbu","ubu" double [4]          input bounds, stages 0..N-1
  *   "lbu0","ubu0" double [4]        input bounds of stage 0 only (set after "lbu"/"ubu"): the node's FIXED_U0
  *                                   branch pins u_0 this way, acados_mpc.cpp:604-608
+ *   "bounds_stage" double [N][8]    input box per STAGE, row k = lbu(4) | ubu(4) of stage k: the reference sets bounds one
+ *                                   stage at a time (ocp_nlp_constraints_model_set(.., k, "lbu"|"ubu", ..),
+ *                                   ocp_nlp_constraints_bgh.c:653-674).  Once given it takes precedence over "lbu","ubu",
+ *                                   "lbu0","ubu0" and the per-instance arrays until cfnmpc_batch_clear("bounds_stage").
  *   "time_steps" double [N]         lengths of the shooting intervals (host or device pointer); each is also the
  *                                   scaling of its stage cost, as crazyflie_acados_create_with_discretization /
  *                                   crazyflie_acados_update_time_steps set them (c_templates_tera/acados_solver.in.c:
@@ -89,7 +93,7 @@ int cfnmpc_batch_set_stream(cfnmpc_batch *h, void *cuda_stream);
  *   "lbu0_batch","ubu0_batch" double [B][4]   stage 0 only
  * Copies are asynchronous on the handle's stream. */
 int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *src, int src_on_device);
-/* Stop using a per-instance parameter array ("W_batch", ...): back to the solver-wide value. */
+/* Stop using a per-instance parameter array ("W_batch", ...) or the per-stage table "bounds_stage": back to the solver-wide value. */
 int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field);
 
 /* Integer options:

@@ -183,6 +183,17 @@ void cfo_set_time_steps(const double *dt, int n)
 }
 #define DTK(k) ((k) < g_dt_n ? g_dt[k] : Ts)
 
+/* Input box per stage, tab[n][8] = lbu(4) | ubu(4): ocp_nlp_constraints_model_set addresses one stage at a time
+ * (ocp_nlp_constraints_bgh.c:653-674).  Global, test use only; n = 0 returns to the boxes of cfo_params. */
+static double g_bst[CFO_MAX_N * 8];
+static int g_bst_n = 0;
+void cfo_set_stage_bounds(const double *tab, int n)
+{
+    if (!tab || n <= 0 || n > CFO_MAX_N) { g_bst_n = 0; return; }
+    memcpy(g_bst, tab, sizeof(double) * 8 * n);
+    g_bst_n = n;
+}
+
 /* ------------------------------------------------------------ linearisation
  * ocp_nlp_common.c:2157-2292 calling dynamics_cont :755-884, cost_ls :810-916,
  * constraints_bgh :1613-1648.  Output layout = cfref_get_qp. */
@@ -216,8 +227,10 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
             for (int i = 0; i < NU; i++) {
                 /* per-stage bounds: ocp_nlp_constraints_bgh.c:653-674 (model_set copies into stage k only) */
                 const int s0 = (k == 0 && p_->has_u0);
-                if (d_lb) d_lb[od + i] = (s0 ? p_->lbu0[i] : p_->lbu[i]) - uk[i];
-                if (d_ub) d_ub[od + i] = uk[i] - (s0 ? p_->ubu0[i] : p_->ubu[i]);
+                const double lb = k < g_bst_n ? g_bst[8 * k + i] : (s0 ? p_->lbu0[i] : p_->lbu[i]);
+                const double ub = k < g_bst_n ? g_bst[8 * k + 4 + i] : (s0 ? p_->ubu0[i] : p_->ubu[i]);
+                if (d_lb) d_lb[od + i] = lb - uk[i];
+                if (d_ub) d_ub[od + i] = uk[i] - ub;
             }
             if (k == 0)
                 for (int i = 0; i < NX; i++) {

@@ -65,6 +65,7 @@ class Port:
         L.cfo_ode.argtypes = [_dp, _dp, _dp]
         L.cfo_default_params.argtypes = [ctypes.POINTER(CfoParams)]
         L.cfo_set_time_steps.argtypes = [_dp, ctypes.c_int]
+        L.cfo_set_stage_bounds.argtypes = [_dp, ctypes.c_int]
         L.cfo_rti_split.restype = ctypes.c_int
         L.cfo_rti_split.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), _dp, _dp, _dp, _dp, _dp, _dp,
                                     ctypes.POINTER(CfoInfo)]
@@ -76,6 +77,14 @@ class Port:
         else:
             dt = np.ascontiguousarray(dt, float)
             self.lib.cfo_set_time_steps(_P(dt), dt.size)
+
+    def set_stage_bounds(self, tab=None):
+        """Input box per stage, [N][8] = lbu | ubu (global in the checker; None returns to the boxes of the params)."""
+        if tab is None:
+            self.lib.cfo_set_stage_bounds(None, 0)
+        else:
+            tab = np.ascontiguousarray(tab, float)
+            self.lib.cfo_set_stage_bounds(_P(tab), tab.shape[0])
 
     def rti_split(self, N, Ts, x0_prep, x0_fb, yref, yref_e, x, u, params=None):
         """Preparation with x0_prep, feedback with x0_fb; x,u updated in place."""
@@ -163,6 +172,7 @@ class Ref:
         L.cfref_set_weights.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.cfref_set_input_bounds.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.cfref_set_input_bounds_stage0.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.cfref_set_input_bounds_at.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp]
         L.cfref_create_dt.restype = ctypes.c_void_p
         L.cfref_create_dt.argtypes = [ctypes.c_int, _dp, ctypes.c_int]
         L.cfref_rti_split.restype = ctypes.c_int
@@ -210,6 +220,9 @@ class RefSolver:
 
     def set_input_bounds(self, lbu, ubu):
         self.lib.cfref_set_input_bounds(self.h, _P(np.ascontiguousarray(lbu, float)), _P(np.ascontiguousarray(ubu, float)))
+
+    def set_input_bounds_at(self, stage, lbu, ubu):
+        self.lib.cfref_set_input_bounds_at(self.h, int(stage), _P(np.ascontiguousarray(lbu, float)), _P(np.ascontiguousarray(ubu, float)))
 
     def set_input_bounds_stage0(self, lbu0, ubu0):
         self.lib.cfref_set_input_bounds_stage0(self.h, _P(np.ascontiguousarray(lbu0, float)), _P(np.ascontiguousarray(ubu0, float)))

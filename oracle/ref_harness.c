@@ -223,6 +223,14 @@ void cfref_set_input_bounds(void *h_, const double *lbu, const double *ubu)
     }
 }
 
+/* input box of ONE stage, as ocp_nlp_constraints_model_set addresses it (ocp_nlp_constraints_bgh.c:653-674) */
+void cfref_set_input_bounds_at(void *h_, int stage, const double *lbu, const double *ubu)
+{
+    cfref *h = h_;
+    ocp_nlp_constraints_model_set(h->config, h->dims, h->in, stage, "lbu", (void *) lbu);
+    ocp_nlp_constraints_model_set(h->config, h->dims, h->in, stage, "ubu", (void *) ubu);
+}
+
 /* stage-0 input box only: what the node's FIXED_U0 branch does (acados_mpc.cpp:604-608) */
 void cfref_set_input_bounds_stage0(void *h_, const double *lbu0, const double *ubu0)
 {

@@ -268,7 +268,7 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
     bv.lbu_b = per_inst ? per_inst[2] : nullptr; bv.ubu_b = per_inst ? per_inst[3] : nullptr;
     bv.lbu0_b = per_inst ? per_inst[4] : nullptr; bv.ubu0_b = per_inst ? per_inst[5] : nullptr;
     bv.prof = nullptr;
-    bv.dts = nullptr; bv.prep = nullptr; bv.prep_stride = 0;
+    bv.dts = nullptr; bv.prep = nullptr; bv.prep_stride = 0; bv.bnd_stage = nullptr;
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(0);
     std::vector<std::thread> th;
@@ -294,6 +294,9 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
 // General variants of the warp program: per-interval time steps `dts` (NULL = uniform Ts) and, with split != 0, the
 // real-time iteration as two phases -- preparation with x0, then (scratch slot and shared memory poisoned in between, as
 // another instance would have used them) feedback with x0_fb (NULL = x0).
+static const double *g_bnd_stage = nullptr;
+// per-stage input boxes [N][8] for the next cfemu_rti_general calls (NULL: none)
+extern "C" void cfemu_set_stage_bounds(const double *tab) { g_bnd_stage = tab; }
 extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int split, const double *x0, const double *x0_fb,
                                  const double *yref, const double *yref_e, double *x, double *u, int *status, int *qp_iter,
                                  int *qp_status, int *flags, double *res, int nthreads)
@@ -314,6 +317,7 @@ extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int
     bv.dts = dtv.data();
     bv.prep = (double *) ((((uintptr_t) prep.data()) + 15) & ~(uintptr_t) 15);
     bv.prep_stride = pstride;
+    bv.bnd_stage = g_bnd_stage;
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(0);
     std::vector<std::thread> th;

@@ -215,3 +215,63 @@ def test_capsule_rti_phases_and_time_steps(port, ref):
     assert st == 0 and np.abs(x2 - xo).max() < 1e-8 and np.abs(u2 - uo).max() < 1e-8
     L.crazyflie_acados_free(cap)
     L.crazyflie_acados_free_capsule(cap)
+
+
+@pytest.mark.gpu
+def test_capsule_per_stage_bounds(ref):
+    """ocp_nlp_constraints_model_set(.., stage, "lbu"|"ubu", ..) addresses ONE stage (ocp_nlp_constraints_bgh.c:653-674):
+    a narrow box on stage 3 only and the FIXED_U0-style pin of stage 0 (acados_mpc.cpp:604-608), against the reference."""
+    import ctypes
+    L = cf.lib()
+    vp, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)
+    L.crazyflie_acados_create_capsule.restype = vp
+    for f in ("crazyflie_acados_get_nlp_in", "crazyflie_acados_get_nlp_out", "crazyflie_acados_get_nlp_config", "crazyflie_acados_get_nlp_dims"):
+        getattr(L, f).restype = vp
+        getattr(L, f).argtypes = [vp]
+    L.crazyflie_acados_create_with_discretization.argtypes = [vp, ctypes.c_int, dp]
+    L.crazyflie_acados_solve.argtypes = [vp]
+    L.crazyflie_acados_free.argtypes = [vp]
+    L.crazyflie_acados_free_capsule.argtypes = [vp]
+    L.ocp_nlp_constraints_model_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_cost_model_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_out_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_out_get.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    N, TS = 20, 0.015
+    w = wl.hover_batch(1, N, seed=8)
+    cap = L.crazyflie_acados_create_capsule()
+    steps = (ctypes.c_double * N)(*([TS] * N))
+    assert L.crazyflie_acados_create_with_discretization(cap, N, steps) == 0
+    cfg, dims, nin, nout = (L.crazyflie_acados_get_nlp_config(cap), L.crazyflie_acados_get_nlp_dims(cap),
+                            L.crazyflie_acados_get_nlp_in(cap), L.crazyflie_acados_get_nlp_out(cap))
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    u0 = np.ascontiguousarray(w["u_init"][0, 0] + 0.25)
+    lb3, ub3 = np.full(4, 14.0), np.full(4, 16.5)
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"lbx", P(w["x0"][0])) == 0
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"ubx", P(w["x0"][0])) == 0
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"lbu", P(u0)) == 0        # FIXED_U0
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"ubu", P(u0)) == 0
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 3, b"lbu", P(lb3)) == 0
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, 3, b"ubu", P(ub3)) == 0
+    assert L.ocp_nlp_constraints_model_set(cfg, dims, nin, N, b"lbu", P(lb3)) != 0       # no inputs at the terminal stage
+    for k in range(N):
+        assert L.ocp_nlp_cost_model_set(cfg, dims, nin, k, b"yref", P(w["yref"][0, k])) == 0
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"u", P(w["u_init"][0, k]))
+    assert L.ocp_nlp_cost_model_set(cfg, dims, nin, N, b"yref", P(w["yref_e"][0])) == 0
+    for k in range(N + 1):
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"x", P(w["x_init"][0, k]))
+    assert L.crazyflie_acados_solve(cap) == 0
+    x, u = np.zeros((N + 1, 13)), np.zeros((N, 4))
+    for k in range(N + 1):
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"x", P(x[k]))
+    for k in range(N):
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"u", P(u[k]))
+    sr = ref.solver(N, TS)
+    sr.set_input_bounds_at(0, u0, u0)
+    sr.set_input_bounds_at(3, lb3, ub3)
+    xr, ur = w["x_init"][0].copy(), w["u_init"][0].copy()
+    assert sr.rti(w["x0"][0], w["yref"][0], w["yref_e"][0], xr, ur)[0] == 0
+    sr.close()
+    assert np.abs(x - xr).max() < 1e-8 and np.abs(u - ur).max() < 1e-8
+    assert np.abs(u[0] - u0).max() < 1e-7 and (u[3] >= lb3 - 1e-6).all() and (u[3] <= ub3 + 1e-6).all()
+    L.crazyflie_acados_free(cap)
+    L.crazyflie_acados_free_capsule(cap)

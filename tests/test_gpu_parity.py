@@ -495,3 +495,40 @@ def test_split_phases_edge_cases(port):
     o = oracle_solve(port, w, N)
     assert (g["status"][ok] == 0).all()
     assert rel_err(g["x"][ok], o["x"][ok]) <= TIGHT and rel_err(g["u"][ok], o["u"][ok]) <= TIGHT
+
+
+def test_per_stage_input_bounds(port, ref):
+    """"bounds_stage": a different input box for every stage, as a sequence of per-stage
+    ocp_nlp_constraints_model_set calls builds it (ocp_nlp_constraints_bgh.c:653-674) -- fused step, two-kernel step and
+    split phases, against the port and the reference driven stage by stage."""
+    N, B = 12, 40
+    w = wl.hover_batch(B, N, seed=17)
+    rng = np.random.default_rng(3)
+    tab = np.ascontiguousarray(np.concatenate([rng.uniform(0.0, 12.0, (N, 4)), rng.uniform(17.0, 22.0, (N, 4))], axis=1))
+    outs = []
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("lin_res_check", 1).set("bounds_stage", tab)
+        outs.append(_outputs(s.set_problem(w).solve(1)))                       # two kernels
+        outs.append(_outputs(s.set_problem(w).prepare().feedback()))           # split phases (general kernels)
+        s.set_option("two_kernels", 0)
+        outs.append(_outputs(s.set_problem(w).solve(1)))                       # fused kernel
+        plain = _outputs(s.clear("bounds_stage").set_problem(w).solve(1))
+    port.set_stage_bounds(tab)
+    try:
+        o = oracle_solve(port, w, N)
+    finally:
+        port.set_stage_bounds(None)
+    for g in outs:
+        assert (g["status"] == 0).all() and (g["flags"] == 0).all()
+        assert np.array_equal(g["x"], outs[0]["x"]) and np.array_equal(g["u"], outs[0]["u"])
+        assert rel_err(g["x"], o["x"]) <= TIGHT and rel_err(g["u"], o["u"]) <= TIGHT
+        assert (g["u"] >= tab[None, :, :4] - 1e-6).all() and (g["u"] <= tab[None, :, 4:] + 1e-6).all()
+    for i in range(0, B, 10):
+        sr = ref.solver(N, TS)
+        for k in range(N):
+            sr.set_input_bounds_at(k, tab[k, :4], tab[k, 4:])
+        xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+        assert sr.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)[0] == 0
+        sr.close()
+        assert rel_err(outs[0]["x"][i], xr) <= TIGHT and rel_err(outs[0]["u"][i], ur) <= TIGHT
+    check(dict(plain, u0=plain["u"][:, 0], u1=plain["u"][:, 1], x4=plain["x"][:, 4]), oracle_solve(port, w, N))

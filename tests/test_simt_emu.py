@@ -290,3 +290,43 @@ def test_emulated_general_variants_edge_cases(emu_general, port, ref):
     xo, uo = w["x_init"].copy(), w["u_init"].copy()
     port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], xo, uo)
     assert rel_err(r["x"][ok], xo[ok]) < 1e-9 and rel_err(r["u"][ok], uo[ok]) < 1e-9
+
+
+def stage_bound_table(N, seed=3):
+    """A different input box for every stage: [N][8] = lbu | ubu."""
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(np.concatenate([rng.uniform(0.0, 12.0, (N, 4)), rng.uniform(17.0, 22.0, (N, 4))], axis=1))
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_emulated_per_stage_input_bounds(emu_general, port, ref, split):
+    """Input boxes set one stage at a time (ocp_nlp_constraints_model_set(.., k, "lbu"|"ubu", ..),
+    ocp_nlp_constraints_bgh.c:653-674), against the reference driven the same way and the port."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    N, B = 12, 4
+    w = wl.hover_batch(B, N, seed=17)
+    tab = stage_bound_table(N)
+    L = ctypes.CDLL(os.path.join(HERE, "simt_emu", "libcfemu.so"))
+    L.cfemu_set_stage_bounds.argtypes = [_dp]
+    L.cfemu_set_stage_bounds(tab.ctypes.data_as(_dp))
+    port.set_stage_bounds(tab)
+    try:
+        r = emu_general(w, N, split=split)
+        assert (r["status"] == 0).all() and (r["flags"] == 0).all()
+        for i in range(B):
+            s = ref.solver(N, TS)
+            for k in range(N):
+                s.set_input_bounds_at(k, tab[k, :4], tab[k, 4:])
+            xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+            st, qi, _, _ = s.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)
+            s.close()
+            assert st == 0 and abs(qi - r["qp_iter"][i]) <= 1
+            assert rel_err(r["x"][i], xr) < 1e-9 and rel_err(r["u"][i], ur) < 1e-9
+            xp, up = w["x_init"][i].copy(), w["u_init"][i].copy()
+            port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], xp, up)
+            assert rel_err(r["x"][i], xp) < 1e-9 and rel_err(r["u"][i], up) < 1e-9
+            assert (r["u"][i] >= tab[:, :4] - 1e-6).all() and (r["u"][i] <= tab[:, 4:] + 1e-6).all()
+    finally:
+        L.cfemu_set_stage_bounds(None)
+        port.set_stage_bounds(None)
+    assert rel_err(emu_general(w, N, split=split)["u"], r["u"]) > 1e-3     # the table mattered
