@@ -79,6 +79,9 @@ static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 &&
 #define CF_FLAG_LIN_RES_FACT 1   // reference would have switched to the LQ factorisation (x_ocp_qp_ipm.c:2029-2059)
 #define CF_FLAG_LIN_RES_CORR 2   // reference would have run iterative refinement (:2311-2318)
 #define CF_FLAG_INPUT_LATE 4     // host-fed tick: the inputs of this instance had not arrived after 5 s (solved with stale data)
+// always on (no option needed, a handful of instructions per stage):
+#define CF_FLAG_BAD_PIVOT 8      // a non-positive pivot was replaced by 0 in the Riccati factorisation (BLASFEO's rule, silent there)
+#define CF_FLAG_NONFINITE 16     // the step length or the duality measure left the finite range (HPIPM status 3 follows)
 
 struct CfParams
 {
@@ -544,6 +547,18 @@ struct CfWarpT
                 const int hi = i > j ? i : j, lo = i > j ? j : i;
                 pa[kk][hh] = ok ? hi * CF_ALST + lo + CF_NU : -1;
             }
+        // The packed lower triangle of P_{k+1} travels to the block of stage k from this shared-memory array, element
+        // e = lane + 32 t of the triangle per lane and trip: three coalesced stores per stage (scattering it from the
+        // tensor-core fragments cost 87 mostly predicate / index instructions per stage)
+        int pk[3];
+        CF_UNROLL
+        for (int t = 0; t < 3; t++) {
+            const int e = lane + 32 * t;
+            int i = 0;
+            CF_UNROLL
+            for (int q = 1; q < CF_NX; q++) i += (e >= cf_tri(q)) ? 1 : 0;
+            pk[t] = (e < 91) ? i * CF_ALST + (e - cf_tri(i)) + CF_NU : -1;
+        }
         double ux_next = 0.0;   // lanes 4..16: x-part of ux_{k+1} (new iterate)
         double pi_k = 0.0;      // lanes 4..16: pi_k (new iterate), read from the record of stage k+1
         CF_NOUNROLL
@@ -553,6 +568,12 @@ struct CfWarpT
             wait(bf);
             cf_syncwarp();  // every lane is done with buffer bf^1 (incl. the W block of stage k+1), PS/PV are complete
             if (k > 0) fetch(bf ^ 1, k - 1, 0, B_RD);
+            if (do_factor && kl) {   // P_{k+1} is complete in shared memory since the barrier above
+                double *LFk = blk(k) + B_PX;
+                CF_UNROLL
+                for (int t = 0; t < 3; t++)
+                    if (pk[t] >= 0) LFk[lane + 32 * t] = PS[pk[t]];
+            }
             double *VS = buf(bf);   // block k from offset 0
             double *rk = rec(k);
             // ---------------- update + residuals of stage k
@@ -629,15 +650,12 @@ struct CfWarpT
             if (!do_factor) continue;
             if (!kl) {
                 // terminal stage: no dynamics. P_N = diag(H_N) + reg, p_N = res_g_N; dummy inputs decoupled.
-                double *PXN = blk(N > 0 ? N - 1 : 0) + B_PX;   // P_N belongs to the block of stage N-1
                 for (int i = lane; i < 13 * CF_ALST; i += 32) PS[i] = 0.0;
-                for (int i = lane; i < CF_LX; i += 32) PXN[i] = 0.0;
                 cf_syncwarp();
                 const double hN = HN + CF_REG_PRIM;
                 if (xl) {
                     PS[ci * CF_ALST + ci + CF_NU] = hN;
                     PV[ci] = rg;
-                    PXN[cf_tri(ci) + ci] = hN;
                     rk[R_DUX + lane] = rg;   // p_N for the forward sweep
                 }
                 continue;
@@ -733,9 +751,9 @@ struct CfWarpT
                     const double piv = cf_shfl(v, j);
                     double dj, inv;
                     cf_sqrt_rsqrt(piv, dj, inv);
-                    if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; }
+                    if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; flags |= CF_FLAG_BAD_PIVOT; }   // piv is warp-uniform
                     o[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
-                    LUs[rl * 4 + j] = o[j];
+                    if (lane < CF_MROWS) LUs[rl * 4 + j] = o[j];   // lanes 18..31 mirror row 17 in registers only (racecheck)
                     og[j] = (rl == j) ? inv : o[j];
                     cf_syncwarp();
                 }
@@ -760,7 +778,6 @@ struct CfWarpT
             }
             cf_syncwarp();  // all reads of PS/PV (first product) are long complete; they are rewritten below
             {
-                double *LFk = blk(k > 0 ? k - 1 : 0) + B_PX;   // P_k goes to the block of stage k-1 (no consumer for k = 0)
                 CF_UNROLL
                 for (int t = 0; t < 3; t++) {
                     CF_UNROLL
@@ -778,14 +795,6 @@ struct CfWarpT
                             for (int e = 0; e < 2; e++) {
                                 const int c = c0 + e;
                                 if (c >= CF_NU && c < CF_NV) { PV[c - CF_NU] = sx[t][tp][e]; rk[R_DUX + c] = sx[t][tp][e]; }
-                            }
-                        }
-                        // packed lower triangle to the block of stage k-1
-                        if (k > 0 && xrow) {
-                            CF_UNROLL
-                            for (int e = 0; e < 2; e++) {
-                                const int c = c0 + e;
-                                if (c >= CF_NU && c <= r) LFk[cf_tri(r - CF_NU) + c - CF_NU] = sx[t][tp][e];
                             }
                         }
                     }
@@ -1191,6 +1200,7 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters, unsigned long long *prof)
         }
     }
     iters = kk;
+    if (!(fabs(w.alpha) <= 1.0) || !(fabs(w.mu) < 1e300)) w.flags |= CF_FLAG_NONFINITE;
     if (kk == itmax) return 1;
     if (w.alpha <= CF_ALPHA_MIN) return 2;
     if (w.mu != w.mu) return 3;

@@ -298,7 +298,9 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     CKH(cudaMemsetAsync(h->d_euler, 0, B * 3 * 8, h->stream));
     CKH(cudaMemsetAsync(h->d_twist, 0, B * 4 * 8, h->stream));
     // uss as the node computes it: float arithmetic, g0 = 9.80665 (acados_mpc.cpp:107,189,253)
-    h->uss = (double) sqrtf((0.033f * 9.80665f) / (4.0f * 3.25e-4f));
+    // `uss = sqrt((mq*g0)/(4*Ct))` with float mq, Ct, uss and g0 a double macro: the product and the quotient are double,
+    // 4*Ct is float, only the result is rounded to float = 15.777770042419434
+    h->uss = (double) (float) sqrt(((double) 0.033f * 9.80665) / (double) (4.0f * 3.25e-4f));
     CKH(cudaMalloc(&h->d_scratch, (size_t) h->n_slots * stride * 8));
     CKH(cudaMemsetAsync(h->d_scratch, 0, (size_t) h->n_slots * stride * 8, h->stream));
     CKH(cudaMemsetAsync(h->d_x0, 0, B * CF_NX * 8, h->stream));
@@ -442,6 +444,9 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         !strcmp(field, "policy") || !strcmp(field, "traj_iter") || !strcmp(field, "setpoint")) {
         batch_field(h, field, r);
         CK(cudaMemcpyAsync(r.dev, src, r.bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        // a preparation phase belongs to the iterate it linearised: a new iterate invalidates it (the reference would
+        // silently combine the two, ocp_nlp_sqp_rti.c:545-683; here cfnmpc_batch_feedback then returns CFNMPC_ESTATE)
+        if (!strcmp(field, "x") || !strcmp(field, "u")) h->prepared = false;
         return CFNMPC_OK;
     }
     return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_set: unknown field '") + field + "'");
@@ -508,6 +513,7 @@ static int ensure_prep_store(cfnmpc_batch *h)
         cudaError_t e = cudaMalloc(&h->d_prep, bytes);
         if (e != cudaSuccess) {
             h->d_prep = nullptr;
+            (void) cudaGetLastError();   // the failed allocation must not surface as the error of the fused-kernel launch that follows
             return fail(CFNMPC_ECUDA, std::string("cannot allocate the prepared linearisations (") + std::to_string(bytes >> 20) +
                                           " MiB): " + cudaGetErrorString(e));
         }

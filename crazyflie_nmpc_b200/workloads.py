@@ -27,9 +27,11 @@ def hover_speed():
 
 
 def node_hover_speed():
-    """uss as the ROS node computes it: float arithmetic, g0 = 9.80665
-    (acados_mpc.cpp:107,189,253)."""
-    return float(np.sqrt(np.float32(np.float32(MQ) * np.float32(9.80665)) / np.float32(4 * np.float32(CT))))
+    """uss as the ROS node computes it (acados_mpc.cpp:107,189,253): `uss = sqrt((mq*g0)/(4*Ct))` with float mq, Ct,
+    uss and the double macro g0 = 9.80665 -- double product and quotient, float 4*Ct, result rounded to float."""
+    num = float(np.float32(MQ)) * 9.80665
+    den = float(np.float32(4.0) * np.float32(CT))
+    return float(np.float32(np.sqrt(num / den)))
 
 
 def helix_table():
@@ -131,3 +133,32 @@ def single_hover(N=50, template_iterate=True, node_yref=False, x0=None):
     return dict(x0=x0[None].copy(), yref=np.ascontiguousarray(np.broadcast_to(y, (1, N, NY))),
                 yref_e=y[None, :NX].copy(), x_init=np.ascontiguousarray(np.broadcast_to(xi, (1, N + 1, NX))),
                 u_init=np.full((1, N, NU), ui))
+
+
+def adversarial_batch(B, N=50, seed=7, level=1.0):
+    """Deliberately ill-conditioned instances for probing the interior-point safety nets (the reference's LQ
+    re-factorisation / iterative refinement, external/hpipm/ocp_qp/x_ocp_qp_ipm.c:2029-2059,2311-2318): weights spread
+    log-uniformly over 1e-8..1e6 per component, 60-90 degree tilts, |omega| up to 20 rad/s, fast translation, input
+    boxes that are nearly coincident or exclude the hover thrust.  Extra keys: W [B,17], W_e [B,13], lbu, ubu [B,4]."""
+    rng = np.random.default_rng(seed)
+    uss = hover_speed()
+    w = hover_batch(B, N, seed=seed + 1)
+    sgn = rng.choice([-1.0, 1.0], (B, 3))
+    rpy = sgn * rng.uniform(np.deg2rad(60), np.deg2rad(90), (B, 3)) * level
+    rpy[:, 2] = rng.uniform(-np.pi, np.pi, B)
+    x0 = w["x0"].copy()
+    x0[:, 3:7] = _quat_from_rpy(rpy[:, 0], rpy[:, 1], rpy[:, 2])
+    x0[:, 7:10] = rng.uniform(-3, 3, (B, 3)) * level
+    om = rng.normal(size=(B, 3))
+    x0[:, 10:13] = om / np.linalg.norm(om, axis=1, keepdims=True) * rng.uniform(10, 20, (B, 1)) * level
+    W = 10.0 ** rng.uniform(-8, 6, (B, NY))
+    W_e = 10.0 ** rng.uniform(-8, 6, (B, NX))
+    kind = rng.integers(0, 3, B)
+    mid = rng.uniform(0.5, 21.5, (B, NU))
+    half = 10.0 ** rng.uniform(-7, 0, (B, NU))
+    lbu = np.where(kind[:, None] == 0, 0.0, mid - half)
+    ubu = np.where(kind[:, None] == 0, U_MAX, mid + half)
+    u_init = np.broadcast_to((0.5 * (lbu + ubu))[:, None, :], (B, N, NU)) if False else np.full((B, N, NU), uss)
+    w.update(x0=np.ascontiguousarray(x0), x_init=np.ascontiguousarray(np.broadcast_to(x0[:, None, :], (B, N + 1, NX))),
+             u_init=np.ascontiguousarray(u_init), W=W, W_e=W_e, lbu=np.ascontiguousarray(lbu), ubu=np.ascontiguousarray(ubu))
+    return w

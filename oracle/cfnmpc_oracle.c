@@ -276,7 +276,10 @@ typedef struct
  * x_ocp_qp_ipm.c:133-161 */
 static const double RES_G_MAX = 1e-6, RES_B_MAX = 1e-8, RES_D_MAX = 1e-8, RES_M_MAX = 1e-8;
 static const double ALPHA_MIN = 1e-8, MU0 = 1.0, REG_PRIM = 1e-15, LAM_MIN = 1e-16, T_MIN = 1e-16, TAU_MIN = 1e-16;
-static const int ITER_MAX = 50, ITREF_CORR_MAX = 2;
+static const int ITREF_CORR_MAX = 2;
+static int ITER_MAX = 50;
+/* qp_iter_max (ocp_qp_hpipm.c:96-108 sets 50); tests lower it to exercise the MAXITER branch of ocp_nlp_sqp_rti.c:651-674 */
+void cfo_set_iter_max(int n) { ITER_MAX = (n > 0 && n < 50) ? n : 50; }
 
 /* 0: square-root Riccati (the reference configuration, x_ocp_qp_kkt.c:445-572);
  * 1: HPIPM's classical Riccati (square_root_alg = 0, x_ocp_qp_kkt.c:573-740) -- the variant the CUDA

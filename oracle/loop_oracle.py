@@ -2,9 +2,11 @@
 
 Follows crazyflie_controller/src/acados_mpc.cpp (file:line in each function) one vehicle at a time in plain
 Python/numpy; used by tests/ to check the device kernels of crazyflie_nmpc_b200/csrc/cf_loop_kernels.h.
-Parity status: the ROS node cannot run here (no ROS, no radio), so these restatements are checked against the
-node's SOURCE semantics only (hand-derived known answers in tests/test_loop_oracle.py); the integrator part is
-pinned against the reference's own sim_erk (oracle/ref_harness.c: cfref_sim_*).
+Parity PINNED: tests/test_node_golden.py checks these restatements bit-for-bit against what the reference's own,
+unmodified NMPC::iteration published and handed to the solver when it was compiled with stand-in ROS headers and run
+on the reference's acados build (tests/dropin/build_node.py, tests/golden/make_node_golden.py ->
+tests/golden/node_loop_golden.npz: Regulation -> set-point change -> Tracking -> end of table -> Position_Hold); the
+integrator part is pinned against the reference's own sim_erk (oracle/ref_harness.c: cfref_sim_*).
 """
 import math
 
@@ -16,9 +18,10 @@ PI_NODE = 3.14159265358979323846       # acados_mpc.cpp:105
 
 
 def node_uss():
-    """uss = sqrt((mq*g0)/(4*Ct)) evaluated in float, g0 = 9.80665 (acados_mpc.cpp:107,189,253)."""
-    mq, g0, Ct = np.float32(33e-3), np.float32(9.80665), np.float32(3.25e-4)
-    return float(np.sqrt((mq * g0) / (np.float32(4) * Ct), dtype=np.float32))
+    """uss = sqrt((mq*g0)/(4*Ct)) as the node's C++ evaluates it (acados_mpc.cpp:107,189,253): mq, Ct, uss are float, g0
+    is a double macro -> mq*g0 and the quotient are double, 4*Ct is float, the result is rounded to float."""
+    mq, Ct = np.float32(33e-3), np.float32(3.25e-4)
+    return float(np.float32(np.sqrt((float(mq) * 9.80665) / float(np.float32(4) * Ct))))
 
 
 def reference_window(policy, it, setpoint, traj, N, uss, yref_prev, yref_e_prev):

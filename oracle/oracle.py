@@ -64,11 +64,16 @@ class Port:
         L.cfo_sim.argtypes = [_dp, _dp, ctypes.c_double, ctypes.c_int, _dp]
         L.cfo_ode.argtypes = [_dp, _dp, _dp]
         L.cfo_default_params.argtypes = [ctypes.POINTER(CfoParams)]
+        L.cfo_set_iter_max.argtypes = [ctypes.c_int]
         L.cfo_set_time_steps.argtypes = [_dp, ctypes.c_int]
         L.cfo_set_stage_bounds.argtypes = [_dp, ctypes.c_int]
         L.cfo_rti_split.restype = ctypes.c_int
         L.cfo_rti_split.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), _dp, _dp, _dp, _dp, _dp, _dp,
                                     ctypes.POINTER(CfoInfo)]
+
+    def set_iter_max(self, n=50):
+        """qp_iter_max of the interior-point loop (global in the checker; 50 = the reference configuration)."""
+        self.lib.cfo_set_iter_max(int(n))
 
     def set_time_steps(self, dt=None):
         """Non-uniform shooting grid (global in the checker; None returns to the uniform grid)."""
@@ -177,6 +182,10 @@ class Ref:
         L.cfref_create_dt.argtypes = [ctypes.c_int, _dp, ctypes.c_int]
         L.cfref_rti_split.restype = ctypes.c_int
         L.cfref_rti_split.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+        L.cfref_set_opt_int.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        L.cfref_get_multipliers.argtypes = [ctypes.c_void_p, _dp, _dp]
+        L.cfref_set_W_at.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp]
+        L.cfref_get_stat.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
         L.cfref_batch.restype = ctypes.c_int
         L.cfref_batch.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
@@ -226,6 +235,31 @@ class RefSolver:
 
     def set_input_bounds_stage0(self, lbu0, ubu0):
         self.lib.cfref_set_input_bounds_stage0(self.h, _P(np.ascontiguousarray(lbu0, float)), _P(np.ascontiguousarray(ubu0, float)))
+
+    def set_opt_int(self, name, value):
+        """ocp_nlp_solver_opts_set with an int value ("qp_iter_max", ...)."""
+        self.lib.cfref_set_opt_int(self.h, name.encode(), int(value))
+
+    def set_W_at(self, stage, W):
+        """Full weight matrix of one stage (column-major; symmetric, so the order does not matter)."""
+        self.lib.cfref_set_W_at(self.h, int(stage), _P(np.ascontiguousarray(W, float)))
+
+    def multipliers(self):
+        """(pi [N,13], lam0 [2,17], lam [N-1,2,4]) of the iterate after the last solve; lam = [lower | upper]."""
+        N = self.N
+        pi, lam = np.zeros((N, NX)), np.zeros(2 * NV + 2 * NU * (N - 1))
+        self.lib.cfref_get_multipliers(self.h, _P(pi), _P(lam))
+        return pi, lam[:2 * NV].reshape(2, NV), lam[2 * NV:].reshape(N - 1, 2, NU)
+
+    def stat_double(self, name):
+        v = ctypes.c_double()
+        self.lib.cfref_get_stat(self.h, name.encode(), ctypes.byref(v))
+        return v.value
+
+    def stat_int(self, name):
+        v = ctypes.c_int()
+        self.lib.cfref_get_stat(self.h, name.encode(), ctypes.byref(v))
+        return v.value
 
     def rti(self, x0, yref, yref_e, x, u):
         """One RTI step; x,u updated in place. Returns (status, qp_iter, qp_status, times[5])."""

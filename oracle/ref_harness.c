@@ -500,3 +500,49 @@ int cfref_sim_solve(void *h_, const double *x, const double *u, double T, double
     if (S_forw && h->sens_forw) sim_out_get(h->config, h->dims, h->out, "S_forw", S_forw);
     return status;
 }
+
+/* ------------------------------------------------------------------ round-2 additions (edge-case parity)
+ * Solver option by name, integer valued ("qp_iter_max", "qp_cond_N", ...): ocp_nlp_solver_opts_set,
+ * acados/interfaces/acados_c/ocp_nlp_interface.h:313. */
+void cfref_set_opt_int(void *h_, const char *name, int value)
+{
+    cfref *h = h_;
+    ocp_nlp_solver_opts_set(h->config, h->opts, name, &value);
+}
+
+/* Multipliers of the iterate after the last solve, as ocp_nlp_out_get hands them out
+ * (acados_c/ocp_nlp_interface.c:549-600): pi[N][13]; lam: stage 0 2*17, stages 1..N-1 2*4 each ([lower | upper]). */
+void cfref_get_multipliers(void *h_, double *pi, double *lam)
+{
+    cfref *h = h_;
+    int N = h->N, ol = 0;
+    for (int k = 0; k < N; k++) {
+        if (pi) ocp_nlp_out_get(h->config, h->dims, h->out, k, "pi", pi + NX * k);
+        int nb = k == 0 ? NX + NU : NU;
+        if (lam) ocp_nlp_out_get(h->config, h->dims, h->out, k, "lam", lam + ol);
+        ol += 2 * nb;
+    }
+}
+
+/* Cost weight of ONE stage as a full column-major matrix (17x17 for k < N, 13x13 for k = N):
+ * ocp_nlp_cost_model_set(.., k, "W", ..), ocp_nlp_cost_ls.c:301-331. */
+void cfref_set_W_at(void *h_, int stage, const double *W)
+{
+    cfref *h = h_;
+    ocp_nlp_cost_model_set(h->config, h->dims, h->in, stage, "W", (void *) W);
+}
+
+/* Solver statistics by name (double or int valued): ocp_nlp_get, ocp_nlp_sqp_rti.c:1361-1425 */
+void cfref_get_stat(void *h_, const char *name, void *value)
+{
+    cfref *h = h_;
+    ocp_nlp_get(h->config, h->solver, name, value);
+}
+
+/* The acados objects behind a handle, for the node harness (tests/dropin/refglue/ref_node_glue.c), which must fill the
+ * process globals the reference's ROS node defines (crazyflie_controller/src/acados_mpc.cpp:76-84). */
+void cfref_export(void *h_, void **plan, void **config, void **dims, void **in, void **out, void **opts, void **solver)
+{
+    cfref *h = h_;
+    *plan = h->plan; *config = h->config; *dims = h->dims; *in = h->in; *out = h->out; *opts = h->opts; *solver = h->solver;
+}

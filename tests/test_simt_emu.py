@@ -29,7 +29,7 @@ def emu():
 
     L.cfemu_rti_batch2.argtypes = L.cfemu_rti_batch.argtypes + [ctypes.POINTER(_dp)]
 
-    def run(w, N, n_rti=1, params=None, per_inst=None):
+    def run(w, N, n_rti=1, params=None, per_inst=None, max_ipm_iter=0):
         B = w["x0"].shape[0]
         x, u = w["x_init"].copy(), w["u_init"].copy()
         st, it, qs, fl = [np.zeros(B, np.int32) for _ in range(4)]
@@ -43,7 +43,7 @@ def emu():
                     for k in ("W", "W_e", "lbu", "ubu", "lbu0", "ubu0")]
             pi = (_dp * 6)(*[P(a) if a is not None else None for a in keep])
         for _ in range(n_rti):
-            L.cfemu_rti_batch2(B, N, TS, P(par) if par is not None else None, 0, P(w["x0"]), P(w["yref"]), P(w["yref_e"]),
+            L.cfemu_rti_batch2(B, N, TS, P(par) if par is not None else None, int(max_ipm_iter), P(w["x0"]), P(w["yref"]), P(w["yref_e"]),
                                P(x), P(u), I(st), I(it), I(qs), I(fl), P(res), None, 4, pi)
         return dict(x=x, u=u, status=st, qp_iter=it, qp_status=qs, flags=fl, res=res)
     return run
@@ -330,3 +330,45 @@ def test_emulated_per_stage_input_bounds(emu_general, port, ref, split):
         L.cfemu_set_stage_bounds(None)
         port.set_stage_bounds(None)
     assert rel_err(emu_general(w, N, split=split)["u"], r["u"]) > 1e-3     # the table mattered
+
+
+# ------------------------------------------------------------------ reference edge cases (tests/golden/edge_golden.npz)
+XSEL = [1, 4, 50]
+
+
+@pytest.fixture(scope="module")
+def edge():
+    return np.load(os.path.join(HERE, "golden", "edge_golden.npz"))
+
+
+@pytest.mark.parametrize("itmax", [3, 5])
+def test_emulated_kernel_qp_maxiter_branch(emu, edge, itmax):
+    """HPIPM stops at its iteration limit: the reference applies the step and returns SUCCESS
+    (ocp_nlp_sqp_rti.c:651-674); status, qp_status, iteration count and iterate must match the reference's."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    n = 8
+    w = {k: v[:n] for k, v in wl.hover_batch(32, 50, seed=11).items()}
+    r = emu(w, 50, max_ipm_iter=itmax)
+    assert np.array_equal(r["status"], edge[f"maxiter_{itmax}_status"][:n])
+    assert np.array_equal(r["qp_status"], edge[f"maxiter_{itmax}_qp_status"][:n])
+    assert np.array_equal(r["qp_iter"], edge[f"maxiter_{itmax}_qp_iter"][:n])
+    assert rel_err(r["u"], edge[f"maxiter_{itmax}_u"][:n]) < 1e-9
+    assert rel_err(r["x"][:, XSEL], edge[f"maxiter_{itmax}_xsel"][:n]) < 1e-9
+
+
+def test_emulated_kernel_flags_where_the_reference_nets_fire(emu, edge):
+    """Ill-conditioned instances: where the reference switched to its LQ factorisation or ran iterative refinement the
+    kernel's linear-residual flags must be set; converged, unflagged instances agree with the reference."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    w = wl.adversarial_batch(128, 50, seed=5)
+    fired = np.nonzero((edge["adv_lq"] > 0) | (edge["adv_itref"] > 0))[0]
+    calm = np.nonzero((edge["adv_qp_status"] == 0) & (edge["adv_lq"] == 0) & (edge["adv_itref"] == 0))[0][:6]
+    sel = np.r_[fired, calm]
+    ws = {k: np.ascontiguousarray(w[k][sel]) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
+    r = emu(ws, 50, per_inst={k: np.ascontiguousarray(w[k][sel]) for k in ("W", "W_e", "lbu", "ubu")})
+    nf = len(fired)
+    assert nf >= 3
+    assert ((r["flags"][:nf] & 3) != 0).all(), r["flags"][:nf]
+    assert (r["flags"][nf:] == 0).all() and (r["status"][nf:] == 0).all() and (r["qp_status"][nf:] == 0).all()
+    assert rel_err(r["u"][nf:], edge["adv_u"][calm]) < 1e-6
+    assert rel_err(r["x"][nf:][:, XSEL], edge["adv_xsel"][calm]) < 1e-6
