@@ -741,7 +741,9 @@ struct CfWarpT
             // ---- POTRF_L_MN(nv+1, nu): the 4 input columns, one per step, lane = row; non-positive pivot -> 0
             // (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
             {
-                const cf_d2 o01 = cf_ld2(LUs + rl * 4), o23 = cf_ld2(LUs + rl * 4 + 2);
+                // lanes 18..31 carry no row: they must not read row 17 while lane 17 rewrites it below (racecheck)
+                cf_d2 o01 = {0.0, 0.0}, o23 = {0.0, 0.0};
+                if (lane < CF_MROWS) { o01 = cf_ld2(LUs + rl * 4); o23 = cf_ld2(LUs + rl * 4 + 2); }
                 double o[CF_NU] = {o01.x, o01.y, o23.x, o23.y}, og[CF_NU];
                 CF_UNROLL
                 for (int j = 0; j < CF_NU; j++) {

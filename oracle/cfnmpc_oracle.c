@@ -247,21 +247,25 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
 
 /* ------------------------------------------------------------------ QP / IPM
  * Reduced QP after x0 elimination (x_ocp_qp_red.c:268-455): stage 0 has nx=0. */
+#define NVM 32 /* largest stage the generic routines handle: partially condensed stages have nu = 4 * block size */
+#define NUM 19
 typedef struct
 {
     int nu, nx, nv, nb;
-    double M[NV][NX]; /* [B';A'] rows (nv of them) */
+    int dense;            /* != 0: Hessian Hm (partially condensed stage) instead of the diagonal H */
+    double M[NVM][NX]; /* [B';A'] rows (nv of them) */
     double b[NX];
-    double H[NV], rq[NV]; /* diagonal Hessian (+ gradient) */
-    double d[2 * NU];     /* [lb; ub] (HPIPM sign convention) */
-    double ux[NV], pi[NX], lam[2 * NU], t[2 * NU];
-    double res_g[NV], res_b[NX], res_d[2 * NU], res_m[2 * NU], res_m_bkp[2 * NU];
-    double dux[NV], dpi[NX], dlam[2 * NU], dt[2 * NU];
-    double rg2[NV], rb2[NX], rd2[2 * NU], rm2[2 * NU];                /* res_itref */
-    double dux2[NV], dpi2[NX], dlam2[2 * NU], dt2[2 * NU];            /* sol_itref */
-    double L[NV + 1][NV];
+    double H[NVM], rq[NVM]; /* diagonal Hessian (+ gradient) */
+    double Hm[NVM][NVM];    /* dense symmetric Hessian of a condensed stage (both triangles) */
+    double d[2 * NUM];     /* [lb; ub] (HPIPM sign convention) */
+    double ux[NVM], pi[NX], lam[2 * NUM], t[2 * NUM];
+    double res_g[NVM], res_b[NX], res_d[2 * NUM], res_m[2 * NUM], res_m_bkp[2 * NUM];
+    double dux[NVM], dpi[NX], dlam[2 * NUM], dt[2 * NUM];
+    double rg2[NVM], rb2[NX], rd2[2 * NUM], rm2[2 * NUM];                /* res_itref */
+    double dux2[NVM], dpi2[NX], dlam2[2 * NUM], dt2[2 * NUM];            /* sol_itref */
+    double L[NVM + 1][NVM];
     double Pm[NX][NX], pv[NX]; /* classical Riccati: cost-to-go Hessian / gradient of this stage */
-    double Gamma[2 * NU], gamma[2 * NU], t_inv[2 * NU], Pb[NX];
+    double Gamma[2 * NUM], gamma[2 * NUM], t_inv[2 * NUM], Pb[NX];
 } stage;
 
 typedef struct
@@ -289,7 +293,7 @@ void cfo_set_classical_riccati(int on) { g_classical = on; }
 
 /* lower Cholesky of the n x n top of an m x n block, remaining rows solved;
  * non-positive pivot -> 0 (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714) */
-static void potrf_l_mn(int m, int n, double L[NV + 1][NV])
+static void potrf_l_mn(int m, int n, double L[NVM + 1][NVM])
 {
     for (int j = 0; j < n; j++) {
         double djj = L[j][j];
@@ -390,7 +394,7 @@ static void fact_solve_kkt_step(ipm *w)
     compute_Gamma_gamma(w, 1, 0);
     for (int k = N; k >= 0 && g_classical; k--) {
         stage *s = &w->s[k];
-        double AL[NV + 1][NX];
+        double AL[NVM + 1][NX];
         if (k < N) {
             stage *n = &w->s[k + 1];
             for (int r = 0; r <= s->nv; r++) /* AL = [B';A';res_b'] * P(k+1)   (GEMM_NT, :621) */
@@ -403,6 +407,9 @@ static void fact_solve_kkt_step(ipm *w)
         }
         memset(s->L, 0, sizeof s->L);
         for (int i = 0; i < s->nv; i++) { s->L[i][i] = s->H[i] + REG_PRIM; s->L[s->nv][i] = s->res_g[i]; }
+        if (s->dense)
+            for (int i = 0; i < s->nv; i++)
+                for (int j = 0; j <= i; j++) s->L[i][j] = s->Hm[i][j] + (i == j ? REG_PRIM : 0.0);
         for (int i = 0; i < s->nb; i++) {
             s->L[i][i] += s->Gamma[i] + s->Gamma[s->nb + i];
             s->L[s->nv][i] += s->gamma[i] - s->gamma[s->nb + i];
@@ -429,7 +436,7 @@ static void fact_solve_kkt_step(ipm *w)
     }
     for (int k = N; k >= 0 && !g_classical; k--) {
         stage *s = &w->s[k];
-        double AL[NV + 1][NX];
+        double AL[NVM + 1][NX];
         if (k < N) {
             stage *n = &w->s[k + 1];
             /* AL = [B';A';res_b'] * Lxx(k+1)   (TRMM_RLNN) */
@@ -450,6 +457,9 @@ static void fact_solve_kkt_step(ipm *w)
         }
         memset(s->L, 0, sizeof s->L);
         for (int i = 0; i < s->nv; i++) { s->L[i][i] = s->H[i] + REG_PRIM; s->L[s->nv][i] = s->res_g[i]; }
+        if (s->dense)
+            for (int i = 0; i < s->nv; i++)
+                for (int j = 0; j <= i; j++) s->L[i][j] = s->Hm[i][j] + (i == j ? REG_PRIM : 0.0);
         for (int i = 0; i < s->nb; i++) {
             s->L[i][i] += s->Gamma[i] + s->Gamma[s->nb + i];
             s->L[s->nv][i] += s->gamma[i] - s->gamma[s->nb + i];
@@ -548,7 +558,11 @@ static void res_compute(ipm *w)
     double mu = 0;
     for (int k = 0; k <= N; k++) {
         stage *s = &w->s[k];
-        for (int i = 0; i < s->nv; i++) s->res_g[i] = s->H[i] * s->ux[i] + s->rq[i];
+        for (int i = 0; i < s->nv; i++) {
+            double v = s->H[i] * s->ux[i];
+            if (s->dense) { v = 0; for (int j = 0; j < s->nv; j++) v += s->Hm[i][j] * s->ux[j]; }   /* SYMV_L */
+            s->res_g[i] = v + s->rq[i];
+        }
         if (k > 0) for (int i = 0; i < s->nx; i++) s->res_g[s->nu + i] -= w->s[k - 1].pi[i];
         for (int i = 0; i < s->nb; i++) {
             s->res_g[i] += s->lam[s->nb + i] - s->lam[i];
@@ -580,7 +594,11 @@ static void res_compute_lin(ipm *w)
     int N = w->N;
     for (int k = 0; k <= N; k++) {
         stage *s = &w->s[k];
-        for (int i = 0; i < s->nv; i++) s->rg2[i] = s->H[i] * s->dux[i] + s->res_g[i];
+        for (int i = 0; i < s->nv; i++) {
+            double v = s->H[i] * s->dux[i];
+            if (s->dense) { v = 0; for (int j = 0; j < s->nv; j++) v += s->Hm[i][j] * s->dux[j]; }
+            s->rg2[i] = v + s->res_g[i];
+        }
         if (k > 0) for (int i = 0; i < s->nx; i++) s->rg2[s->nu + i] -= w->s[k - 1].dpi[i];
         for (int i = 0; i < s->nb; i++) {
             s->rg2[i] += s->dlam[s->nb + i] - s->dlam[i];
@@ -861,6 +879,174 @@ int cfo_rti(int N, double Ts, const cfo_params *p_, const double *x0, const doub
     return status;
 }
 
+/* ------------------------------------------------------------------ partial condensing
+ * d_part_cond_qp_cond / d_part_cond_qp_expand_sol (external/hpipm/cond/x_part_cond.c:505-560,658-742) with the block
+ * sizes of PART_COND_QP_COMPUTE_BLOCK_SIZE (:36-54): the first N mod N2 blocks hold floor(N/N2)+1 stages, the others
+ * floor(N/N2); the terminal stage stays alone.  A block [k0, k0+bs) becomes ONE stage with state x_k0 and inputs
+ * [u_{k0+bs-1}; ...; u_k0] (last stage first, x_cond_aux.c:251-273).  Restated mathematically (the products HPIPM forms
+ * in COND_BABT :36-100 / COND_RSQRQ :208-470 / COND_DCTD :840 differ from these sums by rounding only):
+ *   x_{k0+j} = G_j' [ubar; xbar; 1],  G_0 = [0; I; 0],  G_{j+1} = G_j A_j' + [E_j B_j'; 0; b_j']
+ *   H2 = blkdiag(R_j.., Q_0) + sum_{j>=1} G_j Q_j G_j',  rq2 = [r_j..; q_0] + sum_{j>=1} G_j (q_j + Q_j c_j)
+ * where c_j is the constant row of G_j.  Only input boxes exist, so the inequality data are just re-ordered. */
+void cfo_block_sizes(int N, int N2, int *bs)
+{
+    int bs0 = N / N2, ii = 0;
+    for (; ii < N - N2 * bs0; ii++) bs[ii] = bs0 + 1;
+    for (; ii < N2; ii++) bs[ii] = bs0;
+    bs[N2] = 0;
+}
+
+static void condense_block(const stage *src, int bs, stage *dst)
+{
+    const int nu2 = NU * bs, nx2 = src[0].nx, nv2 = nu2 + nx2;
+    static double G[2][NVM + 1][NX];
+    memset(dst, 0, sizeof *dst);
+    dst->nu = nu2; dst->nx = nx2; dst->nv = nv2; dst->nb = nu2; dst->dense = 1;
+    memset(G, 0, sizeof G);
+    for (int i = 0; i < nx2; i++) G[0][nu2 + i][i] = 1.0;
+    for (int i = 0; i < nx2; i++) { dst->Hm[nu2 + i][nu2 + i] = src[0].H[NU + i]; dst->rq[nu2 + i] = src[0].rq[NU + i]; }
+    for (int j = 0; j < bs; j++) {
+        const stage *sj = &src[j];
+        const int off = NU * (bs - 1 - j);
+        double (*Gc)[NX] = G[j & 1], (*Gn)[NX] = G[(j + 1) & 1];
+        for (int e = 0; e < NU; e++) {
+            dst->Hm[off + e][off + e] = sj->H[e];
+            dst->rq[off + e] = sj->rq[e];
+            dst->d[off + e] = sj->d[e];
+            dst->d[nu2 + off + e] = sj->d[NU + e];
+        }
+        if (j >= 1) {   /* cost of x_{k0+j}: 1/2 x'Qx + q'x with x = G_j' z */
+            for (int r = 0; r < nv2; r++) {
+                for (int c = 0; c <= r; c++) {
+                    double v = 0;
+                    for (int i = 0; i < NX; i++) v += Gc[r][i] * sj->H[NU + i] * Gc[c][i];
+                    dst->Hm[r][c] += v;
+                }
+                double g = 0;
+                for (int i = 0; i < NX; i++) g += Gc[r][i] * (sj->rq[NU + i] + sj->H[NU + i] * Gc[nv2][i]);
+                dst->rq[r] += g;
+            }
+        }
+        /* G_{j+1} = G_j A_j' + [E_j B_j' ; 0 ; b_j'] */
+        for (int r = 0; r <= nv2; r++)
+            for (int c = 0; c < NX; c++) {
+                double v = 0;
+                if (sj->nx > 0) for (int i = 0; i < NX; i++) v += Gc[r][i] * sj->M[NU + i][c];
+                Gn[r][c] = v;
+            }
+        for (int e = 0; e < NU; e++) for (int c = 0; c < NX; c++) Gn[off + e][c] += sj->M[e][c];
+        for (int c = 0; c < NX; c++) Gn[nv2][c] += sj->b[c];
+    }
+    for (int r = 0; r < nv2; r++) {
+        for (int c = 0; c < NX; c++) dst->M[r][c] = G[bs & 1][r][c];
+        for (int c = r + 1; c < nv2; c++) dst->Hm[r][c] = dst->Hm[c][r];   /* filled below the diagonal above */
+    }
+    for (int r = 0; r < nv2; r++) for (int c = 0; c < r; c++) dst->Hm[c][r] = dst->Hm[r][c];
+    for (int c = 0; c < NX; c++) dst->b[c] = G[bs & 1][nv2][c];
+}
+
+/* uncondensed, x0-eliminated stages of one RTI step (shared by cfo_rti and cfo_rti_pcond) */
+static void build_reduced_stages(int N, double Ts, const cfo_params *p_, const double *BAbt, const double *b, const double *rqz,
+                                 const double *dl, const double *du, stage *st, double *xbar)
+{
+    (void) Ts;
+    for (int i = 0; i < NX; i++) xbar[i] = dl[NU + i]; /* lower-bound entry is the value (x_ocp_qp_red.c:310-315) */
+    for (int k = 0; k <= N; k++) {
+        stage *s = &st[k];
+        s->nu = k < N ? NU : 0;
+        s->nx = k == 0 ? 0 : NX;
+        s->nv = s->nu + s->nx;
+        s->nb = k < N ? NU : 0;
+        for (int i = 0; i < s->nu; i++) { double r = sqrt(p_->Wdiag[NX + i]); s->H[i] = DTK(k) * (r * r); }
+        for (int i = 0; i < s->nx; i++) {
+            double r = sqrt(k < N ? p_->Wdiag[i] : p_->WNdiag[i]);
+            s->H[s->nu + i] = (k < N ? DTK(k) : 1.0) * (r * r);
+        }
+        const double *g = rqz + NV * k;
+        if (k == 0) { for (int i = 0; i < NU; i++) s->rq[i] = g[i]; }
+        else { for (int i = 0; i < s->nv; i++) s->rq[i] = g[i]; }
+        if (k < N) {
+            const double *M = BAbt + (size_t) k * NV * NX;
+            if (k == 0) {
+                for (int r = 0; r < NU; r++) for (int c = 0; c < NX; c++) s->M[r][c] = M[r * NX + c];
+                for (int c = 0; c < NX; c++) {
+                    double v = 0;
+                    for (int r = 0; r < NX; r++) v += M[(NU + r) * NX + c] * xbar[r];
+                    s->b[c] = v + b[c];
+                }
+            } else {
+                for (int r = 0; r < NV; r++) for (int c = 0; c < NX; c++) s->M[r][c] = M[r * NX + c];
+                for (int c = 0; c < NX; c++) s->b[c] = b[NX * k + c];
+            }
+            int od = k == 0 ? 0 : NV + NU * (k - 1);
+            for (int i = 0; i < NU; i++) { s->d[i] = dl[od + i]; s->d[NU + i] = du[od + i]; }
+        }
+    }
+}
+
+/* One RTI step with the QP partially condensed to N2 stages before the interior-point solve (qp_cond_N = N2 < N in the
+ * reference: ocp_qp_partial_condensing.c:457-576, ocp_qp_xcond_solver.c:487-533).  N2 >= N or <= 0: plain cfo_rti. */
+int cfo_rti_pcond(int N, double Ts, const cfo_params *p_, int N2, const double *x0, const double *yref,
+                  const double *yref_e, double *x, double *u, cfo_info *info_)
+{
+    if (N2 <= 0 || N2 >= N) return cfo_rti(N, Ts, p_, x0, yref, yref_e, x, u, info_, NULL, NULL);
+    cfo_params pd;
+    cfo_info li;
+    cfo_info *info = info_ ? info_ : &li;
+    memset(info, 0, sizeof *info);
+    if (!p_) { cfo_default_params(&pd); p_ = &pd; }
+    if ((N + N2 - 1) / N2 * NU + NX > NVM) return -1;   /* block too large for the generic stage */
+    double *BAbt = malloc(sizeof(double) * N * NV * NX), *b = malloc(sizeof(double) * N * NX);
+    double *rqz = malloc(sizeof(double) * (N * NV + NX));
+    double *dl = malloc(sizeof(double) * (NV + NU * N)), *du = malloc(sizeof(double) * (NV + NU * N));
+    cfo_linearize(N, Ts, p_, x0, yref, yref_e, x, u, BAbt, b, rqz, dl, du);
+    stage *st = calloc(N + 1, sizeof(stage));
+    double xbar[NX];
+    build_reduced_stages(N, Ts, p_, BAbt, b, rqz, dl, du, st, xbar);
+
+    int *bs = malloc(sizeof(int) * (N2 + 1));
+    cfo_block_sizes(N, N2, bs);
+    ipm w;
+    w.N = N2;
+    w.nc = 2 * NU * N;
+    w.s = calloc(N2 + 1, sizeof(stage));
+    int k0 = 0;
+    for (int i = 0; i < N2; i++) { condense_block(st + k0, bs[i], &w.s[i]); k0 += bs[i]; }
+    w.s[N2] = st[N];
+    ipm_solve(&w, info);
+
+    int status = 0;
+    if (info->qp_status == 0 || info->qp_status == 1) {
+        /* expansion (EXPAND_SOL, x_cond_aux.c:1820-): inner states by the dynamics, then the full step */
+        k0 = 0;
+        for (int i = 0; i < N2; i++) {
+            const stage *c = &w.s[i];
+            double xs[NX], xn[NX];
+            for (int r = 0; r < NX; r++) xs[r] = c->nx ? c->ux[c->nu + r] : 0.0;
+            for (int j = 0; j < bs[i]; j++) {
+                const stage *sj = &st[k0 + j];
+                const double *uj = c->ux + NU * (bs[i] - 1 - j);
+                if (k0 + j == 0) { for (int r = 0; r < NX; r++) x[r] += xbar[r]; }
+                else for (int r = 0; r < NX; r++) x[NX * (k0 + j) + r] += xs[r];
+                for (int e = 0; e < NU; e++) u[NU * (k0 + j) + e] += uj[e];
+                for (int cc = 0; cc < NX; cc++) {
+                    double v = sj->b[cc];
+                    for (int e = 0; e < NU; e++) v += sj->M[e][cc] * uj[e];
+                    if (sj->nx) for (int r = 0; r < NX; r++) v += sj->M[NU + r][cc] * xs[r];
+                    xn[cc] = v;
+                }
+                memcpy(xs, xn, sizeof xs);
+            }
+            k0 += bs[i];
+        }
+        for (int r = 0; r < NX; r++) x[NX * N + r] += w.s[N2].ux[r];
+    } else {
+        status = 4;
+    }
+    free(w.s); free(st); free(bs); free(BAbt); free(b); free(rqz); free(dl); free(du);
+    return status;
+}
+
 /* Split real-time iteration (rti_phase 1 then 2, ocp_nlp_sqp_rti.c:495-683): the preparation linearises around the
  * iterate -- the measured state does not enter it -- and the feedback evaluates the bound vectors, i.e. the stage-0
  * equality x_0 = x0, with the data of the moment (ocp_nlp_approximate_qp_vectors_sqp, ocp_nlp_common.c:2258-2292).  The
@@ -882,6 +1068,20 @@ void cfo_batch(int N, double Ts, const cfo_params *p, int n_rti, int n, const do
         for (int r = 0; r < n_rti; r++)
             st = cfo_rti(N, Ts, p, x0 + NX * (size_t) i, yref + (size_t) N * NV * i, yref_e + NX * (size_t) i,
                          x + (size_t) (N + 1) * NX * i, u + (size_t) N * NU * i, &info, NULL, NULL);
+        if (status) status[i] = st;
+        if (qp_iter) qp_iter[i] = info.qp_iter;
+    }
+}
+
+void cfo_batch_pcond(int N, double Ts, const cfo_params *p, int N2, int n_rti, int n, const double *x0,
+                     const double *yref, const double *yref_e, double *x, double *u, int *status, int *qp_iter)
+{
+    for (int i = 0; i < n; i++) {
+        cfo_info info;
+        int st = 0;
+        for (int r = 0; r < n_rti; r++)
+            st = cfo_rti_pcond(N, Ts, p, N2, x0 + NX * (size_t) i, yref + (size_t) N * NV * i, yref_e + NX * (size_t) i,
+                               x + (size_t) (N + 1) * NX * i, u + (size_t) N * NU * i, &info);
         if (status) status[i] = st;
         if (qp_iter) qp_iter[i] = info.qp_iter;
     }

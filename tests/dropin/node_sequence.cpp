@@ -45,8 +45,9 @@ int main(int argc, char **argv)
         return 3;
     }
     // regulation reference as the node builds it (:435-454): set-point (0,0,0.4), float hover speed, g0 = 9.80665
-    const float mq = 33e-3f, g0 = 9.80665f, Ct = 3.25e-4f;
-    const double uss = sqrtf((mq * g0) / (4 * Ct));
+    const float mq = 33e-3f, Ct = 3.25e-4f;
+    const double g0 = 9.80665;
+    const float uss = sqrt((mq * g0) / (4 * Ct));   // as the node: float mq, Ct, uss; g0 a double macro (acados_mpc.cpp:107,189,253)
     double x0[NX] = {0.1, -0.05, 0.3, 1, 0, 0, 0, 0.1, 0, -0.1, 0, 0, 0};
     double yref_sign[(N + 1) * NY];
     for (int k = 0; k <= N; k++) {
