@@ -191,6 +191,8 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     s = cf.BatchSolver(B, N, TS, device=local)
     s.set_stream(stream.cuda_stream)
+    if args.qp_cond_N:
+        s.set_option("qp_cond_N", args.qp_cond_N)
 
     dev = torch.device("cuda", local)
     d_in = {k: torch.from_numpy(w[k]).to(dev) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
@@ -367,6 +369,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--ref-sample", type=int, default=0, help="instances per CPU step (default: scaled to the core count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--qp-cond-N", type=int, default=0, help="partial condensing to this many stages (0 = the reference's configuration, qp_cond_N = N)")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks of the overlapped host-to-device upload in the e2e path")
     args = ap.parse_args()
     if args.impl == "reference":

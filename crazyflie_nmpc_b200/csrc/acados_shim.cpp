@@ -132,7 +132,13 @@ int crazyflie_acados_update_time_steps(crazyflie_solver_capsule *c, int N, doubl
 int crazyflie_acados_update_qp_solver_cond_N(crazyflie_solver_capsule *c, int cond_N)
 {
     if (!c || cond_N < 1) return 1;
-    c->cond_N = cond_N;  // partial condensing changes nothing in the result for this OCP
+    c->cond_N = cond_N;
+    // blocks of up to 3 stages run on the partially condensed kernel (cf_pcond_warp.h); for coarser condensing the QP is
+    // solved uncondensed: same solution to the interior-point tolerances, stated on stderr once
+    if (c->batch && cfnmpc_batch_set_option(c->batch, "qp_cond_N", cond_N) != CFNMPC_OK) {
+        fprintf(stderr, "crazyflie_acados_update_qp_solver_cond_N: %s; solving uncondensed\n", cfnmpc_last_error());
+        cfnmpc_batch_set_option(c->batch, "qp_cond_N", 0);
+    }
     return 0;
 }
 
@@ -276,7 +282,7 @@ void ocp_nlp_out_get(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_out *out, int sta
 void ocp_nlp_solver_opts_set(ocp_nlp_config *config, void *, const char *field, void *value)
 {
     if (!config || !config->capsule || !field || !value) return;
-    if (!strcmp(field, "qp_cond_N")) config->capsule->cond_N = *static_cast<int *>(value);
+    if (!strcmp(field, "qp_cond_N")) crazyflie_acados_update_qp_solver_cond_N(config->capsule, *static_cast<int *>(value));
     else if (!strcmp(field, "rti_phase")) {
         const int v = *static_cast<int *>(value);
         if (v < 0 || v > 2) fprintf(stderr, "ocp_nlp_solver_opts_set: invalid value %d for rti_phase (0, 1, 2)\n", v);

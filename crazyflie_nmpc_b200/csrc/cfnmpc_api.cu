@@ -13,6 +13,7 @@
 
 #include "../../include/cfnmpc.h"
 #include "cf_rti_warp.h"
+#include "cf_pcond_warp.h"
 #include "cf_loop_kernels.h"
 
 
@@ -67,6 +68,30 @@ __global__ void __launch_bounds__(WPB * 32, MINB)
 cf_rti_kernel(const __grid_constant__ CfParams P, const __grid_constant__ CfBatchView bv)
 {
     cf_rti_kernel_body<WPB, PH, VDT>(P, bv);
+}
+// Feedback phase with the QP partially condensed to blk.N2 stages (cf_pcond_warp.h): same persistent-warp scheme; needs
+// the prepared linearisations of a preparation kernel.  BS = stages per block (the reference's qp_cond_N = ceil(N / BS)..).
+template <int WPB, int MINB, int BS>
+__global__ void __launch_bounds__(WPB * 32, MINB)
+cf_pcond_kernel(const __grid_constant__ CfParams P, const __grid_constant__ CfBatchView bv, const __grid_constant__ CfPcBlocks blk)
+{
+    extern __shared__ __align__(128) double cf_smem[];
+    const int warp = threadIdx.x >> 5;
+    double *sm = cf_smem + warp * CfPcWarpT<BS>::SM_DOUBLES;
+    double *slot = bv.scratch + (long) (blockIdx.x * WPB + warp) * bv.scratch_stride;
+    {
+        uint64_t *bar = reinterpret_cast<uint64_t *>(sm + CfPcWarpT<BS>::SM_BAR);
+        if ((threadIdx.x & 31) == 0) { cf_mbar_init(bar); cf_mbar_init(bar + 1); }
+        __syncwarp();
+    }
+    unsigned par = 0;
+    for (;;) {
+        int inst = 0;
+        if ((threadIdx.x & 31) == 0) inst = atomicAdd(bv.counter, 1);
+        inst = __shfl_sync(0xffffffffu, inst, 0);
+        if (inst >= bv.B) break;
+        cf_pcond_instance<BS>(&P, bv, blk, bv.first + inst, slot, sm, par);
+    }
 }
 // out[i][0:w] = src[i][stage*w : stage*w + w]   (ocp_nlp_out_get for every instance at once)
 __global__ void cf_gather_stage_kernel(const double *__restrict__ src, double *__restrict__ out, int B, int per_inst, int stage, int w)
@@ -128,6 +153,11 @@ struct cfnmpc_batch
     void (*kernel_prep_u)(const CfParams, const CfBatchView) = nullptr;
     void (*kernel_fb_u)(const CfParams, const CfBatchView) = nullptr;
     bool two_kernels = true;
+    // partial condensing (option "qp_cond_N"): 0 = off (every block holds one stage, the reference's own configuration)
+    int cond_N = 0, pc_bs = 0, pc_wpb = 4, pc_minb = 2, grid_pc = 0, pc_regs = 0, pc_blocks_per_sm = 0;
+    size_t smem_pc = 0;
+    CfPcBlocks pcb;
+    void (*kernel_pc)(const CfParams, const CfBatchView, const CfPcBlocks) = nullptr;
     int grid_prep_u = 0, prep_minb = 3;
     int grid_fb = 0, fb_minb = 4, fb_regs = 0, fb_blocks_per_sm = 0;
     cudaEvent_t ev_mid = nullptr;     // between the two launches of a two-kernel step
@@ -452,9 +482,63 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
     return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_set: unknown field '") + field + "'");
 }
 
+// Select the launch shape of the condensed feedback kernel for block size `bs`: <warps per block, blocks per SM>
+template <int BS>
+static void (*pc_kernel_for(int wpb, int minb))(const CfParams, const CfBatchView, const CfPcBlocks)
+{
+    switch (wpb * 100 + minb) {
+    case 402: return cf_pcond_kernel<4, 2, BS>;
+    case 205: return cf_pcond_kernel<2, 5, BS>;
+    case 303: return cf_pcond_kernel<3, 3, BS>;
+    default: return nullptr;
+    }
+}
+
+// Partial condensing to N2 stages (the reference's qp_cond_N, ocp_qp_partial_condensing.c:235-258): 0 or >= N switches it
+// off.  Block sizes up to 3 stages are implemented (one row of the condensed stage per lane: 4*3 + 13 + 1 = 26 <= 32).
+static int set_cond_N(cfnmpc_batch *h, int N2)
+{
+    if (N2 <= 0 || N2 >= h->N) { h->cond_N = 0; return CFNMPC_OK; }
+    const CfPcBlocks b = cf_pc_blocks(h->N, N2);
+    const int bs = b.n_big ? b.bs0 + 1 : b.bs0;
+    if (bs > 3) return fail(CFNMPC_EINVAL, "qp_cond_N: blocks of more than 3 stages are not implemented (need qp_cond_N >= ceil(N / 3))");
+    CK(cudaSetDevice(h->device));
+    if (const char *e = getenv("CFNMPC_PC_WARPS_PER_BLOCK")) h->pc_wpb = atoi(e);
+    if (const char *e = getenv("CFNMPC_PC_MIN_BLOCKS")) h->pc_minb = atoi(e);
+    auto k = bs == 3 ? pc_kernel_for<3>(h->pc_wpb, h->pc_minb) : pc_kernel_for<2>(h->pc_wpb, h->pc_minb);
+    if (!k) { h->pc_wpb = 4; h->pc_minb = 2; k = bs == 3 ? pc_kernel_for<3>(4, 2) : pc_kernel_for<2>(4, 2); }
+    const size_t smem = (size_t) h->pc_wpb * (bs == 3 ? (int) CfPcWarpT<3>::SM_DOUBLES : (int) CfPcWarpT<2>::SM_DOUBLES) * sizeof(double);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k));
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, h->pc_wpb * 32, smem));
+    if (bps < 1) return fail(CFNMPC_ECUDA, "the condensed feedback kernel does not fit on an SM");
+    const long want = (long) h->sm_count * bps, need = ((long) h->B + h->pc_wpb - 1) / h->pc_wpb;
+    const int grid = (int) (want < need ? want : need);
+    // scratch: every resident warp needs a slot of (N2 + 1) condensed stage blocks
+    const long stride_pc = bs == 3 ? cf_pc_scratch_doubles<3>(N2) : cf_pc_scratch_doubles<2>(N2);
+    const long stride = stride_pc > h->bv.scratch_stride ? stride_pc : h->bv.scratch_stride;
+    const int slots = grid * h->pc_wpb > h->n_slots ? grid * h->pc_wpb : h->n_slots;
+    if (stride != h->bv.scratch_stride || slots != h->n_slots) {
+        CK(cudaStreamSynchronize(h->stream));
+        double *ns = nullptr;
+        CK(cudaMalloc(&ns, (size_t) slots * stride * 8));
+        CK(cudaMemsetAsync(ns, 0, (size_t) slots * stride * 8, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_scratch);
+        h->d_scratch = ns; h->bv.scratch = ns; h->bv.scratch_stride = stride; h->n_slots = slots;
+    }
+    h->kernel_pc = k; h->smem_pc = smem; h->grid_pc = grid; h->pc_regs = fa.numRegs; h->pc_blocks_per_sm = bps;
+    h->pcb = b; h->pc_bs = bs; h->cond_N = N2;
+    h->prepared = false;
+    return CFNMPC_OK;
+}
+
 extern "C" int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int value)
 {
     if (!h || !option) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set_option: null argument");
+    if (!strcmp(option, "qp_cond_N")) return set_cond_N(h, value);
     if (!strcmp(option, "lin_res_check")) h->P.lin_res_check = value != 0;
     else if (!strcmp(option, "two_kernels")) h->two_kernels = value != 0;
     else if (!strcmp(option, "max_ipm_iter")) h->P.max_ipm_iter = (value > 0 && value < CF_ITER_MAX) ? value : CF_ITER_MAX;
@@ -482,12 +566,22 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
     if (!h) return fail(CFNMPC_EINVAL, "null handle");
     if (n_rti < 1) return fail(CFNMPC_EINVAL, "cfnmpc_batch_solve: n_rti must be >= 1");
     CK(cudaSetDevice(h->device));
-    if (h->two_kernels && !h->vdt && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;   // no room: the fused kernel
+    if (h->cond_N) { if (int rc = ensure_prep_store(h)) return rc; }   // the condensed feedback needs the prepared linearisations
+    else if (h->two_kernels && !h->vdt && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;   // no room: the fused kernel
     h->mid_valid = false;
     CK(cudaEventRecord(h->ev0, h->stream));
     for (int r = 0; r < n_rti; r++) {
         CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
-        if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+        if (h->cond_N) {
+            // preparation (uniform or per-interval grid), then the feedback on the partially condensed QP
+            if (h->vdt) h->kernel_prep<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+            else h->kernel_prep_u<<<h->grid_prep_u, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+            if (r == n_rti - 1) { CK(cudaEventRecord(h->ev_mid, h->stream)); h->mid_valid = n_rti == 1; }
+            h->kernel_pc<<<h->grid_pc, h->pc_wpb * 32, h->smem_pc, h->stream>>>(h->P, h->bv, h->pcb);
+            h->launches++;
+        } else if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
         else if (h->two_kernels) {
             h->kernel_prep_u<<<h->grid_prep_u, 128, h->smem_general, h->stream>>>(h->P, h->bv);
             CK(cudaGetLastError());
@@ -547,7 +641,8 @@ extern "C" int cfnmpc_batch_feedback(cfnmpc_batch *h)
     h->mid_valid = false;
     CK(cudaEventRecord(h->ev0, h->stream));
     CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
-    h->kernel_fb<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+    if (h->cond_N) h->kernel_pc<<<h->grid_pc, h->pc_wpb * 32, h->smem_pc, h->stream>>>(h->P, h->bv, h->pcb);
+    else h->kernel_fb<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
     CK(cudaGetLastError());
     h->launches++;
     CK(cudaEventRecord(h->ev1, h->stream));
@@ -568,7 +663,8 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
     if (n_chunks > CF_MAX_CHUNKS) n_chunks = CF_MAX_CHUNKS;
     if (n_chunks > h->B) n_chunks = h->B;
     CK(cudaSetDevice(h->device));
-    if (h->two_kernels && !h->vdt && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;
+    if (h->cond_N) { if (int rc = ensure_prep_store(h)) return rc; }
+    else if (h->two_kernels && !h->vdt && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;
     h->mid_valid = false;
     if (!h->copy_stream) {
         CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -601,7 +697,16 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
     // the copies are enqueued BEFORE the launch: a synchronous launch (profilers, CUDA_LAUNCH_BLOCKING) cannot dead-lock
     CfBatchView bv = h->bv;
     bv.ready = h->d_ready;
-    if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, bv);
+    if (h->cond_N) {
+        bv.prep = h->d_prep;
+        if (h->vdt) h->kernel_prep<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, bv);
+        else h->kernel_prep_u<<<h->grid_prep_u, 128, h->smem_general, h->stream>>>(h->P, bv);
+        CK(cudaGetLastError());
+        CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+        bv.ready = nullptr;
+        h->kernel_pc<<<h->grid_pc, h->pc_wpb * 32, h->smem_pc, h->stream>>>(h->P, bv, h->pcb);
+        h->launches++;
+    } else if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, bv);
     else if (h->two_kernels) {
         // the preparation follows the upload front; by the time it has finished every input is in place
         bv.prep = h->d_prep;
@@ -870,7 +975,13 @@ extern "C" int cfnmpc_batch_info(cfnmpc_batch *h, const char *what, long long *v
     else if (!strcmp(what, "smem_per_block")) *value = (long long) h->smem;
     else if (!strcmp(what, "scratch_bytes")) *value = (long long) h->n_slots * h->bv.scratch_stride * 8;
     else if (!strcmp(what, "launches")) *value = h->launches;
-    else if (!strcmp(what, "two_kernels")) *value = h->two_kernels && !h->vdt;
+    else if (!strcmp(what, "two_kernels")) *value = h->cond_N ? 1 : (h->two_kernels && !h->vdt);
+    else if (!strcmp(what, "qp_cond_N")) *value = h->cond_N ? h->cond_N : h->N;
+    else if (!strcmp(what, "pcond_block_size")) *value = h->cond_N ? h->pc_bs : 1;
+    else if (!strcmp(what, "pcond_regs_per_thread")) *value = h->pc_regs;
+    else if (!strcmp(what, "pcond_blocks_per_sm")) *value = h->pc_blocks_per_sm;
+    else if (!strcmp(what, "pcond_warps_per_block")) *value = h->pc_wpb;
+    else if (!strcmp(what, "pcond_grid")) *value = h->grid_pc;
     else if (!strcmp(what, "feedback_regs_per_thread")) *value = h->fb_regs;
     else if (!strcmp(what, "feedback_blocks_per_sm")) *value = h->fb_blocks_per_sm;
     else if (!strcmp(what, "feedback_grid")) *value = h->grid_fb;

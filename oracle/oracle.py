@@ -60,6 +60,11 @@ class Port:
         L.cfo_linearize.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams)] + [_dp] * 10
         L.cfo_batch.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), ctypes.c_int, ctypes.c_int,
                                 _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+        L.cfo_batch_pcond.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+        L.cfo_rti_pcond.restype = ctypes.c_int
+        L.cfo_rti_pcond.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), ctypes.c_int, _dp, _dp, _dp, _dp, _dp,
+                                    ctypes.POINTER(CfoInfo)]
         L.cfo_erk4.argtypes = [_dp, _dp, ctypes.c_double, _dp, _dp, _dp]
         L.cfo_sim.argtypes = [_dp, _dp, ctypes.c_double, ctypes.c_int, _dp]
         L.cfo_ode.argtypes = [_dp, _dp, _dp]
@@ -146,12 +151,24 @@ class Port:
                               ctypes.byref(info), _P(dux), _P(dpi))
         return (st, info, dux, dpi) if want_step else (st, info)
 
-    def batch(self, N, Ts, x0, yref, yref_e, x, u, n_rti=1, params=None):
+    def batch(self, N, Ts, x0, yref, yref_e, x, u, n_rti=1, params=None, cond_N=0):
+        """cond_N: partial condensing to cond_N stages before the interior-point solve (the reference's qp_cond_N)."""
         n = x0.shape[0]
         status, qp_iter = np.zeros(n, np.int32), np.zeros(n, np.int32)
-        self.lib.cfo_batch(N, Ts, ctypes.byref(params) if params else None, n_rti, n, _P(x0), _P(yref), _P(yref_e),
-                           _P(x), _P(u), _I(status), _I(qp_iter))
+        if cond_N and cond_N < N:
+            self.lib.cfo_batch_pcond(N, Ts, ctypes.byref(params) if params else None, cond_N, n_rti, n, _P(x0), _P(yref),
+                                     _P(yref_e), _P(x), _P(u), _I(status), _I(qp_iter))
+        else:
+            self.lib.cfo_batch(N, Ts, ctypes.byref(params) if params else None, n_rti, n, _P(x0), _P(yref), _P(yref_e),
+                               _P(x), _P(u), _I(status), _I(qp_iter))
         return status, qp_iter
+
+    def rti_pcond(self, N, Ts, cond_N, x0, yref, yref_e, x, u, params=None):
+        info = CfoInfo()
+        a = [np.ascontiguousarray(v, float) for v in (x0, yref, yref_e)]
+        st = self.lib.cfo_rti_pcond(N, Ts, ctypes.byref(params) if params else None, cond_N, *[_P(v) for v in a], _P(x), _P(u),
+                                    ctypes.byref(info))
+        return st, info
 
 
 def ref_available():

@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "libcfemu.so")
 
 
 def build(force=False):
-    deps = [os.path.join(HERE, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("cf_simt.h", "cf_model.h", "cf_rti_warp.h")]
+    deps = [os.path.join(HERE, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("cf_simt.h", "cf_model.h", "cf_rti_warp.h", "cf_pcond_warp.h", "cf_spec_generated.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, os.path.join(HERE, "emu.cpp"),

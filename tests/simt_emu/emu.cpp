@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "cf_rti_warp.h"
+#include "cf_pcond_warp.h"
 
 namespace cfemu {
 struct Warp
@@ -341,6 +342,89 @@ extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int
                     if (x0_fb) j.bv.x0 = x0_fb;
                     cfemu::run_warp(job_fn_t<CF_PH_FEEDBACK, true>, &j);
                 }
+            }
+        });
+    for (auto &t : th) t.join();
+    return 0;
+}
+
+
+// Partially condensed feedback (cf_pcond_warp.h): preparation phase of the general warp program, then -- scratch slot
+// and shared memory poisoned in between -- the condensed feedback with block size BS = ceil(N / N2).
+struct PcJob
+{
+    const CfParams *P;
+    CfBatchView bv;
+    CfPcBlocks blk;
+    int inst;
+    double *slot;
+    double *sm;
+};
+template <int BS>
+static void pc_job_fn(void *a)
+{
+    PcJob *j = (PcJob *) a;
+    cf_warp_init_smem(j->sm + CfPcWarpT<BS>::SM_BAR - CF_SM_BAR);   // the two mbarriers of the condensed layout
+    unsigned par = 0;
+    cf_pcond_instance<BS>(j->P, j->bv, j->blk, j->inst, j->slot, j->sm, par);
+}
+extern "C" int cfemu_rti_pcond(int B, int N, double Ts, int N2, const double *params, const double *x0, const double *yref,
+                               const double *yref_e, double *x, double *u, int *status, int *qp_iter, int *qp_status, int *flags,
+                               double *res, int nthreads, const double *const *per_inst)
+{
+    if (N2 < 1 || N2 >= N) return -1;
+    const CfPcBlocks blk = cf_pc_blocks(N, N2);
+    const int BS = blk.n_big ? blk.bs0 + 1 : blk.bs0;
+    if (BS != 2 && BS != 3) return -2;
+    CfParams P;
+    static const double Q[13] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
+    for (int i = 0; i < 13; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
+    for (int i = 0; i < 4; i++) { P.Wdiag[13 + i] = 0.06; P.lbu[i] = 0; P.ubu[i] = 22; }
+    if (params) {
+        memcpy(P.Wdiag, params, 17 * 8); memcpy(P.WNdiag, params + 17, 13 * 8);
+        memcpy(P.lbu, params + 30, 4 * 8); memcpy(P.ubu, params + 34, 4 * 8);
+    }
+    memcpy(P.lbu0, P.lbu, sizeof P.lbu); memcpy(P.ubu0, P.ubu, sizeof P.ubu);
+    P.Ts = Ts; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = 0; P.pad_ = 0;
+    const long stride0 = cf_scratch_layout(N).total, pstride = cf_prep_stride(N);
+    const long stride1 = BS == 3 ? cf_pc_scratch_doubles<3>(N2) : cf_pc_scratch_doubles<2>(N2);
+    const long stride = stride0 > stride1 ? stride0 : stride1;
+    const int smd = BS == 3 ? (int) CfPcWarpT<3>::SM_DOUBLES : (int) CfPcWarpT<2>::SM_DOUBLES;
+    const int smn = smd > CF_SM_DOUBLES ? smd : CF_SM_DOUBLES;
+    std::vector<double> dtv(N, Ts);
+    std::vector<double> prep((size_t) B * pstride + 2, std::nan(""));
+    CfBatchView bv;
+    memset(&bv, 0, sizeof bv);
+    bv.B = B; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
+    bv.qp_iter = qp_iter; bv.qp_status = qp_status; bv.flags = flags; bv.res = res; bv.scratch_stride = stride;
+    bv.dts = dtv.data();
+    bv.prep = (double *) ((((uintptr_t) prep.data()) + 15) & ~(uintptr_t) 15);
+    bv.prep_stride = pstride;
+    bv.bnd_stage = g_bnd_stage;
+    if (per_inst) {
+        bv.W_b = per_inst[0]; bv.WN_b = per_inst[1]; bv.lbu_b = per_inst[2]; bv.ubu_b = per_inst[3];
+        bv.lbu0_b = per_inst[4]; bv.ubu0_b = per_inst[5];
+    }
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&]() {
+            std::vector<double> slot(stride + 2, 0.0), sm(smn + 2, 0.0);
+            double *slot_a = (double *) ((((uintptr_t) slot.data()) + 15) & ~(uintptr_t) 15), *sm_a = (double *) ((((uintptr_t) sm.data()) + 15) & ~(uintptr_t) 15);
+            auto poison = [&]() {
+                for (long q = 0; q < stride; q++) slot_a[q] = std::nan("");
+                for (int q = 0; q < smn; q++) sm_a[q] = std::nan("");
+            };
+            for (;;) {
+                int i = next.fetch_add(1);
+                if (i >= B) break;
+                poison();
+                Job j{&P, bv, i, slot_a, sm_a};
+                cfemu::run_warp(job_fn_t<CF_PH_PREPARATION, true>, &j);
+                poison();
+                PcJob pj{&P, bv, blk, i, slot_a, sm_a};
+                cfemu::run_warp(BS == 3 ? pc_job_fn<3> : pc_job_fn<2>, &pj);
             }
         });
     for (auto &t : th) t.join();
