@@ -161,8 +161,13 @@ def run_reference(args):
     line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=(sample / v * 1e3) if v else None, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic",
-                config=dict(workload=f"{args.workload} regulation OCPs, N={args.horizon}, nx=13, nu=4, bounded sample of {sample} instances per step",
-                            batch_per_step=sample, horizon=args.horizon, host_threads=cores),
+                config=dict(workload=f"BASELINE configs[{2 if args.workload == 'helix' else 1}]: batch={args.batch} {args.workload} "
+                                     f"OCPs per GPU, N={args.horizon}, nx=13, nu=4, random feasible x0, 1 RTI step per step",
+                            sample=f"bounded sample of {sample} seeded instances of that workload per step (CPU throughput per solve does "
+                                   f"not depend on the batch size)", batch_per_step=sample, horizon=args.horizon, host_threads=cores,
+                            qp_cond_N=args.horizon),
+                value_best_config=(dict(cb["with_partial_condensing"], note="the same reference solver with real partial condensing "
+                                        "(not its own configuration, which is qp_cond_N = N)") if "with_partial_condensing" in cb else None),
                 cpu_baseline=cb, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
@@ -251,16 +256,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, per_step=None):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = s.info("launches")
-        e0.record(stream)
-        for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        l0 = s.info("launches") if s is not None else 0
+        ev[0].record(stream)
+        for i in range(steps):
             fn()
-        e1.record(stream)
+            ev[i + 1].record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = ev[0].elapsed_time(ev[steps])
+        if per_step is not None:
+            per_step.extend(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -271,7 +278,8 @@ def run_ours(args):
         step_device()
     # kernel-only time of the dominant kernel, CUDA events on its own stream, averaged over the timed steps
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_total, launches = timed(step_device, args.steps)
+    step_ms = []
+    ms_total, launches = timed(step_device, args.steps, step_ms)
     kern_ms, phase_ms = [], []
     for _ in range(min(args.steps, 5)):
         s.set("x", d_in["x_init"]).set("u", d_in["u_init"])
@@ -288,6 +296,88 @@ def run_ours(args):
     ms_tick, _ = timed(step_tick, args.steps)
     # the driver built the same references: same first controls as the host-fed path (motors = trunc(u0))
     tick_consistent = bool((motors_host.numpy() == u0_e2e.numpy().astype(np.int32)).all())
+
+    # the same device-timed step with the reference's per-iteration linear-system residual checks switched on
+    # (x_ocp_qp_ipm.c:2029-2059,2311-2318: what feeds its LQ / iterative-refinement nets; flags only, same results)
+    ms_chk = None
+    if not args.qp_cond_N:
+        s.set_option("lin_res_check", 1)
+        step_device()
+        ms_chk, _ = timed(step_device, max(2, args.steps // 2))
+        ms_chk /= max(2, args.steps // 2)
+        flags_chk = int((s.get("flags") & 3 != 0).sum())
+        s.set_option("lin_res_check", 0)
+
+    # host -> device rate of this rank's pinned input upload, all ranks copying at the same time (names the e2e limiter)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record(stream)
+    for _ in range(3):
+        d_in["yref"].copy_(pin["yref"], non_blocking=True)
+    h1.record(stream)
+    barrier()
+    h2d_gbs = 3 * pin["yref"].numel() * 8 / (h0.elapsed_time(h1) * 1e-3) / 1e9
+    if world > 1:
+        t = torch.tensor([h2d_gbs], dtype=torch.float64, device=dev)
+        tl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(tl, t)
+        h2d_all = [float(v.item()) for v in tl]
+    else:
+        h2d_all = [h2d_gbs]
+
+    # N > 1: the gathered first controls must contain every rank's own results, and a sample of each rank's solves is
+    # checked against the CPU oracle (checker only: outside every timed region)
+    multi = None
+    if world > 1:
+        step_device()
+        s.get("u", 0, out=u0_dev)
+        allu = sharding.gather_u0(u0_dev, world * B)
+        own_ok = bool(torch.equal(allu[rank * B:(rank + 1) * B], u0_dev))
+        from oracle.oracle import Port
+        idx = np.arange(0, B, B // 16)[:16]
+        xo, uo = np.ascontiguousarray(w["x_init"][idx]), np.ascontiguousarray(w["u_init"][idx])
+        Port().batch(N, TS, np.ascontiguousarray(w["x0"][idx]), np.ascontiguousarray(w["yref"][idx]),
+                     np.ascontiguousarray(w["yref_e"][idx]), xo, uo, cond_N=args.qp_cond_N)
+        ug = s.get("u_all")[idx]
+        err = float((np.abs(ug - uo) / (1 + np.abs(uo))).max())
+        t = torch.tensor([0.0 if own_ok else 1.0, err], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        multi = dict(gathered_u0_contains_every_rank=bool(t[0].item() == 0.0), oracle_checked_per_rank=16,
+                     max_rel_err_vs_oracle=float(t[1].item()), tolerance=1e-6)
+        if not multi["gathered_u0_contains_every_rank"] or multi["max_rel_err_vs_oracle"] > 1e-6:
+            raise SystemExit(f"bench.py: multi-GPU result check failed: {multi}")
+
+    # BASELINE configs[3] (262,144 helix OCPs over 8 GPUs = 32,768 per GPU, NCCL all-gather of u0): measured inside the
+    # multi-GPU run, with and without the gather
+    config4 = None
+    if world > 1 and not args.no_config4:
+        B4 = 262144 // 8
+        w4 = make_workload("helix", B4, N, args.seed + 1 + rank)
+        s4 = cf.BatchSolver(B4, N, TS, device=local)
+        s4.set_stream(stream.cuda_stream)
+        if args.qp_cond_N:
+            s4.set_option("qp_cond_N", args.qp_cond_N)
+        d4 = {k: torch.from_numpy(w4[k]).to(dev) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
+        s4.set("x0", d4["x0"]).set("yref", d4["yref"]).set("yref_e", d4["yref_e"])
+        u4 = torch.empty(B4, 4, dtype=torch.float64, device=dev)
+
+        def step4(gather):
+            s4.set("x", d4["x_init"]).set("u", d4["u_init"])
+            s4.solve(1)
+            s4.get("u", 0, out=u4)
+            if gather:
+                sharding.gather_u0(u4, world * B4)
+        for _ in range(3):
+            step4(True)
+        ms_g, _ = timed(lambda: step4(True), args.steps)
+        ms_n, _ = timed(lambda: step4(False), args.steps)
+        ok4 = torch.tensor([int((s4.get("status") == 0).sum())], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok4)
+        config4 = dict(workload=f"BASELINE configs[3]: batch={world * B4} helix OCPs over {world} GPUs ({B4} per GPU), NCCL all-gather of u0",
+                       value_with_gather=world * B4 / (ms_g / args.steps * 1e-3), value_without_gather=world * B4 / (ms_n / args.steps * 1e-3),
+                       unit=UNIT, ms_per_step_with_gather=ms_g / args.steps, ms_per_step_without_gather=ms_n / args.steps,
+                       status_ok=int(ok4.item()), of=world * B4)
+        s4.close()
 
     # sanity: the timed work really solved the batch
     status = s.get("status")
@@ -316,11 +406,23 @@ def run_ours(args):
                 traffic = json.load(open(tp)).get(f"bytes_per_launch_B{B}_N{N}")
             except Exception:
                 traffic = None
+        it_mean = float(iters.mean())
+        # secondary figure of SURVEY 8(d): fp64 FLOPs of one solve, N (13.5k + n_ipm (9.5k + 1.5 * 1.5k + 3 * 1.5k)),
+        # against the measured fp64 FMA peak of this device (cfnmpc_measure_fp64_peak)
+        flop_per_solve = N * (13500.0 + it_mean * (9500.0 + 1.5 * 1500.0 + 3 * 1500.0))
+        fp64_peak = cf.measure_fp64_peak(local)
+        tf = B * flop_per_solve / (k_ms * 1e-3) / 1e12
+        pc = bool(args.qp_cond_N)
+        kname = (f"cf_pcond_kernel<BS={s.info('pcond_block_size')}> (dominant; qp_cond_N={args.qp_cond_N}) after cf_rti_kernel<4,3,PREPARATION>" if pc else
+                 "cf_rti_kernel<4,4,FEEDBACK> (dominant) after cf_rti_kernel<4,3,PREPARATION>" if two else "cf_rti_kernel<4,3> (fused)")
         roofline = dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                        traffic=traffic, kernel_ms=k_ms, peak_source=how,
-                        kernel="cf_rti_kernel<4,4,FEEDBACK> (dominant) after cf_rti_kernel<4,3,PREPARATION>" if two else "cf_rti_kernel<4,3> (fused)",
+                        traffic=None if pc else traffic, kernel_ms=k_ms, dominant_kernel_ms=fb_ms if two else k_ms, peak_source=how,
+                        kernel=kname,
                         kernels_ms=dict(preparation=prep_ms, feedback=fb_ms) if two else None,
                         alg_bytes_per_solve=alg_bytes(N),
+                        achieved_dominant_kernel=B * alg_bytes(N) / ((fb_ms if two else k_ms) * 1e-3) / 1e9,
+                        flops=dict(mflop_per_solve=flop_per_solve / 1e6, achieved_tflops=tf, peak_tflops=fp64_peak,
+                                   frac=tf / fp64_peak if fp64_peak else None, peak_source="measured: cfnmpc_measure_fp64_peak (DFMA stream)"),
                         note="algorithmic bytes = x0 + yref + iterate in/out (SURVEY 8d); real traffic is dominated by factor/linearisation spill")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -332,7 +434,7 @@ def run_ours(args):
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                     config=dict(workload=f"BASELINE configs[{2 if args.workload == 'helix' else 1}]: batch={B} {args.workload} "
                                          f"OCPs per GPU, N={N}, nx=13, nu=4, random feasible x0, 1 RTI step per step",
-                                batch_per_gpu=B, global_batch=world * B, horizon=N, parallelism=f"dp{world} (independent shards"
+                                batch_per_gpu=B, global_batch=world * B, horizon=N, qp_cond_N=args.qp_cond_N or N, parallelism=f"dp{world} (independent shards"
                                 + (", NCCL all-gather of u0)" if world > 1 else ")"),
                                 l2="inputs larger than L2 (iterate+yref 900 MB, scratch %d MB per GPU)" % (s.info("scratch_bytes") >> 20),
                                 occupancy=(dict(kernels="preparation + feedback", warps_per_sm=s.info("feedback_blocks_per_sm") * 4,
@@ -349,6 +451,16 @@ def run_ours(args):
                                          consistent_with_e2e=tick_consistent,
                                          note="cfnmpc_batch_tick: reference window from (policy, set-point | trajectory row) on the device, "
                                               "RTI step, motor/twist commands; only x0 goes up"),
+                    ms_per_step_best=float(np.min(step_ms)), ms_per_step_median=float(np.median(step_ms)),
+                    value_best=world * B / (float(np.min(step_ms)) * 1e-3) if world == 1 else None,
+                    value_median=world * B / (float(np.median(step_ms)) * 1e-3) if world == 1 else None,
+                    value_with_lin_res_check=(dict(value=world * B / (ms_chk * 1e-3), unit=UNIT, ms_per_step=ms_chk, flagged_instances=flags_chk,
+                                                   note="same step with the reference's linear-system residual checks evaluated every "
+                                                        "IPM iteration (option lin_res_check); default off, always-on detection = status / "
+                                                        "qp_status / BAD_PIVOT / NONFINITE flags") if ms_chk else None),
+                    h2d_gbs_per_rank=dict(min=min(h2d_all), mean=float(np.mean(h2d_all)), max=max(h2d_all),
+                                          note="pinned host -> device copy of this rank's yref (%.0f MB), all ranks at once" % (pin["yref"].numel() * 8 / 1e6)),
+                    multi_gpu_check=multi, config4=config4,
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                     solved=dict(status_ok=ok, of=world * B, ipm_iter_mean=float(iters.mean()), ipm_iter_max=int(iters.max())))
         print(json.dumps(line))
@@ -369,6 +481,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--ref-sample", type=int, default=0, help="instances per CPU step (default: scaled to the core count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE configs[3] record of a multi-GPU run")
     ap.add_argument("--qp-cond-N", type=int, default=0, help="partial condensing to this many stages (0 = the reference's configuration, qp_cond_N = N)")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks of the overlapped host-to-device upload in the e2e path")
     args = ap.parse_args()

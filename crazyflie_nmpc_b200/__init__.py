@@ -70,6 +70,21 @@ def lib():
         L.cfnmpc_sim_solve.argtypes = [vp]
         L.cfnmpc_sim_get.argtypes = [vp, cp, vp, ci]
         L.cfnmpc_sim_launches.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
+        L.cfnmpc_multi_create.argtypes = [ci, ci, cd, ci, ctypes.POINTER(ci), ctypes.POINTER(vp)]
+        L.cfnmpc_multi_destroy.argtypes = [vp]
+        L.cfnmpc_multi_num_shards.argtypes = [vp]
+        L.cfnmpc_multi_shard.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.cfnmpc_multi_set.argtypes = [vp, cp, vp]
+        L.cfnmpc_multi_set_option.argtypes = [vp, cp, ci]
+        L.cfnmpc_multi_set_trajectory.argtypes = [vp, vp, ci]
+        L.cfnmpc_multi_solve.argtypes = [vp, ci]
+        L.cfnmpc_multi_solve_from_host.argtypes = [vp, vp, vp, vp, ci]
+        L.cfnmpc_multi_tick.argtypes = [vp, ci]
+        L.cfnmpc_multi_sync.argtypes = [vp]
+        L.cfnmpc_multi_get.argtypes = [vp, cp, ci, vp]
+        L.cfnmpc_multi_last_solve_ms.argtypes = [vp, ctypes.POINTER(cd)]
+        L.cfnmpc_multi_last_error.restype = cp
+        L.cfnmpc_measure_fp64_peak.argtypes = [ci, ctypes.POINTER(cd)]
         L.cfnmpc_last_error.restype = cp
         L.cfnmpc_version.restype = cp
         _lib = L
@@ -89,6 +104,13 @@ def _ptr(a):
         return a.data_ptr(), 1 if a.is_cuda else 0, a
     a = np.ascontiguousarray(a)
     return a.ctypes.data, 0, a
+
+
+def measure_fp64_peak(device=0):
+    """Measured fp64 FMA throughput of the device in TFLOP/s (roofline denominator of bench.py)."""
+    v = ctypes.c_double()
+    _check(lib().cfnmpc_measure_fp64_peak(int(device), ctypes.byref(v)))
+    return v.value
 
 
 class BatchSolver:
@@ -369,4 +391,85 @@ class SimBatch:
     def launches(self):
         v = ctypes.c_longlong()
         _check(lib().cfnmpc_sim_launches(self._h, ctypes.byref(v)))
+        return v.value
+
+
+class MultiBatchSolver:
+    """B instances sharded over several GPUs of one node behind one handle (mirror of cfnmpc_multi_* in include/cfnmpc.h):
+    contiguous shards, one host thread and stream per device, no exchange between shards.  Host (numpy) arrays only."""
+    _INT = ("status", "qp_iter", "qp_status", "flags", "policy", "traj_iter", "motors")
+
+    def __init__(self, batch, N=50, Ts=0.015, devices=(0,)):
+        self._h = ctypes.c_void_p()
+        self.B, self.N = int(batch), int(N)
+        devs = (ctypes.c_int * len(devices))(*devices)
+        self._check(lib().cfnmpc_multi_create(self.B, self.N, float(Ts), len(devices), devs, ctypes.byref(self._h)))
+
+    @staticmethod
+    def _check(rc):
+        if rc != 0:
+            raise CfnmpcError(f"cfnmpc_multi error {rc}: {lib().cfnmpc_multi_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().cfnmpc_multi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shards(self):
+        out = []
+        for i in range(lib().cfnmpc_multi_num_shards(self._h)):
+            d, f, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            self._check(lib().cfnmpc_multi_shard(self._h, i, None, ctypes.byref(d), ctypes.byref(f), ctypes.byref(c)))
+            out.append((d.value, f.value, c.value))
+        return out
+
+    def set(self, field, a):
+        a = np.ascontiguousarray(a, dtype=np.int32 if field in self._INT else np.float64)
+        self._check(lib().cfnmpc_multi_set(self._h, field.encode(), ctypes.c_void_p(a.ctypes.data)))
+        return self
+
+    def set_option(self, option, value):
+        self._check(lib().cfnmpc_multi_set_option(self._h, option.encode(), int(value)))
+        return self
+
+    def set_problem(self, w):
+        for k, f in (("x0", "x0"), ("yref", "yref"), ("yref_e", "yref_e"), ("x_init", "x"), ("u_init", "u")):
+            self.set(f, w[k])
+        return self
+
+    def solve(self, n_rti=1):
+        self._check(lib().cfnmpc_multi_solve(self._h, int(n_rti)))
+        return self
+
+    def solve_from_host(self, x0, yref, yref_e, n_chunks=4):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (x0, yref, yref_e)]
+        self._check(lib().cfnmpc_multi_solve_from_host(self._h, *[ctypes.c_void_p(v.ctypes.data) for v in a], int(n_chunks)))
+        return self
+
+    def sync(self):
+        self._check(lib().cfnmpc_multi_sync(self._h))
+
+    def get(self, field, stage=0):
+        B, N = self.B, self.N
+        shapes = {"u": (B, NU), "x": (B, NX), "u_all": (B, N, NU), "x_all": (B, N + 1, NX), "status": (B,), "qp_iter": (B,),
+                  "qp_status": (B,), "flags": (B,), "res": (B, 4), "motors": (B, NU), "euler": (B, 3), "twist": (B, 4)}
+        out = np.empty(shapes[field], np.int32 if field in self._INT else np.float64)
+        self._check(lib().cfnmpc_multi_get(self._h, field.encode(), int(stage), ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def last_solve_ms(self):
+        v = ctypes.c_double()
+        self._check(lib().cfnmpc_multi_last_solve_ms(self._h, ctypes.byref(v)))
         return v.value

@@ -9,8 +9,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcfnmpc.so")
-SOURCES = ["cfnmpc_api.cu", "acados_shim.cpp"]
-HEADERS = ["cf_simt.h", "cf_model.h", "cf_spec_generated.h", "cf_rti_warp.h", "cf_loop_kernels.h"]
+SOURCES = ["cfnmpc_api.cu", "acados_shim.cpp", "cfnmpc_multi.cpp"]
+HEADERS = ["cf_simt.h", "cf_model.h", "cf_spec_generated.h", "cf_rti_warp.h", "cf_pcond_warp.h", "cf_loop_kernels.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

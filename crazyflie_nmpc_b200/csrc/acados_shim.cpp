@@ -27,7 +27,8 @@ struct crazyflie_solver_capsule
     int status = 0, qp_iter = 0, qp_status = 0, cond_N = 0;
     int rti_phase = 0;   // 0 preparation + feedback, 1 preparation, 2 feedback (ocp_nlp_sqp_rti.c:189-198)
     std::vector<double> bnd;   // input box per stage, [N][8] = lbu | ubu (ocp_nlp_constraints_bgh.c:653-674)
-    double time_tot = 0.0;
+    double time_tot = 0.0, time_lin = 0.0, time_qp_sol = 0.0;
+    double stat[4] = {0, 0, 0, 0};   // SQP_RTI statistics table: stat_m = 2 rows x stat_n = 2 (qp_status, qp_iter), ocp_nlp_sqp_rti.c:264-265,648-649
     ocp_nlp_plan_t plan;
     ocp_nlp_config config;
     ocp_nlp_dims dims;
@@ -188,13 +189,19 @@ int crazyflie_acados_solve(crazyflie_solver_capsule *c)
     rc |= cfnmpc_batch_get(b, "status", 0, &c->status, 0);
     rc |= cfnmpc_batch_get(b, "qp_iter", 0, &c->qp_iter, 0);
     rc |= cfnmpc_batch_get(b, "qp_status", 0, &c->qp_status, 0);
-    double ms = 0.0;
+    double ms = 0.0, ph[2] = {0.0, 0.0};
     rc |= cfnmpc_batch_last_solve_ms(b, &ms);
+    rc |= cfnmpc_batch_last_phase_ms(b, ph);
     if (rc) {
         fprintf(stderr, "crazyflie_acados_solve: %s\n", cfnmpc_last_error());
         return ACADOS_QP_FAILURE;
     }
     c->time_tot = ms * 1e-3;
+    // device time of the two launches of the step: linearisation (preparation kernel) and QP solution (feedback kernel);
+    // a fused or feedback-only step reports everything as time_qp_sol (mem->time_lin / time_qp_sol, ocp_nlp_sqp_rti.c:1361-1384)
+    c->time_lin = ph[0] * 1e-3;
+    c->time_qp_sol = ph[1] * 1e-3;
+    c->stat[0] = c->qp_status; c->stat[1] = c->qp_iter;
     c->out.total_time = c->time_tot;
     return c->status;
 }
@@ -305,6 +312,21 @@ void ocp_nlp_get(ocp_nlp_config *, ocp_nlp_solver *solver, const char *field, vo
     else if (!strcmp(field, "sqp_iter")) *static_cast<int *>(ret) = 1;
     else if (!strcmp(field, "status")) *static_cast<int *>(ret) = c->status;
     else if (!strcmp(field, "qp_status")) *static_cast<int *>(ret) = c->qp_status;
+    // ocp_nlp_sqp_rti.c:1361-1425
+    else if (!strcmp(field, "time_lin")) *static_cast<double *>(ret) = c->time_lin;
+    else if (!strcmp(field, "time_qp_sol") || !strcmp(field, "time_qp")) *static_cast<double *>(ret) = c->time_qp_sol;
+    else if (!strcmp(field, "time_qp_solver") || !strcmp(field, "time_qp_solver_call")) *static_cast<double *>(ret) = c->time_qp_sol;
+    else if (!strcmp(field, "time_qp_xcond") || !strcmp(field, "time_reg") || !strcmp(field, "time_glob") || !strcmp(field, "time_sim") ||
+             !strcmp(field, "time_sim_ad") || !strcmp(field, "time_sim_la") || !strcmp(field, "time_solution_sensitivities"))
+        *static_cast<double *>(ret) = 0.0;   // not separated from the two kernel times above
+    else if (!strcmp(field, "stat")) *static_cast<double **>(ret) = c->stat;
+    else if (!strcmp(field, "stat_m")) *static_cast<int *>(ret) = 2;
+    else if (!strcmp(field, "stat_n")) *static_cast<int *>(ret) = 2;
+    else if (!strcmp(field, "statistics")) {
+        // n_row = min(stat_m, sqp_iter + 1) = 1 row, column-major [iter | qp_status | qp_iter]
+        double *v = static_cast<double *>(ret);
+        v[0] = 0; v[1] = c->stat[0]; v[2] = c->stat[1];
+    }
 }
 
 // ------------------------------------------------------------------ legacy surface (process globals)

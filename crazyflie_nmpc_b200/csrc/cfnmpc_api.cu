@@ -1077,3 +1077,48 @@ extern "C" int cfnmpc_debug_max_ipm_iter(cfnmpc_batch *h, int max_iter)
     h->P.max_ipm_iter = (max_iter > 0 && max_iter < CF_ITER_MAX) ? max_iter : CF_ITER_MAX;
     return CFNMPC_OK;
 }
+
+// ------------------------------------------------------------------ measured fp64 peak (roofline denominator)
+// Dependent-chain-free DFMA stream: 8 independent accumulators per thread, all SMs filled; FLOP = 2 per FMA.
+__global__ void __launch_bounds__(256) cf_fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = a + threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = fma(v[i], b, a);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += v[i];
+    if (s == 12345.678) out[0] = s;   // never true: keeps the loop alive
+}
+
+extern "C" int cfnmpc_measure_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return fail(CFNMPC_EINVAL, "null argument");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(e0));
+        cf_fp64_peak_kernel<<<blocks, 256>>>(d, iters, 1.0000001, 0.9999999);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * (double) iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return CFNMPC_OK;
+}

@@ -106,7 +106,15 @@ int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field);
  *                   of every instance, then feedback of every instance, the linearisations travelling through a
  *                   per-instance store of 8 * (252 N + 18) bytes -- instead of one fused kernel (0).  Same results bit for
  *                   bit; 2 % faster on B200 (profiles/README.md).  Falls back to the fused kernel when the store cannot
- *                   be allocated.  Also CFNMPC_TWO_KERNELS=0 in the environment. */
+ *                   be allocated.  Also CFNMPC_TWO_KERNELS=0 in the environment.
+ *   "qp_cond_N"     (default 0 = N: the reference's own configuration) partial condensing of the stage-wise QP to this many
+ *                   stages before the interior-point solve = qp_cond_N of the reference (ocp_nlp_solver_opts_set /
+ *                   crazyflie_acados_update_qp_solver_cond_N; acados/acados/ocp_qp/ocp_qp_partial_condensing.c:235-258,
+ *                   457-576 -> external/hpipm/cond/x_part_cond.c:36-54,505-560,658-742).  Blocks of up to 3 stages are
+ *                   implemented (qp_cond_N >= ceil(N/3); coarser values return CFNMPC_EINVAL).  Results equal the
+ *                   reference's at the same qp_cond_N (~1e-13) and its qp_cond_N = N results to the interior-point
+ *                   tolerances.  The step runs as preparation kernel + condensed feedback kernel; "lin_res_check" is not
+ *                   available on this path. */
 int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int value);
 
 /* Enqueue n_rti consecutive RTI steps (preparation + feedback) for every instance,
@@ -217,6 +225,34 @@ int cfnmpc_debug_pass_cycles(cfnmpc_batch *h, unsigned long long *cycles_calls12
 
 const char *cfnmpc_last_error(void);
 const char *cfnmpc_version(void);
+
+/* ------------------------------------------------------------------ several GPUs behind one handle
+ * The batch dimension sharded over the GPUs of one node: shard i owns the contiguous instances
+ * [first_i, first_i + count_i), count = B / n_dev (+1 for the first B mod n_dev), has its own cfnmpc_batch and stream on
+ * devices[i], and every call below runs the shards concurrently, one host thread per device.  There is no exchange
+ * between shards.  All pointers are HOST pointers covering the whole batch ([B][...], instance-major); solver-wide
+ * fields ("W", "lbu", "bounds_stage", "time_steps", ...) are given once and applied to every shard.  A device may be
+ * listed more than once (several shards on one GPU).  For device-resident data use the per-shard handle. */
+typedef struct cfnmpc_multi cfnmpc_multi;
+int cfnmpc_multi_create(int batch, int N, double Ts, int n_dev, const int *devices, cfnmpc_multi **out);
+int cfnmpc_multi_destroy(cfnmpc_multi *m);
+int cfnmpc_multi_num_shards(cfnmpc_multi *m);
+/* the single-device handle, device, first instance and instance count of shard i (any output may be NULL) */
+int cfnmpc_multi_shard(cfnmpc_multi *m, int i, cfnmpc_batch **h, int *device, int *first, int *count);
+int cfnmpc_multi_set(cfnmpc_multi *m, const char *field, const void *host_src);   /* fields of cfnmpc_batch_set; returns when copied */
+int cfnmpc_multi_set_option(cfnmpc_multi *m, const char *option, int value);
+int cfnmpc_multi_set_trajectory(cfnmpc_multi *m, const double *table, int n_rows);
+int cfnmpc_multi_solve(cfnmpc_multi *m, int n_rti);                                 /* asynchronous on every device */
+int cfnmpc_multi_solve_from_host(cfnmpc_multi *m, const double *x0, const double *yref, const double *yref_e, int n_chunks);
+int cfnmpc_multi_tick(cfnmpc_multi *m, int motors_from_u1);
+int cfnmpc_multi_sync(cfnmpc_multi *m);
+int cfnmpc_multi_get(cfnmpc_multi *m, const char *field, int stage, void *host_dst);   /* per-instance fields of cfnmpc_batch_get */
+int cfnmpc_multi_last_solve_ms(cfnmpc_multi *m, double *ms);                        /* slowest shard */
+const char *cfnmpc_multi_last_error(void);
+
+/* Measured fp64 FMA throughput of the device in TFLOP/s (a dependency-free DFMA stream on every SM): the denominator of
+ * the secondary, FLOP-based roofline figure of bench.py.  No reference counterpart. */
+int cfnmpc_measure_fp64_peak(int device, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 w = wl.hover_batch(B, N)
 with cf.BatchSolver(B, N, 0.015) as s:
+    s.set_option("qp_cond_N", int(os.environ.get("PCOND", "0")))
     s.set_problem(w).solve(1)
     s.debug_pass_cycles(read=False)
     s.set_problem(w).solve(1)

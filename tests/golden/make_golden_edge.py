@@ -7,6 +7,9 @@
                     statistics that show where the reference's safety nets fired: LQ re-factorisation
                     (x_ocp_qp_ipm.c:2029-2059, stat column 11) and corrector iterative refinement (:2311-2318, column 13)
 
+* pcond_{17,25}_*   8 helix instances (seed 21) solved by the reference with qp_cond_N = 17 / 25 (partial condensing,
+                    ocp_qp_partial_condensing.c:457-576)
+
 Inputs are regenerated from the seeds by the tests; only the reference's outputs are stored (u of every stage, x of
 stages 1, 4, N).  Needs /root/reference:  python tests/golden/make_golden_edge.py"""
 import os
@@ -68,6 +71,13 @@ def main():
     out["adv_xsel"] = r["x"][:, XSEL]
     print("adversarial: converged", int((r["qp_status"] == 0).sum()), "maxiter", int((r["qp_status"] == 1).sum()),
           "LQ fired", np.nonzero(r["lq"])[0].tolist(), "itref fired", np.nonzero(r["itref"])[0].tolist())
+    # partial condensing: the reference at qp_cond_N = 17 (blocks of 3 and 2 stages) and 25 (blocks of 2)
+    wp = wl.helix_batch(8, N, seed=21)
+    for cn in (17, 25):
+        x, u = wp["x_init"].copy(), wp["u_init"].copy()
+        st, it, _ = ref.batch(N, TS, wp["x0"], wp["yref"], wp["yref_e"], x, u, cond_N=cn)
+        out[f"pcond_{cn}_status"], out[f"pcond_{cn}_qp_iter"], out[f"pcond_{cn}_u"], out[f"pcond_{cn}_xsel"] = st, it, u, x[:, XSEL]
+        print("pcond", cn, "status", np.unique(st).tolist(), "iterations", it.tolist())
     np.savez_compressed(os.path.join(HERE, "edge_golden.npz"), **out)
 
 

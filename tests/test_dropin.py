@@ -123,6 +123,31 @@ def test_capsule_api_through_ctypes(port):
     xo, uo = w["x_init"][0].copy(), w["u_init"][0].copy()
     st, info = port.rti(N, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], xo, uo)
     assert np.abs(x - xo).max() < 1e-8 and np.abs(u - uo).max() < 1e-8 and abs(qi.value - info.qp_iter) <= 1
+    # statistics getters of the SQP_RTI module (ocp_nlp_sqp_rti.c:1361-1425)
+    t_tot, t_lin, t_qp = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    L.ocp_nlp_get(cfg, sol, b"time_tot", ctypes.byref(t_tot))
+    L.ocp_nlp_get(cfg, sol, b"time_lin", ctypes.byref(t_lin))
+    L.ocp_nlp_get(cfg, sol, b"time_qp_sol", ctypes.byref(t_qp))
+    assert t_tot.value > 0 and t_lin.value > 0 and t_qp.value > 0 and t_lin.value + t_qp.value <= t_tot.value * 1.05
+    sm, sn, stat = ctypes.c_int(), ctypes.c_int(), ctypes.POINTER(ctypes.c_double)()
+    L.ocp_nlp_get(cfg, sol, b"stat_m", ctypes.byref(sm))
+    L.ocp_nlp_get(cfg, sol, b"stat_n", ctypes.byref(sn))
+    L.ocp_nlp_get(cfg, sol, b"stat", ctypes.byref(stat))
+    assert (sm.value, sn.value) == (2, 2) and (stat[0], stat[1]) == (0.0, float(qi.value))   # [qp_status, qp_iter]
+    # qp_cond_N through the reference's own setter: partial condensing, same solution to the IPM tolerances
+    L.crazyflie_acados_update_qp_solver_cond_N.argtypes = [vp, ctypes.c_int]
+    assert L.crazyflie_acados_update_qp_solver_cond_N(cap, 7) == 0
+    for k in range(N):
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"u", P(w["u_init"][0, k]))
+    for k in range(N + 1):
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"x", P(w["x_init"][0, k]))
+    assert L.crazyflie_acados_solve(cap) == 0
+    uc = np.zeros((N, 4))
+    for k in range(N):
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"u", P(uc[k]))
+    xp, up = w["x_init"][0].copy(), w["u_init"][0].copy()
+    port.rti_pcond(N, TS, 7, w["x0"][0], w["yref"][0], w["yref_e"][0], xp, up)
+    assert np.abs(uc - up).max() < 1e-8 and np.abs(uc - uo).max() < 1e-5
     L.crazyflie_acados_free(cap)
     L.crazyflie_acados_free_capsule(cap)
 

@@ -16,7 +16,7 @@ while [ $# -gt 0 ]; do
   shift
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "${extra[@]}" \
-  -I "$TMP/include" "$TMP/crazyflie_nmpc_b200/csrc/cfnmpc_api.cu" "$TMP/crazyflie_nmpc_b200/csrc/acados_shim.cpp" \
+  -I "$TMP/include" "$TMP/crazyflie_nmpc_b200/csrc/cfnmpc_api.cu" "$TMP/crazyflie_nmpc_b200/csrc/acados_shim.cpp" "$TMP/crazyflie_nmpc_b200/csrc/cfnmpc_multi.cpp" \
   -o "$ROOT/crazyflie_nmpc_b200/variants/libcfnmpc_$name.so"
 rm -rf "$TMP"
 echo "built variants/libcfnmpc_$name.so"
