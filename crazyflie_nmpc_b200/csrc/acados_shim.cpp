@@ -27,6 +27,8 @@ struct crazyflie_solver_capsule
     int status = 0, qp_iter = 0, qp_status = 0, cond_N = 0;
     int rti_phase = 0;   // 0 preparation + feedback, 1 preparation, 2 feedback (ocp_nlp_sqp_rti.c:189-198)
     std::vector<double> bnd;   // input box per stage, [N][8] = lbu | ubu (ocp_nlp_constraints_bgh.c:653-674)
+    std::vector<double> wst;   // weight diagonals per stage, [N+1][17] (ocp_nlp_cost_ls.c:301-331); uploaded once stages differ
+    bool wst_used = false;
     double time_tot = 0.0, time_lin = 0.0, time_qp_sol = 0.0;
     double stat[4] = {0, 0, 0, 0};   // SQP_RTI statistics table: stat_m = 2 rows x stat_n = 2 (qp_status, qp_iter), ocp_nlp_sqp_rti.c:264-265,648-649
     ocp_nlp_plan_t plan;
@@ -95,6 +97,10 @@ int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int
     c->N = N;
     c->Ts = Ts;
     c->rti_phase = 0;
+    c->wst.assign((size_t) (N + 1) * 17, 0.0);
+    for (int k = 0; k <= N; k++)
+        for (int i = 0; i < 17; i++) c->wst[(size_t) k * 17 + i] = k < N ? CfSpec::W[i] : (i < 13 ? CfSpec::W_e[i] : 0.0);
+    c->wst_used = false;
     c->bnd.assign((size_t) N * 8, 0.0);   // generate_c_code.py:133-134
     for (int k = 0; k < N; k++)
         for (int i = 0; i < 4; i++) { c->bnd[(size_t) k * 8 + i] = CfSpec::lbu[i]; c->bnd[(size_t) k * 8 + 4 + i] = CfSpec::ubu[i]; }
@@ -263,7 +269,20 @@ int ocp_nlp_cost_model_set(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_in *in, int
                 else if (W[i + n * j] != 0.0) return 1;
             }
         if (!c->batch) return 1;
-        return cfnmpc_batch_set(c->batch, stage < c->N ? "W" : "W_e", d, 0) != CFNMPC_OK;
+        // the reference sets the weight of ONE stage (ocp_nlp_cost_ls.c:301-331).  While all stages < N carry the same
+        // diagonal (the node's SET_WEIGHTS loop, acados_mpc.cpp:596-602) the solver-wide value and the fast kernels are
+        // used; as soon as stages differ the per-stage table takes over.
+        memcpy(&c->wst[(size_t) stage * 17], d, n * sizeof(double));
+        bool same = true;
+        for (int k = 1; k < c->N && same; k++) same = !memcmp(&c->wst[0], &c->wst[(size_t) k * 17], 17 * sizeof(double));
+        if (same) {
+            if (c->wst_used) { cfnmpc_batch_clear(c->batch, "W_stage"); c->wst_used = false; }
+            int rc = cfnmpc_batch_set(c->batch, "W", &c->wst[0], 0);
+            rc |= cfnmpc_batch_set(c->batch, "W_e", &c->wst[(size_t) c->N * 17], 0);
+            return rc != CFNMPC_OK;
+        }
+        c->wst_used = true;
+        return cfnmpc_batch_set(c->batch, "W_stage", c->wst.data(), 0) != CFNMPC_OK;
     }
     return 1;
 }

@@ -74,7 +74,7 @@ struct CfPcWarpT
     uint64_t *bar;
     unsigned par;
     double *SLOT, *PREP;
-    const double *DT, *BST;
+    const double *DT, *BST, *WTAB;
     double mu, alpha, mu_aff, sigma, pm_max;
     double nrm[4], lin[4];
     int flags;
@@ -84,12 +84,13 @@ struct CfPcWarpT
     {
         P = P_; PG = PG_; N = PG_->N; sm = sm_; lane = cf_lane();
         N2 = b.N2; bs0 = b.bs0; n_big = b.n_big;
-        PREP = prep_; DT = dts_; BST = nullptr; SLOT = slot;
+        PREP = prep_; DT = dts_; BST = nullptr; WTAB = nullptr; SLOT = slot;
         bar = reinterpret_cast<uint64_t *>(sm_ + SM_BAR);
         par = 0;
         lin[0] = lin[1] = lin[2] = lin[3] = 0.0;
     }
     CF_MEM double dt(int k) const { return DT ? DT[k] : PG->Ts; }
+    CF_MEM double wgt(int k, int idx) const { return WTAB ? WTAB[k * CF_NY + idx] : (k < N ? P->Wdiag[idx] : P->WNdiag[idx]); }
     CF_MEM int bsz(int i) const { return i < N2 ? (i < n_big ? bs0 + 1 : bs0) : 0; }             // stages in block i
     CF_MEM int kfirst(int i) const { return i < n_big ? i * (bs0 + 1) : n_big * (bs0 + 1) + (i - n_big) * bs0; }
     CF_MEM double step_adjust(double a) const { return (a < 1.0) ? a * ((1.0 - a) * 0.99 + a * 0.9999999) : a; }
@@ -146,7 +147,7 @@ struct CfPcWarpT
             if (i == 0) eliminate_x0(ST, xg, x0g);
             cf_syncwarp();
             if (xl) {
-                const double r = sqrt(P->Wdiag[ci]);
+                const double r = sqrt(wgt(k0, ci));
                 hdiag = dt(k0) * (r * r);
                 rq = ST[CF_MSZ + CF_NU + ci];               // zero for stage 0 (its x is eliminated)
             }
@@ -158,7 +159,7 @@ struct CfPcWarpT
                 const int e = lane - off;
                 const bool mine = e >= 0 && e < CF_NU;     // this lane's input belongs to stage k
                 if (mine) {
-                    const double r = sqrt(P->Wdiag[CF_NX + e]);
+                    const double r = sqrt(wgt(k, CF_NX + e));
                     hdiag = h * (r * r);
                     rq = gj[e];
                     // bounds (ocp_nlp_constraints_bgh.c:1634-1636) and OCP_QP_INIT_VAR scheme 1 (x_ocp_qp_ipm.c:1636-1769)
@@ -185,7 +186,7 @@ struct CfPcWarpT
                     double t[CF_NX], g = 0.0;
                     CF_UNROLL
                     for (int c = 0; c < CF_NX; c++) {
-                        const double r = sqrt(P->Wdiag[c]);
+                        const double r = sqrt(wgt(k, c));
                         const double q = h * (r * r);
                         t[c] = grow[c] * q;
                         g += grow[c] * (gj[CF_NU + c] + q * GS[c * MR + NVB]);
@@ -253,7 +254,7 @@ struct CfPcWarpT
             cf_syncwarp();
             if (vl) {
                 double hN = 1.0;
-                if (xl) { const double r = sqrt(P->WNdiag[ci]); hN = r * r; }
+                if (xl) { const double r = sqrt(wgt(N, ci)); hN = r * r; }
                 bk[P_H + trl + lane] = hN;
             }
             if (lane < MR) {
@@ -901,6 +902,7 @@ CF_DEV void cf_pcond_instance(const CfParams *Pg, const CfBatchView &bv, const C
     w.bind(P, Pg, slot, sm, bv.prep + (long) inst * bv.prep_stride, bv.dts, blk);
     w.par = par;
     w.BST = bv.bnd_stage;
+    w.WTAB = bv.W_stage;
     const int N = Pg->N;
     double *xg = bv.x + (long) inst * (N + 1) * CF_NX;
     double *ug = bv.u + (long) inst * N * CF_NU;

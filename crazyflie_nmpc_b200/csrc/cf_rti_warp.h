@@ -134,6 +134,10 @@ struct CfBatchView
     // time, ocp_nlp_constraints_bgh.c:653-674); null = the stage-0 / path boxes of CfParams.  Takes precedence over them
     // and over the per-instance arrays.
     const double *bnd_stage;
+    // cost weights per STAGE, [N+1][17]: row k < N = diagonal of W_k in cost order y = [x;u], row N = diagonal of W_e (13
+    // used): ocp_nlp_cost_model_set addresses one stage at a time (ocp_nlp_cost_ls.c:301-331); null = the weights of
+    // CfParams / the per-instance arrays.  Only read by the general kernel variants (VDT) and the condensed feedback.
+    const double *W_stage;
 };
 // layout of the prepared linearisation of one instance (doubles)
 #define CF_PREP_STAGE (CF_MSZ + 18)
@@ -205,6 +209,7 @@ struct CfWarpT
     double *PREP;      // this instance's prepared linearisation (split phases only)
     const double *DT;  // per-interval time steps (VDT only)
     const double *BST; // per-stage input boxes (null: the boxes of P)
+    const double *WST; // per-stage weights (general variants only; null: the weights of P)
     // lane constants
     double Hs, HN;     // Hessian diagonal for this lane's variable (stage / terminal)
     double W2;         // (sqrt(w))^2 of this lane's stage weight: the stage Hessian is dt_k * W2
@@ -217,7 +222,7 @@ struct CfWarpT
     CF_MEM void bind(const CfParams *P_, const CfParams *PG_, double *slot, double *sm_, double *prep_, const double *dts_)
     {
         P = P_; PG = PG_; N = PG_->N; sm = sm_; lane = cf_lane();
-        PREP = prep_; DT = dts_; BST = nullptr;
+        PREP = prep_; DT = dts_; BST = nullptr; WST = nullptr;
         bar = reinterpret_cast<uint64_t *>(sm_ + CF_SM_BAR);
         par = 0;
         CfScratchLayout s = cf_scratch_layout(N);
@@ -231,6 +236,20 @@ struct CfWarpT
         Hs = PG->Ts * W2;
         HN = (lane < CF_NU) ? Hs : (rN * rN);
     }
+    // weights that differ from stage to stage (general variants): the terminal Hessian comes from row N of the table
+    CF_MEM void set_stage_weights(const double *wst)
+    {
+        if constexpr (VDT) {
+            WST = wst;
+            if (WST && lane >= CF_NU && lane < CF_NV) { const double rN = sqrt(WST[N * CF_NY + lane - CF_NU]); HN = rN * rN; }
+        }
+    }
+    // weight of cost component idx (cost order y = [x;u]) at stage k <= N
+    CF_MEM double wgt(int k, int idx) const
+    {
+        if constexpr (VDT) { if (WST) return WST[k * CF_NY + idx]; }
+        return k < N ? P->Wdiag[idx] : P->WNdiag[idx];
+    }
     // length of shooting interval k = scaling of its cost term (ocp_nlp_in "Ts" / cost "scaling")
     CF_MEM double dt(int k) const
     {
@@ -240,8 +259,13 @@ struct CfWarpT
     // Hessian diagonal of this lane's variable at stage k < N
     CF_MEM double hess(int k) const
     {
-        if constexpr (VDT) return DT[k] * W2;
-        else return Hs;
+        if constexpr (VDT) {
+            if (WST) {
+                const double r = sqrt(WST[k * CF_NY + (lane < CF_NU ? CF_NX + lane : (lane < CF_NV ? lane - CF_NU : 0))]);
+                return DT[k] * (r * r);
+            }
+            return DT[k] * W2;
+        } else return Hs;
     }
 
     // ---- TMA staging: one mbarrier per buffer; lane 0 issues, every lane waits
@@ -383,8 +407,8 @@ struct CfWarpT
         const double uk = (lane < CF_NU) ? NOMS[5 * 14 + lane] : 0.0;
         if (lane < CF_NV) {
             double g;
-            if (lane < CF_NU) g = (P->Wdiag[CF_NX + lane] * (uk - yr_pre)) * h;
-            else g = (k == 0) ? 0.0 : (P->Wdiag[lane - CF_NU] * (NOMS[lane - CF_NU] - yr_pre)) * h;
+            if (lane < CF_NU) g = (wgt(k, CF_NX + lane) * (uk - yr_pre)) * h;
+            else g = (k == 0) ? 0.0 : (wgt(k, lane - CF_NU) * (NOMS[lane - CF_NU] - yr_pre)) * h;
             rqdst[lane] = g;
         }
         if (PH == CF_PH_PREPARATION && lane == CF_NV) rqdst[lane] = 0.0;   // pad of the 18-double gradient record
@@ -448,7 +472,7 @@ struct CfWarpT
         if (PH != CF_PH_PREPARATION) init_stage_vectors(N, 0.0);
         if (lane < CF_NV) {
             double g = 0.0;
-            if (lane >= CF_NU) g = P->WNdiag[lane - CF_NU] * (xg[N * CF_NX + lane - CF_NU] - yref_eg[lane - CF_NU]);
+            if (lane >= CF_NU) g = wgt(N, lane - CF_NU) * (xg[N * CF_NX + lane - CF_NU] - yref_eg[lane - CF_NU]);
             if (PH == CF_PH_PREPARATION) PREP[(long) N * CF_PREP_STAGE + lane] = g;
             else rec(N)[R_RQ + lane] = g;
         }
@@ -1245,6 +1269,7 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     w.bind(P, Pg, slot, sm, (PH != CF_PH_BOTH) ? bv.prep + (long) inst * bv.prep_stride : nullptr, VDT ? bv.dts : nullptr);
     w.par = par;
     w.BST = bv.bnd_stage;
+    w.set_stage_weights(bv.W_stage);
     const int N = Pg->N;
     double *xg = bv.x + (long) inst * (N + 1) * CF_NX;
     double *ug = bv.u + (long) inst * N * CF_NU;

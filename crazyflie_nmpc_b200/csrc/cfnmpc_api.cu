@@ -167,7 +167,9 @@ struct cfnmpc_batch
     double *d_dts = nullptr, *d_prep = nullptr;
     double *h_dts = nullptr;          // host copy of the time grid (N doubles)
     double *d_bst = nullptr;          // per-stage input boxes [N][8] (allocated on first use)
-    bool vdt = false, prepared = false;
+    double *d_wst = nullptr;          // per-stage weights [N+1][17] (allocated on first use); while set, the general kernels run
+    bool vdt_grid = false, wst = false, prepared = false;   // non-uniform time grid / per-stage weights: the general kernels
+    bool vdt = false;                                        // = vdt_grid || wst
     size_t smem = 0;
     long long launches = 0;
     bool timed = false;
@@ -192,7 +194,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
                     h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter,
                     h->d_policy, h->d_titer, h->d_motors, h->d_setpoint, h->d_traj, h->d_euler, h->d_twist,
-                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep, h->d_bst};
+                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep, h->d_bst, h->d_wst};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -354,7 +356,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     bv.res = h->d_res; bv.scratch = h->d_scratch; bv.scratch_stride = stride; bv.counter = h->d_counter;
     bv.W_b = bv.WN_b = bv.lbu_b = bv.ubu_b = bv.lbu0_b = bv.ubu0_b = nullptr;
     bv.prof = nullptr;
-    bv.dts = h->d_dts; bv.prep = nullptr; bv.prep_stride = cf_prep_stride(N); bv.bnd_stage = nullptr;
+    bv.dts = h->d_dts; bv.prep = nullptr; bv.prep_stride = cf_prep_stride(N); bv.bnd_stage = nullptr; bv.W_stage = nullptr;
     CKH(cudaStreamSynchronize(h->stream));
 #undef CKH
     *out = h;
@@ -447,6 +449,18 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         h->bv.bnd_stage = h->d_bst;
         return CFNMPC_OK;
     }
+    if (!strcmp(field, "W_stage")) {
+        // [N+1][17]: diagonal of W_k per stage (cost order y = [x;u]), row N = diagonal of W_e -- what a sequence of
+        // per-stage ocp_nlp_cost_model_set(.., k, "W", ..) calls builds (ocp_nlp_cost_ls.c:301-331)
+        const size_t bytes = (size_t) (h->N + 1) * CF_NY * 8;
+        if (!h->d_wst) CK(cudaMalloc(&h->d_wst, bytes));
+        CK(cudaMemcpyAsync(h->d_wst, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        h->bv.W_stage = h->d_wst;
+        h->wst = true;
+        h->vdt = true;
+        h->prepared = false;
+        return CFNMPC_OK;
+    }
     if (!strcmp(field, "time_steps")) {
         // crazyflie_acados_update_time_steps (c_templates_tera/acados_solver.in.c:133-153): interval lengths = cost scalings
         std::vector<double> dt(h->N);
@@ -461,7 +475,8 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         memcpy(h->h_dts, dt.data(), (size_t) h->N * 8);
         CK(cudaMemcpy(h->d_dts, h->h_dts, (size_t) h->N * 8, cudaMemcpyHostToDevice));
         h->P.Ts = dt[0];
-        h->vdt = !uniform;
+        h->vdt_grid = !uniform;
+        h->vdt = h->vdt_grid || h->wst;
         h->prepared = false;
         return CFNMPC_OK;
     }
@@ -556,6 +571,7 @@ extern "C" int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field)
     else if (!strcmp(field, "lbu0_batch")) h->bv.lbu0_b = nullptr;
     else if (!strcmp(field, "ubu0_batch")) h->bv.ubu0_b = nullptr;
     else if (!strcmp(field, "bounds_stage")) h->bv.bnd_stage = nullptr;
+    else if (!strcmp(field, "W_stage")) { h->bv.W_stage = nullptr; h->wst = false; h->vdt = h->vdt_grid; h->prepared = false; }
     else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_clear: '") + field + "' is not a per-instance parameter array");
     return CFNMPC_OK;
 }

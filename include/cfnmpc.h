@@ -81,6 +81,11 @@ int cfnmpc_batch_set_stream(cfnmpc_batch *h, void *cuda_stream);
  *                                   stage at a time (ocp_nlp_constraints_model_set(.., k, "lbu"|"ubu", ..),
  *                                   ocp_nlp_constraints_bgh.c:653-674).  Once given it takes precedence over "lbu","ubu",
  *                                   "lbu0","ubu0" and the per-instance arrays until cfnmpc_batch_clear("bounds_stage").
+ *   "W_stage" double [N+1][17]      weight diagonals per STAGE (row k < N: W_k in cost order y = [x;u]; row N: W_e, 13 used): the
+ *                                   reference sets the weight of one stage at a time (ocp_nlp_cost_model_set(.., k, "W", ..),
+ *                                   ocp_nlp_cost_ls.c:301-331).  Takes precedence over "W", "W_e" and the per-instance arrays
+ *                                   until cfnmpc_batch_clear("W_stage"); runs the general kernels.  Non-diagonal weights are
+ *                                   not supported (the single-instance setter rejects them).
  *   "time_steps" double [N]         lengths of the shooting intervals (host or device pointer); each is also the
  *                                   scaling of its stage cost, as crazyflie_acados_create_with_discretization /
  *                                   crazyflie_acados_update_time_steps set them (c_templates_tera/acados_solver.in.c:

@@ -185,6 +185,17 @@ void cfo_set_time_steps(const double *dt, int n)
 
 /* Input box per stage, tab[n][8] = lbu(4) | ubu(4): ocp_nlp_constraints_model_set addresses one stage at a time
  * (ocp_nlp_constraints_bgh.c:653-674).  Global, test use only; n = 0 returns to the boxes of cfo_params. */
+/* cost weights per stage, [N+1][17] (row N: W_e): ocp_nlp_cost_model_set(.., k, "W", ..) addresses one stage at a time
+ * (ocp_nlp_cost_ls.c:301-331).  Global in the checker, like the time grid. */
+static double g_wst[(CFO_MAX_N + 1) * 17];
+static int g_wst_n = 0;
+void cfo_set_stage_weights(const double *tab, int n_rows)
+{
+    g_wst_n = 0;
+    if (tab && n_rows > 0 && n_rows <= CFO_MAX_N + 1) { memcpy(g_wst, tab, sizeof(double) * 17 * n_rows); g_wst_n = n_rows; }
+}
+#define WKS(p, k, idx) ((k) < g_wst_n ? g_wst[17 * (k) + (idx)] : (p)->Wdiag[idx])   /* stages k < N */
+#define WK(p, k, N, idx) ((k) < g_wst_n ? g_wst[17 * (k) + (idx)] : ((k) < (N) ? (p)->Wdiag[idx] : (p)->WNdiag[idx]))
 static double g_bst[CFO_MAX_N * 8];
 static int g_bst_n = 0;
 void cfo_set_stage_bounds(const double *tab, int n)
@@ -220,8 +231,8 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
                 /* grad = scaling * Cyt * W * (Cy ux - yref), [u;x] order */
                 double *g = rqz + NV * k;
                 const double *yr = yref + NV * k;
-                for (int i = 0; i < NU; i++) g[i] = (p_->Wdiag[NX + i] * (uk[i] - yr[NX + i])) * DTK(k);
-                for (int i = 0; i < NX; i++) g[NU + i] = (p_->Wdiag[i] * (xk[i] - yr[i])) * DTK(k);
+                for (int i = 0; i < NU; i++) g[i] = (WK(p_, k, N, NX + i) * (uk[i] - yr[NX + i])) * DTK(k);
+                for (int i = 0; i < NX; i++) g[NU + i] = (WK(p_, k, N, i) * (xk[i] - yr[i])) * DTK(k);
             }
             int nb = k == 0 ? NV : NU;
             for (int i = 0; i < NU; i++) {
@@ -240,7 +251,7 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
             od += nb;
         } else if (rqz) {
             double *g = rqz + NV * N;
-            for (int i = 0; i < NX; i++) g[i] = p_->WNdiag[i] * (xk[i] - yref_e[i]);
+            for (int i = 0; i < NX; i++) g[i] = WK(p_, N, N, i) * (xk[i] - yref_e[i]);
         }
     }
 }
@@ -826,9 +837,9 @@ int cfo_rti(int N, double Ts, const cfo_params *p_, const double *x0, const doub
         s->nv = s->nu + s->nx;
         s->nb = k < N ? NU : 0;
         /* Hessian: scaling * (sqrt(w))^2, cost_ls.c:739-772 */
-        for (int i = 0; i < s->nu; i++) { double r = sqrt(p_->Wdiag[NX + i]); s->H[i] = DTK(k) * (r * r); }
+        for (int i = 0; i < s->nu; i++) { double r = sqrt(WKS(p_, k, NX + i)); s->H[i] = DTK(k) * (r * r); }
         for (int i = 0; i < s->nx; i++) {
-            double r = sqrt(k < N ? p_->Wdiag[i] : p_->WNdiag[i]);
+            double r = sqrt(WK(p_, k, N, i));
             s->H[s->nu + i] = (k < N ? DTK(k) : 1.0) * (r * r);
         }
         const double *g = rqz + NV * k;
@@ -957,9 +968,9 @@ static void build_reduced_stages(int N, double Ts, const cfo_params *p_, const d
         s->nx = k == 0 ? 0 : NX;
         s->nv = s->nu + s->nx;
         s->nb = k < N ? NU : 0;
-        for (int i = 0; i < s->nu; i++) { double r = sqrt(p_->Wdiag[NX + i]); s->H[i] = DTK(k) * (r * r); }
+        for (int i = 0; i < s->nu; i++) { double r = sqrt(WKS(p_, k, NX + i)); s->H[i] = DTK(k) * (r * r); }
         for (int i = 0; i < s->nx; i++) {
-            double r = sqrt(k < N ? p_->Wdiag[i] : p_->WNdiag[i]);
+            double r = sqrt(WK(p_, k, N, i));
             s->H[s->nu + i] = (k < N ? DTK(k) : 1.0) * (r * r);
         }
         const double *g = rqz + NV * k;

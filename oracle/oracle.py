@@ -70,6 +70,7 @@ class Port:
         L.cfo_ode.argtypes = [_dp, _dp, _dp]
         L.cfo_default_params.argtypes = [ctypes.POINTER(CfoParams)]
         L.cfo_set_iter_max.argtypes = [ctypes.c_int]
+        L.cfo_set_stage_weights.argtypes = [_dp, ctypes.c_int]
         L.cfo_set_time_steps.argtypes = [_dp, ctypes.c_int]
         L.cfo_set_stage_bounds.argtypes = [_dp, ctypes.c_int]
         L.cfo_rti_split.restype = ctypes.c_int
@@ -79,6 +80,14 @@ class Port:
     def set_iter_max(self, n=50):
         """qp_iter_max of the interior-point loop (global in the checker; 50 = the reference configuration)."""
         self.lib.cfo_set_iter_max(int(n))
+
+    def set_stage_weights(self, tab=None):
+        """Cost weights per stage, [N+1][17] (row N = W_e, 13 used); global in the checker, None returns to the params."""
+        if tab is None:
+            self.lib.cfo_set_stage_weights(None, 0)
+        else:
+            tab = np.ascontiguousarray(tab, float)
+            self.lib.cfo_set_stage_weights(_P(tab), tab.shape[0])
 
     def set_time_steps(self, dt=None):
         """Non-uniform shooting grid (global in the checker; None returns to the uniform grid)."""

@@ -633,3 +633,40 @@ def test_full_size_sample_against_reference(port, gen, N):
         sr, ir = port.batch(N, TS, ws["x0"], ws["yref"], ws["yref_e"], xr, ur)
     assert (sr == 0).all() and np.abs(it - ir).max() <= 1
     assert rel_err(x, xr) <= TIGHT and rel_err(u, ur) <= TIGHT
+
+
+def test_per_stage_weights(port, ref):
+    """Weights that differ from stage to stage -- the reference sets W one stage at a time
+    (ocp_nlp_cost_model_set(.., k, "W", ..), ocp_nlp_cost_ls.c:301-331) -- uncondensed and partially condensed."""
+    N, B = 20, 6
+    w = wl.hover_batch(B, N, seed=4)
+    rng = np.random.default_rng(0)
+    Q = np.array([120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0, 0.06, 0.06, 0.06, 0.06])
+    tab = Q * rng.uniform(0.5, 2.0, (N + 1, 17))
+    tab[N, :13] *= 50
+    port.set_stage_weights(tab)
+    try:
+        for cond_N in (0, 7):
+            xo, uo = w["x_init"].copy(), w["u_init"].copy()
+            so, io = port.batch(N, TS, w["x0"], w["yref"], w["yref_e"], xo, uo, cond_N=cond_N)
+            with cf.BatchSolver(B, N, TS) as s:
+                s.set_option("qp_cond_N", cond_N)
+                s.set("W_stage", tab).set_problem(w).solve(1)
+                assert (s.get("status") == so).all() and np.abs(s.get("qp_iter") - io).max() <= 1
+                assert rel_err(s.get("x_all"), xo) <= TIGHT and rel_err(s.get("u_all"), uo) <= TIGHT
+                if cond_N == 0:   # the reference itself, stage by stage
+                    r = ref.solver(N, TS)
+                    for k in range(N):
+                        r.set_W_at(k, np.diag(tab[k]))
+                    r.set_W_at(N, np.diag(tab[N, :13]))
+                    xr, ur = w["x_init"][0].copy(), w["u_init"][0].copy()
+                    r.rti(w["x0"][0], w["yref"][0], w["yref_e"][0], xr, ur)
+                    assert rel_err(s.get("x_all")[0], xr) <= TIGHT and rel_err(s.get("u_all")[0], ur) <= TIGHT
+                    # the split phases take the table too, and clearing it returns to the solver-wide weights
+                    s.set_problem(w).prepare().feedback()
+                    assert rel_err(s.get("u_all"), uo) <= TIGHT
+                    s.clear("W_stage").set_problem(w).solve(1)
+                    d = gpu_solve(w, N)
+                    assert np.array_equal(s.get("u_all"), d["u"])
+    finally:
+        port.set_stage_weights(None)
