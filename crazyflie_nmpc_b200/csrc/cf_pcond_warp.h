@@ -55,18 +55,19 @@ struct CfPcWarpT
         P_H = 0, R_UX = HSZ, R_PI = R_UX + MR, R_DPI = R_PI + 14, R_RQ = R_DPI + 14, R_D = R_RQ + MR, R_BKP = R_D + NB2,
         R_PB = R_BKP + NB2, R_DLAM = R_PB + 14, R_DT = R_DLAM + NB2, R_LAM = R_DT + NB2, R_T = R_LAM + NB2, R_DUX = R_T + NB2,
         B_M = R_DUX + MR, MSZ = MR * CF_NX, B_RD = B_M + MSZ, R_RESD = B_RD, R_RESM = R_RESD + NB2, R_RESG = R_RESM + NB2,
-        R_RESB = R_RESG + MR, B_LU = R_RESB + 14, LUSZ = MR * NUB, B_PX = B_LU + LUSZ, SB = B_PX + CF_LX,
+        R_RESB = R_RESG + MR, B_LU = R_RESB + 14, LUSZ = MR * NUB,   // factor columns, element (r,j) at j*MR + r
+        B_PX = B_LU + LUSZ, SB = B_PX + CF_LX,
         RT = (MR + 7) / 8, CTV = (NVB + 7) / 8, T0 = NUB / 8, KSU = NUB / 4,
-        ALP = (NVB <= 28) ? 28 : 36,                 // row stride of P in shared memory: = 4 or 12 (mod 16) -> conflict-free fragments
+        ALP = 20, PCO = 4,                           // P in shared memory as in the uncondensed program: element (i,j) at i*20 + 4 + j
         WST = 20,                                    // row stride of W
         BUFSZ = B_RD,
         SM_BUF0 = 0, SM_BUF1 = BUFSZ, SM_P = 2 * BUFSZ, SM_V0 = SM_P + 13 * ALP, VST = 32, SM_V1 = SM_V0 + VST, SM_V2 = SM_V1 + VST,
-        SM_V3 = SM_V2 + VST, SM_BAR = SM_V3 + VST, SM_PAR = SM_BAR + 4, SM_DOUBLES = SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1)
+        SM_BAR = SM_V2 + VST, SM_PAR = SM_BAR + 4, SM_DOUBLES = SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1)
     };
     static_assert(MR <= 32 && (MR & 1) == 0, "one row per lane");
     static_assert(B_RD >= SB - R_LAM && B_RD >= B_PX - R_BKP && MR * WST <= B_RD - HSZ, "staging buffers");
     static_assert((HSZ & 1) == 0 && (MSZ & 1) == 0 && (LUSZ & 1) == 0 && (SB & 1) == 0 && (ALP * 13) % 2 == 0, "16-byte alignment");
-    static_assert(BS * CF_PREP_STAGE + MSZ + HSZ <= 2 * BUFSZ, "staging area of the condensing pass");
+    static_assert(2 * BS * CF_PREP_STAGE + MSZ + HSZ <= SM_V2, "staging area of the condensing pass (buffers, P and two vectors; V2 holds the weights)");
 
     const CfParams *P, *PG;
     int lane, N, N2, bs0, n_big;
@@ -124,31 +125,40 @@ struct CfPcWarpT
     // (x_ocp_qp_red.c:310-330).  Lane r < MR owns row r of G (registers) and of the condensed Hessian (shared memory).
     CF_MEM void condense(const double *xg, const double *ug, const double *x0g)
     {
-        double *ST = sm;                                    // bs prepared records
-        double *GS = sm + BS * CF_PREP_STAGE;               // G (MR x 13, element (r,c) at c*MR + r) for the products
+        double *GS = sm + 2 * BS * CF_PREP_STAGE;           // G (MR x 13, element (r,c) at c*MR + r) for the products
         double *HS = GS + MSZ;                              // packed lower triangle of H2
         const bool vl = lane < NVB, ul = lane < NUB, xl = lane >= NUB && vl;
         const int ci = xl ? lane - NUB : 0, lv = vl ? lane : 0, trl = cf_tri(lv);
+        // (sqrt(w))^2 of the 13 state weights (ocp_nlp_cost_ls.c:739-772), once per instance unless they differ per stage
+        double *QW = sm + SM_V2;   // (the staging area of this pass extends over P, V0 and V1)
         pass_begin();
+        if (lane < CF_NX) { const double r = sqrt(P->Wdiag[lane]); QW[lane] = r * r; }
+        // the prepared records of block i+1 travel while block i is condensed (two staging areas, two mbarriers)
+        if (lane == 0) {
+            cf_bulk_expect(bar, bsz(0) * CF_PREP_STAGE * 8);
+            cf_bulk_g2s_raw(sm, PREP, bsz(0) * CF_PREP_STAGE * 8, bar);
+        }
         CF_NOUNROLL
         for (int i = 0; i < N2; i++) {
-            const int bs = bsz(i), k0 = kfirst(i);
+            const int bs = bsz(i), k0 = kfirst(i), bf = i & 1;
+            double *ST = sm + bf * (BS * CF_PREP_STAGE);
             double *bk = blk(i);
-            if (lane == 0) {
-                cf_bulk_expect(bar, bs * CF_PREP_STAGE * 8);
-                cf_bulk_g2s_raw(ST, PREP + (long) k0 * CF_PREP_STAGE, bs * CF_PREP_STAGE * 8, bar);
+            if (i + 1 < N2 && lane == 0) {   // (the barrier that ended block i-1 ordered its reads of that staging area)
+                cf_fence_proxy_async();
+                cf_bulk_expect(bar + (bf ^ 1), bsz(i + 1) * CF_PREP_STAGE * 8);
+                cf_bulk_g2s_raw(sm + (bf ^ 1) * (BS * CF_PREP_STAGE), PREP + (long) kfirst(i + 1) * CF_PREP_STAGE,
+                                bsz(i + 1) * CF_PREP_STAGE * 8, bar + (bf ^ 1));
             }
             for (int e = lane; e < HSZ; e += 32) HS[e] = 0.0;
             double grow[CF_NX];
-            CF_UNROLL
-            for (int c = 0; c < CF_NX; c++) grow[c] = (lane - NUB == c) ? 1.0 : 0.0;
             double rq = 0.0, hdiag = 1.0, v0 = 0.0;        // dummy inputs: unit Hessian, nothing else
-            wait(0);
+            wait(bf);
             if (i == 0) eliminate_x0(ST, xg, x0g);
             cf_syncwarp();
             if (xl) {
-                const double r = sqrt(wgt(k0, ci));
-                hdiag = dt(k0) * (r * r);
+                double w2 = QW[ci];
+                if (WTAB) { const double r = sqrt(WTAB[k0 * CF_NY + ci]); w2 = r * r; }
+                hdiag = dt(k0) * w2;
                 rq = ST[CF_MSZ + CF_NU + ci];               // zero for stage 0 (its x is eliminated)
             }
             CF_NOUNROLL
@@ -176,35 +186,59 @@ struct CfPcWarpT
                     bk[R_T + lane] = tl; bk[R_T + NUB + lane] = tu;
                     bk[R_LAM + lane] = CF_MU0 / tl; bk[R_LAM + NUB + lane] = CF_MU0 / tu;
                 }
-                if (j >= 1) {
-                    // cost of the inner state x_k = G' z:  H2 += G Q_k G',  rq2 += G (q_k + Q_k c)
-                    if (lane < MR) {
-                        CF_UNROLL
-                        for (int c = 0; c < CF_NX; c++) GS[c * MR + lane] = grow[c];
-                    }
-                    cf_syncwarp();
-                    double t[CF_NX], g = 0.0;
+                const double *Mrow = Mj + (mine ? e : (lane == NVB ? 17 : (xl ? CF_NU + ci : 0)));   // this lane's row of the record
+                if (j == 0) {
+                    // G_1 = G_0 A' + [E B'; 0; b'] with G_0 = [0; I; 0]: the rows of the record itself, no product
+                    const bool any = mine || xl || lane == NVB;
+                    CF_UNROLL
+                    for (int c = 0; c < CF_NX; c++) grow[c] = any ? Mrow[c * CF_MROWS] : 0.0;
+                    continue;
+                }
+                // cost of the inner state x_k = G' z:  H2 += G Q_k G',  rq2 += G (q_k + Q_k c)
+                if (lane < MR) {
+                    CF_UNROLL
+                    for (int c = 0; c < CF_NX; c++) GS[c * MR + lane] = grow[c];
+                }
+                cf_syncwarp();
+                {
+                    double t[CF_NX], g0 = 0.0, g1 = 0.0;
                     CF_UNROLL
                     for (int c = 0; c < CF_NX; c++) {
-                        const double r = sqrt(wgt(k, c));
-                        const double q = h * (r * r);
+                        double w2 = QW[c];
+                        if (WTAB) { const double r = sqrt(WTAB[k * CF_NY + c]); w2 = r * r; }
+                        const double q = h * w2;
                         t[c] = grow[c] * q;
-                        g += grow[c] * (gj[CF_NU + c] + q * GS[c * MR + NVB]);
+                        const double v = grow[c] * (gj[CF_NU + c] + q * GS[c * MR + NVB]);
+                        if (c & 1) g1 += v;
+                        else g0 += v;
                     }
-                    rq += g;
+                    rq += g0 + g1;
                     CF_NOUNROLL
-                    for (int c2 = 0; c2 < NVB; c2++) {
+                    for (int c2 = 0; c2 < NVB - 1; c2 += 2) {   // two columns per trip: four independent chains
+                        double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
+                        CF_UNROLL
+                        for (int c = 0; c + 1 < CF_NX; c += 2) {
+                            const cf_d2 ga = cf_ld2(GS + c * MR + c2), gb = cf_ld2(GS + (c + 1) * MR + c2);
+                            s0 += t[c] * ga.x; r0 += t[c] * ga.y;
+                            s1 += t[c + 1] * gb.x; r1 += t[c + 1] * gb.y;
+                        }
+                        const cf_d2 gl = cf_ld2(GS + (CF_NX - 1) * MR + c2);
+                        s0 += t[CF_NX - 1] * gl.x; r0 += t[CF_NX - 1] * gl.y;
+                        if (vl && c2 <= lane) HS[trl + c2] += s0 + s1;
+                        if (vl && c2 + 1 <= lane) HS[trl + c2 + 1] += r0 + r1;
+                    }
+                    {   // NVB is odd: the last column
                         double s0 = 0.0, s1 = 0.0;
                         CF_UNROLL
                         for (int c = 0; c + 1 < CF_NX; c += 2) {
-                            s0 += t[c] * GS[c * MR + c2];
-                            s1 += t[c + 1] * GS[(c + 1) * MR + c2];
+                            s0 += t[c] * GS[c * MR + NVB - 1];
+                            s1 += t[c + 1] * GS[(c + 1) * MR + NVB - 1];
                         }
-                        s0 += t[CF_NX - 1] * GS[(CF_NX - 1) * MR + c2];
-                        if (vl && c2 <= lane) HS[trl + c2] += s0 + s1;
+                        s0 += t[CF_NX - 1] * GS[(CF_NX - 1) * MR + NVB - 1];
+                        if (lane == NVB - 1) HS[trl + NVB - 1] += s0 + s1;
                     }
-                    cf_syncwarp();
                 }
+                cf_syncwarp();
                 // G <- G A_k' + [E B_k' ; 0 ; b_k']   (A_k'[i][c] = M_k[4+i][c], element (r,c) of a record at c*18 + r)
                 double gn[CF_NX];
                 CF_UNROLL
@@ -218,9 +252,7 @@ struct CfPcWarpT
                         s1 += grow[2 * ip + 1] * a2.y;
                     }
                     s0 += grow[12] * Ac[12];
-                    double add = 0.0;
-                    if (mine) add = Mj[c * CF_MROWS + e];
-                    if (lane == NVB) add = Mj[c * CF_MROWS + 17];
+                    const double add = (mine || lane == NVB) ? Mrow[c * CF_MROWS] : 0.0;
                     gn[c] = (s0 + s1) + add;
                 }
                 CF_UNROLL
@@ -244,8 +276,7 @@ struct CfPcWarpT
                 bk[R_T + lane] = 1.0; bk[R_T + NUB + lane] = 1.0;
                 bk[R_LAM + lane] = 1.0; bk[R_LAM + NUB + lane] = 1.0;
             }
-            cf_syncwarp();   // ST / GS / HS are rewritten for the next block
-            if (lane == 0) cf_fence_proxy_async();
+            cf_syncwarp();   // this block's staging area, GS and HS may be rewritten
         }
         // terminal stage: diagonal Hessian (dummy inputs 1, states W_e), gradient from the preparation, no dynamics
         {
@@ -306,7 +337,7 @@ struct CfPcWarpT
                 const int i = 4 * kk + fq, j = 8 * hh + fg;
                 const bool ok = i < CF_NX && j < CF_NX;
                 const int hi = i > j ? i : j, lo = i > j ? j : i;
-                pa[kk][hh] = ok ? hi * ALP + lo + NUB : -1;
+                pa[kk][hh] = ok ? hi * ALP + lo + PCO : -1;
             }
         int pk[3];      // packed lower triangle of P_{k+1}: element e = lane + 32 t
         CF_UNROLL
@@ -315,7 +346,7 @@ struct CfPcWarpT
             int i = 0;
             CF_UNROLL
             for (int q = 1; q < CF_NX; q++) i += (e >= cf_tri(q)) ? 1 : 0;
-            pk[t] = (e < 91) ? i * ALP + (e - cf_tri(i)) + NUB : -1;
+            pk[t] = (e < 91) ? i * ALP + (e - cf_tri(i)) + PCO : -1;
         }
         int trr[RT];    // packed row starts of the fragment rows
         CF_UNROLL
@@ -425,7 +456,7 @@ struct CfPcWarpT
                 cf_syncwarp();
                 const double hN = HP[trl + lv] + CF_REG_PRIM;
                 if (xl) {
-                    PS[ci * ALP + ci + NUB] = hN;
+                    PS[ci * ALP + ci + PCO] = hN;
                     PV[ci] = rg;
                     rk[R_DUX + lane] = rg;
                 }
@@ -512,7 +543,7 @@ struct CfPcWarpT
                 for (int tp = 0; tp < CTV; tp++) {
                     if (tp > t || 8 * tp >= NUB) continue;
                     const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
-                    if (r < MR && c0 < NUB) cf_st2(LUs + r * NUB + c0, sx[t][tp][0], sx[t][tp][1]);
+                    if (r < MR && c0 < NUB) { LUs[c0 * MR + r] = sx[t][tp][0]; LUs[(c0 + 1) * MR + r] = sx[t][tp][1]; }
                 }
             }
             cf_syncwarp();
@@ -520,29 +551,25 @@ struct CfPcWarpT
             {
                 double o[NUB], og[NUB];
                 CF_UNROLL
-                for (int jp = 0; jp < NUB / 2; jp++) {
-                    cf_d2 v = {0.0, 0.0};
-                    if (lane < MR) v = cf_ld2(LUs + rl * NUB + 2 * jp);
-                    o[2 * jp] = v.x; o[2 * jp + 1] = v.y;
-                }
+                for (int j = 0; j < NUB; j++) o[j] = (lane < MR) ? LUs[j * MR + rl] : 0.0;
                 CF_UNROLL
                 for (int j = 0; j < NUB; j++) {
                     double v = o[j];
                     CF_UNROLL
-                    for (int c = 0; c < j; c++) v -= o[c] * LUs[j * NUB + c];
+                    for (int c = 0; c < j; c++) v -= o[c] * LUs[c * MR + j];
                     const double piv = cf_shfl(v, j);
                     double dj, inv;
                     cf_sqrt_rsqrt(piv, dj, inv);
                     if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; flags |= CF_FLAG_BAD_PIVOT; }
                     o[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
-                    if (lane < MR) LUs[rl * NUB + j] = o[j];
+                    if (lane < MR) LUs[j * MR + rl] = o[j];
                     og[j] = (rl == j) ? inv : o[j];
                     cf_syncwarp();
                 }
                 double *LFk = blk(k) + B_LU;
                 if (lane < MR) {
                     CF_UNROLL
-                    for (int jp = 0; jp < NUB / 2; jp++) cf_st2(LFk + lane * NUB + 2 * jp, og[2 * jp], og[2 * jp + 1]);
+                    for (int j = 0; j < NUB; j++) LFk[j * MR + lane] = og[j];
                 }
                 if (lane == NVB) {
                     CF_UNROLL
@@ -555,7 +582,7 @@ struct CfPcWarpT
             for (int t = 0; t < RT; t++) {
                 const int r = 8 * t + fg;
                 CF_UNROLL
-                for (int ks = 0; ks < KSU; ks++) la[t][ks] = (t >= T0 && r < MR) ? LUs[r * NUB + 4 * ks + fq] : 0.0;
+                for (int ks = 0; ks < KSU; ks++) la[t][ks] = (t >= T0 && r < MR) ? LUs[(4 * ks + fq) * MR + r] : 0.0;
             }
             cf_syncwarp();
             CF_UNROLL
@@ -567,7 +594,7 @@ struct CfPcWarpT
                     for (int ks = 0; ks < KSU; ks++) cf_dmma(sx[t][tp][0], sx[t][tp][1], -la[t][ks], la[tp][ks]);
                     const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
                     const bool xrow = r >= NUB && r < NVB;
-                    if (xrow && c0 + 1 < ALP) cf_st2(PS + (r - NUB) * ALP + c0, sx[t][tp][0], sx[t][tp][1]);
+                    if (xrow && c0 + PCO >= NUB && c0 < NUB + 16) cf_st2(PS + (r - NUB) * ALP + (c0 - NUB + PCO), sx[t][tp][0], sx[t][tp][1]);
                     if (r == NVB) {
                         CF_UNROLL
                         for (int e = 0; e < 2; e++) {
@@ -603,13 +630,13 @@ struct CfPcWarpT
     // forward substitution + dlam, dt, step length (x_ocp_qp_kkt.c:536-570,741-758, x_core_qp_ipm_aux.c:117-216)
     CF_MEM void forward(const bool need_pi)
     {
-        double *XS = sm + SM_V0, *DS = sm + SM_V1, *PSv = sm + SM_V3;
+        double *XS = sm + SM_V0, *DS = sm + SM_V1;
         double dn = 1.0, dd = -1.0, pn_ = 1.0, pd_ = -1.0;
         double dxk = 0.0;
         const int VO = R_LAM, VN = (need_pi ? SB : B_PX) - R_LAM;
         pass_begin();
         if (N2 > 0) fetch(0, 0, VO, VN);
-        XS[lane] = 0.0; PSv[lane] = 0.0;
+        XS[lane] = 0.0;
         const bool vl = lane < NVB, ul = lane < NUB, xl = lane >= NUB && vl;
         const int ci = xl ? lane - NUB : 0, lv = vl ? lane : 0, ju = ul ? lane : 0;
         double *PE = sm + SM_P;   // P_{k+1} expanded to full symmetric rows, stride CF_PST
@@ -653,18 +680,18 @@ struct CfPcWarpT
                 CF_UNROLL
                 for (int ip = 0; ip < 6; ip++) {
                     const cf_d2 x2 = cf_ld2(XS + 2 * ip);
-                    v0 -= LU[(NUB + 2 * ip) * NUB + ju] * x2.x;
-                    v1 -= LU[(NUB + 2 * ip + 1) * NUB + ju] * x2.y;
+                    v0 -= LU[ju * MR + NUB + 2 * ip] * x2.x;
+                    v1 -= LU[ju * MR + NUB + 2 * ip + 1] * x2.y;
                 }
-                v0 -= LU[(NUB + 12) * NUB + ju] * XS[12];
+                v0 -= LU[ju * MR + NUB + 12] * XS[12];
                 v = v0 + v1;
             }
-            const double invd = LU[ju * NUB + ju];
+            const double invd = LU[ju * MR + ju];
             double du = 0.0;
             CF_UNROLL
             for (int j = NUB - 1; j >= 0; j--) {
                 const double duj = cf_shfl(v * invd, j);
-                const double vn = v - LU[j * NUB + ju] * duj;
+                const double vn = v - LU[ju * MR + j] * duj;
                 du = (ju == j) ? duj : du;
                 v = (ju < j) ? vn : v;
             }
@@ -770,11 +797,8 @@ struct CfPcWarpT
             // TRSV_LNN_MN(nv, nu)
             double Lr[NUB];
             CF_UNROLL
-            for (int jp = 0; jp < NUB / 2; jp++) {
-                const cf_d2 l2 = cf_ld2(LU + lv * NUB + 2 * jp);
-                Lr[2 * jp] = l2.x; Lr[2 * jp + 1] = l2.y;
-            }
-            const double invd = LU[ju * NUB + ju];
+            for (int j = 0; j < NUB; j++) Lr[j] = LU[j * MR + lv];
+            const double invd = LU[ju * MR + ju];
             CF_UNROLL
             for (int j = 0; j < NUB; j++) {
                 const double zj = cf_shfl(rhs * invd, j);
@@ -790,20 +814,38 @@ struct CfPcWarpT
     // COMPUTE_MU_AFF_QP (x_core_qp_ipm_aux.c:329-352) + the complementarity norm the adjusted step would produce
     CF_MEM void compute_mu_aff()
     {
-        double s0 = 0.0, pm = 0.0;
+        double s0 = 0.0, s1 = 0.0, pm = 0.0;
         const double aa = step_adjust(alpha);
         const int e = lane < NB2 ? lane : 0, inp = e < NUB ? e : e - NUB;
+        int k = 0;
         CF_NOUNROLL
-        for (int k = 0; k < N2; k++) {
+        for (; k + 3 < N2; k += 4) {   // four stages per trip: sixteen independent loads in flight per lane
+            double l[4], d[4], t[4], u[4];
+            CF_UNROLL
+            for (int q = 0; q < 4; q++) {
+                const double *r = rec(k + q);
+                l[q] = r[R_LAM + e]; d[q] = r[R_DLAM + e]; t[q] = r[R_T + e]; u[q] = r[R_DT + e];
+            }
+            CF_UNROLL
+            for (int q = 0; q < 4; q++) {
+                if (lane < NB2 && inp < CF_NU * bsz(k + q)) {
+                    const double v = (l[q] + alpha * d[q]) * (t[q] + alpha * u[q]);
+                    if (q & 1) s1 += v;
+                    else s0 += v;
+                    cf_amax(pm, (l[q] + aa * d[q]) * (t[q] + aa * u[q]));
+                }
+            }
+        }
+        CF_NOUNROLL
+        for (; k < N2; k++) {
             const double *r = rec(k);
-            const bool on = lane < NB2 && inp < CF_NU * bsz(k);
             const double l = r[R_LAM + e], d = r[R_DLAM + e], t = r[R_T + e], u = r[R_DT + e];
-            if (on) {
+            if (lane < NB2 && inp < CF_NU * bsz(k)) {
                 s0 += (l + alpha * d) * (t + alpha * u);
                 cf_amax(pm, (l + aa * d) * (t + aa * u));
             }
         }
-        mu_aff = cf_warp_sum(s0) * (1.0 / (double) (2 * CF_NU * N));
+        mu_aff = cf_warp_sum(s0 + s1) * (1.0 / (double) (2 * CF_NU * N));
         pm_max = cf_warp_max(pm);
     }
 
@@ -816,30 +858,47 @@ struct CfPcWarpT
     // (ocp_nlp_common.c:2900-2952), x_0 taking the eliminated step x0 - x_0.
     CF_MEM void expand_update(double *xg, double *ug, const double *x0g)
     {
-        double *ST = sm, *DS = sm + SM_V1;
+        double *DS = sm + SM_V1, *UXB = sm + SM_V2;
         const bool xs_l = lane >= CF_NU && lane < CF_NV;      // 18-row layout of the records: lanes 4..16 carry the state
         const int ci = xs_l ? lane - CF_NU : 0;
         pass_begin();
+        // the records of block i+1 and its solution travel while block i is expanded (two staging areas, two mbarriers)
+        if (lane == 0) {
+            cf_bulk_expect(bar, bsz(0) * CF_PREP_STAGE * 8);
+            cf_bulk_g2s_raw(sm, PREP, bsz(0) * CF_PREP_STAGE * 8, bar);
+        }
+        double unext = lane < NVB ? rec(0)[R_UX + lane] : 0.0;
         CF_NOUNROLL
         for (int i = 0; i < N2; i++) {
-            const int bs = bsz(i), k0 = kfirst(i);
-            if (lane == 0) {
-                cf_bulk_expect(bar, bs * CF_PREP_STAGE * 8);
-                cf_bulk_g2s_raw(ST, PREP + (long) k0 * CF_PREP_STAGE, bs * CF_PREP_STAGE * 8, bar);
+            const int bs = bsz(i), k0 = kfirst(i), bf = i & 1;
+            const double *ST = sm + bf * (BS * CF_PREP_STAGE);
+            const double ucur = unext;
+            cf_syncwarp();   // every lane is done with block i-1: its staging area and UXB may be rewritten
+            if (i + 1 < N2) {
+                if (lane == 0) {
+                    cf_fence_proxy_async();
+                    cf_bulk_expect(bar + (bf ^ 1), bsz(i + 1) * CF_PREP_STAGE * 8);
+                    cf_bulk_g2s_raw(sm + (bf ^ 1) * (BS * CF_PREP_STAGE), PREP + (long) kfirst(i + 1) * CF_PREP_STAGE,
+                                    bsz(i + 1) * CF_PREP_STAGE * 8, bar + (bf ^ 1));
+                }
+                unext = lane < NVB ? rec(i + 1)[R_UX + lane] : 0.0;
             }
+            UXB[lane] = ucur;
+            wait(bf);
+            cf_syncwarp();
             double xs = 0.0;
-            if (xs_l) xs = (i == 0) ? x0g[ci] - xg[ci] : rec(i)[R_UX + NUB + ci];
-            wait(0);
+            if (xs_l) xs = (i == 0) ? x0g[ci] - xg[ci] : UXB[NUB + ci];
             CF_NOUNROLL
             for (int j = 0; j < bs; j++) {
                 const double *Mj = ST + j * CF_PREP_STAGE;
                 const int k = k0 + j;
                 double uj = 0.0;
                 if (lane < CF_NU) {
-                    uj = rec(i)[R_UX + CF_NU * (bs - 1 - j) + lane];
+                    uj = UXB[CF_NU * (bs - 1 - j) + lane];
                     ug[k * CF_NU + lane] += uj;
                 }
                 if (xs_l) xg[k * CF_NX + ci] += xs;
+                if (j + 1 == bs) break;     // the next block's state is a QP variable
                 if (lane < CF_MROWS) DS[lane] = lane < CF_NU ? uj : (xs_l ? xs : 0.0);
                 cf_syncwarp();
                 const double *Mc = Mj + ci * CF_MROWS;
@@ -855,10 +914,9 @@ struct CfPcWarpT
                 xs = xs_l ? m2.y + (s0 + s1) : 0.0;
                 cf_syncwarp();
             }
-            if (lane == 0) cf_fence_proxy_async();   // the generic reads of ST precede the next bulk write
-            cf_syncwarp();
         }
         if (xs_l) xg[N * CF_NX + ci] += rec(N2)[R_UX + NUB + ci];
+        cf_syncwarp();
     }
 };
 

@@ -505,6 +505,9 @@ static void (*pc_kernel_for(int wpb, int minb))(const CfParams, const CfBatchVie
     case 402: return cf_pcond_kernel<4, 2, BS>;
     case 205: return cf_pcond_kernel<2, 5, BS>;
     case 303: return cf_pcond_kernel<3, 3, BS>;
+    case 403: return cf_pcond_kernel<4, 3, BS>;
+    case 305: return cf_pcond_kernel<3, 5, BS>;
+    case 404: return cf_pcond_kernel<4, 4, BS>;
     default: return nullptr;
     }
 }

@@ -14,6 +14,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 N = 50
 w = wl.hover_batch(B, N)
 with cf.BatchSolver(B, N, 0.015) as s:
+    s.set_option("qp_cond_N", int(os.environ.get("PCOND", "0")))
     def run(ww):
         ts = []
         for _ in range(3):
