@@ -32,6 +32,13 @@
 #pragma once
 #include "cf_model.h"
 
+#ifndef CF_KSPLIT_LXU
+#define CF_KSPLIT_LXU 1   // Lxu' dx of the forward substitution split over the lane groups
+#endif
+#ifndef CF_KSPLIT_COL
+#define CF_KSPLIT_COL 1   // column products [A B] v split over lane pairs (CfWarpT::col_gemv)
+#endif
+
 // ------------------------------------------------------------------ sizes / layout
 #define CF_MROWS 18                       // rows of [B';A';res_b'] held per stage
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
@@ -519,6 +526,34 @@ struct CfWarpT
     }
 
     // =============================================================== IPM pieces
+    // y[c] = sum_{r < 17} M[r][c] v[r]  (+ M[17][c] when `with_row17`) for the state column c of lanes 4..16, the 18 rows of
+    // a column shared by the lane pair (L, L ^ 16): the state lane takes rows 0..9, its partner (lanes 20..31 and lane 0)
+    // rows 10..17; one exchange combines them.  Five 128-bit loads of M and of v per lane instead of nine, and dependent
+    // chains of 5 instead of 9 multiply-adds (the column products were 21 % of the kernel's shared-memory wavefronts,
+    // profiles/prof_r2_v15_wavefronts.txt).  Mk: staged [B';A';b'] (element (r,c) at c*18 + r), v: 20-double vector.
+    CF_MEM double col_gemv(const double *Mk, const double *v, const bool with_row17) const
+    {
+        const int lp = lane ^ 16;
+        const bool lo = lane >= CF_NU && lane < CF_NV, hi = lp >= CF_NU && lp < CF_NV;
+        const int cc = lo ? lane - CF_NU : (hi ? lp - CF_NU : 0), r0 = lo ? 0 : 10;
+        const double *Mc = Mk + cc * CF_MROWS + r0, *vc = v + r0;
+        double s0 = 0.0, s1 = 0.0;
+        CF_UNROLL
+        for (int rp = 0; rp < 3; rp++) {   // rows 0..5 | 10..15
+            const cf_d2 m2 = cf_ld2(Mc + 2 * rp), v2 = cf_ld2(vc + 2 * rp);
+            s0 += m2.x * v2.x;
+            s1 += m2.y * v2.y;
+        }
+        const cf_d2 m3 = cf_ld2(Mc + 6), v3 = cf_ld2(vc + 6);                       // rows 6, 7 | 16, 17
+        const cf_d2 m4 = cf_ld2(Mc + (lo ? 8 : 6)), v4 = cf_ld2(vc + (lo ? 8 : 6));   // rows 8, 9 | (none)
+        s0 += m3.x * v3.x;
+        s1 += lo ? m3.y * v3.y : (with_row17 ? m3.y : 0.0);
+        s0 += lo ? m4.x * v4.x : 0.0;
+        s1 += lo ? m4.y * v4.y : 0.0;
+        const double part = s0 + s1;
+        return part + cf_shfl(part, lp);
+    }
+
     // One BACKWARD sweep that does, per stage, everything the reference spreads over three passes:
     //   UPDATE_VAR_QP            x_core_qp_ipm_aux.c:220-325   (variables += step length * direction, clipping)
     //   OCP_QP_RES_COMPUTE + _INF_NORM   x_ocp_qp_res.c:334-470,602-637   (residuals of the new iterate, norms, mu)
@@ -648,6 +683,9 @@ struct CfWarpT
                     rg += s0 + s1;
                 }
                 {   // res_b_k = (b_k - x_{k+1}) + [A B] ux_k   (column layout: contiguous; b_k is row 17 of the column)
+#if CF_KSPLIT_COL
+                    const double rb = col_gemv(Mk, UXS, true) - ux_next;
+#else
                     const double *Mc = Mk + ci * CF_MROWS;
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
@@ -659,6 +697,7 @@ struct CfWarpT
                     const cf_d2 m2 = cf_ld2(Mc + 16);
                     s0 += m2.x * UXS[16];
                     const double rb = (m2.y - ux_next) + (s0 + s1);
+#endif
                     cf_syncwarp();   // every lane has read its column: row 17 of the staged block becomes res_b (ROWIN :490)
                     if (xl) {
                         cf_amax(nb, rb);
@@ -919,6 +958,20 @@ struct CfWarpT
             }
             // ---- u-part: du = Luu^-T ( -l_u - Lxu' dx )      TRSV_LTN_MN(nv, nu); input l4 on every lane
             double v;
+#if CF_KSPLIT_LXU
+            {   // the 13 terms of input l4 are spread over the 8 lane groups (lane >> 2 takes states g and g + 8: the factor
+                // rows 4.. are then two contiguous 32-lane loads) and summed by three exchanges, instead of every lane
+                // running through all 13 (20 loads per lane)
+                const int g = lane >> 2;
+                double t = LU[16 + lane] * XS[g];
+                const double t2 = LU[lane < 20 ? 48 + lane : 48] * XS[8 + g];
+                t += (g < 5) ? t2 : 0.0;
+                t += cf_shfl(t, lane ^ 4);
+                t += cf_shfl(t, lane ^ 8);
+                t += cf_shfl(t, lane ^ 16);
+                v = -VS[R_DUX + l4] - t;
+            }
+#else
             {
                 double v0 = -VS[R_DUX + l4], v1 = 0.0;
                 CF_UNROLL
@@ -930,6 +983,7 @@ struct CfWarpT
                 v0 -= LU[16 * 4 + l4] * XS[12];
                 v = v0 + v1;
             }
+#endif
             const double invd = LU[l4 * 4 + l4];   // inverse pivot
             double du = 0.0;
             CF_UNROLL
@@ -979,6 +1033,9 @@ struct CfWarpT
             cf_syncwarp();
             double dxn;
             {
+#if CF_KSPLIT_COL
+                const double sacc = col_gemv(Mk, DS, false), rbk = VS[R_RESB + ci];
+#else
                 const double *Mc = Mk + ci * CF_MROWS;
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
@@ -989,6 +1046,7 @@ struct CfWarpT
                 }
                 s0 += Mc[16] * DS[16];
                 const double sacc = s0 + s1, rbk = VS[R_RESB + ci];
+#endif
                 dxn = xl ? sacc + rbk : 0.0;
                 if (chk) cf_amax(lb, xl ? (rbk - dxn) + sacc : 0.0);
                 if (xl) XS[ci] = dxn;
