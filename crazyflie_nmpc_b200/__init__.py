@@ -106,6 +106,11 @@ def _ptr(a):
     return a.ctypes.data, 0, a
 
 
+def _torch_dtype_is(t, is_int):
+    """float64 (or int32) torch tensor?  Compared by name: torch is not a dependency of this module."""
+    return str(t.dtype) == ("torch.int32" if is_int else "torch.float64")
+
+
 def measure_fp64_peak(device=0):
     """Measured fp64 FMA throughput of the device in TFLOP/s (roofline denominator of bench.py)."""
     v = ctypes.c_double()
@@ -120,6 +125,8 @@ class BatchSolver:
                         | "W" [17] | "W_e" [13] | "lbu" | "ubu" | "lbu0" | "ubu0" [4]   (solver-wide)
                         | "W_batch" [B,17] | "W_e_batch" [B,13] | "lbu_batch" | "ubu_batch" | "lbu0_batch"
                         | "ubu0_batch" [B,4]   (per instance; clear(field) returns to the solver-wide value)
+                        Device-resident sources (CUDA tensors) are copied on the solver's stream: call
+                        set_stream(torch.cuda.current_stream().cuda_stream) first, or synchronise the producing stream.
     solve(n_rti=1)      enqueue RTI steps (asynchronous)
     get(field, stage)   "u"/"x" at a stage, "u_all", "x_all", "status", "qp_iter", "qp_status", "flags", "res"
     """
@@ -174,8 +181,8 @@ class BatchSolver:
         n = int(np.prod(self._expected(field)))
         is_int = field in ("policy", "traj_iter")
         if hasattr(a, "data_ptr"):
-            if a.numel() != n or a.element_size() != (4 if is_int else 8):
-                raise CfnmpcError(f"'{field}' needs {n} {'int32' if is_int else 'float64'} values")
+            if a.numel() != n or not _torch_dtype_is(a, is_int):
+                raise CfnmpcError(f"'{field}' needs {n} {'int32' if is_int else 'float64'} values, got {a.numel()} of {a.dtype}")
         else:
             a = np.ascontiguousarray(a, dtype=np.int32 if is_int else np.float64)
             if a.size != n:
@@ -234,12 +241,23 @@ class BatchSolver:
                   "qp_status": ((B,), np.int32), "flags": ((B,), np.int32), "res": ((B, 4), np.float64),
                   "policy": ((B,), np.int32), "traj_iter": ((B,), np.int32), "motors": ((B, NU), np.int32),
                   "euler": ((B, 3), np.float64), "twist": ((B, 4), np.float64), "x0": ((B, NX), np.float64),
-                  "yref": ((B, N, NY), np.float64), "yref_e": ((B, NX), np.float64), "setpoint": ((B, 3), np.float64)}
+                  "yref": ((B, N, NY), np.float64), "yref_e": ((B, NX), np.float64), "setpoint": ((B, 3), np.float64),
+                  # option "multipliers": per stage, see include/cfnmpc.h
+                  "pi": ((B, NX), np.float64), "lam": ((B, 8), np.float64), "t": ((B, 8), np.float64),
+                  "lam_x0": ((B, NX), np.float64), "pi_all": ((B, N, NX), np.float64), "lam_all": ((B, N, 8), np.float64),
+                  "t_all": ((B, N, 8), np.float64)}
         if field not in shapes:
             raise CfnmpcError(f"unknown field '{field}'")
         shape, dt = shapes[field]
         if out is None:
             out = np.empty(shape, dt)
+        else:   # a caller-provided buffer is written by a raw device copy: size, type and layout must be right
+            n = int(np.prod(shape))
+            if hasattr(out, "data_ptr"):
+                if out.numel() != n or not _torch_dtype_is(out, dt is np.int32) or not out.is_contiguous():
+                    raise CfnmpcError(f"get('{field}', out=...): need a contiguous {np.dtype(dt).name} tensor of {n} elements")
+            elif not (isinstance(out, np.ndarray) and out.size == n and out.dtype == dt and out.flags.c_contiguous):
+                raise CfnmpcError(f"get('{field}', out=...): need a C-contiguous {np.dtype(dt).name} array of {n} elements")
         p, dev, keep = _ptr(out)
         _check(lib().cfnmpc_batch_get(self._h, field.encode(), int(stage), ctypes.c_void_p(p), dev))
         return out
@@ -248,6 +266,8 @@ class BatchSolver:
     def set_trajectory(self, table):
         """Trajectory table [rows,17] (crazyflie_controller/traj/*.txt format) for the Tracking / Hold policies."""
         if hasattr(table, "data_ptr"):
+            if table.dim() != 2 or table.shape[1] != NY or not _torch_dtype_is(table, False):
+                raise CfnmpcError("trajectory table must be a float64 tensor [rows, 17]")
             rows = table.shape[0]
         else:
             table = np.ascontiguousarray(table, dtype=np.float64)

@@ -29,6 +29,9 @@ struct crazyflie_solver_capsule
     std::vector<double> bnd;   // input box per stage, [N][8] = lbu | ubu (ocp_nlp_constraints_bgh.c:653-674)
     std::vector<double> wst;   // weight diagonals per stage, [N+1][17] (ocp_nlp_cost_ls.c:301-331); uploaded once stages differ
     bool wst_used = false;
+    // multipliers of the iterate as ocp_nlp_out carries them (zero until the first feedback; acados_c/ocp_nlp_interface.c:576-590)
+    std::vector<double> pi, lam, t, lam_x0;   // [N][13], [N][8], [N][8], [13] (signed, see include/cfnmpc.h)
+    bool mult_on = false, mult_valid = false;
     double time_tot = 0.0, time_lin = 0.0, time_qp_sol = 0.0;
     double stat[4] = {0, 0, 0, 0};   // SQP_RTI statistics table: stat_m = 2 rows x stat_n = 2 (qp_status, qp_iter), ocp_nlp_sqp_rti.c:264-265,648-649
     ocp_nlp_plan_t plan;
@@ -97,6 +100,9 @@ int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int
     c->N = N;
     c->Ts = Ts;
     c->rti_phase = 0;
+    c->pi.assign((size_t) N * 13, 0.0); c->lam.assign((size_t) N * 8, 0.0); c->t.assign((size_t) N * 8, 0.0); c->lam_x0.assign(13, 0.0);
+    c->mult_on = cfnmpc_batch_set_option(c->batch, "multipliers", 1) == CFNMPC_OK;
+    c->mult_valid = false;
     c->wst.assign((size_t) (N + 1) * 17, 0.0);
     for (int k = 0; k <= N; k++)
         for (int i = 0; i < 17; i++) c->wst[(size_t) k * 17 + i] = k < N ? CfSpec::W[i] : (i < 13 ? CfSpec::W_e[i] : 0.0);
@@ -142,10 +148,17 @@ int crazyflie_acados_update_qp_solver_cond_N(crazyflie_solver_capsule *c, int co
     c->cond_N = cond_N;
     // blocks of up to 3 stages run on the partially condensed kernel (cf_pcond_warp.h); for coarser condensing the QP is
     // solved uncondensed: same solution to the interior-point tolerances, stated on stderr once
+    // (the condensed feedback does not recover the multipliers of the eliminated stages: ocp_nlp_out_get "pi"/"lam"/"t"
+    // then keep the values of the last uncondensed step)
+    if (c->batch) {
+        if (cond_N < c->N) { cfnmpc_batch_set_option(c->batch, "multipliers", 0); c->mult_on = false; }
+    }
     if (c->batch && cfnmpc_batch_set_option(c->batch, "qp_cond_N", cond_N) != CFNMPC_OK) {
         fprintf(stderr, "crazyflie_acados_update_qp_solver_cond_N: %s; solving uncondensed\n", cfnmpc_last_error());
         cfnmpc_batch_set_option(c->batch, "qp_cond_N", 0);
+        cond_N = c->N;
     }
+    if (c->batch && cond_N >= c->N && !c->mult_on) c->mult_on = cfnmpc_batch_set_option(c->batch, "multipliers", 1) == CFNMPC_OK;
     return 0;
 }
 
@@ -195,6 +208,13 @@ int crazyflie_acados_solve(crazyflie_solver_capsule *c)
     rc |= cfnmpc_batch_get(b, "status", 0, &c->status, 0);
     rc |= cfnmpc_batch_get(b, "qp_iter", 0, &c->qp_iter, 0);
     rc |= cfnmpc_batch_get(b, "qp_status", 0, &c->qp_status, 0);
+    if (c->mult_on && !rc && c->status == ACADOS_SUCCESS) {   // a failed QP leaves the duals untouched, like the primal iterate
+        rc |= cfnmpc_batch_get(b, "pi_all", 0, c->pi.data(), 0);
+        rc |= cfnmpc_batch_get(b, "lam_all", 0, c->lam.data(), 0);
+        rc |= cfnmpc_batch_get(b, "t_all", 0, c->t.data(), 0);
+        rc |= cfnmpc_batch_get(b, "lam_x0", 0, c->lam_x0.data(), 0);
+        c->mult_valid = true;
+    }
     double ms = 0.0, ph[2] = {0.0, 0.0};
     rc |= cfnmpc_batch_last_solve_ms(b, &ms);
     rc |= cfnmpc_batch_last_phase_ms(b, ph);
@@ -303,6 +323,27 @@ void ocp_nlp_out_get(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_out *out, int sta
     crazyflie_solver_capsule *c = out->capsule;
     if (!strcmp(field, "x") && stage >= 0 && stage <= c->N) memcpy(value, &c->x[(size_t) stage * 13], 13 * sizeof(double));
     else if (!strcmp(field, "u") && stage >= 0 && stage < c->N) memcpy(value, &c->u[(size_t) stage * 4], 4 * sizeof(double));
+    else if (!strcmp(field, "pi") && stage >= 0 && stage < c->N) memcpy(value, &c->pi[(size_t) stage * 13], 13 * sizeof(double));
+    else if ((!strcmp(field, "lam") || !strcmp(field, "t")) && stage >= 0 && stage < c->N) {
+        // 2 * ni[stage] values, [lower | upper], inputs before states: stage 0 carries the 13 bounds lbx_0 = ubx_0 = x0 whose
+        // multipliers the reference restores after the elimination (x_ocp_qp_red.c:796-840: slacks t_min, multipliers
+        // lam_min except the side the stationarity condition selects)
+        const bool is_lam = field[0] == 'l';
+        const double *src = &(is_lam ? c->lam : c->t)[(size_t) stage * 8];
+        double *v = static_cast<double *>(value);
+        if (stage > 0) memcpy(v, src, 8 * sizeof(double));
+        else {
+            const double fill = c->mult_valid ? 1e-16 : 0.0;
+            for (int i = 0; i < 4; i++) { v[i] = src[i]; v[17 + i] = src[4 + i]; }
+            for (int i = 0; i < 13; i++) {
+                v[4 + i] = fill; v[21 + i] = fill;
+                if (is_lam && c->mult_valid) {
+                    if (c->lam_x0[i] >= 0) v[4 + i] = c->lam_x0[i];
+                    else v[21 + i] = -c->lam_x0[i];
+                }
+            }
+        }
+    }
 }
 
 void ocp_nlp_solver_opts_set(ocp_nlp_config *config, void *, const char *field, void *value)

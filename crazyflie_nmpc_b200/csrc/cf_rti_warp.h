@@ -145,7 +145,20 @@ struct CfBatchView
     // used): ocp_nlp_cost_model_set addresses one stage at a time (ocp_nlp_cost_ls.c:301-331); null = the weights of
     // CfParams / the per-instance arrays.  Only read by the general kernel variants (VDT) and the condensed feedback.
     const double *W_stage;
+    // optional per-instance multiplier output (null = off; option "multipliers"): what ocp_nlp_out_get "pi" / "lam" / "t"
+    // hand out after a step (acados_c/ocp_nlp_interface.c:576-590; full-step duals, ocp_nlp_common.c:2917-2925).  Layout
+    // per instance (mult_stride doubles): pi [N][13] | lam [N][8] = lower(4) | upper(4) of the input box | t [N][8] |
+    // lam_x0 [13]: SIGNED multiplier of the eliminated constraint x_0 = x0 (>= 0: lower-bound multiplier, < 0: minus the
+    // upper-bound one, x_ocp_qp_red.c:820-840) | A_0 [13][13] scratch (the stage-0 state rows, saved before the
+    // elimination drops them; element (c, r) = d x1_c / d x0_r at c*13 + r)
+    double *mult;
+    long mult_stride;
 };
+static inline
+#if !defined(CF_SIMT_EMU)
+    __host__ __device__
+#endif
+    long cf_mult_stride(int N) { return ((long) N * 29 + 13 + 169 + 1) & ~1L; }
 // layout of the prepared linearisation of one instance (doubles)
 #define CF_PREP_STAGE (CF_MSZ + 18)
 static inline
@@ -217,6 +230,7 @@ struct CfWarpT
     const double *DT;  // per-interval time steps (VDT only)
     const double *BST; // per-stage input boxes (null: the boxes of P)
     const double *WST; // per-stage weights (general variants only; null: the weights of P)
+    double *A0S;       // where the stage-0 state rows go before the x0 elimination drops them (null: not wanted)
     // lane constants
     double Hs, HN;     // Hessian diagonal for this lane's variable (stage / terminal)
     double W2;         // (sqrt(w))^2 of this lane's stage weight: the stage Hessian is dt_k * W2
@@ -229,7 +243,7 @@ struct CfWarpT
     CF_MEM void bind(const CfParams *P_, const CfParams *PG_, double *slot, double *sm_, double *prep_, const double *dts_)
     {
         P = P_; PG = PG_; N = PG_->N; sm = sm_; lane = cf_lane();
-        PREP = prep_; DT = dts_; BST = nullptr; WST = nullptr;
+        PREP = prep_; DT = dts_; BST = nullptr; WST = nullptr; A0S = nullptr;
         bar = reinterpret_cast<uint64_t *>(sm_ + CF_SM_BAR);
         par = 0;
         CfScratchLayout s = cf_scratch_layout(N);
@@ -433,6 +447,7 @@ struct CfWarpT
         const double xbar = xl ? (x0g[lane - CF_NU] - xg[lane - CF_NU]) : 0.0;
         CF_NOUNROLL
         for (int i = 0; i < CF_NX; i++) {
+            if (A0S && xl) A0S[i * CF_NX + lane - CF_NU] = Mrow[i * CF_MROWS];   // kept for the x0 multipliers
             const double tot = cf_warp_sum(xl ? Mrow[i * CF_MROWS] * xbar : 0.0);
             if (lane == 17) MS[i * CF_MROWS + 17] = tot + MS[i * CF_MROWS + 17];
             else if (xl) Mrow[i * CF_MROWS] = 0.0;
@@ -1328,6 +1343,7 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     w.par = par;
     w.BST = bv.bnd_stage;
     w.set_stage_weights(bv.W_stage);
+    if (PH != CF_PH_PREPARATION && bv.mult) w.A0S = bv.mult + (long) inst * bv.mult_stride + (long) Pg->N * 29 + CF_NX;
     const int N = Pg->N;
     double *xg = bv.x + (long) inst * (N + 1) * CF_NX;
     double *ug = bv.u + (long) inst * N * CF_NU;
@@ -1362,6 +1378,27 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
         const int lane = w.lane;
         const bool ul = lane < CF_NU, xl = lane >= CF_NU && lane < CF_NV;
         const int i = xl ? lane - CF_NU : 0;
+        if (bv.mult) {
+            // full-step duals (ocp_nlp_common.c:2917-2925): the multipliers of the QP solution, and for the eliminated
+            // x_0 = x0 what OCP_QP_RESTORE_EQ_DOF recovers from the stationarity condition of the unreduced stage 0
+            // (x_ocp_qp_red.c:820-840): q_0 + Q_0 xbar + A_0' pi_0
+            double *mo = bv.mult + (long) inst * bv.mult_stride;
+            double *pi_o = mo, *lam_o = mo + (long) N * CF_NX, *t_o = lam_o + (long) N * 8, *l0 = t_o + (long) N * 8;
+            CF_NOUNROLL
+            for (int k = 0; k < N; k++) {
+                if (lane < CF_NX) pi_o[k * CF_NX + lane] = w.rec(k + 1)[R_PI + lane];
+                if (lane < 8) { lam_o[k * 8 + lane] = w.rec(k)[R_LAM + lane]; t_o[k * 8 + lane] = w.rec(k)[R_T + lane]; }
+            }
+            if (xl && N > 0) {
+                const double xbar = x0g[i] - xg[i];
+                const double q0 = (w.wgt(0, i) * (xg[i] - yrefg[i])) * w.dt(0);
+                const double *a0 = l0 + CF_NX;
+                double s0 = 0.0;
+                CF_NOUNROLL
+                for (int c = 0; c < CF_NX; c++) s0 += a0[c * CF_NX + i] * w.rec(1)[R_PI + c];
+                l0[i] = (q0 + w.hess(0) * xbar) + s0;
+            }
+        }
         if (xl) xg[i] += x0g[i] - xg[i];
         if (ul && N > 0) ug[lane] += w.rec(0)[R_UX + lane];
         CF_NOUNROLL

@@ -167,6 +167,7 @@ struct cfnmpc_batch
     double *d_dts = nullptr, *d_prep = nullptr;
     double *h_dts = nullptr;          // host copy of the time grid (N doubles)
     double *d_bst = nullptr;          // per-stage input boxes [N][8] (allocated on first use)
+    double *d_mult = nullptr;         // multiplier output [B][cf_mult_stride(N)] (option "multipliers")
     double *d_wst = nullptr;          // per-stage weights [N+1][17] (allocated on first use); while set, the general kernels run
     bool vdt_grid = false, wst = false, prepared = false;   // non-uniform time grid / per-stage weights: the general kernels
     bool vdt = false;                                        // = vdt_grid || wst
@@ -194,7 +195,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
                     h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter,
                     h->d_policy, h->d_titer, h->d_motors, h->d_setpoint, h->d_traj, h->d_euler, h->d_twist,
-                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep, h->d_bst, h->d_wst};
+                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep, h->d_bst, h->d_wst, h->d_mult};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -357,6 +358,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     bv.W_b = bv.WN_b = bv.lbu_b = bv.ubu_b = bv.lbu0_b = bv.ubu0_b = nullptr;
     bv.prof = nullptr;
     bv.dts = h->d_dts; bv.prep = nullptr; bv.prep_stride = cf_prep_stride(N); bv.bnd_stage = nullptr; bv.W_stage = nullptr;
+    bv.mult = nullptr; bv.mult_stride = cf_mult_stride(N);
     CKH(cudaStreamSynchronize(h->stream));
 #undef CKH
     *out = h;
@@ -517,6 +519,7 @@ static void (*pc_kernel_for(int wpb, int minb))(const CfParams, const CfBatchVie
 static int set_cond_N(cfnmpc_batch *h, int N2)
 {
     if (N2 <= 0 || N2 >= h->N) { h->cond_N = 0; return CFNMPC_OK; }
+    if (h->bv.mult) return fail(CFNMPC_EINVAL, "qp_cond_N: partial condensing does not produce the multiplier output (option multipliers)");
     const CfPcBlocks b = cf_pc_blocks(h->N, N2);
     const int bs = b.n_big ? b.bs0 + 1 : b.bs0;
     if (bs > 3) return fail(CFNMPC_EINVAL, "qp_cond_N: blocks of more than 3 stages are not implemented (need qp_cond_N >= ceil(N / 3))");
@@ -560,6 +563,17 @@ extern "C" int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int 
     if (!strcmp(option, "lin_res_check")) h->P.lin_res_check = value != 0;
     else if (!strcmp(option, "two_kernels")) h->two_kernels = value != 0;
     else if (!strcmp(option, "max_ipm_iter")) h->P.max_ipm_iter = (value > 0 && value < CF_ITER_MAX) ? value : CF_ITER_MAX;
+    else if (!strcmp(option, "multipliers")) {
+        // keep pi / lam / t of every solved instance (ocp_nlp_out_get "pi" / "lam" / "t"): 8 (29 N + 182) bytes per instance
+        if (value && h->cond_N) return fail(CFNMPC_EINVAL, "option multipliers: not available with partial condensing (qp_cond_N < N)");
+        CK(cudaSetDevice(h->device));
+        if (value && !h->d_mult) {
+            const size_t bytes = (size_t) h->B * h->bv.mult_stride * 8;
+            CK(cudaMalloc(&h->d_mult, bytes));
+            CK(cudaMemsetAsync(h->d_mult, 0, bytes, h->stream));
+        }
+        h->bv.mult = value ? h->d_mult : nullptr;
+    }
     else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_set_option: unknown option '") + option + "'");
     return CFNMPC_OK;
 }
@@ -622,7 +636,8 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
 static int ensure_prep_store(cfnmpc_batch *h)
 {
     if (!h->d_prep) {
-        const size_t bytes = (size_t) h->B * h->bv.prep_stride * 8;
+        size_t bytes = (size_t) h->B * h->bv.prep_stride * 8;
+        if (getenv("CFNMPC_TEST_FAIL_PREP_ALLOC")) bytes = (size_t) 1 << 60;   // tests: a real failed allocation
         cudaError_t e = cudaMalloc(&h->d_prep, bytes);
         if (e != cudaSuccess) {
             h->d_prep = nullptr;
@@ -758,7 +773,26 @@ extern "C" int cfnmpc_batch_get(cfnmpc_batch *h, const char *field, int stage, v
     CK(cudaSetDevice(h->device));
     const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const bool is_u = !strcmp(field, "u"), is_x = !strcmp(field, "x");
-    if (is_u || is_x) {
+    const bool is_pi = !strcmp(field, "pi"), is_lam = !strcmp(field, "lam"), is_t = !strcmp(field, "t"), is_l0 = !strcmp(field, "lam_x0");
+    const bool all_pi = !strcmp(field, "pi_all"), all_lam = !strcmp(field, "lam_all"), all_t = !strcmp(field, "t_all");
+    if (all_pi || all_lam || all_t) {   // every stage at once: [B][N][13] / [B][N][8]
+        if (!h->bv.mult) return fail(CFNMPC_ESTATE, "cfnmpc_batch_get: set option multipliers before the solve");
+        const size_t w = (size_t) h->N * (all_pi ? CF_NX : 8) * 8;
+        const long sec = all_pi ? 0 : (all_lam ? (long) h->N * 13 : (long) h->N * 21);
+        CK(cudaMemcpy2DAsync(dst, w, h->d_mult + sec, (size_t) h->bv.mult_stride * 8, w, h->B, kind, h->stream));
+    } else if (is_pi || is_lam || is_t || is_l0) {
+        // multipliers of the iterate: pi_k [B][13]; lam_k / t_k [B][8] = lower(4) | upper(4) of the input box of stage k;
+        // lam_x0 [B][13] signed multiplier of x_0 = x0 (CfBatchView::mult)
+        if (!h->bv.mult) return fail(CFNMPC_ESTATE, "cfnmpc_batch_get: set option multipliers before the solve");
+        if (stage < 0 || stage >= (is_l0 ? 1 : h->N)) return fail(CFNMPC_EINVAL, "cfnmpc_batch_get: stage out of range");
+        const int w = (is_pi || is_l0) ? CF_NX : 8;
+        const long sec = is_pi ? 0 : (is_lam ? (long) h->N * 13 : (is_t ? (long) h->N * 21 : (long) h->N * 29));
+        const int n = h->B * w;
+        cf_gather_stage_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_mult + sec, h->d_stage, h->B, (int) h->bv.mult_stride, stage, w);
+        CK(cudaGetLastError());
+        h->launches++;
+        CK(cudaMemcpyAsync(dst, h->d_stage, (size_t) n * 8, kind, h->stream));
+    } else if (is_u || is_x) {
         const int w = is_u ? CF_NU : CF_NX, nst = is_u ? h->N : h->N + 1;
         if (stage < 0 || stage >= nst) return fail(CFNMPC_EINVAL, "cfnmpc_batch_get: stage out of range");
         const int n = h->B * w;

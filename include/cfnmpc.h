@@ -119,7 +119,11 @@ int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field);
  *                   implemented (qp_cond_N >= ceil(N/3); coarser values return CFNMPC_EINVAL).  Results equal the
  *                   reference's at the same qp_cond_N (~1e-13) and its qp_cond_N = N results to the interior-point
  *                   tolerances.  The step runs as preparation kernel + condensed feedback kernel; "lin_res_check" is not
- *                   available on this path. */
+ *                   available on this path.
+ *   "multipliers"   (default 0) 1: keep the multipliers of every solved instance = what ocp_nlp_out_get "pi" / "lam" / "t"
+ *                   hand out after a step in the reference (acados_c/ocp_nlp_interface.c:576-590; full-step duals,
+ *                   ocp_nlp_common.c:2917-2925), 8 (29 N + 182) bytes per instance; read them with cfnmpc_batch_get
+ *                   "pi", "lam", "t", "lam_x0".  Not available together with "qp_cond_N" < N. */
 int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int value);
 
 /* Enqueue n_rti consecutive RTI steps (preparation + feedback) for every instance,
@@ -155,6 +159,14 @@ int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, const double
  *                        "lin_res_check"; 0 otherwise); bit 2: cfnmpc_batch_solve_from_host gave up waiting for this
  *                        instance's inputs (5 s) and solved it with whatever was in device memory
  *   "res"      double [B][4]  final QP residual inf-norms (stationarity, dynamics, bounds, complementarity)
+ * and, with the option "multipliers" set before the solve (instances whose QP failed keep their previous values):
+ *   "pi"       double [B][13]  multiplier of the dynamics x_{stage+1} = phi(x_stage, u_stage), stage 0..N-1
+ *   "lam"      double [B][8]   multipliers of the input box of `stage`: lower(4) | upper(4), stage 0..N-1
+ *   "t"        double [B][8]   the slacks of those bounds
+ *   "pi_all" [B][N][13], "lam_all" [B][N][8], "t_all" [B][N][8]: every stage at once (stage ignored)
+ *   "lam_x0"   double [B][13]  signed multiplier of the eliminated constraint x_0 = x0 (stage must be 0): a value v >= 0
+ *                              is the lower-bound multiplier of the reference's lbx_0 (upper one 1e-16), v < 0 means the
+ *                              upper-bound multiplier is -v (external/hpipm/ocp_qp/x_ocp_qp_red.c:820-840)
  * Copies to host pointers synchronise the stream before returning. */
 int cfnmpc_batch_get(cfnmpc_batch *h, const char *field, int stage, void *dst, int dst_on_device);
 

@@ -808,6 +808,20 @@ static void ipm_solve(ipm *w, cfo_info *info)
     for (int i = 0; i < 4; i++) info->res[i] = w->res_max[i];
 }
 
+/* Multipliers of the iterate after the next cfo_rti calls with this N, in the layout of oracle/ref_harness.c:
+ * cfref_get_multipliers (pi[N][13]; lam / t: stage 0 2*17 = [lbu lbx | ubu ubx], stages 1..N-1 2*4).  Global, test use
+ * only; N = 0 switches the recording off. */
+static int g_mult_N = 0;
+static double g_mult_pi[CFO_MAX_N * NX], g_mult_lam[2 * NV + 2 * NU * CFO_MAX_N], g_mult_t[2 * NV + 2 * NU * CFO_MAX_N];
+void cfo_record_multipliers(int N) { g_mult_N = (N > 0 && N <= CFO_MAX_N) ? N : 0; }
+void cfo_last_multipliers(double *pi, double *lam, double *t)
+{
+    const int N = g_mult_N;
+    if (pi) memcpy(pi, g_mult_pi, sizeof(double) * N * NX);
+    if (lam) memcpy(lam, g_mult_lam, sizeof(double) * (2 * NV + 2 * NU * (N - 1)));
+    if (t) memcpy(t, g_mult_t, sizeof(double) * (2 * NV + 2 * NU * (N - 1)));
+}
+
 int cfo_rti(int N, double Ts, const cfo_params *p_, const double *x0, const double *yref,
             const double *yref_e, double *x, double *u, cfo_info *info_, double *dux_out, double *dpi_out)
 {
@@ -877,6 +891,33 @@ int cfo_rti(int N, double Ts, const cfo_params *p_, const double *x0, const doub
     if (dpi_out) for (int k = 0; k < N; k++) for (int i = 0; i < NX; i++) dpi_out[NX * k + i] = w.s[k].pi[i];
     int status = 0;
     if (info->qp_status == 0 || info->qp_status == 1) {
+        if (g_mult_N == N) {
+            /* full-step duals (ocp_nlp_common.c:2917-2925) in the layout ocp_nlp_out_get hands them out; the multipliers
+             * of the eliminated x_0 = x0 from the stationarity of the unreduced stage 0 (x_ocp_qp_red.c:820-840):
+             * tmp = q_0 + Q_0 xbar + A_0' pi_0; tmp >= 0 -> lower-bound multiplier, else minus the upper-bound one */
+            int ol = 0;
+            for (int k = 0; k < N; k++) {
+                for (int i = 0; i < NX; i++) g_mult_pi[NX * k + i] = w.s[k].pi[i];
+                const int nb = k == 0 ? NV : NU;
+                for (int i = 0; i < NU; i++) {
+                    g_mult_lam[ol + i] = w.s[k].lam[i]; g_mult_lam[ol + nb + i] = w.s[k].lam[NU + i];
+                    g_mult_t[ol + i] = w.s[k].t[i]; g_mult_t[ol + nb + i] = w.s[k].t[NU + i];
+                }
+                if (k == 0) {
+                    const double *M = BAbt, *g = rqz;
+                    for (int i = 0; i < NX; i++) {
+                        double r = sqrt(WK(p_, 0, N, i));
+                        double tmp = g[NU + i] + (DTK(0) * (r * r)) * xbar[i];
+                        for (int c = 0; c < NX; c++) tmp += M[(NU + i) * NX + c] * w.s[0].pi[c];
+                        g_mult_lam[NU + i] = LAM_MIN; g_mult_lam[NV + NU + i] = LAM_MIN;
+                        g_mult_t[NU + i] = T_MIN; g_mult_t[NV + NU + i] = T_MIN;
+                        if (tmp >= 0) g_mult_lam[NU + i] = tmp;
+                        else g_mult_lam[NV + NU + i] = -tmp;
+                    }
+                }
+                ol += 2 * nb;
+            }
+        }
         for (int i = 0; i < NU; i++) u[i] += w.s[0].ux[i];
         for (int i = 0; i < NX; i++) x[i] += xbar[i];
         for (int k = 1; k <= N; k++) {

@@ -70,12 +70,27 @@ class Port:
         L.cfo_ode.argtypes = [_dp, _dp, _dp]
         L.cfo_default_params.argtypes = [ctypes.POINTER(CfoParams)]
         L.cfo_set_iter_max.argtypes = [ctypes.c_int]
+        L.cfo_record_multipliers.argtypes = [ctypes.c_int]
+        L.cfo_last_multipliers.argtypes = [_dp, _dp, _dp]
         L.cfo_set_stage_weights.argtypes = [_dp, ctypes.c_int]
         L.cfo_set_time_steps.argtypes = [_dp, ctypes.c_int]
         L.cfo_set_stage_bounds.argtypes = [_dp, ctypes.c_int]
         L.cfo_rti_split.restype = ctypes.c_int
         L.cfo_rti_split.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(CfoParams), _dp, _dp, _dp, _dp, _dp, _dp,
                                     ctypes.POINTER(CfoInfo)]
+
+    def record_multipliers(self, N=0):
+        """Keep the multipliers of the iterate after the next rti() calls with horizon N (0: off); global in the checker."""
+        self.lib.cfo_record_multipliers(int(N))
+        self._mult_N = int(N)
+
+    def multipliers(self):
+        """(pi [N,13], lam0 [2,17], lam [N-1,2,4], t0 [2,17], t [N-1,2,4]) of the last rti(); lam = [lower | upper]."""
+        N = self._mult_N
+        pi, lam, t = np.zeros((N, NX)), np.zeros(2 * NV + 2 * NU * (N - 1)), np.zeros(2 * NV + 2 * NU * (N - 1))
+        self.lib.cfo_last_multipliers(_P(pi), _P(lam), _P(t))
+        return (pi, lam[:2 * NV].reshape(2, NV), lam[2 * NV:].reshape(N - 1, 2, NU),
+                t[:2 * NV].reshape(2, NV), t[2 * NV:].reshape(N - 1, 2, NU))
 
     def set_iter_max(self, n=50):
         """qp_iter_max of the interior-point loop (global in the checker; 50 = the reference configuration)."""

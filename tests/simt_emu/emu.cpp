@@ -198,6 +198,11 @@ static void run_warp(void (*fn)(void *), void *arg)
 }
 }  // namespace cfemu
 
+// multiplier output [B][cf_mult_stride(N)] for the next runs (NULL: off), see CfBatchView::mult
+static double *g_mult = nullptr;
+extern "C" void cfemu_set_mult(double *buf) { g_mult = buf; }
+extern "C" long cfemu_mult_stride(int N) { return cf_mult_stride(N); }
+
 struct Job
 {
     const CfParams *P;
@@ -261,7 +266,8 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
     P.Ts = Ts; P.N = N; P.max_ipm_iter = max_ipm_iter > 0 ? max_ipm_iter : CF_ITER_MAX;
     P.lin_res_check = 1; P.pad_ = 0;
     const long stride = cf_scratch_layout(N).total;
-    CfBatchView bv;
+    CfBatchView bv = {};
+    bv.mult = g_mult; bv.mult_stride = cf_mult_stride(N);
     bv.B = B; bv.first = 0; bv.ready = nullptr; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
     bv.qp_iter = qp_iter; bv.qp_status = qp_status; bv.flags = flags; bv.res = res; bv.scratch = nullptr;
     bv.scratch_stride = stride; bv.counter = nullptr;
@@ -311,7 +317,8 @@ extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int
     P.Ts = dtv[0]; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = 1; P.pad_ = 0;
     const long stride = cf_scratch_layout(N).total, pstride = cf_prep_stride(N);
     std::vector<double> prep((size_t) B * pstride + 2, std::nan(""));
-    CfBatchView bv;
+    CfBatchView bv = {};
+    bv.mult = g_mult; bv.mult_stride = cf_mult_stride(N);
     memset(&bv, 0, sizeof bv);
     bv.B = B; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
     bv.qp_iter = qp_iter; bv.qp_status = qp_status; bv.flags = flags; bv.res = res; bv.scratch_stride = stride;
@@ -393,7 +400,8 @@ extern "C" int cfemu_rti_pcond(int B, int N, double Ts, int N2, const double *pa
     const int smn = smd > CF_SM_DOUBLES ? smd : CF_SM_DOUBLES;
     std::vector<double> dtv(N, Ts);
     std::vector<double> prep((size_t) B * pstride + 2, std::nan(""));
-    CfBatchView bv;
+    CfBatchView bv = {};
+    bv.mult = g_mult; bv.mult_stride = cf_mult_stride(N);
     memset(&bv, 0, sizeof bv);
     bv.B = B; bv.x0 = x0; bv.yref = yref; bv.yref_e = yref_e; bv.x = x; bv.u = u; bv.status = status;
     bv.qp_iter = qp_iter; bv.qp_status = qp_status; bv.flags = flags; bv.res = res; bv.scratch_stride = stride;

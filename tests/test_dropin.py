@@ -123,6 +123,22 @@ def test_capsule_api_through_ctypes(port):
     xo, uo = w["x_init"][0].copy(), w["u_init"][0].copy()
     st, info = port.rti(N, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], xo, uo)
     assert np.abs(x - xo).max() < 1e-8 and np.abs(u - uo).max() < 1e-8 and abs(qi.value - info.qp_iter) <= 1
+    # multipliers of the iterate (acados_c/ocp_nlp_interface.c:576-590), incl. the restored ones of lbx_0 = ubx_0 = x0
+    port.record_multipliers(N)
+    try:
+        xm, um = w["x_init"][0].copy(), w["u_init"][0].copy()
+        port.rti(N, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], xm, um)
+        ppi, pl0, pl, pt0, pt = port.multipliers()
+    finally:
+        port.record_multipliers(0)
+    pi, lam0, t0, lam, t = np.zeros((N, 13)), np.zeros(34), np.zeros(34), np.zeros((N, 8)), np.zeros((N, 8))
+    for k in range(N):
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"pi", P(pi[k]))
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"lam", P(lam0) if k == 0 else P(lam[k]))
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"t", P(t0) if k == 0 else P(t[k]))
+    assert np.abs(pi - ppi).max() < 1e-8 * (1 + np.abs(ppi).max())
+    assert np.abs(lam0.reshape(2, 17) - pl0).max() < 1e-8 * (1 + np.abs(pl0).max()) and np.abs(t0.reshape(2, 17) - pt0).max() < 1e-7
+    assert np.abs(lam[1:].reshape(N - 1, 2, 4) - pl).max() < 1e-8 * (1 + np.abs(pl).max()) and np.abs(t[1:].reshape(N - 1, 2, 4) - pt).max() < 1e-7
     # statistics getters of the SQP_RTI module (ocp_nlp_sqp_rti.c:1361-1425)
     t_tot, t_lin, t_qp = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
     L.ocp_nlp_get(cfg, sol, b"time_tot", ctypes.byref(t_tot))

@@ -670,3 +670,60 @@ def test_per_stage_weights(port, ref):
                     assert np.array_equal(s.get("u_all"), d["u"])
     finally:
         port.set_stage_weights(None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("two_kernels", [1, 0])
+def test_multiplier_output(port, two_kernels):
+    """Option "multipliers": pi / lam / t and the restored multipliers of x_0 = x0 of every instance against the port
+    (pinned to the reference's ocp_nlp_out_get values: tests/test_oracle_golden.py::test_port_multipliers_match_reference),
+    on the two-kernel and the fused path; switching the option on does not change the iterate."""
+    N, B = 50, 12
+    w = wl.helix_batch(B, N, seed=9)
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("two_kernels", two_kernels)
+        s.set_problem(w).solve(1)
+        x_ref = s.get("x_all")
+        with pytest.raises(cf.CfnmpcError):
+            s.get("pi", 0)
+        s.set_option("multipliers", 1)
+        s.set_problem(w).solve(1)
+        assert np.array_equal(s.get("x_all"), x_ref)
+        pi_all, lam_all, t_all, l0 = s.get("pi_all"), s.get("lam_all"), s.get("t_all"), s.get("lam_x0", 0)
+        assert np.array_equal(s.get("pi", 7), pi_all[:, 7]) and np.array_equal(s.get("lam", 3), lam_all[:, 3])
+        assert np.array_equal(s.get("t", N - 1), t_all[:, N - 1])
+        with pytest.raises(cf.CfnmpcError):
+            s.set_option("qp_cond_N", 25)
+    port.record_multipliers(N)
+    try:
+        for i in range(B):
+            x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+            port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u)
+            pi, pl0, pl, pt0, pt = port.multipliers()
+            assert np.abs(pi_all[i] - pi).max() < 1e-9 * (1 + np.abs(pi).max())
+            la, ta = lam_all[i].reshape(N, 2, 4), t_all[i].reshape(N, 2, 4)
+            assert np.abs(la[1:] - pl).max() < 1e-9 * (1 + np.abs(pl).max()) and np.abs(ta[1:] - pt).max() < 1e-8
+            assert np.abs(la[0] - pl0[:, :4]).max() < 1e-9 * (1 + np.abs(pl0).max()) and np.abs(ta[0] - pt0[:, :4]).max() < 1e-8
+            signed = np.where(pl0[0, 4:] > 1e-16, pl0[0, 4:], -pl0[1, 4:])
+            assert np.abs(l0[i] - signed).max() < 1e-9 * (1 + np.abs(signed).max())
+    finally:
+        port.record_multipliers(0)
+
+
+@pytest.mark.gpu
+def test_fused_fallback_when_the_prepared_store_cannot_be_allocated(monkeypatch):
+    """No room for the per-instance linearisation store: the step falls back to the fused kernel and the FIRST solve
+    already succeeds (the failed allocation must not surface as the launch's error), same results bit for bit."""
+    N, B = 20, 48
+    w = wl.helix_batch(B, N, seed=2)
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("two_kernels", 0)
+        s.set_problem(w).solve(1)
+        x0, u0, st0 = s.get("x_all"), s.get("u_all"), s.get("status")
+    monkeypatch.setenv("CFNMPC_TEST_FAIL_PREP_ALLOC", "1")
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_problem(w).solve(1)      # two_kernels is the default: the allocation fails inside this call
+        assert s.info("two_kernels") == 0
+        assert np.array_equal(s.get("x_all"), x0) and np.array_equal(s.get("u_all"), u0) and np.array_equal(s.get("status"), st0)
+        with pytest.raises(cf.CfnmpcError):
+            s.prepare()                # the split phases need the store: a clean error, not a crash

@@ -188,3 +188,26 @@ def test_reference_library_reproduces_phase_golden(ref, gold_phases):
             s.rti(g[f"{name}_x0_fb"][i], g[f"{name}_yref"][i], g[f"{name}_yref_e"][i], x2, u2)
             s.close()
             assert np.array_equal(x, x2) and np.array_equal(u, u2)
+
+
+def test_port_multipliers_match_reference(port, ref):
+    """pi / lam of the iterate as ocp_nlp_out_get hands them out, incl. the multipliers OCP_QP_RESTORE_EQ_DOF recovers for
+    the eliminated x_0 = x0 (x_ocp_qp_red.c:820-840): port against the reference's own code."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    N = 20
+    w = wl.helix_batch(4, N, seed=5)
+    port.record_multipliers(N)
+    rs = ref.solver(N, TS)
+    try:
+        for i in range(4):
+            x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+            xr, ur = x.copy(), u.copy()
+            port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u)
+            pi, l0, l, t0, t = port.multipliers()
+            rs.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)
+            rpi, rl0, rl = rs.multipliers()
+            assert np.abs(pi - rpi).max() < 1e-12 * (1 + np.abs(rpi).max())
+            assert np.abs(l0 - rl0).max() < 1e-12 * (1 + np.abs(rl0).max()) and np.abs(l - rl).max() < 1e-12 * (1 + np.abs(rl).max())
+    finally:
+        port.record_multipliers(0)
+        rs.close()

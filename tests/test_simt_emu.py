@@ -372,3 +372,45 @@ def test_emulated_kernel_flags_where_the_reference_nets_fire(emu, edge):
     assert (r["flags"][nf:] == 0).all() and (r["status"][nf:] == 0).all() and (r["qp_status"][nf:] == 0).all()
     assert rel_err(r["u"][nf:], edge["adv_u"][calm]) < 1e-6
     assert rel_err(r["x"][nf:][:, XSEL], edge["adv_xsel"][calm]) < 1e-6
+
+
+def test_emulated_multiplier_output_matches_port(gold, port):
+    """pi / lam / t of the iterate and the restored multipliers of x_0 = x0 (ocp_nlp_out_get "pi"/"lam"/"t",
+    x_ocp_qp_red.c:820-840) from the kernel source against the port (itself pinned to the reference: test_oracle_golden)."""
+    subprocess.run([sys.executable, os.path.join(HERE, "simt_emu", "build.py")], check=True)
+    L = ctypes.CDLL(os.path.join(HERE, "simt_emu", "libcfemu.so"))
+    L.cfemu_rti_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, ctypes.c_int, _dp, _dp, _dp, _dp, _dp,
+                                  _ip, _ip, _ip, _ip, _dp, _dp, ctypes.c_int]
+    L.cfemu_set_mult.argtypes = [_dp]
+    L.cfemu_mult_stride.restype = ctypes.c_long
+    N, B = 50, 3
+    w = batch(gold, "helix", B)
+    stride = L.cfemu_mult_stride(N)
+    mult = np.full((B, stride), np.nan)
+    x, u = w["x_init"].copy(), w["u_init"].copy()
+    st, it, qs, fl = [np.zeros(B, np.int32) for _ in range(4)]
+    res = np.zeros((B, 4))
+    P = lambda a: a.ctypes.data_as(_dp)
+    I = lambda a: a.ctypes.data_as(_ip)
+    L.cfemu_set_mult(P(mult))
+    try:
+        L.cfemu_rti_batch(B, N, TS, None, 0, P(w["x0"]), P(w["yref"]), P(w["yref_e"]), P(x), P(u), I(st), I(it), I(qs), I(fl), P(res), None, 2)
+    finally:
+        L.cfemu_set_mult(None)
+    port.record_multipliers(N)
+    try:
+        for i in range(B):
+            xo, uo = w["x_init"][i].copy(), w["u_init"][i].copy()
+            port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], xo, uo)
+            pi, l0, l, t0, t = port.multipliers()
+            m = mult[i]
+            k_pi, k_lam, k_t = m[:N * 13].reshape(N, 13), m[N * 13:N * 21].reshape(N, 2, 4), m[N * 21:N * 29].reshape(N, 2, 4)
+            k_l0 = m[N * 29:N * 29 + 13]
+            sc = 1 + np.abs(pi).max()
+            assert np.abs(k_pi - pi).max() / sc < 1e-9
+            assert np.abs(k_lam[1:] - l).max() < 1e-9 * (1 + np.abs(l).max()) and np.abs(k_t[1:] - t).max() < 1e-9 * 23
+            assert np.abs(k_lam[0] - l0[:, :4]).max() < 1e-9 * (1 + np.abs(l0).max()) and np.abs(k_t[0] - t0[:, :4]).max() < 1e-9 * 23
+            signed = np.where(l0[0, 4:] > 1e-16, l0[0, 4:], -l0[1, 4:])
+            assert np.abs(k_l0 - signed).max() < 1e-9 * (1 + np.abs(signed).max())
+    finally:
+        port.record_multipliers(0)

@@ -68,20 +68,59 @@ def stub_modules():
     return {"casadi": casadi, "acados_template": at}
 
 
+ALLOWED_IMPORTS = {"casadi", "acados_template", "export_ode_model", "numpy", "scipy", "scipy.linalg", "math"}
+FORBIDDEN_NAMES = {"exec", "eval", "compile", "open", "__import__", "input", "globals", "locals", "vars", "getattr", "setattr",
+                   "delattr", "breakpoint", "exit", "quit", "os", "sys", "subprocess", "shutil", "socket", "pathlib", "importlib",
+                   "ctypes", "pickle", "builtins"}
+
+
+def vetted_source(path):
+    """The two OCP description scripts come from an untrusted tree and are executed to obtain the symbolic model: before
+    that, their syntax tree is checked -- imports outside ALLOWED_IMPORTS are dropped, no use of FORBIDDEN_NAMES, no access to
+    dunder attributes, no `with` / `try` / class / async / lambda / global constructs.  Anything else aborts the
+    generation (the committed csrc/cf_spec_generated.h stays the source of truth)."""
+    import ast
+    src = open(path).read()
+    tree = ast.parse(src, path)
+    banned = (ast.With, ast.AsyncWith, ast.Try, ast.ClassDef, ast.AsyncFunctionDef, ast.Lambda, ast.Global, ast.Nonlocal,
+              ast.Await, ast.Yield, ast.YieldFrom, ast.Delete, ast.Raise)
+    for node in ast.walk(tree):
+        bad = None
+        if isinstance(node, banned):
+            bad = type(node).__name__
+        elif isinstance(node, ast.Name) and node.id in FORBIDDEN_NAMES:
+            bad = node.id
+        elif isinstance(node, ast.Attribute) and node.attr.startswith("__"):
+            bad = "." + node.attr
+        if bad:
+            raise RuntimeError(f"{path}:{getattr(node, 'lineno', 0)}: '{bad}' is not allowed in an OCP description executed by gen_spec")
+    # imports outside the allowlist are not executed at all (a later use of their names fails with NameError)
+    class DropImports(ast.NodeTransformer):
+        def visit_Import(self, node):
+            node.names = [a for a in node.names if a.name in ALLOWED_IMPORTS]
+            return node if node.names else None
+
+        def visit_ImportFrom(self, node):
+            return node if (node.module in ALLOWED_IMPORTS and node.level == 0) else None
+
+    tree = ast.fix_missing_locations(DropImports().visit(tree))
+    return compile(tree, os.path.basename(path), "exec")
+
+
 def load_reference(ref):
     d = os.path.join(ref, "crazyflie_controller", "scripts", "crazyflie_full_model")
     saved = {k: sys.modules.get(k) for k in ("casadi", "acados_template", "export_ode_model")}
     sys.modules.update(stub_modules())
     try:
         em = types.ModuleType("export_ode_model")
-        exec(compile(open(os.path.join(d, "export_ode_model.py")).read(), "export_ode_model.py", "exec"), em.__dict__)
+        exec(vetted_source(os.path.join(d, "export_ode_model.py")), em.__dict__)
         sys.modules["export_ode_model"] = em
         model = em.export_ode_model()
         g = {"__name__": "generate_c_code", "__file__": os.path.join(d, "generate_c_code.py")}
         import io
         import contextlib
         with contextlib.redirect_stdout(io.StringIO()):
-            exec(compile(open(os.path.join(d, "generate_c_code.py")).read(), "generate_c_code.py", "exec"), g)
+            exec(vetted_source(os.path.join(d, "generate_c_code.py")), g)
         return model, g["ocp"]
     finally:
         for k, v in saved.items():
