@@ -164,7 +164,8 @@ class BatchSolver:
                 "W": (NY,), "W_e": (NX,), "lbu": (NU,), "ubu": (NU,), "lbu0": (NU,), "ubu0": (NU,),
                 "W_batch": (B, NY), "W_e_batch": (B, NX), "lbu_batch": (B, NU), "ubu_batch": (B, NU),
                 "lbu0_batch": (B, NU), "ubu0_batch": (B, NU), "setpoint": (B, 3), "uss": (1,),
-                "policy": (B,), "traj_iter": (B,), "time_steps": (N,), "bounds_stage": (N, 8), "W_stage": (N + 1, NY)}.get(field)
+                "policy": (B,), "traj_iter": (B,), "time_steps": (N,), "bounds_stage": (N, 8), "W_stage": (N + 1, NY),
+                "W_dense_table": (N + 1, NY, NY)}.get(field)
 
     def set_option(self, option, value):
         """"lin_res_check" (0/1: the reference's linear-system residual diagnostics -> "flags"), "max_ipm_iter"."""

@@ -29,6 +29,9 @@ struct crazyflie_solver_capsule
     std::vector<double> bnd;   // input box per stage, [N][8] = lbu | ubu (ocp_nlp_constraints_bgh.c:653-674)
     std::vector<double> wst;   // weight diagonals per stage, [N+1][17] (ocp_nlp_cost_ls.c:301-331); uploaded once stages differ
     bool wst_used = false;
+    std::vector<double> wdense;      // full weight matrices per stage, [N+1][17][17] row-major (filled on the first "W" set)
+    std::vector<char> wdense_nd;     // stage carries an off-diagonal entry
+    bool wdense_used = false;
     // multipliers of the iterate as ocp_nlp_out carries them (zero until the first feedback; acados_c/ocp_nlp_interface.c:576-590)
     std::vector<double> pi, lam, t, lam_x0;   // [N][13], [N][8], [N][8], [13] (signed, see include/cfnmpc.h)
     bool mult_on = false, mult_valid = false;
@@ -107,6 +110,7 @@ int crazyflie_acados_create_with_discretization(crazyflie_solver_capsule *c, int
     for (int k = 0; k <= N; k++)
         for (int i = 0; i < 17; i++) c->wst[(size_t) k * 17 + i] = k < N ? CfSpec::W[i] : (i < 13 ? CfSpec::W_e[i] : 0.0);
     c->wst_used = false;
+    c->wdense.clear(); c->wdense_nd.clear(); c->wdense_used = false;
     c->bnd.assign((size_t) N * 8, 0.0);   // generate_c_code.py:133-134
     for (int k = 0; k < N; k++)
         for (int i = 0; i < 4; i++) { c->bnd[(size_t) k * 8 + i] = CfSpec::lbu[i]; c->bnd[(size_t) k * 8 + 4 + i] = CfSpec::ubu[i]; }
@@ -279,16 +283,46 @@ int ocp_nlp_cost_model_set(ocp_nlp_config *, ocp_nlp_dims *, ocp_nlp_in *in, int
         return 0;
     }
     if (!strcmp(field, "W")) {
-        // column-major ny x ny as the node fills it (acados_mpc.cpp:526-542); only diagonal weights are supported
+        // column-major ny x ny as the node fills it (acados_mpc.cpp:526-542)
         const int n = stage < c->N ? 17 : 13;
         const double *W = static_cast<const double *>(value);
         double d[17];
+        bool diag = true;
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 if (i == j) d[i] = W[i + n * j];
-                else if (W[i + n * j] != 0.0) return 1;
+                else if (W[i + n * j] != 0.0) diag = false;
             }
         if (!c->batch) return 1;
+        // Any SPD matrix is accepted, as in the reference (ocp_nlp_cost_ls.c:301-331).  The full matrices of all stages are
+        // kept; once one of them has an off-diagonal entry the table goes to the dense-Hessian kernel ("W_dense_table"),
+        // and back to the diagonal paths when every stage is diagonal again.
+        if (c->wdense.empty()) {
+            c->wdense.assign((size_t) (c->N + 1) * 289, 0.0);
+            for (int k = 0; k <= c->N; k++)
+                for (int i = 0; i < (k < c->N ? 17 : 13); i++) c->wdense[(size_t) k * 289 + i * 18] = c->wst[(size_t) k * 17 + i];
+            c->wdense_nd.assign((size_t) c->N + 1, 0);
+        }
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) c->wdense[(size_t) stage * 289 + i * 17 + j] = 0.5 * (W[i + n * j] + W[j + n * i]);
+        c->wdense_nd[stage] = diag ? 0 : 1;
+        bool any_nd = false;
+        for (char f : c->wdense_nd) any_nd = any_nd || f;
+        if (any_nd) {
+            if (c->mult_on) { cfnmpc_batch_set_option(c->batch, "multipliers", 0); c->mult_on = false; }
+            if (cfnmpc_batch_set(c->batch, "W_dense_table", c->wdense.data(), 0) != CFNMPC_OK) {
+                fprintf(stderr, "ocp_nlp_cost_model_set W: %s\n", cfnmpc_last_error());
+                return 1;
+            }
+            c->wdense_used = true;
+            memcpy(&c->wst[(size_t) stage * 17], d, n * sizeof(double));
+            return 0;
+        }
+        if (c->wdense_used) {
+            cfnmpc_batch_clear(c->batch, "W_dense_table");
+            c->wdense_used = false;
+            if (c->cond_N >= c->N && !c->mult_on) c->mult_on = cfnmpc_batch_set_option(c->batch, "multipliers", 1) == CFNMPC_OK;
+        }
         // the reference sets the weight of ONE stage (ocp_nlp_cost_ls.c:301-331).  While all stages < N carry the same
         // diagonal (the node's SET_WEIGHTS loop, acados_mpc.cpp:596-602) the solver-wide value and the fast kernels are
         // used; as soon as stages differ the per-stage table takes over.

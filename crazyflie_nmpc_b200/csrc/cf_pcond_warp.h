@@ -76,6 +76,7 @@ struct CfPcWarpT
     unsigned par;
     double *SLOT, *PREP;
     const double *DT, *BST, *WTAB;
+    const double *WD;    // full weight matrices per stage (block size 1 only): [(N+1)][2][17*17], see CfBatchView::W_dense
     double mu, alpha, mu_aff, sigma, pm_max;
     double nrm[4], lin[4];
     int flags;
@@ -85,7 +86,7 @@ struct CfPcWarpT
     {
         P = P_; PG = PG_; N = PG_->N; sm = sm_; lane = cf_lane();
         N2 = b.N2; bs0 = b.bs0; n_big = b.n_big;
-        PREP = prep_; DT = dts_; BST = nullptr; WTAB = nullptr; SLOT = slot;
+        PREP = prep_; DT = dts_; BST = nullptr; WTAB = nullptr; WD = nullptr; SLOT = slot;
         bar = reinterpret_cast<uint64_t *>(sm_ + SM_BAR);
         par = 0;
         lin[0] = lin[1] = lin[2] = lin[3] = 0.0;
@@ -123,7 +124,7 @@ struct CfPcWarpT
     // (CF_PREP_STAGE records [ [B';A';b'] 18 x 13 | gradient 18 ]), evaluates the bound vectors and the initial
     // interior-point variables (OCP_QP_INIT_VAR scheme 1) of every real input, and eliminates x0 from stage 0
     // (x_ocp_qp_red.c:310-330).  Lane r < MR owns row r of G (registers) and of the condensed Hessian (shared memory).
-    CF_MEM void condense(const double *xg, const double *ug, const double *x0g)
+    CF_MEM void condense(const double *xg, const double *ug, const double *x0g, const double *yrefg, const double *yref_eg)
     {
         double *GS = sm + 2 * BS * CF_PREP_STAGE;           // G (MR x 13, element (r,c) at c*MR + r) for the products
         double *HS = GS + MSZ;                              // packed lower triangle of H2
@@ -260,6 +261,35 @@ struct CfPcWarpT
             }
             // ---- the condensed stage block
             if (vl) HS[trl + lane] += hdiag;
+            if constexpr (BS == 1) {
+                if (WD) {
+                    // full weight matrix of stage k0 (ocp_nlp_cost_ls.c:743-772,883-912): Hessian dt (Cyt W_chol)(Cyt W_chol)'
+                    // (the product comes from the host, [u;x] order), gradient dt Cyt W (y - yref).  Stage 0: its states are
+                    // eliminated -- decoupled dummies here -- and leave S xbar in the input gradient (x_ocp_qp_red.c:354).
+                    const double *Hd = WD + (long) k0 * 578, *Wp = Hd + 289;
+                    const double h = dt(k0);
+                    double *RS = sm + SM_V0, *XB = sm + SM_V1;
+                    cf_syncwarp();
+                    if (vl) {
+                        RS[lane] = ul ? ug[k0 * CF_NU + lane] - yrefg[k0 * CF_NY + CF_NX + lane]
+                                      : xg[k0 * CF_NX + ci] - yrefg[k0 * CF_NY + ci];
+                        XB[lane] = (i == 0 && xl) ? x0g[ci] - xg[ci] : 0.0;
+                    }
+                    cf_syncwarp();
+                    if (vl) {
+                        double g = 0.0, sx = 0.0;
+                        CF_NOUNROLL
+                        for (int c = 0; c < NVB; c++) {
+                            const double hv = h * Hd[lane * CF_NV + c];
+                            g += Wp[lane * CF_NV + c] * RS[c];
+                            sx += hv * XB[c];
+                            const bool dummy = i == 0 && (c >= NUB || xl);       // eliminated states: unit diagonal, no coupling
+                            if (c <= lane) HS[trl + c] = dummy ? (c == lane ? 1.0 : 0.0) : hv;
+                        }
+                        rq = (i == 0 && xl) ? 0.0 : h * g + ((i == 0) ? sx : 0.0);
+                    }
+                }
+            }
             cf_syncwarp();
             for (int e = lane; e < HSZ; e += 32) bk[P_H + e] = HS[e];
             if (lane < MR) {
@@ -288,8 +318,27 @@ struct CfPcWarpT
                 if (xl) { const double r = sqrt(wgt(N, ci)); hN = r * r; }
                 bk[P_H + trl + lane] = hN;
             }
+            double gN = xl ? PREP[(long) N * CF_PREP_STAGE + CF_NU + ci] : 0.0;
+            if constexpr (BS == 1) {
+                if (WD) {   // full terminal weight (13 x 13 state block of table row N; terminal scaling 1)
+                    const double *Hd = WD + (long) N * 578, *Wp = Hd + 289;
+                    double *RS = sm + SM_V0;
+                    cf_syncwarp();
+                    if (xl) RS[lane] = xg[N * CF_NX + ci] - yref_eg[ci];
+                    cf_syncwarp();
+                    if (xl) {
+                        double g = 0.0;
+                        CF_NOUNROLL
+                        for (int c = NUB; c < NVB; c++) {
+                            g += Wp[lane * CF_NV + c] * RS[c];
+                            if (c <= lane) bk[P_H + trl + c] = Hd[lane * CF_NV + c];
+                        }
+                        gN = g;
+                    }
+                }
+            }
             if (lane < MR) {
-                bk[R_RQ + lane] = xl ? PREP[(long) N * CF_PREP_STAGE + CF_NU + ci] : 0.0;
+                bk[R_RQ + lane] = gN;
                 bk[R_UX + lane] = 0.0; bk[R_DUX + lane] = 0.0;
             }
             if (lane < CF_NX) { bk[R_PI + lane] = 0.0; bk[R_DPI + lane] = 0.0; }
@@ -454,9 +503,10 @@ struct CfPcWarpT
             if (!kl) {
                 for (int i = lane; i < 13 * ALP; i += 32) PS[i] = 0.0;
                 cf_syncwarp();
-                const double hN = HP[trl + lv] + CF_REG_PRIM;
                 if (xl) {
-                    PS[ci * ALP + ci + PCO] = hN;
+                    // P_N = state block of the terminal Hessian (+ reg); lower triangle (dense with full weight matrices)
+                    CF_NOUNROLL
+                    for (int c = 0; c <= ci; c++) PS[ci * ALP + c + PCO] = HP[trl + NUB + c] + (c == ci ? CF_REG_PRIM : 0.0);
                     PV[ci] = rg;
                     rk[R_DUX + lane] = rg;
                 }
@@ -961,14 +1011,17 @@ CF_DEV void cf_pcond_instance(const CfParams *Pg, const CfBatchView &bv, const C
     w.par = par;
     w.BST = bv.bnd_stage;
     w.WTAB = bv.W_stage;
+    w.WD = (BS == 1) ? bv.W_dense : nullptr;
     const int N = Pg->N;
     double *xg = bv.x + (long) inst * (N + 1) * CF_NX;
     double *ug = bv.u + (long) inst * N * CF_NU;
     const double *x0g = bv.x0 + (long) inst * CF_NX;
+    const double *yrefg = bv.yref + (long) inst * N * CF_NY;
+    const double *yref_eg = bv.yref_e + (long) inst * CF_NX;
     unsigned long long *prof = bv.prof;
     {
         CF_PROF_BEGIN();
-        w.condense(xg, ug, x0g);
+        w.condense(xg, ug, x0g, yrefg, yref_eg);
         CF_PROF_END(CF_PROF_LIN);
     }
     int iters = 0;

@@ -153,6 +153,11 @@ struct CfBatchView
     // elimination drops them; element (c, r) = d x1_c / d x0_r at c*13 + r)
     double *mult;
     long mult_stride;
+    // full (non-diagonal) weight matrices per stage (ocp_nlp_cost_ls.c:301-331 accepts any SPD W), null = diagonal weights:
+    // [(N+1)][2][17*17] in stage-variable order [u;x] -- first (Cyt W_chol)(Cyt W_chol)' (what the reference's Hessian is,
+    // :743-772), then W itself (gradient, :883-912); row N carries W_e in its state block.  Read by the condensed feedback
+    // program with block size 1 (cf_pcond_warp.h), which has the dense stage Hessian the uncondensed program lacks.
+    const double *W_dense;
 };
 static inline
 #if !defined(CF_SIMT_EMU)

@@ -167,6 +167,8 @@ struct cfnmpc_batch
     double *d_dts = nullptr, *d_prep = nullptr;
     double *h_dts = nullptr;          // host copy of the time grid (N doubles)
     double *d_bst = nullptr;          // per-stage input boxes [N][8] (allocated on first use)
+    double *d_wdense = nullptr;       // full weight matrices per stage [(N+1)][2][289] (field "W_dense_table")
+    bool dense_w = false;
     double *d_mult = nullptr;         // multiplier output [B][cf_mult_stride(N)] (option "multipliers")
     double *d_wst = nullptr;          // per-stage weights [N+1][17] (allocated on first use); while set, the general kernels run
     bool vdt_grid = false, wst = false, prepared = false;   // non-uniform time grid / per-stage weights: the general kernels
@@ -195,7 +197,7 @@ extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
     void *ptrs[] = {h->d_x0, h->d_yref, h->d_yref_e, h->d_x, h->d_u, h->d_res, h->d_scratch, h->d_stage,
                     h->d_status, h->d_qp_iter, h->d_qp_status, h->d_flags, h->d_counter,
                     h->d_policy, h->d_titer, h->d_motors, h->d_setpoint, h->d_traj, h->d_euler, h->d_twist,
-                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep, h->d_bst, h->d_wst, h->d_mult};
+                    h->d_prof, h->d_Wb, h->d_WNb, h->d_lbub, h->d_ubub, h->d_lbu0b, h->d_ubu0b, h->d_dts, h->d_prep, h->d_bst, h->d_wst, h->d_mult, h->d_wdense};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -358,7 +360,7 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     bv.W_b = bv.WN_b = bv.lbu_b = bv.ubu_b = bv.lbu0_b = bv.ubu0_b = nullptr;
     bv.prof = nullptr;
     bv.dts = h->d_dts; bv.prep = nullptr; bv.prep_stride = cf_prep_stride(N); bv.bnd_stage = nullptr; bv.W_stage = nullptr;
-    bv.mult = nullptr; bv.mult_stride = cf_mult_stride(N);
+    bv.mult = nullptr; bv.mult_stride = cf_mult_stride(N); bv.W_dense = nullptr;
     CKH(cudaStreamSynchronize(h->stream));
 #undef CKH
     *out = h;
@@ -402,6 +404,7 @@ static bool batch_field(cfnmpc_batch *h, const char *f, FieldRef &r)
     return true;
 }
 
+static int set_cond_N(cfnmpc_batch *h, int N2);
 extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *src, int src_on_device)
 {
     if (!h || !field || !src) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set: null argument");
@@ -463,6 +466,54 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         h->prepared = false;
         return CFNMPC_OK;
     }
+    if (!strcmp(field, "W_dense_table")) {
+        // [N+1][17][17] row-major, cost order y = [x;u]: the full weight matrix of every stage (row N: W_e in its leading
+        // 13 x 13 block) -- what per-stage ocp_nlp_cost_model_set(.., k, "W", ..) calls with non-diagonal matrices build
+        // (ocp_nlp_cost_ls.c:301-331).  The reference's Hessian is scaling (Cyt W_chol)(Cyt W_chol)' with W_chol from
+        // blasfeo_dpotrf_l (:743-772), its gradient uses W itself (:883-912): both are handed to the kernel in [u;x] order.
+        if (h->bv.mult) return fail(CFNMPC_EINVAL, "W_dense_table: not available together with the option multipliers");
+        if (h->cond_N && !h->dense_w) return fail(CFNMPC_EINVAL, "W_dense_table: not available together with qp_cond_N < N");
+        const int N = h->N;
+        std::vector<double> W((size_t) (N + 1) * 289), T((size_t) (N + 1) * 578, 0.0);
+        if (src_on_device) CK(cudaMemcpy(W.data(), src, W.size() * 8, cudaMemcpyDeviceToHost));
+        else memcpy(W.data(), src, W.size() * 8);
+        auto yidx = [](int r) { return r < CF_NU ? CF_NX + r : r - CF_NU; };   // cost index of stage variable r
+        for (int k = 0; k <= N; k++) {
+            const int n = k < N ? CF_NY : CF_NX;
+            const double *Wk = &W[(size_t) k * 289];
+            double L[17][17] = {};
+            for (int j = 0; j < n; j++) {
+                double d = Wk[j * 17 + j];
+                for (int c = 0; c < j; c++) d -= L[j][c] * L[j][c];
+                if (!(d > 0.0)) return fail(CFNMPC_EINVAL, "W_dense_table: a weight matrix is not symmetric positive definite");
+                d = sqrt(d);
+                L[j][j] = d;
+                for (int i = j + 1; i < n; i++) {
+                    if (Wk[i * 17 + j] != Wk[j * 17 + i]) return fail(CFNMPC_EINVAL, "W_dense_table: a weight matrix is not symmetric");
+                    double v = Wk[i * 17 + j];
+                    for (int c = 0; c < j; c++) v -= L[i][c] * L[j][c];
+                    L[i][j] = v / d;
+                }
+            }
+            double *Hd = &T[(size_t) k * 578], *Wp = Hd + 289;
+            for (int r = 0; r < 17; r++)
+                for (int c = 0; c < 17; c++) {
+                    const int i = yidx(r), j = yidx(c);
+                    if (i >= n || j >= n) continue;
+                    double v = 0.0;
+                    for (int q = 0; q <= (i < j ? i : j); q++) v += L[i][q] * L[j][q];
+                    Hd[r * 17 + c] = v;
+                    Wp[r * 17 + c] = Wk[i * 17 + j];
+                }
+        }
+        if (!h->d_wdense) CK(cudaMalloc(&h->d_wdense, T.size() * 8));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(h->d_wdense, T.data(), T.size() * 8, cudaMemcpyHostToDevice));
+        h->bv.W_dense = h->d_wdense;
+        h->dense_w = true;
+        h->prepared = false;
+        return set_cond_N(h, 0);   // selects the block-size-1 condensed feedback kernel
+    }
     if (!strcmp(field, "time_steps")) {
         // crazyflie_acados_update_time_steps (c_templates_tera/acados_solver.in.c:133-153): interval lengths = cost scalings
         std::vector<double> dt(h->N);
@@ -518,17 +569,23 @@ static void (*pc_kernel_for(int wpb, int minb))(const CfParams, const CfBatchVie
 // off.  Block sizes up to 3 stages are implemented (one row of the condensed stage per lane: 4*3 + 13 + 1 = 26 <= 32).
 static int set_cond_N(cfnmpc_batch *h, int N2)
 {
-    if (N2 <= 0 || N2 >= h->N) { h->cond_N = 0; return CFNMPC_OK; }
-    if (h->bv.mult) return fail(CFNMPC_EINVAL, "qp_cond_N: partial condensing does not produce the multiplier output (option multipliers)");
+    // full weight matrices need the dense stage Hessian of the condensed program: block size 1 stands in for "off"
+    if (N2 <= 0 || N2 >= h->N) {
+        if (!h->dense_w) { h->cond_N = 0; return CFNMPC_OK; }
+        N2 = h->N;
+    } else if (h->dense_w) return fail(CFNMPC_EINVAL, "qp_cond_N: partial condensing with full weight matrices (W_dense_table) is not implemented");
+    if (h->bv.mult) return fail(CFNMPC_EINVAL, "qp_cond_N / W_dense_table: the condensed feedback program does not produce the multiplier output (option multipliers)");
     const CfPcBlocks b = cf_pc_blocks(h->N, N2);
     const int bs = b.n_big ? b.bs0 + 1 : b.bs0;
     if (bs > 3) return fail(CFNMPC_EINVAL, "qp_cond_N: blocks of more than 3 stages are not implemented (need qp_cond_N >= ceil(N / 3))");
     CK(cudaSetDevice(h->device));
     if (const char *e = getenv("CFNMPC_PC_WARPS_PER_BLOCK")) h->pc_wpb = atoi(e);
     if (const char *e = getenv("CFNMPC_PC_MIN_BLOCKS")) h->pc_minb = atoi(e);
-    auto k = bs == 3 ? pc_kernel_for<3>(h->pc_wpb, h->pc_minb) : pc_kernel_for<2>(h->pc_wpb, h->pc_minb);
-    if (!k) { h->pc_wpb = 4; h->pc_minb = 2; k = bs == 3 ? pc_kernel_for<3>(4, 2) : pc_kernel_for<2>(4, 2); }
-    const size_t smem = (size_t) h->pc_wpb * (bs == 3 ? (int) CfPcWarpT<3>::SM_DOUBLES : (int) CfPcWarpT<2>::SM_DOUBLES) * sizeof(double);
+    auto pick = [&](int w, int m) { return bs == 3 ? pc_kernel_for<3>(w, m) : (bs == 2 ? pc_kernel_for<2>(w, m) : pc_kernel_for<1>(w, m)); };
+    auto k = pick(h->pc_wpb, h->pc_minb);
+    if (!k) { h->pc_wpb = 4; h->pc_minb = 2; k = pick(4, 2); }
+    const int smd = bs == 3 ? (int) CfPcWarpT<3>::SM_DOUBLES : (bs == 2 ? (int) CfPcWarpT<2>::SM_DOUBLES : (int) CfPcWarpT<1>::SM_DOUBLES);
+    const size_t smem = (size_t) h->pc_wpb * smd * sizeof(double);
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, k));
@@ -538,7 +595,7 @@ static int set_cond_N(cfnmpc_batch *h, int N2)
     const long want = (long) h->sm_count * bps, need = ((long) h->B + h->pc_wpb - 1) / h->pc_wpb;
     const int grid = (int) (want < need ? want : need);
     // scratch: every resident warp needs a slot of (N2 + 1) condensed stage blocks
-    const long stride_pc = bs == 3 ? cf_pc_scratch_doubles<3>(N2) : cf_pc_scratch_doubles<2>(N2);
+    const long stride_pc = bs == 3 ? cf_pc_scratch_doubles<3>(N2) : (bs == 2 ? cf_pc_scratch_doubles<2>(N2) : cf_pc_scratch_doubles<1>(N2));
     const long stride = stride_pc > h->bv.scratch_stride ? stride_pc : h->bv.scratch_stride;
     const int slots = grid * h->pc_wpb > h->n_slots ? grid * h->pc_wpb : h->n_slots;
     if (stride != h->bv.scratch_stride || slots != h->n_slots) {
@@ -565,7 +622,7 @@ extern "C" int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int 
     else if (!strcmp(option, "max_ipm_iter")) h->P.max_ipm_iter = (value > 0 && value < CF_ITER_MAX) ? value : CF_ITER_MAX;
     else if (!strcmp(option, "multipliers")) {
         // keep pi / lam / t of every solved instance (ocp_nlp_out_get "pi" / "lam" / "t"): 8 (29 N + 182) bytes per instance
-        if (value && h->cond_N) return fail(CFNMPC_EINVAL, "option multipliers: not available with partial condensing (qp_cond_N < N)");
+        if (value && h->cond_N) return fail(CFNMPC_EINVAL, "option multipliers: not available with partial condensing (qp_cond_N < N) or full weight matrices");
         CK(cudaSetDevice(h->device));
         if (value && !h->d_mult) {
             const size_t bytes = (size_t) h->B * h->bv.mult_stride * 8;
@@ -589,6 +646,7 @@ extern "C" int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field)
     else if (!strcmp(field, "ubu0_batch")) h->bv.ubu0_b = nullptr;
     else if (!strcmp(field, "bounds_stage")) h->bv.bnd_stage = nullptr;
     else if (!strcmp(field, "W_stage")) { h->bv.W_stage = nullptr; h->wst = false; h->vdt = h->vdt_grid; h->prepared = false; }
+    else if (!strcmp(field, "W_dense_table")) { h->bv.W_dense = nullptr; h->dense_w = false; h->cond_N = 0; h->prepared = false; }
     else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_clear: '") + field + "' is not a per-instance parameter array");
     return CFNMPC_OK;
 }

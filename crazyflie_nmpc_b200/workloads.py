@@ -162,3 +162,20 @@ def adversarial_batch(B, N=50, seed=7, level=1.0):
     w.update(x0=np.ascontiguousarray(x0), x_init=np.ascontiguousarray(np.broadcast_to(x0[:, None, :], (B, N + 1, NX))),
              u_init=np.ascontiguousarray(u_init), W=W, W_e=W_e, lbu=np.ascontiguousarray(lbu), ubu=np.ascontiguousarray(ubu))
     return w
+
+
+def dense_weight_table(N, seed=0, coupling=0.3):
+    """Full (non-diagonal) SPD weight matrices, one per stage, [N+1][17][17] in cost order y = [x;u] (row N: W_e in its
+    leading 13 x 13 block): the node's diagonal weights scaled per stage and correlated by a random SPD factor.  What a
+    caller builds with per-stage ocp_nlp_cost_model_set(.., k, "W", ..) calls (ocp_nlp_cost_ls.c:301-331)."""
+    rng = np.random.default_rng(seed)
+    Q = np.array([120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0, 0.06, 0.06, 0.06, 0.06])
+    tab = np.zeros((N + 1, NY, NY))
+    for k in range(N + 1):
+        n = NY if k < N else NX
+        d = np.sqrt(Q[:n] * (50.0 if k == N else 1.0) * rng.uniform(0.5, 2.0, n))
+        C = np.eye(n) + coupling * rng.uniform(-1, 1, (n, n))
+        C = 0.5 * (C + C.T)
+        Wk = d[:, None] * (C @ C.T) * d[None, :]
+        tab[k, :n, :n] = 0.5 * (Wk + Wk.T)
+    return tab

@@ -84,8 +84,14 @@ int cfnmpc_batch_set_stream(cfnmpc_batch *h, void *cuda_stream);
  *   "W_stage" double [N+1][17]      weight diagonals per STAGE (row k < N: W_k in cost order y = [x;u]; row N: W_e, 13 used): the
  *                                   reference sets the weight of one stage at a time (ocp_nlp_cost_model_set(.., k, "W", ..),
  *                                   ocp_nlp_cost_ls.c:301-331).  Takes precedence over "W", "W_e" and the per-instance arrays
- *                                   until cfnmpc_batch_clear("W_stage"); runs the general kernels.  Non-diagonal weights are
- *                                   not supported (the single-instance setter rejects them).
+ *                                   until cfnmpc_batch_clear("W_stage"); runs the general kernels.
+ *   "W_dense_table" double [N+1][17][17]  FULL weight matrix per stage (row-major, symmetric positive definite, cost order
+ *                                   y = [x;u]; row N: W_e in its leading 13 x 13 block): the reference accepts any SPD W
+ *                                   (ocp_nlp_cost_ls.c:301-331; Hessian scaling (Cyt W_chol)(Cyt W_chol)', :743-772, gradient
+ *                                   scaling Cyt W res, :883-912).  Takes precedence over every other weight field until
+ *                                   cfnmpc_batch_clear("W_dense_table").  The step then runs as preparation kernel + the
+ *                                   condensed feedback program with block size 1 (the program with a dense stage Hessian,
+ *                                   csrc/cf_pcond_warp.h); not available together with "qp_cond_N" < N or "multipliers".
  *   "time_steps" double [N]         lengths of the shooting intervals (host or device pointer); each is also the
  *                                   scaling of its stage cost, as crazyflie_acados_create_with_discretization /
  *                                   crazyflie_acados_update_time_steps set them (c_templates_tera/acados_solver.in.c:

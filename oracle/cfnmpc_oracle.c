@@ -196,6 +196,45 @@ void cfo_set_stage_weights(const double *tab, int n_rows)
 }
 #define WKS(p, k, idx) ((k) < g_wst_n ? g_wst[17 * (k) + (idx)] : (p)->Wdiag[idx])   /* stages k < N */
 #define WK(p, k, N, idx) ((k) < g_wst_n ? g_wst[17 * (k) + (idx)] : ((k) < (N) ? (p)->Wdiag[idx] : (p)->WNdiag[idx]))
+/* Full (non-diagonal) weight matrices, one per stage: tab[n_rows][17*17] row-major, symmetric, cost order y = [x;u]; row N
+ * is W_e (its leading 13 x 13 block).  ocp_nlp_cost_ls.c:301-331 (any SPD W; the Cholesky factor enters the Hessian,
+ * W itself the gradient).  Global, test use only; n_rows = 0 returns to the diagonal weights. */
+#define CFO_MAX_DENSE 257
+static double g_wd[CFO_MAX_DENSE * 289], g_hd[CFO_MAX_DENSE * 289];   /* W and chol(W) chol(W)' per stage */
+static int g_wd_n = 0;
+void cfo_set_dense_weights(const double *tab, int n_rows)
+{
+    g_wd_n = 0;
+    if (!tab || n_rows <= 0 || n_rows > CFO_MAX_DENSE) return;
+    memcpy(g_wd, tab, sizeof(double) * 289 * n_rows);
+    for (int k = 0; k < n_rows; k++) {
+        /* hess = (Cyt W_chol)(Cyt W_chol)' (ocp_nlp_cost_ls.c:743-772, blasfeo_dpotrf_l + dtrmm + dsyrk) */
+        const int n = (k == n_rows - 1) ? NX : NV;
+        const double *W = g_wd + 289 * k;
+        double L[17][17];
+        memset(L, 0, sizeof L);
+        for (int j = 0; j < n; j++) {
+            double d = W[j * 17 + j];
+            for (int c = 0; c < j; c++) d -= L[j][c] * L[j][c];
+            d = d > 0 ? sqrt(d) : 0.0;
+            L[j][j] = d;
+            for (int i = j + 1; i < n; i++) {
+                double v = W[i * 17 + j];
+                for (int c = 0; c < j; c++) v -= L[i][c] * L[j][c];
+                L[i][j] = d > 0 ? v / d : 0.0;
+            }
+        }
+        double *H = g_hd + 289 * k;
+        for (int i = 0; i < 17; i++) for (int j = 0; j < 17; j++) {
+            double v = 0;
+            if (i < n && j < n) for (int c = 0; c <= (i < j ? i : j); c++) v += L[i][c] * L[j][c];
+            H[i * 17 + j] = v;
+        }
+    }
+    g_wd_n = n_rows;
+}
+/* cost index (y = [x;u]) of stage variable r ([u;x] order) */
+#define YIDX(r) ((r) < NU ? NX + (r) : (r) - NU)
 static double g_bst[CFO_MAX_N * 8];
 static int g_bst_n = 0;
 void cfo_set_stage_bounds(const double *tab, int n)
@@ -233,6 +272,16 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
                 const double *yr = yref + NV * k;
                 for (int i = 0; i < NU; i++) g[i] = (WK(p_, k, N, NX + i) * (uk[i] - yr[NX + i])) * DTK(k);
                 for (int i = 0; i < NX; i++) g[NU + i] = (WK(p_, k, N, i) * (xk[i] - yr[i])) * DTK(k);
+                if (k < g_wd_n) {   /* tmp = W res (symv), grad = scaling * Cyt tmp  (ocp_nlp_cost_ls.c:883-912) */
+                    double res[NV];
+                    for (int j = 0; j < NX; j++) res[j] = xk[j] - yr[j];
+                    for (int j = 0; j < NU; j++) res[NX + j] = uk[j] - yr[NX + j];
+                    for (int r = 0; r < NV; r++) {
+                        double v = 0;
+                        for (int j = 0; j < NV; j++) v += g_wd[289 * k + YIDX(r) * 17 + j] * res[j];
+                        g[r] = v * DTK(k);
+                    }
+                }
             }
             int nb = k == 0 ? NV : NU;
             for (int i = 0; i < NU; i++) {
@@ -252,6 +301,12 @@ void cfo_linearize(int N, double Ts, const cfo_params *p_, const double *x0, con
         } else if (rqz) {
             double *g = rqz + NV * N;
             for (int i = 0; i < NX; i++) g[i] = WK(p_, N, N, i) * (xk[i] - yref_e[i]);
+            if (N < g_wd_n)
+                for (int i = 0; i < NX; i++) {
+                    double v = 0;
+                    for (int j = 0; j < NX; j++) v += g_wd[289 * N + i * 17 + j] * (xk[j] - yref_e[j]);
+                    g[i] = v;
+                }
         }
     }
 }
@@ -861,6 +916,22 @@ int cfo_rti(int N, double Ts, const cfo_params *p_, const double *x0, const doub
             for (int i = 0; i < NU; i++) s->rq[i] = g[i]; /* diagonal RSQ: no cross term from xbar (:354) */
         } else {
             for (int i = 0; i < s->nv; i++) s->rq[i] = g[i];
+        }
+        if (k < g_wd_n) {
+            /* full weight matrix: dense stage Hessian scaling * (Cyt W_chol)(Cyt W_chol)'; the eliminated x_0 leaves the
+             * cross term S xbar in the stage-0 gradient (SYMV_L with the masked vector, x_ocp_qp_red.c:354) */
+            const double *Hd = g_hd + 289 * k;
+            const double sc = k < N ? DTK(k) : 1.0;
+            const int off = k == N ? NU : 0;   /* first [u;x] index among the stage's variables */
+            s->dense = 1;
+            for (int i = 0; i < s->nv; i++)
+                for (int j = 0; j < s->nv; j++) s->Hm[i][j] = sc * Hd[YIDX(off + i) * 17 + YIDX(off + j)];
+            if (k == 0)
+                for (int i = 0; i < NU; i++) {
+                    double v = 0;
+                    for (int j = 0; j < NX; j++) v += (sc * Hd[YIDX(i) * 17 + j]) * xbar[j];
+                    s->rq[i] = v + g[i];
+                }
         }
         if (k < N) {
             const double *M = BAbt + (size_t) k * NV * NX;

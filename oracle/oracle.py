@@ -70,6 +70,7 @@ class Port:
         L.cfo_ode.argtypes = [_dp, _dp, _dp]
         L.cfo_default_params.argtypes = [ctypes.POINTER(CfoParams)]
         L.cfo_set_iter_max.argtypes = [ctypes.c_int]
+        L.cfo_set_dense_weights.argtypes = [_dp, ctypes.c_int]
         L.cfo_record_multipliers.argtypes = [ctypes.c_int]
         L.cfo_last_multipliers.argtypes = [_dp, _dp, _dp]
         L.cfo_set_stage_weights.argtypes = [_dp, ctypes.c_int]
@@ -91,6 +92,15 @@ class Port:
         self.lib.cfo_last_multipliers(_P(pi), _P(lam), _P(t))
         return (pi, lam[:2 * NV].reshape(2, NV), lam[2 * NV:].reshape(N - 1, 2, NU),
                 t[:2 * NV].reshape(2, NV), t[2 * NV:].reshape(N - 1, 2, NU))
+
+    def set_dense_weights(self, tab=None):
+        """Full weight matrices per stage, [N+1][17][17] in cost order y = [x;u] (row N: W_e in its leading 13 x 13 block);
+        global in the checker, None returns to the diagonal weights."""
+        if tab is None:
+            self.lib.cfo_set_dense_weights(None, 0)
+        else:
+            tab = np.ascontiguousarray(tab, float)
+            self.lib.cfo_set_dense_weights(_P(tab), tab.shape[0])
 
     def set_iter_max(self, n=50):
         """qp_iter_max of the interior-point loop (global in the checker; 50 = the reference configuration)."""

@@ -375,14 +375,18 @@ static void pc_job_fn(void *a)
     unsigned par = 0;
     cf_pcond_instance<BS>(j->P, j->bv, j->blk, j->inst, j->slot, j->sm, par);
 }
+// full weight matrices in the kernel's table format [(N+1)][2][17*17] ([u;x] order: Hessian factor product, W) for the next
+// cfemu_rti_pcond calls (NULL: diagonal weights); with it N2 = N selects the block-size-1 program
+static const double *g_wdense = nullptr;
+extern "C" void cfemu_set_dense_weights(const double *tab) { g_wdense = tab; }
 extern "C" int cfemu_rti_pcond(int B, int N, double Ts, int N2, const double *params, const double *x0, const double *yref,
                                const double *yref_e, double *x, double *u, int *status, int *qp_iter, int *qp_status, int *flags,
                                double *res, int nthreads, const double *const *per_inst)
 {
-    if (N2 < 1 || N2 >= N) return -1;
+    if (N2 < 1 || N2 > N || (N2 == N && !g_wdense)) return -1;   // block size 1 only serves the full weight matrices
     const CfPcBlocks blk = cf_pc_blocks(N, N2);
     const int BS = blk.n_big ? blk.bs0 + 1 : blk.bs0;
-    if (BS != 2 && BS != 3) return -2;
+    if (BS < 1 || BS > 3) return -2;
     CfParams P;
     static const double Q[13] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
     for (int i = 0; i < 13; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
@@ -394,9 +398,9 @@ extern "C" int cfemu_rti_pcond(int B, int N, double Ts, int N2, const double *pa
     memcpy(P.lbu0, P.lbu, sizeof P.lbu); memcpy(P.ubu0, P.ubu, sizeof P.ubu);
     P.Ts = Ts; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = 0; P.pad_ = 0;
     const long stride0 = cf_scratch_layout(N).total, pstride = cf_prep_stride(N);
-    const long stride1 = BS == 3 ? cf_pc_scratch_doubles<3>(N2) : cf_pc_scratch_doubles<2>(N2);
+    const long stride1 = BS == 3 ? cf_pc_scratch_doubles<3>(N2) : (BS == 2 ? cf_pc_scratch_doubles<2>(N2) : cf_pc_scratch_doubles<1>(N2));
     const long stride = stride0 > stride1 ? stride0 : stride1;
-    const int smd = BS == 3 ? (int) CfPcWarpT<3>::SM_DOUBLES : (int) CfPcWarpT<2>::SM_DOUBLES;
+    const int smd = BS == 3 ? (int) CfPcWarpT<3>::SM_DOUBLES : (BS == 2 ? (int) CfPcWarpT<2>::SM_DOUBLES : (int) CfPcWarpT<1>::SM_DOUBLES);
     const int smn = smd > CF_SM_DOUBLES ? smd : CF_SM_DOUBLES;
     std::vector<double> dtv(N, Ts);
     std::vector<double> prep((size_t) B * pstride + 2, std::nan(""));
@@ -409,6 +413,7 @@ extern "C" int cfemu_rti_pcond(int B, int N, double Ts, int N2, const double *pa
     bv.prep = (double *) ((((uintptr_t) prep.data()) + 15) & ~(uintptr_t) 15);
     bv.prep_stride = pstride;
     bv.bnd_stage = g_bnd_stage;
+    bv.W_dense = g_wdense;
     if (per_inst) {
         bv.W_b = per_inst[0]; bv.WN_b = per_inst[1]; bv.lbu_b = per_inst[2]; bv.ubu_b = per_inst[3];
         bv.lbu0_b = per_inst[4]; bv.ubu0_b = per_inst[5];
@@ -432,7 +437,7 @@ extern "C" int cfemu_rti_pcond(int B, int N, double Ts, int N2, const double *pa
                 cfemu::run_warp(job_fn_t<CF_PH_PREPARATION, true>, &j);
                 poison();
                 PcJob pj{&P, bv, blk, i, slot_a, sm_a};
-                cfemu::run_warp(BS == 3 ? pc_job_fn<3> : pc_job_fn<2>, &pj);
+                cfemu::run_warp(BS == 3 ? pc_job_fn<3> : (BS == 2 ? pc_job_fn<2> : pc_job_fn<1>), &pj);
             }
         });
     for (auto &t : th) t.join();

