@@ -48,7 +48,41 @@ def run(N):
         s.set("x", w["x_init"]).set("u", w["u_init"])
         s.tick().plant_step(TS)
         s.get("motors"), s.get("twist"), s.get("euler")
+    # round 2: multiplier output, partial condensing (block sizes 2 and 3; solve, split and host-fed), full weight matrices
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("multipliers", 1)
+        s.set_problem(w).solve(1)
+        res["multipliers"] = (s.get("x_all"), s.get("u_all"), s.get("status"))
+        s.get("pi_all"), s.get("lam_all"), s.get("t_all"), s.get("lam_x0", 0)
+    loose = {}
+    for cond_N in sorted({(N + 1) // 2, (N + 2) // 3} - {N, 0}):
+        with cf.BatchSolver(B, N, TS) as s:
+            s.set_option("qp_cond_N", cond_N)
+            s.set_problem(w).solve(1)
+            loose[f"qp_cond_N={cond_N}"] = (s.get("x_all"), s.get("u_all"), s.get("status"))
+            s.set_problem(w).prepare().feedback()
+            loose[f"qp_cond_N={cond_N} split"] = (s.get("x_all"), s.get("u_all"), s.get("status"))
+            s.set("x", w["x_init"]).set("u", w["u_init"])
+            s.solve_from_host(w["x0"], w["yref"], w["yref_e"], n_chunks=4)
+            loose[f"qp_cond_N={cond_N} host_fed"] = (s.get("x_all"), s.get("u_all"), s.get("status"))
+    Q = np.array([120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0, 0.06, 0.06, 0.06, 0.06])
+    tab = np.zeros((N + 1, 17, 17))
+    tab[:N] = np.diag(Q)
+    tab[N, :13, :13] = np.diag(50 * Q[:13])
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set("W_dense_table", tab)          # the default weights as full matrices: same problem, dense-Hessian kernel
+        s.set_problem(w).solve(1)
+        loose["W_dense_table"] = (s.get("x_all"), s.get("u_all"), s.get("status"))
+        s.set("W_dense_table", wl.dense_weight_table(N, seed=1))
+        s.set_problem(w).solve(1)
+        s.get("x_all")
     ref = res["two_kernels"]
+    for k, v in loose.items():   # same QP solution, different arithmetic: interior-point tolerances
+        ex = float(np.abs(v[0] - ref[0]).max())
+        eu = float(np.abs(v[1] - ref[1]).max())
+        ok = (v[2] == ref[2]).all() and ex < 1e-5 and eu < 1e-5
+        print(f"N={N} {k:22s} status_ok={int((v[2] == 0).sum())}/{B} max|dx|={ex:.2e} max|du|={eu:.2e} {'OK' if ok else 'MISMATCH'}")
+        assert ok, k
     for k, v in res.items():
         ex = float(np.abs(v[0] - ref[0]).max())
         eu = float(np.abs(v[1] - ref[1]).max())
