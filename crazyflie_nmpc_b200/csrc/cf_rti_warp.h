@@ -43,6 +43,8 @@
 #define CF_MROWS 18                       // rows of [B';A';res_b'] held per stage
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
 #define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
+#define CF_LUST 6                         // row stride of the 18 x 4 block while it is factorised in shared memory: 128-bit
+                                          //   row loads without bank conflicts, column stores 2-way instead of 5-way
 #define CF_PST 14                         // row stride of the cost-to-go Hessian once expanded in shared memory
 #define CF_LX 92                          // cost-to-go Hessian P of the state block in HBM: packed lower triangle (91) + pad
 // One contiguous block per stage in the scratch slot.  The field order makes whatever a sweep needs of a stage ONE
@@ -547,14 +549,16 @@ struct CfWarpT
 
     // =============================================================== IPM pieces
     // y[c] = sum_{r < 17} M[r][c] v[r]  (+ M[17][c] when `with_row17`) for the state column c of lanes 4..16, the 18 rows of
-    // a column shared by the lane pair (L, L ^ 16): the state lane takes rows 0..9, its partner (lanes 20..31 and lane 0)
+    // a column shared by a lane pair: the state lane takes rows 0..9, its partner (lanes 20..31 and lane 17)
     // rows 10..17; one exchange combines them.  Five 128-bit loads of M and of v per lane instead of nine, and dependent
     // chains of 5 instead of 9 multiply-adds (the column products were 21 % of the kernel's shared-memory wavefronts,
     // profiles/prof_r2_v15_wavefronts.txt).  Mk: staged [B';A';b'] (element (r,c) at c*18 + r), v: 20-double vector.
     CF_MEM double col_gemv(const double *Mk, const double *v, const bool with_row17) const
     {
-        const int lp = lane ^ 16;
-        const bool lo = lane >= CF_NU && lane < CF_NV, hi = lp >= CF_NU && lp < CF_NV;
+        // partner of state lane L: L ^ 16 (lanes 20..31), except lane 16 whose partner is lane 17 (lane 0 would collide with
+        // lane 5 on the banks of its column); lanes 0..3, 18, 19 compute a throw-away duplicate of column 0
+        const int lp = lane == 16 ? 17 : (lane == 17 ? 16 : lane ^ 16);
+        const bool lo = lane >= CF_NU && lane < CF_NV, hi = lane == 17 || lane >= 20;
         const int cc = lo ? lane - CF_NU : (hi ? lp - CF_NU : 0), r0 = lo ? 0 : 10;
         const double *Mc = Mk + cc * CF_MROWS + r0, *vc = v + r0;
         double s0 = 0.0, s1 = 0.0;
@@ -608,7 +612,8 @@ struct CfWarpT
         fetch(N & 1, N, 0, B_M);
         const bool ul = lane < CF_NU, vl = lane < CF_NV;
         const bool xl = lane >= CF_NU && vl;
-        const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
+        // (idle lanes read element 8, not 0: in the second half-warp lane 16 sits on the banks of element 0)
+        const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 8;
         // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
         const int fg = lane >> 2, fq = lane & 3;
         const int rl = lane < CF_MROWS ? lane : 17;
@@ -817,7 +822,7 @@ struct CfWarpT
                 CF_UNROLL
                 for (int t = 0; t < 3; t++) {
                     const int r = 8 * t + fg;
-                    if (r < CF_MROWS) cf_st2(LUs + r * 4 + 2 * fq, sx[t][0][0], sx[t][0][1]);
+                    if (r < CF_MROWS) cf_st2(LUs + r * CF_LUST + 2 * fq, sx[t][0][0], sx[t][0][1]);
                 }
             }
             cf_syncwarp();
@@ -826,19 +831,19 @@ struct CfWarpT
             {
                 // lanes 18..31 carry no row: they must not read row 17 while lane 17 rewrites it below (racecheck)
                 cf_d2 o01 = {0.0, 0.0}, o23 = {0.0, 0.0};
-                if (lane < CF_MROWS) { o01 = cf_ld2(LUs + rl * 4); o23 = cf_ld2(LUs + rl * 4 + 2); }
+                if (lane < CF_MROWS) { o01 = cf_ld2(LUs + rl * CF_LUST); o23 = cf_ld2(LUs + rl * CF_LUST + 2); }
                 double o[CF_NU] = {o01.x, o01.y, o23.x, o23.y}, og[CF_NU];
                 CF_UNROLL
                 for (int j = 0; j < CF_NU; j++) {
                     double v = o[j];
                     CF_UNROLL
-                    for (int c = 0; c < j; c++) v -= o[c] * LUs[j * 4 + c];
+                    for (int c = 0; c < j; c++) v -= o[c] * LUs[j * CF_LUST + c];
                     const double piv = cf_shfl(v, j);
                     double dj, inv;
                     cf_sqrt_rsqrt(piv, dj, inv);
                     if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; flags |= CF_FLAG_BAD_PIVOT; }   // piv is warp-uniform
                     o[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
-                    if (lane < CF_MROWS) LUs[rl * 4 + j] = o[j];   // lanes 18..31 mirror row 17 in registers only (racecheck)
+                    if (lane < CF_MROWS) LUs[rl * CF_LUST + j] = o[j];   // lanes 18..31 mirror row 17 in registers only (racecheck)
                     og[j] = (rl == j) ? inv : o[j];
                     cf_syncwarp();
                 }
@@ -859,7 +864,7 @@ struct CfWarpT
             CF_UNROLL
             for (int t = 0; t < 3; t++) {
                 const int r = 8 * t + fg;
-                la[t] = (r < CF_MROWS) ? LUs[r * 4 + fq] : 0.0;
+                la[t] = (r < CF_MROWS) ? LUs[r * CF_LUST + fq] : 0.0;
             }
             cf_syncwarp();  // all reads of PS/PV (first product) are long complete; they are rewritten below
             {
@@ -941,7 +946,8 @@ struct CfWarpT
         if (lane < 20) { XS[lane] = 0.0; PS[lane] = 0.0; }
         const bool ul = lane < CF_NU, vl = lane < CF_NV;
         const bool xl = lane >= CF_NU && vl;
-        const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 0;
+        // (idle lanes read element 8, not 0: in the second half-warp lane 16 sits on the banks of element 0)
+        const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 8;
         // P_{k+1} travels packed (lower triangle) and is expanded to full symmetric rows in shared memory: element
         // e = lane + 32 t of the packed triangle goes to (i,j) and (j,i)
         double *PE = sm + CF_SM_P;
