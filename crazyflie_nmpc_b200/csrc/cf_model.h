@@ -12,14 +12,29 @@
 // (tests/test_spec_generated.py).
 #pragma once
 #include "cf_simt.h"
-#include "cf_spec_generated.h"
-static_assert(CF_SPEC_NX == 13 && CF_SPEC_NU == 4, "the warp mapping is built for nx = 13, nu = 4");
+// The OCP description the library is built for.  Default: the Crazyflie OCP; another generated header (tools/gen_spec.py
+// --model ...) is selected with -DCF_SPEC_HEADER='"cf_spec_pendulum.h"' -- the same kernel sources then compile for its
+// sizes: preparation kernel + the dense-stage feedback program of cf_pcond_warp.h.  The hand-tuned
+// uncondensed feedback program (cf_rti_warp.h) and the node-specific kernels exist for nx = 13, nu = 4 only.
+#ifndef CF_SPEC_HEADER
+#define CF_SPEC_HEADER "cf_spec_generated.h"
+#endif
+#include CF_SPEC_HEADER
 
-#define CF_NX 13
-#define CF_NU 4
-#define CF_NV 17  // stage variables [u; x]  (acados/ocp_nlp/ocp_nlp_common.h:229)
-#define CF_NY 17
+#define CF_NX CF_SPEC_NX
+#define CF_NU CF_SPEC_NU
+#define CF_NV (CF_NX + CF_NU)  // stage variables [u; x]  (acados/ocp_nlp/ocp_nlp_common.h:229)
+#define CF_NY CF_NV            // cost output y = [x; u]
+#if CF_SPEC_NX == 13 && CF_SPEC_NU == 4
+#define CF_CRAZYFLIE 1
+#else
+#define CF_CRAZYFLIE 0
+#endif
+static_assert(CF_NV + 1 <= 32, "one row of the (nv + 1) x nx stage matrices per lane");
+static_assert(CF_NV % 2 == 1, "nv + 1 rows must be an even number (16-byte aligned columns): pad the model by one variable");
+static_assert(CF_NX <= 16, "two 8-column tiles hold the cost-to-go Hessian");
 
+#if CF_CRAZYFLIE
 struct CfModel
 {
     // export_ode_model.py:34-42
@@ -96,6 +111,8 @@ CF_DEV void cf_add_ju_col_hand(const double *u, int j, double *o)
     o[11] += -2 * CfModel::Ct * CfModel::arm * s11 * uj / CfModel::Iyy;
     o[12] += -2 * CfModel::Cd * s12 * uj / CfModel::Izz;
 }
+
+#endif  // CF_CRAZYFLIE (hand-derived cross-check)
 
 // ---- what the kernels call: the generated model
 CF_DEV void cf_ode(const double *x, const double *u, double *f) { cf_ode_gen(x, u, f); }

@@ -52,21 +52,23 @@ struct CfPcWarpT
         HSZ = ((NVB * (NVB + 1)) / 2 + 1) & ~1,       // packed lower triangle of the condensed Hessian
         // stage block: same field order as the uncondensed program (cf_rti_warp.h), the Hessian in front so that only the
         // residual+factorisation sweep stages it
-        P_H = 0, R_UX = HSZ, R_PI = R_UX + MR, R_DPI = R_PI + 14, R_RQ = R_DPI + 14, R_D = R_RQ + MR, R_BKP = R_D + NB2,
-        R_PB = R_BKP + NB2, R_DLAM = R_PB + 14, R_DT = R_DLAM + NB2, R_LAM = R_DT + NB2, R_T = R_LAM + NB2, R_DUX = R_T + NB2,
+        P_H = 0, R_UX = HSZ, R_PI = R_UX + MR, R_DPI = R_PI + CF_XP, R_RQ = R_DPI + CF_XP, R_D = R_RQ + MR, R_BKP = R_D + NB2,
+        R_PB = R_BKP + NB2, R_DLAM = R_PB + CF_XP, R_DT = R_DLAM + NB2, R_LAM = R_DT + NB2, R_T = R_LAM + NB2, R_DUX = R_T + NB2,
         B_M = R_DUX + MR, MSZ = MR * CF_NX, B_RD = B_M + MSZ, R_RESD = B_RD, R_RESM = R_RESD + NB2, R_RESG = R_RESM + NB2,
-        R_RESB = R_RESG + MR, B_LU = R_RESB + 14, LUSZ = MR * NUB,   // factor columns, element (r,j) at j*MR + r
+        R_RESB = R_RESG + MR, B_LU = R_RESB + CF_XP, LUSZ = MR * NUB,   // factor columns, element (r,j) at j*MR + r
         B_PX = B_LU + LUSZ, SB = B_PX + CF_LX,
-        RT = (MR + 7) / 8, CTV = (NVB + 7) / 8, T0 = NUB / 8, KSU = NUB / 4,
-        ALP = 20, PCO = 4,                           // P in shared memory as in the uncondensed program: element (i,j) at i*20 + 4 + j
+        RT = (MR + 7) / 8, CTV = (NVB + 7) / 8, T0 = NUB / 8, KSU = (NUB + 3) / 4, PKT = (CF_TRI_NX + 31) / 32,
+        ALP = 20, PCO = 4 - (NUB & 1),               // P in shared memory as in the uncondensed program: element (i,j) at i*20 + 4 + j
+                                                     //   (3 + j when the number of inputs is odd: the tile stores stay 16-byte aligned)
         WST = 20,                                    // row stride of W
-        BUFSZ = B_RD,
-        SM_BUF0 = 0, SM_BUF1 = BUFSZ, SM_P = 2 * BUFSZ, SM_V0 = SM_P + 13 * ALP, VST = 32, SM_V1 = SM_V0 + VST, SM_V2 = SM_V1 + VST,
+        BUFSZ = (B_RD > HSZ + MR * WST) ? B_RD : HSZ + MR * WST,   // the W block (MR x 20) overlays the staged block behind the Hessian
+        SM_BUF0 = 0, SM_BUF1 = BUFSZ, SM_P = 2 * BUFSZ, SM_V0 = SM_P + CF_NX * ALP, VST = 32, SM_V1 = SM_V0 + VST, SM_V2 = SM_V1 + VST,
         SM_BAR = SM_V2 + VST, SM_PAR = SM_BAR + 4, SM_DOUBLES = SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1)
     };
     static_assert(MR <= 32 && (MR & 1) == 0, "one row per lane");
-    static_assert(B_RD >= SB - R_LAM && B_RD >= B_PX - R_BKP && MR * WST <= B_RD - HSZ, "staging buffers");
-    static_assert((HSZ & 1) == 0 && (MSZ & 1) == 0 && (LUSZ & 1) == 0 && (SB & 1) == 0 && (ALP * 13) % 2 == 0, "16-byte alignment");
+    static_assert(BUFSZ >= B_RD && BUFSZ >= SB - R_LAM && BUFSZ >= B_PX - R_BKP && MR * WST <= BUFSZ - HSZ, "staging buffers");
+    static_assert((HSZ & 1) == 0 && (MSZ & 1) == 0 && (LUSZ & 1) == 0 && (SB & 1) == 0 && (ALP * CF_NX) % 2 == 0, "16-byte alignment");
+    static_assert(CF_NX + PCO <= ALP && CF_NX <= 16, "two 8-column tiles hold the cost-to-go Hessian");
     static_assert(2 * BS * CF_PREP_STAGE + MSZ + HSZ <= SM_V2, "staging area of the condensing pass (buffers, P and two vectors; V2 holds the weights)");
 
     const CfParams *P, *PG;
@@ -176,7 +178,7 @@ struct CfPcWarpT
                     // bounds (ocp_nlp_constraints_bgh.c:1634-1636) and OCP_QP_INIT_VAR scheme 1 (x_ocp_qp_ipm.c:1636-1769)
                     const double uk = ug[k * CF_NU + e];
                     double lb = (k == 0) ? P->lbu0[e] : P->lbu[e], ub = (k == 0) ? P->ubu0[e] : P->ubu[e];
-                    if (BST) { lb = BST[k * 8 + e]; ub = BST[k * 8 + 4 + e]; }
+                    if (BST) { lb = BST[k * 2 * CF_NU + e]; ub = BST[k * 2 * CF_NU + CF_NU + e]; }
                     const double dl = lb - uk, du = uk - ub;
                     double tl = -dl, tu = -du;
                     if (tl < CF_THR0) {
@@ -187,7 +189,7 @@ struct CfPcWarpT
                     bk[R_T + lane] = tl; bk[R_T + NUB + lane] = tu;
                     bk[R_LAM + lane] = CF_MU0 / tl; bk[R_LAM + NUB + lane] = CF_MU0 / tu;
                 }
-                const double *Mrow = Mj + (mine ? e : (lane == NVB ? 17 : (xl ? CF_NU + ci : 0)));   // this lane's row of the record
+                const double *Mrow = Mj + (mine ? e : (lane == NVB ? CF_NV : (xl ? CF_NU + ci : 0)));   // this lane's row of the record
                 if (j == 0) {
                     // G_1 = G_0 A' + [E B'; 0; b'] with G_0 = [0; I; 0]: the rows of the record itself, no product
                     const bool any = mine || xl || lane == NVB;
@@ -246,13 +248,21 @@ struct CfPcWarpT
                 for (int c = 0; c < CF_NX; c++) {
                     const double *Ac = Mj + c * CF_MROWS + CF_NU;
                     double s0 = 0.0, s1 = 0.0;
-                    CF_UNROLL
-                    for (int ip = 0; ip < 6; ip++) {
-                        const cf_d2 a2 = cf_ld2(Ac + 2 * ip);
-                        s0 += grow[2 * ip] * a2.x;
-                        s1 += grow[2 * ip + 1] * a2.y;
+                    if constexpr ((CF_NU & 1) == 0) {   // 16-byte aligned column start
+                        CF_UNROLL
+                        for (int ip = 0; ip < CF_NX / 2; ip++) {
+                            const cf_d2 a2 = cf_ld2(Ac + 2 * ip);
+                            s0 += grow[2 * ip] * a2.x;
+                            s1 += grow[2 * ip + 1] * a2.y;
+                        }
+                        if (CF_NX & 1) s0 += grow[CF_NX - 1] * Ac[CF_NX - 1];
+                    } else {
+                        CF_UNROLL
+                        for (int ip = 0; ip < CF_NX; ip++) {
+                            if (ip & 1) s1 += grow[ip] * Ac[ip];
+                            else s0 += grow[ip] * Ac[ip];
+                        }
                     }
-                    s0 += grow[12] * Ac[12];
                     const double add = (mine || lane == NVB) ? Mrow[c * CF_MROWS] : 0.0;
                     gn[c] = (s0 + s1) + add;
                 }
@@ -266,7 +276,7 @@ struct CfPcWarpT
                     // full weight matrix of stage k0 (ocp_nlp_cost_ls.c:743-772,883-912): Hessian dt (Cyt W_chol)(Cyt W_chol)'
                     // (the product comes from the host, [u;x] order), gradient dt Cyt W (y - yref).  Stage 0: its states are
                     // eliminated -- decoupled dummies here -- and leave S xbar in the input gradient (x_ocp_qp_red.c:354).
-                    const double *Hd = WD + (long) k0 * 578, *Wp = Hd + 289;
+                    const double *Hd = WD + (long) k0 * (2 * CF_NV * CF_NV), *Wp = Hd + CF_NV * CF_NV;
                     const double h = dt(k0);
                     double *RS = sm + SM_V0, *XB = sm + SM_V1;
                     cf_syncwarp();
@@ -321,7 +331,7 @@ struct CfPcWarpT
             double gN = xl ? PREP[(long) N * CF_PREP_STAGE + CF_NU + ci] : 0.0;
             if constexpr (BS == 1) {
                 if (WD) {   // full terminal weight (13 x 13 state block of table row N; terminal scaling 1)
-                    const double *Hd = WD + (long) N * 578, *Wp = Hd + 289;
+                    const double *Hd = WD + (long) N * (2 * CF_NV * CF_NV), *Wp = Hd + CF_NV * CF_NV;
                     double *RS = sm + SM_V0;
                     cf_syncwarp();
                     if (xl) RS[lane] = xg[N * CF_NX + ci] - yref_eg[ci];
@@ -353,12 +363,12 @@ struct CfPcWarpT
     CF_MEM void eliminate_x0(double *MS, const double *xg, const double *x0g)
     {
         const bool xs = lane >= CF_NU && lane < CF_NV;
-        double *Mrow = MS + (lane < CF_NV ? lane : 17);
+        double *Mrow = MS + (lane < CF_NV ? lane : CF_NV);
         const double xbar = xs ? (x0g[lane - CF_NU] - xg[lane - CF_NU]) : 0.0;
         CF_NOUNROLL
         for (int i = 0; i < CF_NX; i++) {
             const double tot = cf_warp_sum(xs ? Mrow[i * CF_MROWS] * xbar : 0.0);
-            if (lane == 17) MS[i * CF_MROWS + 17] = tot + MS[i * CF_MROWS + 17];
+            if (lane == CF_NV) MS[i * CF_MROWS + CF_NV] = tot + MS[i * CF_MROWS + CF_NV];
             else if (xs) Mrow[i * CF_MROWS] = 0.0;
         }
         cf_syncwarp();
@@ -388,14 +398,14 @@ struct CfPcWarpT
                 const int hi = i > j ? i : j, lo = i > j ? j : i;
                 pa[kk][hh] = ok ? hi * ALP + lo + PCO : -1;
             }
-        int pk[3];      // packed lower triangle of P_{k+1}: element e = lane + 32 t
+        int pk[PKT];    // packed lower triangle of P_{k+1}: element e = lane + 32 t
         CF_UNROLL
-        for (int t = 0; t < 3; t++) {
+        for (int t = 0; t < PKT; t++) {
             const int e = lane + 32 * t;
             int i = 0;
             CF_UNROLL
             for (int q = 1; q < CF_NX; q++) i += (e >= cf_tri(q)) ? 1 : 0;
-            pk[t] = (e < 91) ? i * ALP + (e - cf_tri(i)) + PCO : -1;
+            pk[t] = (e < CF_TRI_NX) ? i * ALP + (e - cf_tri(i)) + PCO : -1;
         }
         int trr[RT];    // packed row starts of the fragment rows
         CF_UNROLL
@@ -414,7 +424,7 @@ struct CfPcWarpT
             if (do_factor && kl) {
                 double *LFk = blk(k) + B_PX;
                 CF_UNROLL
-                for (int t = 0; t < 3; t++)
+                for (int t = 0; t < PKT; t++)
                     if (pk[t] >= 0) LFk[lane + 32 * t] = PS[pk[t]];
             }
             double *VS = buf(bf);
@@ -467,12 +477,12 @@ struct CfPcWarpT
                 {   // res_g += [B';A'] pi_k
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
-                    for (int cp = 0; cp < 6; cp++) {
+                    for (int cp = 0; cp < CF_NX / 2; cp++) {
                         const cf_d2 p2 = cf_ld2(PIS + 2 * cp);
                         s0 += Mk[(2 * cp) * MR + lv] * p2.x;
                         s1 += Mk[(2 * cp + 1) * MR + lv] * p2.y;
                     }
-                    s0 += Mk[12 * MR + lv] * PIS[12];
+                    if (CF_NX & 1) s0 += Mk[(CF_NX - 1) * MR + lv] * PIS[CF_NX - 1];
                     rg += s0 + s1;
                 }
                 {   // res_b = (b - x+) + [A B] ux   (column ci: rows 0..NVB-1, row NVB = b)
@@ -501,7 +511,7 @@ struct CfPcWarpT
             // ---------------- factorisation
             if (!do_factor) continue;
             if (!kl) {
-                for (int i = lane; i < 13 * ALP; i += 32) PS[i] = 0.0;
+                for (int i = lane; i < CF_NX * ALP; i += 32) PS[i] = 0.0;
                 cf_syncwarp();
                 if (xl) {
                     // P_N = state block of the terminal Hessian (+ reg); lower triangle (dense with full weight matrices)
@@ -593,7 +603,8 @@ struct CfPcWarpT
                 for (int tp = 0; tp < CTV; tp++) {
                     if (tp > t || 8 * tp >= NUB) continue;
                     const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
-                    if (r < MR && c0 < NUB) { LUs[c0 * MR + r] = sx[t][tp][0]; LUs[(c0 + 1) * MR + r] = sx[t][tp][1]; }
+                    if (r < MR && c0 < NUB) LUs[c0 * MR + r] = sx[t][tp][0];
+                    if (r < MR && c0 + 1 < NUB) LUs[(c0 + 1) * MR + r] = sx[t][tp][1];
                 }
             }
             cf_syncwarp();
@@ -624,6 +635,7 @@ struct CfPcWarpT
                 if (lane == NVB) {
                     CF_UNROLL
                     for (int jp = 0; jp < NUB / 2; jp++) cf_st2(rk + R_DUX + 2 * jp, o[2 * jp], o[2 * jp + 1]);
+                    if (NUB & 1) rk[R_DUX + NUB - 1] = o[NUB - 1];
                 }
             }
             // ---- Schur complement: S_xx -= Ls Ls' (K = NUB)
@@ -632,7 +644,7 @@ struct CfPcWarpT
             for (int t = 0; t < RT; t++) {
                 const int r = 8 * t + fg;
                 CF_UNROLL
-                for (int ks = 0; ks < KSU; ks++) la[t][ks] = (t >= T0 && r < MR) ? LUs[(4 * ks + fq) * MR + r] : 0.0;
+                for (int ks = 0; ks < KSU; ks++) la[t][ks] = (t >= T0 && r < MR && 4 * ks + fq < NUB) ? LUs[(4 * ks + fq < NUB ? 4 * ks + fq : 0) * MR + r] : 0.0;
             }
             cf_syncwarp();
             CF_UNROLL
@@ -690,15 +702,15 @@ struct CfPcWarpT
         const bool vl = lane < NVB, ul = lane < NUB, xl = lane >= NUB && vl;
         const int ci = xl ? lane - NUB : 0, lv = vl ? lane : 0, ju = ul ? lane : 0;
         double *PE = sm + SM_P;   // P_{k+1} expanded to full symmetric rows, stride CF_PST
-        int pe_a[3], pe_b[3];
+        int pe_a[PKT], pe_b[PKT];
         CF_UNROLL
-        for (int t = 0; t < 3; t++) {
+        for (int t = 0; t < PKT; t++) {
             const int e = lane + 32 * t;
             int i = 0;
             CF_UNROLL
             for (int q = 1; q < CF_NX; q++) i += (e >= cf_tri(q)) ? 1 : 0;
             const int j = e - cf_tri(i);
-            pe_a[t] = (e < 91) ? i * CF_PST + j : -1;
+            pe_a[t] = (e < CF_TRI_NX) ? i * CF_PST + j : -1;
             pe_b[t] = j * CF_PST + i;
         }
         CF_NOUNROLL
@@ -715,7 +727,7 @@ struct CfPcWarpT
             const double *Mk = VS + B_M, *LU = VS + B_LU;
             if (need_pi) {
                 CF_UNROLL
-                for (int t = 0; t < 3; t++) {
+                for (int t = 0; t < PKT; t++) {
                     if (pe_a[t] >= 0) {
                         const double v = VS[B_PX + lane + 32 * t];
                         PE[pe_a[t]] = v;
@@ -728,12 +740,12 @@ struct CfPcWarpT
             {
                 double v0 = -VS[R_DUX + ju], v1 = 0.0;
                 CF_UNROLL
-                for (int ip = 0; ip < 6; ip++) {
+                for (int ip = 0; ip < CF_NX / 2; ip++) {
                     const cf_d2 x2 = cf_ld2(XS + 2 * ip);
                     v0 -= LU[ju * MR + NUB + 2 * ip] * x2.x;
                     v1 -= LU[ju * MR + NUB + 2 * ip + 1] * x2.y;
                 }
-                v0 -= LU[ju * MR + NUB + 12] * XS[12];
+                if (CF_NX & 1) v0 -= LU[ju * MR + NUB + CF_NX - 1] * XS[CF_NX - 1];
                 v = v0 + v1;
             }
             const double invd = LU[ju * MR + ju];
@@ -789,12 +801,12 @@ struct CfPcWarpT
                 const double *Li = PE + ci * CF_PST;
                 double z0 = pnext, z1 = 0.0;
                 CF_UNROLL
-                for (int cp = 0; cp < 6; cp++) {
+                for (int cp = 0; cp < CF_NX / 2; cp++) {
                     const cf_d2 p2 = cf_ld2(Li + 2 * cp), x2 = cf_ld2(XS + 2 * cp);
                     z0 += p2.x * x2.x;
                     z1 += p2.y * x2.y;
                 }
-                z0 += Li[12] * XS[12];
+                if (CF_NX & 1) z0 += Li[CF_NX - 1] * XS[CF_NX - 1];
                 if (xl) rec(k + 1)[R_DPI + ci] = z0 + z1;
             }
             dxk = dxn;
@@ -836,12 +848,12 @@ struct CfPcWarpT
             if (vl) {
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
-                for (int cp = 0; cp < 6; cp++) {
+                for (int cp = 0; cp < CF_NX / 2; cp++) {
                     const cf_d2 t2 = cf_ld2(TS + 2 * cp);
                     s0 += Mk[(2 * cp) * MR + lane] * t2.x;
                     s1 += Mk[(2 * cp + 1) * MR + lane] * t2.y;
                 }
-                s0 += Mk[12 * MR + lane] * TS[12];
+                if (CF_NX & 1) s0 += Mk[(CF_NX - 1) * MR + lane] * TS[CF_NX - 1];
                 rhs += s0 + s1;
             }
             // TRSV_LNN_MN(nv, nu)
@@ -954,13 +966,13 @@ struct CfPcWarpT
                 const double *Mc = Mj + ci * CF_MROWS;
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
-                for (int rp = 0; rp < 8; rp++) {
+                for (int rp = 0; rp < (CF_NV - 1) / 2; rp++) {
                     const cf_d2 m2 = cf_ld2(Mc + 2 * rp), d2 = cf_ld2(DS + 2 * rp);
                     s0 += m2.x * d2.x;
                     s1 += m2.y * d2.y;
                 }
-                const cf_d2 m2 = cf_ld2(Mc + 16);
-                s0 += m2.x * DS[16];
+                const cf_d2 m2 = cf_ld2(Mc + CF_NV - 1);   // last variable row and the b row
+                s0 += m2.x * DS[CF_NV - 1];
                 xs = xs_l ? m2.y + (s0 + s1) : 0.0;
                 cf_syncwarp();
             }
@@ -993,7 +1005,7 @@ CF_DEV void cf_pcond_instance(const CfParams *Pg, const CfBatchView &bv, const C
         const int lane = cf_lane();
         const double *src = reinterpret_cast<const double *>(Pg);
         double *dst = sm + W::SM_PAR;
-        dst[lane] = src[lane];
+        if (lane < CF_PAR_DOUBLES) dst[lane] = src[lane];
         if (lane + 32 < CF_PAR_DOUBLES) dst[lane + 32] = src[lane + 32];
         cf_syncwarp();
         if (bv.W_b && lane < CF_NY) P->Wdiag[lane] = bv.W_b[(long) inst * CF_NY + lane];

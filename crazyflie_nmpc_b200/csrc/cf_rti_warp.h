@@ -40,13 +40,16 @@
 #endif
 
 // ------------------------------------------------------------------ sizes / layout
-#define CF_MROWS 18                       // rows of [B';A';res_b'] held per stage
+#define CF_MROWS (CF_NV + 1)              // rows of [B';A';res_b'] held per stage (18)
 #define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
-#define CF_LU 72                          // factor, input columns: 18 x 4, (r,j) at r*4 + j
+#define CF_LU (CF_MROWS * CF_NU)          // factor, input columns: 18 x 4, (r,j) at r*4 + j
+#define CF_XP ((CF_NX + 1) & ~1)          // a state vector padded to an even number of doubles (14)
+#define CF_UP ((CF_NU + 1) & ~1)          // an input vector padded likewise (4)
+#define CF_TRI_NX ((CF_NX * (CF_NX + 1)) / 2)   // packed lower triangle of an nx x nx matrix (91)
 #define CF_LUST 6                         // row stride of the 18 x 4 block while it is factorised in shared memory: 128-bit
                                           //   row loads without bank conflicts, column stores 2-way instead of 5-way
-#define CF_PST 14                         // row stride of the cost-to-go Hessian once expanded in shared memory
-#define CF_LX 92                          // cost-to-go Hessian P of the state block in HBM: packed lower triangle (91) + pad
+#define CF_PST CF_XP                      // row stride of the cost-to-go Hessian once expanded in shared memory (14)
+#define CF_LX ((CF_TRI_NX + 1) & ~1)      // cost-to-go Hessian P of the state block in HBM: packed lower triangle (91) + pad
 // One contiguous block per stage in the scratch slot.  The field order makes whatever a sweep needs of a stage ONE
 // contiguous, 16-byte aligned range = one TMA bulk copy, issued one stage ahead of the arithmetic:
 //   residual+factorisation sweep [0, B_RD)      rhs-only backward sweep [R_BKP, B_PX)      forward sweep [R_LAM, CF_SB)
@@ -61,10 +64,17 @@
 //   B_LU   factor of the 4 input columns (18 x 4), INVERSE pivots on the diagonal (like BLASFEO's dA)
 //   B_PX   packed lower triangle of P_{k+1} (what the forward sweep of stage k multiplies with, after expanding it to
 //          full symmetric rows in shared memory; written by the factorisation of stage k+1)
-enum { R_UX = 0, R_PI = 18, R_DPI = 32, R_RQ = 46, R_D = 64, R_BKP = 72, R_PB = 80, R_DLAM = 94, R_DT = 102, R_LAM = 110,
-       R_T = 118, R_DUX = 126, B_M = 144, B_RD = B_M + CF_MSZ, R_RESD = B_RD, R_RESM = B_RD + 8, R_RESG = B_RD + 16,
-       R_RESB = B_RD + 34, B_LU = B_RD + 48, B_PX = B_LU + CF_LU, CF_SB = B_PX + CF_LX };   // 590 doubles per stage
+enum { R_UX = 0, R_PI = R_UX + CF_MROWS, R_DPI = R_PI + CF_XP, R_RQ = R_DPI + CF_XP, R_D = R_RQ + CF_MROWS, R_BKP = R_D + 2 * CF_NU,
+       R_PB = R_BKP + 2 * CF_NU, R_DLAM = R_PB + CF_XP, R_DT = R_DLAM + 2 * CF_NU, R_LAM = R_DT + 2 * CF_NU, R_T = R_LAM + 2 * CF_NU,
+       R_DUX = R_T + 2 * CF_NU, B_M = R_DUX + CF_MROWS, B_RD = B_M + CF_MSZ, R_RESD = B_RD, R_RESM = R_RESD + 2 * CF_NU,
+       R_RESG = R_RESM + 2 * CF_NU, R_RESB = R_RESG + CF_MROWS, B_LU = R_RESB + CF_XP, B_PX = B_LU + CF_LU,
+       CF_SB = B_PX + CF_LX };   // 590 doubles per stage (nx = 13, nu = 4)
 static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 && CF_SB % 2 == 0, "16-byte alignment of TMA ranges");
+#if CF_CRAZYFLIE
+static_assert(R_PI == 18 && R_DPI == 32 && R_RQ == 46 && R_D == 64 && R_BKP == 72 && R_PB == 80 && R_DLAM == 94 && R_DT == 102 &&
+              R_LAM == 110 && R_T == 118 && R_DUX == 126 && B_M == 144 && B_RD == 378 && R_RESM == B_RD + 8 && R_RESG == B_RD + 16 &&
+              R_RESB == B_RD + 34 && B_LU == B_RD + 48 && CF_SB == 590, "stage block layout of the tuned program");
+#endif
 
 // HPIPM arguments in effect for the reference configuration (BALANCE mode + acados
 // overrides): acados/acados/ocp_qp/ocp_qp_hpipm.c:96-108, x_ocp_qp_ipm.c:133-161
@@ -104,7 +114,7 @@ struct CfParams
     int lin_res_check;     // != 0: evaluate the linear-system residuals of every solve (sets the CF_FLAG_LIN_RES_* bits)
     int pad_;
 };
-#define CF_PAR_DOUBLES 49  // sizeof(CfParams) / 8: the per-warp copy in shared memory
+#define CF_PAR_DOUBLES (CF_NY + CF_NX + 4 * CF_NU + 3)  // sizeof(CfParams) / 8 (49): the per-warp copy in shared memory
 static_assert(sizeof(CfParams) == CF_PAR_DOUBLES * 8, "CfParams layout");
 
 struct CfBatchView
@@ -167,12 +177,12 @@ static inline
 #endif
     long cf_mult_stride(int N) { return ((long) N * 29 + 13 + 169 + 1) & ~1L; }
 // layout of the prepared linearisation of one instance (doubles)
-#define CF_PREP_STAGE (CF_MSZ + 18)
+#define CF_PREP_STAGE (CF_MSZ + CF_MROWS)
 static inline
 #if !defined(CF_SIMT_EMU)
     __host__ __device__
 #endif
-    long cf_prep_stride(int N) { return ((long) N * CF_PREP_STAGE + 18 + 15) & ~15L; }
+    long cf_prep_stride(int N) { return ((long) N * CF_PREP_STAGE + CF_MROWS + 15) & ~15L; }
 enum { CF_PROF_LIN = 0, CF_PROF_RF, CF_PROF_FWD, CF_PROF_BWD, CF_PROF_MUAFF, CF_PROF_UPDATE, CF_PROF_N };
 
 // offsets (in doubles) of the arrays inside one scratch slot; every block that the TMA engine
@@ -195,7 +205,9 @@ static inline
 }
 
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
-#define CF_SM_BUFSZ 480                        // sweeps: staged range of a stage block, double buffered
+#define CF_MAX2(a, b) ((a) > (b) ? (a) : (b))
+// sweeps: staged range of a stage block, double buffered (480 doubles for nx = 13, nu = 4)
+#define CF_SM_BUFSZ CF_MAX2(CF_MAX2(B_RD, CF_SB - R_LAM), CF_MAX2(CF_MAX2(B_PX - R_BKP, CF_MROWS * 20), 2 * CF_MSZ))
 #define CF_SM_BUF0 0
 #define CF_SM_BUF1 CF_SM_BUFSZ
 #define CF_SM_MS0 0                            // linearisation: [B';A';b'] staging, double buffered
@@ -204,7 +216,7 @@ static inline
 #define CF_SM_P (2 * CF_SM_BUFSZ)              // factorisation: P_{k+1}, 13 x 20 (the W / input-column block, 18 x 20,
                                                //   overlays the staged block of the stage being factorised);
                                                //   forward sweep: P_{k+1} expanded to full rows, 13 x 14
-#define CF_SM_V0 (CF_SM_P + 13 * CF_ALST)      // four 20-double broadcast vectors
+#define CF_SM_V0 (CF_SM_P + CF_NX * CF_ALST)   // four 20-double broadcast vectors
 #define CF_SM_V1 (CF_SM_V0 + 20)
 #define CF_SM_V2 (CF_SM_V1 + 20)
 #define CF_SM_V3 (CF_SM_V2 + 20)
@@ -212,8 +224,9 @@ static inline
 #define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
 #define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1354 doubles = 10832 bytes per warp
 static_assert(CF_SM_DOUBLES % 2 == 0, "every warp's shared-memory slice must start on a 16-byte boundary");
-static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && 18 * CF_ALST <= CF_SM_BUFSZ,
+static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && CF_MROWS * CF_ALST <= CF_SM_BUFSZ,
               "staging buffers");
+static_assert(!CF_CRAZYFLIE || CF_SM_BUFSZ == 480, "shared-memory layout of the tuned program");
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
@@ -327,28 +340,33 @@ struct CfWarpT
     // the four RK stage states, b_k = phi(x_k,u_k) - x_{k+1} (ocp_nlp_dynamics_cont.c:822-823) and u_k in the (still
     // unused) factor area of the stage block, from where the sensitivity pass stages them by TMA:
     //   NOM = [ xs_0 (13+1) | xs_1 | xs_2 | xs_3 | b (13+1) | u (4) ]  at B_LU
-#define CF_NOM 74
+#define CF_NOM (5 * CF_XP + CF_UP)    // 74
+    // where the NOM record sits in the stage block: the factor area, or -- preparation-only builds of small models whose
+    // factor area is too short -- the start of the block (nothing else of the block is touched by a preparation phase)
+#define CF_NOM_OFF ((CF_NOM <= CF_SB - B_LU) ? B_LU : 0)
+    static_assert(CF_NOM <= CF_SB - CF_NOM_OFF && (CF_NOM_OFF == B_LU || PH == CF_PH_PREPARATION || !CF_CRAZYFLIE), "NOM record");
     CF_MEM void nominal_pass(const double *xg, const double *ug)
     {
         CF_NOUNROLL
         for (int k = lane; k < N; k += 32) {
             const double h = dt(k);
-            double *nom = blk(k) + B_LU;
+            double *nom = blk(k) + CF_NOM_OFF;
             double x[CF_NX], xs[CF_NX], acc[CF_NX], uu[CF_NU];
             CF_UNROLL
             for (int i = 0; i < CF_NX; i++) { x[i] = xg[k * CF_NX + i]; xs[i] = x[i]; acc[i] = x[i]; }
             CF_UNROLL
             for (int i = 0; i < CF_NU; i++) uu[i] = ug[k * CF_NU + i];
-            cf_st2(nom + 5 * 14, uu[0], uu[1]);
-            cf_st2(nom + 5 * 14 + 2, uu[2], uu[3]);
+            CF_UNROLL
+            for (int i = 0; i + 1 < CF_NU; i += 2) cf_st2(nom + 5 * CF_XP + i, uu[i], uu[i + 1]);
+            if (CF_NU & 1) nom[5 * CF_XP + CF_NU - 1] = uu[CF_NU - 1];
             CF_UNROLL
             for (int s = 0; s < 4; s++) {
                 const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
                 const double a_next = (s == 2) ? 1.0 : 0.5;
                 const double bh = h * bw, ah = a_next * h;
                 CF_UNROLL
-                for (int i = 0; i < 12; i += 2) cf_st2(nom + s * 14 + i, xs[i], xs[i + 1]);
-                nom[s * 14 + 12] = xs[12];
+                for (int i = 0; i + 1 < CF_NX; i += 2) cf_st2(nom + s * CF_XP + i, xs[i], xs[i + 1]);
+                if (CF_NX & 1) nom[s * CF_XP + CF_NX - 1] = xs[CF_NX - 1];
                 double f[CF_NX];
                 cf_ode(xs, uu, f);
                 CF_UNROLL
@@ -360,18 +378,18 @@ struct CfWarpT
             CF_UNROLL
             for (int i = 0; i < CF_NX; i++) acc[i] -= xg[(k + 1) * CF_NX + i];
             CF_UNROLL
-            for (int i = 0; i < 12; i += 2) cf_st2(nom + 4 * 14 + i, acc[i], acc[i + 1]);
-            nom[4 * 14 + 12] = acc[12];
+            for (int i = 0; i + 1 < CF_NX; i += 2) cf_st2(nom + 4 * CF_XP + i, acc[i], acc[i + 1]);
+            if (CF_NX & 1) nom[4 * CF_XP + CF_NX - 1] = acc[CF_NX - 1];
         }
         pass_begin();   // the generic stores above are read back by bulk copies
         if (N > 0) fetch_nom(0, 0);
     }
-    CF_MEM double *nom_buf(int bf) const { return sm + 480 + bf * 80; }
+    CF_MEM double *nom_buf(int bf) const { return sm + CF_SM_BUFSZ + bf * ((CF_NOM + 7) & ~7); }   // (sm + 480 + bf * 80)
     CF_MEM void fetch_nom(int bf, int k)
     {
         if (lane == 0) {
             cf_bulk_expect(bar + bf, CF_NOM * 8);
-            cf_bulk_g2s_raw(nom_buf(bf), blk(k) + B_LU, CF_NOM * 8, bar + bf);
+            cf_bulk_g2s_raw(nom_buf(bf), blk(k) + CF_NOM_OFF, CF_NOM * 8, bar + bf);
         }
     }
 
@@ -395,14 +413,13 @@ struct CfWarpT
         cf_syncwarp();
         const double *NOMS = nom_buf(bf);
         double uu[CF_NU];
-        {
-            const cf_d2 u01 = cf_ld2(NOMS + 5 * 14), u23 = cf_ld2(NOMS + 5 * 14 + 2);
-            uu[0] = u01.x; uu[1] = u01.y; uu[2] = u23.x; uu[3] = u23.y;
-        }
+        CF_UNROLL
+        for (int i = 0; i + 1 < CF_NU; i += 2) { const cf_d2 v = cf_ld2(NOMS + 5 * CF_XP + i); uu[i] = v.x; uu[i + 1] = v.y; }
+        if (CF_NU & 1) uu[CF_NU - 1] = NOMS[5 * CF_XP + CF_NU - 1];
         // the accumulated sensitivity column of this lane lives in its row of the staging block (MS[c*18+lane]),
         // not in registers: the RK stage below is register-hungry enough
         const bool col = lane < CF_NV;
-        double *Mrow = MS + (col ? lane : 17);
+        double *Mrow = MS + (col ? lane : CF_NV);
         double Ss[CF_NX];
         CF_UNROLL
         for (int i = 0; i < CF_NX; i++) {
@@ -416,8 +433,8 @@ struct CfWarpT
             const double bh = h * bw, ah = a_next * h;
             double xs[CF_NX];
             CF_UNROLL
-            for (int i = 0; i < 12; i += 2) { const cf_d2 v = cf_ld2(NOMS + s * 14 + i); xs[i] = v.x; xs[i + 1] = v.y; }
-            xs[12] = NOMS[s * 14 + 12];
+            for (int i = 0; i + 1 < CF_NX; i += 2) { const cf_d2 v = cf_ld2(NOMS + s * CF_XP + i); xs[i] = v.x; xs[i + 1] = v.y; }
+            if (CF_NX & 1) xs[CF_NX - 1] = NOMS[s * CF_XP + CF_NX - 1];
             double ks[CF_NX];
             cf_jvp_x(xs, uu, Ss, ks);
             if (lane < CF_NU) cf_add_ju_col(xs, uu, lane, ks);
@@ -427,12 +444,12 @@ struct CfWarpT
                 Ss[i] = ((lane - CF_NU == i) ? 1.0 : 0.0) + ah * ks[i];
             }
         }
-        // row 17: b_k
-        if (lane < CF_NX) MS[lane * CF_MROWS + 17] = NOMS[4 * 14 + lane];
+        // row nv (17): b_k
+        if (lane < CF_NX) MS[lane * CF_MROWS + CF_NV] = NOMS[4 * CF_XP + lane];
         cf_syncwarp();
         if (PH != CF_PH_PREPARATION && k == 0) eliminate_x0(MS, xg, x0g);   // (the feedback phase does it otherwise)
         // gradient: scaling * W * (y - yref), [u;x] order (ocp_nlp_cost_ls.c:883-912)
-        const double uk = (lane < CF_NU) ? NOMS[5 * 14 + lane] : 0.0;
+        const double uk = (lane < CF_NU) ? NOMS[5 * CF_XP + lane] : 0.0;
         if (lane < CF_NV) {
             double g;
             if (lane < CF_NU) g = (wgt(k, CF_NX + lane) * (uk - yr_pre)) * h;
@@ -450,13 +467,13 @@ struct CfWarpT
     CF_MEM void eliminate_x0(double *MS, const double *xg, const double *x0g)
     {
         const bool xl = lane >= CF_NU && lane < CF_NV;
-        double *Mrow = MS + (lane < CF_NV ? lane : 17);
+        double *Mrow = MS + (lane < CF_NV ? lane : CF_NV);
         const double xbar = xl ? (x0g[lane - CF_NU] - xg[lane - CF_NU]) : 0.0;
         CF_NOUNROLL
         for (int i = 0; i < CF_NX; i++) {
             if (A0S && xl) A0S[i * CF_NX + lane - CF_NU] = Mrow[i * CF_MROWS];   // kept for the x0 multipliers
             const double tot = cf_warp_sum(xl ? Mrow[i * CF_MROWS] * xbar : 0.0);
-            if (lane == 17) MS[i * CF_MROWS + 17] = tot + MS[i * CF_MROWS + 17];
+            if (lane == CF_NV) MS[i * CF_MROWS + CF_NV] = tot + MS[i * CF_MROWS + CF_NV];
             else if (xl) Mrow[i * CF_MROWS] = 0.0;
         }
         cf_syncwarp();
@@ -469,19 +486,19 @@ struct CfWarpT
         double v0 = 0.0;
         if (lane < CF_NU) {
             double lb = (k == 0) ? P->lbu0[lane] : P->lbu[lane], ub = (k == 0) ? P->ubu0[lane] : P->ubu[lane];
-            if (BST) { lb = BST[k * 8 + lane]; ub = BST[k * 8 + 4 + lane]; }
+            if (BST) { lb = BST[k * 2 * CF_NU + lane]; ub = BST[k * 2 * CF_NU + CF_NU + lane]; }
             const double dl = lb - uk;
             const double du = uk - ub;
             rec(k)[R_D + lane] = dl;
-            rec(k)[R_D + 4 + lane] = du;
+            rec(k)[R_D + CF_NU + lane] = du;
             // OCP_QP_INIT_VAR scheme 1 (x_ocp_qp_ipm.c:1491-1530,1636-1769): slacks at ux = 0, pushed 0.1 inside
             double tl = -dl, tu = -du;
             if (tl < CF_THR0) {
                 if (tu < CF_THR0) { v0 = 0.5 * (dl - du); tl = CF_THR0; tu = CF_THR0; }
                 else { tl = CF_THR0; v0 = dl + CF_THR0; }
             } else if (tu < CF_THR0) { tu = CF_THR0; v0 = -du - CF_THR0; }
-            rec(k)[R_T + lane] = tl; rec(k)[R_T + 4 + lane] = tu;
-            rec(k)[R_LAM + lane] = CF_MU0 / tl; rec(k)[R_LAM + 4 + lane] = CF_MU0 / tu;
+            rec(k)[R_T + lane] = tl; rec(k)[R_T + CF_NU + lane] = tu;
+            rec(k)[R_LAM + lane] = CF_MU0 / tl; rec(k)[R_LAM + CF_NU + lane] = CF_MU0 / tu;
         }
         init_stage_vectors(k, v0);
     }
@@ -508,6 +525,7 @@ struct CfWarpT
         if (lane == 0) cf_bulk_s2g_wait_all();  // every M_k has landed in global memory
     }
 
+#if CF_CRAZYFLIE   // ---- everything below, up to the end of the class, is the tuned program for nx = 13, nu = 4
     // Feedback phase of a split real-time iteration (ocp_nlp_sqp_rti.c:545-683): the linearisation comes from the
     // instance's prepared record; what depends on data that may have changed since the preparation -- the measured
     // state (stage-0 elimination), the bound vectors (ocp_nlp_approximate_qp_vectors_sqp, ocp_nlp_common.c:2258-2292) --
@@ -1223,6 +1241,7 @@ struct CfWarpT
         return (lin[0] < CF_RES_G_MAX || lin[0] < 1e-3 * nrm[0]) && (lin[1] < CF_RES_B_MAX || lin[1] < 1e-3 * nrm[1]) &&
                (lin[2] < CF_RES_D_MAX || lin[2] < 1e-3 * nrm[2]) && (lin[3] < CF_RES_M_MAX || lin[3] < 1e-3 * nrm[3]);
     }
+#endif  // CF_CRAZYFLIE
 };
 
 // OCP_QP_IPM_SOLVE, delta formulation (x_ocp_qp_ipm.c:2409-2759), written as a small state
@@ -1336,7 +1355,7 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
         const int lane = cf_lane();
         const double *src = reinterpret_cast<const double *>(Pg);
         double *dst = sm + CF_SM_PAR;
-        dst[lane] = src[lane];
+        if (lane < CF_PAR_DOUBLES) dst[lane] = src[lane];
         if (lane + 32 < CF_PAR_DOUBLES) dst[lane + 32] = src[lane + 32];
         cf_syncwarp();
         if (bv.W_b && lane < CF_NY) P->Wdiag[lane] = bv.W_b[(long) inst * CF_NY + lane];
@@ -1362,7 +1381,7 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     const double *yrefg = bv.yref + (long) inst * N * CF_NY;
     const double *yref_eg = bv.yref_e + (long) inst * CF_NX;
     unsigned long long *prof = bv.prof;
-    if (PH != CF_PH_FEEDBACK) {
+    if constexpr (PH != CF_PH_FEEDBACK) {
         CF_PROF_BEGIN();
         w.nominal_pass(xg, ug);
         CF_NOUNROLL
@@ -1374,10 +1393,10 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
         w.load_prepared(xg, ug, x0g);
         cf_syncwarp();
     }
-    if (PH == CF_PH_PREPARATION) {   // the solution, status and statistics of the instance are left as they are
+    if constexpr (PH == CF_PH_PREPARATION) {   // the solution, status and statistics of the instance are left as they are
         par = w.par;
         return;
-    }
+    } else {
     int iters = 0;
     const int qp_status = cf_ipm_solve(w, iters, prof);
     CF_PROF_BEGIN();
@@ -1442,4 +1461,5 @@ CF_DEV void cf_rti_instance(const CfParams *Pg, const CfBatchView &bv, int inst,
     par = w.par;
     cf_syncwarp();
     CF_PROF_END(CF_PROF_UPDATE);
+    }   // PH != CF_PH_PREPARATION
 }

@@ -205,18 +205,23 @@ class Port:
         return st, info
 
 
-def ref_available():
-    return os.path.exists(os.path.join(HERE, "_ref", "libcfref.so"))
+def ref_available(model="crazyflie"):
+    return os.path.exists(os.path.join(HERE, "_ref", "libcfref.so" if model == "crazyflie" else f"libcfref_{model}.so"))
 
 
 class Ref:
-    """The reference's own implementation (needs oracle/_ref/libcfref.so)."""
+    """The reference's own implementation (needs oracle/_ref/libcfref.so; model="pendulum": the same harness built for
+    the second model, oracle/_ref/libcfref_pendulum.so -- sizes in .nx / .nu, only solver() / RefSolver.rti are meant
+    for it)."""
 
-    def __init__(self):
-        path = os.path.join(HERE, "_ref", "libcfref.so")
+    def __init__(self, model="crazyflie"):
+        path = os.path.join(HERE, "_ref", "libcfref.so" if model == "crazyflie" else f"libcfref_{model}.so")
         if not os.path.exists(path):
-            raise FileNotFoundError("oracle/_ref/libcfref.so missing: run `make -C oracle ref` where /root/reference exists")
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
         L = self.lib = ctypes.CDLL(path)
+        nx, nu = ctypes.c_int(), ctypes.c_int()
+        L.cfref_dims(ctypes.byref(nx), ctypes.byref(nu))
+        self.nx, self.nu = nx.value, nu.value
         L.cfref_create.restype = ctypes.c_void_p
         L.cfref_create.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int]
         L.cfref_destroy.argtypes = [ctypes.c_void_p]

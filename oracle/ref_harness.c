@@ -29,11 +29,58 @@
 #include "blasfeo/include/blasfeo_d_aux.h"
 #include "hpipm_d_ocp_qp_ipm.h"
 
+/* Second model ("other nx, nu compile without touching kernels"): -DCFREF_MODEL_PENDULUM builds the same
+ * harness for the pendulum on a cart (nx = 4, nu = 1) with the CasADi-generated external functions the reference ships
+ * in acados/examples/c/pendulum_model/ (compiled from there by oracle/Makefile) and the OCP data of
+ * acados/examples/acados_python/tests/test_ocp_setting.py:150-205 (N, Tf, Q, R, Fmax, x0 are the caller's / those values). */
+#if defined(CFREF_MODEL_PENDULUM)
+#define NX 4
+#define NU 1
+#define NY 5
+int pendulum_ode_expl_vde_forw(const double **arg, double **res, int *iw, double *w, void *mem);
+int pendulum_ode_expl_ode_fun(const double **arg, double **res, int *iw, double *w, void *mem);
+/* The checked-in C functions order the state as [x1, v1, theta, dtheta] (export_pendulum_ode_model.m:62), the Python model
+ * the spec is generated from as [x1, theta, v1, dtheta] (pendulum_model.py:50-55): same dynamics, states 1 and 2 swapped.
+ * The wrappers present the Python order (the swap is its own inverse; matrices are column-major). */
+static const int PP[4] = {0, 2, 1, 3};
+static void cf_ref_vde_forw(const double *x, const double *Sx, const double *Su, const double *u, double *f, double *dSx, double *dSu)
+{
+    double xc[4], Sxc[16], Suc[4], fc[4], dSxc[16], dSuc[4];
+    for (int i = 0; i < 4; i++) {
+        xc[PP[i]] = x[i];
+        Suc[PP[i]] = Su[i];
+        for (int j = 0; j < 4; j++) Sxc[PP[i] + 4 * PP[j]] = Sx[i + 4 * j];
+    }
+    const double *arg[4] = {xc, Sxc, Suc, u};
+    double *res[3] = {fc, dSxc, dSuc};
+    int iw[64];
+    double w[512];
+    pendulum_ode_expl_vde_forw(arg, res, iw, w, 0);
+    for (int i = 0; i < 4; i++) {
+        f[i] = fc[PP[i]];
+        dSu[i] = dSuc[PP[i]];
+        for (int j = 0; j < 4; j++) dSx[i + 4 * j] = dSxc[PP[i] + 4 * PP[j]];
+    }
+}
+static void cf_ref_ode(const double *x, const double *u, double *f)
+{
+    double xc[4], fc[4];
+    for (int i = 0; i < 4; i++) xc[PP[i]] = x[i];
+    const double *arg[2] = {xc, u};
+    double *res[1] = {fc};
+    int iw[64];
+    double w[512];
+    pendulum_ode_expl_ode_fun(arg, res, iw, w, 0);
+    for (int i = 0; i < 4; i++) f[i] = fc[PP[i]];
+}
+#else
 #include "cf_model_ref.h"
 
 #define NX 13
 #define NU 4
 #define NY 17
+#endif
+#define NV (NX + NU)
 
 typedef struct
 {
@@ -138,14 +185,22 @@ void *cfref_create_dt(int N, const double *dt, int cond_N)
         ocp_nlp_dynamics_model_set(config, dims, in, i, "expl_ode_fun", &h->ode);
     }
 
+#if defined(CFREF_MODEL_PENDULUM)
+    /* test_ocp_setting.py:160-163,199-205: Q = 2 diag(1e3, 1e3, 1e-2, 1e-2), R = 2 diag(1e-2), W_e = Q, yref = 0 */
+    double Qd[NX] = {2e3, 2e3, 2e-2, 2e-2};
+    const double Rd = 2e-2, WNscale = 1.0;
+    double yref[NY] = {0, 0, 0, 0, 0};
+#else
     /* generate_c_code.py:50-129 */
     const double g0 = 9.8066, mq = 33e-3, Ct = 3.25e-4;
     double hov = sqrt((mq * g0) / (4 * Ct));
     double Qd[NX] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
-    double W[NY * NY] = {0}, WN[NX * NX] = {0}, Vx[NY * NX] = {0}, Vu[NY * NU] = {0}, VxN[NX * NX] = {0};
-    for (int i = 0; i < NX; i++) { W[i + NY * i] = Qd[i]; WN[i + NX * i] = 50 * Qd[i]; Vx[i + NY * i] = 1; VxN[i + NX * i] = 1; }
-    for (int i = 0; i < NU; i++) { W[(NX + i) + NY * (NX + i)] = 0.06; Vu[(NX + i) + NY * i] = 1; }
+    const double Rd = 0.06, WNscale = 50.0;
     double yref[NY] = {0, 0, 0.5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, hov, hov, hov, hov};
+#endif
+    double W[NY * NY] = {0}, WN[NX * NX] = {0}, Vx[NY * NX] = {0}, Vu[NY * NU] = {0}, VxN[NX * NX] = {0};
+    for (int i = 0; i < NX; i++) { W[i + NY * i] = Qd[i]; WN[i + NX * i] = WNscale * Qd[i]; Vx[i + NY * i] = 1; VxN[i + NX * i] = 1; }
+    for (int i = 0; i < NU; i++) { W[(NX + i) + NY * (NX + i)] = Rd; Vu[(NX + i) + NY * i] = 1; }
     for (int i = 0; i < N; i++) {
         ocp_nlp_cost_model_set(config, dims, in, i, "W", W);
         ocp_nlp_cost_model_set(config, dims, in, i, "Vx", Vx);
@@ -156,14 +211,23 @@ void *cfref_create_dt(int N, const double *dt, int cond_N)
     ocp_nlp_cost_model_set(config, dims, in, N, "Vx", VxN);
     ocp_nlp_cost_model_set(config, dims, in, N, "yref", yref);
 
-    int idxbx0[NX], idxbu[NU] = {0, 1, 2, 3};
+    int idxbx0[NX], idxbu[NU];
     for (int i = 0; i < NX; i++) idxbx0[i] = i;
+    for (int i = 0; i < NU; i++) idxbu[i] = i;
+#if defined(CFREF_MODEL_PENDULUM)
+    double x0[NX] = {0, 3.14159265358979323846, 0, 0};
+#else
     double x0[NX] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     ocp_nlp_constraints_model_set(config, dims, in, 0, "idxbx", idxbx0);
     ocp_nlp_constraints_model_set(config, dims, in, 0, "lbx", x0);
     ocp_nlp_constraints_model_set(config, dims, in, 0, "ubx", x0);
     ocp_nlp_constraints_model_set(config, dims, in, 0, "idxbxe", idxbx0);
+#if defined(CFREF_MODEL_PENDULUM)
+    double lbu[NU] = {-80}, ubu[NU] = {80};
+#else
     double lbu[NU] = {0, 0, 0, 0}, ubu[NU] = {22, 22, 22, 22};
+#endif
     for (int i = 0; i < N; i++) {
         ocp_nlp_constraints_model_set(config, dims, in, i, "idxbu", idxbu);
         ocp_nlp_constraints_model_set(config, dims, in, i, "lbu", lbu);
@@ -192,7 +256,7 @@ void *cfref_create_dt(int N, const double *dt, int cond_N)
     ocp_nlp_solver_opts_set(config, opts, "qp_ric_alg", &one);
 
     ocp_nlp_out *out = h->out = ocp_nlp_out_create(config, dims);
-    double u_init[NU] = {0, 0, 0, 0};
+    double u_init[NU] = {0};
     for (int i = 0; i <= N; i++) {
         ocp_nlp_out_set(config, dims, out, i, "x", x0);
         if (i < N) ocp_nlp_out_set(config, dims, out, i, "u", u_init);
@@ -324,20 +388,20 @@ void cfref_get_qp(void *h_, double *BAbt, double *b, double *rqz, double *d_lb, 
     ocp_nlp_get(h->config, h->solver, "nlp_mem", &m);
     struct d_ocp_qp *qp = m->qp_in;
     struct d_ocp_qp_sol *sol = m->qp_out;
-    double tmp[17 * 13];
+    double tmp[NV * NX];
     int od = 0;
     for (int k = 0; k <= N; k++) {
-        int nv = k < N ? 17 : 13;
+        int nv = k < N ? NV : NX;
         if (k < N && BAbt) {
-            blasfeo_unpack_dmat(17, 13, qp->BAbt + k, 0, 0, tmp, 17); /* col-major */
-            for (int r = 0; r < 17; r++)
-                for (int cc = 0; cc < 13; cc++) BAbt[(k * 17 + r) * 13 + cc] = tmp[r + 17 * cc];
+            blasfeo_unpack_dmat(NV, NX, qp->BAbt + k, 0, 0, tmp, NV); /* col-major */
+            for (int r = 0; r < NV; r++)
+                for (int cc = 0; cc < NX; cc++) BAbt[(k * NV + r) * NX + cc] = tmp[r + NV * cc];
         }
-        if (k < N && b) blasfeo_unpack_dvec(13, qp->b + k, 0, b + 13 * k, 1);
-        if (rqz) blasfeo_unpack_dvec(nv, qp->rqz + k, 0, rqz + 17 * k, 1);
-        if (dux) blasfeo_unpack_dvec(nv, sol->ux + k, 0, dux + 17 * k, 1);
-        if (k < N && dpi) blasfeo_unpack_dvec(13, sol->pi + k, 0, dpi + 13 * k, 1);
-        int nb = k == 0 ? 17 : (k < N ? 4 : 0);
+        if (k < N && b) blasfeo_unpack_dvec(NX, qp->b + k, 0, b + NX * k, 1);
+        if (rqz) blasfeo_unpack_dvec(nv, qp->rqz + k, 0, rqz + NV * k, 1);
+        if (dux) blasfeo_unpack_dvec(nv, sol->ux + k, 0, dux + NV * k, 1);
+        if (k < N && dpi) blasfeo_unpack_dvec(NX, sol->pi + k, 0, dpi + NX * k, 1);
+        int nb = k == 0 ? NV : (k < N ? NU : 0);
         if (d_lb) blasfeo_unpack_dvec(nb, qp->d + k, 0, d_lb + od, 1);
         if (d_ub) blasfeo_unpack_dvec(nb, qp->d + k, nb, d_ub + od, 1);
         od += nb;
@@ -386,8 +450,8 @@ static void *slice_run(void *arg)
         double t[5], tt = 0;
         int st = 0, it = 0;
         for (int r = 0; r < s->n_rti; r++) {
-            st = cfref_rti(h, s->x0 + 13 * (size_t) i, s->yref + (size_t) N * 17 * i, s->yref_e + 13 * (size_t) i,
-                           s->x + (size_t) (N + 1) * 13 * i, s->u + (size_t) N * 4 * i, &it, NULL, t);
+            st = cfref_rti(h, s->x0 + NX * (size_t) i, s->yref + (size_t) N * NY * i, s->yref_e + NX * (size_t) i,
+                           s->x + (size_t) (N + 1) * NX * i, s->u + (size_t) N * NU * i, &it, NULL, t);
             tt += t[0];
         }
         if (s->status) s->status[i] = st;
@@ -546,3 +610,6 @@ void cfref_export(void *h_, void **plan, void **config, void **dims, void **in, 
     cfref *h = h_;
     *plan = h->plan; *config = h->config; *dims = h->dims; *in = h->in; *out = h->out; *opts = h->opts; *solver = h->solver;
 }
+
+/* sizes this build of the harness was compiled for */
+void cfref_dims(int *nx, int *nu) { *nx = NX; *nu = NU; }

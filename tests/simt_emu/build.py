@@ -11,11 +11,13 @@ LIB = os.path.join(HERE, "libcfemu.so")
 
 
 def build(force=False):
-    deps = [os.path.join(HERE, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("cf_simt.h", "cf_model.h", "cf_rti_warp.h", "cf_pcond_warp.h", "cf_spec_generated.h")]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
-        return LIB
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, os.path.join(HERE, "emu.cpp"),
-                    "-o", LIB, "-lpthread"], check=True)
+    """libcfemu.so (Crazyflie OCP) and libcfemu_pendulum.so (the same sources with the pendulum's generated description)."""
+    for lib, spec in ((LIB, "cf_spec_generated.h"), (os.path.join(HERE, "libcfemu_pendulum.so"), "cf_spec_pendulum.h")):
+        deps = [os.path.join(HERE, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("cf_simt.h", "cf_model.h", "cf_rti_warp.h", "cf_pcond_warp.h", spec)]
+        if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+            continue
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, f'-DCF_SPEC_HEADER="{spec}"',
+                        os.path.join(HERE, "emu.cpp"), "-o", lib, "-lpthread"], check=True)
     return LIB
 
 

@@ -211,6 +211,7 @@ struct Job
     double *slot;
     double *sm;
 };
+#if CF_CRAZYFLIE   // the tuned uncondensed program exists for nx = 13, nu = 4 only
 static void job_fn(void *a)
 {
     Job *j = (Job *) a;
@@ -218,6 +219,7 @@ static void job_fn(void *a)
     unsigned par = 0;
     cf_rti_instance(j->P, j->bv, j->inst, j->slot, j->sm, par);
 }
+#endif
 template <int PH, bool VDT>
 static void job_fn_t(void *a)
 {
@@ -227,6 +229,10 @@ static void job_fn_t(void *a)
     cf_rti_instance<PH, VDT>(j->P, j->bv, j->inst, j->slot, j->sm, par);
 }
 
+static const double *g_bnd_stage = nullptr;
+// per-stage input boxes [N][8] for the next cfemu_rti_general calls (NULL: none)
+extern "C" void cfemu_set_stage_bounds(const double *tab) { g_bnd_stage = tab; }
+#if CF_CRAZYFLIE
 extern "C" long cfemu_scratch_doubles(int N) { return cf_scratch_layout(N).total; }
 extern "C" void cfemu_scratch_offsets(int N, long *out)
 {
@@ -301,9 +307,6 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
 // General variants of the warp program: per-interval time steps `dts` (NULL = uniform Ts) and, with split != 0, the
 // real-time iteration as two phases -- preparation with x0, then (scratch slot and shared memory poisoned in between, as
 // another instance would have used them) feedback with x0_fb (NULL = x0).
-static const double *g_bnd_stage = nullptr;
-// per-stage input boxes [N][8] for the next cfemu_rti_general calls (NULL: none)
-extern "C" void cfemu_set_stage_bounds(const double *tab) { g_bnd_stage = tab; }
 extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int split, const double *x0, const double *x0_fb,
                                  const double *yref, const double *yref_e, double *x, double *u, int *status, int *qp_iter,
                                  int *qp_status, int *flags, double *res, int nthreads)
@@ -356,6 +359,8 @@ extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int
 }
 
 
+#endif  // CF_CRAZYFLIE
+
 // Partially condensed feedback (cf_pcond_warp.h): preparation phase of the general warp program, then -- scratch slot
 // and shared memory poisoned in between -- the condensed feedback with block size BS = ceil(N / N2).
 struct PcJob
@@ -383,24 +388,30 @@ extern "C" int cfemu_rti_pcond(int B, int N, double Ts, int N2, const double *pa
                                const double *yref_e, double *x, double *u, int *status, int *qp_iter, int *qp_status, int *flags,
                                double *res, int nthreads, const double *const *per_inst)
 {
-    if (N2 < 1 || N2 > N || (N2 == N && !g_wdense)) return -1;   // block size 1 only serves the full weight matrices
+    // block size 1 serves the full weight matrices and, for models other than the Crazyflie, the whole feedback phase
+    if (N2 < 1 || N2 > N || (N2 == N && !g_wdense && CF_CRAZYFLIE)) return -1;
     const CfPcBlocks blk = cf_pc_blocks(N, N2);
     const int BS = blk.n_big ? blk.bs0 + 1 : blk.bs0;
-    if (BS < 1 || BS > 3) return -2;
+    if (BS < 1 || BS > (CF_CRAZYFLIE ? 3 : 1)) return -2;
     CfParams P;
-    static const double Q[13] = {120, 100, 100, 1e-3, 1e-3, 1e-3, 1e-3, 0.7, 1.0, 4.0, 1e-5, 1e-5, 10.0};
-    for (int i = 0; i < 13; i++) { P.Wdiag[i] = Q[i]; P.WNdiag[i] = 50 * Q[i]; }
-    for (int i = 0; i < 4; i++) { P.Wdiag[13 + i] = 0.06; P.lbu[i] = 0; P.ubu[i] = 22; }
+    for (int i = 0; i < CF_NY; i++) P.Wdiag[i] = CfSpec::W[i];     // the generated OCP description (any model)
+    for (int i = 0; i < CF_NX; i++) P.WNdiag[i] = CfSpec::W_e[i];
+    for (int i = 0; i < CF_NU; i++) { P.lbu[i] = CfSpec::lbu[i]; P.ubu[i] = CfSpec::ubu[i]; }
     if (params) {
-        memcpy(P.Wdiag, params, 17 * 8); memcpy(P.WNdiag, params + 17, 13 * 8);
-        memcpy(P.lbu, params + 30, 4 * 8); memcpy(P.ubu, params + 34, 4 * 8);
+        memcpy(P.Wdiag, params, CF_NY * 8); memcpy(P.WNdiag, params + CF_NY, CF_NX * 8);
+        memcpy(P.lbu, params + CF_NY + CF_NX, CF_NU * 8); memcpy(P.ubu, params + CF_NY + CF_NX + CF_NU, CF_NU * 8);
     }
     memcpy(P.lbu0, P.lbu, sizeof P.lbu); memcpy(P.ubu0, P.ubu, sizeof P.ubu);
     P.Ts = Ts; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = 0; P.pad_ = 0;
     const long stride0 = cf_scratch_layout(N).total, pstride = cf_prep_stride(N);
+#if CF_CRAZYFLIE
     const long stride1 = BS == 3 ? cf_pc_scratch_doubles<3>(N2) : (BS == 2 ? cf_pc_scratch_doubles<2>(N2) : cf_pc_scratch_doubles<1>(N2));
-    const long stride = stride0 > stride1 ? stride0 : stride1;
     const int smd = BS == 3 ? (int) CfPcWarpT<3>::SM_DOUBLES : (BS == 2 ? (int) CfPcWarpT<2>::SM_DOUBLES : (int) CfPcWarpT<1>::SM_DOUBLES);
+#else
+    const long stride1 = cf_pc_scratch_doubles<1>(N2);
+    const int smd = (int) CfPcWarpT<1>::SM_DOUBLES;
+#endif
+    const long stride = stride0 > stride1 ? stride0 : stride1;
     const int smn = smd > CF_SM_DOUBLES ? smd : CF_SM_DOUBLES;
     std::vector<double> dtv(N, Ts);
     std::vector<double> prep((size_t) B * pstride + 2, std::nan(""));
@@ -437,9 +448,15 @@ extern "C" int cfemu_rti_pcond(int B, int N, double Ts, int N2, const double *pa
                 cfemu::run_warp(job_fn_t<CF_PH_PREPARATION, true>, &j);
                 poison();
                 PcJob pj{&P, bv, blk, i, slot_a, sm_a};
+                #if CF_CRAZYFLIE
                 cfemu::run_warp(BS == 3 ? pc_job_fn<3> : (BS == 2 ? pc_job_fn<2> : pc_job_fn<1>), &pj);
+#else
+                cfemu::run_warp(pc_job_fn<1>, &pj);
+#endif
             }
         });
     for (auto &t : th) t.join();
     return 0;
 }
+
+extern "C" void cfemu_dims(int *nx, int *nu) { *nx = CF_NX; *nu = CF_NU; }

@@ -1,0 +1,83 @@
+"""SURVEY 8f-4, "other nx, nu compile without touching kernels": the pendulum on a cart (nx = 4, nu = 1) through the same
+generator (tools/gen_spec.py --model pendulum -> csrc/cf_spec_pendulum.h) and the SAME kernel sources (preparation
+program of cf_rti_warp.h + the dense-stage feedback program of cf_pcond_warp.h with block size 1), selected with
+-DCF_SPEC_HEADER.  Parity: golden vectors minted by the reference's own acados/HPIPM build with the CasADi-generated
+pendulum functions the reference ships (tests/golden/make_golden_pendulum.py), and that library live where it exists."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+_dp, _ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+TS = 1.0 / 20
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "pendulum_golden.npz"))
+
+
+def take(gold, tag):
+    return {k: np.ascontiguousarray(gold[f"{tag}_{k}"]) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run([sys.executable, os.path.join(HERE, "simt_emu", "build.py")], check=True)
+    L = ctypes.CDLL(os.path.join(HERE, "simt_emu", "libcfemu_pendulum.so"))
+    L.cfemu_rti_pcond.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
+                                  _ip, _ip, _ip, _ip, _dp, ctypes.c_int, ctypes.c_void_p]
+    nx, nu = ctypes.c_int(), ctypes.c_int()
+    L.cfemu_dims(ctypes.byref(nx), ctypes.byref(nu))
+    assert (nx.value, nu.value) == (4, 1)
+
+    def run(w, N, n_rti=1):
+        B = w["x0"].shape[0]
+        x, u = w["x_init"].copy(), w["u_init"].copy()
+        st, it, qs, fl = [np.zeros(B, np.int32) for _ in range(4)]
+        res = np.zeros((B, 4))
+        P = lambda a: a.ctypes.data_as(_dp)
+        I = lambda a: a.ctypes.data_as(_ip)
+        for _ in range(n_rti):
+            assert L.cfemu_rti_pcond(B, N, TS, N, None, P(w["x0"]), P(w["yref"]), P(w["yref_e"]), P(x), P(u), I(st), I(it), I(qs), I(fl), P(res), 2, None) == 0
+        return dict(x=x, u=u, status=st, qp_iter=it, qp_status=qs, flags=fl)
+    return run
+
+
+def test_generated_header_is_up_to_date():
+    if not os.path.isdir("/root/reference/acados/examples/acados_python/pendulum_on_cart"):
+        pytest.skip("needs the reference tree")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_spec.py"), "--model", "pendulum", "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    src = open(os.path.join(ROOT, "crazyflie_nmpc_b200", "csrc", "cf_spec_pendulum.h")).read()
+    assert "#define CF_SPEC_NX 4" in src and "#define CF_SPEC_NU 1" in src and "#define CF_SPEC_N 20" in src
+
+
+@pytest.mark.parametrize("tag,N,n_rti", [("N20_r1", 20, 1), ("N20_r6", 20, 6), ("N7_r1", 7, 1)])
+def test_emulated_kernels_match_the_reference_golden(emu, gold, tag, N, n_rti):
+    w = take(gold, tag)
+    r = emu(w, N, n_rti)
+    assert (r["status"] == 0).all() and (r["qp_status"] == 0).all() and (r["flags"] == 0).all()
+    assert np.abs(r["qp_iter"] - gold[f"{tag}_qp_iter"][:, -1]).max() <= 1
+    assert rel_err(r["x"], gold[f"{tag}_x"]) < 1e-9 and rel_err(r["u"], gold[f"{tag}_u"]) < 1e-9
+    assert np.abs(gold[f"{tag}_u"]).max() > 79.0      # the input bound |F| <= 80 is active: the interior-point part is exercised
+
+
+def test_reference_library_reproduces_the_golden(gold):
+    from oracle.oracle import Ref, ref_available
+    if not ref_available("pendulum"):
+        pytest.skip("oracle/_ref/libcfref_pendulum.so not built (needs /root/reference)")
+    w = take(gold, "N20_r1")
+    rs = Ref("pendulum").solver(20, TS)
+    for i in range(4):
+        x, u = w["x_init"][i].copy(), w["u_init"][i].copy()
+        rs.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], x, u)
+        assert np.array_equal(x, gold["N20_r1_x"][i]) and np.array_equal(u, gold["N20_r1_u"][i])
+    rs.close()

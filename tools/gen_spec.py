@@ -59,6 +59,8 @@ def stub_modules():
         return SymVec(items)
 
     casadi.SX, casadi.vertcat = SX, vertcat
+    casadi.sin, casadi.cos, casadi.tan, casadi.sqrt, casadi.exp = sp.sin, sp.cos, sp.tan, sp.sqrt, sp.exp
+    casadi.Function = lambda *a, **k: None
     at = types.ModuleType("acados_template")
     at.AcadosModel = Bag
     at.AcadosOcp = Bag
@@ -130,6 +132,28 @@ def load_reference(ref):
                 sys.modules[k] = v
 
 
+def load_description(model_py, ocp_py):
+    """Generic form of load_reference: a model file defining export_*_ode_model functions (untrusted: vetted) and an OCP
+    description that imports it and leaves `ocp` and `model` at module level."""
+    mod_name = os.path.splitext(os.path.basename(model_py))[0]
+    saved = {k: sys.modules.get(k) for k in ("casadi", "acados_template", mod_name)}
+    sys.modules.update(stub_modules())
+    try:
+        em = types.ModuleType(mod_name)
+        exec(vetted_source(model_py), em.__dict__)
+        sys.modules[mod_name] = em
+        g = {"__name__": "ocp_description", "__file__": ocp_py}
+        ALLOWED_IMPORTS.add(mod_name)
+        exec(vetted_source(ocp_py), g)
+        return g["model"], g["ocp"]
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
 from sympy.printing.c import C99CodePrinter
 
 
@@ -169,12 +193,25 @@ def emit_function(name, args_doc, exprs, out_name, accumulate=False):
     return lines
 
 
-def generate(ref):
-    model, ocp = load_reference(ref)
+MODELS = {
+    # name: (model file under the reference tree, OCP description, generated header, source lines of the header comment)
+    "crazyflie": (None, None, "cf_spec_generated.h",
+                  ["//   crazyflie_controller/scripts/crazyflie_full_model/export_ode_model.py  (model)",
+                   "//   crazyflie_controller/scripts/crazyflie_full_model/generate_c_code.py   (horizon, cost, bounds, solver choices)"]),
+    "pendulum": ("acados/examples/acados_python/pendulum_on_cart/common/pendulum_model.py",
+                 os.path.join(ROOT, "tools", "specs", "pendulum_ocp.py"), "cf_spec_pendulum.h",
+                 ["//   acados/examples/acados_python/pendulum_on_cart/common/pendulum_model.py  (model)",
+                  "//   tools/specs/pendulum_ocp.py  (horizon, cost, bounds of acados/examples/acados_python/tests/test_ocp_setting.py:150-205)"]),
+}
+
+
+def generate(ref, which="crazyflie"):
+    model_py, ocp_py, _, src_lines = MODELS[which]
+    model, ocp = load_reference(ref) if which == "crazyflie" else load_description(os.path.join(ref, model_py), ocp_py)
     x, u = list(model.x), list(model.u)
     f = list(model.f_expl_expr)
     nx, nu = len(x), len(u)
-    assert (nx, nu) == (13, 4), "the warp mapping of the kernels is built for nx = 13, nu = 4"
+    assert nx + nu + 1 <= 32, "one row of the stage matrices per lane: nx + nu + 1 <= 32"
     xs = [sp.Symbol(f"x[{i}]", real=True) for i in range(nx)]
     us = [sp.Symbol(f"u[{i}]", real=True) for i in range(nu)]
     ds = [sp.Symbol(f"d[{i}]", real=True) for i in range(nx)]
@@ -202,8 +239,7 @@ def generate(ref):
 
     out = []
     out.append("// GENERATED by tools/gen_spec.py from the reference's OCP description -- do not edit.")
-    out.append("//   crazyflie_controller/scripts/crazyflie_full_model/export_ode_model.py  (model)")
-    out.append("//   crazyflie_controller/scripts/crazyflie_full_model/generate_c_code.py   (horizon, cost, bounds, solver choices)")
+    out += src_lines
     out.append(f"// solver choices: {', '.join(f'{k} = {v}' for k, v in choices.items())}")
     out.append(f"// structural non-zeros: df/dx {nnz_x}, df/du {nnz_u}")
     out.append("#pragma once")
@@ -254,10 +290,13 @@ def generate(ref):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
-    ap.add_argument("--out", default=os.path.join(ROOT, "crazyflie_nmpc_b200", "csrc", "cf_spec_generated.h"))
+    ap.add_argument("--model", default="crazyflie", choices=sorted(MODELS))
+    ap.add_argument("--out", default=None)
     ap.add_argument("--check", action="store_true")
     a = ap.parse_args()
-    text = generate(a.ref)
+    if a.out is None:
+        a.out = os.path.join(ROOT, "crazyflie_nmpc_b200", "csrc", MODELS[a.model][2])
+    text = generate(a.ref, a.model)
     if a.check:
         cur = open(a.out).read() if os.path.exists(a.out) else ""
         if cur != text:
