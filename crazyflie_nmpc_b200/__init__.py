@@ -494,3 +494,107 @@ class MultiBatchSolver:
         v = ctypes.c_double()
         self._check(lib().cfnmpc_multi_last_solve_ms(self._h, ctypes.byref(v)))
         return v.value
+
+
+class ModelSolver:
+    """Batch solver of a generic-model library, crazyflie_nmpc_b200/libcfnmpc_<model>.so: the same kernel sources compiled
+    for another generated OCP description (tools/gen_spec.py --model <model>).  Core subset of the batch
+    C-ABI (include/cfnmpc.h): set / solve / prepare / feedback / get.  Sizes come from the library (cfnmpc_model_dims)."""
+
+    def __init__(self, model, batch, N=None, Ts=None, device=0):
+        path = os.path.join(_PKG, f"libcfnmpc_{model}.so")
+        if not os.path.exists(path):
+            raise CfnmpcError(f"{path} is missing: build it with `python -m crazyflie_nmpc_b200.build`. There is no CPU implementation.")
+        L = self._L = ctypes.CDLL(path)
+        L.cfnmpc_last_error.restype = ctypes.c_char_p
+        nx, nu, n0, tf = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        L.cfnmpc_model_dims(ctypes.byref(nx), ctypes.byref(nu), ctypes.byref(n0), ctypes.byref(tf))
+        self.nx, self.nu, self.ny = nx.value, nu.value, nx.value + nu.value
+        self.B, self.N = int(batch), int(N if N is not None else n0.value)
+        self.Ts = float(Ts if Ts is not None else tf.value / n0.value)
+        L.cfnmpc_batch_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.cfnmpc_batch_set.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int]
+        L.cfnmpc_batch_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.cfnmpc_batch_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        L.cfnmpc_batch_info.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_longlong)]
+        L.cfnmpc_batch_last_solve_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        for f in ("cfnmpc_batch_solve",):
+            getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_int]
+        for f in ("cfnmpc_batch_prepare", "cfnmpc_batch_feedback", "cfnmpc_batch_sync", "cfnmpc_batch_destroy"):
+            getattr(L, f).argtypes = [ctypes.c_void_p]
+        self._h = ctypes.c_void_p()
+        self._check(L.cfnmpc_batch_create(self.B, self.N, self.Ts, int(device), ctypes.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CfnmpcError(f"cfnmpc error {rc}: {self._L.cfnmpc_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.cfnmpc_batch_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _shape(self, field):
+        B, N, nx, nu, ny = self.B, self.N, self.nx, self.nu, self.ny
+        return {"x0": (B, nx), "yref": (B, N, ny), "yref_e": (B, nx), "x": (B, N + 1, nx), "u": (B, N, nu), "W": (ny,), "W_e": (nx,),
+                "lbu": (nu,), "ubu": (nu,), "lbu0": (nu,), "ubu0": (nu,), "time_steps": (N,), "bounds_stage": (N, 2 * nu),
+                "W_stage": (N + 1, ny)}.get(field)
+
+    def set(self, field, a):
+        shape = self._shape(field)
+        if shape is None:
+            raise CfnmpcError(f"unknown field '{field}'")
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.size != int(np.prod(shape)):
+            raise CfnmpcError(f"'{field}' needs {int(np.prod(shape))} values, got {a.size}")
+        self._check(self._L.cfnmpc_batch_set(self._h, field.encode(), ctypes.c_void_p(a.ctypes.data), 0))
+        self._check(self._L.cfnmpc_batch_sync(self._h))
+        return self
+
+    def set_problem(self, w):
+        for k, f in (("x0", "x0"), ("yref", "yref"), ("yref_e", "yref_e"), ("x_init", "x"), ("u_init", "u")):
+            self.set(f, w[k])
+        return self
+
+    def set_option(self, option, value):
+        self._check(self._L.cfnmpc_batch_set_option(self._h, option.encode(), int(value)))
+        return self
+
+    def solve(self, n_rti=1):
+        self._check(self._L.cfnmpc_batch_solve(self._h, int(n_rti)))
+        return self
+
+    def prepare(self):
+        self._check(self._L.cfnmpc_batch_prepare(self._h))
+        return self
+
+    def feedback(self):
+        self._check(self._L.cfnmpc_batch_feedback(self._h))
+        return self
+
+    def get(self, field, stage=0):
+        B, N = self.B, self.N
+        shapes = {"x": ((B, self.nx), np.float64), "u": ((B, self.nu), np.float64), "x_all": ((B, N + 1, self.nx), np.float64),
+                  "u_all": ((B, N, self.nu), np.float64), "status": ((B,), np.int32), "qp_iter": ((B,), np.int32),
+                  "qp_status": ((B,), np.int32), "flags": ((B,), np.int32), "res": ((B, 4), np.float64)}
+        if field not in shapes:
+            raise CfnmpcError(f"unknown field '{field}'")
+        out = np.empty(*shapes[field])
+        self._check(self._L.cfnmpc_batch_get(self._h, field.encode(), int(stage), ctypes.c_void_p(out.ctypes.data), 0))
+        return out
+
+    def last_solve_ms(self):
+        v = ctypes.c_double()
+        self._check(self._L.cfnmpc_batch_last_solve_ms(self._h, ctypes.byref(v)))
+        return v.value
+
+    def info(self, what):
+        v = ctypes.c_longlong()
+        self._check(self._L.cfnmpc_batch_info(self._h, what.encode(), ctypes.byref(v)))
+        return v.value
