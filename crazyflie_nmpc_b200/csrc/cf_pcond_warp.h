@@ -913,6 +913,7 @@ struct CfPcWarpT
 
     CF_MEM bool lin_res_ok_fact() const { return true; }
     CF_MEM bool lin_res_ok_corr() const { return true; }
+    static constexpr bool HAS_REFINE = false;   // iterative refinement belongs to the linear-residual diagnostics of the uncondensed program
 
     // =============================================================== expansion + primal update
     // d_part_cond_qp_expand_sol (x_part_cond.c:658-742 -> EXPAND_SOL, x_cond_aux.c:1820-): block states and inputs are the

@@ -101,6 +101,8 @@ static_assert(R_PI == 18 && R_DPI == 32 && R_RQ == 46 && R_D == 64 && R_BKP == 7
 // always on (no option needed, a handful of instructions per stage):
 #define CF_FLAG_BAD_PIVOT 8      // a non-positive pivot was replaced by 0 in the Riccati factorisation (BLASFEO's rule, silent there)
 #define CF_FLAG_NONFINITE 16     // the step length or the duality measure left the finite range (HPIPM status 3 follows)
+#define CF_FLAG_ITREF 32         // lin_res_check = 2: the corrector step was iteratively refined (x_ocp_qp_ipm.c:2275-2366)
+#define CF_FLAG_ITREF_LEFT 64    // ... and two rounds left a residual above the reference's tolerances (it continues, as HPIPM does)
 
 struct CfParams
 {
@@ -111,7 +113,9 @@ struct CfParams
     double Ts;
     int N;
     int max_ipm_iter;      // CF_ITER_MAX unless a test truncates the loop
-    int lin_res_check;     // != 0: evaluate the linear-system residuals of every solve (sets the CF_FLAG_LIN_RES_* bits)
+    int lin_res_check;     // != 0: evaluate the linear-system residuals of every solve (sets the CF_FLAG_LIN_RES_* bits);
+                           // 2: and refine the corrector step iteratively where the reference would (itref_corr_max = 2);
+                           // 4 (tests): 2 with every corrector solve deliberately 10 % off in du, so that refinement runs
     int pad_;
 };
 #define CF_PAR_DOUBLES (CF_NY + CF_NX + 4 * CF_NU + 3)  // sizeof(CfParams) / 8 (49): the per-warp copy in shared memory
@@ -948,7 +952,19 @@ struct CfWarpT
     // lane & 3 hold identical input/bound quantities), stores and norm contributions are predicated.
     // `need_pi`: the multiplier step dpi is only consumed by the variable update (and by the optional linear-residual
     // check), never by the corrector -- the affine (predictor) solve skips it together with the P_{k+1} it would read.
-    CF_MEM void forward(const bool need_pi_)
+    // MODE 1 / 2 are the two cold variants of iterative refinement (OCP_QP_IPM_DELTA_STEP, x_ocp_qp_ipm.c:2275-2366; only
+    // with lin_res_check = 2).  1: no substitution -- the STORED corrector step (dux, dpi, dlam, dt of the records) is put
+    // through the residual formulas and the residual VECTORS of the linear system are left in the right-hand-side fields
+    // (res_g, res_b, res_d, res_m of every stage; they are dead until the next residual sweep rewrites them), a copy of dux
+    // in the R_BKP | R_PB area.  2: the right-hand side is such a residual: solve for the correction, ADD it to the stored
+    // step, leave the new residual in place, step length from the sums.
+    CF_MEM void forward(const bool need_pi_) { forward_t<0>(need_pi_); }
+    // Compiled into the GENERAL kernel variants only (VDT), which the API selects for lin_res_check >= 2: three copies of
+    // the forward sweep in the benchmarked kernels cost 1.8 % there (profiles/README.md) although they are never executed.
+    static constexpr bool HAS_REFINE = VDT;
+    CF_MEM bool refine_enabled() const { return HAS_REFINE && PG->lin_res_check >= 2; }
+    template <int MODE>
+    CF_MEM void forward_t(const bool need_pi_)
     {
         double *XS = sm + CF_SM_V0, *DS = sm + CF_SM_V1, *PS = sm + CF_SM_V3;
         // running step lengths to the boundary kept as ratios num/den (den < 0): alpha = min(1, min -lam/dlam, -t/dt)
@@ -956,7 +972,7 @@ struct CfWarpT
         double lg = 0, lb = 0, ld = 0, lm = 0;    // linear residual norms
         double dxk = 0.0;        // lanes 4..16: dx_k ; stage 0 has none
         double dpi_prev = 0.0;   // lanes 4..16: dpi_{k-1}
-        const bool chk = PG->lin_res_check != 0;   // the reference's linear-system residual checks (diagnostic flags only)
+        const bool chk = MODE ? true : PG->lin_res_check != 0;   // the reference's linear-system residual checks
         const bool need_pi = need_pi_ || chk;
         const int VO = R_LAM, VN = (need_pi ? CF_SB : B_PX) - R_LAM;   // staged part of the stage block: [R_LAM, end | B_PX)
         pass_begin();
@@ -1037,8 +1053,18 @@ struct CfWarpT
                 du = (l4 == j) ? duj : du;
                 v = (l4 < j) ? vn : v;
             }
-            const double duxk = ul ? du : dxk;  // lane r: dux_k[r]
-            if (vl && need_pi) rk[R_DUX + lane] = duxk;   // the affine primal step itself is never read again
+            if constexpr (HAS_REFINE && MODE == 0) {
+                if (chk && need_pi_ && PG->lin_res_check == 4) du *= 0.9;   // tests: a deliberately inaccurate corrector
+            }
+            if constexpr (MODE == 1) du = rk[R_DUX + l4];   // the stored step
+            const double duxk = (MODE == 1) ? (vl ? rk[R_DUX + lv] : 0.0) : (ul ? du : dxk);  // lane r: dux_k[r]
+            if constexpr (MODE == 2) {
+                if (vl) { const double tot = rk[R_BKP + lane] + duxk; rk[R_DUX + lane] = tot; rk[R_BKP + lane] = tot; }
+            } else if constexpr (MODE == 1) {
+                if (vl) rk[R_BKP + lane] = duxk;
+            } else {
+                if (vl && need_pi) rk[R_DUX + lane] = duxk;   // the affine primal step itself is never read again
+            }
             // ---- dlam, dt, alpha for the bounds of input l4
             double dlam_l, dlam_u;
             {
@@ -1051,19 +1077,35 @@ struct CfWarpT
                 dlam_l = -til * (rml + (ll * dtl) - (ll * rdl));
                 dlam_u = -tiu * (rmu + (lu * dtu) - (lu * rdu));
                 dtl -= rdl; dtu -= rdu;
-                if (ul) {
-                    rk[R_DLAM + lane] = dlam_l; rk[R_DLAM + 4 + lane] = dlam_u;
-                    rk[R_DT + lane] = dtl; rk[R_DT + 4 + lane] = dtu;
+                if constexpr (MODE == 1) {
+                    dlam_l = rk[R_DLAM + l4]; dlam_u = rk[R_DLAM + 4 + l4];
+                    dtl = rk[R_DT + l4]; dtu = rk[R_DT + 4 + l4];
+                }
+                // the step the length test sees and the records keep: this solve's, or (refinement) the sum so far
+                double al = dlam_l, au = dlam_u, bl = dtl, bu = dtu;
+                if constexpr (MODE == 2) {
+                    al += rk[R_DLAM + l4]; au += rk[R_DLAM + 4 + l4];
+                    bl += rk[R_DT + l4]; bu += rk[R_DT + 4 + l4];
+                }
+                if (MODE != 1 && ul) {
+                    rk[R_DLAM + lane] = al; rk[R_DLAM + 4 + lane] = au;
+                    rk[R_DT + lane] = bl; rk[R_DT + 4 + lane] = bu;
                 }
                 // a*d > v with a = n/dd, dd < 0  <=>  n*d < v*dd ; then the new ratio is v/d (d < 0)
                 bool c;
-                c = dn * dlam_l < ll * dd; dn = c ? ll : dn; dd = c ? dlam_l : dd;
-                c = pn_ * dtl < tl * pd_; pn_ = c ? tl : pn_; pd_ = c ? dtl : pd_;
-                c = dn * dlam_u < lu * dd; dn = c ? lu : dn; dd = c ? dlam_u : dd;
-                c = pn_ * dtu < tu * pd_; pn_ = c ? tu : pn_; pd_ = c ? dtu : pd_;
+                c = dn * al < ll * dd; dn = c ? ll : dn; dd = c ? al : dd;
+                c = pn_ * bl < tl * pd_; pn_ = c ? tl : pn_; pd_ = c ? bl : pd_;
+                c = dn * au < lu * dd; dn = c ? lu : dn; dd = c ? au : dd;
+                c = pn_ * bu < tu * pd_; pn_ = c ? tu : pn_; pd_ = c ? bu : pd_;
                 if (chk) {   // linear residuals of the complementarity / bound rows
-                    cf_amax(ld, rdl + dtl - du); cf_amax(ld, rdu + dtu + du);
-                    cf_amax(lm, rml + ll * dtl + dlam_l * tl); cf_amax(lm, rmu + lu * dtu + dlam_u * tu);
+                    const double qdl = rdl + dtl - du, qdu = rdu + dtu + du;
+                    const double qml = rml + ll * dtl + dlam_l * tl, qmu = rmu + lu * dtu + dlam_u * tu;
+                    cf_amax(ld, qdl); cf_amax(ld, qdu);
+                    cf_amax(lm, qml); cf_amax(lm, qmu);
+                    if (MODE != 0 && ul) {
+                        rk[R_RESD + lane] = qdl; rk[R_RESD + 4 + lane] = qdu;
+                        rk[R_RESM + lane] = qml; rk[R_RESM + 4 + lane] = qmu;
+                    }
                 }
             }
             // stationarity residual, part 1: H dux + rhs_g - dpi_{k-1} + dlam_ub - dlam_lb
@@ -1092,7 +1134,9 @@ struct CfWarpT
                 const double sacc = s0 + s1, rbk = VS[R_RESB + ci];
 #endif
                 dxn = xl ? sacc + rbk : 0.0;
+                if constexpr (MODE == 1) dxn = xl ? rec(k + 1)[R_DUX + lane] : 0.0;
                 if (chk) cf_amax(lb, xl ? (rbk - dxn) + sacc : 0.0);
+                if (MODE != 0 && xl) rk[R_RESB + ci] = (rbk - dxn) + sacc;
                 if (xl) XS[ci] = dxn;
             }
             double dpik = 0.0;
@@ -1109,7 +1153,11 @@ struct CfWarpT
                 }
                 z0 += Li[12] * XS[12];
                 dpik = xl ? z0 + z1 : 0.0;
-                if (xl) { rec(k + 1)[R_DPI + ci] = dpik; PS[ci] = dpik; }   // the record of stage k+1 holds pi_k
+                if constexpr (MODE == 1) dpik = xl ? rec(k + 1)[R_DPI + ci] : 0.0;
+                if (xl) {   // the record of stage k+1 holds pi_k
+                    if (MODE != 1) rec(k + 1)[R_DPI + ci] = (MODE == 2) ? rec(k + 1)[R_DPI + ci] + dpik : dpik;
+                    PS[ci] = dpik;
+                }
             }
             if (chk) {   // warp-uniform
             cf_syncwarp();
@@ -1123,6 +1171,7 @@ struct CfWarpT
                 }
                 s0 += Mk[12 * CF_MROWS + lv] * PS[12];
                 cf_amax(lg, vl ? rgl + (s0 + s1) : 0.0);
+                if (MODE != 0 && vl) rk[R_RESG + lane] = rgl + (s0 + s1);
             }
             dpi_prev = dpik;
             dxk = dxn;
@@ -1130,8 +1179,18 @@ struct CfWarpT
         // terminal stage: no inputs, no bounds, no dynamics
         if (vl) {
             const double duxN = ul ? 0.0 : dxk;
-            if (need_pi) rec(N)[R_DUX + lane] = duxN;
-            if (chk) cf_amax(lg, HN * duxN + rec(N)[R_RESG + lane] - dpi_prev);
+            double *rN = rec(N);
+            const double qg = chk ? HN * duxN + rN[R_RESG + lane] - dpi_prev : 0.0;
+            if constexpr (MODE == 2) {
+                const double tot = rN[R_BKP + lane] + duxN;
+                rN[R_DUX + lane] = tot; rN[R_BKP + lane] = tot;
+            } else if constexpr (MODE == 1) {
+                rN[R_BKP + lane] = duxN;
+            } else {
+                if (need_pi) rN[R_DUX + lane] = duxN;
+            }
+            if (chk) cf_amax(lg, qg);
+            if (MODE != 0) rN[R_RESG + lane] = qg;
         }
         if (chk) { lin[0] = cf_warp_max(lg); lin[1] = cf_warp_max(lb); lin[2] = cf_warp_max(ld); lin[3] = cf_warp_max(lm); }
         else { lin[0] = lin[1] = lin[2] = lin[3] = 0.0; }
@@ -1143,7 +1202,12 @@ struct CfWarpT
 
     // OCP_QP_SOLVE_KKT_STEP, backward vector recursion with cached Pb (x_ocp_qp_kkt.c:1147-1245):
     // leaves l_k = [L^-1 rhs]_u ; p_k in dux_k for the forward sweep.
-    CF_MEM void backward_rhs(int rm_mode, double sigma_mu)
+    // FRESH (iterative refinement only): the right-hand side is new, so P_{k+1} res_b is computed instead of taken from
+    // the cache R_PB of the factorisation (use_Pb = 0, x_ocp_qp_kkt.c:1187-1190); the packed P_{k+1} is read from the
+    // stage block in global memory.
+    CF_MEM void backward_rhs(int rm_mode, double sigma_mu) { backward_rhs_t<false>(rm_mode, sigma_mu); }
+    template <bool FRESH>
+    CF_MEM void backward_rhs_t(int rm_mode, double sigma_mu)
     {
         double *TS = sm + CF_SM_V0;
         const int VO = R_BKP, VN = B_PX - R_BKP;   // staged part of the stage block: [R_BKP, B_PX)
@@ -1167,7 +1231,20 @@ struct CfWarpT
             if (lane < CF_NU) bound_terms(k, VS + R_DLAM, rm_mode, sigma_mu, Gam, gam);
             double rhs = 0.0;
             if (lane < CF_NV) rhs = VS[R_RESG + lane] + gam;
-            if (lane >= CF_NU && lane < CF_NV) TS[lane - CF_NU] = pn + VS[R_PB + lane - CF_NU];
+            if constexpr (FRESH) {
+                double *RB = sm + CF_SM_V1;
+                const bool xq = lane >= CF_NU && lane < CF_NV;
+                const int iq = xq ? lane - CF_NU : 0;
+                if (xq) RB[iq] = VS[R_RESB + iq];
+                cf_syncwarp();
+                const double *Pp = blk(k) + B_PX;
+                double pb = 0.0;
+                CF_NOUNROLL
+                for (int j = 0; j < CF_NX; j++) pb += Pp[iq >= j ? cf_tri(iq) + j : cf_tri(j) + iq] * RB[j];
+                if (xq) TS[iq] = pn + pb;
+            } else {
+                if (lane >= CF_NU && lane < CF_NV) TS[lane - CF_NU] = pn + VS[R_PB + lane - CF_NU];
+            }
             cf_syncwarp();
             if (lane < CF_NV) {
                 double s0 = 0.0, s1 = 0.0;
@@ -1309,7 +1386,23 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters, unsigned long long *prof)
                 const bool recenter = brm == 1 && w.mu_aff > 2.0 * mu_aff0;
                 if (recenter) { brm = 2; st = ST_BWD; }
                 else {
-                    if (!w.lin_res_ok_corr()) w.flags |= CF_FLAG_LIN_RES_CORR;
+                    if (!w.lin_res_ok_corr()) {
+                        w.flags |= CF_FLAG_LIN_RES_CORR;
+                        if constexpr (CfWarp::HAS_REFINE) if (w.refine_enabled()) {
+                            // iterative refinement of the corrector step, at most itref_corr_max = 2 rounds
+                            // (x_ocp_qp_ipm.c:2275-2366): residual of the linear system -> right-hand side -> correction
+                            w.flags |= CF_FLAG_ITREF;
+                            w.template forward_t<1>(true);
+                            bool ok = false;
+                            for (int r = 0; r < 2 && !ok; r++) {
+                                w.template backward_rhs_t<true>(3, 0.0);
+                                w.template forward_t<2>(true);
+                                ok = w.lin_res_ok_corr();
+                            }
+                            if (!ok) w.flags |= CF_FLAG_ITREF_LEFT;
+                            w.compute_mu_aff();   // the complementarity prediction of the refined step
+                        }
+                    }
                     // will the updated iterate pass the exit test?  The linear residuals shrink by (1 - step), the
                     // complementarity products were just evaluated; half the tolerances as margin.
                     const double r = 1.0 - w.step_adjust(w.alpha);

@@ -85,7 +85,8 @@ struct cfnmpc_batch
     double *d_mult = nullptr;         // multiplier output [B][cf_mult_stride(N)] (option "multipliers")
     double *d_wst = nullptr;          // per-stage weights [N+1][17] (allocated on first use); while set, the general kernels run
     bool vdt_grid = false, wst = false, prepared = false;   // non-uniform time grid / per-stage weights: the general kernels
-    bool vdt = false;                                        // = vdt_grid || wst
+    bool itref = false;                                      // lin_res_check >= 2: iterative refinement (general kernels)
+    bool vdt = false;                                        // = vdt_grid || wst || itref
     size_t smem = 0;
     long long launches = 0;
     bool timed = false;
@@ -442,7 +443,7 @@ extern "C" int cfnmpc_batch_set(cfnmpc_batch *h, const char *field, const void *
         CK(cudaMemcpy(h->d_dts, h->h_dts, (size_t) h->N * 8, cudaMemcpyHostToDevice));
         h->P.Ts = dt[0];
         h->vdt_grid = !uniform;
-        h->vdt = h->vdt_grid || h->wst;
+        h->vdt = h->vdt_grid || h->wst || h->itref;
         h->prepared = false;
         return CFNMPC_OK;
     }
@@ -530,7 +531,13 @@ extern "C" int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int 
 {
     if (!h || !option) return fail(CFNMPC_EINVAL, "cfnmpc_batch_set_option: null argument");
     if (!strcmp(option, "qp_cond_N")) return set_cond_N(h, value);
-    if (!strcmp(option, "lin_res_check")) h->P.lin_res_check = value != 0;
+    if (!strcmp(option, "lin_res_check")) {
+        h->P.lin_res_check = value <= 0 ? 0 : (value == 4 ? 4 : (value >= 2 ? 2 : 1));
+        // iterative refinement is compiled into the general kernel variants only (CfWarpT::HAS_REFINE)
+        h->itref = h->P.lin_res_check >= 2;
+        h->vdt = h->vdt_grid || h->wst || h->itref;
+        h->prepared = false;
+    }
     else if (!strcmp(option, "two_kernels")) h->two_kernels = value != 0;
     else if (!strcmp(option, "max_ipm_iter")) h->P.max_ipm_iter = (value > 0 && value < CF_ITER_MAX) ? value : CF_ITER_MAX;
     else if (!strcmp(option, "multipliers")) {
@@ -558,7 +565,7 @@ extern "C" int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field)
     else if (!strcmp(field, "lbu0_batch")) h->bv.lbu0_b = nullptr;
     else if (!strcmp(field, "ubu0_batch")) h->bv.ubu0_b = nullptr;
     else if (!strcmp(field, "bounds_stage")) h->bv.bnd_stage = nullptr;
-    else if (!strcmp(field, "W_stage")) { h->bv.W_stage = nullptr; h->wst = false; h->vdt = h->vdt_grid; h->prepared = false; }
+    else if (!strcmp(field, "W_stage")) { h->bv.W_stage = nullptr; h->wst = false; h->vdt = h->vdt_grid || h->itref; h->prepared = false; }
     else if (!strcmp(field, "W_dense_table")) { h->bv.W_dense = nullptr; h->dense_w = false; h->cond_N = 0; h->prepared = false; }
     else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_clear: '") + field + "' is not a per-instance parameter array");
     return CFNMPC_OK;

@@ -110,8 +110,11 @@ int cfnmpc_batch_clear(cfnmpc_batch *h, const char *field);
 /* Integer options:
  *   "lin_res_check" (default 0)  1: evaluate, after every Riccati solve, the linear-system residuals HPIPM evaluates for
  *                   its safety nets (x_ocp_qp_ipm.c:2029-2059 LQ re-factorisation, :2311-2318 iterative refinement) and
- *                   report in "flags" where the reference would have taken one of them.  Diagnostic only: the nets
- *                   themselves are not implemented (they never fire on this OCP), results do not depend on the option.
+ *                   report in "flags" where the reference would have taken one of them.  1 is diagnostic only (results do
+ *                   not depend on it).  2 also performs the second net, iterative refinement of the corrector step (at most
+ *                   two rounds, itref_corr_max = 2; "flags" bit 5, bit 6 when two rounds were not enough).  The first net has
+ *                   no counterpart: HPIPM's LQ re-factorisation exists for its square-root recursion only and falls through
+ *                   to the plain factorisation for the classical recursion used here (x_ocp_qp_kkt.c:769-774).
  *   "max_ipm_iter"  (default 50 = qp_solver_iter_max of the reference configuration)
  *   "two_kernels"   (default 1) cfnmpc_batch_solve / _solve_from_host / _tick run the step as two launches -- preparation
  *                   of every instance, then feedback of every instance, the linearisations travelling through a
@@ -161,7 +164,9 @@ int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, const double
  *   "status"   int [B]   acados status of the last step (0 ok, 4 QP failure)
  *   "qp_iter"  int [B]   interior-point iterations of the last step
  *   "qp_status" int [B]  HPIPM status 0 ok / 1 max-iter / 2 min-step / 3 NaN
- *   "flags"    int [B]   bit 0/1: the reference's LQ / iterative-refinement safety nets would have fired (needs the option
+ *   "flags"    int [B]   bit 3: a non-positive Riccati pivot was replaced by 0; bit 4: step length or duality measure not
+ *                        finite (both always on); bit 5/6: iterative refinement ran / left a residual (lin_res_check 2);
+ *                        bit 0/1: the reference's LQ / iterative-refinement safety nets would have fired (needs the option
  *                        "lin_res_check"; 0 otherwise); bit 2: cfnmpc_batch_solve_from_host gave up waiting for this
  *                        instance's inputs (5 s) and solved it with whatever was in device memory
  *   "res"      double [B][4]  final QP residual inf-norms (stationarity, dynamics, bounds, complementarity)

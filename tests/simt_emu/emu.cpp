@@ -232,6 +232,9 @@ static void job_fn_t(void *a)
 static const double *g_bnd_stage = nullptr;
 // per-stage input boxes [N][8] for the next cfemu_rti_general calls (NULL: none)
 extern "C" void cfemu_set_stage_bounds(const double *tab) { g_bnd_stage = tab; }
+// lin_res_check of the next cfemu_rti_batch calls: 1 = flags only (default), 2 = with iterative refinement
+static int g_lin_res_check = 1;
+extern "C" void cfemu_set_lin_res_check(int v) { g_lin_res_check = v; }
 #if CF_CRAZYFLIE
 extern "C" long cfemu_scratch_doubles(int N) { return cf_scratch_layout(N).total; }
 extern "C" void cfemu_scratch_offsets(int N, long *out)
@@ -270,7 +273,7 @@ extern "C" int cfemu_rti_batch2(int B, int N, double Ts, const double *params, i
     }
     memcpy(P.lbu0, P.lbu, sizeof P.lbu); memcpy(P.ubu0, P.ubu, sizeof P.ubu);
     P.Ts = Ts; P.N = N; P.max_ipm_iter = max_ipm_iter > 0 ? max_ipm_iter : CF_ITER_MAX;
-    P.lin_res_check = 1; P.pad_ = 0;
+    P.lin_res_check = g_lin_res_check; P.pad_ = 0;
     const long stride = cf_scratch_layout(N).total;
     CfBatchView bv = {};
     bv.mult = g_mult; bv.mult_stride = cf_mult_stride(N);
@@ -317,7 +320,7 @@ extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int
     for (int i = 0; i < 4; i++) { P.Wdiag[13 + i] = 0.06; P.lbu[i] = P.lbu0[i] = 0; P.ubu[i] = P.ubu0[i] = 22; }
     std::vector<double> dtv(N, Ts);
     if (dts) dtv.assign(dts, dts + N);
-    P.Ts = dtv[0]; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = 1; P.pad_ = 0;
+    P.Ts = dtv[0]; P.N = N; P.max_ipm_iter = CF_ITER_MAX; P.lin_res_check = g_lin_res_check; P.pad_ = 0;
     const long stride = cf_scratch_layout(N).total, pstride = cf_prep_stride(N);
     std::vector<double> prep((size_t) B * pstride + 2, std::nan(""));
     CfBatchView bv = {};

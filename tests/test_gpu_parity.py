@@ -732,3 +732,34 @@ def test_fused_fallback_when_the_prepared_store_cannot_be_allocated(monkeypatch)
         assert np.array_equal(s.get("x_all"), x0) and np.array_equal(s.get("u_all"), u0) and np.array_equal(s.get("status"), st0)
         with pytest.raises(cf.CfnmpcError):
             s.prepare()                # the split phases need the store: a clean error, not a crash
+
+
+@pytest.mark.gpu
+def test_iterative_refinement_of_the_corrector_step():
+    """Option lin_res_check = 2: the reference's iterative refinement (itref_corr_max = 2, x_ocp_qp_ipm.c:2275-2366) where the
+    corrector step fails its linear-residual test.  Healthy solves: never fires, bit-identical results.  Test mode 4 (every
+    corrector solve 10 % off in du): refinement runs, restores the residual within two rounds, the solve converges to the
+    same solution.  The ill-conditioned set: same statuses as without it."""
+    N, B = 50, 256
+    w = wl.helix_batch(B, N, seed=14)
+    runs = {}
+    for mode in (0, 2, 4):
+        with cf.BatchSolver(B, N, TS) as s:
+            s.set_option("lin_res_check", mode)
+            s.set_problem(w).solve(1)
+            runs[mode] = dict(x=s.get("x_all"), u=s.get("u_all"), st=s.get("status"), qs=s.get("qp_status"), fl=s.get("flags"))
+    assert np.array_equal(runs[2]["x"], runs[0]["x"]) and np.array_equal(runs[2]["u"], runs[0]["u"]) and (runs[2]["fl"] == 0).all()
+    f4 = runs[4]["fl"]
+    assert ((f4 & 32) != 0).all() and ((f4 & 64) == 0).all() and (runs[4]["st"] == 0).all() and (runs[4]["qs"] == 0).all()
+    assert rel_err(runs[4]["x"], runs[0]["x"]) < 1e-3 and rel_err(runs[4]["u"], runs[0]["u"]) < 1e-3
+    wa = wl.adversarial_batch(128, N, seed=5)
+    adv = {}
+    for mode in (1, 2):
+        with cf.BatchSolver(128, N, TS) as s:
+            s.set_option("lin_res_check", mode)
+            s.set("W_batch", wa["W"]).set("W_e_batch", wa["W_e"]).set("lbu_batch", wa["lbu"]).set("ubu_batch", wa["ubu"])
+            s.set_problem(wa).solve(1)
+            adv[mode] = dict(u=s.get("u_all"), st=s.get("status"), qs=s.get("qp_status"), fl=s.get("flags"))
+    assert np.array_equal(adv[1]["st"], adv[2]["st"]) and np.array_equal(adv[1]["qs"], adv[2]["qs"])
+    conv = adv[1]["qs"] == 0
+    assert rel_err(adv[2]["u"][conv], adv[1]["u"][conv]) < 1e-6

@@ -414,3 +414,36 @@ def test_emulated_multiplier_output_matches_port(gold, port):
             assert np.abs(k_l0 - signed).max() < 1e-9 * (1 + np.abs(signed).max())
     finally:
         port.record_multipliers(0)
+
+
+def test_emulated_iterative_refinement(gold):
+    """lin_res_check = 2: where the corrector step fails the reference's linear-residual test it is refined as HPIPM does
+    (x_ocp_qp_ipm.c:2275-2366: residual of the linear system -> right-hand side -> correction, at most two rounds).  The
+    test mode 4 makes every corrector solve 10 % inaccurate in du: refinement must run (CF_FLAG_ITREF), bring the residual
+    back under the tolerances within two rounds (no CF_FLAG_ITREF_LEFT) and the interior-point method must still converge
+    to the same solution.  On a healthy solve mode 2 never fires and changes nothing."""
+    subprocess.run([sys.executable, os.path.join(HERE, "simt_emu", "build.py")], check=True)
+    L = ctypes.CDLL(os.path.join(HERE, "simt_emu", "libcfemu.so"))
+    L.cfemu_rti_general.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, _dp, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
+                                    _ip, _ip, _ip, _ip, _dp, ctypes.c_int]
+    L.cfemu_set_lin_res_check.argtypes = [ctypes.c_int]
+    w = batch(gold, "helix", 3)
+    B, N = 3, 50
+    P = lambda a: a.ctypes.data_as(_dp)
+    I = lambda a: a.ctypes.data_as(_ip)
+    out = {}
+    try:
+        for mode in (1, 2, 4):
+            L.cfemu_set_lin_res_check(mode)
+            x, u = w["x_init"].copy(), w["u_init"].copy()
+            st, it, qs, fl = [np.zeros(B, np.int32) for _ in range(4)]
+            res = np.zeros((B, 4))
+            # the general kernel variant, fused and as two phases (refinement is compiled into the general variants only)
+            L.cfemu_rti_general(B, N, TS, None, int(mode == 4), P(w["x0"]), None, P(w["yref"]), P(w["yref_e"]), P(x), P(u), I(st), I(it), I(qs), I(fl), P(res), 2)
+            out[mode] = dict(x=x, u=u, st=st, it=it, qs=qs, fl=fl)
+    finally:
+        L.cfemu_set_lin_res_check(1)
+    assert np.array_equal(out[2]["x"], out[1]["x"]) and np.array_equal(out[2]["u"], out[1]["u"]) and (out[2]["fl"] == 0).all()
+    f4 = out[4]["fl"]
+    assert ((f4 & 32) != 0).all() and ((f4 & 64) == 0).all() and (out[4]["st"] == 0).all() and (out[4]["qs"] == 0).all()
+    assert rel_err(out[4]["x"], out[1]["x"]) < 1e-3 and rel_err(out[4]["u"], out[1]["u"]) < 1e-3
