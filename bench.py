@@ -456,7 +456,7 @@ def run_ours(args):
                     value_median=world * B / (float(np.median(step_ms)) * 1e-3) if world == 1 else None,
                     value_with_lin_res_check=(dict(value=world * B / (ms_chk * 1e-3), unit=UNIT, ms_per_step=ms_chk, flagged_instances=flags_chk,
                                                    note="same step with the reference's linear-system residual checks evaluated every "
-                                                        "IPM iteration (option lin_res_check); default off, always-on detection = status / "
+                                                        "IPM iteration (option lin_res_check: the general kernel variants, which carry that code, as two launches); default off, always-on detection = status / "
                                                         "qp_status / BAD_PIVOT / NONFINITE flags") if ms_chk else None),
                     h2d_gbs_per_rank=dict(min=min(h2d_all), mean=float(np.mean(h2d_all)), max=max(h2d_all),
                                           note="pinned host -> device copy of this rank's yref (%.0f MB), all ranks at once" % (pin["yref"].numel() * 8 / 1e6)),

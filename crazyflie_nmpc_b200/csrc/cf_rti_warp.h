@@ -32,6 +32,9 @@
 #pragma once
 #include "cf_model.h"
 
+#ifndef CF_CHK_IN_UNIFORM
+#define CF_CHK_IN_UNIFORM 0   // 1: the uniform-grid (benchmarked) kernels also carry the lin_res_check code
+#endif
 #ifndef CF_KSPLIT_LXU
 #define CF_KSPLIT_LXU 1   // Lxu' dx of the forward substitution split over the lane groups
 #endif
@@ -972,7 +975,9 @@ struct CfWarpT
         double lg = 0, lb = 0, ld = 0, lm = 0;    // linear residual norms
         double dxk = 0.0;        // lanes 4..16: dx_k ; stage 0 has none
         double dpi_prev = 0.0;   // lanes 4..16: dpi_{k-1}
-        const bool chk = MODE ? true : PG->lin_res_check != 0;   // the reference's linear-system residual checks
+        // the reference's linear-system residual checks: like the refinement, compiled into the general variants only (the
+        // API selects them for lin_res_check != 0), so that the benchmarked kernels do not carry the code
+        const bool chk = MODE ? true : (CF_CHK_IN_UNIFORM || VDT) && PG->lin_res_check != 0;
         const bool need_pi = need_pi_ || chk;
         const int VO = R_LAM, VN = (need_pi ? CF_SB : B_PX) - R_LAM;   // staged part of the stage block: [R_LAM, end | B_PX)
         pass_begin();

@@ -60,6 +60,8 @@ struct cfnmpc_batch
     void (*kernel)(const CfParams, const CfBatchView) = nullptr;
     // general variants (default launch shape): per-interval time steps, split phases
     void (*kernel_vdt)(const CfParams, const CfBatchView) = nullptr;
+    void (*kernel_fb_g4)(const CfParams, const CfBatchView) = nullptr;   // general feedback kernel at 4 x 4 (two-kernel step of the general path)
+    int grid_fb_g4 = 0;
     void (*kernel_prep)(const CfParams, const CfBatchView) = nullptr;
     void (*kernel_fb)(const CfParams, const CfBatchView) = nullptr;
     // the two halves specialised for the uniform grid: cfnmpc_batch_solve as two launches (option "two_kernels")
@@ -85,7 +87,7 @@ struct cfnmpc_batch
     double *d_mult = nullptr;         // multiplier output [B][cf_mult_stride(N)] (option "multipliers")
     double *d_wst = nullptr;          // per-stage weights [N+1][17] (allocated on first use); while set, the general kernels run
     bool vdt_grid = false, wst = false, prepared = false;   // non-uniform time grid / per-stage weights: the general kernels
-    bool itref = false;                                      // lin_res_check >= 2: iterative refinement (general kernels)
+    bool itref = false;                                      // lin_res_check >= 1: diagnostics / iterative refinement (general kernels)
     bool vdt = false;                                        // = vdt_grid || wst || itref
     size_t smem = 0;
     long long launches = 0;
@@ -193,6 +195,8 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
         if (h->fb_blocks_per_sm < 1) { cfnmpc_batch_destroy(h); return fail(CFNMPC_ECUDA, "feedback kernel does not fit on an SM"); }
     }
     CKH(cudaFuncSetAttribute(h->kernel_vdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
+    h->kernel_fb_g4 = cf_rti_kernel<4, 4, CF_PH_FEEDBACK, true>;
+    CKH(cudaFuncSetAttribute(h->kernel_fb_g4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
     CKH(cudaFuncSetAttribute(h->kernel_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
     CKH(cudaFuncSetAttribute(h->kernel_fb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
     cudaFuncAttributes fa;
@@ -212,6 +216,11 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
         const long want_fb = (long) h->sm_count * h->fb_blocks_per_sm, need_fb = ((long) batch + 3) / 4;
         h->grid_fb = (int) (want_fb < need_fb ? want_fb : need_fb);
         if (h->grid_fb * 4 > h->n_slots) h->n_slots = h->grid_fb * 4;
+        int bg = 0;
+        CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bg, h->kernel_fb_g4, 128, h->smem_general));
+        const long want_g = (long) h->sm_count * (bg > 0 ? bg : 1);
+        h->grid_fb_g4 = (int) (want_g < need_fb ? want_g : need_fb);
+        if (h->grid_fb_g4 * 4 > h->n_slots) h->n_slots = h->grid_fb_g4 * 4;
         const long want_p = (long) h->sm_count * h->prep_minb;
         h->grid_prep_u = (int) (want_p < need_fb ? want_p : need_fb);
         if (h->grid_prep_u * 4 > h->n_slots) h->n_slots = h->grid_prep_u * 4;
@@ -533,8 +542,8 @@ extern "C" int cfnmpc_batch_set_option(cfnmpc_batch *h, const char *option, int 
     if (!strcmp(option, "qp_cond_N")) return set_cond_N(h, value);
     if (!strcmp(option, "lin_res_check")) {
         h->P.lin_res_check = value <= 0 ? 0 : (value == 4 ? 4 : (value >= 2 ? 2 : 1));
-        // iterative refinement is compiled into the general kernel variants only (CfWarpT::HAS_REFINE)
-        h->itref = h->P.lin_res_check >= 2;
+        // the linear-residual diagnostics and the iterative refinement are compiled into the general kernel variants only
+        h->itref = h->P.lin_res_check >= 1;
         h->vdt = h->vdt_grid || h->wst || h->itref;
         h->prepared = false;
     }
@@ -578,7 +587,7 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
     if (n_rti < 1) return fail(CFNMPC_EINVAL, "cfnmpc_batch_solve: n_rti must be >= 1");
     CK(cudaSetDevice(h->device));
     if (h->cond_N) { if (int rc = ensure_prep_store(h)) return rc; }   // the condensed feedback needs the prepared linearisations
-    else if (h->two_kernels && !h->vdt && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;   // no room: the fused kernel
+    else if (h->two_kernels && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;   // no room: the fused kernel
     h->mid_valid = false;
     CK(cudaEventRecord(h->ev0, h->stream));
     for (int r = 0; r < n_rti; r++) {
@@ -592,8 +601,16 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
             if (r == n_rti - 1) { CK(cudaEventRecord(h->ev_mid, h->stream)); h->mid_valid = n_rti == 1; }
             h->kernel_pc<<<h->grid_pc, h->pc_wpb * 32, h->smem_pc, h->stream>>>(h->P, h->bv, h->pcb);
             h->launches++;
-        } else if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
-        else if (h->two_kernels) {
+        } else if (h->vdt && !h->two_kernels) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+        else if (h->vdt) {
+            // the general path (per-interval steps, per-stage weights, linear-residual diagnostics) as two launches as well
+            h->kernel_prep<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+            if (r == n_rti - 1) { CK(cudaEventRecord(h->ev_mid, h->stream)); h->mid_valid = n_rti == 1; }
+            h->kernel_fb_g4<<<h->grid_fb_g4, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+            h->launches++;
+        } else if (h->two_kernels) {
             h->kernel_prep_u<<<h->grid_prep_u, 128, h->smem_general, h->stream>>>(h->P, h->bv);
             CK(cudaGetLastError());
             CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
@@ -676,7 +693,7 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
     if (n_chunks > h->B) n_chunks = h->B;
     CK(cudaSetDevice(h->device));
     if (h->cond_N) { if (int rc = ensure_prep_store(h)) return rc; }
-    else if (h->two_kernels && !h->vdt && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;
+    else if (h->two_kernels && ensure_prep_store(h) != CFNMPC_OK) h->two_kernels = false;
     h->mid_valid = false;
     if (!h->copy_stream) {
         CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -718,8 +735,16 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
         bv.ready = nullptr;
         h->kernel_pc<<<h->grid_pc, h->pc_wpb * 32, h->smem_pc, h->stream>>>(h->P, bv, h->pcb);
         h->launches++;
-    } else if (h->vdt) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, bv);
-    else if (h->two_kernels) {
+    } else if (h->vdt && !h->two_kernels) h->kernel_vdt<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, bv);
+    else if (h->vdt) {
+        bv.prep = h->d_prep;
+        h->kernel_prep<<<h->grid_general, 128, h->smem_general, h->stream>>>(h->P, bv);
+        CK(cudaGetLastError());
+        CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
+        bv.ready = nullptr;
+        h->kernel_fb_g4<<<h->grid_fb_g4, 128, h->smem_general, h->stream>>>(h->P, bv);
+        h->launches++;
+    } else if (h->two_kernels) {
         // the preparation follows the upload front; by the time it has finished every input is in place
         bv.prep = h->d_prep;
         h->kernel_prep_u<<<h->grid_prep_u, 128, h->smem_general, h->stream>>>(h->P, bv);
@@ -1006,7 +1031,7 @@ extern "C" int cfnmpc_batch_info(cfnmpc_batch *h, const char *what, long long *v
     else if (!strcmp(what, "smem_per_block")) *value = (long long) h->smem;
     else if (!strcmp(what, "scratch_bytes")) *value = (long long) h->n_slots * h->bv.scratch_stride * 8;
     else if (!strcmp(what, "launches")) *value = h->launches;
-    else if (!strcmp(what, "two_kernels")) *value = h->cond_N ? 1 : (h->two_kernels && !h->vdt);
+    else if (!strcmp(what, "two_kernels")) *value = h->cond_N ? 1 : h->two_kernels;
     else if (!strcmp(what, "qp_cond_N")) *value = h->cond_N ? h->cond_N : h->N;
     else if (!strcmp(what, "pcond_block_size")) *value = h->cond_N ? h->pc_bs : 1;
     else if (!strcmp(what, "pcond_regs_per_thread")) *value = h->pc_regs;

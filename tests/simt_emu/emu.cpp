@@ -232,6 +232,9 @@ static void job_fn_t(void *a)
 static const double *g_bnd_stage = nullptr;
 // per-stage input boxes [N][8] for the next cfemu_rti_general calls (NULL: none)
 extern "C" void cfemu_set_stage_bounds(const double *tab) { g_bnd_stage = tab; }
+// per-instance parameter arrays {W, W_e, lbu, ubu, lbu0, ubu0} for the next cfemu_rti_general calls (NULL: none)
+static const double *const *g_per_inst = nullptr;
+extern "C" void cfemu_set_per_inst(const double *const *p) { g_per_inst = p; }
 // lin_res_check of the next cfemu_rti_batch calls: 1 = flags only (default), 2 = with iterative refinement
 static int g_lin_res_check = 1;
 extern "C" void cfemu_set_lin_res_check(int v) { g_lin_res_check = v; }
@@ -332,6 +335,10 @@ extern "C" int cfemu_rti_general(int B, int N, double Ts, const double *dts, int
     bv.prep = (double *) ((((uintptr_t) prep.data()) + 15) & ~(uintptr_t) 15);
     bv.prep_stride = pstride;
     bv.bnd_stage = g_bnd_stage;
+    if (g_per_inst) {
+        bv.W_b = g_per_inst[0]; bv.WN_b = g_per_inst[1]; bv.lbu_b = g_per_inst[2]; bv.ubu_b = g_per_inst[3];
+        bv.lbu0_b = g_per_inst[4]; bv.ubu0_b = g_per_inst[5];
+    }
     if (nthreads < 1) nthreads = 1;
     std::atomic<int> next(0);
     std::vector<std::thread> th;

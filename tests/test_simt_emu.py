@@ -356,7 +356,7 @@ def test_emulated_kernel_qp_maxiter_branch(emu, edge, itmax):
     assert rel_err(r["x"][:, XSEL], edge[f"maxiter_{itmax}_xsel"][:n]) < 1e-9
 
 
-def test_emulated_kernel_flags_where_the_reference_nets_fire(emu, edge):
+def test_emulated_kernel_flags_where_the_reference_nets_fire(emu_general, edge):
     """Ill-conditioned instances: where the reference switched to its LQ factorisation or ran iterative refinement the
     kernel's linear-residual flags must be set; converged, unflagged instances agree with the reference."""
     from crazyflie_nmpc_b200 import workloads as wl
@@ -365,7 +365,16 @@ def test_emulated_kernel_flags_where_the_reference_nets_fire(emu, edge):
     calm = np.nonzero((edge["adv_qp_status"] == 0) & (edge["adv_lq"] == 0) & (edge["adv_itref"] == 0))[0][:6]
     sel = np.r_[fired, calm]
     ws = {k: np.ascontiguousarray(w[k][sel]) for k in ("x0", "yref", "yref_e", "x_init", "u_init")}
-    r = emu(ws, 50, per_inst={k: np.ascontiguousarray(w[k][sel]) for k in ("W", "W_e", "lbu", "ubu")})
+    # the linear-residual diagnostics are compiled into the general kernel variants (the library routes lin_res_check there)
+    L = ctypes.CDLL(os.path.join(HERE, "simt_emu", "libcfemu.so"))
+    keep = [np.ascontiguousarray(w[k][sel]) for k in ("W", "W_e", "lbu", "ubu")]
+    ptrs = (_dp * 6)(*[a.ctypes.data_as(_dp) for a in keep], None, None)
+    L.cfemu_set_per_inst.argtypes = [ctypes.POINTER(_dp)]
+    L.cfemu_set_per_inst(ptrs)
+    try:
+        r = emu_general(ws, 50)
+    finally:
+        L.cfemu_set_per_inst(None)
     nf = len(fired)
     assert nf >= 3
     assert ((r["flags"][:nf] & 3) != 0).all(), r["flags"][:nf]
