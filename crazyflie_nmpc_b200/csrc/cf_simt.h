@@ -183,16 +183,24 @@ CF_DEV void cf_amax(double &acc, double x)
     acc = (ax > acc) ? ax : acc;
 }
 
-// butterfly reductions (all lanes get the result)
-CF_DEV double cf_warp_sum(double v)
+// butterfly reductions (all lanes get the result).  Called a dozen times per interior-point iteration, never inside a
+// stage loop: ONE out-of-line copy each -- inlined and unrolled they were 3 000 of the feedback kernel's 11 000 SASS
+// instructions (every 64-bit exchange carries its divergent-warp fallback), and the kernel is sensitive to code size
+// (profiles/README.md, v18/v19).
+#if defined(CF_SIMT_EMU)
+#define CF_OUTLINE static inline
+#else
+#define CF_OUTLINE static __device__ __noinline__
+#endif
+CF_OUTLINE double cf_warp_sum(double v)
 {
-    CF_UNROLL
+    CF_NOUNROLL
     for (int o = 16; o > 0; o >>= 1) v += cf_shfl(v, cf_lane() ^ o);
     return v;
 }
-CF_DEV double cf_warp_max(double v)
+CF_OUTLINE double cf_warp_max(double v)
 {
-    CF_UNROLL
+    CF_NOUNROLL
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, cf_shfl(v, cf_lane() ^ o));
     return v;
 }
