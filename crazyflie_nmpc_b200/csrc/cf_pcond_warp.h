@@ -913,6 +913,7 @@ struct CfPcWarpT
 
     CF_MEM bool lin_res_ok_fact() const { return true; }
     CF_MEM bool lin_res_ok_corr() const { return true; }
+    template <int MODE, int NPI> CF_MEM void forward_t(const bool need_pi) { forward(need_pi); }
     static constexpr bool HAS_REFINE = false;   // iterative refinement belongs to the linear-residual diagnostics of the uncondensed program
 
     // =============================================================== expansion + primal update

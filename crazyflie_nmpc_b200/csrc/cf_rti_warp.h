@@ -32,6 +32,9 @@
 #pragma once
 #include "cf_model.h"
 
+#ifndef CF_SPLIT_FWD
+#define CF_SPLIT_FWD 0   // 1: separate copies of the forward sweep for predictor (no multiplier step) and corrector
+#endif
 #ifndef CF_CHK_IN_UNIFORM
 #define CF_CHK_IN_UNIFORM 0   // 1: the uniform-grid (benchmarked) kernels also carry the lin_res_check code
 #endif
@@ -966,7 +969,9 @@ struct CfWarpT
     // the forward sweep in the benchmarked kernels cost 1.8 % there (profiles/README.md) although they are never executed.
     static constexpr bool HAS_REFINE = VDT;
     CF_MEM bool refine_enabled() const { return HAS_REFINE && PG->lin_res_check >= 2; }
-    template <int MODE>
+    // NPI: -1 = `need_pi_` decides at run time (one copy of the sweep serves predictor and corrector); 0 / 1 = compile-time
+    // (CF_SPLIT_FWD: one copy each, without the warp-uniform branches around the multiplier step in the stage loop)
+    template <int MODE, int NPI = -1>
     CF_MEM void forward_t(const bool need_pi_)
     {
         double *XS = sm + CF_SM_V0, *DS = sm + CF_SM_V1, *PS = sm + CF_SM_V3;
@@ -978,7 +983,7 @@ struct CfWarpT
         // the reference's linear-system residual checks: like the refinement, compiled into the general variants only (the
         // API selects them for lin_res_check != 0), so that the benchmarked kernels do not carry the code
         const bool chk = MODE ? true : (CF_CHK_IN_UNIFORM || VDT) && PG->lin_res_check != 0;
-        const bool need_pi = need_pi_ || chk;
+        const bool need_pi = (NPI >= 0 ? NPI != 0 : need_pi_) || chk;
         const int VO = R_LAM, VN = (need_pi ? CF_SB : B_PX) - R_LAM;   // staged part of the stage block: [R_LAM, end | B_PX)
         pass_begin();
         if (N > 0) fetch(0, 0, VO, VN);
@@ -1369,7 +1374,12 @@ CF_DEV int cf_ipm_solve(CfWarp &w, int &iters, unsigned long long *prof)
             st = ST_FWD;
         } else if (st == ST_FWD) {
             CF_PROF_BEGIN();
+#if CF_SPLIT_FWD
+            if (predictor) w.template forward_t<0, 0>(false);
+            else w.template forward_t<0, 1>(true);
+#else
             w.forward(!predictor);
+#endif
             CF_PROF_END(CF_PROF_FWD);
             if (predictor) {
                 if (!w.lin_res_ok_fact()) w.flags |= CF_FLAG_LIN_RES_FACT;
