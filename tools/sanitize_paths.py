@@ -76,6 +76,15 @@ def run(N):
         s.set("W_dense_table", wl.dense_weight_table(N, seed=1))
         s.set_problem(w).solve(1)
         s.get("x_all")
+    # iterative refinement (general kernels; test mode 4 makes every corrector inaccurate so that the refinement runs)
+    with cf.BatchSolver(B, N, TS) as s:
+        s.set_option("lin_res_check", 4)
+        s.set_problem(w).solve(1)
+        fl = s.get("flags")
+        assert ((fl & 32) != 0).any() and ((fl & 64) == 0).all(), fl
+        s.set_option("lin_res_check", 2)
+        s.set_problem(w).solve(1)
+        res["lin_res_check=2"] = (s.get("x_all"), s.get("u_all"), s.get("status"))
     ref = res["two_kernels"]
     for k, v in loose.items():   # same QP solution, different arithmetic: interior-point tolerances
         ex = float(np.abs(v[0] - ref[0]).max())
@@ -97,6 +106,20 @@ def run(N):
         sim.get("xn")
 
 
+def run_second_model():
+    """The generic-model library (pendulum, nx = 4, nu = 1): preparation kernel + dense-stage feedback program."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden"))
+    from make_golden_pendulum import pendulum_batch
+    wp = pendulum_batch(B, 20, seed=2)
+    with cf.ModelSolver("pendulum", B) as s:
+        s.set_problem(wp).solve(2)
+        st = s.get("status")
+        s.set_problem(wp).prepare().feedback()
+        print(f"pendulum status_ok={int((st == 0).sum())}/{B} OK")
+        assert (st == 0).all()
+
+
 for N in HORIZONS:
     run(N)
+run_second_model()
 print("sanitize_paths: done")
