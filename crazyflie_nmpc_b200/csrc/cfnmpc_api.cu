@@ -104,7 +104,17 @@ static void default_params(CfParams &P, int N, double Ts)
 }
 
 extern "C" const char *cfnmpc_last_error(void) { return g_err.c_str(); }
-extern "C" const char *cfnmpc_version(void) { return "crazyflie_nmpc_b200 0.1 (sm_100a)"; }
+extern "C" const char *cfnmpc_version(void) { return "crazyflie_nmpc_b200 0.2 (sm_100a)"; }
+// sizes the library was generated for and the horizon / final time of its OCP description (the same entry point exists in
+// the generic-model libraries, cfnmpc_generic.cu)
+extern "C" int cfnmpc_model_dims(int *nx, int *nu, int *N, double *Tf)
+{
+    if (nx) *nx = CF_NX;
+    if (nu) *nu = CF_NU;
+    if (N) *N = CF_SPEC_N;
+    if (Tf) *Tf = CF_SPEC_TF;
+    return CFNMPC_OK;
+}
 
 extern "C" int cfnmpc_batch_destroy(cfnmpc_batch *h)
 {

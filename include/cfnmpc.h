@@ -253,6 +253,13 @@ int cfnmpc_debug_pass_cycles(cfnmpc_batch *h, unsigned long long *cycles_calls12
 
 const char *cfnmpc_last_error(void);
 const char *cfnmpc_version(void);
+/* Sizes this library was generated for (nx, nu) and the horizon / final time of its OCP description; any pointer may be
+ * NULL.  libcfnmpc.so is the Crazyflie OCP (13, 4, 50, 0.75).  The same kernel sources compiled against another generated
+ * description (tools/gen_spec.py --model <name>, crazyflie_nmpc_b200/build.py) give libcfnmpc_<name>.so, which exports the
+ * core of this header -- cfnmpc_batch_create / destroy / set / set_option / solve / prepare / feedback / sync / get /
+ * last_solve_ms / info, cfnmpc_last_error, cfnmpc_version, cfnmpc_model_dims -- with array shapes following its nx, nu
+ * (csrc/cfnmpc_generic.cu). */
+int cfnmpc_model_dims(int *nx, int *nu, int *N, double *Tf);
 
 /* ------------------------------------------------------------------ several GPUs behind one handle
  * The batch dimension sharded over the GPUs of one node: shard i owns the contiguous instances
