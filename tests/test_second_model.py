@@ -166,3 +166,33 @@ def test_gpu_generic_path_on_the_crazyflie_ocp_equals_the_tuned_library(port):
     xo, uo = w["x_init"].copy(), w["u_init"].copy()
     port.batch(N, 0.015, w["x0"], w["yref"], w["yref_e"], xo, uo)
     assert rel_err(xg, xo) < 1e-9 and rel_err(ug, uo) < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_pendulum_runtime_weights_and_bounds_against_live_reference():
+    """Run-time weights and a tighter input box on the second model, against the reference library given the same values."""
+    import crazyflie_nmpc_b200 as cf
+    from oracle.oracle import Ref, ref_available
+    if not ref_available("pendulum"):
+        pytest.skip("oracle/_ref/libcfref_pendulum.so did not travel")
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_golden_pendulum import pendulum_batch
+    N, B = 20, 8
+    w = pendulum_batch(B, N, seed=5)
+    W = np.array([500.0, 3000.0, 0.5, 0.05, 0.004])
+    We = np.array([800.0, 2500.0, 0.1, 0.2])
+    lbu, ubu = np.array([-25.0]), np.array([40.0])
+    with cf.ModelSolver("pendulum", B, N=N, Ts=TS) as s:
+        s.set("W", W).set("W_e", We).set("lbu", lbu).set("ubu", ubu)
+        s.set_problem(w).solve(2)
+        x, u, st = s.get("x_all"), s.get("u_all"), s.get("status")
+    rs = Ref("pendulum").solver(N, TS)
+    rs.set_weights(W, We)
+    rs.set_input_bounds(lbu, ubu)
+    for i in range(B):
+        xr, ur = w["x_init"][i].copy(), w["u_init"][i].copy()
+        for _ in range(2):
+            rs.rti(w["x0"][i], w["yref"][i], w["yref_e"][i], xr, ur)
+        assert st[i] == 0 and rel_err(x[i], xr) < 1e-9 and rel_err(u[i], ur) < 1e-9
+    rs.close()
+    assert u.min() >= -25.0 - 1e-9 and u.max() <= 40.0 + 1e-9 and (u.max() > 39.9 or u.min() < -24.9)
