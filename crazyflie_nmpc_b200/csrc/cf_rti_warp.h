@@ -27,8 +27,16 @@
 // (its A-rows are zeroed after the x0 elimination folded A0*xbar into b0) and stage N keeps 4
 // decoupled dummy inputs; both stay exactly zero and cost 2/51 of the work.
 //
-// The per-instance working set (51 stage blocks of 590 doubles = 240 KB) does not fit on chip; it
+// The per-instance working set (51 stage blocks of 552 doubles = 225 KB) does not fit on chip; it
 // lives in a per-warp scratch slot in global memory (L2/HBM).
+//
+// Free states.  The dynamics do not depend on the first CF_NF states (CF_SPEC_NFREE, derived by tools/gen_spec.py from
+// df/dx: the position of the Crazyflie), so the forward sensitivities of those states stay exactly [I;0] through every
+// RK stage (sim_erk_integrator.c:658-731 applied to a zero Jacobian column) and their rows of [B';A'] are unit vectors
+// in every stage.  The feedback program neither stores nor multiplies them: the scratch slot keeps the CF_CR = 14 real
+// rows (inputs, then states CF_NF..12) with b_k as a vector of its own, the factorisation runs on two instead of three
+// 8-row tensor-core tiles (34 instead of 54 DMMA per stage), and the unit rows enter as copies (W rows = P rows, columns
+// of S = columns of W).  Stage 0, whose state rows the x0 elimination drops, treats them as zero where it matters.
 #pragma once
 #include "cf_model.h"
 
@@ -41,17 +49,20 @@
 #ifndef CF_KSPLIT_LXU
 #define CF_KSPLIT_LXU 1   // Lxu' dx of the forward substitution split over the lane groups
 #endif
-#ifndef CF_KSPLIT_COL
-#define CF_KSPLIT_COL 1   // column products [A B] v split over lane pairs (CfWarpT::col_gemv)
-#endif
 
 // ------------------------------------------------------------------ sizes / layout
 #define CF_MROWS (CF_NV + 1)              // rows of [B';A';res_b'] held per stage (18)
-#define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r
+#define CF_MSZ (CF_MROWS * CF_NX)         // 234 doubles, element (r,c) at c*18 + r: the form the preparation produces
 #define CF_LU (CF_MROWS * CF_NU)          // factor, input columns: 18 x 4, (r,j) at r*4 + j
 #define CF_XP ((CF_NX + 1) & ~1)          // a state vector padded to an even number of doubles (14)
 #define CF_UP ((CF_NU + 1) & ~1)          // an input vector padded likewise (4)
 #define CF_TRI_NX ((CF_NX * (CF_NX + 1)) / 2)   // packed lower triangle of an nx x nx matrix (91)
+// compact [B';A'] of the scratch slot (see "Free states" above)
+#define CF_NF CF_SPEC_NFREE
+#define CF_CR (CF_NV - CF_NF)             // stored rows (14): row m = input m (m < nu), state m - nu + CF_NF otherwise
+#define CF_CST ((CF_CR + 1) & ~1)         // column stride (14): element (m,c) at c*14 + m
+#define CF_CMSZ (CF_CST * CF_NX)          // 182 doubles
+#define CF_PC0 (CF_NU - CF_NF)            // column of state 0 in the shared-memory array of P (state i at column i + 1)
 #define CF_LUST 6                         // row stride of the 18 x 4 block while it is factorised in shared memory: 128-bit
                                           //   row loads without bank conflicts, column stores 2-way instead of 5-way
 #define CF_PST CF_XP                      // row stride of the cost-to-go Hessian once expanded in shared memory (14)
@@ -61,25 +72,27 @@
 //   residual+factorisation sweep [0, B_RD)      rhs-only backward sweep [R_BKP, B_PX)      forward sweep [R_LAM, CF_SB)
 // 17-vectors are padded to 18, 13-vectors to 14; bound fields are [lb(4) | ub(4)].
 //   R_UX  ux_k            R_PI  pi_{k-1} (multiplier of the dynamics ENTERING stage k)   R_DPI  its step
-//   R_RQ  gradient        R_D   bound data [lb - u ; u - ub]
+//   R_RQ  gradient        R_D   bound data [lb - u ; u - ub]        R_B  b_k (linearisation, never changes inside the IPM)
 //   R_BKP lam*t of the iterate (res_m backup)          R_PB   P_{k+1} res_b (cached for the rhs-only sweeps)
 //   R_DLAM, R_DT steps    R_LAM, R_T multipliers / slacks
 //   R_DUX  in: l_u | p_k left by a backward sweep, out: the step dux_k
-//   B_M    [B';A'] rows 0..16, row 17 = b_k (linearisation, never changes inside the IPM), element (r,c) at c*18 + r
+//   B_M    [B';A'] in compact form: the CF_CR = 14 rows that are not unit vectors, element (m,c) at c*14 + m
 //   R_RESD, R_RESM, R_RESG, R_RESB residuals (R_RESM = the complementarity rhs of the next solve)
 //   B_LU   factor of the 4 input columns (18 x 4), INVERSE pivots on the diagonal (like BLASFEO's dA)
 //   B_PX   packed lower triangle of P_{k+1} (what the forward sweep of stage k multiplies with, after expanding it to
 //          full symmetric rows in shared memory; written by the factorisation of stage k+1)
-enum { R_UX = 0, R_PI = R_UX + CF_MROWS, R_DPI = R_PI + CF_XP, R_RQ = R_DPI + CF_XP, R_D = R_RQ + CF_MROWS, R_BKP = R_D + 2 * CF_NU,
-       R_PB = R_BKP + 2 * CF_NU, R_DLAM = R_PB + CF_XP, R_DT = R_DLAM + 2 * CF_NU, R_LAM = R_DT + 2 * CF_NU, R_T = R_LAM + 2 * CF_NU,
-       R_DUX = R_T + 2 * CF_NU, B_M = R_DUX + CF_MROWS, B_RD = B_M + CF_MSZ, R_RESD = B_RD, R_RESM = R_RESD + 2 * CF_NU,
-       R_RESG = R_RESM + 2 * CF_NU, R_RESB = R_RESG + CF_MROWS, B_LU = R_RESB + CF_XP, B_PX = B_LU + CF_LU,
-       CF_SB = B_PX + CF_LX };   // 590 doubles per stage (nx = 13, nu = 4)
-static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 && CF_SB % 2 == 0, "16-byte alignment of TMA ranges");
+enum { R_UX = 0, R_PI = R_UX + CF_MROWS, R_DPI = R_PI + CF_XP, R_RQ = R_DPI + CF_XP, R_D = R_RQ + CF_MROWS, R_B = R_D + 2 * CF_NU,
+       R_BKP = R_B + CF_XP, R_PB = R_BKP + 2 * CF_NU, R_DLAM = R_PB + CF_XP, R_DT = R_DLAM + 2 * CF_NU, R_LAM = R_DT + 2 * CF_NU,
+       R_T = R_LAM + 2 * CF_NU, R_DUX = R_T + 2 * CF_NU, B_M = R_DUX + CF_MROWS, B_RD = B_M + CF_CMSZ, R_RESD = B_RD,
+       R_RESM = R_RESD + 2 * CF_NU, R_RESG = R_RESM + 2 * CF_NU, R_RESB = R_RESG + CF_MROWS, B_LU = R_RESB + CF_XP, B_PX = B_LU + CF_LU,
+       CF_SB = B_PX + CF_LX };   // 552 doubles per stage (nx = 13, nu = 4)
+static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 && CF_SB % 2 == 0 && R_BKP % 2 == 0 && R_LAM % 2 == 0,
+              "16-byte alignment of TMA ranges");
 #if CF_CRAZYFLIE
-static_assert(R_PI == 18 && R_DPI == 32 && R_RQ == 46 && R_D == 64 && R_BKP == 72 && R_PB == 80 && R_DLAM == 94 && R_DT == 102 &&
-              R_LAM == 110 && R_T == 118 && R_DUX == 126 && B_M == 144 && B_RD == 378 && R_RESM == B_RD + 8 && R_RESG == B_RD + 16 &&
-              R_RESB == B_RD + 34 && B_LU == B_RD + 48 && CF_SB == 590, "stage block layout of the tuned program");
+static_assert(R_PI == 18 && R_DPI == 32 && R_RQ == 46 && R_D == 64 && R_B == 72 && R_BKP == 86 && R_PB == 94 && R_DLAM == 108 &&
+              R_DT == 116 && R_LAM == 124 && R_T == 132 && R_DUX == 140 && B_M == 158 && B_RD == 340 && R_RESM == B_RD + 8 &&
+              R_RESG == B_RD + 16 && R_RESB == B_RD + 34 && B_LU == B_RD + 48 && CF_SB == 552, "stage block layout of the tuned program");
+static_assert(CF_NF == 3 && CF_CR == 14 && CF_CST == 14 && CF_PC0 == 1, "compact [B';A'] of the tuned program");
 #endif
 
 // HPIPM arguments in effect for the reference configuration (BALANCE mode + acados
@@ -216,8 +229,9 @@ static inline
 
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
 #define CF_MAX2(a, b) ((a) > (b) ? (a) : (b))
-// sweeps: staged range of a stage block, double buffered (480 doubles for nx = 13, nu = 4)
-#define CF_SM_BUFSZ CF_MAX2(CF_MAX2(B_RD, CF_SB - R_LAM), CF_MAX2(CF_MAX2(B_PX - R_BKP, CF_MROWS * 20), 2 * CF_MSZ))
+// sweeps: staged range of a stage block, double buffered (468 doubles for nx = 13, nu = 4: the two [B';A';b'] of the linearisation)
+#define CF_SM_WLU (16 * 20 + CF_MROWS * CF_LUST)   // factorisation: W (16 rows, stride 20) and the 18 x 4 block behind it
+#define CF_SM_BUFSZ CF_MAX2(CF_MAX2(B_RD, CF_SB - R_LAM), CF_MAX2(CF_MAX2(B_PX - R_BKP, CF_SM_WLU), 2 * CF_MSZ))
 #define CF_SM_BUF0 0
 #define CF_SM_BUF1 CF_SM_BUFSZ
 #define CF_SM_MS0 0                            // linearisation: [B';A';b'] staging, double buffered
@@ -232,11 +246,11 @@ static inline
 #define CF_SM_V3 (CF_SM_V2 + 20)
 #define CF_SM_BAR (CF_SM_V3 + 20)              // two mbarriers
 #define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
-#define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1354 doubles = 10832 bytes per warp
+#define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1330 doubles = 10640 bytes per warp
 static_assert(CF_SM_DOUBLES % 2 == 0, "every warp's shared-memory slice must start on a 16-byte boundary");
-static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && CF_MROWS * CF_ALST <= CF_SM_BUFSZ,
+static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && CF_SM_WLU <= CF_SM_BUFSZ,
               "staging buffers");
-static_assert(!CF_CRAZYFLIE || CF_SM_BUFSZ == 480, "shared-memory layout of the tuned program");
+static_assert(!CF_CRAZYFLIE || CF_SM_BUFSZ == 468, "shared-memory layout of the tuned program");
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
 
@@ -394,7 +408,7 @@ struct CfWarpT
         pass_begin();   // the generic stores above are read back by bulk copies
         if (N > 0) fetch_nom(0, 0);
     }
-    CF_MEM double *nom_buf(int bf) const { return sm + CF_SM_BUFSZ + bf * ((CF_NOM + 7) & ~7); }   // (sm + 480 + bf * 80)
+    CF_MEM double *nom_buf(int bf) const { return sm + CF_SM_BUFSZ + bf * ((CF_NOM + 7) & ~7); }   // (sm + 468 + bf * 80)
     CF_MEM void fetch_nom(int bf, int k)
     {
         if (lane == 0) {
@@ -469,7 +483,18 @@ struct CfWarpT
         if (PH == CF_PH_PREPARATION && lane == CF_NV) rqdst[lane] = 0.0;   // pad of the 18-double gradient record
         if (PH != CF_PH_PREPARATION) stage_bounds_init(k, uk);
         cf_syncwarp();
-        if (lane == 0) cf_bulk_s2g(mdst, MS, CF_MSZ * 8);
+        if constexpr (PH == CF_PH_PREPARATION) {
+            if (lane == 0) cf_bulk_s2g(mdst, MS, CF_MSZ * 8);
+        } else {
+            // one-launch step: the compact form goes straight to the scratch slot (generic stores; the pass_begin() of the
+            // first sweep orders them before its bulk reads)
+            CF_NOUNROLL
+            for (int e = lane; e < CF_CMSZ; e += 32) {
+                const int c = e / CF_CST, m = e - c * CF_CST;
+                mdst[e] = (m < CF_CR) ? MS[c * CF_MROWS + (m < CF_NU ? m : m + CF_NF)] : 0.0;
+            }
+            if (lane < CF_NX) rec(k)[R_B + lane] = MS[lane * CF_MROWS + CF_NV];
+        }
     }
 
     // x0 elimination on the staged block of stage 0 (x_ocp_qp_red.c:310-330): xbar = lbx - x_0 ; b_0 += A_0 xbar ; drop
@@ -543,8 +568,9 @@ struct CfWarpT
     CF_MEM void load_prepared(const double *xg, const double *ug, const double *x0g)
     {
         // Four stage records per trip travel prepared store -> shared memory -> scratch slot on the TMA engine (one bulk
-        // load of the contiguous records, two bulk stores per stage: [B';A';b'] and the gradient); the lanes meanwhile
-        // evaluate the bound vectors and the initial interior-point variables of those stages.
+        // load of the contiguous records, two bulk stores per stage: [B';A'] and the gradient); the lanes meanwhile
+        // evaluate the bound vectors and the initial interior-point variables of those stages, and then bring [B';A';b']
+        // into the compact form of the slot (CF_CR): b_k leaves as a vector, the rows that are not unit vectors move up.
         double *ST = sm;
         static_assert(4 * CF_PREP_STAGE <= CF_SM_V0, "staging area of load_prepared");
         pass_begin();   // generic accesses of the previous instance to this shared memory precede the bulk writes
@@ -560,10 +586,25 @@ struct CfWarpT
             wait(0);
             if (k0 == 0) eliminate_x0(ST, xg, x0g);
             cf_syncwarp();
+            CF_NOUNROLL
+            for (int q = 0; q < n; q++) {
+                double *Sq = ST + q * CF_PREP_STAGE;
+                if (lane < CF_NX) rec(k0 + q)[R_B + lane] = Sq[lane * CF_MROWS + CF_NV];
+                // in place, 32 elements per trip in increasing order: a destination never lies above a source still to be read
+                CF_NOUNROLL
+                for (int e0 = 0; e0 < CF_CMSZ; e0 += 32) {
+                    const int e = e0 + lane, c = e / CF_CST, m = e - c * CF_CST;
+                    const bool on = e < CF_CMSZ;
+                    const double v = (on && m < CF_CR) ? Sq[c * CF_MROWS + (m < CF_NU ? m : m + CF_NF)] : 0.0;
+                    cf_syncwarp();
+                    if (on) Sq[e] = v;
+                }
+            }
+            cf_syncwarp();
             if (lane == 0) {
                 CF_NOUNROLL
                 for (int q = 0; q < n; q++) {
-                    cf_bulk_s2g(blk(k0 + q) + B_M, ST + q * CF_PREP_STAGE, CF_MSZ * 8);
+                    cf_bulk_s2g(blk(k0 + q) + B_M, ST + q * CF_PREP_STAGE, CF_CMSZ * 8);
                     cf_bulk_s2g(rec(k0 + q) + R_RQ, ST + q * CF_PREP_STAGE + CF_MSZ, 18 * 8);
                 }
                 cf_bulk_s2g_wait_read0();   // the staging area may be refilled
@@ -576,32 +617,42 @@ struct CfWarpT
     }
 
     // =============================================================== IPM pieces
-    // y[c] = sum_{r < 17} M[r][c] v[r]  (+ M[17][c] when `with_row17`) for the state column c of lanes 4..16, the 18 rows of
-    // a column shared by a lane pair: the state lane takes rows 0..9, its partner (lanes 20..31 and lane 17)
-    // rows 10..17; one exchange combines them.  Five 128-bit loads of M and of v per lane instead of nine, and dependent
-    // chains of 5 instead of 9 multiply-adds (the column products were 21 % of the kernel's shared-memory wavefronts,
-    // profiles/prof_r2_v15_wavefronts.txt).  Mk: staged [B';A';b'] (element (r,c) at c*18 + r), v: 20-double vector.
-    CF_MEM double col_gemv(const double *Mk, const double *v, const bool with_row17) const
+    // lane -> stored row of the compact [B';A'] (inputs 0..3, states CF_NF.. behind them); free states and idle lanes get a
+    // harmless row of their own half-warp (the same address as an active lane: a broadcast, no bank conflict)
+    CF_MEM bool stored_lane() const { return lane < CF_NU || (lane >= CF_NU + CF_NF && lane < CF_NV); }
+    CF_MEM bool free_lane() const { return lane >= CF_NU && lane < CF_NU + CF_NF; }
+    CF_MEM int mrow() const { return stored_lane() ? (lane < CF_NU ? lane : lane - CF_NF) : (lane < 16 ? 0 : CF_CR - 1); }
+    // lane -> position of its variable in a broadcast vector for the column products: stored rows first, free states behind
+    CF_MEM int vidx() const { return lane < CF_NU ? lane : (lane < CF_NU + CF_NF ? CF_CR + lane - CF_NU : lane - CF_NF); }
+
+    // y[c] = sum_{m < 14} M[m][c] v[m] + v[14 + c] (c < CF_NF: the unit row of free state c) + bv[c] (when given) for the
+    // state column c of lanes 4..16, the 14 stored rows of a column shared by a lane pair: the state lane takes rows 0..5
+    // and the two extra terms, its partner (lanes 20..31 and lane 17) rows 6..13; one exchange combines them.  (The split at
+    // row 6 keeps the 128-bit loads of every quarter warp on distinct banks at column stride 14.)  Mk: staged compact
+    // [B';A'] (element (m,c) at c*14 + m), v: 20-double vector in the order of vidx().
+    CF_MEM double col_gemv(const double *Mk, const double *v, const double *bv) const
     {
-        // partner of state lane L: L ^ 16 (lanes 20..31), except lane 16 whose partner is lane 17 (lane 0 would collide with
-        // lane 5 on the banks of its column); lanes 0..3, 18, 19 compute a throw-away duplicate of column 0
+        // partner of state lane L: L ^ 16 (lanes 20..31), except lane 16 whose partner is lane 17; lanes 0..3, 18, 19 compute
+        // a throw-away duplicate of column 0
         const int lp = lane == 16 ? 17 : (lane == 17 ? 16 : lane ^ 16);
         const bool lo = lane >= CF_NU && lane < CF_NV, hi = lane == 17 || lane >= 20;
-        const int cc = lo ? lane - CF_NU : (hi ? lp - CF_NU : 0), r0 = lo ? 0 : 10;
-        const double *Mc = Mk + cc * CF_MROWS + r0, *vc = v + r0;
+        const int cc = lo ? lane - CF_NU : (hi ? lp - CF_NU : 0), r0 = lo ? 0 : 6;
+        const double *Mc = Mk + cc * CF_CST + r0, *vc = v + r0;
         double s0 = 0.0, s1 = 0.0;
         CF_UNROLL
-        for (int rp = 0; rp < 3; rp++) {   // rows 0..5 | 10..15
+        for (int rp = 0; rp < 3; rp++) {   // rows 0..5 | 6..11
             const cf_d2 m2 = cf_ld2(Mc + 2 * rp), v2 = cf_ld2(vc + 2 * rp);
             s0 += m2.x * v2.x;
             s1 += m2.y * v2.y;
         }
-        const cf_d2 m3 = cf_ld2(Mc + 6), v3 = cf_ld2(vc + 6);                       // rows 6, 7 | 16, 17
-        const cf_d2 m4 = cf_ld2(Mc + (lo ? 8 : 6)), v4 = cf_ld2(vc + (lo ? 8 : 6));   // rows 8, 9 | (none)
-        s0 += m3.x * v3.x;
-        s1 += lo ? m3.y * v3.y : (with_row17 ? m3.y : 0.0);
-        s0 += lo ? m4.x * v4.x : 0.0;
-        s1 += lo ? m4.y * v4.y : 0.0;
+        if (lo) {
+            s0 += (cc < CF_NF) ? v[CF_CR + cc] : 0.0;
+            s1 += bv ? bv[cc] : 0.0;
+        } else {                           // rows 12, 13
+            const cf_d2 m3 = cf_ld2(Mc + 6), v3 = cf_ld2(vc + 6);
+            s0 += m3.x * v3.x;
+            s1 += m3.y * v3.y;
+        }
         const double part = s0 + s1;
         return part + cf_shfl(part, lp);
     }
@@ -632,23 +683,31 @@ struct CfWarpT
     {
         const double a = step_adjust(a_raw);
         double ng = 0, nb = 0, nd = 0, nm = 0, mus = 0;
-        double *PS = sm + CF_SM_P;                 // P_{k+1}, full symmetric 13 x 13, stride 20
+        double *PS = sm + CF_SM_P;                 // P_{k+1}, lower triangle of a 13 x 20 array
         double *PV = sm + CF_SM_V0;                // p_{k+1}
-        double *UXS = sm + CF_SM_V1, *PIS = sm + CF_SM_V2;   // residual part: ux_k, pi_k broadcast
-        double *G = sm + CF_SM_V1, *HD = sm + CF_SM_V2;      // factor part: gradient row / Hessian diagonal
+        double *UXS = sm + CF_SM_V1, *PIS = sm + CF_SM_V2;   // residual part: ux_k (order of vidx()), pi_k broadcast
+        double *G = sm + CF_SM_V1, *HD = sm + CF_SM_V2;      // factor part: gradient row / Hessian diagonal (order of vidx())
         pass_begin();
         fetch(N & 1, N, 0, B_M);
         const bool ul = lane < CF_NU, vl = lane < CF_NV;
         const bool xl = lane >= CF_NU && vl;
+        const bool sl = stored_lane(), fl = free_lane();
         // (idle lanes read element 8, not 0: in the second half-warp lane 16 sits on the banks of element 0)
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 8;
+        const int mr = mrow(), vi = vidx();
         // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
         const int fg = lane >> 2, fq = lane & 3;
         const int rl = lane < CF_MROWS ? lane : 17;
+        // Row order of the tiles: the 14 stored rows, then (row 14) the gradient / res_b row; row 15 is padding.  Row r of the
+        // tiles is row lr(r) of the 18 x 4 input-column block, whose rows stay in the order of the stage variables.
+        const int r1 = 8 + fg;   // this lane's row in the second row tile
+        const int lr0 = fg < CF_NU ? fg : fg + CF_NF, lr1 = r1 < CF_CR ? r1 + CF_NF : 17;
+        // A fragments of the second row tile: rows 8..13 of the staged [B';A'], row 14 from the res_b vector, row 15 zero
+        const int a1o = r1 < CF_CR ? B_M + r1 : R_B, a1s = r1 < CF_CR ? CF_CST : 1;
         // P_{k+1} is kept in shared memory as the lower triangle of a 13 x 20 array, row = state index, column = the
-        // state's index among the stage variables (4 + state index): exactly where the Schur-complement tiles fall, so
-        // they are stored as whole tiles; the fragment loads of the next stage's first product swap indices instead
-        // (addresses are loop-invariant): pa[kk][h] = address of P[4kk+fq][8h+fg]
+        // state's column among the tile columns (state i: i + CF_PC0; stored states: exactly where the Schur-complement
+        // tiles fall, so they are stored as whole tiles); the fragment loads of the next stage's first product swap indices
+        // instead (addresses are loop-invariant): pa[kk][h] = address of P[4kk+fq][8h+fg]
         int pa[4][2];
         CF_UNROLL
         for (int kk = 0; kk < 4; kk++)
@@ -657,7 +716,7 @@ struct CfWarpT
                 const int i = 4 * kk + fq, j = 8 * hh + fg;
                 const bool ok = i < CF_NX && j < CF_NX;
                 const int hi = i > j ? i : j, lo = i > j ? j : i;
-                pa[kk][hh] = ok ? hi * CF_ALST + lo + CF_NU : -1;
+                pa[kk][hh] = ok ? hi * CF_ALST + lo + CF_PC0 : -1;
             }
         // The packed lower triangle of P_{k+1} travels to the block of stage k from this shared-memory array, element
         // e = lane + 32 t of the triangle per lane and trip: three coalesced stores per stage (scattering it from the
@@ -669,7 +728,7 @@ struct CfWarpT
             int i = 0;
             CF_UNROLL
             for (int q = 1; q < CF_NX; q++) i += (e >= cf_tri(q)) ? 1 : 0;
-            pk[t] = (e < 91) ? i * CF_ALST + (e - cf_tri(i)) + CF_NU : -1;
+            pk[t] = (e < 91) ? i * CF_ALST + (e - cf_tri(i)) + CF_PC0 : -1;
         }
         double ux_next = 0.0;   // lanes 4..16: x-part of ux_{k+1} (new iterate)
         double pi_k = 0.0;      // lanes 4..16: pi_k (new iterate), read from the record of stage k+1
@@ -720,42 +779,29 @@ struct CfWarpT
                 }
             }
             if (kl) {   // warp-uniform
-                if (vl) UXS[lane] = uxc;
+                if (vl) UXS[vi] = uxc;
                 if (xl) PIS[ci] = pi_k;
                 cf_syncwarp();
                 double *Mk = VS + B_M;
-                {   // res_g += [B';A'] pi_k   (row layout: own elements stride 18)
+                {   // res_g += [B';A'] pi_k   (row layout: own elements stride 14; a free state's row is a unit vector, and
+                    // dropped like the other state rows at stage 0)
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
                     for (int cp = 0; cp < 6; cp++) {
                         const cf_d2 p2 = cf_ld2(PIS + 2 * cp);
-                        s0 += Mk[(2 * cp) * CF_MROWS + lv] * p2.x;
-                        s1 += Mk[(2 * cp + 1) * CF_MROWS + lv] * p2.y;
+                        s0 += Mk[(2 * cp) * CF_CST + mr] * p2.x;
+                        s1 += Mk[(2 * cp + 1) * CF_CST + mr] * p2.y;
                     }
-                    s0 += Mk[12 * CF_MROWS + lv] * PIS[12];
-                    rg += s0 + s1;
+                    s0 += Mk[12 * CF_CST + mr] * PIS[12];
+                    rg += sl ? s0 + s1 : ((fl && k > 0) ? pi_k : 0.0);
                 }
-                {   // res_b_k = (b_k - x_{k+1}) + [A B] ux_k   (column layout: contiguous; b_k is row 17 of the column)
-#if CF_KSPLIT_COL
-                    const double rb = col_gemv(Mk, UXS, true) - ux_next;
-#else
-                    const double *Mc = Mk + ci * CF_MROWS;
-                    double s0 = 0.0, s1 = 0.0;
-                    CF_UNROLL
-                    for (int rp = 0; rp < 8; rp++) {
-                        const cf_d2 m2 = cf_ld2(Mc + 2 * rp), u2 = cf_ld2(UXS + 2 * rp);
-                        s0 += m2.x * u2.x;
-                        s1 += m2.y * u2.y;
-                    }
-                    const cf_d2 m2 = cf_ld2(Mc + 16);
-                    s0 += m2.x * UXS[16];
-                    const double rb = (m2.y - ux_next) + (s0 + s1);
-#endif
-                    cf_syncwarp();   // every lane has read its column: row 17 of the staged block becomes res_b (ROWIN :490)
+                {   // res_b_k = (b_k - x_{k+1}) + [A B] ux_k   (column layout: contiguous)
+                    const double rb = col_gemv(Mk, UXS, VS + R_B) - ux_next;
+                    cf_syncwarp();   // every lane has read b_k: the staged vector becomes res_b (ROWIN :490)
                     if (xl) {
                         cf_amax(nb, rb);
                         rk[R_RESB + ci] = rb;
-                        Mk[ci * CF_MROWS + 17] = rb;
+                        VS[R_B + ci] = rb;
                     }
                 }
             }
@@ -770,88 +816,86 @@ struct CfWarpT
                 cf_syncwarp();
                 const double hN = HN + CF_REG_PRIM;
                 if (xl) {
-                    PS[ci * CF_ALST + ci + CF_NU] = hN;
+                    PS[ci * CF_ALST + ci + CF_PC0] = hN;
                     PV[ci] = rg;
                     rk[R_DUX + lane] = rg;   // p_N for the forward sweep
                 }
                 continue;
             }
             const double g = vl ? rg + gam : 0.0, hd = Hk + CF_REG_PRIM + Gam;
-            cf_syncwarp();  // row 17 of M_k is complete
-            const double *Mk = VS + B_M;
-            double *WS = VS;   // W rows 18 x 16 (stride 20) overlay the staged block once M is in registers
-            // ---- W(18x13) = M(18x13) * P(13x13): row tiles t (rows 8t+fg), column tiles 0..1, K padded to 16
-            double am[3][4];     // am[t][kk] = M[8t+fg][4kk+fq]: A fragment here, B fragment (M') of the second product
-            double wt[3][2][2];
+            cf_syncwarp();  // res_b is complete
+            double *WS = VS;                      // W rows 16 x 16 (stride 20) overlay the staged block once M is in registers,
+            double *LUs = VS + 16 * CF_ALST;      // the 18 x 4 input-column block sits behind them
+            // ---- W(15x13) = [M;res_b'](15x13) * P(13x13): row tiles t (rows 8t+fg), column tiles 0..1, K padded to 16
+            double am[2][4];     // am[t][kk] = M[8t+fg][4kk+fq]: A fragment here, B fragment (M') of the second product
+            double wt[2][2][2];
             CF_UNROLL
-            for (int t = 0; t < 3; t++) { wt[t][0][0] = wt[t][0][1] = wt[t][1][0] = wt[t][1][1] = 0.0; }
+            for (int t = 0; t < 2; t++) { wt[t][0][0] = wt[t][0][1] = wt[t][1][0] = wt[t][1][1] = 0.0; }
             CF_UNROLL
             for (int kk = 0; kk < 4; kk++) {
                 const int kc = 4 * kk + fq;
                 const bool kv = kc < CF_NX;
                 const double b0 = pa[kk][0] >= 0 ? PS[pa[kk][0]] : 0.0;   // P[kc][fg]
                 const double b1 = pa[kk][1] >= 0 ? PS[pa[kk][1]] : 0.0;   // P[kc][8+fg]
+                am[0][kk] = kv ? VS[B_M + kc * CF_CST + fg] : 0.0;
+                am[1][kk] = (kv && r1 <= CF_CR) ? VS[a1o + kc * a1s] : 0.0;
                 CF_UNROLL
-                for (int t = 0; t < 3; t++) {
-                    const int r = 8 * t + fg;
-                    am[t][kk] = (kv && r < CF_MROWS) ? Mk[kc * CF_MROWS + r] : 0.0;
+                for (int t = 0; t < 2; t++) {
                     cf_dmma(wt[t][0][0], wt[t][0][1], am[t][kk], b0);
                     cf_dmma(wt[t][1][0], wt[t][1][1], am[t][kk], b1);
                 }
             }
-            // row 17 (tile 2, fg == 1): Pb_k = P res_b (ROWEX :622), then + p_{k+1}' (GEAD :623)
-            if (fg == 1) {
+            // row 14 (tile 1, fg == 6): Pb_k = P res_b (ROWEX :622), then + p_{k+1}' (GEAD :623)
+            if (r1 == CF_CR) {
                 double *pb = rk + R_PB;
                 CF_UNROLL
                 for (int tp = 0; tp < 2; tp++)
                     CF_UNROLL
                     for (int e = 0; e < 2; e++) {
                         const int c = 8 * tp + 2 * fq + e;
-                        if (c < CF_NX) { pb[c] = wt[2][tp][e]; wt[2][tp][e] += PV[c]; }
+                        if (c < CF_NX) { pb[c] = wt[1][tp][e]; wt[1][tp][e] += PV[c]; }
                     }
             }
             cf_syncwarp();  // every lane holds its M fragments: the staged block may be overwritten by W
             CF_UNROLL
-            for (int t = 0; t < 3; t++) {
+            for (int t = 0; t < 2; t++) {
                 const int r = 8 * t + fg;
-                if (r < CF_MROWS) {
-                    cf_st2(WS + r * CF_ALST + 2 * fq, wt[t][0][0], wt[t][0][1]);
-                    cf_st2(WS + r * CF_ALST + 8 + 2 * fq, wt[t][1][0], wt[t][1][1]);
-                }
+                cf_st2(WS + r * CF_ALST + 2 * fq, wt[t][0][0], wt[t][0][1]);
+                cf_st2(WS + r * CF_ALST + 8 + 2 * fq, wt[t][1][0], wt[t][1][1]);
             }
-            if (lane < CF_MROWS) { G[lane] = g; HD[lane] = hd; }
+            // rows of the free states in the input-column block: S[p_i][u_j] = W[u_j][i] (their rows of [B';A'] are unit
+            // vectors), held by the lanes of tile row j < nu
+            if (fg < CF_NU && fq < 2) {
+                CF_UNROLL
+                for (int e = 0; e < 2; e++)
+                    if (2 * fq + e < CF_NF) LUs[(CF_NU + 2 * fq + e) * CF_LUST + fg] = wt[0][0][e];
+            }
+            if (vl) { G[vi] = g; HD[vi] = hd; }
             cf_syncwarp();
             // ---- S = D + W * M': A fragments from W, B fragments are the M fragments already in registers
-            double wf[3][4];
+            double wf[2][4];
             CF_UNROLL
-            for (int t = 0; t < 3; t++) {
-                const int r = 8 * t + fg;
+            for (int t = 0; t < 2; t++)
                 CF_UNROLL
-                for (int kk = 0; kk < 4; kk++) wf[t][kk] = (r < CF_MROWS) ? WS[r * CF_ALST + 4 * kk + fq] : 0.0;
-            }
-            double sx[3][3][2];  // lower tiles (t, tp <= t): S[8t+fg][8tp+2fq+{0,1}]
+                for (int kk = 0; kk < 4; kk++) wf[t][kk] = WS[(8 * t + fg) * CF_ALST + 4 * kk + fq];
+            double sx[2][2][2];  // lower tiles (t, tp <= t): S[8t+fg][8tp+2fq+{0,1}]
             CF_UNROLL
-            for (int t = 0; t < 3; t++) {
+            for (int t = 0; t < 2; t++) {
                 CF_UNROLL
                 for (int tp = 0; tp <= t; tp++) {
                     double s0 = 0.0, s1 = 0.0;
                     CF_UNROLL
                     for (int kk = 0; kk < 4; kk++) cf_dmma(s0, s1, wf[t][kk], am[tp][kk]);
                     const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
-                    if (r == 17) { s0 += G[c0 < 17 ? c0 : 0]; s1 += G[c0 + 1 < 17 ? c0 + 1 : 0]; }
+                    if (r == CF_CR) { s0 += G[c0 < CF_CR ? c0 : 0]; s1 += G[c0 + 1 < CF_CR ? c0 + 1 : 0]; }
                     if (r == c0) s0 += HD[r];
                     if (r == c0 + 1) s1 += HD[r];
                     sx[t][tp][0] = s0; sx[t][tp][1] = s1;
                 }
             }
-            cf_syncwarp();  // every lane has its W fragments: WS is reused for the 18 x 4 input-column block
-            double *LUs = WS;
-            if (fq < 2) {
-                CF_UNROLL
-                for (int t = 0; t < 3; t++) {
-                    const int r = 8 * t + fg;
-                    if (r < CF_MROWS) cf_st2(LUs + r * CF_LUST + 2 * fq, sx[t][0][0], sx[t][0][1]);
-                }
+            if (fq < 2) {   // the 4 input columns of the stored rows and of the gradient row
+                cf_st2(LUs + lr0 * CF_LUST + 2 * fq, sx[0][0][0], sx[0][0][1]);
+                if (r1 <= CF_CR) cf_st2(LUs + lr1 * CF_LUST + 2 * fq, sx[1][0][0], sx[1][0][1]);
             }
             cf_syncwarp();
             // ---- POTRF_L_MN(nv+1, nu): the 4 input columns, one per step, lane = row; non-positive pivot -> 0
@@ -888,33 +932,59 @@ struct CfWarpT
                 }
             }
             // ---- Schur complement on the tensor cores (K = 4 = the input columns): S -= Ls Ls'
-            double la[3];
-            CF_UNROLL
-            for (int t = 0; t < 3; t++) {
-                const int r = 8 * t + fg;
-                la[t] = (r < CF_MROWS) ? LUs[r * CF_LUST + fq] : 0.0;
-            }
+            const double la0 = LUs[lr0 * CF_LUST + fq], la1 = (r1 <= CF_CR) ? LUs[lr1 * CF_LUST + fq] : 0.0;
+            const double lf = (fg < CF_NF) ? LUs[(CF_NU + fg) * CF_LUST + fq] : 0.0;   // rows of the free states: A and B fragment
+            const double la[2] = {la0, la1};
             cf_syncwarp();  // all reads of PS/PV (first product) are long complete; they are rewritten below
             {
                 CF_UNROLL
-                for (int t = 0; t < 3; t++) {
+                for (int t = 0; t < 2; t++) {
+                    const int r = 8 * t + fg;
+                    const bool xrow = r >= CF_NU && r < CF_CR;           // row of stored state r - nu + CF_NF
+                    double *Pr = PS + (xrow ? r - CF_NU + CF_NF : CF_NF) * CF_ALST;
                     CF_UNROLL
                     for (int tp = 0; tp <= t; tp++) {
                         cf_dmma(sx[t][tp][0], sx[t][tp][1], -la[t], la[tp]);
-                        const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
-                        // P_k: whole tile rows into the shared-memory array (positions above the diagonal or in the input
-                        // columns are never read); the last tile has a single valid element (16,16)
-                        const bool xrow = r >= CF_NU && r < CF_NV;
-                        if (tp < 2) { if (xrow) cf_st2(PS + (r - CF_NU) * CF_ALST + c0, sx[t][tp][0], sx[t][tp][1]); }
-                        else if (r == 16 && fq == 0) PS[12 * CF_ALST + 16] = sx[t][tp][0];
-                        // p_k (row 17) for the next stage and for the forward sweep
-                        if (t == 2 && r == 17) {
+                        const int c0 = 8 * tp + 2 * fq;
+                        // P_k: whole tile rows into the shared-memory array (positions above the diagonal are never read);
+                        // the input columns of the first column tile are skipped: the free states' columns live there
+                        if (xrow && (tp > 0 || fq >= 2)) cf_st2(Pr + c0, sx[t][tp][0], sx[t][tp][1]);
+                        // p_k (gradient row) for the next stage and for the forward sweep
+                        if (t == 1 && r == CF_CR) {
                             CF_UNROLL
                             for (int e = 0; e < 2; e++) {
                                 const int c = c0 + e;
-                                if (c >= CF_NU && c < CF_NV) { PV[c - CF_NU] = sx[t][tp][e]; rk[R_DUX + c] = sx[t][tp][e]; }
+                                if (c >= CF_NU && c < CF_CR) { PV[c - CF_NU + CF_NF] = sx[t][tp][e]; rk[R_DUX + c + CF_NF] = sx[t][tp][e]; }
                             }
                         }
+                    }
+                    // columns of the free states: S[r][p_c] = W[r][c] (+ their gradient in the gradient row), same update
+                    const cf_d2 w2 = cf_ld2(WS + r * CF_ALST + 2 * (fq & 1));
+                    double s0 = w2.x, s1 = w2.y;
+                    if (t == 1 && r == CF_CR) { s0 += G[CF_CR + 2 * (fq & 1)]; s1 += G[CF_CR + 2 * (fq & 1) + 1]; }
+                    cf_dmma(s0, s1, -la[t], lf);
+                    if (fq < 2) {
+                        const double se[2] = {s0, s1};
+                        CF_UNROLL
+                        for (int e = 0; e < 2; e++) {
+                            const int c = 2 * fq + e;
+                            if (c < CF_NF) {
+                                if (xrow) Pr[CF_PC0 + c] = se[e];
+                                if (t == 1 && r == CF_CR) { PV[c] = se[e]; rk[R_DUX + CF_NU + c] = se[e]; }
+                            }
+                        }
+                    }
+                }
+                {   // free x free block: S[p_i][p_j] = P_{k+1}[i][j] + the diagonal; rows fg < CF_NF, columns 2fq, 2fq+1
+                    const int i = fg < CF_NF ? fg : 0, j0 = 2 * (fq & 1);
+                    double *Pi = PS + i * CF_ALST + CF_PC0 + j0;
+                    double s0 = Pi[0], s1 = Pi[1];
+                    if (i == j0) s0 += HD[CF_CR + i];
+                    if (i == j0 + 1) s1 += HD[CF_CR + i];
+                    cf_dmma(s0, s1, -lf, lf);
+                    if (fg < CF_NF && fq < 2) {
+                        if (j0 <= i) Pi[0] = s0;
+                        if (j0 + 1 <= i) Pi[1] = s1;
                     }
                 }
             }
@@ -992,6 +1062,7 @@ struct CfWarpT
         const bool xl = lane >= CF_NU && vl;
         // (idle lanes read element 8, not 0: in the second half-warp lane 16 sits on the banks of element 0)
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 8;
+        const int vi = vidx();
         // P_{k+1} travels packed (lower triangle) and is expanded to full symmetric rows in shared memory: element
         // e = lane + 32 t of the packed triangle goes to (i,j) and (j,i)
         double *PE = sm + CF_SM_P;
@@ -1125,24 +1196,11 @@ struct CfWarpT
                 rgl += ul ? dlam_u - dlam_l : 0.0;
             }
             // ---- dx+ = [A B] dux + res_b        GEMV_T, column layout of M_k (contiguous)
-            if (vl) DS[lane] = duxk;
+            if (vl) DS[vi] = duxk;
             cf_syncwarp();
             double dxn;
             {
-#if CF_KSPLIT_COL
-                const double sacc = col_gemv(Mk, DS, false), rbk = VS[R_RESB + ci];
-#else
-                const double *Mc = Mk + ci * CF_MROWS;
-                double s0 = 0.0, s1 = 0.0;
-                CF_UNROLL
-                for (int rp = 0; rp < 8; rp++) {
-                    const cf_d2 m2 = cf_ld2(Mc + 2 * rp), d2 = cf_ld2(DS + 2 * rp);
-                    s0 += m2.x * d2.x;
-                    s1 += m2.y * d2.y;
-                }
-                s0 += Mc[16] * DS[16];
-                const double sacc = s0 + s1, rbk = VS[R_RESB + ci];
-#endif
+                const double sacc = col_gemv(Mk, DS, nullptr), rbk = VS[R_RESB + ci];
                 dxn = xl ? sacc + rbk : 0.0;
                 if constexpr (MODE == 1) dxn = xl ? rec(k + 1)[R_DUX + lane] : 0.0;
                 if (chk) cf_amax(lb, xl ? (rbk - dxn) + sacc : 0.0);
@@ -1171,17 +1229,19 @@ struct CfWarpT
             }
             if (chk) {   // warp-uniform
             cf_syncwarp();
-            // stationarity residual, part 2: + [B';A'] dpi_k   (row layout)
+            // stationarity residual, part 2: + [B';A'] dpi_k   (row layout; unit rows of the free states, none at stage 0)
+                const int mr = mrow();
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
                 for (int cp = 0; cp < 6; cp++) {
                     const cf_d2 p2 = cf_ld2(PS + 2 * cp);
-                    s0 += Mk[(2 * cp) * CF_MROWS + lv] * p2.x;
-                    s1 += Mk[(2 * cp + 1) * CF_MROWS + lv] * p2.y;
+                    s0 += Mk[(2 * cp) * CF_CST + mr] * p2.x;
+                    s1 += Mk[(2 * cp + 1) * CF_CST + mr] * p2.y;
                 }
-                s0 += Mk[12 * CF_MROWS + lv] * PS[12];
-                cf_amax(lg, vl ? rgl + (s0 + s1) : 0.0);
-                if (MODE != 0 && vl) rk[R_RESG + lane] = rgl + (s0 + s1);
+                s0 += Mk[12 * CF_CST + mr] * PS[12];
+                const double sp = stored_lane() ? s0 + s1 : ((free_lane() && k > 0) ? dpik : 0.0);
+                cf_amax(lg, vl ? rgl + sp : 0.0);
+                if (MODE != 0 && vl) rk[R_RESG + lane] = rgl + sp;
             }
             dpi_prev = dpik;
             dxk = dxn;
@@ -1256,17 +1316,18 @@ struct CfWarpT
                 if (lane >= CF_NU && lane < CF_NV) TS[lane - CF_NU] = pn + VS[R_PB + lane - CF_NU];
             }
             cf_syncwarp();
-            if (lane < CF_NV) {
+            if (stored_lane()) {
+                const int mr = mrow();
                 double s0 = 0.0, s1 = 0.0;
                 CF_UNROLL
                 for (int cp = 0; cp < 6; cp++) {
                     const cf_d2 t2 = cf_ld2(TS + 2 * cp);
-                    s0 += Mk[(2 * cp) * CF_MROWS + lane] * t2.x;
-                    s1 += Mk[(2 * cp + 1) * CF_MROWS + lane] * t2.y;
+                    s0 += Mk[(2 * cp) * CF_CST + mr] * t2.x;
+                    s1 += Mk[(2 * cp + 1) * CF_CST + mr] * t2.y;
                 }
-                s0 += Mk[12 * CF_MROWS + lane] * TS[12];
+                s0 += Mk[12 * CF_CST + mr] * TS[12];
                 rhs += s0 + s1;
-            }
+            } else if (free_lane() && k > 0) rhs += TS[lane - CF_NU];   // unit row of a free state (none at stage 0)
             // TRSV_LNN_MN(nv, nu): rows of the 4 input columns of L_k
             const int rl = lane < CF_NV ? lane : 0;
             const cf_d2 l01 = cf_ld2(LU + rl * 4), l23 = cf_ld2(LU + rl * 4 + 2);

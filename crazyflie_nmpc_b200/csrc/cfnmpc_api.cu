@@ -1094,7 +1094,7 @@ extern "C" int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_dou
     if (!h) return fail(CFNMPC_EINVAL, "null handle");
     CfScratchLayout s = cf_scratch_layout(h->N);
     if (offsets12) {
-        long long v[12] = {s.total, CF_SB, B_M, B_LU, B_PX, R_UX, R_PI, R_RQ, -1, R_RESG, R_DUX, R_D};
+        long long v[12] = {s.total, CF_SB, B_M, B_LU, B_PX, R_UX, R_PI, R_RQ, R_B, R_RESG, R_DUX, R_D};
         memcpy(offsets12, v, sizeof v);
     }
     if (n_doubles) *n_doubles = (size_t) s.total;
@@ -1106,10 +1106,10 @@ extern "C" int cfnmpc_debug_scratch(cfnmpc_batch *h, double *dst, size_t max_dou
         // any warp of the (single) block may have pulled instance 0: find the slot that was written
         int slot = 0;
         for (int w = 0; w < h->n_slots; w++) {
-            double probe[CF_MSZ];
+            double probe[CF_CMSZ];
             CK(cudaMemcpy(probe, h->d_scratch + (size_t) w * s.total + B_M, sizeof probe, cudaMemcpyDeviceToHost));
             bool used = false;
-            for (int i = 0; i < CF_MSZ; i++) used |= probe[i] != 0.0;
+            for (int i = 0; i < CF_CMSZ; i++) used |= probe[i] != 0.0;
             if (used) { slot = w; break; }
         }
         CK(cudaMemcpy(dst, h->d_scratch + (size_t) slot * s.total, (size_t) s.total * 8, cudaMemcpyDeviceToHost));

@@ -243,7 +243,7 @@ extern "C" long cfemu_scratch_doubles(int N) { return cf_scratch_layout(N).total
 extern "C" void cfemu_scratch_offsets(int N, long *out)
 {
     CfScratchLayout s = cf_scratch_layout(N);
-    long v[12] = {s.total, CF_SB, B_M, B_LU, B_PX, R_UX, R_PI, R_RQ, -1, R_RESG, R_DUX, R_D};
+    long v[12] = {s.total, CF_SB, B_M, B_LU, B_PX, R_UX, R_PI, R_RQ, R_B, R_RESG, R_DUX, R_D};
     memcpy(out, v, sizeof v);
 }
 

@@ -126,13 +126,17 @@ def test_qp_data_intermediates(port):
             buf, off = s.debug_scratch()
         lin = port.linearize(N, TS, wi["x0"][0], wi["yref"][0], wi["yref_e"][0], wi["x_init"][0], wi["u_init"][0])
         blocks = buf[: (N + 1) * off["blk_stride"]].reshape(N + 1, off["blk_stride"])
-        M = blocks[:N, off["b_m"]: off["b_m"] + 234].reshape(N, 13, 18)   # [k][c][r]
-        BAbt = np.transpose(M[:, :, :17], (0, 2, 1))                   # [k][r][c]
+        # compact [B';A'] of the scratch slot: the 14 rows that are not unit vectors (inputs, states 3..12), [k][c][m];
+        # the rows of the free states (position) are exactly [I;0] in the reference's linearisation and are not stored
+        Mc = blocks[:N, off["b_m"]: off["b_m"] + 182].reshape(N, 13, 14)
         ref_BAbt = lin["BAbt"].copy()
+        assert (ref_BAbt[:, 4:7, :] == np.eye(13)[:3][None]).all()
         ref_BAbt[0, 4:, :] = 0.0                                       # A0 rows dropped by the x0 elimination
-        assert np.abs(BAbt - ref_BAbt).max() <= 1e-11 * np.abs(ref_BAbt).max()
+        rows = np.r_[0:4, 7:17]
+        BAbt = np.transpose(Mc, (0, 2, 1))                             # [k][m][c]
+        assert np.abs(BAbt - ref_BAbt[:, rows, :]).max() <= 1e-11 * np.abs(ref_BAbt).max()
         rec = blocks
-        b = M[:, :, 17]                                                # row 17 of the stage block holds b_k
+        b = blocks[:N, off["r_b"]: off["r_b"] + 13]                    # b_k is a vector of its own in the stage block
         xbar = wi["x0"][0] - wi["x_init"][0, 0]
         ref_b = lin["b"].copy()
         ref_b[0] += lin["BAbt"][0, 4:, :].T @ xbar

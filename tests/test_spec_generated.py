@@ -63,3 +63,18 @@ def test_generated_model_matches_hand_derived_and_oracle(model_lib, port):
         for a, b in zip(out["gen"], out["hand"]):
             assert np.abs(a - b).max() <= 1e-12 * (1 + np.abs(b).max())
         assert np.abs(out["gen"][0] - port.ode(x, u)).max() <= 1e-12 * (1 + np.abs(out["gen"][0]).max())
+
+
+def test_free_states_have_unit_rows_in_the_linearisation(port):
+    """CF_SPEC_NFREE (tools/gen_spec.py: leading states with a zero column of df/dx) is what lets the feedback program of
+    cf_rti_warp.h drop their rows of [B';A']: in the oracle's linearisation (the reference's sim_erk forward
+    sensitivities) those rows are EXACTLY the unit vectors, whatever the state, on benign and on adversarial instances."""
+    from crazyflie_nmpc_b200 import workloads as wl
+    src = open(HDR).read()
+    assert "#define CF_SPEC_NFREE 3 " in src
+    assert "#define CF_SPEC_NFREE 1 " in open(HDR.replace("cf_spec_generated.h", "cf_spec_pendulum.h")).read()
+    N = 50
+    for w in (wl.hover_batch(4, N, seed=77), wl.helix_batch(4, N, seed=78), wl.adversarial_batch(4, N, seed=79)):
+        for i in range(4):
+            lin = port.linearize(N, 0.015, w["x0"][i], w["yref"][i], w["yref_e"][i], w["x_init"][i], w["u_init"][i])
+            assert (lin["BAbt"][:, 4:7, :] == np.eye(13)[:3][None]).all()

@@ -223,6 +223,11 @@ def generate(ref, which="crazyflie"):
     jvp = list(J * sp.Matrix(ds))
     nnz_x = sum(1 for e in J if e != 0)
     nnz_u = sum(1 for e in Ju if e != 0)
+    # leading states that f does not depend on: their column of df/dx is zero, so their forward sensitivities stay [I;0]
+    # and their rows of [B';A'] are unit vectors (the feedback program of cf_rti_warp.h neither stores nor multiplies them)
+    nfree = 0
+    while nfree < nx and all(J[i, nfree] == 0 for i in range(nx)):
+        nfree += 1
 
     W, We = np.asarray(ocp.cost.W, float), np.asarray(ocp.cost.W_e, float)
     assert np.count_nonzero(W - np.diag(np.diag(W))) == 0 and np.count_nonzero(We - np.diag(np.diag(We))) == 0, \
@@ -247,6 +252,7 @@ def generate(ref, which="crazyflie"):
     out.append(f"#define CF_SPEC_NU {nu}")
     out.append(f"#define CF_SPEC_N {N}")
     out.append(f"#define CF_SPEC_TF {c_double(Tf)}")
+    out.append(f"#define CF_SPEC_NFREE {nfree}   // leading states with a zero column of df/dx (f does not depend on them)")
     out.append("struct CfSpec")
     out.append("{")
     out.append("    " + c_array("W", list(np.diag(W))) + "    // stage weights, cost order y = [x; u]")
