@@ -62,7 +62,9 @@
 #define CF_CR (CF_NV - CF_NF)             // stored rows (14): row m = input m (m < nu), state m - nu + CF_NF otherwise
 #define CF_CST ((CF_CR + 1) & ~1)         // column stride (14): element (m,c) at c*14 + m
 #define CF_CMSZ (CF_CST * CF_NX)          // 182 doubles
-#define CF_PC0 (CF_NU - CF_NF)            // column of state 0 in the shared-memory array of P (state i at column i + 1)
+#define CF_PC0 (CF_NU - CF_NF)            // shared-memory array of P: stored state i sits at column i + 1 (its tile column),
+#define CF_PCF 16                         //   free state i at column 16 + i (an aligned pair + one), column 19 stays zero
+#define CF_PCOL(i) ((i) < CF_NF ? CF_PCF + (i) : (i) + CF_PC0)
 #define CF_LUST 6                         // row stride of the 18 x 4 block while it is factorised in shared memory: 128-bit
                                           //   row loads without bank conflicts, column stores 2-way instead of 5-way
 #define CF_PST CF_XP                      // row stride of the cost-to-go Hessian once expanded in shared memory (14)
@@ -230,7 +232,9 @@ static inline
 // per-warp shared memory (doubles); every region starts on a 16-byte boundary
 #define CF_MAX2(a, b) ((a) > (b) ? (a) : (b))
 // sweeps: staged range of a stage block, double buffered (468 doubles for nx = 13, nu = 4: the two [B';A';b'] of the linearisation)
-#define CF_SM_WLU (16 * 20 + CF_MROWS * CF_LUST)   // factorisation: W (16 rows, stride 20) and the 18 x 4 block behind it
+#define CF_WST CF_ALST                                 // row stride of W (a swizzled stride-24 layout without bank conflicts in
+                                                       //   stores and loads was measured: fewer wavefronts, not faster)
+#define CF_SM_WLU (16 * CF_WST + CF_MROWS * CF_LUST)   // factorisation: W (16 rows) and the 18 x 4 block behind it
 #define CF_SM_BUFSZ CF_MAX2(CF_MAX2(B_RD, CF_SB - R_LAM), CF_MAX2(CF_MAX2(B_PX - R_BKP, CF_SM_WLU), 2 * CF_MSZ))
 #define CF_SM_BUF0 0
 #define CF_SM_BUF1 CF_SM_BUFSZ
@@ -253,7 +257,6 @@ static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BK
 static_assert(!CF_CRAZYFLIE || CF_SM_BUFSZ == 468, "shared-memory layout of the tuned program");
 
 CF_DEV int cf_tri(int i) { return (i * (i + 1)) >> 1; }
-
 // PH: 0 = preparation + feedback in one go (what acados_solve() does with rti_phase 0), 1 = preparation only,
 //     2 = feedback only (ocp_nlp_sqp_rti.c:1213-1237).  VDT: per-interval time steps CfBatchView::dts instead of the
 //     uniform CfParams::Ts.  The benchmarked kernel is <0, false>; the other variants cost it nothing.
@@ -493,7 +496,7 @@ struct CfWarpT
                 const int c = e / CF_CST, m = e - c * CF_CST;
                 mdst[e] = (m < CF_CR) ? MS[c * CF_MROWS + (m < CF_NU ? m : m + CF_NF)] : 0.0;
             }
-            if (lane < CF_NX) rec(k)[R_B + lane] = MS[lane * CF_MROWS + CF_NV];
+            if (lane < CF_XP) rec(k)[R_B + lane] = lane < CF_NX ? MS[lane * CF_MROWS + CF_NV] : 0.0;   // (pad: a staged zero)
         }
     }
 
@@ -589,7 +592,7 @@ struct CfWarpT
             CF_NOUNROLL
             for (int q = 0; q < n; q++) {
                 double *Sq = ST + q * CF_PREP_STAGE;
-                if (lane < CF_NX) rec(k0 + q)[R_B + lane] = Sq[lane * CF_MROWS + CF_NV];
+                if (lane < CF_XP) rec(k0 + q)[R_B + lane] = lane < CF_NX ? Sq[lane * CF_MROWS + CF_NV] : 0.0;   // (pad: a staged zero)
                 // in place, 32 elements per trip in increasing order: a destination never lies above a source still to be read
                 CF_NOUNROLL
                 for (int e0 = 0; e0 < CF_CMSZ; e0 += 32) {
@@ -702,12 +705,38 @@ struct CfWarpT
         // tiles is row lr(r) of the 18 x 4 input-column block, whose rows stay in the order of the stage variables.
         const int r1 = 8 + fg;   // this lane's row in the second row tile
         const int lr0 = fg < CF_NU ? fg : fg + CF_NF, lr1 = r1 < CF_CR ? r1 + CF_NF : 17;
-        // A fragments of the second row tile: rows 8..13 of the staged [B';A'], row 14 from the res_b vector, row 15 zero
-        const int a1o = r1 < CF_CR ? B_M + r1 : R_B, a1s = r1 < CF_CR ? CF_CST : 1;
+        // A fragments of the first product, as offsets into the staged block (loop-invariant): am[t][kk] = M[8t+fg][4kk+fq];
+        // tile 1 takes row 14 from the res_b vector, row 15 and the columns past nx - 1 from a staged zero (the pad of b_k)
+        const int zo = R_B + CF_NX;
+        const int ao0 = B_M + fq * CF_CST + fg;   // tile 0, kk < 3: + kk * 4 * CF_CST
+        int ao03 = (fq == 0) ? B_M + 12 * CF_CST + fg : zo, ao1[4];
+        CF_UNROLL
+        for (int kk = 0; kk < 4; kk++) {
+            const int kc = 4 * kk + fq;
+            ao1[kk] = (kc < CF_NX && r1 <= CF_CR) ? (r1 < CF_CR ? B_M + kc * CF_CST + r1 : R_B + kc) : zo;
+            cf_keep(ao1[kk]);
+        }
+        cf_keep(ao03);
+        // W tile stores / fragment loads (row stride 20) and the rows of this lane in the 18 x 4 input-column block, which
+        // sits behind the 16 rows of W; row 15 of W is all zero and stands in where a lane has no row (fg == 7)
+        int wso = fg * CF_WST + 2 * fq, wfo = fg * CF_WST + fq;
+        int lo0 = 16 * CF_WST + lr0 * CF_LUST + fq, lo1 = (r1 <= CF_CR) ? 16 * CF_WST + lr1 * CF_LUST + fq : 15 * CF_WST + fq;
+        // Schur-complement tile rows land in the array of P: tile row r = state r - 1, and the gradient row (r = 14) in the
+        // row behind the 13 x 20 array, which is the vector p (indexed like the columns of P: state i at i + CF_PC0)
+        int pso = (fg - 1) * CF_ALST + 2 * fq;
+        cf_keep(wso); cf_keep(wfo); cf_keep(lo0); cf_keep(lo1); cf_keep(pso);
+        static_assert(CF_SM_V0 == CF_SM_P + CF_NX * CF_ALST, "p_{k+1} is row 13 of the shared-memory array of P");
+        // free states: their rows of the input-column block as A / B fragment (Ls[p_fg][fq], zero for fg >= CF_NF), the
+        // free x free block of P_{k+1} as C fragment, and this lane's own column in the arrays of P / p
+        int lfo = (fg < CF_NF) ? 16 * CF_WST + (CF_NU + fg) * CF_LUST + fq : 15 * CF_WST + fq;
+        int pfo = (fg < CF_NF ? fg : 0) * CF_ALST + CF_PCF + 2 * (fq & 1);
+        const int pcl = CF_PCOL(ci);
+        cf_keep(lfo); cf_keep(pfo);
         // P_{k+1} is kept in shared memory as the lower triangle of a 13 x 20 array, row = state index, column = the
-        // state's column among the tile columns (state i: i + CF_PC0; stored states: exactly where the Schur-complement
-        // tiles fall, so they are stored as whole tiles); the fragment loads of the next stage's first product swap indices
-        // instead (addresses are loop-invariant): pa[kk][h] = address of P[4kk+fq][8h+fg]
+        // state's column CF_PCOL (stored states: their tile column, exactly where the Schur-complement tiles fall, so they
+        // are stored as whole tiles; free states: columns 16..18); the fragment loads of the next stage's first product swap indices
+        // instead (addresses are loop-invariant): pa[kk][h] = address of P[4kk+fq][8h+fg], or of an element that is always
+        // zero (column 19 of row 0: filled at the terminal stage, never stored to)
         int pa[4][2];
         CF_UNROLL
         for (int kk = 0; kk < 4; kk++)
@@ -716,7 +745,8 @@ struct CfWarpT
                 const int i = 4 * kk + fq, j = 8 * hh + fg;
                 const bool ok = i < CF_NX && j < CF_NX;
                 const int hi = i > j ? i : j, lo = i > j ? j : i;
-                pa[kk][hh] = ok ? hi * CF_ALST + lo + CF_PC0 : -1;
+                pa[kk][hh] = ok ? hi * CF_ALST + CF_PCOL(lo) : CF_ALST - 1;
+                cf_keep(pa[kk][hh]);
             }
         // The packed lower triangle of P_{k+1} travels to the block of stage k from this shared-memory array, element
         // e = lane + 32 t of the triangle per lane and trip: three coalesced stores per stage (scattering it from the
@@ -728,7 +758,8 @@ struct CfWarpT
             int i = 0;
             CF_UNROLL
             for (int q = 1; q < CF_NX; q++) i += (e >= cf_tri(q)) ? 1 : 0;
-            pk[t] = (e < 91) ? i * CF_ALST + (e - cf_tri(i)) + CF_PC0 : -1;
+            pk[t] = (e < 91) ? i * CF_ALST + CF_PCOL(e - cf_tri(i)) : -1;
+            cf_keep(pk[t]);
         }
         double ux_next = 0.0;   // lanes 4..16: x-part of ux_{k+1} (new iterate)
         double pi_k = 0.0;      // lanes 4..16: pi_k (new iterate), read from the record of stage k+1
@@ -739,11 +770,12 @@ struct CfWarpT
             wait(bf);
             cf_syncwarp();  // every lane is done with buffer bf^1 (incl. the W block of stage k+1), PS/PV are complete
             if (k > 0) fetch(bf ^ 1, k - 1, 0, B_RD);
-            if (do_factor && kl) {   // P_{k+1} is complete in shared memory since the barrier above
+            if (do_factor && kl) {   // P_{k+1}, p_{k+1} are complete in shared memory since the barrier above
                 double *LFk = blk(k) + B_PX;
                 CF_UNROLL
                 for (int t = 0; t < 3; t++)
                     if (pk[t] >= 0) LFk[lane + 32 * t] = PS[pk[t]];
+                if (xl) rec(k + 1)[R_DUX + lane] = PV[pcl];   // p_{k+1} for the forward sweep
             }
             double *VS = buf(bf);   // block k from offset 0
             double *rk = rec(k);
@@ -816,16 +848,15 @@ struct CfWarpT
                 cf_syncwarp();
                 const double hN = HN + CF_REG_PRIM;
                 if (xl) {
-                    PS[ci * CF_ALST + ci + CF_PC0] = hN;
-                    PV[ci] = rg;
-                    rk[R_DUX + lane] = rg;   // p_N for the forward sweep
+                    PS[ci * CF_ALST + pcl] = hN;
+                    PV[pcl] = rg;    // p_N
                 }
                 continue;
             }
             const double g = vl ? rg + gam : 0.0, hd = Hk + CF_REG_PRIM + Gam;
             cf_syncwarp();  // res_b is complete
-            double *WS = VS;                      // W rows 16 x 16 (stride 20) overlay the staged block once M is in registers,
-            double *LUs = VS + 16 * CF_ALST;      // the 18 x 4 input-column block sits behind them
+            double *WS = VS;                      // W rows 16 x 16 (CF_WST) overlay the staged block once M is in registers,
+            double *LUs = VS + 16 * CF_WST;       // the 18 x 4 input-column block sits behind them
             // ---- W(15x13) = [M;res_b'](15x13) * P(13x13): row tiles t (rows 8t+fg), column tiles 0..1, K padded to 16
             double am[2][4];     // am[t][kk] = M[8t+fg][4kk+fq]: A fragment here, B fragment (M') of the second product
             double wt[2][2][2];
@@ -833,12 +864,10 @@ struct CfWarpT
             for (int t = 0; t < 2; t++) { wt[t][0][0] = wt[t][0][1] = wt[t][1][0] = wt[t][1][1] = 0.0; }
             CF_UNROLL
             for (int kk = 0; kk < 4; kk++) {
-                const int kc = 4 * kk + fq;
-                const bool kv = kc < CF_NX;
-                const double b0 = pa[kk][0] >= 0 ? PS[pa[kk][0]] : 0.0;   // P[kc][fg]
-                const double b1 = pa[kk][1] >= 0 ? PS[pa[kk][1]] : 0.0;   // P[kc][8+fg]
-                am[0][kk] = kv ? VS[B_M + kc * CF_CST + fg] : 0.0;
-                am[1][kk] = (kv && r1 <= CF_CR) ? VS[a1o + kc * a1s] : 0.0;
+                const double b0 = PS[pa[kk][0]];   // P[kc][fg]
+                const double b1 = PS[pa[kk][1]];   // P[kc][8+fg]
+                am[0][kk] = VS[kk < 3 ? ao0 + kk * 4 * CF_CST : ao03];
+                am[1][kk] = VS[ao1[kk]];
                 CF_UNROLL
                 for (int t = 0; t < 2; t++) {
                     cf_dmma(wt[t][0][0], wt[t][0][1], am[t][kk], b0);
@@ -853,15 +882,14 @@ struct CfWarpT
                     CF_UNROLL
                     for (int e = 0; e < 2; e++) {
                         const int c = 8 * tp + 2 * fq + e;
-                        if (c < CF_NX) { pb[c] = wt[1][tp][e]; wt[1][tp][e] += PV[c]; }
+                        if (c < CF_NX) { pb[c] = wt[1][tp][e]; wt[1][tp][e] += PV[CF_PCOL(c)]; }
                     }
             }
             cf_syncwarp();  // every lane holds its M fragments: the staged block may be overwritten by W
             CF_UNROLL
             for (int t = 0; t < 2; t++) {
-                const int r = 8 * t + fg;
-                cf_st2(WS + r * CF_ALST + 2 * fq, wt[t][0][0], wt[t][0][1]);
-                cf_st2(WS + r * CF_ALST + 8 + 2 * fq, wt[t][1][0], wt[t][1][1]);
+                cf_st2(WS + wso + 8 * t * CF_WST, wt[t][0][0], wt[t][0][1]);
+                cf_st2(WS + wso + 8 * t * CF_WST + 8, wt[t][1][0], wt[t][1][1]);
             }
             // rows of the free states in the input-column block: S[p_i][u_j] = W[u_j][i] (their rows of [B';A'] are unit
             // vectors), held by the lanes of tile row j < nu
@@ -871,14 +899,16 @@ struct CfWarpT
                     if (2 * fq + e < CF_NF) LUs[(CF_NU + 2 * fq + e) * CF_LUST + fg] = wt[0][0][e];
             }
             if (vl) { G[vi] = g; HD[vi] = hd; }
+            if (fl) PS[ci * CF_ALST + pcl] += hd;   // S[p_i][p_i] = P_{k+1}[i][i] + the diagonal (the first product has read P_{k+1})
             cf_syncwarp();
             // ---- S = D + W * M': A fragments from W, B fragments are the M fragments already in registers
             double wf[2][4];
             CF_UNROLL
             for (int t = 0; t < 2; t++)
                 CF_UNROLL
-                for (int kk = 0; kk < 4; kk++) wf[t][kk] = WS[(8 * t + fg) * CF_ALST + 4 * kk + fq];
+                for (int kk = 0; kk < 4; kk++) wf[t][kk] = WS[wfo + 8 * t * CF_WST + 4 * kk];
             double sx[2][2][2];  // lower tiles (t, tp <= t): S[8t+fg][8tp+2fq+{0,1}]
+            const double *GG = (r1 == CF_CR) ? G : WS + 15 * CF_WST;   // row 15 of W: sixteen zeros
             CF_UNROLL
             for (int t = 0; t < 2; t++) {
                 CF_UNROLL
@@ -887,24 +917,26 @@ struct CfWarpT
                     CF_UNROLL
                     for (int kk = 0; kk < 4; kk++) cf_dmma(s0, s1, wf[t][kk], am[tp][kk]);
                     const int r = 8 * t + fg, c0 = 8 * tp + 2 * fq;
-                    if (r == CF_CR) { s0 += G[c0 < CF_CR ? c0 : 0]; s1 += G[c0 + 1 < CF_CR ? c0 + 1 : 0]; }
+                    if (t == 1) { const cf_d2 g2 = cf_ld2(GG + c0); s0 += g2.x; s1 += g2.y; }   // gradient row (zeros elsewhere)
                     if (r == c0) s0 += HD[r];
                     if (r == c0 + 1) s1 += HD[r];
                     sx[t][tp][0] = s0; sx[t][tp][1] = s1;
                 }
             }
             if (fq < 2) {   // the 4 input columns of the stored rows and of the gradient row
-                cf_st2(LUs + lr0 * CF_LUST + 2 * fq, sx[0][0][0], sx[0][0][1]);
-                if (r1 <= CF_CR) cf_st2(LUs + lr1 * CF_LUST + 2 * fq, sx[1][0][0], sx[1][0][1]);
+                cf_st2(VS + lo0 + fq, sx[0][0][0], sx[0][0][1]);
+                if (r1 <= CF_CR) cf_st2(VS + lo1 + fq, sx[1][0][0], sx[1][0][1]);
             }
             cf_syncwarp();
             // ---- POTRF_L_MN(nv+1, nu): the 4 input columns, one per step, lane = row; non-positive pivot -> 0
             // (BLASFEO kernel_dgemm_4x4_lib4.c:5701-5714)
+            double o[CF_NU];
             {
                 // lanes 18..31 carry no row: they must not read row 17 while lane 17 rewrites it below (racecheck)
                 cf_d2 o01 = {0.0, 0.0}, o23 = {0.0, 0.0};
                 if (lane < CF_MROWS) { o01 = cf_ld2(LUs + rl * CF_LUST); o23 = cf_ld2(LUs + rl * CF_LUST + 2); }
-                double o[CF_NU] = {o01.x, o01.y, o23.x, o23.y}, og[CF_NU];
+                double og[CF_NU];
+                o[0] = o01.x; o[1] = o01.y; o[2] = o23.x; o[3] = o23.y;
                 CF_UNROLL
                 for (int j = 0; j < CF_NU; j++) {
                     double v = o[j];
@@ -914,9 +946,12 @@ struct CfWarpT
                     double dj, inv;
                     cf_sqrt_rsqrt(piv, dj, inv);
                     if (!(piv > 0.0)) { dj = 0.0; inv = 0.0; flags |= CF_FLAG_BAD_PIVOT; }   // piv is warp-uniform
-                    o[j] = (rl == j) ? dj : ((rl > j) ? v * inv : 0.0);
+                    // (rows above the pivot keep a finite throw-away value: the strictly upper part of the 4 x 4 block is
+                    // never used -- no select for it)
+                    const double vi_ = v * inv;
+                    o[j] = (rl == j) ? dj : vi_;
                     if (lane < CF_MROWS) LUs[rl * CF_LUST + j] = o[j];   // lanes 18..31 mirror row 17 in registers only (racecheck)
-                    og[j] = (rl == j) ? inv : o[j];
+                    og[j] = (rl == j) ? inv : vi_;
                     cf_syncwarp();
                 }
                 // factor columns to global memory (LU block of stage k), inverse pivots on the diagonal; the gradient row
@@ -932,61 +967,33 @@ struct CfWarpT
                 }
             }
             // ---- Schur complement on the tensor cores (K = 4 = the input columns): S -= Ls Ls'
-            const double la0 = LUs[lr0 * CF_LUST + fq], la1 = (r1 <= CF_CR) ? LUs[lr1 * CF_LUST + fq] : 0.0;
-            const double lf = (fg < CF_NF) ? LUs[(CF_NU + fg) * CF_LUST + fq] : 0.0;   // rows of the free states: A and B fragment
-            const double la[2] = {la0, la1};
-            cf_syncwarp();  // all reads of PS/PV (first product) are long complete; they are rewritten below
-            {
+            const double la[2] = {VS[lo0], VS[lo1]};
+            const double lf = VS[lfo];             // rows of the free states
+            const cf_d2 pf = cf_ld2(PS + pfo);     // S[p_i][p_j] = P_{k+1}[i][j] (+ the diagonal, added above)
+            cf_syncwarp();  // all reads of PS/PV are complete; they are rewritten below
+            CF_UNROLL
+            for (int t = 0; t < 2; t++) {
+                const bool row_on = (t == 0) ? fg >= CF_NU : fg < 7;   // tile row = a state (or, row 14, the gradient row)
                 CF_UNROLL
-                for (int t = 0; t < 2; t++) {
-                    const int r = 8 * t + fg;
-                    const bool xrow = r >= CF_NU && r < CF_CR;           // row of stored state r - nu + CF_NF
-                    double *Pr = PS + (xrow ? r - CF_NU + CF_NF : CF_NF) * CF_ALST;
-                    CF_UNROLL
-                    for (int tp = 0; tp <= t; tp++) {
-                        cf_dmma(sx[t][tp][0], sx[t][tp][1], -la[t], la[tp]);
-                        const int c0 = 8 * tp + 2 * fq;
-                        // P_k: whole tile rows into the shared-memory array (positions above the diagonal are never read);
-                        // the input columns of the first column tile are skipped: the free states' columns live there
-                        if (xrow && (tp > 0 || fq >= 2)) cf_st2(Pr + c0, sx[t][tp][0], sx[t][tp][1]);
-                        // p_k (gradient row) for the next stage and for the forward sweep
-                        if (t == 1 && r == CF_CR) {
-                            CF_UNROLL
-                            for (int e = 0; e < 2; e++) {
-                                const int c = c0 + e;
-                                if (c >= CF_NU && c < CF_CR) { PV[c - CF_NU + CF_NF] = sx[t][tp][e]; rk[R_DUX + c + CF_NF] = sx[t][tp][e]; }
-                            }
-                        }
-                    }
-                    // columns of the free states: S[r][p_c] = W[r][c] (+ their gradient in the gradient row), same update
-                    const cf_d2 w2 = cf_ld2(WS + r * CF_ALST + 2 * (fq & 1));
-                    double s0 = w2.x, s1 = w2.y;
-                    if (t == 1 && r == CF_CR) { s0 += G[CF_CR + 2 * (fq & 1)]; s1 += G[CF_CR + 2 * (fq & 1) + 1]; }
-                    cf_dmma(s0, s1, -la[t], lf);
-                    if (fq < 2) {
-                        const double se[2] = {s0, s1};
-                        CF_UNROLL
-                        for (int e = 0; e < 2; e++) {
-                            const int c = 2 * fq + e;
-                            if (c < CF_NF) {
-                                if (xrow) Pr[CF_PC0 + c] = se[e];
-                                if (t == 1 && r == CF_CR) { PV[c] = se[e]; rk[R_DUX + CF_NU + c] = se[e]; }
-                            }
-                        }
-                    }
+                for (int tp = 0; tp <= t; tp++) {
+                    cf_dmma(sx[t][tp][0], sx[t][tp][1], -la[t], la[tp]);
+                    // P_k / p_k: whole tile rows into the shared-memory array (positions above the diagonal are never read;
+                    // row 13 of the array is p_k); the input columns of the first column tile are skipped
+                    if (row_on && (tp > 0 || fq >= 2)) cf_st2(PS + pso + 8 * t * CF_ALST + 8 * tp, sx[t][tp][0], sx[t][tp][1]);
                 }
-                {   // free x free block: S[p_i][p_j] = P_{k+1}[i][j] + the diagonal; rows fg < CF_NF, columns 2fq, 2fq+1
-                    const int i = fg < CF_NF ? fg : 0, j0 = 2 * (fq & 1);
-                    double *Pi = PS + i * CF_ALST + CF_PC0 + j0;
-                    double s0 = Pi[0], s1 = Pi[1];
-                    if (i == j0) s0 += HD[CF_CR + i];
-                    if (i == j0 + 1) s1 += HD[CF_CR + i];
-                    cf_dmma(s0, s1, -lf, lf);
-                    if (fg < CF_NF && fq < 2) {
-                        if (j0 <= i) Pi[0] = s0;
-                        if (j0 + 1 <= i) Pi[1] = s1;
-                    }
-                }
+                // columns of the free states: their rows of [B';A'] are unit vectors, so S[r][p_c] = W[r][c] -- still in the
+                // accumulators of the first product (+ the gradient of p_c in the gradient row); same update
+                double s0 = wt[t][0][0], s1 = wt[t][0][1];
+                if (t == 1 && r1 == CF_CR) { const cf_d2 g2 = cf_ld2(G + CF_CR + 2 * (fq & 1)); s0 += g2.x; s1 += g2.y; }
+                cf_dmma(s0, s1, -la[t], lf);
+                if (row_on && fq == 0) cf_st2(PS + pso + 8 * t * CF_ALST + CF_PCF, s0, s1);   // columns 16, 17
+                if (row_on && fq == 1) PS[pso + 8 * t * CF_ALST + CF_PCF] = s0;                // column 18 (pso holds 2 fq)
+            }
+            {   // free x free block, rows fg < CF_NF
+                double s0 = pf.x, s1 = pf.y;
+                cf_dmma(s0, s1, -lf, lf);
+                if (fg < CF_NF && fq == 0) cf_st2(PS + pfo, s0, s1);   // (above the diagonal: never read)
+                if (fg < CF_NF && fq == 1) PS[pfo] = s0;
             }
         }
         nrm[0] = cf_warp_max(ng); nrm[1] = cf_warp_max(nb); nrm[2] = cf_warp_max(nd); nrm[3] = cf_warp_max(nm);

@@ -62,6 +62,7 @@ CF_DEV double cf_rcp_seed(double x) { return (double) (float) (1.0 / x); }      
 #define cf_bulk_s2g_wait_read1() cfemu::bulk_s2g_wait(1, __LINE__)
 #define cf_bulk_s2g_wait_read0() cfemu::bulk_s2g_wait(0, __LINE__)
 CF_DEV void cf_fence_proxy_async() {}
+CF_DEV void cf_keep(int &) {}
 #define cf_dmma(d0, d1, a, b) cfemu::dmma((d0), (d1), (a), (b), __LINE__)
 #else
 // ---------------------------------------------------------------- CUDA (sm_100a)
@@ -147,6 +148,9 @@ CF_DEV void cf_dmma(double &d0, double &d1, double a, double b)
 }
 // Order earlier generic-proxy accesses before later async-proxy (TMA) accesses.
 CF_DEV void cf_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Make a loop-invariant index opaque to the compiler, so that it is kept (register or local memory) instead of being
+// recomputed inside a stage loop (ptxas rematerialised 26 instructions per stage for three packed-triangle indices).
+CF_DEV void cf_keep(int &v) { asm volatile("" : "+r"(v)); }
 #endif
 
 // sqrt(x) and 1/sqrt(x) for x > 0 in the normal range: hardware seed (2^-22) refined by two coupled
