@@ -437,7 +437,7 @@ def run_ours(args):
                                 batch_per_gpu=B, global_batch=world * B, horizon=N, qp_cond_N=args.qp_cond_N or N, parallelism=f"dp{world} (independent shards"
                                 + (", NCCL all-gather of u0)" if world > 1 else ")"),
                                 l2="inputs larger than L2 (iterate+yref 900 MB, scratch %d MB per GPU)" % (s.info("scratch_bytes") >> 20),
-                                occupancy=(dict(kernels="preparation + feedback", warps_per_sm=s.info("feedback_blocks_per_sm") * 4,
+                                occupancy=(dict(kernels="preparation + feedback", warps_per_sm=s.info("feedback_blocks_per_sm") * s.info("feedback_warps_per_block"),
                                                 regs=s.info("feedback_regs_per_thread"), grid=s.info("feedback_grid"),
                                                 preparation=dict(warps_per_sm=12, grid=s.info("preparation_grid")),
                                                 prepared_mb=s.info("prepared_bytes") >> 20) if two else

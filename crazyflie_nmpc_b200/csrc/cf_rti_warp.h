@@ -27,7 +27,7 @@
 // (its A-rows are zeroed after the x0 elimination folded A0*xbar into b0) and stage N keeps 4
 // decoupled dummy inputs; both stay exactly zero and cost 2/51 of the work.
 //
-// The per-instance working set (51 stage blocks of 552 doubles = 225 KB) does not fit on chip; it
+// The per-instance working set (51 stage blocks of 556 doubles = 227 KB) does not fit on chip; it
 // lives in a per-warp scratch slot in global memory (L2/HBM).
 //
 // Free states.  The dynamics do not depend on the first CF_NF states (CF_SPEC_NFREE, derived by tools/gen_spec.py from
@@ -70,30 +70,33 @@
 #define CF_PST CF_XP                      // row stride of the cost-to-go Hessian once expanded in shared memory (14)
 #define CF_LX ((CF_TRI_NX + 1) & ~1)      // cost-to-go Hessian P of the state block in HBM: packed lower triangle (91) + pad
 // One contiguous block per stage in the scratch slot.  The field order makes whatever a sweep needs of a stage ONE
-// contiguous, 16-byte aligned range = one TMA bulk copy, issued one stage ahead of the arithmetic:
-//   residual+factorisation sweep [0, B_RD)      rhs-only backward sweep [R_BKP, B_PX)      forward sweep [R_LAM, CF_SB)
+// contiguous, 16-byte aligned range = one TMA bulk copy, issued one stage ahead of the arithmetic, with as little as
+// possible that the sweep does not need (the residual sweep carries 40 unused doubles, the other two 4):
+//   residual+factorisation sweep [0, B_RD)      rhs-only backward sweep [R_BKP, B_BWE)      forward sweep [R_LAM, B_PX | CF_SB)
 // 17-vectors are padded to 18, 13-vectors to 14; bound fields are [lb(4) | ub(4)].
 //   R_UX  ux_k            R_PI  pi_{k-1} (multiplier of the dynamics ENTERING stage k)   R_DPI  its step
 //   R_RQ  gradient        R_D   bound data [lb - u ; u - ub]        R_B  b_k (linearisation, never changes inside the IPM)
+//   R_DUX  x-part in: p_k left by a backward sweep; out: the step dux_k
 //   R_BKP lam*t of the iterate (res_m backup)          R_PB   P_{k+1} res_b (cached for the rhs-only sweeps)
-//   R_DLAM, R_DT steps    R_LAM, R_T multipliers / slacks
-//   R_DUX  in: l_u | p_k left by a backward sweep, out: the step dux_k
+//   R_RESG stationarity residual (the right-hand side of the rhs-only sweeps)
+//   R_DLAM, R_DT steps    R_LAM, R_T multipliers / slacks       R_LU4  l_u left by a backward sweep for the forward sweep
 //   B_M    [B';A'] in compact form: the CF_CR = 14 rows that are not unit vectors, element (m,c) at c*14 + m
-//   R_RESD, R_RESM, R_RESG, R_RESB residuals (R_RESM = the complementarity rhs of the next solve)
+//   R_RESD bound residual
 //   B_LU   factor of the 4 input columns (18 x 4), INVERSE pivots on the diagonal (like BLASFEO's dA)
+//   R_RESM complementarity rhs of the next solve       R_RESB dynamics residual
 //   B_PX   packed lower triangle of P_{k+1} (what the forward sweep of stage k multiplies with, after expanding it to
 //          full symmetric rows in shared memory; written by the factorisation of stage k+1)
 enum { R_UX = 0, R_PI = R_UX + CF_MROWS, R_DPI = R_PI + CF_XP, R_RQ = R_DPI + CF_XP, R_D = R_RQ + CF_MROWS, R_B = R_D + 2 * CF_NU,
-       R_BKP = R_B + CF_XP, R_PB = R_BKP + 2 * CF_NU, R_DLAM = R_PB + CF_XP, R_DT = R_DLAM + 2 * CF_NU, R_LAM = R_DT + 2 * CF_NU,
-       R_T = R_LAM + 2 * CF_NU, R_DUX = R_T + 2 * CF_NU, B_M = R_DUX + CF_MROWS, B_RD = B_M + CF_CMSZ, R_RESD = B_RD,
-       R_RESM = R_RESD + 2 * CF_NU, R_RESG = R_RESM + 2 * CF_NU, R_RESB = R_RESG + CF_MROWS, B_LU = R_RESB + CF_XP, B_PX = B_LU + CF_LU,
-       CF_SB = B_PX + CF_LX };   // 552 doubles per stage (nx = 13, nu = 4)
-static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_PX % 2 == 0 && CF_SB % 2 == 0 && R_BKP % 2 == 0 && R_LAM % 2 == 0,
-              "16-byte alignment of TMA ranges");
+       R_DUX = R_B + CF_XP, R_BKP = R_DUX + CF_MROWS, R_PB = R_BKP + 2 * CF_NU, R_RESG = R_PB + CF_XP, R_DLAM = R_RESG + CF_MROWS,
+       R_DT = R_DLAM + 2 * CF_NU, R_LAM = R_DT + 2 * CF_NU, R_T = R_LAM + 2 * CF_NU, R_LU4 = R_T + 2 * CF_NU, B_M = R_LU4 + CF_UP,
+       B_RD = B_M + CF_CMSZ, R_RESD = B_RD, B_LU = R_RESD + 2 * CF_NU, B_BWE = B_LU + CF_LU, R_RESM = B_BWE,
+       R_RESB = R_RESM + 2 * CF_NU, B_PX = R_RESB + CF_XP, CF_SB = B_PX + CF_LX };   // 556 doubles per stage (nx = 13, nu = 4)
+static_assert(B_M % 2 == 0 && B_RD % 2 == 0 && B_LU % 2 == 0 && B_BWE % 2 == 0 && B_PX % 2 == 0 && CF_SB % 2 == 0 && R_BKP % 2 == 0 &&
+              R_LAM % 2 == 0, "16-byte alignment of TMA ranges");
 #if CF_CRAZYFLIE
-static_assert(R_PI == 18 && R_DPI == 32 && R_RQ == 46 && R_D == 64 && R_B == 72 && R_BKP == 86 && R_PB == 94 && R_DLAM == 108 &&
-              R_DT == 116 && R_LAM == 124 && R_T == 132 && R_DUX == 140 && B_M == 158 && B_RD == 340 && R_RESM == B_RD + 8 &&
-              R_RESG == B_RD + 16 && R_RESB == B_RD + 34 && B_LU == B_RD + 48 && CF_SB == 552, "stage block layout of the tuned program");
+static_assert(R_PI == 18 && R_DPI == 32 && R_RQ == 46 && R_D == 64 && R_B == 72 && R_DUX == 86 && R_BKP == 104 && R_PB == 112 &&
+              R_RESG == 126 && R_DLAM == 144 && R_DT == 152 && R_LAM == 160 && R_T == 168 && R_LU4 == 176 && B_M == 180 && B_RD == 362 &&
+              B_LU == 370 && B_BWE == 442 && R_RESB == 450 && B_PX == 464 && CF_SB == 556, "stage block layout of the tuned program");
 static_assert(CF_NF == 3 && CF_CR == 14 && CF_CST == 14 && CF_PC0 == 1, "compact [B';A'] of the tuned program");
 #endif
 
@@ -235,7 +238,7 @@ static inline
 #define CF_WST CF_ALST                                 // row stride of W (a swizzled stride-24 layout without bank conflicts in
                                                        //   stores and loads was measured: fewer wavefronts, not faster)
 #define CF_SM_WLU (16 * CF_WST + CF_MROWS * CF_LUST)   // factorisation: W (16 rows) and the 18 x 4 block behind it
-#define CF_SM_BUFSZ CF_MAX2(CF_MAX2(B_RD, CF_SB - R_LAM), CF_MAX2(CF_MAX2(B_PX - R_BKP, CF_SM_WLU), 2 * CF_MSZ))
+#define CF_SM_BUFSZ CF_MAX2(CF_MAX2(B_RD, CF_SB - R_LAM), CF_MAX2(CF_MAX2(B_BWE - R_BKP, CF_SM_WLU), 2 * CF_MSZ))
 #define CF_SM_BUF0 0
 #define CF_SM_BUF1 CF_SM_BUFSZ
 #define CF_SM_MS0 0                            // linearisation: [B';A';b'] staging, double buffered
@@ -252,7 +255,7 @@ static inline
 #define CF_SM_PAR (CF_SM_BAR + 4)              // this instance's CfParams (solver-wide values + per-instance overrides)
 #define CF_SM_DOUBLES (CF_SM_PAR + ((CF_PAR_DOUBLES + 1) & ~1))  // 1330 doubles = 10640 bytes per warp
 static_assert(CF_SM_DOUBLES % 2 == 0, "every warp's shared-memory slice must start on a 16-byte boundary");
-static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_PX - R_BKP <= CF_SM_BUFSZ && CF_SM_WLU <= CF_SM_BUFSZ,
+static_assert(B_RD <= CF_SM_BUFSZ && CF_SB - R_LAM <= CF_SM_BUFSZ && B_BWE - R_BKP <= CF_SM_BUFSZ && CF_SM_WLU <= CF_SM_BUFSZ,
               "staging buffers");
 static_assert(!CF_CRAZYFLIE || CF_SM_BUFSZ == 468, "shared-memory layout of the tuned program");
 
@@ -680,7 +683,7 @@ struct CfWarpT
     //   L   = chol of the 4 input columns of S               POTRF_L_MN(nv+1, nu) :653
     //   P_k = S_xx - Ls Ls',  p_k = s_x - Ls l_u             SYRK -1 :655
     // Stored per stage: LU (18 x 4 factor columns, inverse pivots on the diagonal), the packed lower triangle of P_k, and
-    // the gradient parts l_u | p_k in R_DUX of the stage record.
+    // the gradient parts l_u (R_LU4) and p_k (x-part of R_DUX) of the stage record.
     CF_MEM double step_adjust(double a) const { return (a < 1.0) ? a * ((1.0 - a) * 0.99 + a * 0.9999999) : a; }
     CF_MEM void residual_factorize(const double a_raw, const bool do_factor)
     {
@@ -962,8 +965,8 @@ struct CfWarpT
                     cf_st2(LFk + lane * 4 + 2, og[2], og[3]);
                 }
                 if (lane == 17) {
-                    cf_st2(rk + R_DUX, o[0], o[1]);
-                    cf_st2(rk + R_DUX + 2, o[2], o[3]);
+                    cf_st2(rk + R_LU4, o[0], o[1]);
+                    cf_st2(rk + R_LU4 + 2, o[2], o[3]);
                 }
             }
             // ---- Schur complement on the tensor cores (K = 4 = the input columns): S -= Ls Ls'
@@ -1011,7 +1014,7 @@ struct CfWarpT
         double ll = f[R_LAM + lane], lu = f[R_LAM + 4 + lane];
         const double til = cf_rcp(f[R_T + lane]), tiu = cf_rcp(f[R_T + 4 + lane]);
         double rml, rmu;
-        if (rm_mode == 3) { rml = f[R_RESM + lane]; rmu = f[R_RESM + 4 + lane]; }
+        if (rm_mode == 3) { rml = rec(k)[R_RESM + lane]; rmu = rec(k)[R_RESM + 4 + lane]; }   // (not staged by the backward sweep)
         else {
             rml = f[R_BKP + lane]; rmu = f[R_BKP + 4 + lane];
             if (rm_mode == 0) { rml -= CF_TAU_MIN; rmu -= CF_TAU_MIN; }
@@ -1028,7 +1031,7 @@ struct CfWarpT
     }
 
     // Forward substitution shared by the factorise-and-solve (:536-570) and the rhs-only solve (:1250-1290): the
-    // backward sweep before it (factorize or backward_rhs) left l_u of stage k and p_k in R_DUX of stage k's record and
+    // backward sweep before it (factorize or backward_rhs) left l_u of stage k in R_LU4, p_k in R_DUX of stage k's record and
     // the complementarity rhs in R_RESM.  Computes dux, dpi, then dlam, dt (:741-758, x_core_qp_ipm_aux.c:117-142), the
     // step length ingredients (:146-216) and the inf-norms of the linear-system residual (OCP_QP_RES_COMPUTE_LIN,
     // x_ocp_qp_res.c:474-598) on the fly.  Branch-free: every lane computes with clamped indices (lanes with equal
@@ -1117,11 +1120,11 @@ struct CfWarpT
                 t += cf_shfl(t, lane ^ 4);
                 t += cf_shfl(t, lane ^ 8);
                 t += cf_shfl(t, lane ^ 16);
-                v = -VS[R_DUX + l4] - t;
+                v = -VS[R_LU4 + l4] - t;
             }
 #else
             {
-                double v0 = -VS[R_DUX + l4], v1 = 0.0;
+                double v0 = -VS[R_LU4 + l4], v1 = 0.0;
                 CF_UNROLL
                 for (int ip = 0; ip < 6; ip++) {
                     const cf_d2 x2 = cf_ld2(XS + 2 * ip);
@@ -1199,7 +1202,7 @@ struct CfWarpT
             // stationarity residual, part 1: H dux + rhs_g - dpi_{k-1} + dlam_ub - dlam_lb
             double rgl = 0.0;
             if (chk) {
-                rgl = hess(k) * duxk + VS[R_RESG + lv] - dpi_prev;
+                rgl = hess(k) * duxk + rk[R_RESG + lv] - dpi_prev;   // (not part of the staged range: cold path)
                 rgl += ul ? dlam_u - dlam_l : 0.0;
             }
             // ---- dx+ = [A B] dux + res_b        GEMV_T, column layout of M_k (contiguous)
@@ -1287,7 +1290,7 @@ struct CfWarpT
     CF_MEM void backward_rhs_t(int rm_mode, double sigma_mu)
     {
         double *TS = sm + CF_SM_V0;
-        const int VO = R_BKP, VN = B_PX - R_BKP;   // staged part of the stage block: [R_BKP, B_PX)
+        const int VO = R_BKP, VN = B_BWE - R_BKP;   // staged part of the stage block: [R_BKP, B_BWE)
         pass_begin();
         if (N > 0) fetch(0, N - 1, VO, VN);
         // terminal stage: rhs = res_g_N, nothing to eliminate (dummy inputs are zero)
@@ -1312,7 +1315,7 @@ struct CfWarpT
                 double *RB = sm + CF_SM_V1;
                 const bool xq = lane >= CF_NU && lane < CF_NV;
                 const int iq = xq ? lane - CF_NU : 0;
-                if (xq) RB[iq] = VS[R_RESB + iq];
+                if (xq) RB[iq] = rec(k)[R_RESB + iq];   // (not staged by the backward sweep)
                 cf_syncwarp();
                 const double *Pp = blk(k) + B_PX;
                 double pb = 0.0;
@@ -1346,7 +1349,7 @@ struct CfWarpT
                 if (lane == j) rhs = zj;
                 else if (lane > j && lane < CF_NV) rhs -= Lr[j] * zj;
             }
-            if (lane < CF_NV) rec(k)[R_DUX + lane] = rhs;
+            if (lane < CF_NV) rec(k)[lane < CF_NU ? R_LU4 + lane : R_DUX + lane] = rhs;
             pn = rhs;
         }
         cf_syncwarp();

@@ -74,7 +74,8 @@ struct cfnmpc_batch
     CfPcBlocks pcb;
     void (*kernel_pc)(const CfParams, const CfBatchView, const CfPcBlocks) = nullptr;
     int grid_prep_u = 0, prep_minb = 3;
-    int grid_fb = 0, fb_minb = 4, fb_regs = 0, fb_blocks_per_sm = 0;
+    int grid_fb = 0, fb_minb = 4, fb_wpb = 4, fb_regs = 0, fb_blocks_per_sm = 0;
+    size_t smem_fb = 0;
     cudaEvent_t ev_mid = nullptr;     // between the two launches of a two-kernel step
     bool mid_valid = false;
     size_t smem_general = 0;
@@ -191,17 +192,29 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     if (const char *e = getenv("CFNMPC_FB_MIN_BLOCKS")) h->fb_minb = atoi(e);
     if (h->fb_minb == 4) h->kernel_fb_u = cf_rti_kernel<4, 4, CF_PH_FEEDBACK, false>;
     else h->fb_minb = 3;
+    // other shapes of the benchmarked feedback kernel, for the occupancy experiments of profiles/README.md:
+    // CFNMPC_FB_SHAPE = 100 * warps per block + blocks per SM (18 / 20 warps per SM at 96 registers: 6 % slower than 4 x 4;
+    // a 112-register cap does not give 18 warps: registers are allocated per warp in units that round it up to 128)
+    if (const char *e = getenv("CFNMPC_FB_SHAPE")) {
+        switch (atoi(e)) {
+        case 603: h->kernel_fb_u = cf_rti_kernel<6, 3, CF_PH_FEEDBACK, false>; h->fb_wpb = 6; h->fb_minb = 3; break;
+        case 306: h->kernel_fb_u = cf_rti_kernel<3, 6, CF_PH_FEEDBACK, false>; h->fb_wpb = 3; h->fb_minb = 6; break;
+        case 405: h->kernel_fb_u = cf_rti_kernel<4, 5, CF_PH_FEEDBACK, false>; h->fb_wpb = 4; h->fb_minb = 5; break;
+        default: break;
+        }
+    }
+    h->smem_fb = (size_t) h->fb_wpb * CF_SM_DOUBLES * sizeof(double);
     if (const char *e = getenv("CFNMPC_PREP_MIN_BLOCKS"))
         if (atoi(e) == 4) { h->kernel_prep_u = cf_rti_kernel<4, 4, CF_PH_PREPARATION, false>; h->prep_minb = 4; }
     h->smem_general = (size_t) 4 * CF_SM_DOUBLES * sizeof(double);
     CKH(cudaFuncSetAttribute(h->kernel_prep_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
-    CKH(cudaFuncSetAttribute(h->kernel_fb_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
+    CKH(cudaFuncSetAttribute(h->kernel_fb_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_fb));
     if (const char *e = getenv("CFNMPC_TWO_KERNELS")) h->two_kernels = atoi(e) != 0;
     {
         cudaFuncAttributes fb;
         CKH(cudaFuncGetAttributes(&fb, h->kernel_fb_u));
         h->fb_regs = fb.numRegs;
-        CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fb_blocks_per_sm, h->kernel_fb_u, 128, h->smem_general));
+        CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->fb_blocks_per_sm, h->kernel_fb_u, h->fb_wpb * 32, h->smem_fb));
         if (h->fb_blocks_per_sm < 1) { cfnmpc_batch_destroy(h); return fail(CFNMPC_ECUDA, "feedback kernel does not fit on an SM"); }
     }
     CKH(cudaFuncSetAttribute(h->kernel_vdt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_general));
@@ -224,8 +237,9 @@ extern "C" int cfnmpc_batch_create(int batch, int N, double Ts, int device, cfnm
     if (h->n_slots < 4) h->n_slots = 4;
     {
         const long want_fb = (long) h->sm_count * h->fb_blocks_per_sm, need_fb = ((long) batch + 3) / 4;
-        h->grid_fb = (int) (want_fb < need_fb ? want_fb : need_fb);
-        if (h->grid_fb * 4 > h->n_slots) h->n_slots = h->grid_fb * 4;
+        const long need_fbw = ((long) batch + h->fb_wpb - 1) / h->fb_wpb;
+        h->grid_fb = (int) (want_fb < need_fbw ? want_fb : need_fbw);
+        if (h->grid_fb * h->fb_wpb > h->n_slots) h->n_slots = h->grid_fb * h->fb_wpb;
         int bg = 0;
         CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bg, h->kernel_fb_g4, 128, h->smem_general));
         const long want_g = (long) h->sm_count * (bg > 0 ? bg : 1);
@@ -625,7 +639,7 @@ extern "C" int cfnmpc_batch_solve(cfnmpc_batch *h, int n_rti)
             CK(cudaGetLastError());
             CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
             if (r == n_rti - 1) { CK(cudaEventRecord(h->ev_mid, h->stream)); h->mid_valid = n_rti == 1; }
-            h->kernel_fb_u<<<h->grid_fb, 128, h->smem_general, h->stream>>>(h->P, h->bv);
+            h->kernel_fb_u<<<h->grid_fb, h->fb_wpb * 32, h->smem_fb, h->stream>>>(h->P, h->bv);
             h->launches++;
         } else h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, h->bv);
         CK(cudaGetLastError());
@@ -761,7 +775,7 @@ extern "C" int cfnmpc_batch_solve_from_host(cfnmpc_batch *h, const double *x0, c
         CK(cudaGetLastError());
         CK(cudaMemsetAsync(h->d_counter, 0, 4, h->stream));
         bv.ready = nullptr;
-        h->kernel_fb_u<<<h->grid_fb, 128, h->smem_general, h->stream>>>(h->P, bv);
+        h->kernel_fb_u<<<h->grid_fb, h->fb_wpb * 32, h->smem_fb, h->stream>>>(h->P, bv);
         h->launches++;
     } else h->kernel<<<h->grid, h->wpb * 32, h->smem, h->stream>>>(h->P, bv);
     CK(cudaGetLastError());
@@ -1051,6 +1065,7 @@ extern "C" int cfnmpc_batch_info(cfnmpc_batch *h, const char *what, long long *v
     else if (!strcmp(what, "feedback_regs_per_thread")) *value = h->fb_regs;
     else if (!strcmp(what, "feedback_blocks_per_sm")) *value = h->fb_blocks_per_sm;
     else if (!strcmp(what, "feedback_grid")) *value = h->grid_fb;
+    else if (!strcmp(what, "feedback_warps_per_block")) *value = h->fb_wpb;
     else if (!strcmp(what, "preparation_grid")) *value = h->grid_prep_u;
     else if (!strcmp(what, "prepared_bytes")) *value = h->d_prep ? (long long) h->B * h->bv.prep_stride * 8 : 0;
     else return fail(CFNMPC_EINVAL, std::string("cfnmpc_batch_info: unknown property '") + what + "'");
