@@ -14,7 +14,8 @@
 //
 // Mapping.  Stage variables are [u(4); x(13)] -> lanes 0..16; lane 17 carries the extra
 // "gradient / b" row of the (nv+1) x nv Riccati blocks.  Lane r owns ROW r of the stage matrices
-// ([B';A';b'] is 18 x 13).  Per IPM iteration the warp runs four sweeps over the stages
+// (the linearisation produces [B';A';b'] as 18 x 13; the feedback program keeps the 14 rows that are not unit vectors,
+// see "Free states" below).  Per IPM iteration the warp runs four sweeps over the stages
 // (residual_factorize, forward, backward_rhs, forward); each sweep stages the part of a stage block it
 // needs in shared memory with ONE TMA bulk copy issued one stage ahead of the arithmetic (double
 // buffered, mbarrier-tracked).  Inside a sweep the code is straight-line and branch-free (clamped
@@ -678,7 +679,7 @@ struct CfWarpT
     // 4 instead of 17 strictly sequential pivot steps per stage and every matrix product is a tensor-core tile product;
     // on this OCP the two recursions agree to 1e-14 (oracle/cfnmpc_oracle.c: cfo_set_classical_riccati,
     // tests/test_oracle_golden.py).  Per stage k < N:
-    //   W   = [B';A';res_b']_k P_{k+1}                      GEMM_NT :621   (row 17: Pb_k = P res_b, then += p_{k+1}')
+    //   W   = [B';A';res_b']_k P_{k+1}                      GEMM_NT :621   (gradient row: Pb_k = P res_b, then += p_{k+1}')
     //   S   = [H_k + Gamma ; (res_g + gamma)'] + W [B';A']'  SYRK_LN_MN :652
     //   L   = chol of the 4 input columns of S               POTRF_L_MN(nv+1, nu) :653
     //   P_k = S_xx - Ls Ls',  p_k = s_x - Ls l_u             SYRK -1 :655
