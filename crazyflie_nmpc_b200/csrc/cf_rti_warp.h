@@ -637,14 +637,23 @@ struct CfWarpT
     // and the two extra terms, its partner (lanes 20..31 and lane 17) rows 6..13; one exchange combines them.  (The split at
     // row 6 keeps the 128-bit loads of every quarter warp on distinct banks at column stride 14.)  Mk: staged compact
     // [B';A'] (element (m,c) at c*14 + m), v: 20-double vector in the order of vidx().
-    CF_MEM double col_gemv(const double *Mk, const double *v, const double *bv) const
+    // (the lane pairing is a per-lane constant: col_consts() computes it once per sweep and pins it in registers -- ptxas
+    // otherwise re-derives it in every stage, 3 % of all executed instructions)
+    CF_MEM void col_consts(int &cgo, int &clp) const
     {
         // partner of state lane L: L ^ 16 (lanes 20..31), except lane 16 whose partner is lane 17; lanes 0..3, 18, 19 compute
         // a throw-away duplicate of column 0
         const int lp = lane == 16 ? 17 : (lane == 17 ? 16 : lane ^ 16);
         const bool lo = lane >= CF_NU && lane < CF_NV, hi = lane == 17 || lane >= 20;
         const int cc = lo ? lane - CF_NU : (hi ? lp - CF_NU : 0), r0 = lo ? 0 : 6;
-        const double *Mc = Mk + cc * CF_CST + r0, *vc = v + r0;
+        cgo = cc * CF_CST + r0;   // this lane's part of its column: rows r0.. of column cc
+        clp = lp;
+        cf_keep(cgo); cf_keep(clp);
+    }
+    CF_MEM double col_gemv(const double *Mk, const double *v, const double *bv, const int cgo, const int clp) const
+    {
+        const bool lo = lane >= CF_NU && lane < CF_NV;
+        const double *Mc = Mk + cgo, *vc = v + (lo ? 0 : 6);
         double s0 = 0.0, s1 = 0.0;
         CF_UNROLL
         for (int rp = 0; rp < 3; rp++) {   // rows 0..5 | 6..11
@@ -653,6 +662,7 @@ struct CfWarpT
             s1 += m2.y * v2.y;
         }
         if (lo) {
+            const int cc = lane - CF_NU;
             s0 += (cc < CF_NF) ? v[CF_CR + cc] : 0.0;
             s1 += bv ? bv[cc] : 0.0;
         } else {                           // rows 12, 13
@@ -661,7 +671,7 @@ struct CfWarpT
             s1 += m3.y * v3.y;
         }
         const double part = s0 + s1;
-        return part + cf_shfl(part, lp);
+        return part + cf_shfl(part, clp);
     }
 
     // One BACKWARD sweep that does, per stage, everything the reference spreads over three passes:
@@ -702,6 +712,8 @@ struct CfWarpT
         // (idle lanes read element 8, not 0: in the second half-warp lane 16 sits on the banks of element 0)
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 8;
         const int mr = mrow(), vi = vidx();
+        int cgo, clp;
+        col_consts(cgo, clp);
         // tensor-core fragment coordinates (mma.sync.m8n8k4.f64): group row / k / n index and column pair
         const int fg = lane >> 2, fq = lane & 3;
         const int rl = lane < CF_MROWS ? lane : 17;
@@ -832,7 +844,7 @@ struct CfWarpT
                     rg += sl ? s0 + s1 : ((fl && k > 0) ? pi_k : 0.0);
                 }
                 {   // res_b_k = (b_k - x_{k+1}) + [A B] ux_k   (column layout: contiguous)
-                    const double rb = col_gemv(Mk, UXS, VS + R_B) - ux_next;
+                    const double rb = col_gemv(Mk, UXS, VS + R_B, cgo, clp) - ux_next;
                     cf_syncwarp();   // every lane has read b_k: the staged vector becomes res_b (ROWIN :490)
                     if (xl) {
                         cf_amax(nb, rb);
@@ -1074,6 +1086,8 @@ struct CfWarpT
         // (idle lanes read element 8, not 0: in the second half-warp lane 16 sits on the banks of element 0)
         const int ci = xl ? lane - CF_NU : 0, l4 = lane & 3, lv = vl ? lane : 8;
         const int vi = vidx();
+        int cgo, clp;
+        col_consts(cgo, clp);
         // P_{k+1} travels packed (lower triangle) and is expanded to full symmetric rows in shared memory: element
         // e = lane + 32 t of the packed triangle goes to (i,j) and (j,i)
         double *PE = sm + CF_SM_P;
@@ -1087,6 +1101,7 @@ struct CfWarpT
             const int j = e - cf_tri(i);
             pe_a[t] = (e < 91) ? i * CF_PST + j : -1;
             pe_b[t] = j * CF_PST + i;
+            cf_keep(pe_a[t]); cf_keep(pe_b[t]);   // (kept: ptxas re-derived them in every stage, 2.7 % of all instructions)
         }
         CF_NOUNROLL
         for (int k = 0; k < N; k++) {
@@ -1211,7 +1226,7 @@ struct CfWarpT
             cf_syncwarp();
             double dxn;
             {
-                const double sacc = col_gemv(Mk, DS, nullptr), rbk = VS[R_RESB + ci];
+                const double sacc = col_gemv(Mk, DS, nullptr, cgo, clp), rbk = VS[R_RESB + ci];
                 dxn = xl ? sacc + rbk : 0.0;
                 if constexpr (MODE == 1) dxn = xl ? rec(k + 1)[R_DUX + lane] : 0.0;
                 if (chk) cf_amax(lb, xl ? (rbk - dxn) + sacc : 0.0);
